@@ -1,0 +1,158 @@
+/*
+ * gtts_b200.h -- C ABI of the B200-native GamaTTS tube-model path.
+ *
+ * One drop-in boundary: batched synthesis of the reference's model-0 vocal-tract tube model
+ * (GS::VTM::VocalTractModel0<double>) driven by control-parameter tracks, i.e. the work of
+ *
+ *     Controller::synthesize()                 gama_tts/src/vtm_control_model/Controller.cpp:277-313
+ *       VocalTractModel::setAllParameters()    gama_tts/src/vtm/VocalTractModel.h:54, VocalTractModel0.h:698-716
+ *       VocalTractModel::execSynthesisStep()   gama_tts/src/vtm/VocalTractModel.h:56, VocalTractModel0.h:396-445
+ *     VocalTractModel::finishSynthesis()       gama_tts/src/vtm/VocalTractModel.h:57, VocalTractModel0.h:720-723
+ *     VocalTractModel::outputBuffer()          gama_tts/src/vtm/VocalTractModel.h:59
+ *
+ * for U independent utterances at once on one GPU.  Plain pointers and sizes only; no C++ or torch
+ * types cross this boundary.  The C++ plugin shim that the unmodified reference loads through
+ * VocalTractModelPlugin (gama_tts/src/vtm/VocalTractModelPlugin.cpp:40-48, model = 2000) is built on
+ * top of these entry points (gama_tts_b200/csrc/plugin_shim.cpp); INTEGRATION.md shows the bindings.
+ *
+ * All functions return GTTS_OK (0) or a GTTS_ERR_* code; gtts_last_error() gives the text of the
+ * last failure on the calling thread.  There is no CPU fallback: device entry points fail with
+ * GTTS_ERR_NO_DEVICE / GTTS_ERR_CUDA when no sm_100 GPU is usable.
+ */
+#ifndef GTTS_B200_H_
+#define GTTS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GTTS_NUM_PARAMS 16          /* control parameters per frame (artic.xml:38-53 order) */
+#define GTTS_ABI_VERSION 1
+
+enum {
+	GTTS_OK = 0,
+	GTTS_ERR_INVALID = 1,           /* bad argument / configuration value */
+	GTTS_ERR_CUDA = 2,              /* a CUDA runtime call failed */
+	GTTS_ERR_NO_DEVICE = 3,         /* no usable sm_100 device */
+	GTTS_ERR_NOMEM = 4,
+	GTTS_ERR_UNSUPPORTED = 5        /* valid in the reference but outside what this path implements */
+};
+
+/* Parameter indices of one control frame (VocalTractModel0.h:160-178). */
+enum {
+	GTTS_PARAM_GLOT_PITCH = 0, GTTS_PARAM_GLOT_VOL = 1, GTTS_PARAM_ASP_VOL = 2, GTTS_PARAM_FRIC_VOL = 3,
+	GTTS_PARAM_FRIC_POS = 4, GTTS_PARAM_FRIC_CF = 5, GTTS_PARAM_FRIC_BW = 6, GTTS_PARAM_R1 = 7,
+	GTTS_PARAM_R8 = 14, GTTS_PARAM_VELUM = 15
+};
+
+/* The configuration keys VocalTractModel0 reads (VocalTractModel0.h:266-305), same names, same units.
+ * It is the merged vtm.txt + variant/<name>.txt map the reference's Controller builds
+ * (Controller.cpp:48-49). */
+typedef struct gtts_voice_config {
+	double output_rate;                 /* Hz */
+	int32_t waveform;                   /* 0 = glottal pulse, 1 = sine */
+	int32_t noise_modulation;           /* 0 = off, 1 = on */
+	double glottal_pulse_tp;            /* % */
+	double glottal_pulse_tn_min;        /* % */
+	double glottal_pulse_tn_max;        /* % */
+	double breathiness;                 /* % */
+	double vocal_tract_length_offset;   /* cm */
+	double vocal_tract_length;          /* cm */
+	double temperature;                 /* deg C */
+	double loss_factor;                 /* % */
+	double mouth_coefficient;
+	double nose_coefficient;
+	double throat_cutoff;               /* Hz */
+	double throat_volume;               /* dB */
+	double mix_offset;                  /* dB */
+	double global_radius_coef;
+	double global_nasal_radius_coef;
+	double aperture_radius;             /* cm */
+	double nasal_radius[5];             /* nasal_radius_1 .. nasal_radius_5, cm */
+	double radius_coef[8];              /* radius_1_coef .. radius_8_coef */
+} gtts_voice_config;
+
+typedef struct gtts_handle gtts_handle;    /* one per GPU */
+typedef struct gtts_batch gtts_batch;      /* a prepared batch (plan + device metadata) */
+typedef struct gtts_stream gtts_stream;    /* one utterance fed control frame by control frame */
+
+const char* gtts_last_error(void);
+int gtts_abi_version(void);
+
+/* ---- host-only helpers (no GPU touched) ----------------------------------------------------------- */
+
+/* VocalTractModel::internalSampleRate() right after construction (VocalTractModel0.h:343-344). */
+int gtts_voice_internal_rate(const gtts_voice_config* voice, int32_t* fs_out);
+/* controlSteps of Controller::synthesize (Controller.cpp:286): rint(fs_int / control_rate). */
+int gtts_voice_control_steps(const gtts_voice_config* voice, double control_rate, int32_t* steps_out);
+/* Number of internal samples and of output samples (outputBuffer().size() after finishSynthesis())
+ * for a track of n_frames control frames stepped `steps` times each
+ * (SampleRateConverter.h:268-282, 295-416, 462-471 reduced to a closed form). */
+int gtts_output_length(const gtts_voice_config* voice, int32_t steps, int64_t n_frames,
+			int64_t* n_internal_out, int64_t* n_output_out);
+/* Greedy longest-first partition of utterances over n_shards GPUs (no collective: SURVEY.md s.8e).
+ * cost[u] is any positive work estimate (e.g. internal samples); shard_of[u] receives 0..n_shards-1. */
+int gtts_shard_plan(const int64_t* cost, int64_t n_utt, int32_t n_shards, int32_t* shard_of);
+/* Known-answer probes of the host-side table builders (used by the tests; cheap). */
+int gtts_probe_fir_taps(double* taps, int32_t cap, int32_t* n_taps_out);
+int gtts_probe_src_tables(double* h3328, double* dh3328);
+int gtts_probe_voice_constants(const gtts_voice_config* voice, double* out, int32_t cap, int32_t* n_out);
+
+/* ---- device ---------------------------------------------------------------------------------------- */
+
+int gtts_create(int32_t device, gtts_handle** handle_out);
+void gtts_destroy(gtts_handle* handle);
+/* Device and kernel facts for logs (SM count, kernel variant, shared memory per CTA ...), JSON text. */
+const char* gtts_describe(gtts_handle* handle);
+
+/* Plans a batch of n_utt utterances.
+ *   voices[n_voices]        voice table; voice_index[u] selects one (NULL: every utterance uses voices[0])
+ *   control_rate            Hz (1000 / control_period of vtm_control_model.txt); steps = rint(fs_int/rate)
+ *   steps_override          NULL, or per-utterance controlSteps (> 0 overrides; 1 = "every frame is one
+ *                           internal sample", the mode the plugin shim uses)
+ *   frame_offsets[n_utt+1]  utterance u owns frames [frame_offsets[u], frame_offsets[u+1]) of the packed
+ *                           float32 [n_frames_total][16] track array
+ * All arrays are host memory and are copied. */
+int gtts_batch_prepare(gtts_handle* handle, const gtts_voice_config* voices, int32_t n_voices,
+			const int32_t* voice_index, double control_rate, const int32_t* steps_override,
+			const int64_t* frame_offsets, int64_t n_utt, gtts_batch** batch_out);
+/* out_offsets[n_utt+1] (in float32 samples) of the packed output; n_internal[n_utt] may be NULL. */
+int gtts_batch_layout(const gtts_batch* batch, int64_t* out_offsets, int64_t* n_internal);
+/* Runs the batch on DEVICE buffers, asynchronously on `cuda_stream` (a cudaStream_t, may be NULL):
+ * d_frames float32 [n_frames_total][16], d_out float32 [out_offsets[n_utt]]. */
+int gtts_batch_run_device(gtts_batch* batch, const float* d_frames, float* d_out, void* cuda_stream);
+/* Same with HOST buffers: host->device copy of the frames, kernels, device->host copy of the audio,
+ * synchronised on return.  Buffers may be pageable or pinned. */
+int gtts_batch_run_host(gtts_batch* batch, const float* h_frames, float* h_out);
+/* Number of kernel launches the last run issued (for bench.py's gpu_launches claim). */
+int gtts_batch_last_launches(const gtts_batch* batch, int32_t* n_out);
+void gtts_batch_free(gtts_batch* batch);
+
+/* One-call convenience over prepare + run_host + free (what a C caller of the reference's
+ * Controller::synthesize + outputBuffer() would use).  out must hold out_offsets[n_utt] samples as
+ * given by gtts_output_length per utterance; out_offsets is filled if not NULL. */
+int gtts_batch_synthesize(gtts_handle* handle, const gtts_voice_config* voices, int32_t n_voices,
+			const int32_t* voice_index, double control_rate, const float* frames,
+			const int64_t* frame_offsets, int64_t n_utt, float* out, int64_t out_capacity,
+			int64_t* out_offsets);
+
+/* ---- streaming (one utterance, control frame by control frame; BASELINE config 5) ------------------ */
+
+int gtts_stream_open(gtts_handle* handle, const gtts_voice_config* voice, double control_rate,
+			int32_t steps_override, gtts_stream** stream_out);
+/* Appends n_frames frames (host float32 [n_frames][16]).  Control periods whose end frame is known
+ * are synthesised now; audio that is final is written to out (host, capacity in samples). */
+int gtts_stream_push_frames(gtts_stream* stream, const float* frames, int64_t n_frames,
+			float* out, int64_t out_capacity, int64_t* n_written);
+/* Last control period (duplicated final frame, Controller.cpp:283) + SRC flush (finishSynthesis()). */
+int gtts_stream_finish(gtts_stream* stream, float* out, int64_t out_capacity, int64_t* n_written);
+/* Back to the state right after open (VocalTractModel::reset(), VocalTractModel0.h:309-326). */
+int gtts_stream_reset(gtts_stream* stream);
+void gtts_stream_close(gtts_stream* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GTTS_B200_H_ */
