@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: batched tube-model synthesis (BASELINE.json metric
+"audio-seconds synthesized per wall-second").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (config.workload): BASELINE config 2 -- 1,024 synthetic control tracks of 2,500 frames (10 s)
+per GPU, voice 0_male/male (fs_int 20,034 Hz, 80 internal samples per 4 ms control frame), i.e.
+204.8 M internal samples -> 490.8 M float32 output samples (10,224 audio-seconds) per step per GPU.
+One step = one pass of the whole batch through the tube path.  N > 1 (torchrun, one rank per GPU):
+every rank synthesises its own 1,024 utterances (weak scaling, no collective on the data path; NCCL
+is used only for the barrier and the max-over-ranks of the timings).
+
+value  = audio-seconds / wall-second with the control tracks already resident in HBM (CUDA events on
+         the launching stream around K launches, max over ranks).
+e2e    = the same through gtts_batch_run_host: pinned HOST buffers in, H2D copy + kernel + D2H copy of
+         the float32 audio inside the timed region.
+roofline: FP64 FMA pipe. achieved = algorithmic flops per launch (384 per internal sample + 106 per
+         output sample) / launch duration; peak = the DFMA peak measured on this
+         GPU by gtts_probe_fp64_peak just before the timed region.
+cpu_baseline: the unmodified reference compiled in place (oracle/_ref, kind "reference"; the oracle
+         port if that build is absent) on the host cores, bounded sample of the same tracks.
+--impl reference: the reference arm -- the reference's own CPU implementation, all host threads.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_UTT = 1024
+N_FRAMES = 2500
+SEED0 = 20240
+FLOP_PER_INTERNAL = 384.0     # SURVEY.md section 8d / BASELINE.md section 4
+FLOP_PER_OUTPUT = 106.0
+FP64_PEAK_FALLBACK_TFLOPS = 34.1   # measured on this pool's B200 (profiles/fp64_pipe_r01.json)
+METRIC = "audio_seconds_per_wall_second"
+UNIT = "audio-s/s"
+
+
+def make_tracks(rank, n_utt, n_frames):
+    from gama_tts_b200 import tracks as T
+    cache = os.path.join(tempfile.gettempdir(), "gtts_bench_tracks_r%d_%d_%d.npy" % (rank, n_utt, n_frames))
+    if os.path.exists(cache):
+        try:
+            a = np.load(cache)
+            if a.shape == (n_utt * n_frames, 16):
+                return a
+        except Exception:
+            pass
+    a = np.concatenate([T.synthetic_track(SEED0 + rank * n_utt + u, n_frames) for u in range(n_utt)])
+    try:
+        np.save(cache, a)
+    except Exception:
+        pass
+    return a
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.proc = None
+        self.path = os.path.join(tempfile.gettempdir(), "gtts_clocks_%d_%d.csv" % (os.getpid(), gpu_index))
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, reasons, smax = [], set(), None
+        for line in open(self.path):
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                smax = float(p[2])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+        if sm:
+            busy = [x for x in sm if x > 0.5 * max(sm)] or sm
+            out.update(sm_mhz=float(np.median(busy)), sm_max_mhz=smax, reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_reference_run(frames, n_frames, n_utt_sample, threads):
+    """Times the reference's CPU path on the first n_utt_sample tracks. Returns (audio_s_per_s, kind, seconds)."""
+    from gama_tts_b200.voices import default_voice
+    from oracle import pyoracle
+    voice = default_voice("male")
+    fo = np.arange(n_utt_sample + 1, dtype=np.int64) * n_frames
+    sub = frames[:n_utt_sample * n_frames]
+    try:
+        ref = pyoracle.Reference()
+        sec, n_each, _ = ref.batch(voice, sub, fo, n_threads=threads)
+        kind = "reference"
+        audio = float(n_each.sum()) / voice["output_rate"]
+    except (FileNotFoundError, OSError, subprocess.CalledProcessError):
+        # the in-place build of the reference is absent: time the oracle port, single thread
+        orc = pyoracle.Oracle()
+        t0 = time.perf_counter()
+        n = 0
+        for u in range(n_utt_sample):
+            n += len(orc.synthesize(voice, sub[u * n_frames:(u + 1) * n_frames]))
+        sec = time.perf_counter() - t0
+        kind = "port"
+        threads = 1
+        audio = n / voice["output_rate"]
+    return audio / sec, kind, sec, threads
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    threads = host_threads()
+    n_sample = min(N_UTT, threads * 16)
+    frames = make_tracks(0, N_UTT, N_FRAMES)
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, kind, sec, used = cpu_reference_run(frames, N_FRAMES, n_sample, threads)
+        if i >= args.warmup:
+            vals.append((v, sec))
+    value = float(np.mean([v for v, _ in vals]))
+    ms = float(np.mean([s for _, s in vals])) * 1e3
+    sample = "%d of the %d tracks (10 s each) per step, %d threads" % (n_sample, N_UTT, used)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config():
+    return {"workload": "BASELINE config 2: 1024 synthetic control tracks x 2500 frames (10 s) per GPU, voice 0_male/male, "
+                        "fs_int 20034 Hz, output 48 kHz float32",
+            "utterances_per_gpu": N_UTT, "frames_per_utterance": N_FRAMES, "control_rate_hz": 250,
+            "cache": "inputs (164 MB) + outputs (1.96 GB) per step exceed the 126 MB L2; no explicit flush"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import gama_tts_b200 as g
+    from gama_tts_b200.voices import default_voice
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+
+    voice = default_voice("male")
+    frames_np = make_tracks(rank, N_UTT, N_FRAMES)
+    fo = np.arange(N_UTT + 1, dtype=np.int64) * N_FRAMES
+    synth = g.TubeSynthesizer(local_rank)
+    batch = synth.prepare(voice, fo)
+    n_out = batch.n_out_total
+    n_internal = int(batch.n_internal.sum())
+    audio_seconds = n_out / voice["output_rate"]
+    flops_per_launch = FLOP_PER_INTERNAL * n_internal + FLOP_PER_OUTPUT * n_out
+
+    h_frames = torch.from_numpy(frames_np).pin_memory()
+    h_out = torch.empty(n_out, dtype=torch.float32).pin_memory()
+    d_frames = h_frames.cuda(non_blocking=True)
+    d_out = torch.empty(n_out, dtype=torch.float32, device="cuda")
+    stream = torch.cuda.current_stream()
+    sptr = stream.cuda_stream
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    peak = synth.fp64_peak_tflops()
+    peak_src = "measured by gtts_probe_fp64_peak on this GPU (register-resident DFMA, burst)"
+    if not peak or peak <= 0:
+        peak, peak_src = FP64_PEAK_FALLBACK_TFLOPS, "fallback: profiles/fp64_pipe_r01.json"
+
+    # ---- device-resident timing -------------------------------------------------------------------
+    for _ in range(args.warmup):
+        batch.run_device(d_frames.data_ptr(), d_out.data_ptr(), sptr)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    e0.record(stream)
+    for _ in range(args.steps):
+        batch.run_device(d_frames.data_ptr(), d_out.data_ptr(), sptr)
+        launches += batch.last_launches()
+    e1.record(stream)
+    barrier()
+    ms_dev = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+
+    # ---- end to end: pinned host buffers through the C ABI ------------------------------------------
+    for _ in range(min(args.warmup, 2)):
+        batch.run_host_ptr(h_frames.data_ptr(), h_out.data_ptr())
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        batch.run_host_ptr(h_frames.data_ptr(), h_out.data_ptr())
+    torch.cuda.synchronize()
+    ms_e2e_local = (time.perf_counter() - t0) * 1e3 / args.steps
+    barrier()
+    ms_e2e = max_over_ranks(ms_e2e_local)
+    clocks = sampler.stop() if sampler is not None else None
+    checksum = float(h_out[::4097].double().abs().sum())
+
+    value = audio_seconds * world / (ms_dev * 1e-3)
+    e2e_value = audio_seconds * world / (ms_e2e * 1e-3)
+    achieved_tflops = flops_per_launch / (ms_dev * 1e-3) * 1e-12
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(),
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": int(frames_np.nbytes), "d2h_bytes_per_step": int(n_out * 4)},
+            "gpu_launches": launches,
+            "roofline": {"bound": "fp64_fma", "achieved": achieved_tflops, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved_tflops / peak, "traffic": None, "peak_source": peak_src,
+                         "flops_per_launch": flops_per_launch,
+                         "hbm_bytes_per_launch_algorithmic": int(frames_np.nbytes + n_out * 4)},
+            "clocks": clocks,
+            "kernel": json.loads(synth.describe()),
+            "checksum": checksum,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = host_threads()
+            n_sample = min(N_UTT, threads * 16)
+            v, kind, sec, used = cpu_reference_run(frames_np, N_FRAMES, n_sample, threads)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": used, "kind": kind,
+                                    "sample": "first %d of the %d tracks (10 s each), %.2f s wall" % (n_sample, N_UTT, sec)}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

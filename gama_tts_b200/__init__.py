@@ -1,0 +1,221 @@
+"""gama_tts_b200 -- B200-native batched GamaTTS tube model (reference model 0) behind a C ABI.
+
+The product is ``csrc/libgtts_b200.so`` (hand-written sm_100a kernels + C++ host runtime, ABI in
+``include/gtts_b200.h``) and the plugin shim ``csrc/libgtts_plugin.so`` the unmodified reference
+loads through its own ``VocalTractModelPlugin`` seam.  This package is the thin Python view used by
+the tests and the benchmark: it mirrors the reference's ``VocalTractModel`` call pattern
+(``gama_tts/src/vtm/VocalTractModel.h:43-71``) for batches:
+
+    synth = TubeSynthesizer(device=0)
+    audio = synth.synthesize(voice, [track0, track1, ...])      # Controller::synthesize + outputBuffer()
+
+There is no CPU implementation here; importing works without a GPU, constructing a synthesizer
+does not.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi, voices  # noqa: F401
+from .capi import GttsError, check, load, voice_array, voice_config
+
+NUM_PARAMS = 16
+
+
+def _as_tracks(tracks):
+    out = []
+    for t in tracks:
+        a = np.ascontiguousarray(t, dtype=np.float32).reshape(-1, NUM_PARAMS)
+        out.append(a)
+    return out
+
+
+def pack_tracks(tracks):
+    """list of [F_u, 16] float32 -> (frames [sum F_u, 16], frame_offsets int64 [U+1])."""
+    tracks = _as_tracks(tracks)
+    fo = np.zeros(len(tracks) + 1, np.int64)
+    if tracks:
+        fo[1:] = np.cumsum([len(t) for t in tracks])
+    frames = np.concatenate(tracks) if tracks else np.zeros((0, NUM_PARAMS), np.float32)
+    return np.ascontiguousarray(frames, np.float32), fo
+
+
+def internal_rate(voice):
+    v = voice_config(voice)
+    fs = C.c_int32()
+    check(load().gtts_voice_internal_rate(C.byref(v), C.byref(fs)))
+    return fs.value
+
+
+def control_steps(voice, control_rate=voices.DEFAULT_CONTROL_RATE):
+    v = voice_config(voice)
+    st = C.c_int32()
+    check(load().gtts_voice_control_steps(C.byref(v), float(control_rate), C.byref(st)))
+    return st.value
+
+
+def output_length(voice, n_frames, control_rate=voices.DEFAULT_CONTROL_RATE, steps=None):
+    """(n_internal, n_output) of a track of n_frames control frames."""
+    v = voice_config(voice)
+    if steps is None:
+        steps = control_steps(voice, control_rate)
+    ni, no = C.c_int64(), C.c_int64()
+    check(load().gtts_output_length(C.byref(v), int(steps), int(n_frames), C.byref(ni), C.byref(no)))
+    return ni.value, no.value
+
+
+def shard_plan(cost, n_shards):
+    """Greedy longest-first assignment of utterances to GPUs; returns int32 [U] shard ids."""
+    cost = np.ascontiguousarray(cost, np.int64)
+    out = np.zeros(len(cost), np.int32)
+    check(load().gtts_shard_plan(cost.ctypes.data, len(cost), int(n_shards), out.ctypes.data))
+    return out
+
+
+class Batch:
+    """A prepared batch (gtts_batch): plan + device metadata; run it as often as you like."""
+
+    def __init__(self, synth, voice_list, n_utt, frame_offsets, voice_index, control_rate, steps_override):
+        self._lib = load()
+        self._synth = synth
+        self._h = C.c_void_p()
+        va = voice_array(voice_list)
+        fo = np.ascontiguousarray(frame_offsets, np.int64)
+        vi = None if voice_index is None else np.ascontiguousarray(voice_index, np.int32)
+        so = None if steps_override is None else np.ascontiguousarray(steps_override, np.int32)
+        check(self._lib.gtts_batch_prepare(synth._h, va, len(voice_list), None if vi is None else vi.ctypes.data,
+                                           float(control_rate), None if so is None else so.ctypes.data,
+                                           fo.ctypes.data, int(n_utt), C.byref(self._h)))
+        self.n_utt = int(n_utt)
+        self.frame_offsets = fo
+        self.out_offsets = np.zeros(self.n_utt + 1, np.int64)
+        self.n_internal = np.zeros(max(self.n_utt, 1), np.int64)
+        check(self._lib.gtts_batch_layout(self._h, self.out_offsets.ctypes.data, self.n_internal.ctypes.data))
+        self.n_internal = self.n_internal[:self.n_utt]
+        self.n_out_total = int(self.out_offsets[-1])
+        self.n_frames_total = int(fo[-1]) if len(fo) else 0
+
+    def run_device(self, d_frames_ptr, d_out_ptr, stream_ptr=0):
+        check(self._lib.gtts_batch_run_device(self._h, C.c_void_p(d_frames_ptr), C.c_void_p(d_out_ptr),
+                                              C.c_void_p(stream_ptr)))
+
+    def run_host(self, frames, out=None):
+        frames = np.ascontiguousarray(frames, np.float32)
+        if out is None:
+            out = np.empty(self.n_out_total, np.float32)
+        check(self._lib.gtts_batch_run_host(self._h, frames.ctypes.data, out.ctypes.data))
+        return out
+
+    def run_host_ptr(self, frames_ptr, out_ptr):
+        check(self._lib.gtts_batch_run_host(self._h, C.c_void_p(frames_ptr), C.c_void_p(out_ptr)))
+
+    def last_launches(self):
+        n = C.c_int32()
+        check(self._lib.gtts_batch_last_launches(self._h, C.byref(n)))
+        return n.value
+
+    def split(self, packed):
+        return [packed[self.out_offsets[u]:self.out_offsets[u + 1]] for u in range(self.n_utt)]
+
+    def close(self):
+        if self._h:
+            self._lib.gtts_batch_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Stream:
+    """One utterance fed control frame by control frame (gtts_stream)."""
+
+    def __init__(self, synth, voice, control_rate, steps_override=0):
+        self._lib = load()
+        self._synth = synth
+        self._h = C.c_void_p()
+        v = voice_config(voice)
+        check(self._lib.gtts_stream_open(synth._h, C.byref(v), float(control_rate), int(steps_override), C.byref(self._h)))
+        self._fs = internal_rate(voice)
+        self._ratio = voice["output_rate"] / self._fs
+        self._steps = steps_override if steps_override > 0 else control_steps(voice, control_rate)
+
+    def _cap(self, n_frames):
+        return int((n_frames * self._steps + 64) * self._ratio) + 256
+
+    def push(self, frames):
+        frames = np.ascontiguousarray(frames, np.float32).reshape(-1, NUM_PARAMS)
+        out = np.empty(self._cap(len(frames) + 1), np.float32)
+        n = C.c_int64()
+        check(self._lib.gtts_stream_push_frames(self._h, frames.ctypes.data, len(frames), out.ctypes.data, len(out), C.byref(n)))
+        return out[:n.value].copy()
+
+    def finish(self):
+        out = np.empty(self._cap(2), np.float32)
+        n = C.c_int64()
+        check(self._lib.gtts_stream_finish(self._h, out.ctypes.data, len(out), C.byref(n)))
+        return out[:n.value].copy()
+
+    def reset(self):
+        check(self._lib.gtts_stream_reset(self._h))
+
+    def close(self):
+        if self._h:
+            self._lib.gtts_stream_close(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class TubeSynthesizer:
+    """One GPU's worth of the tube path (gtts_handle)."""
+
+    def __init__(self, device=0):
+        self._lib = load()
+        self._h = C.c_void_p()
+        check(self._lib.gtts_create(int(device), C.byref(self._h)))
+        self.device = int(device)
+
+    def describe(self):
+        return self._lib.gtts_describe(self._h).decode()
+
+    def fp64_peak_tflops(self):
+        t = C.c_double()
+        check(self._lib.gtts_probe_fp64_peak(self._h, C.byref(t)))
+        return t.value
+
+    def prepare(self, voice_or_voices, frame_offsets, voice_index=None, control_rate=voices.DEFAULT_CONTROL_RATE,
+                steps_override=None):
+        vl = [voice_or_voices] if isinstance(voice_or_voices, dict) else list(voice_or_voices)
+        return Batch(self, vl, len(frame_offsets) - 1, frame_offsets, voice_index, control_rate, steps_override)
+
+    def synthesize(self, voice_or_voices, tracks, voice_index=None, control_rate=voices.DEFAULT_CONTROL_RATE,
+                   steps_override=None):
+        """Host-buffer path: tracks (list of [F,16] float32) -> list of float32 audio arrays, the raw
+        outputBuffer() of each utterance (before the reference's peak normalisation)."""
+        frames, fo = pack_tracks(tracks)
+        b = self.prepare(voice_or_voices, fo, voice_index, control_rate, steps_override)
+        try:
+            return [a.copy() for a in b.split(b.run_host(frames))]
+        finally:
+            b.close()
+
+    def stream(self, voice, control_rate=voices.DEFAULT_CONTROL_RATE, steps_override=0):
+        return Stream(self, voice, control_rate, steps_override)
+
+    def close(self):
+        if self._h:
+            self._lib.gtts_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

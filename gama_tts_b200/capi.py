@@ -1,0 +1,116 @@
+"""ctypes view of include/gtts_b200.h: structures, prototypes and the library loader.
+
+Python is test / benchmark orchestration only; the product is the C-ABI library
+``gama_tts_b200/csrc/libgtts_b200.so`` (CUDA kernels + C++ host runtime).  Loading fails loudly when
+the library is missing -- there is no Python or CPU implementation to fall back to.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libgtts_b200.so")
+
+GTTS_OK, GTTS_ERR_INVALID, GTTS_ERR_CUDA, GTTS_ERR_NO_DEVICE, GTTS_ERR_NOMEM, GTTS_ERR_UNSUPPORTED = range(6)
+
+
+class VoiceConfig(C.Structure):
+    """struct gtts_voice_config"""
+    _fields_ = [
+        ("output_rate", C.c_double), ("waveform", C.c_int32), ("noise_modulation", C.c_int32),
+        ("glottal_pulse_tp", C.c_double), ("glottal_pulse_tn_min", C.c_double), ("glottal_pulse_tn_max", C.c_double),
+        ("breathiness", C.c_double), ("vocal_tract_length_offset", C.c_double), ("vocal_tract_length", C.c_double),
+        ("temperature", C.c_double), ("loss_factor", C.c_double), ("mouth_coefficient", C.c_double),
+        ("nose_coefficient", C.c_double), ("throat_cutoff", C.c_double), ("throat_volume", C.c_double),
+        ("mix_offset", C.c_double), ("global_radius_coef", C.c_double), ("global_nasal_radius_coef", C.c_double),
+        ("aperture_radius", C.c_double), ("nasal_radius", C.c_double * 5), ("radius_coef", C.c_double * 8),
+    ]
+
+
+def voice_config(voice):
+    """dict keyed like the reference's vtm.txt / variant files -> struct gtts_voice_config."""
+    s = VoiceConfig()
+    for name, ctype in VoiceConfig._fields_:
+        if name == "nasal_radius":
+            for i in range(5):
+                s.nasal_radius[i] = float(voice["nasal_radius_%d" % (i + 1)])
+        elif name == "radius_coef":
+            for i in range(8):
+                s.radius_coef[i] = float(voice["radius_%d_coef" % (i + 1)])
+        elif ctype is C.c_int32:
+            setattr(s, name, int(voice[name]))
+        else:
+            setattr(s, name, float(voice[name]))
+    return s
+
+
+def voice_array(voices):
+    arr = (VoiceConfig * len(voices))()
+    for i, v in enumerate(voices):
+        arr[i] = voice_config(v)
+    return arr
+
+
+EXPORTS = [
+    "gtts_last_error", "gtts_abi_version", "gtts_voice_internal_rate", "gtts_voice_control_steps",
+    "gtts_output_length", "gtts_shard_plan", "gtts_probe_fir_taps", "gtts_probe_src_tables",
+    "gtts_probe_voice_constants", "gtts_probe_fp64_peak", "gtts_create", "gtts_destroy", "gtts_describe", "gtts_batch_prepare",
+    "gtts_batch_layout", "gtts_batch_run_device", "gtts_batch_run_host", "gtts_batch_last_launches",
+    "gtts_batch_free", "gtts_batch_synthesize", "gtts_stream_open", "gtts_stream_push_frames",
+    "gtts_stream_finish", "gtts_stream_reset", "gtts_stream_close",
+]
+
+_lib = None
+
+
+def load():
+    """Loads libgtts_b200.so and declares the prototypes of include/gtts_b200.h."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    PV = C.POINTER(VoiceConfig)
+    L.gtts_last_error.restype = C.c_char_p
+    L.gtts_describe.restype = C.c_char_p
+    L.gtts_describe.argtypes = [vp]
+    L.gtts_voice_internal_rate.argtypes = [PV, C.POINTER(i32)]
+    L.gtts_voice_control_steps.argtypes = [PV, dbl, C.POINTER(i32)]
+    L.gtts_output_length.argtypes = [PV, i32, i64, C.POINTER(i64), C.POINTER(i64)]
+    L.gtts_shard_plan.argtypes = [vp, i64, i32, vp]
+    L.gtts_probe_fir_taps.argtypes = [vp, i32, C.POINTER(i32)]
+    L.gtts_probe_src_tables.argtypes = [vp, vp]
+    L.gtts_probe_voice_constants.argtypes = [PV, vp, i32, C.POINTER(i32)]
+    L.gtts_probe_fp64_peak.argtypes = [vp, C.POINTER(dbl)]
+    L.gtts_create.argtypes = [i32, C.POINTER(vp)]
+    L.gtts_destroy.argtypes = [vp]
+    L.gtts_destroy.restype = None
+    L.gtts_batch_prepare.argtypes = [vp, PV, i32, vp, dbl, vp, vp, i64, C.POINTER(vp)]
+    L.gtts_batch_layout.argtypes = [vp, vp, vp]
+    L.gtts_batch_run_device.argtypes = [vp, vp, vp, vp]
+    L.gtts_batch_run_host.argtypes = [vp, vp, vp]
+    L.gtts_batch_last_launches.argtypes = [vp, C.POINTER(i32)]
+    L.gtts_batch_free.argtypes = [vp]
+    L.gtts_batch_free.restype = None
+    L.gtts_batch_synthesize.argtypes = [vp, PV, i32, vp, dbl, vp, vp, i64, vp, i64, vp]
+    L.gtts_stream_open.argtypes = [vp, PV, dbl, i32, C.POINTER(vp)]
+    L.gtts_stream_push_frames.argtypes = [vp, vp, i64, vp, i64, C.POINTER(i64)]
+    L.gtts_stream_finish.argtypes = [vp, vp, i64, C.POINTER(i64)]
+    L.gtts_stream_reset.argtypes = [vp]
+    L.gtts_stream_close.argtypes = [vp]
+    L.gtts_stream_close.restype = None
+    _lib = L
+    return L
+
+
+class GttsError(RuntimeError):
+    def __init__(self, code, text):
+        super().__init__("gtts error %d: %s" % (code, text))
+        self.code = code
+
+
+def check(rc):
+    if rc != GTTS_OK:
+        raise GttsError(rc, load().gtts_last_error().decode(errors="replace"))

@@ -1,0 +1,72 @@
+#include "batch_plan.h"
+
+#include <algorithm>
+#include <numeric>
+
+namespace gtts {
+
+std::string planBatch(const gtts_voice_config* voices, int32_t nVoices, const int32_t* voiceIndex,
+			double controlRate, const int32_t* stepsOverride, const int64_t* frameOffsets,
+			int64_t nUtt, BatchPlan& plan, int* err)
+{
+	*err = GTTS_ERR_INVALID;
+	if (!voices || nVoices <= 0) return "no voices given";
+	if (nUtt < 0 || (nUtt > 0 && !frameOffsets)) return "bad utterance count / frame offsets";
+	if (!stepsOverride && !(controlRate > 0.0)) return "control_rate must be positive";
+	plan.voices.resize(nVoices);
+	for (int32_t i = 0; i < nVoices; ++i) {
+		const char* e = deriveVoice(voices[i], plan.voices[i]);
+		if (e) return std::string("voice ") + std::to_string(i) + ": " + e;
+		if (!plan.voices[i].src_upsample) {
+			// fs_int > output_rate (vocal tract shorter than ~7.3 cm at 48 kHz): the reference switches
+			// to its down-sampling loop (SampleRateConverter.h:362-415), which this path does not implement.
+			*err = GTTS_ERR_UNSUPPORTED;
+			return std::string("voice ") + std::to_string(i) + ": internal rate above output rate (down-sampling SRC) is not supported";
+		}
+	}
+	plan.utts.resize(nUtt);
+	plan.out_offsets.assign(nUtt + 1, 0);
+	plan.n_internal_total = 0;
+	for (int64_t u = 0; u < nUtt; ++u) {
+		UttDesc& d = plan.utts[u];
+		const int32_t vi = voiceIndex ? voiceIndex[u] : 0;
+		if (vi < 0 || vi >= nVoices) return "voice_index out of range";
+		const int64_t f0 = frameOffsets[u], f1 = frameOffsets[u + 1];
+		if (f1 < f0 || f0 < 0) return "frame_offsets must be non-decreasing";
+		const VoiceDev& v = plan.voices[vi];
+		int32_t steps = (stepsOverride && stepsOverride[u] > 0) ? stepsOverride[u] : controlSteps(v.fs, controlRate);
+		if (steps <= 0) return "control steps must be positive (control_rate above the internal rate?)";
+		d.frame_begin = f0;
+		d.n_frames = f1 - f0;
+		d.voice = vi;
+		d.steps = steps;
+		d.inv_steps = 1.0f / static_cast<float>(static_cast<unsigned int>(steps));   // Controller.cpp:287
+		d.n_internal = d.n_frames * steps;
+		d.n_out = outputLength(v, d.n_internal);
+		d.out_begin = plan.out_offsets[u];
+		d.flags = 0;
+		d.state_index = -1;
+		plan.out_offsets[u + 1] = plan.out_offsets[u] + d.n_out;
+		plan.n_internal_total += d.n_internal;
+	}
+	plan.n_frames_total = nUtt ? frameOffsets[nUtt] : 0;
+	plan.order.resize(nUtt);
+	std::iota(plan.order.begin(), plan.order.end(), 0);
+	std::stable_sort(plan.order.begin(), plan.order.end(), [&](int32_t a, int32_t b) {
+		return plan.utts[a].n_internal > plan.utts[b].n_internal;
+	});
+	*err = GTTS_OK;
+	return std::string();
+}
+
+void lcgMultipliers(unsigned long long* out32)
+{
+	const unsigned long long mask = (1ull << 44) - 1;
+	unsigned long long p = 1;
+	for (int j = 0; j < 32; ++j) {
+		p = (p * 377ull) & mask;
+		out32[j] = p;
+	}
+}
+
+} // namespace gtts

@@ -1,0 +1,33 @@
+// Host-side planning of a batch: per-utterance descriptors, output layout, processing order.
+// Pure C++ (no CUDA) so that it can be unit-tested without a GPU.
+#ifndef GTTS_BATCH_PLAN_H_
+#define GTTS_BATCH_PLAN_H_
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "host_tables.h"
+
+namespace gtts {
+
+struct BatchPlan {
+	std::vector<VoiceDev> voices;
+	std::vector<UttDesc> utts;
+	std::vector<int32_t> order;          // longest first (persistent warps pop from the front)
+	std::vector<int64_t> out_offsets;    // n_utt + 1
+	int64_t n_frames_total = 0;
+	int64_t n_internal_total = 0;
+};
+
+// Returns an empty string on success, else the error text (code in *err: GTTS_ERR_*).
+std::string planBatch(const gtts_voice_config* voices, int32_t nVoices, const int32_t* voiceIndex,
+			double controlRate, const int32_t* stepsOverride, const int64_t* frameOffsets,
+			int64_t nUtt, BatchPlan& plan, int* err);
+
+// 377^(j+1) mod 2^44, j = 0..31: jump-ahead multipliers of the noise generator
+// (reference NoiseSource.h:40-44 is exactly this LCG on the 2^-44 grid).
+void lcgMultipliers(unsigned long long* out32);
+
+} // namespace gtts
+#endif

@@ -1,0 +1,251 @@
+// Host-side, init-time arithmetic of the tube path: per-voice derived constants, the glottal FIR
+// design, the SRC windowed-sinc tables, output-length closed form and the multi-GPU shard plan.
+// Everything here is double precision libm work done once per voice / per process (SURVEY.md
+// Appendix B); nothing here runs per sample.  Compiled with -ffp-contract=off so that the table
+// values do not depend on the host compiler's FMA contraction.
+#include "host_tables.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+namespace gtts {
+
+namespace {
+
+constexpr double kPi = 3.14159265358979323846;
+
+// Util::amplitude60dB (reference gama_tts/src/vtm/VTMUtil.h:50-67)
+double amplitude60dB(double db)
+{
+	if (db <= 0.0) return 0.0;
+	if (db == 60.0) return 1.0;
+	return std::pow(10.0, (db - 60.0) * (1.0 / 20.0));
+}
+
+// Best rational approximation with bounded denominator
+// (WavetableGlottalSourceFIRFilter.h:336-382).
+void bestRational(double number, int& order, int& numerator, int& denominator)
+{
+	if (order <= 0) { numerator = 0; denominator = 0; order = -1; return; }
+	const double frac = std::fabs(number - static_cast<int>(number));
+	const int maxDen = std::min(2 * order, 200);
+	double best = 1.0;
+	int bestNum = 0;
+	for (int den = order; den <= maxDen; ++den) {
+		const double scaled = den * frac;
+		const int nearest = static_cast<int>(scaled + 0.5);
+		const double err = std::fabs((scaled - static_cast<double>(nearest)) / den);
+		if (err < best) { best = err; bestNum = nearest; denominator = den; }
+	}
+	numerator = static_cast<int>(std::fabs(number)) * denominator + bestNum;
+	if (number < 0.0) numerator = -numerator;
+	order = denominator - 1;
+	if (numerator == denominator) {
+		denominator = maxDen;
+		order = numerator = denominator - 1;
+	}
+}
+
+} // namespace
+
+// Maximally-flat linear-phase lowpass (beta = transition centre, gamma = transition width), trimmed
+// at |c| < cutoff and laid out symmetric (WavetableGlottalSourceFIRFilter.h:74-114, 137-215, 228-237).
+std::vector<double> designGlottalFir(double beta, double gamma, double cutoff)
+{
+	std::vector<double> mag(202), cosv(202), half(202);
+	int order = static_cast<int>(1.0 / (4.0 * gamma * gamma));
+	const double edge = (1.0 + std::cos((2.0 * kPi) * beta)) / 2.0;
+	int numer = 0, points = 0;
+	bestRational(edge, order, numer, points);
+	const int n = 2 * points - 1;
+	if (numer == 0) numer = 1;
+	cosv[1] = mag[1] = 1.0;
+	const int flatOrder = order - numer;
+	for (int i = 2; i <= points; ++i) {
+		cosv[i] = std::cos((2.0 * kPi) * (static_cast<double>(i - 1) / n));
+		const double x = (1.0 - cosv[i]) / 2.0;
+		if (numer == order) continue;
+		double xpow = x, series = 1.0;
+		for (int j = 1; j <= flatOrder; ++j) {
+			double term = xpow;
+			for (int q = 1; q <= numer - 1; ++q) term *= 1.0 + (static_cast<double>(j) / q);
+			xpow *= x;
+			series += term;
+		}
+		mag[i] = series * std::pow(1.0 - x, numer);
+	}
+	for (int i = 1; i <= points; ++i) {
+		half[i] = mag[1] / 2.0;
+		for (int j = 2; j <= points; ++j) {
+			int m = ((i - 1) * (j - 1)) % n;
+			if (m > order) m = n - m;
+			half[i] += cosv[m + 1] * mag[j];
+		}
+		half[i] *= 2.0 / static_cast<double>(n);
+	}
+	int kept = points;
+	for (int i = points; i > 0; --i) {
+		if (std::fabs(half[i]) >= std::fabs(cutoff)) { kept = i; break; }
+	}
+	std::vector<double> taps(2 * kept - 1);
+	for (int i = 0; i < kept; ++i) {
+		taps[kept - 1 - i] = half[i + 1];
+		taps[kept - 1 + i] = half[i + 1];
+	}
+	return taps;
+}
+
+namespace {
+
+// Modified Bessel I0 by its power series (SampleRateConverter.h:175-194).
+double besselI0(double x)
+{
+	double sum = 1.0, term = 1.0;
+	const double hx = x / 2.0;
+	int n = 1;
+	do {
+		double t = hx / n;
+		n += 1;
+		t *= t;
+		term *= t;
+		sum += term;
+	} while (term >= 1e-21 * sum);
+	return sum;
+}
+
+} // namespace
+
+// Kaiser-windowed sinc, 13 zero crossings x 256 phases, and its first differences
+// (SampleRateConverter.h:230-255).
+void buildSrcTables(double* h, double* dh)
+{
+	const double kaiserBeta = 5.658, cutoff = 11.0 / 13.0;
+	const double step = kPi / kSrcLRange;
+	h[0] = cutoff;
+	for (int i = 1; i < kSrcFilterLen; ++i) {
+		const double y = i * step;
+		h[i] = std::sin(y * cutoff) / y;
+	}
+	const double norm = 1.0 / besselI0(kaiserBeta);
+	for (int i = 0; i < kSrcFilterLen; ++i) {
+		const double t = static_cast<double>(i) / kSrcFilterLen;
+		h[i] *= besselI0(kaiserBeta * std::sqrt(1.0 - (t * t))) * norm;
+	}
+	for (int i = 0; i + 1 < kSrcFilterLen; ++i) dh[i] = h[i + 1] - h[i];
+	dh[kSrcFilterLen - 1] = 0.0 - h[kSrcFilterLen - 1];
+}
+
+int internalRate(const gtts_voice_config& c)
+{
+	// VocalTractModel0.h:274-279, 343-344
+	double length = c.vocal_tract_length_offset + c.vocal_tract_length;
+	if (length < 3.0) length = 3.0; else if (length > 30.0) length = 30.0;
+	const double speed = 331.4 + (0.6 * c.temperature);       // VTMUtil.h:107-113
+	return static_cast<int>((speed * 10 * 100.0) / length);
+}
+
+int controlSteps(int fs, double controlRate)
+{
+	return static_cast<int>(static_cast<unsigned int>(std::rint(fs / controlRate)));   // Controller.cpp:286
+}
+
+const char* deriveVoice(const gtts_voice_config& c, VoiceDev& v)
+{
+	std::memset(&v, 0, sizeof v);
+	if (!(c.output_rate > 0.0)) return "output_rate must be positive";
+	if (c.waveform != 0 && c.waveform != 1) return "waveform must be 0 (pulse) or 1 (sine)";
+	v.fs = internalRate(c);
+	if (v.fs <= 0) return "internal sample rate is not positive";
+	v.waveform = c.waveform;
+	v.modulation = c.noise_modulation ? 1 : 0;
+	const double nyquist = static_cast<double>(static_cast<float>(v.fs) / 2.0f);   // :345 (int / 2.0f is float)
+
+	v.breath = c.breathiness / 100.0;                       // :349
+	v.one_minus_breath = 1.0 - v.breath;                    // :422
+	const double mix = amplitude60dB(c.mix_offset);
+	if (mix == 0.0) return "mix_offset must be > 0 dB";
+	v.crossmix = 1.0 / mix;                                 // :352
+	v.damping = 1.0 - (c.loss_factor / 100.0);              // :355
+
+	// Wavetable geometry (WavetableGlottalSource.h:104-109)
+	const unsigned d1 = static_cast<unsigned>(std::rint(kTableLen * (c.glottal_pulse_tp / 100.0)));
+	const unsigned d2 = static_cast<unsigned>(std::rint(kTableLen * ((c.glottal_pulse_tp + c.glottal_pulse_tn_max) / 100.0)));
+	if (c.waveform == 0 && (d1 == 0 || d2 <= d1 || d2 > kTableLen)) return "glottal pulse tp/tn out of range";
+	v.div1 = static_cast<int32_t>(d1);
+	v.div2 = static_cast<int32_t>(d2);
+	v.tn_length = static_cast<double>(d2 - d1);
+	v.tn_delta = std::rint(kTableLen * ((c.glottal_pulse_tn_max - c.glottal_pulse_tn_min) / 100.0));
+	if (v.tn_delta < 0.0 || v.tn_delta >= v.tn_length) return "glottal_pulse_tn_min/max out of range";
+	v.basic_inc = kTableLen / static_cast<double>(v.fs);
+
+	const double am = (nyquist - c.mouth_coefficient) / nyquist;    // :366
+	v.rad_m = am; v.refl_b0_m = 1.0 - std::fabs(am); v.refl_a1_m = -am;   // RadiationFilter.h:54-62, ReflectionFilter.h:55-61
+	const double an = (nyquist - c.nose_coefficient) / nyquist;     // :371
+	v.rad_n = an; v.refl_b0_n = 1.0 - std::fabs(an); v.refl_a1_n = -an;
+
+	const double apr = c.aperture_radius * c.global_radius_coef;   // :290
+	double nr[6];
+	nr[0] = 0.0;
+	for (int i = 0; i < 5; ++i) nr[i + 1] = c.nasal_radius[i] * c.global_nasal_radius_coef;   // :291-296
+	for (int i = 1; i < 5; ++i) {                                   // :460-464
+		const double a2 = nr[i] * nr[i], b2 = nr[i + 1] * nr[i + 1];
+		v.nasal_k[i] = (a2 - b2) / (a2 + b2);
+	}
+	{
+		const double a2 = nr[5] * nr[5], b2 = apr * apr;            // :467-469
+		v.nasal_k[5] = (a2 - b2) / (a2 + b2);
+	}
+	v.ap2 = apr * apr;
+	v.nr1_2 = nr[1] * nr[1];
+	for (int i = 0; i < 8; ++i) v.radius_coef[i] = c.radius_coef[i] * c.global_radius_coef;   // :297-304
+
+	v.throat_b0 = (c.throat_cutoff * 2.0) / v.fs;                  // Throat.h:52-61
+	v.throat_a1 = v.throat_b0 - 1.0;
+	v.throat_gain = amplitude60dB(c.throat_volume);
+	v.Ts = 1.0 / v.fs;
+
+	// SampleRateConverter.h:136-164
+	v.src_ratio = c.output_rate / v.fs;
+	v.src_inc = static_cast<uint32_t>(std::rint(std::pow(2.0, 16) / v.src_ratio));
+	if (v.src_inc == 0) return "sample rate ratio too large";
+	const double rounded = std::pow(2.0, 16) / v.src_inc;
+	if (v.src_ratio >= 1.0) {
+		v.src_upsample = 1;
+		v.src_pad = kSrcZeroCrossings;
+		v.src_phase_inc = 0;
+	} else {
+		v.src_upsample = 0;
+		v.src_phase_inc = static_cast<uint32_t>(std::rint(v.src_ratio * 65536));
+		v.src_pad = static_cast<int>(kSrcZeroCrossings / rounded) + 1;
+	}
+	return nullptr;
+}
+
+// Number of outputs after dataFill x n_internal + flushBuffer (SampleRateConverter.h:268-282,
+// 295-416, 462-471): output k sits at ring position (k*inc)>>16 and exists while that position is
+// below n_internal + 2*pad.
+int64_t outputLength(const VoiceDev& v, int64_t nInternal)
+{
+	const unsigned __int128 limit = static_cast<unsigned __int128>(nInternal + 2 * static_cast<int64_t>(v.src_pad)) << 16;
+	return static_cast<int64_t>((limit + v.src_inc - 1) / v.src_inc);
+}
+
+// Longest-processing-time-first greedy partition.
+void shardPlan(const int64_t* cost, int64_t n, int shards, int32_t* shardOf)
+{
+	std::vector<int64_t> order(n);
+	std::iota(order.begin(), order.end(), 0);
+	std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return cost[a] > cost[b]; });
+	std::vector<int64_t> load(shards, 0);
+	for (int64_t u : order) {
+		int best = 0;
+		for (int s = 1; s < shards; ++s) if (load[s] < load[best]) best = s;
+		shardOf[u] = best;
+		load[best] += cost[u];
+	}
+}
+
+} // namespace gtts

@@ -1,0 +1,530 @@
+// Host runtime + C ABI (include/gtts_b200.h) of the B200 tube path.
+//
+// One gtts_handle per GPU.  A gtts_batch owns the plan of U utterances (descriptors, voice
+// constants, processing order) in device memory; running it is one persistent kernel launch whose
+// warps pull utterances longest-first from an atomic queue.  No CPU fallback exists: every device
+// entry point fails with GTTS_ERR_NO_DEVICE / GTTS_ERR_CUDA if CUDA is unusable.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/gtts_b200.h"
+#include "batch_plan.h"
+#include "host_tables.h"
+#include "tube_kernel.cuh"
+
+using namespace gtts;
+
+namespace {
+
+thread_local std::string t_error;
+
+int fail(int code, const std::string& text)
+{
+	t_error = text;
+	return code;
+}
+
+int failCuda(cudaError_t e, const char* what)
+{
+	return fail(e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? GTTS_ERR_NO_DEVICE : GTTS_ERR_CUDA,
+			std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define GTTS_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return failCuda(e_, #call); } while (0)
+
+constexpr int kWarpsPerCta = 8;
+
+// FP64 FMA-pipe peak probe: 8 independent register-resident DFMA chains per thread.
+__global__ void fp64_peak_kernel(double* out, int iters, double a, double b)
+{
+	double x[8];
+#pragma unroll
+	for (int i = 0; i < 8; i++) x[i] = threadIdx.x * 1e-9 + i;
+	for (int it = 0; it < iters; it++) {
+#pragma unroll
+		for (int i = 0; i < 8; i++) x[i] = fma(x[i], a, b);
+	}
+	double s = 0;
+#pragma unroll
+	for (int i = 0; i < 8; i++) s += x[i];
+	out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+} // namespace
+
+struct gtts_handle {
+	int device = 0;
+	int sms = 0;
+	double2* d_src_tab = nullptr;
+	std::string description;
+};
+
+struct gtts_batch {
+	gtts_handle* h = nullptr;
+	BatchPlan plan;
+	VoiceDev* d_voices = nullptr;
+	UttDesc* d_utts = nullptr;
+	int32_t* d_order = nullptr;
+	int32_t* d_queue = nullptr;
+	UttState* d_states = nullptr;       // streaming only
+	float* d_frames = nullptr;          // staging for run_host
+	float* d_out = nullptr;
+	int64_t cap_frames = 0, cap_out = 0;
+	cudaStream_t stream = nullptr;      // used by run_host
+	int32_t last_launches = 0;
+};
+
+struct gtts_stream {
+	gtts_handle* h = nullptr;
+	gtts_voice_config voice;
+	VoiceDev vdev;
+	int32_t steps = 0;
+	gtts_batch* batch = nullptr;        // one-utterance batch re-used for every chunk
+	std::vector<float> pending;         // frames not yet consumed as a period start (<= 1 after a push)
+	int64_t n_in_done = 0, n_out_done = 0;
+	bool finished = false;
+};
+
+namespace {
+
+int launchBatch(gtts_batch* b, const float* dFrames, float* dOut, cudaStream_t stream)
+{
+	const int64_t nUtt = static_cast<int64_t>(b->plan.utts.size());
+	b->last_launches = 0;
+	if (nUtt == 0) return GTTS_OK;
+	GTTS_CUDA(cudaSetDevice(b->h->device));
+	GTTS_CUDA(cudaMemsetAsync(b->d_queue, 0, sizeof(int32_t), stream));
+	KernelParams P;
+	P.voices = b->d_voices;
+	P.utts = b->d_utts;
+	P.order = b->d_order;
+	P.frames = dFrames;
+	P.out = dOut;
+	P.states = b->d_states;
+	P.src_tab = b->h->d_src_tab;
+	P.queue = b->d_queue;
+	P.n_utt = static_cast<int32_t>(nUtt);
+	const int64_t ctasWanted = (nUtt + kWarpsPerCta - 1) / kWarpsPerCta;
+	const int grid = static_cast<int>(std::min<int64_t>(ctasWanted, b->h->sms));
+	const size_t smem = tube_smem_bytes(kWarpsPerCta);
+	tube_kernel_v0<kWarpsPerCta><<<grid, kWarpsPerCta * 32, smem, stream>>>(P);
+	GTTS_CUDA(cudaGetLastError());
+	b->last_launches = 1;
+	return GTTS_OK;
+}
+
+int uploadPlan(gtts_batch* b)
+{
+	const BatchPlan& p = b->plan;
+	GTTS_CUDA(cudaSetDevice(b->h->device));
+	GTTS_CUDA(cudaMalloc(&b->d_voices, sizeof(VoiceDev) * std::max<size_t>(p.voices.size(), 1)));
+	GTTS_CUDA(cudaMalloc(&b->d_utts, sizeof(UttDesc) * std::max<size_t>(p.utts.size(), 1)));
+	GTTS_CUDA(cudaMalloc(&b->d_order, sizeof(int32_t) * std::max<size_t>(p.order.size(), 1)));
+	GTTS_CUDA(cudaMalloc(&b->d_queue, sizeof(int32_t)));
+	GTTS_CUDA(cudaMemcpy(b->d_voices, p.voices.data(), sizeof(VoiceDev) * p.voices.size(), cudaMemcpyHostToDevice));
+	if (!p.utts.empty()) {
+		GTTS_CUDA(cudaMemcpy(b->d_utts, p.utts.data(), sizeof(UttDesc) * p.utts.size(), cudaMemcpyHostToDevice));
+		GTTS_CUDA(cudaMemcpy(b->d_order, p.order.data(), sizeof(int32_t) * p.order.size(), cudaMemcpyHostToDevice));
+	}
+	return GTTS_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+const char* gtts_last_error(void) { return t_error.c_str(); }
+int gtts_abi_version(void) { return GTTS_ABI_VERSION; }
+
+int gtts_voice_internal_rate(const gtts_voice_config* voice, int32_t* fs_out)
+{
+	if (!voice || !fs_out) return fail(GTTS_ERR_INVALID, "null argument");
+	*fs_out = internalRate(*voice);
+	return GTTS_OK;
+}
+
+int gtts_voice_control_steps(const gtts_voice_config* voice, double control_rate, int32_t* steps_out)
+{
+	if (!voice || !steps_out) return fail(GTTS_ERR_INVALID, "null argument");
+	if (!(control_rate > 0.0)) return fail(GTTS_ERR_INVALID, "control_rate must be positive");
+	*steps_out = controlSteps(internalRate(*voice), control_rate);
+	return GTTS_OK;
+}
+
+int gtts_output_length(const gtts_voice_config* voice, int32_t steps, int64_t n_frames,
+			int64_t* n_internal_out, int64_t* n_output_out)
+{
+	if (!voice) return fail(GTTS_ERR_INVALID, "null argument");
+	if (steps <= 0 || n_frames < 0) return fail(GTTS_ERR_INVALID, "steps must be > 0 and n_frames >= 0");
+	VoiceDev v;
+	if (const char* e = deriveVoice(*voice, v)) return fail(GTTS_ERR_INVALID, e);
+	if (!v.src_upsample) return fail(GTTS_ERR_UNSUPPORTED, "down-sampling SRC (internal rate above output rate) is not supported");
+	const int64_t nInternal = n_frames * steps;
+	if (n_internal_out) *n_internal_out = nInternal;
+	if (n_output_out) *n_output_out = outputLength(v, nInternal);
+	return GTTS_OK;
+}
+
+int gtts_shard_plan(const int64_t* cost, int64_t n_utt, int32_t n_shards, int32_t* shard_of)
+{
+	if (n_utt < 0 || n_shards <= 0 || (n_utt > 0 && (!cost || !shard_of))) return fail(GTTS_ERR_INVALID, "bad shard plan arguments");
+	shardPlan(cost, n_utt, n_shards, shard_of);
+	return GTTS_OK;
+}
+
+int gtts_probe_fir_taps(double* taps, int32_t cap, int32_t* n_taps_out)
+{
+	const std::vector<double> t = designGlottalFir();
+	if (n_taps_out) *n_taps_out = static_cast<int32_t>(t.size());
+	for (size_t i = 0; i < t.size() && static_cast<int32_t>(i) < cap; ++i) taps[i] = t[i];
+	return GTTS_OK;
+}
+
+int gtts_probe_src_tables(double* h3328, double* dh3328)
+{
+	if (!h3328 || !dh3328) return fail(GTTS_ERR_INVALID, "null argument");
+	buildSrcTables(h3328, dh3328);
+	return GTTS_OK;
+}
+
+int gtts_probe_voice_constants(const gtts_voice_config* voice, double* out, int32_t cap, int32_t* n_out)
+{
+	if (!voice || !out) return fail(GTTS_ERR_INVALID, "null argument");
+	VoiceDev v;
+	if (const char* e = deriveVoice(*voice, v)) return fail(GTTS_ERR_INVALID, e);
+	const double vals[] = {
+		(double) v.fs, v.breath, v.crossmix, v.damping, v.rad_m, v.refl_b0_m, v.refl_a1_m, v.rad_n, v.refl_b0_n,
+		v.refl_a1_n, v.throat_b0, v.throat_a1, v.throat_gain, v.nasal_k[1], v.nasal_k[2], v.nasal_k[3], v.nasal_k[4],
+		v.nasal_k[5], std::sqrt(v.ap2), std::sqrt(v.nr1_2), v.basic_inc, (double) v.div1, (double) v.div2, v.tn_delta,
+		(double) v.src_inc, (double) v.src_pad };
+	const int32_t n = static_cast<int32_t>(sizeof vals / sizeof vals[0]);
+	if (n_out) *n_out = n;
+	for (int32_t i = 0; i < n && i < cap; ++i) out[i] = vals[i];
+	return GTTS_OK;
+}
+
+int gtts_create(int32_t device, gtts_handle** handle_out)
+{
+	if (!handle_out) return fail(GTTS_ERR_INVALID, "null handle_out");
+	*handle_out = nullptr;
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess) return failCuda(e, "cudaGetDeviceCount");
+	if (count == 0) return fail(GTTS_ERR_NO_DEVICE, "no CUDA device");
+	if (device < 0 || device >= count) return fail(GTTS_ERR_INVALID, "device index out of range");
+	GTTS_CUDA(cudaSetDevice(device));
+	cudaDeviceProp prop;
+	GTTS_CUDA(cudaGetDeviceProperties(&prop, device));
+	if (prop.major != 10) {
+		return fail(GTTS_ERR_NO_DEVICE, std::string("device is sm_") + std::to_string(prop.major) + std::to_string(prop.minor) +
+				"; this library carries sm_100a code only");
+	}
+	gtts_handle* h = new (std::nothrow) gtts_handle;
+	if (!h) return fail(GTTS_ERR_NOMEM, "out of memory");
+	h->device = device;
+	h->sms = prop.multiProcessorCount;
+
+	// constants: FIR taps, LCG jump multipliers, SRC tables
+	const std::vector<double> taps = designGlottalFir();
+	if (taps.size() != kFirTaps) { delete h; return fail(GTTS_ERR_INVALID, "unexpected glottal FIR length"); }
+	double fir[kFirMaxTaps] = {0};
+	std::copy(taps.begin(), taps.end(), fir);
+	unsigned long long lcg[kBlock];
+	lcgMultipliers(lcg);
+	std::vector<double> hh(kSrcFilterLen), dh(kSrcFilterLen);
+	buildSrcTables(hh.data(), dh.data());
+	std::vector<double2> tab(kSrcFilterLen);
+	for (int i = 0; i < kSrcFilterLen; ++i) tab[i] = make_double2(hh[i], dh[i]);
+	cudaError_t ce;
+	if ((ce = cudaMemcpyToSymbol(c_fir, fir, sizeof fir)) != cudaSuccess ||
+	    (ce = cudaMemcpyToSymbol(c_lcg, lcg, sizeof lcg)) != cudaSuccess ||
+	    (ce = cudaMalloc(&h->d_src_tab, sizeof(double2) * kSrcFilterLen)) != cudaSuccess ||
+	    (ce = cudaMemcpy(h->d_src_tab, tab.data(), sizeof(double2) * kSrcFilterLen, cudaMemcpyHostToDevice)) != cudaSuccess ||
+	    (ce = cudaFuncSetAttribute(tube_kernel_v0<kWarpsPerCta>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                               (int) tube_smem_bytes(kWarpsPerCta))) != cudaSuccess) {
+		if (h->d_src_tab) cudaFree(h->d_src_tab);
+		delete h;
+		return failCuda(ce, "gtts_create: device setup");
+	}
+	char buf[512];
+	std::snprintf(buf, sizeof buf,
+			"{\"device\": %d, \"name\": \"%s\", \"sm\": \"%d.%d\", \"sms\": %d, \"kernel\": \"tube_kernel_v0\", "
+			"\"warps_per_cta\": %d, \"smem_per_cta\": %zu, \"utterances_per_warp\": 1}",
+			device, prop.name, prop.major, prop.minor, h->sms, kWarpsPerCta, tube_smem_bytes(kWarpsPerCta));
+	h->description = buf;
+	*handle_out = h;
+	return GTTS_OK;
+}
+
+void gtts_destroy(gtts_handle* h)
+{
+	if (!h) return;
+	cudaSetDevice(h->device);
+	if (h->d_src_tab) cudaFree(h->d_src_tab);
+	delete h;
+}
+
+const char* gtts_describe(gtts_handle* h) { return h ? h->description.c_str() : "{}"; }
+
+int gtts_probe_fp64_peak(gtts_handle* h, double* tflops_out)
+{
+	if (!h || !tflops_out) return fail(GTTS_ERR_INVALID, "null argument");
+	GTTS_CUDA(cudaSetDevice(h->device));
+	const int blocks = h->sms * 8, threads = 512, iters = 8192;
+	double* d = nullptr;
+	GTTS_CUDA(cudaMalloc(&d, sizeof(double) * blocks * threads));
+	cudaEvent_t e0, e1;
+	GTTS_CUDA(cudaEventCreate(&e0));
+	GTTS_CUDA(cudaEventCreate(&e1));
+	double best = 0.0;
+	for (int rep = 0; rep < 6; ++rep) {
+		GTTS_CUDA(cudaEventRecord(e0));
+		fp64_peak_kernel<<<blocks, threads>>>(d, iters, 1.0000001, 1e-9);
+		GTTS_CUDA(cudaEventRecord(e1));
+		GTTS_CUDA(cudaEventSynchronize(e1));
+		float ms = 0.f;
+		GTTS_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+		const double tf = 2.0 * 8 * iters * (double) blocks * threads / (ms * 1e-3) * 1e-12;
+		if (rep >= 2 && tf > best) best = tf;
+	}
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	cudaFree(d);
+	*tflops_out = best;
+	return GTTS_OK;
+}
+
+int gtts_batch_prepare(gtts_handle* h, const gtts_voice_config* voices, int32_t n_voices,
+			const int32_t* voice_index, double control_rate, const int32_t* steps_override,
+			const int64_t* frame_offsets, int64_t n_utt, gtts_batch** batch_out)
+{
+	if (!h || !batch_out) return fail(GTTS_ERR_INVALID, "null argument");
+	*batch_out = nullptr;
+	if (n_utt > std::numeric_limits<int32_t>::max()) return fail(GTTS_ERR_INVALID, "too many utterances");
+	gtts_batch* b = new (std::nothrow) gtts_batch;
+	if (!b) return fail(GTTS_ERR_NOMEM, "out of memory");
+	b->h = h;
+	int err = GTTS_OK;
+	const std::string msg = planBatch(voices, n_voices, voice_index, control_rate, steps_override, frame_offsets, n_utt, b->plan, &err);
+	if (err != GTTS_OK) { delete b; return fail(err, msg); }
+	const int rc = uploadPlan(b);
+	if (rc != GTTS_OK) { gtts_batch_free(b); return rc; }
+	*batch_out = b;
+	return GTTS_OK;
+}
+
+int gtts_batch_layout(const gtts_batch* b, int64_t* out_offsets, int64_t* n_internal)
+{
+	if (!b) return fail(GTTS_ERR_INVALID, "null batch");
+	if (out_offsets) std::copy(b->plan.out_offsets.begin(), b->plan.out_offsets.end(), out_offsets);
+	if (n_internal) for (size_t u = 0; u < b->plan.utts.size(); ++u) n_internal[u] = b->plan.utts[u].n_internal;
+	return GTTS_OK;
+}
+
+int gtts_batch_run_device(gtts_batch* b, const float* d_frames, float* d_out, void* cuda_stream)
+{
+	if (!b) return fail(GTTS_ERR_INVALID, "null batch");
+	if (!b->plan.utts.empty() && (!d_out || (b->plan.n_frames_total > 0 && !d_frames))) return fail(GTTS_ERR_INVALID, "null device buffer");
+	return launchBatch(b, d_frames, d_out, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int gtts_batch_run_host(gtts_batch* b, const float* h_frames, float* h_out)
+{
+	if (!b) return fail(GTTS_ERR_INVALID, "null batch");
+	const int64_t nFrames = b->plan.n_frames_total;
+	const int64_t nOut = b->plan.out_offsets.empty() ? 0 : b->plan.out_offsets.back();
+	if ((nFrames > 0 && !h_frames) || (nOut > 0 && !h_out)) return fail(GTTS_ERR_INVALID, "null host buffer");
+	GTTS_CUDA(cudaSetDevice(b->h->device));
+	if (!b->stream) GTTS_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+	if (nFrames > b->cap_frames) {
+		if (b->d_frames) cudaFree(b->d_frames);
+		b->d_frames = nullptr; b->cap_frames = 0;
+		GTTS_CUDA(cudaMalloc(&b->d_frames, sizeof(float) * kNumParams * nFrames));
+		b->cap_frames = nFrames;
+	}
+	if (nOut > b->cap_out) {
+		if (b->d_out) cudaFree(b->d_out);
+		b->d_out = nullptr; b->cap_out = 0;
+		GTTS_CUDA(cudaMalloc(&b->d_out, sizeof(float) * nOut));
+		b->cap_out = nOut;
+	}
+	if (nFrames > 0) GTTS_CUDA(cudaMemcpyAsync(b->d_frames, h_frames, sizeof(float) * kNumParams * nFrames, cudaMemcpyHostToDevice, b->stream));
+	const int rc = launchBatch(b, b->d_frames, b->d_out, b->stream);
+	if (rc != GTTS_OK) return rc;
+	if (nOut > 0) GTTS_CUDA(cudaMemcpyAsync(h_out, b->d_out, sizeof(float) * nOut, cudaMemcpyDeviceToHost, b->stream));
+	GTTS_CUDA(cudaStreamSynchronize(b->stream));
+	return GTTS_OK;
+}
+
+int gtts_batch_last_launches(const gtts_batch* b, int32_t* n_out)
+{
+	if (!b || !n_out) return fail(GTTS_ERR_INVALID, "null argument");
+	*n_out = b->last_launches;
+	return GTTS_OK;
+}
+
+void gtts_batch_free(gtts_batch* b)
+{
+	if (!b) return;
+	cudaSetDevice(b->h->device);
+	if (b->stream) { cudaStreamSynchronize(b->stream); cudaStreamDestroy(b->stream); }
+	cudaFree(b->d_voices); cudaFree(b->d_utts); cudaFree(b->d_order); cudaFree(b->d_queue);
+	cudaFree(b->d_states); cudaFree(b->d_frames); cudaFree(b->d_out);
+	delete b;
+}
+
+int gtts_batch_synthesize(gtts_handle* h, const gtts_voice_config* voices, int32_t n_voices,
+			const int32_t* voice_index, double control_rate, const float* frames,
+			const int64_t* frame_offsets, int64_t n_utt, float* out, int64_t out_capacity,
+			int64_t* out_offsets)
+{
+	gtts_batch* b = nullptr;
+	int rc = gtts_batch_prepare(h, voices, n_voices, voice_index, control_rate, nullptr, frame_offsets, n_utt, &b);
+	if (rc != GTTS_OK) return rc;
+	if (out_offsets) std::copy(b->plan.out_offsets.begin(), b->plan.out_offsets.end(), out_offsets);
+	if (b->plan.out_offsets.back() > out_capacity) {
+		gtts_batch_free(b);
+		return fail(GTTS_ERR_INVALID, "output buffer too small");
+	}
+	rc = gtts_batch_run_host(b, frames, out);
+	gtts_batch_free(b);
+	return rc;
+}
+
+// ---- streaming ----------------------------------------------------------------------------------------
+
+int gtts_stream_open(gtts_handle* h, const gtts_voice_config* voice, double control_rate,
+			int32_t steps_override, gtts_stream** stream_out)
+{
+	if (!h || !voice || !stream_out) return fail(GTTS_ERR_INVALID, "null argument");
+	*stream_out = nullptr;
+	gtts_stream* s = new (std::nothrow) gtts_stream;
+	if (!s) return fail(GTTS_ERR_NOMEM, "out of memory");
+	s->h = h;
+	s->voice = *voice;
+	// a one-utterance batch whose descriptor is rewritten for every chunk
+	const int64_t fo[2] = {0, 0};
+	const int32_t so[1] = {steps_override};
+	int rc = gtts_batch_prepare(h, voice, 1, nullptr, control_rate, steps_override > 0 ? so : nullptr, fo, 1, &s->batch);
+	if (rc != GTTS_OK) { delete s; return rc; }
+	s->vdev = s->batch->plan.voices[0];
+	s->steps = s->batch->plan.utts[0].steps;
+	cudaError_t e = cudaMalloc(&s->batch->d_states, sizeof(UttState));
+	if (e == cudaSuccess) e = cudaMemset(s->batch->d_states, 0, sizeof(UttState));
+	if (e != cudaSuccess) { gtts_batch_free(s->batch); delete s; return failCuda(e, "gtts_stream_open"); }
+	*stream_out = s;
+	return GTTS_OK;
+}
+
+namespace {
+
+// Runs `periods` control periods over the first `periods` (+1 if lookahead) pending frames.
+int streamChunk(gtts_stream* s, int64_t periods, bool lookahead, bool flush, float* out, int64_t cap, int64_t* written)
+{
+	gtts_batch* b = s->batch;
+	UttDesc& d = b->plan.utts[0];
+	const int64_t nInAfter = s->n_in_done + periods * s->steps;
+	int64_t kAfter;
+	if (flush) {
+		kAfter = outputLength(s->vdev, nInAfter);
+	} else {
+		kAfter = static_cast<int64_t>(((static_cast<unsigned __int128>(nInAfter) << 16) + s->vdev.src_inc - 1) / s->vdev.src_inc);
+		// nothing is final before the first input exists
+		if (nInAfter == 0) kAfter = 0;
+	}
+	const int64_t produced = kAfter - s->n_out_done;
+	if (produced > cap) return fail(GTTS_ERR_INVALID, "stream output buffer too small");
+	d.frame_begin = 0;
+	d.n_frames = periods;
+	d.n_internal = periods * s->steps;
+	d.out_begin = -s->n_out_done;            // the kernel indexes outputs absolutely
+	d.n_out = flush ? kAfter : std::numeric_limits<int64_t>::max() / 4;
+	d.flags = 1 | (flush ? 0 : 2) | (lookahead ? 4 : 0);
+	d.state_index = 0;
+	const int64_t nFrames = periods + (lookahead ? 1 : 0);
+	GTTS_CUDA(cudaSetDevice(s->h->device));
+	if (!b->stream) GTTS_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+	if (nFrames > b->cap_frames) {
+		if (b->d_frames) cudaFree(b->d_frames);
+		b->d_frames = nullptr; b->cap_frames = 0;
+		const int64_t want = std::max<int64_t>(nFrames, 64);
+		GTTS_CUDA(cudaMalloc(&b->d_frames, sizeof(float) * kNumParams * want));
+		b->cap_frames = want;
+	}
+	if (produced > b->cap_out) {
+		if (b->d_out) cudaFree(b->d_out);
+		b->d_out = nullptr; b->cap_out = 0;
+		const int64_t want = std::max<int64_t>(produced, 16384);
+		GTTS_CUDA(cudaMalloc(&b->d_out, sizeof(float) * want));
+		b->cap_out = want;
+	}
+	GTTS_CUDA(cudaMemcpyAsync(b->d_utts, &d, sizeof d, cudaMemcpyHostToDevice, b->stream));
+	if (nFrames > 0) GTTS_CUDA(cudaMemcpyAsync(b->d_frames, s->pending.data(), sizeof(float) * kNumParams * nFrames, cudaMemcpyHostToDevice, b->stream));
+	const int rc = launchBatch(b, b->d_frames, b->d_out, b->stream);
+	if (rc != GTTS_OK) return rc;
+	if (produced > 0) GTTS_CUDA(cudaMemcpyAsync(out, b->d_out, sizeof(float) * produced, cudaMemcpyDeviceToHost, b->stream));
+	GTTS_CUDA(cudaStreamSynchronize(b->stream));
+	s->n_in_done = nInAfter;
+	s->n_out_done = kAfter;
+	if (written) *written = produced;
+	return GTTS_OK;
+}
+
+} // namespace
+
+int gtts_stream_push_frames(gtts_stream* s, const float* frames, int64_t n_frames,
+			float* out, int64_t out_capacity, int64_t* n_written)
+{
+	if (!s || (n_frames > 0 && !frames)) return fail(GTTS_ERR_INVALID, "null argument");
+	if (s->finished) return fail(GTTS_ERR_INVALID, "stream already finished; call gtts_stream_reset");
+	if (n_written) *n_written = 0;
+	if (n_frames <= 0) return GTTS_OK;
+	s->pending.insert(s->pending.end(), frames, frames + n_frames * kNumParams);
+	const int64_t have = static_cast<int64_t>(s->pending.size()) / kNumParams;
+	if (have < 2) return GTTS_OK;
+	const int rc = streamChunk(s, have - 1, true, false, out, out_capacity, n_written);
+	if (rc != GTTS_OK) return rc;
+	s->pending.erase(s->pending.begin(), s->pending.begin() + (have - 1) * kNumParams);
+	return GTTS_OK;
+}
+
+int gtts_stream_finish(gtts_stream* s, float* out, int64_t out_capacity, int64_t* n_written)
+{
+	if (!s) return fail(GTTS_ERR_INVALID, "null argument");
+	if (s->finished) return fail(GTTS_ERR_INVALID, "stream already finished; call gtts_stream_reset");
+	if (n_written) *n_written = 0;
+	const int64_t have = static_cast<int64_t>(s->pending.size()) / kNumParams;
+	const int rc = streamChunk(s, have, false, true, out, out_capacity, n_written);
+	if (rc != GTTS_OK) return rc;
+	s->pending.clear();
+	s->finished = true;
+	return GTTS_OK;
+}
+
+int gtts_stream_reset(gtts_stream* s)
+{
+	if (!s) return fail(GTTS_ERR_INVALID, "null argument");
+	GTTS_CUDA(cudaSetDevice(s->h->device));
+	GTTS_CUDA(cudaMemset(s->batch->d_states, 0, sizeof(UttState)));
+	s->pending.clear();
+	s->n_in_done = 0;
+	s->n_out_done = 0;
+	s->finished = false;
+	return GTTS_OK;
+}
+
+void gtts_stream_close(gtts_stream* s)
+{
+	if (!s) return;
+	gtts_batch_free(s->batch);
+	delete s;
+}
+
+} // extern "C"

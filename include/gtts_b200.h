@@ -107,6 +107,10 @@ void gtts_destroy(gtts_handle* handle);
 /* Device and kernel facts for logs (SM count, kernel variant, shared memory per CTA ...), JSON text. */
 const char* gtts_describe(gtts_handle* handle);
 
+/* Measures this GPU's FP64 FMA-pipe peak (TFLOP/s) with a register-resident DFMA kernel (~30 ms):
+ * the roofline denominator of this path (MEASURED_PEAKS.json only carries HBM and bf16 figures). */
+int gtts_probe_fp64_peak(gtts_handle* handle, double* tflops_out);
+
 /* Plans a batch of n_utt utterances.
  *   voices[n_voices]        voice table; voice_index[u] selects one (NULL: every utterance uses voices[0])
  *   control_rate            Hz (1000 / control_period of vtm_control_model.txt); steps = rint(fs_int/rate)

@@ -42,7 +42,7 @@ def voice_struct(voice):
 
 def config_text(voice, model=0):
     """key = value text in the reference's ConfigurationData format (ConfigurationData.cpp:67-118)."""
-    lines = ["model = %d" % model]
+    lines = ["model = %d" % model, "log_parameters = false"]   # log_parameters: read by models 2/3/5 only
     for k, t in VOICE_KEYS_SCALAR:
         lines.append("%s = %s" % (k, repr(float(voice[k])) if t is float else int(voice[k])))
     for i in range(5):
@@ -100,8 +100,6 @@ class Oracle:
         m = self.lib.oracle_create(C.byref(vs))
         try:
             self.lib.oracle_run_track(m, control_rate, frames.ctypes.data, frames.shape[0])
-            if frames.shape[0] == 0:
-                self.lib.oracle_finish(m)
             n = self.lib.oracle_output_size(m)
             out = np.ctypeslib.as_array(self.lib.oracle_output(m), shape=(max(n, 1),))[:n].copy()
             if return_internal:

@@ -76,10 +76,11 @@ std::unique_ptr<GS::VTM::VocalTractModel> makeModel(const char* configText)
 	return vtm;
 }
 
-// The loop of Controller::synthesize (Controller.cpp:277-313) on a packed float32 track.
+// The loop of Controller::synthesize (Controller.cpp:277-313) on a packed float32 track, followed by
+// finishSynthesis() as in Controller::synthesizeToFile/ToBuffer (Controller.cpp:231-234).
 void runTrack(GS::VTM::VocalTractModel& vtm, double controlRate, const float* frames, long nFrames, int nParam)
 {
-	if (nFrames <= 0) return;
+	if (nFrames <= 0) { vtm.finishSynthesis(); return; } // synthesize() returns early, finishSynthesis() still runs (Controller.cpp:232-233)
 	const unsigned int controlSteps = static_cast<unsigned int>(std::rint(vtm.internalSampleRate() / controlRate));
 	const float coef = 1.0f / controlSteps;
 	std::vector<float> cur(nParam), delta(nParam);

@@ -565,7 +565,7 @@ void oracle_step(oracle_model* m, const float* p)
 /* ---- vtm_control_model/Controller.cpp:277-313 ---- */
 void oracle_run_track(oracle_model* m, double control_rate, const float* frames, long n_frames)
 {
-	if (n_frames <= 0) return;
+	if (n_frames <= 0) { oracle_finish(m); return; }   /* Controller.cpp:232-233 */
 	const unsigned steps = (unsigned) rint((double) m->fs / control_rate);
 	const float coef = 1.0f / steps;
 	float cur[N_PARAM], delta[N_PARAM];
@@ -601,7 +601,6 @@ long oracle_synthesize(const oracle_voice* voice, double control_rate, const flo
 	oracle_model* m = oracle_create(voice);
 	if (!m) return -1;
 	oracle_run_track(m, control_rate, frames, n_frames);
-	if (n_frames <= 0) oracle_finish(m);
 	const long n = m->n_out;
 	if (out) memcpy(out, m->out, sizeof(float) * (n < cap ? n : cap));
 	oracle_destroy(m);

@@ -1,0 +1,68 @@
+// TEST INFRASTRUCTURE ONLY: runs the device source of the tube kernel under the SIMT emulator
+// (see simt_emu.h).  Built by tests/simt_emu/Makefile into tests/simt_emu/libemu_tube.so.
+#include "simt_emu.h"
+
+#define GTTS_EMU 1
+namespace gtts {
+double c_fir[64];
+unsigned long long c_lcg[32];
+}
+#include "../../gama_tts_b200/csrc/tube_kernel.cuh"
+#include "../../gama_tts_b200/csrc/batch_plan.h"
+
+namespace simt {
+Cta* g_cta = nullptr;
+void fiber_entry(int tid)
+{
+	g_cta->body(tid);
+	g_cta->fibers[tid].state = 2;
+}
+}
+
+static std::string g_err;
+
+extern "C" const char* emu_last_error() { return g_err.c_str(); }
+
+// Same planning code as the product host runtime, kernel body run CTA by CTA on fibers.
+extern "C" int emu_batch(const gtts_voice_config* voices, int n_voices, const int* voice_index, double control_rate,
+			const int* steps_override, const float* frames, const long long* frame_offsets, long long n_utt,
+			float* out, long long* out_offsets, int warps_per_cta, int n_ctas)
+{
+	using namespace gtts;
+	BatchPlan plan;
+	int err = 0;
+	g_err = planBatch(voices, n_voices, voice_index, control_rate, steps_override,
+			reinterpret_cast<const int64_t*>(frame_offsets), n_utt, plan, &err);
+	if (err) return err;
+	for (long long u = 0; u <= n_utt; ++u) out_offsets[u] = plan.out_offsets[u];
+	if (!out) return 0;
+
+	std::vector<double> taps = designGlottalFir();
+	std::memset(c_fir, 0, sizeof c_fir);
+	for (size_t i = 0; i < taps.size(); ++i) c_fir[i] = taps[i];
+	lcgMultipliers(c_lcg);
+	std::vector<double> h(kSrcFilterLen), dh(kSrcFilterLen);
+	buildSrcTables(h.data(), dh.data());
+	std::vector<double2> tab(kSrcFilterLen);
+	for (int i = 0; i < kSrcFilterLen; ++i) { tab[i].x = h[i]; tab[i].y = dh[i]; }
+
+	int queue = 0;
+	KernelParams P;
+	P.voices = plan.voices.data();
+	P.utts = plan.utts.data();
+	P.order = plan.order.data();
+	P.frames = frames;
+	P.out = out;
+	P.states = nullptr;
+	P.src_tab = tab.data();
+	P.queue = &queue;
+	P.n_utt = static_cast<int32_t>(n_utt);
+
+	const int nthreads = warps_per_cta * 32;
+	std::vector<unsigned char> smem(tube_smem_bytes(warps_per_cta) + 64);
+	unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem.data()) + 15) & ~uintptr_t(15));
+	for (int b = 0; b < n_ctas; ++b) {
+		simt::run_cta(nthreads, [&](int tid) { tube_cta_body(P, base, tid, nthreads); });
+	}
+	return 0;
+}

@@ -1,0 +1,65 @@
+"""The device source (gama_tts_b200/csrc/tube_kernel.cuh) compiled for the host under the SIMT emulator
+of tests/simt_emu, against the oracle.  This checks the kernel's blocking, ring indexing, lane roles
+and shuffles in the GPU-less container; the real parity gate is tests/test_gpu_parity.py on the B200.
+With -ffp-contract=off and pow() the emulated kernel follows the oracle's arithmetic exactly except for
+the analytic wavetable fall segment (voices with tn_min != tn_max)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import full_scale_error
+from gama_tts_b200 import pack_tracks
+from gama_tts_b200 import tracks as T
+from gama_tts_b200.capi import voice_array
+from gama_tts_b200.voices import default_voice, random_voice
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def emu():
+    subprocess.run(["make", "-s", "-C", os.path.join(HERE, "simt_emu")], check=True)
+    L = C.CDLL(os.path.join(HERE, "simt_emu", "libemu_tube.so"))
+    L.emu_last_error.restype = C.c_char_p
+    L.emu_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
+                            C.c_longlong, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+
+    def run(voices, vidx, tracks, warps=4, ctas=1, rate=250.0, steps=None):
+        va = voice_array(voices)
+        frames, fo = pack_tracks(tracks)
+        vi = np.ascontiguousarray(vidx, np.int32)
+        so = None if steps is None else np.ascontiguousarray(steps, np.int32)
+        oo = np.zeros(len(tracks) + 1, np.int64)
+        args = [va, len(voices), vi.ctypes.data, rate, None if so is None else so.ctypes.data, frames.ctypes.data,
+                fo.ctypes.data, len(tracks)]
+        assert L.emu_batch(*args, None, oo.ctypes.data, warps, ctas) == 0, L.emu_last_error()
+        out = np.zeros(int(oo[-1]), np.float32)
+        assert L.emu_batch(*args, out.ctypes.data, oo.ctypes.data, warps, ctas) == 0
+        return [out[oo[i]:oo[i + 1]] for i in range(len(tracks))]
+    return run
+
+
+def test_emulated_kernel_matches_oracle(emu, oracle, real_tracks):
+    rng = np.random.Generator(np.random.PCG64(5))
+    hello, shells = real_tracks[0], real_tracks[2]
+    voices = [default_voice("male"), default_voice("female"), default_voice("baby"), random_voice(rng), random_voice(rng)]
+    tracks = [hello[:90], shells[230:290], shells[640:690], T.synthetic_track(3, 50), shells[900:950], hello[:1], hello[:0]]
+    vidx = [0, 1, 2, 3, 4, 3, 0]
+    res = emu(voices, vidx, tracks, warps=4)
+    for vi, tr, out in zip(vidx, tracks, res):
+        ref = oracle.synthesize(voices[vi], tr)
+        assert len(out) == len(ref)
+        assert full_scale_error(out, ref) <= 1e-9
+        if voices[vi]["glottal_pulse_tn_min"] == voices[vi]["glottal_pulse_tn_max"]:
+            assert np.array_equal(out, ref)
+
+
+def test_emulated_kernel_steps_override(emu, oracle, real_tracks):
+    # steps = 1: every frame is one internal sample (what the plugin shim sends)
+    v = default_voice("male")
+    params = np.repeat(real_tracks[0][100:112], 9, axis=0)
+    out = emu([v], [0], [params], warps=1, steps=[1])[0]
+    assert np.array_equal(out, oracle.synthesize_samples(v, params))

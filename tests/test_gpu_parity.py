@@ -1,0 +1,163 @@
+"""The parity gate: the CUDA path (through the C ABI) against the oracle and the committed golden
+vectors of the unmodified reference.  Tolerance (north_star): max abs sample error <= 1e-6 of full
+scale, full scale being the reference's own 0.95-peak normalisation (VTMUtil.cpp:48-67)."""
+import numpy as np
+import pytest
+
+from conftest import full_scale_error, snr_db
+import gama_tts_b200 as g
+from gama_tts_b200 import tracks as T
+from gama_tts_b200.voices import default_voice, random_voice
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-6          # of full scale (north_star)
+TIGHT = 2e-7        # what we actually expect: the reference's own FMA on/off noise floor is 7e-8
+
+
+def test_golden_vectors(synth, golden):
+    for name in golden.names:
+        voice, track, ref, ref_nofma = golden.case(name)
+        out = synth.synthesize(voice, [track])[0]
+        assert len(out) == len(ref), name
+        err = full_scale_error(out, ref)
+        assert err <= TOL, (name, err)
+        assert err <= TIGHT, (name, err)
+        if len(ref) > 100 and np.abs(ref).max() > 0:
+            assert snr_db(out, ref) >= 100.0, name
+
+
+def test_vs_oracle_fresh_tracks_and_voices(synth, oracle):
+    rng = np.random.Generator(np.random.PCG64(2024))
+    voices = [default_voice(v) for v in ("male", "female", "large_child", "small_child", "baby")]
+    voices += [random_voice(rng) for _ in range(11)]
+    tracks = [T.synthetic_track(100 + i, int(rng.integers(20, 160))) for i in range(len(voices))]
+    outs = synth.synthesize(voices, tracks, voice_index=np.arange(len(voices)))
+    for v, tr, out in zip(voices, tracks, outs):
+        ref = oracle.synthesize(v, tr)
+        assert len(out) == len(ref)
+        assert full_scale_error(out, ref) <= TIGHT
+
+
+def test_ragged_batch_equals_singles(synth, real_tracks):
+    # batch == N x single, bitwise, whatever the batch composition and ordering
+    v = default_voice("male")
+    hello, fox = real_tracks[0], real_tracks[1]
+    tracks = [hello, fox[:1], fox[100:163], hello[:0], fox[400:640], hello[50:51], fox[:333]] * 3
+    batch = synth.synthesize(v, tracks)
+    for tr, out in zip(tracks, batch):
+        single = synth.synthesize(v, [tr])[0]
+        assert np.array_equal(out, single)
+    n_out = [g.output_length(v, len(t))[1] for t in tracks]
+    assert [len(o) for o in batch] == n_out
+
+
+def test_empty_and_tiny_inputs(synth, oracle):
+    v = default_voice("male")
+    assert synth.synthesize(v, []) == []
+    out = synth.synthesize(v, [np.zeros((0, 16), np.float32)])[0]
+    assert len(out) == 63 and not out.any()
+    one = T.synthetic_track(1, 1)
+    assert full_scale_error(synth.synthesize(v, [one])[0], oracle.synthesize(v, one)) <= TIGHT
+
+
+def test_edge_parameter_values(synth, oracle):
+    # silent glottis, zero radii (clamped to 0.01), velum 0 and 1.5, frication at both ends of the tract,
+    # tiny negative volumes as the real front end produces them
+    v = default_voice("male")
+    tr = np.tile(T.VOWEL_AA, (60, 1)).astype(np.float32)
+    tr[10:20, 1] = -6.7e-32
+    tr[20:30, 7:15] = 0.0
+    tr[30:40, 15] = 0.0
+    tr[40:50, 15] = 1.5
+    tr[5:25, 3] = 10.0
+    tr[5:15, 4] = 0.0
+    tr[15:25, 4] = 7.0
+    tr[25:35, 2] = 10.0
+    tr[45:55, 5] = 20000.0
+    tr[45:55, 6] = 20000.0
+    out = synth.synthesize(v, [tr])[0]
+    ref = oracle.synthesize(v, tr)
+    assert np.isfinite(out).all()
+    assert full_scale_error(out, ref) <= TIGHT
+
+
+def test_steps_override_per_sample_mode(synth, oracle, real_tracks):
+    # steps = 1: the plugin shim's mode, parameters used verbatim for one internal sample each
+    v = default_voice("male")
+    params = np.repeat(real_tracks[0][100:130], 11, axis=0)
+    out = synth.synthesize(v, [params], steps_override=[1])[0]
+    ref = oracle.synthesize_samples(v, params)
+    assert len(out) == len(ref) and full_scale_error(out, ref) <= TIGHT
+
+
+def test_control_rates(synth, oracle):
+    # control_period 1..4 ms (VTMControlModelConfiguration.cpp:37-41)
+    v = default_voice("female")
+    tr = T.synthetic_track(9, 50)
+    for period in (1, 2, 3, 4):
+        out = synth.synthesize(v, [tr], control_rate=1000.0 / period)[0]
+        ref = oracle.synthesize(v, tr, control_rate=1000.0 / period)
+        assert len(out) == len(ref) and full_scale_error(out, ref) <= TIGHT
+
+
+def test_streaming_equals_batch(synth, real_tracks):
+    v = default_voice("male")
+    track = real_tracks[3][:200]
+    whole = synth.synthesize(v, [track])[0]
+    st = synth.stream(v)
+    parts = []
+    rng = np.random.Generator(np.random.PCG64(4))
+    i = 0
+    while i < len(track):
+        n = int(rng.integers(1, 9))
+        parts.append(st.push(track[i:i + n]))
+        i += n
+    parts.append(st.finish())
+    streamed = np.concatenate(parts)
+    assert len(streamed) == len(whole)
+    assert np.array_equal(streamed, whole)
+    # frame-by-frame (BASELINE config 5 pattern) after a reset
+    st.reset()
+    parts = [st.push(track[i:i + 1]) for i in range(60)] + [st.finish()]
+    assert np.array_equal(np.concatenate(parts), synth.synthesize(v, [track[:60]])[0])
+    st.close()
+
+
+def test_rerun_is_deterministic(synth):
+    v = default_voice("male")
+    tracks = [T.synthetic_track(40 + i, 64) for i in range(20)]
+    a = synth.synthesize(v, tracks)
+    b = synth.synthesize(v, tracks)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+def test_device_buffer_entry_point(synth):
+    import torch
+    v = default_voice("male")
+    tracks = [T.synthetic_track(70 + i, 40) for i in range(9)]
+    frames, fo = g.pack_tracks(tracks)
+    b = synth.prepare(v, fo)
+    d_frames = torch.from_numpy(frames).cuda()
+    d_out = torch.zeros(b.n_out_total, dtype=torch.float32, device="cuda")
+    b.run_device(d_frames.data_ptr(), d_out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    host = b.run_host(frames)
+    assert np.array_equal(d_out.cpu().numpy(), host)
+    assert b.last_launches() == 1
+    b.close()
+
+
+@pytest.mark.slow
+def test_full_size_track_properties(synth, oracle):
+    # BASELINE config 2 shape (10 s tracks): one track checked sample by sample against the oracle,
+    # the rest through size-independent properties (exact length, finite, batch == single)
+    v = default_voice("male")
+    tracks = [T.synthetic_track(20240 + u, 2500) for u in range(24)]
+    outs = synth.synthesize(v, tracks)
+    assert all(len(o) == 479250 for o in outs)
+    assert all(np.isfinite(o).all() and np.abs(o).max() < 0.1 for o in outs)
+    ref = oracle.synthesize(v, tracks[5])
+    assert full_scale_error(outs[5], ref) <= TOL
+    assert snr_db(outs[5], ref) >= 100.0
+    assert np.array_equal(outs[7], synth.synthesize(v, [tracks[7]])[0])

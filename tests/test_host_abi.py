@@ -1,0 +1,121 @@
+"""CPU-side checks of the product library: it loads, exports every symbol include/gtts_b200.h declares,
+its host-only entry points agree with the oracle, and device entry points fail loudly without a GPU
+(no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import gama_tts_b200 as g
+from gama_tts_b200 import capi
+from gama_tts_b200 import tracks as T
+from gama_tts_b200.voices import default_voice, random_voice
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_all_exported(product_lib):
+    hdr = open(os.path.join(ROOT, "include", "gtts_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(gtts_[a-z0-9_]+)\s*\(", hdr)))
+    assert declared and set(declared) == set(capi.EXPORTS)
+    for name in declared:
+        assert hasattr(product_lib, name), name
+    assert product_lib.gtts_abi_version() == 1
+
+
+def test_voice_struct_layout_matches_header():
+    # 2 int32 + 17 doubles + 5 + 8 doubles
+    assert C.sizeof(capi.VoiceConfig) == 8 + 8 + 8 * (16 + 5 + 8) + 0 or C.sizeof(capi.VoiceConfig) == 8 * (1 + 1 + 16 + 5 + 8)
+
+
+def test_internal_rate_and_steps(product_lib):
+    for var, fs, steps in (("male", 20034, 80), ("female", 23373, 93), ("large_child", 28047, 112),
+                           ("small_child", 35059, 140), ("baby", 46746, 187)):
+        v = default_voice(var)
+        assert g.internal_rate(v) == fs
+        assert g.control_steps(v, 250.0) == steps
+
+
+def test_output_length_matches_oracle(product_lib, oracle):
+    rng = np.random.Generator(np.random.PCG64(3))
+    v = default_voice("male")
+    assert g.output_length(v, 2500) == (200000, 479250)
+    assert g.output_length(v, 250) == (20000, 47981)
+    assert g.output_length(v, 0) == (0, 63)
+    for i in range(6):
+        voice = random_voice(rng)
+        n_frames = int(rng.integers(0, 40))
+        ni, no = g.output_length(voice, n_frames)
+        out = oracle.synthesize(voice, T.synthetic_track(i, n_frames))
+        assert no == len(out) and ni == n_frames * g.control_steps(voice)
+
+
+def test_host_tables_match_oracle(product_lib, oracle, golden):
+    taps = np.zeros(64)
+    n = C.c_int32()
+    capi.check(product_lib.gtts_probe_fir_taps(taps.ctypes.data, 64, C.byref(n)))
+    assert n.value == 49 and np.array_equal(taps[:49], oracle.fir_taps())
+    assert np.array_equal(taps[:49], golden.kat("fir_taps"))
+    h, dh = np.zeros(3328), np.zeros(3328)
+    capi.check(product_lib.gtts_probe_src_tables(h.ctypes.data, dh.ctypes.data))
+    oh, odh = oracle.src_tables()
+    assert np.array_equal(h, oh) and np.array_equal(dh, odh)
+
+
+def test_voice_constants_match_reference_kat(product_lib, golden):
+    for var in ("male", "female", "large_child", "small_child", "baby"):
+        v = capi.voice_config(default_voice(var))
+        out = np.zeros(32)
+        n = C.c_int32()
+        capi.check(product_lib.gtts_probe_voice_constants(C.byref(v), out.ctypes.data, 32, C.byref(n)))
+        ref = golden.kat("constants_" + var)       # 24 values from the reference's private members
+        assert np.allclose(out[:24], ref, rtol=1e-15, atol=0)
+        assert np.array_equal(out[:18], ref[:18])
+
+
+def test_shard_plan_balanced(product_lib):
+    rng = np.random.Generator(np.random.PCG64(7))
+    cost = np.exp(rng.uniform(np.log(250), np.log(5000), 4096)).astype(np.int64)
+    for shards in (1, 2, 4, 8):
+        s = g.shard_plan(cost, shards)
+        assert s.min() == 0 and s.max() == shards - 1
+        loads = np.bincount(s, weights=cost, minlength=shards)
+        assert loads.max() / loads.mean() < 1.01
+    assert len(g.shard_plan(np.zeros(0, np.int64), 4)) == 0
+
+
+def test_invalid_arguments_are_reported(product_lib):
+    v = default_voice("male")
+    with pytest.raises(capi.GttsError) as e:
+        g.output_length(v, 10, steps=0)
+    assert e.value.code == capi.GTTS_ERR_INVALID
+    short = dict(v, vocal_tract_length=6.0)           # fs_int > 48 kHz: down-sampling branch
+    with pytest.raises(capi.GttsError) as e:
+        g.output_length(short, 10)
+    assert e.value.code == capi.GTTS_ERR_UNSUPPORTED
+
+
+def test_no_cpu_fallback_without_gpu(product_lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(capi.GttsError) as e:
+        g.TubeSynthesizer(0)
+    assert e.value.code in (capi.GTTS_ERR_NO_DEVICE, capi.GTTS_ERR_CUDA)
+
+
+def test_product_does_not_reference_the_oracle():
+    # The product tree must not import, link or execute anything under oracle/ (or the test emulator).
+    bad = []
+    for base in ("gama_tts_b200", "include"):
+        for dp, _, files in os.walk(os.path.join(ROOT, base)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", "Makefile")):
+                    text = open(os.path.join(dp, f), errors="replace").read()
+                    if re.search(r"oracle/|pyoracle|liboracle|libgtts_ref|simt_emu\.h", text):
+                        bad.append(os.path.join(dp, f))
+    # tube_kernel.cuh only *mentions* the emulator in a comment; it must not include it
+    bad = [b for b in bad if not b.endswith("tube_kernel.cuh")]
+    assert not bad, bad
