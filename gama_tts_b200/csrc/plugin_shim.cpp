@@ -1,0 +1,193 @@
+// Plugin shim: makes the B200 tube path a drop-in GS::VTM::VocalTractModel for the UNMODIFIED
+// reference through its own plugin seam.
+//
+//   reference side (not rebuilt here)                      this file
+//   ---------------------------------                      ---------
+//   vtm.txt: model = 2000, dll_path = .../libgtts_plugin.so
+//   VocalTractModel::getInstance case 2000                 (gama_tts/src/vtm/VocalTractModel.cpp:53-54)
+//   VocalTractModelPlugin: dlopen + dlsym of               (gama_tts/src/vtm/VocalTractModelPlugin.cpp:57-91)
+//     GAMA_TTS_construct_vocal_tract_model(const void* config_data, int is_interactive)   -> exported below
+//     GAMA_TTS_destruct_vocal_tract_model(void* vtm)                                       -> exported below
+//   every virtual forwarded to the returned object         (VocalTractModelPlugin.cpp:104-150)
+//
+// The returned object is used through the Itanium vtable of GS::VTM::VocalTractModel
+// (gama_tts/src/vtm/VocalTractModel.h:43-71) and receives a GS::ConfigurationData, so this one file is
+// compiled against the reference headers where they lie (-I$(REF)/gama_tts/src{,/vtm}, plus the
+// reference's ConfigurationData.cpp for the non-inline convertString<> specialisations) with the same
+// g++ / libstdc++ as the host binary.  Nothing of the reference is copied.  Everything below the seam
+// goes through the C ABI of include/gtts_b200.h.
+//
+// Call pattern honoured (Controller.cpp:231-234, 277-313):
+//   [reset] -> (setAllParameters -> execSynthesisStep) x N -> finishSynthesis -> outputBuffer()
+// execSynthesisStep() records the 16 float parameters of that internal sample; finishSynthesis() runs
+// the whole recording as ONE utterance with steps = 1 (every recorded row is used verbatim for one
+// internal sample, so the host's own float32 interpolation is reproduced exactly) and fills the
+// output buffer.  Interactive callers (the editor drains outputBuffer() after every step, SURVEY.md
+// section 3.5) are not served: construction with is_interactive != 0 returns NULL, which the host
+// reports as "Could not construct the vocal tract model" (VocalTractModelPlugin.cpp:88-90).
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "ConfigurationData.h"
+#include "VocalTractModel.h"
+
+#include "../../include/gtts_b200.h"
+
+namespace {
+
+class B200VocalTractModel final : public GS::VTM::VocalTractModel {
+public:
+	B200VocalTractModel(const GS::ConfigurationData& data, int device);
+	~B200VocalTractModel() noexcept override;
+
+	void reset() noexcept override;
+	double internalSampleRate() const noexcept override { return internalRate_; }
+	double outputSampleRate() const noexcept override { return voice_.output_rate; }
+	void setParameter(int parameter, float value) noexcept override;
+	void setAllParameters(const std::vector<float>& parameters) noexcept override;
+	void execSynthesisStep() noexcept override;
+	void finishSynthesis() noexcept override;
+	std::vector<float>& outputBuffer() noexcept override { return outputBuffer_; }
+
+private:
+	gtts_voice_config voice_;
+	gtts_handle* handle_ = nullptr;
+	int32_t internalRate_ = 0;
+	float current_[GTTS_NUM_PARAMS];
+	std::vector<float> recorded_;          // one row of 16 per execSynthesisStep()
+	std::vector<float> outputBuffer_;
+};
+
+// Same keys, same order as VocalTractModel0::loadConfiguration (VocalTractModel0.h:266-305).
+B200VocalTractModel::B200VocalTractModel(const GS::ConfigurationData& data, int device)
+{
+	std::memset(&voice_, 0, sizeof voice_);
+	std::memset(current_, 0, sizeof current_);
+	voice_.output_rate = data.value<double>("output_rate");
+	voice_.waveform = data.value<int>("waveform");
+	voice_.glottal_pulse_tp = data.value<double>("glottal_pulse_tp");
+	voice_.glottal_pulse_tn_min = data.value<double>("glottal_pulse_tn_min");
+	voice_.glottal_pulse_tn_max = data.value<double>("glottal_pulse_tn_max");
+	voice_.breathiness = data.value<double>("breathiness");
+	voice_.vocal_tract_length_offset = data.value<double>("vocal_tract_length_offset");
+	voice_.vocal_tract_length = data.value<double>("vocal_tract_length");
+	voice_.temperature = data.value<double>("temperature");
+	voice_.loss_factor = data.value<double>("loss_factor");
+	voice_.mouth_coefficient = data.value<double>("mouth_coefficient");
+	voice_.nose_coefficient = data.value<double>("nose_coefficient");
+	voice_.throat_cutoff = data.value<double>("throat_cutoff");
+	voice_.throat_volume = data.value<double>("throat_volume");
+	voice_.noise_modulation = data.value<int>("noise_modulation");
+	voice_.mix_offset = data.value<double>("mix_offset");
+	voice_.global_radius_coef = data.value<double>("global_radius_coef");
+	voice_.global_nasal_radius_coef = data.value<double>("global_nasal_radius_coef");
+	voice_.aperture_radius = data.value<double>("aperture_radius");
+	for (int i = 0; i < 5; ++i) voice_.nasal_radius[i] = data.value<double>("nasal_radius_" + std::to_string(i + 1));
+	for (int i = 0; i < 8; ++i) voice_.radius_coef[i] = data.value<double>("radius_" + std::to_string(i + 1) + "_coef");
+
+	if (gtts_voice_internal_rate(&voice_, &internalRate_) != GTTS_OK) throw std::runtime_error(gtts_last_error());
+	int64_t nInternal = 0, nOut = 0;
+	if (gtts_output_length(&voice_, 1, 0, &nInternal, &nOut) != GTTS_OK) throw std::runtime_error(gtts_last_error());
+	if (gtts_create(device, &handle_) != GTTS_OK) throw std::runtime_error(gtts_last_error());
+	outputBuffer_.reserve(OUTPUT_BUFFER_RESERVE);
+}
+
+B200VocalTractModel::~B200VocalTractModel() noexcept
+{
+	gtts_destroy(handle_);
+}
+
+// VocalTractModel0::reset (VocalTractModel0.h:309-326): all dynamic state back to zero, output cleared;
+// like the reference, the current parameters are kept.
+void B200VocalTractModel::reset() noexcept
+{
+	recorded_.clear();
+	outputBuffer_.clear();
+}
+
+// VocalTractModel0.h:665-694: an invalid index is ignored silently.  The radius scaling
+// (max(r * radiusCoef, 0.01)) is applied on the device from the raw float.
+void B200VocalTractModel::setParameter(int parameter, float value) noexcept
+{
+	if (parameter < 0 || parameter >= GTTS_NUM_PARAMS) return;
+	current_[parameter] = value;
+}
+
+// VocalTractModel0.h:698-716: a vector of the wrong size is ignored silently.
+void B200VocalTractModel::setAllParameters(const std::vector<float>& parameters) noexcept
+{
+	if (parameters.size() != GTTS_NUM_PARAMS) return;
+	std::memcpy(current_, parameters.data(), sizeof current_);
+}
+
+void B200VocalTractModel::execSynthesisStep() noexcept
+{
+	try {
+		recorded_.insert(recorded_.end(), current_, current_ + GTTS_NUM_PARAMS);
+	} catch (...) {
+		std::fprintf(stderr, "[gtts_plugin] out of memory while recording parameters\n");
+	}
+}
+
+// VocalTractModel0.h:720-723 (SRC flush) -- here: the deferred synthesis of everything recorded.
+void B200VocalTractModel::finishSynthesis() noexcept
+{
+	try {
+		const int64_t nSamples = static_cast<int64_t>(recorded_.size() / GTTS_NUM_PARAMS);
+		const int64_t frameOffsets[2] = {0, nSamples};
+		const int32_t steps[1] = {1};
+		gtts_batch* batch = nullptr;
+		if (gtts_batch_prepare(handle_, &voice_, 1, nullptr, 250.0, steps, frameOffsets, 1, &batch) != GTTS_OK) {
+			std::fprintf(stderr, "[gtts_plugin] %s\n", gtts_last_error());
+			return;
+		}
+		int64_t outOffsets[2] = {0, 0};
+		gtts_batch_layout(batch, outOffsets, nullptr);
+		const size_t base = outputBuffer_.size();
+		outputBuffer_.resize(base + static_cast<size_t>(outOffsets[1]));
+		if (gtts_batch_run_host(batch, recorded_.data(), outputBuffer_.data() + base) != GTTS_OK) {
+			std::fprintf(stderr, "[gtts_plugin] %s\n", gtts_last_error());
+			outputBuffer_.resize(base);
+		}
+		gtts_batch_free(batch);
+		recorded_.clear();
+	} catch (...) {
+		std::fprintf(stderr, "[gtts_plugin] finishSynthesis failed\n");
+	}
+}
+
+} // namespace
+
+extern "C" {
+
+// Replaces nothing in the reference: these are the two symbols VocalTractModelPlugin looks up
+// (gama_tts/src/vtm/VocalTractModelPlugin.cpp:37-38, 77, 82).
+void* GAMA_TTS_construct_vocal_tract_model(const void* config_data, int is_interactive)
+{
+	if (!config_data || is_interactive) {
+		if (is_interactive) std::fprintf(stderr, "[gtts_plugin] interactive mode is not supported by the batched GPU model\n");
+		return nullptr;
+	}
+	try {
+		const char* dev = std::getenv("GTTS_DEVICE");
+		const GS::ConfigurationData& data = *static_cast<const GS::ConfigurationData*>(config_data);
+		GS::VTM::VocalTractModel* vtm = new B200VocalTractModel(data, dev ? std::atoi(dev) : 0);
+		return vtm;
+	} catch (const std::exception& e) {
+		std::fprintf(stderr, "[gtts_plugin] %s\n", e.what());
+		return nullptr;
+	} catch (...) {
+		return nullptr;
+	}
+}
+
+void GAMA_TTS_destruct_vocal_tract_model(void* vtm)
+{
+	delete static_cast<GS::VTM::VocalTractModel*>(vtm);
+}
+
+} // extern "C"

@@ -40,9 +40,11 @@ def voice_struct(voice):
     return s
 
 
-def config_text(voice, model=0):
+def config_text(voice, model=0, extra=None):
     """key = value text in the reference's ConfigurationData format (ConfigurationData.cpp:67-118)."""
     lines = ["model = %d" % model, "log_parameters = false"]   # log_parameters: read by models 2/3/5 only
+    for k, v in (extra or {}).items():
+        lines.append("%s = %s" % (k, v))
     for k, t in VOICE_KEYS_SCALAR:
         lines.append("%s = %s" % (k, repr(float(voice[k])) if t is float else int(voice[k])))
     for i in range(5):
@@ -207,10 +209,11 @@ class Reference:
         self.lib.ref_free(p)
         return out
 
-    def synthesize(self, voice, frames, control_rate=250.0, model=0):
+    def synthesize(self, voice, frames, control_rate=250.0, model=0, extra=None):
+        """extra: additional config keys, e.g. {"dll_path": ...} with model=2000 (the plugin seam)."""
         frames = _f32(frames).reshape(-1, 16)
         p, n, rate = C.POINTER(C.c_float)(), C.c_long(), C.c_double()
-        rc = self.lib.ref_synthesize(config_text(voice, model), control_rate, frames.ctypes.data, frames.shape[0],
+        rc = self.lib.ref_synthesize(config_text(voice, model, extra), control_rate, frames.ctypes.data, frames.shape[0],
                                      C.byref(p), C.byref(n), C.byref(rate))
         if rc:
             raise RuntimeError(self.lib.ref_last_error().decode())

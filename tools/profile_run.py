@@ -1,0 +1,45 @@
+#!/usr/bin/env python
+"""Small, fixed workload for ncu: `python tools/profile_run.py [--utts U] [--frames F] [--reps R]`.
+Runs the batch R times on device-resident buffers and prints the CUDA-event time per launch."""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--utts", type=int, default=1024)
+    ap.add_argument("--frames", type=int, default=100)
+    ap.add_argument("--reps", type=int, default=3)
+    args = ap.parse_args()
+    import torch
+    import gama_tts_b200 as g
+    from gama_tts_b200 import tracks as T
+    from gama_tts_b200.voices import default_voice
+    base = [T.synthetic_track(20240 + u, args.frames) for u in range(min(args.utts, 64))]
+    frames = np.concatenate([base[u % len(base)] for u in range(args.utts)])
+    fo = np.arange(args.utts + 1, dtype=np.int64) * args.frames
+    synth = g.TubeSynthesizer(0)
+    b = synth.prepare(default_voice("male"), fo)
+    d_frames = torch.from_numpy(frames).cuda()
+    d_out = torch.zeros(b.n_out_total, dtype=torch.float32, device="cuda")
+    s = torch.cuda.current_stream()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for r in range(args.reps):
+        e0.record(s)
+        b.run_device(d_frames.data_ptr(), d_out.data_ptr(), s.cuda_stream)
+        e1.record(s)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        print("launch %d: %.3f ms  (%.1f ns per internal sample per utterance, %.0f audio-s/s)" %
+              (r, ms, ms * 1e6 / (args.frames * 80), b.n_out_total / 48000.0 / (ms * 1e-3)))
+    print("checksum", float(d_out[::997].double().abs().sum()))
+
+
+if __name__ == "__main__":
+    main()
