@@ -13,6 +13,8 @@
 
 namespace gtts {
 
+static constexpr double kPiTable = 3.14159265358979323846;
+
 namespace {
 
 constexpr double kPi = 3.14159265358979323846;
@@ -245,6 +247,33 @@ void shardPlan(const int64_t* cost, int64_t n, int shards, int32_t* shardOf)
 		for (int s = 1; s < shards; ++s) if (load[s] < load[best]) best = s;
 		shardOf[u] = best;
 		load[best] += cost[u];
+	}
+}
+
+} // namespace gtts
+
+namespace gtts {
+
+// Glottal wavetable of one voice (WavetableGlottalSource.h:111-136): rise 3x^2 - 2x^3, fall 1 - x^2,
+// closed phase 0; or one sine period.  For tn_min != tn_max the fall segment stored here is the
+// initial one; the kernels evaluate the amplitude-dependent fall segment analytically.
+void buildWavetable(const VoiceDev& v, double* table)
+{
+	if (v.waveform == 0) {
+		for (int i = 0; i < v.div1; ++i) {
+			const double x = static_cast<double>(i) / static_cast<double>(v.div1);
+			const double x2 = x * x;
+			const double x3 = x2 * x;
+			table[i] = (3.0 * x2) - (2.0 * x3);
+		}
+		for (int i = v.div1, j = 0; i < v.div2; ++i, ++j) {
+			const double x = static_cast<double>(j) / v.tn_length;
+			table[i] = 1.0 - (x * x);
+		}
+		for (int i = v.div2; i < kTableLen; ++i) table[i] = 0.0;
+	} else {
+		for (int i = 0; i < kTableLen; ++i)
+			table[i] = std::sin((static_cast<double>(i) / kTableLen) * 2.0 * kPiTable);
 	}
 }
 

@@ -16,6 +16,7 @@ int controlSteps(int fs, double controlRate);
 // Returns nullptr on success, else a static error text.
 const char* deriveVoice(const gtts_voice_config& c, VoiceDev& v);
 int64_t outputLength(const VoiceDev& v, int64_t nInternal);
+void buildWavetable(const VoiceDev& v, double* table512);
 void shardPlan(const int64_t* cost, int64_t n, int shards, int32_t* shardOf);
 
 } // namespace gtts

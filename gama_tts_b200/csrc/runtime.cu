@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <new>
@@ -18,6 +19,7 @@
 #include "batch_plan.h"
 #include "host_tables.h"
 #include "tube_kernel.cuh"
+#include "tube_kernel_v1.cuh"
 
 using namespace gtts;
 
@@ -79,6 +81,9 @@ struct gtts_batch {
 	int64_t cap_frames = 0, cap_out = 0;
 	cudaStream_t stream = nullptr;      // used by run_host
 	int32_t last_launches = 0;
+	double* d_tables = nullptr;         // per-voice glottal wavetables (v1 kernel)
+	bool use_v1 = false;
+	const char* last_kernel = "none";
 };
 
 struct gtts_stream {
@@ -111,11 +116,31 @@ int launchBatch(gtts_batch* b, const float* dFrames, float* dOut, cudaStream_t s
 	P.src_tab = b->h->d_src_tab;
 	P.queue = b->d_queue;
 	P.n_utt = static_cast<int32_t>(nUtt);
-	const int64_t ctasWanted = (nUtt + kWarpsPerCta - 1) / kWarpsPerCta;
-	const int grid = static_cast<int>(std::min<int64_t>(ctasWanted, b->h->sms));
-	const size_t smem = tube_smem_bytes(kWarpsPerCta);
-	tube_kernel_v0<kWarpsPerCta><<<grid, kWarpsPerCta * 32, smem, stream>>>(P);
-	GTTS_CUDA(cudaGetLastError());
+	if (b->use_v1 && b->d_states == nullptr) {
+		// pipelined warp-specialised kernel: one persistent CTA per SM, 7 utterance slots each
+		v1::KernelParamsV1 Q;
+		Q.voices = b->d_voices;
+		Q.tables = b->d_tables;
+		Q.utts = b->d_utts;
+		Q.order = b->d_order;
+		Q.frames = dFrames;
+		Q.out = dOut;
+		Q.src_tab = b->h->d_src_tab;
+		Q.queue = b->d_queue;
+		Q.n_utt = static_cast<int32_t>(nUtt);
+		const int64_t ctasWanted = (nUtt + v1::kSlots - 1) / v1::kSlots;
+		const int grid = static_cast<int>(std::min<int64_t>(ctasWanted, b->h->sms));
+		v1::tube_kernel_v1<<<grid, v1::kThreads, v1::smem_bytes(), stream>>>(Q);
+		GTTS_CUDA(cudaGetLastError());
+		b->last_kernel = "tube_kernel_v1";
+	} else {
+		const int64_t ctasWanted = (nUtt + kWarpsPerCta - 1) / kWarpsPerCta;
+		const int grid = static_cast<int>(std::min<int64_t>(ctasWanted, b->h->sms));
+		const size_t smem = tube_smem_bytes(kWarpsPerCta);
+		tube_kernel_v0<kWarpsPerCta><<<grid, kWarpsPerCta * 32, smem, stream>>>(P);
+		GTTS_CUDA(cudaGetLastError());
+		b->last_kernel = "tube_kernel_v0";
+	}
 	b->last_launches = 1;
 	return GTTS_OK;
 }
@@ -128,6 +153,17 @@ int uploadPlan(gtts_batch* b)
 	GTTS_CUDA(cudaMalloc(&b->d_utts, sizeof(UttDesc) * std::max<size_t>(p.utts.size(), 1)));
 	GTTS_CUDA(cudaMalloc(&b->d_order, sizeof(int32_t) * std::max<size_t>(p.order.size(), 1)));
 	GTTS_CUDA(cudaMalloc(&b->d_queue, sizeof(int32_t)));
+	// kernel choice: v1 (pipelined) needs control periods of at least one 32-sample block; the general
+	// v0 kernel takes everything else (and all streaming / resumed work).  GTTS_KERNEL=v0 forces v0.
+	b->use_v1 = true;
+	for (const UttDesc& d : p.utts) if (d.steps < kBlock) b->use_v1 = false;
+	if (const char* env = std::getenv("GTTS_KERNEL")) { if (std::strcmp(env, "v0") == 0) b->use_v1 = false; }
+	if (b->use_v1) {
+		std::vector<double> tables(p.voices.size() * kTableLen);
+		for (size_t v = 0; v < p.voices.size(); ++v) buildWavetable(p.voices[v], tables.data() + v * kTableLen);
+		GTTS_CUDA(cudaMalloc(&b->d_tables, sizeof(double) * std::max<size_t>(tables.size(), 1)));
+		GTTS_CUDA(cudaMemcpy(b->d_tables, tables.data(), sizeof(double) * tables.size(), cudaMemcpyHostToDevice));
+	}
 	GTTS_CUDA(cudaMemcpy(b->d_voices, p.voices.data(), sizeof(VoiceDev) * p.voices.size(), cudaMemcpyHostToDevice));
 	if (!p.utts.empty()) {
 		GTTS_CUDA(cudaMemcpy(b->d_utts, p.utts.data(), sizeof(UttDesc) * p.utts.size(), cudaMemcpyHostToDevice));
@@ -248,16 +284,20 @@ int gtts_create(int32_t device, gtts_handle** handle_out)
 	    (ce = cudaMalloc(&h->d_src_tab, sizeof(double2) * kSrcFilterLen)) != cudaSuccess ||
 	    (ce = cudaMemcpy(h->d_src_tab, tab.data(), sizeof(double2) * kSrcFilterLen, cudaMemcpyHostToDevice)) != cudaSuccess ||
 	    (ce = cudaFuncSetAttribute(tube_kernel_v0<kWarpsPerCta>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-	                               (int) tube_smem_bytes(kWarpsPerCta))) != cudaSuccess) {
+	                               (int) tube_smem_bytes(kWarpsPerCta))) != cudaSuccess ||
+	    (ce = cudaFuncSetAttribute(v1::tube_kernel_v1, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                               (int) v1::smem_bytes())) != cudaSuccess) {
 		if (h->d_src_tab) cudaFree(h->d_src_tab);
 		delete h;
 		return failCuda(ce, "gtts_create: device setup");
 	}
-	char buf[512];
+	char buf[1024];
 	std::snprintf(buf, sizeof buf,
-			"{\"device\": %d, \"name\": \"%s\", \"sm\": \"%d.%d\", \"sms\": %d, \"kernel\": \"tube_kernel_v0\", "
-			"\"warps_per_cta\": %d, \"smem_per_cta\": %zu, \"utterances_per_warp\": 1}",
-			device, prop.name, prop.major, prop.minor, h->sms, kWarpsPerCta, tube_smem_bytes(kWarpsPerCta));
+			"{\"device\": %d, \"name\": \"%s\", \"sm\": \"%d.%d\", \"sms\": %d, "
+			"\"kernels\": {\"tube_kernel_v1\": {\"warps_per_cta\": %d, \"utterance_slots_per_cta\": %d, \"smem_per_cta\": %zu}, "
+			"\"tube_kernel_v0\": {\"warps_per_cta\": %d, \"utterances_per_warp\": 1, \"smem_per_cta\": %zu}}}",
+			device, prop.name, prop.major, prop.minor, h->sms, (int) v1::kWarps, (int) v1::kSlots, v1::smem_bytes(),
+			kWarpsPerCta, tube_smem_bytes(kWarpsPerCta));
 	h->description = buf;
 	*handle_out = h;
 	return GTTS_OK;
@@ -376,7 +416,7 @@ void gtts_batch_free(gtts_batch* b)
 	cudaSetDevice(b->h->device);
 	if (b->stream) { cudaStreamSynchronize(b->stream); cudaStreamDestroy(b->stream); }
 	cudaFree(b->d_voices); cudaFree(b->d_utts); cudaFree(b->d_order); cudaFree(b->d_queue);
-	cudaFree(b->d_states); cudaFree(b->d_frames); cudaFree(b->d_out);
+	cudaFree(b->d_states); cudaFree(b->d_frames); cudaFree(b->d_out); cudaFree(b->d_tables);
 	delete b;
 }
 

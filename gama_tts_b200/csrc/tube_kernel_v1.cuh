@@ -1,0 +1,629 @@
+// Pipelined, warp-specialised tube kernel (sm_100a): one persistent CTA per SM steps kSlots = 7
+// utterances in lockstep, 32 internal samples ("block") per iteration, through a software pipeline
+// whose stages run concurrently on different warps and different blocks:
+//
+//   it = b     slot helper   float32 walk of parameter 0 -> f0 -> oscillator increments        (lane = sample)
+//   it = b+1   chain A       oscillator phase recurrence (serial, lane = slot)
+//   it = b+2   slot helper   float32 walk of parameters 1..6 -> amplitudes, frication taps, bandpass
+//                            coefficients; noise (LCG jump); wavetable lookup; 49-tap FIR; mixing   (lane = sample)
+//   it = b+3   chain A       frication bandpass biquad + throat lowpass (serial, lane = slot)
+//              pool          float32 walk of parameters 7..15 -> junction coefficients            (lane = sample)
+//   it = b+4   tube warps    the waveguide itself: 8 lanes per utterance, waves in registers, shuffles
+//   it = b+5   chain B       radiation filters (serial, lane = slot x filter) + output sum
+//   it = b+6   pool          windowed-sinc sample-rate conversion, lane = output sample, coalesced stores
+//
+// Warps: 0-1 tube (slots 0-3 / 4-6), 2 chain A, 3 chain B, 4-10 slot helpers, 11-15 pool (dynamic
+// task queue in shared memory).  Two CTA barriers per iteration (work | slot bookkeeping).
+// The per-sample arithmetic is the same as in tube_kernel.cuh (v0), which stays as the general
+// kernel for streaming / resumed utterances and control periods shorter than one block.
+#ifndef GTTS_TUBE_KERNEL_V1_CUH_
+#define GTTS_TUBE_KERNEL_V1_CUH_
+
+#include "tube_kernel.cuh"
+
+namespace gtts {
+namespace v1 {
+
+enum {
+	kSlots = 7,
+	kWarps = 16,
+	kThreads = kWarps * 32,
+	kTubeWarps = 2,
+	kChainAWarp = 2,
+	kChainBWarp = 3,
+	kHelper0 = 4,                 // warps 4..10: slot helpers
+	kPool0 = kHelper0 + kSlots,   // warps 11..15: pool
+	kPoolWarps = kWarps - kPool0,
+	kStages = 6,                  // last stage (SRC) runs at it = b + 6
+	kRow = 33,
+};
+
+struct SlotSm {
+	double osc[2][kRow];
+	double pos[2][2][kRow];
+	double sig[2][kRow];
+	double bp[2][3][kRow];        // b0, a1, a2
+	double tapa[2][kRow], tapb[2][kRow];
+	double thr[4][kRow];
+	double in[3][kRow];
+	double2 pab[2][kRow];         // {tapA * fric, tapB * fric}
+	double2 kab[2][6][kRow];      // per tube lane g < 6: {kA, kB}; kab[.][1].y = alpha left/right, kab[.][2].y = alpha upper
+	double onepk7[3][kRow];
+	double endm[2][kRow], endn[2][kRow];
+	double rad[3][kRow];          // mouth radiation, nose radiation, throat outputs of one block
+	double ve[kVRing], vo[kVRing];
+	double xring[kSrcRing];
+	float  cur[kBlock][8];        // slot helper scratch: parameters 0..6 of the block being converted
+	int    ip[3][kBlock];
+	// coefficient-walk cursor (parameters 7..15), advanced by whichever pool warp runs the task
+	float  ccur[9], cdelta[9];
+	int    cframe, coff;
+	// descriptor
+	UttDesc U;
+	int     it;                   // iteration counter of the current utterance; -1: idle
+	int     nblocks;
+	int     voice;
+};
+
+struct CtaSm {
+	double2 tab[kSrcFilterLen];
+	SlotSm slot[kSlots];
+	float  pscratch[kPoolWarps][kBlock][10];   // pool scratch: parameters 7..15 of one block
+	int    task_counter;
+	int    live;                  // number of slots with work
+};
+
+struct KernelParamsV1 {
+	const VoiceDev* voices;
+	const double* tables;         // per-voice glottal wavetables, 512 doubles each (host-built)
+	const UttDesc* utts;
+	const int32_t* order;
+	const float* frames;
+	float* out;
+	const double2* src_tab;
+	int32_t* queue;
+	int32_t n_utt;
+};
+
+GTTS_DEV int block_len(const SlotSm& s, int b)
+{
+	const long long left = s.U.n_internal - (long long) b * kBlock;
+	return left < kBlock ? (int) left : kBlock;
+}
+
+// ---- float32 walk of a group of parameters over one block (Controller.cpp:297-311) -----------------
+// lane k walks parameter base + k: cur/delta/off/frame are the lane's cursor (registers or shared),
+// out[j][k] receives the value used for sample j.  Control periods are >= one block, so at most one
+// frame boundary falls inside the block.
+GTTS_DEV void walk_block(const float* frames, long long nFrames, int steps, float invSteps, int param,
+			int nb, float& cur, float& delta, int& off, int& frame, float* out, int outStride, bool active)
+{
+	if (active) {
+		const int first = (steps - off) < nb ? (steps - off) : nb;
+		// prefetch the next frame pair in case the boundary falls inside this block
+		float nxt0 = 0.f, nxt1 = 0.f;
+		const bool crosses = first < nb;
+		if (crosses) {
+			const long long f1 = frame + 1;
+			nxt0 = frames[f1 * kNumParams + param];
+			nxt1 = (f1 + 1 < nFrames) ? frames[(f1 + 1) * kNumParams + param] : nxt0;
+		}
+		int j = 0;
+		for (; j < first; ++j) { out[j * outStride] = cur; cur = __fadd_rn(cur, delta); }
+		off += first;
+		if (off == steps) {
+			off = 0;
+			frame += 1;
+			if (crosses) {
+				cur = nxt0;
+				delta = __fmul_rn(__fsub_rn(nxt1, nxt0), invSteps);
+				for (; j < nb; ++j) { out[j * outStride] = cur; cur = __fadd_rn(cur, delta); }
+				off = nb - first;
+			} else if (frame < nFrames) {
+				// boundary exactly at the end of the block: start the next frame
+				const float a = frames[(long long) frame * kNumParams + param];
+				const float b = (frame + 1 < nFrames) ? frames[(long long) (frame + 1) * kNumParams + param] : a;
+				cur = a;
+				delta = __fmul_rn(__fsub_rn(b, a), invSteps);
+			}
+		}
+	}
+}
+
+GTTS_DEV void cursor_init(const float* frames, long long nFrames, float invSteps, int param, float& cur, float& delta)
+{
+	const float a = frames[param];
+	const float b = (nFrames > 1) ? frames[kNumParams + param] : a;
+	cur = a;
+	delta = __fmul_rn(__fsub_rn(b, a), invSteps);
+}
+
+// ---- slot helper (warp 4 + s): stages at it = b and it = b + 2 ------------------------------------------
+struct HelperRegs {
+	float cur, delta;             // lane 0: parameter 0 (block it); lanes 1..6: parameters 1..6 (block it - 2)
+	int off, frame;
+	double seed, noise_x1;
+};
+
+GTTS_DEV void helper_iteration(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int lane, HelperRegs& h)
+{
+	const int it = S->it;
+	if (it < 0) return;
+	const VoiceDev& V = P.voices[S->voice];
+	const float* frames = P.frames + S->U.frame_begin * kNumParams;
+	const long long nFrames = S->U.n_frames;
+	if (it == 0) {
+		// new utterance: clear the rings, reset cursors and the noise generator
+		for (int i = lane; i < kVRing; i += 32) { S->ve[i] = 0.0; S->vo[i] = 0.0; }
+		for (int i = lane; i < kSrcRing; i += 32) S->xring[i] = 0.0;
+		if (lane < 7) cursor_init(frames, nFrames, S->U.inv_steps, lane, h.cur, h.delta);
+		h.off = 0; h.frame = 0;
+		h.seed = 0.7892347; h.noise_x1 = 0.0;
+		if (lane < 9) {
+			float c, d;
+			cursor_init(frames, nFrames, S->U.inv_steps, 7 + lane, c, d);
+			S->ccur[lane] = c; S->cdelta[lane] = d;
+		}
+		if (lane == 0) { S->cframe = 0; S->coff = 0; }
+		__syncwarp();
+	}
+	const int b0 = it, b2 = it - 2;
+	const bool do0 = b0 < S->nblocks, do2 = b2 >= 0 && b2 < S->nblocks;
+	// one walk loop serves both cursors: lane 0 (block b0), lanes 1..6 (block b2)
+	{
+		const bool mine = (lane == 0) ? do0 : (lane < 7 && do2);
+		const int nb = (lane == 0) ? block_len(*S, b0) : block_len(*S, b2);
+		walk_block(frames, nFrames, S->U.steps, S->U.inv_steps, lane, nb, h.cur, h.delta, h.off, h.frame,
+				&S->cur[0][lane], 8, mine);
+	}
+	__syncwarp();
+	if (do0) {
+		const int nb = block_len(*S, b0);
+		if (lane < nb) {
+			const double f0 = 220.0 * gtts_exp2(((double) S->cur[lane][0] + 3.0) * (1.0 / 12.0));
+			S->osc[b0 & 1][lane] = (f0 / 2.0) * V.basic_inc;
+		}
+	}
+	if (do2) {
+		const int nb = block_len(*S, b2);
+		const int buf = b2 & 1;
+		const long long n0 = (long long) b2 * kBlock;
+		double ax = 0.0, ah1 = 0.0;
+		if (lane < nb) {
+			const float* p = S->cur[lane];
+			ax = amp60((double) p[1]);
+			ah1 = amp60((double) p[2]);
+			const double fa = amp60((double) p[3]);
+			const double fpos = (double) p[4];
+			int ip = (int) fpos;
+			const double comp = fpos - ip;
+			double ta = (1.0 - comp) * fa, tb = comp * fa;
+			if (ip < 0 || ip > 7) { ta = 0.0; tb = 0.0; ip = -50; }
+			S->tapa[buf][lane] = ta;
+			S->tapb[buf][lane] = tb;
+			S->ip[b2 % 3][lane] = ip;
+			const double pi = 3.14159265358979323846;
+			const double tv = tan(pi * (double) p[6] * V.Ts);
+			const double cv = cos(2.0 * pi * (double) p[5] * V.Ts);
+			const double a2 = (1.0 - tv) / (1.0 + tv);
+			S->bp[buf][2][lane] = a2;
+			S->bp[buf][1][lane] = -(1.0 + a2) * cv;
+			S->bp[buf][0][lane] = 0.5 - 0.5 * a2;
+		}
+		const double lp = stage_noise(lane, nb, h.seed, h.noise_x1);
+		// wavetable lookup of both half samples (WavetableGlottalSource.h:212-228)
+		if (lane < nb) {
+			const double* table = P.tables + (size_t) S->voice * kTableLen;
+			const bool dynamic = (V.waveform == 0) && (V.tn_delta != 0.0);
+			double nd2 = 0.0, inv = 0.0;
+			if (dynamic) {
+				nd2 = (double) V.div2 - rint(ax * V.tn_delta);
+				nd2 = nd2 > 0.0 ? nd2 : 0.0;
+				inv = 1.0 / (nd2 - (double) V.div1);
+			}
+			double v[2];
+#pragma unroll
+			for (int s = 0; s < 2; ++s) {
+				const double pos = S->pos[buf][s][lane];
+				const unsigned lo = __double2uint_rz(pos);
+				const unsigned up = (lo + 1 > 511u) ? lo + 1 - 512u : lo + 1;
+				double tl, tu;
+				if (dynamic && lo >= (unsigned) V.div1 && lo < (unsigned) V.div2) {
+					const double x = (double) (int) (lo - V.div1) * inv;
+					tl = (lo >= (unsigned) nd2) ? 0.0 : 1.0 - (x * x);
+				} else {
+					tl = table[lo];
+				}
+				if (dynamic && up >= (unsigned) V.div1 && up < (unsigned) V.div2) {
+					const double x = (double) (int) (up - V.div1) * inv;
+					tu = (up >= (unsigned) nd2) ? 0.0 : 1.0 - (x * x);
+				} else {
+					tu = table[up];
+				}
+				v[s] = tl + ((pos - (double) lo) * (tu - tl));
+			}
+			const int slot = (int) ((n0 + lane) & (kVRing - 1));
+			S->ve[slot] = v[0];
+			S->vo[slot] = v[1];
+		}
+		__syncwarp();
+		if (lane < nb) {
+			const long long n = n0 + lane;
+			double acc = 0.0;
+#pragma unroll
+			for (int i = 0; i < kFirTaps; ++i) {
+				const int idx = (int) ((n - ((i & 1) ? (i - 1) / 2 : i / 2)) & (kVRing - 1));
+				const double x = (i & 1) ? S->ve[idx] : S->vo[idx];
+				acc += x * c_fir[i];
+			}
+			double pulse = acc;
+			const double pn = lp * pulse;
+			pulse = ax * ((pulse * V.one_minus_breath) + (pn * V.breath));
+			double sig;
+			if (V.modulation) {
+				double cm = ax * V.crossmix;
+				cm = (cm < 1.0) ? cm : 1.0;
+				sig = (pn * cm) + (lp * (1.0 - cm));
+			} else {
+				sig = lp;
+			}
+			S->sig[buf][lane] = sig;
+			S->in[b2 % 3][lane] = (pulse + (ah1 * sig)) * 0.125;
+			S->thr[b2 & 3][lane] = pulse * 0.125;
+		}
+	}
+	(void) C;
+}
+
+// ---- pool task: junction coefficients of block b = it - 3 (VocalTractModel0.h:484-512, 698-716) ---------
+GTTS_DEV void coef_task(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int lane, int poolWarp)
+{
+	const int b = S->it - 3;
+	if (S->it < 0 || b < 0 || b >= S->nblocks) return;
+	const VoiceDev& V = P.voices[S->voice];
+	const float* frames = P.frames + S->U.frame_begin * kNumParams;
+	const int nb = block_len(*S, b);
+	float (*scr)[10] = C->pscratch[poolWarp];
+	{
+		float cur = 0.f, delta = 0.f;
+		int off = S->coff, frame = S->cframe;
+		if (lane < 9) { cur = S->ccur[lane]; delta = S->cdelta[lane]; }
+		__syncwarp();
+		walk_block(frames, S->U.n_frames, S->U.steps, S->U.inv_steps, 7 + lane, nb, cur, delta, off, frame,
+				&scr[0][lane], 10, lane < 9);
+		if (lane < 9) { S->ccur[lane] = cur; S->cdelta[lane] = delta; }
+		if (lane == 0) { S->coff = off; S->cframe = frame; }
+	}
+	__syncwarp();
+	if (lane < nb) {
+		const float* p = scr[lane];
+		double r2[8];
+#pragma unroll
+		for (int i = 0; i < 8; ++i) {
+			double r = (double) p[i] * V.radius_coef[i];
+			r = r > 0.01 ? r : 0.01;
+			r2[i] = r * r;
+		}
+		const double vel = (double) p[8];
+		const double v2 = vel * vel;
+		const double sum = 2.0 / (r2[3] + r2[3] + v2);
+		const double k7 = kcoef(r2[7], V.ap2);
+		const int buf = b & 1;
+		S->kab[buf][0][lane] = make_double2(kcoef(r2[0], r2[1]), kcoef(r2[1], r2[2]));
+		S->kab[buf][1][lane] = make_double2(kcoef(r2[2], r2[3]), sum * r2[3]);
+		S->kab[buf][2][lane] = make_double2(kcoef(r2[3], r2[4]), sum * v2);
+		S->kab[buf][3][lane] = make_double2(kcoef(r2[4], r2[5]), kcoef(r2[5], r2[6]));
+		S->kab[buf][4][lane] = make_double2(kcoef(r2[6], r2[7]), k7);
+		S->kab[buf][5][lane] = make_double2(kcoef(v2, V.nr1_2), 0.0);
+		S->onepk7[b % 3][lane] = 1.0 + k7;
+	}
+	__syncwarp();
+}
+
+// ---- pool task: sample-rate conversion of the outputs that block b = it - 6 completes ---------------
+GTTS_DEV void src_task(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int lane)
+{
+	const int b = S->it - kStages;
+	if (S->it < 0 || b < 0 || b >= S->nblocks) return;
+	const VoiceDev& V = P.voices[S->voice];
+	const long long nStart = (long long) b * kBlock;
+	const long long nEnd = nStart + block_len(*S, b);
+	const unsigned inc = V.src_inc;
+	long long k0 = (long long) ((((unsigned long long) nStart << 16) + inc - 1) / inc);
+	long long k1 = (long long) ((((unsigned long long) nEnd << 16) + inc - 1) / inc);
+	if (b == S->nblocks - 1) k1 = S->U.n_out;          // flush: chain B appended the 26 zeros
+	if (k1 > S->U.n_out) k1 = S->U.n_out;
+	float* out = P.out + S->U.out_begin;
+	for (long long k = k0 + lane; k < k1; k += 32) {
+		const unsigned long long t = (unsigned long long) k * inc;
+		const int e = (int) (t >> 16);
+		const unsigned f = (unsigned) (t & 0xFFFFu);
+		double acc = 0.0;
+		{
+			const double interp = (double) (f & 0xFFu) / 256;
+			const unsigned L = f >> 8;
+#pragma unroll
+			for (int j = 0; j < kSrcZeroCrossings; ++j) {
+				const double2 c = C->tab[L + 256 * j];
+				const double x = S->xring[(e - 13 - j) & (kSrcRing - 1)];
+				acc += (x * (c.x + (c.y * interp)));
+			}
+		}
+		{
+			const unsigned gph = (~f) & 0xFFFFu;
+			const double interp = (double) (gph & 0xFFu) / 256;
+			const unsigned L = gph >> 8;
+#pragma unroll
+			for (int j = 0; j < kSrcZeroCrossings; ++j) {
+				const double2 c = C->tab[L + 256 * j];
+				const double x = S->xring[(e - 12 + j) & (kSrcRing - 1)];
+				acc += (x * (c.x + (c.y * interp)));
+			}
+		}
+		out[k] = (float) acc;
+	}
+}
+
+// ---- chain A (warp 2, lane = slot): oscillator phase (block it-1), frication bandpass (block it-3) ------
+struct ChainARegs { double pos; BandpassState bp; };
+
+GTTS_DEV void chain_a_iteration(CtaSm* C, const KernelParamsV1& P, int lane, ChainARegs& r)
+{
+	if (lane >= kSlots) return;
+	SlotSm* S = &C->slot[lane];
+	const int it = S->it;
+	if (it < 0) return;
+	const int b1 = it - 1, b3 = it - 3;
+	const bool do1 = b1 >= 0 && b1 < S->nblocks, do3 = b3 >= 0 && b3 < S->nblocks;
+	if (b1 == 0) r.pos = 0.0;
+	if (b3 == 0) { r.bp.x1 = r.bp.x2 = r.bp.y1 = r.bp.y2 = 0.0; }
+	const int nb1 = do1 ? block_len(*S, b1) : 0, nb3 = do3 ? block_len(*S, b3) : 0;
+	const int buf1 = b1 & 1, buf3 = b3 & 1;
+	for (int j = 0; j < kBlock; ++j) {
+		if (j < nb1) {
+			const double inc = S->osc[buf1][j];
+			double s = r.pos + inc;
+			r.pos = (s > 511.0) ? s - 512.0 : s;
+			S->pos[buf1][0][j] = r.pos;
+			s = r.pos + inc;
+			r.pos = (s > 511.0) ? s - 512.0 : s;
+			S->pos[buf1][1][j] = r.pos;
+		}
+		if (j < nb3) {
+			const double x = S->sig[buf3][j];
+			const double y = S->bp[buf3][0][j] * (x - r.bp.x2) - S->bp[buf3][1][j] * r.bp.y1 - S->bp[buf3][2][j] * r.bp.y2;
+			r.bp.x2 = r.bp.x1; r.bp.x1 = x; r.bp.y2 = r.bp.y1; r.bp.y1 = y;
+			S->pab[buf3][j] = make_double2(S->tapa[buf3][j] * y, S->tapb[buf3][j] * y);
+		}
+	}
+}
+
+// ---- chain B (warp 3, lane = slot * 4 + filter): radiation filters + throat lowpass of block it - 5 ------
+// One code path for the three one-pole filters: y = b0 x + b1 x1 - a1 y1, out = y * gain
+//   f = 0 mouth radiation (b0 = A, b1 = a1 = -A, gain 1) on (1 + k7) T[S10]     (RadiationFilter.h:73-79)
+//   f = 1 nose radiation on (1 + nk5) NT[N6]
+//   f = 2 throat lowpass (b0, b1 = 0, a1, gain = throat gain) on pulse * 0.125   (Throat.h:80-85)
+struct ChainBRegs { double x1, y1; };
+
+GTTS_DEV void chain_b_iteration(CtaSm* C, const KernelParamsV1& P, int lane, ChainBRegs& r)
+{
+	const int s = lane >> 2, f = lane & 3;
+	int nb = 0, b = -1;
+	SlotSm* S = nullptr;
+	if (s < kSlots && f < 3) {
+		S = &C->slot[s];
+		b = S->it - 5;
+		if (S->it >= 0 && b >= 0 && b < S->nblocks) nb = block_len(*S, b);
+	}
+	if (nb > 0) {
+		const VoiceDev& V = P.voices[S->voice];
+		if (b == 0) { r.x1 = 0.0; r.y1 = 0.0; }
+		const double b0 = f == 0 ? V.rad_m : (f == 1 ? V.rad_n : V.throat_b0);
+		const double b1 = f == 0 ? -V.rad_m : (f == 1 ? -V.rad_n : 0.0);
+		const double a1 = f == 0 ? -V.rad_m : (f == 1 ? -V.rad_n : V.throat_a1);
+		const double gain = f == 2 ? V.throat_gain : 1.0;
+		const double onePlusN = 1.0 + V.nasal_k[5];
+		const double* in = f == 0 ? S->endm[b & 1] : (f == 1 ? S->endn[b & 1] : S->thr[b & 3]);
+		const double* scale = S->onepk7[b % 3];
+		for (int j = 0; j < nb; ++j) {
+			double x = in[j];
+			if (f == 0) x = scale[j] * x; else if (f == 1) x = onePlusN * x;
+			const double y = b0 * x + b1 * r.x1 - a1 * r.y1;
+			r.x1 = x;
+			r.y1 = y;
+			S->rad[f][j] = y * gain;
+		}
+	}
+	__syncwarp();
+	// output sum, lane = sample: (mouth + nose) + throat (VocalTractModel0.h:657-660, 441)
+	for (int q = 0; q < kSlots; ++q) {
+		SlotSm* Q = &C->slot[q];
+		const int qb = Q->it - 5;
+		if (Q->it < 0 || qb < 0 || qb >= Q->nblocks) continue;
+		const int qn = block_len(*Q, qb);
+		const long long n0 = (long long) qb * kBlock;
+		if (lane < qn) {
+			const int idx = (int) ((n0 + lane) & (kSrcRing - 1));
+			Q->xring[idx] = (Q->rad[0][lane] + Q->rad[1][lane]) + Q->rad[2][lane];
+		}
+		if (qb == Q->nblocks - 1 && lane < 2 * kSrcZeroCrossings) {
+			// flushBuffer(): 26 zeros after the last input (SampleRateConverter.h:462-471)
+			Q->xring[(Q->U.n_internal + lane) & (kSrcRing - 1)] = 0.0;
+		}
+	}
+}
+
+// ---- tube warps (0, 1): block it - 4, four utterances per warp, 8 lanes each ----------------------------
+GTTS_DEV void tube_iteration(CtaSm* C, const KernelParamsV1& P, int warp, int lane, TubeLane& t)
+{
+	const int g = lane & 7;
+	const int slot = warp * 4 + (lane >> 3);
+	const int base = lane & ~7;
+	SlotSm* S = &C->slot[slot < kSlots ? slot : 0];
+	int nb = 0, b = -1;
+	if (slot < kSlots) {
+		b = S->it - 4;
+		if (S->it >= 0 && b >= 0 && b < S->nblocks) nb = block_len(*S, b);
+	}
+	const VoiceDev& V = P.voices[S->voice];
+	if (b == 0) { t.aT = t.aB = t.bT = t.bB = t.extra = 0.0; }
+	const double d = V.damping;
+	// lane role constants (see tube_kernel.cuh: stage_tube)
+	const int tapA = (g >= 1 && g <= 4) ? 2 * g - 1 : -100;
+	const int tapB = (g <= 3) ? 2 * g : -100;
+	const double constA = g == 6 ? V.nasal_k[2] : (g == 7 ? V.nasal_k[4] : 0.0);
+	const double constB = g == 5 ? V.nasal_k[1] : (g == 6 ? V.nasal_k[3] : (g == 7 ? V.nasal_k[5] : 0.0));
+	const double reflB0 = g == 4 ? V.refl_b0_m : V.refl_b0_n;
+	const double reflA1 = g == 4 ? V.refl_a1_m : V.refl_a1_n;
+	const int buf = b & 1;
+	const double2* kabRow = S->kab[buf][g < 6 ? g : 0];
+	const double* extraRow = (g == 0) ? S->in[(b % 3 + 3) % 3] : &S->kab[buf][2][0].y;   // g0: input, g1: alpha upper
+	const int extraStride = (g == 0) ? 1 : 2;
+	const int* ipRow = S->ip[(b % 3 + 3) % 3];
+	double* endRow = (g == 4) ? S->endm[buf] : S->endn[buf];
+	const int nbMax = __reduce_max_sync(0xffffffffu, nb);
+	for (int j = 0; j < nbMax; ++j) {
+		const bool on = j < nb;
+		const double2 kk = kabRow[j];
+		const double2 pab = S->pab[buf][j];
+		const int ip = ipRow[j];
+		const double ex = extraRow[j * extraStride];
+		const double kA = (g == 6 || g == 7) ? constA : kk.x;
+		const double kB = (g >= 5 || g == 2) ? constB : kk.y;
+		const double tfA = (tapA == ip) ? pab.x : ((tapA == ip + 1) ? pab.y : 0.0);
+		const double tfB = (tapB == ip) ? pab.x : ((tapB == ip + 1) ? pab.y : 0.0);
+
+		const double dlA = kA * (t.aT - t.aB);
+		const double aTo = ((t.aT + dlA) * d) + tfA;
+		const double aBo = (t.aB + dlA) * d;
+
+		double bTo, bBo, linkOut = aBo, newExtra = t.extra;
+		if (g == 1) {
+			const double aL = kk.y, aU = ex;
+			const double jp = (aL * t.bT) + (aL * t.bB) + (aU * t.extra);
+			bBo = (jp - t.bT) * d;
+			bTo = ((jp - t.bB) * d) + tfB;
+			linkOut = (jp - t.extra) * d;
+		} else if (g == 4 || g == 7) {
+			if (on) endRow[j] = t.bT;
+			const double y = reflB0 * (kB * t.bT) - reflA1 * t.extra;
+			newExtra = y;
+			bBo = d * y;
+			bTo = 0.0;
+		} else {
+			const double dlB = kB * (t.bT - t.bB);
+			bTo = ((t.bT + dlB) * d) + tfB;
+			bBo = (t.bB + dlB) * d;
+		}
+		const double fromPrev = shfl_d(bTo, base + ((g + 7) & 7), 32);
+		const double fromNext = shfl_d(aBo, base + ((g + 1) & 7), 32);
+		const double link = shfl_d(linkOut, base + ((g == 1) ? 5 : 1), 32);
+		double nextAT = fromPrev;
+		if (g == 0) {
+			nextAT = (t.extra * d) + ex;
+			newExtra = aBo;
+		} else if (g == 5) {
+			nextAT = link;
+		} else if (g == 1) {
+			newExtra = link;
+		}
+		if (on) {
+			t.aT = nextAT;
+			t.aB = bBo;
+			t.bT = aTo;
+			t.bB = fromNext;
+			t.extra = newExtra;
+		}
+	}
+}
+
+// ---- slot bookkeeping (between the two barriers; warp 2, lane = slot) -----------------------------------
+GTTS_DEV void schedule_slots(CtaSm* C, const KernelParamsV1& P, int lane)
+{
+	int alive = 0;
+	if (lane < kSlots) {
+		SlotSm* S = &C->slot[lane];
+		if (S->it >= 0) {
+			S->it += 1;
+			if (S->it > S->nblocks - 1 + kStages) S->it = -1;      // every stage has seen every block
+		}
+		if (S->it < 0) {
+			for (;;) {
+				const int q = atomicAdd(P.queue, 1);
+				if (q >= P.n_utt) break;
+				const UttDesc U = P.utts[P.order[q]];
+				if (U.n_internal == 0) {
+					// no input at all: finishSynthesis() alone converts the 26 flush zeros into zeros
+					for (long long k = 0; k < U.n_out; ++k) P.out[U.out_begin + k] = 0.0f;
+					continue;
+				}
+				S->U = U;
+				S->voice = U.voice;
+				S->nblocks = (int) ((U.n_internal + kBlock - 1) / kBlock);
+				S->it = 0;
+				break;
+			}
+		}
+		alive = S->it >= 0;
+	}
+	const unsigned any = __ballot_sync(0xffffffffu, alive);
+	if (lane == 0) { C->live = any != 0; C->task_counter = 0; }
+}
+
+GTTS_DEV void tube_v1_cta_body(const KernelParamsV1& P, unsigned char* smem, int tid)
+{
+	CtaSm* C = reinterpret_cast<CtaSm*>(smem);
+	const int warp = tid >> 5, lane = tid & 31;
+	for (int i = tid; i < kSrcFilterLen; i += kThreads) C->tab[i] = P.src_tab[i];
+	if (tid < kSlots) { C->slot[tid].it = -1; C->slot[tid].voice = 0; C->slot[tid].nblocks = 0; }
+	if (tid == 0) { C->live = 0; C->task_counter = 0; }
+	__syncthreads();
+	if (warp == kChainAWarp) schedule_slots(C, P, lane);
+	__syncthreads();
+
+	TubeLane tl = {0.0, 0.0, 0.0, 0.0, 0.0};
+	ChainARegs ca = {0.0, {0.0, 0.0, 0.0, 0.0}};
+	ChainBRegs cb = {0.0, 0.0};
+	HelperRegs hr = {0.f, 0.f, 0, 0, 0.7892347, 0.0};
+
+	while (C->live) {
+		if (warp < kTubeWarps) {
+			tube_iteration(C, P, warp, lane, tl);
+		} else if (warp == kChainAWarp) {
+			chain_a_iteration(C, P, lane, ca);
+		} else if (warp == kChainBWarp) {
+			chain_b_iteration(C, P, lane, cb);
+		} else if (warp < kPool0) {
+			SlotSm* S = &C->slot[warp - kHelper0];
+			helper_iteration(C, S, P, lane, hr);
+		} else {
+			// pool: 2 tasks per slot (SRC first: it is the longer one), pulled from a shared counter
+			for (;;) {
+				int task = 0;
+				if (lane == 0) task = atomicAdd(&C->task_counter, 1);
+				task = __shfl_sync(0xffffffffu, task, 0, 32);
+				if (task >= 2 * kSlots) break;
+				SlotSm* S = &C->slot[task % kSlots];
+				if (task < kSlots) src_task(C, S, P, lane);
+				else coef_task(C, S, P, lane, warp - kPool0);
+			}
+		}
+		__syncthreads();
+		if (warp == kChainAWarp) schedule_slots(C, P, lane);
+		__syncthreads();
+	}
+}
+
+#ifndef GTTS_EMU
+__global__ void __launch_bounds__(kThreads, 1) tube_kernel_v1(const KernelParamsV1 P)
+{
+	extern __shared__ __align__(16) unsigned char gtts_smem_v1[];
+	tube_v1_cta_body(P, gtts_smem_v1, threadIdx.x);
+}
+#endif
+
+inline size_t smem_bytes() { return sizeof(CtaSm); }
+
+} // namespace v1
+} // namespace gtts
+#endif

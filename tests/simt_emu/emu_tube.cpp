@@ -66,3 +66,52 @@ extern "C" int emu_batch(const gtts_voice_config* voices, int n_voices, const in
 	}
 	return 0;
 }
+
+// ---- v1 (pipelined, warp-specialised kernel) -----------------------------------------------------------
+#include "../../gama_tts_b200/csrc/tube_kernel_v1.cuh"
+
+extern "C" int emu_batch_v1(const gtts_voice_config* voices, int n_voices, const int* voice_index, double control_rate,
+			const int* steps_override, const float* frames, const long long* frame_offsets, long long n_utt,
+			float* out, long long* out_offsets, int n_ctas)
+{
+	using namespace gtts;
+	BatchPlan plan;
+	int err = 0;
+	g_err = planBatch(voices, n_voices, voice_index, control_rate, steps_override,
+			reinterpret_cast<const int64_t*>(frame_offsets), n_utt, plan, &err);
+	if (err) return err;
+	for (long long u = 0; u <= n_utt; ++u) out_offsets[u] = plan.out_offsets[u];
+	if (!out) return 0;
+	for (const UttDesc& d : plan.utts) {
+		if (d.steps < kBlock) { g_err = "v1 needs control periods of at least one block"; return GTTS_ERR_UNSUPPORTED; }
+	}
+	std::vector<double> taps = designGlottalFir();
+	std::memset(c_fir, 0, sizeof c_fir);
+	for (size_t i = 0; i < taps.size(); ++i) c_fir[i] = taps[i];
+	lcgMultipliers(c_lcg);
+	std::vector<double> h(kSrcFilterLen), dh(kSrcFilterLen);
+	buildSrcTables(h.data(), dh.data());
+	std::vector<double2> tab(kSrcFilterLen);
+	for (int i = 0; i < kSrcFilterLen; ++i) { tab[i].x = h[i]; tab[i].y = dh[i]; }
+	std::vector<double> tables(static_cast<size_t>(n_voices) * kTableLen);
+	for (int v = 0; v < n_voices; ++v) buildWavetable(plan.voices[v], tables.data() + static_cast<size_t>(v) * kTableLen);
+
+	int queue = 0;
+	v1::KernelParamsV1 P;
+	P.voices = plan.voices.data();
+	P.tables = tables.data();
+	P.utts = plan.utts.data();
+	P.order = plan.order.data();
+	P.frames = frames;
+	P.out = out;
+	P.src_tab = tab.data();
+	P.queue = &queue;
+	P.n_utt = static_cast<int32_t>(n_utt);
+
+	std::vector<unsigned char> smem(v1::smem_bytes() + 64);
+	unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem.data()) + 15) & ~uintptr_t(15));
+	for (int b = 0; b < n_ctas; ++b) {
+		simt::run_cta(v1::kThreads, [&](int tid) { v1::tube_v1_cta_body(P, base, tid); });
+	}
+	return 0;
+}

@@ -175,6 +175,19 @@ template<class T> inline T __shfl_sync(unsigned mask, T v, int src, int width = 
 	return simt::shfl<T>(mask, v, s);
 }
 inline int atomicAdd(int* p, int v) { const int old = *p; *p += v; return old; }
+inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
+inline int __reduce_max_sync(unsigned mask, int v)
+{
+	int m = v;
+	for (int l = 0; l < 32; ++l) if ((mask >> l) & 1) { const int o = __shfl_sync(mask, v, l, 32); if (o > m) m = o; }
+	return m;
+}
+inline unsigned __ballot_sync(unsigned mask, int pred)
+{
+	unsigned r = 0;
+	for (int l = 0; l < 32; ++l) if ((mask >> l) & 1) { if (__shfl_sync(mask, pred, l, 32)) r |= 1u << l; }
+	return r;
+}
 inline float __fadd_rn(float a, float b) { return a + b; }
 inline float __fsub_rn(float a, float b) { return a - b; }
 inline float __fmul_rn(float a, float b) { return a * b; }
