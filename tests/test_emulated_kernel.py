@@ -63,3 +63,50 @@ def test_emulated_kernel_steps_override(emu, oracle, real_tracks):
     params = np.repeat(real_tracks[0][100:112], 9, axis=0)
     out = emu([v], [0], [params], warps=1, steps=[1])[0]
     assert np.array_equal(out, oracle.synthesize_samples(v, params))
+
+
+@pytest.fixture(scope="module")
+def emu_v1():
+    subprocess.run(["make", "-s", "-C", os.path.join(HERE, "simt_emu")], check=True)
+    L = C.CDLL(os.path.join(HERE, "simt_emu", "libemu_tube.so"))
+    L.emu_last_error.restype = C.c_char_p
+    L.emu_batch_v1.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
+                               C.c_longlong, C.c_void_p, C.c_void_p, C.c_int]
+
+    def run(voices, vidx, tracks, ctas=1, rate=250.0):
+        va = voice_array(voices)
+        frames, fo = pack_tracks(tracks)
+        vi = np.ascontiguousarray(vidx, np.int32)
+        oo = np.zeros(len(tracks) + 1, np.int64)
+        args = [va, len(voices), vi.ctypes.data, rate, None, frames.ctypes.data, fo.ctypes.data, len(tracks)]
+        assert L.emu_batch_v1(*args, None, oo.ctypes.data, ctas) == 0, L.emu_last_error()
+        out = np.full(int(oo[-1]), np.nan, np.float32)
+        assert L.emu_batch_v1(*args, out.ctypes.data, oo.ctypes.data, ctas) == 0, L.emu_last_error()
+        return [out[oo[i]:oo[i + 1]] for i in range(len(tracks))]
+    return run
+
+
+def test_emulated_pipelined_kernel_matches_oracle(emu_v1, oracle, real_tracks):
+    # the warp-specialised pipeline (tube_kernel_v1.cuh): 10 utterances over 7 slots, so slots are re-used;
+    # ragged lengths, partial last blocks, frame boundaries inside and at the end of blocks, 5 voices
+    rng = np.random.Generator(np.random.PCG64(5))
+    hello, shells = real_tracks[0], real_tracks[2]
+    voices = [default_voice("male"), default_voice("female"), default_voice("baby"), random_voice(rng), random_voice(rng)]
+    tracks = [hello[:40], shells[230:262], shells[640:670], T.synthetic_track(3, 25), shells[900:930], hello[:1],
+              hello[:0], hello[100:133], hello[200:209], shells[300:320]]
+    vidx = [0, 1, 2, 3, 4, 3, 0, 0, 1, 2]
+    res = emu_v1(voices, vidx, tracks)
+    for vi, tr, out in zip(vidx, tracks, res):
+        ref = oracle.synthesize(voices[vi], tr)
+        assert len(out) == len(ref) and not np.isnan(out).any()
+        assert full_scale_error(out, ref) <= 1e-9
+        if voices[vi]["glottal_pulse_tn_min"] == voices[vi]["glottal_pulse_tn_max"]:
+            assert np.array_equal(out, ref)
+
+
+def test_emulated_pipelined_kernel_control_rates(emu_v1, oracle):
+    v = default_voice("small_child")          # fs_int 35059: 35 / 70 / 105 / 140 steps per control period
+    tr = T.synthetic_track(9, 30)
+    for period in (1, 2, 3, 4):
+        out = emu_v1([v], [0], [tr], rate=1000.0 / period)[0]
+        assert np.array_equal(out, oracle.synthesize(v, tr, control_rate=1000.0 / period))

@@ -161,3 +161,24 @@ def test_full_size_track_properties(synth, oracle):
     assert full_scale_error(outs[5], ref) <= TOL
     assert snr_db(outs[5], ref) >= 100.0
     assert np.array_equal(outs[7], synth.synthesize(v, [tracks[7]])[0])
+
+
+def test_general_kernel_golden_vectors(synth, golden, monkeypatch):
+    # GTTS_KERNEL=v0 forces the general warp-per-utterance kernel (the one streaming uses) on batches
+    monkeypatch.setenv("GTTS_KERNEL", "v0")
+    for name in golden.names:
+        voice, track, ref, _ = golden.case(name)
+        out = synth.synthesize(voice, [track])[0]
+        assert len(out) == len(ref), name
+        assert full_scale_error(out, ref) <= TIGHT, name
+
+
+def test_both_kernels_agree_bitwise(synth, monkeypatch):
+    rng = np.random.Generator(np.random.PCG64(31))
+    voices = [default_voice("male"), random_voice(rng), default_voice("baby")]
+    tracks = [T.synthetic_track(300 + i, int(rng.integers(1, 120))) for i in range(23)]
+    vidx = [i % 3 for i in range(23)]
+    a = synth.synthesize(voices, tracks, voice_index=vidx)
+    monkeypatch.setenv("GTTS_KERNEL", "v0")
+    b = synth.synthesize(voices, tracks, voice_index=vidx)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
