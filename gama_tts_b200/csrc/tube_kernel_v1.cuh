@@ -47,7 +47,8 @@ struct SlotSm {
 	double thr[4][kRow];
 	double in[3][kRow];
 	double2 pab[2][kRow];         // {tapA * fric, tapB * fric}
-	double2 kab[2][6][kRow];      // per tube lane g < 6: {kA, kB}; kab[.][1].y = alpha left/right, kab[.][2].y = alpha upper
+	double2 kab[2][8][kRow];      // per tube lane g: {kA, kB} (lane 1: {k2, alpha left/right}; lanes 5-7 hold the fixed nasal k)
+	double au[2][kRow];           // alpha upper of the 3-way junction
 	double onepk7[3][kRow];
 	double endm[2][kRow], endn[2][kRow];
 	double rad[3][kRow];          // mouth radiation, nose radiation, throat outputs of one block
@@ -63,7 +64,9 @@ struct SlotSm {
 	int     it;                   // iteration counter of the current utterance; -1: idle
 	int     nblocks;
 	int     voice;
+	int     pad_[9];              // slot stride = 16 mod 128 bytes: the 7 slots start in different banks
 };
+static_assert(sizeof(SlotSm) % 128 == 16, "slot stride should be 16 mod 128 bytes (bank spreading); adjust pad_");
 
 struct CtaSm {
 	double2 tab[kSrcFilterLen];
@@ -311,10 +314,13 @@ GTTS_DEV void coef_task(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int lane, 
 		const int buf = b & 1;
 		S->kab[buf][0][lane] = make_double2(kcoef(r2[0], r2[1]), kcoef(r2[1], r2[2]));
 		S->kab[buf][1][lane] = make_double2(kcoef(r2[2], r2[3]), sum * r2[3]);
-		S->kab[buf][2][lane] = make_double2(kcoef(r2[3], r2[4]), sum * v2);
+		S->kab[buf][2][lane] = make_double2(kcoef(r2[3], r2[4]), 0.0);      // S6-S7 is a pure damped delay: k = 0
 		S->kab[buf][3][lane] = make_double2(kcoef(r2[4], r2[5]), kcoef(r2[5], r2[6]));
 		S->kab[buf][4][lane] = make_double2(kcoef(r2[6], r2[7]), k7);
-		S->kab[buf][5][lane] = make_double2(kcoef(v2, V.nr1_2), 0.0);
+		S->kab[buf][5][lane] = make_double2(kcoef(v2, V.nr1_2), V.nasal_k[1]);
+		S->kab[buf][6][lane] = make_double2(V.nasal_k[2], V.nasal_k[3]);
+		S->kab[buf][7][lane] = make_double2(V.nasal_k[4], V.nasal_k[5]);
+		S->au[buf][lane] = sum * v2;
 		S->onepk7[b % 3][lane] = 1.0 + k7;
 	}
 	__syncwarp();
@@ -365,37 +371,51 @@ GTTS_DEV void src_task(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int lane)
 }
 
 // ---- chain A (warp 2, lane = slot): oscillator phase (block it-1), frication bandpass (block it-3) ------
+// Both recurrences are stepped in one loop so that their latencies overlap; the operands of step j+1
+// are loaded while step j computes.  Lanes whose slot has no such block run on dummy data (their
+// results are never read), which keeps the loop free of divergent branches.
 struct ChainARegs { double pos; BandpassState bp; };
 
 GTTS_DEV void chain_a_iteration(CtaSm* C, const KernelParamsV1& P, int lane, ChainARegs& r)
 {
+	(void) P;
 	if (lane >= kSlots) return;
 	SlotSm* S = &C->slot[lane];
 	const int it = S->it;
-	if (it < 0) return;
 	const int b1 = it - 1, b3 = it - 3;
-	const bool do1 = b1 >= 0 && b1 < S->nblocks, do3 = b3 >= 0 && b3 < S->nblocks;
 	if (b1 == 0) r.pos = 0.0;
 	if (b3 == 0) { r.bp.x1 = r.bp.x2 = r.bp.y1 = r.bp.y2 = 0.0; }
-	const int nb1 = do1 ? block_len(*S, b1) : 0, nb3 = do3 ? block_len(*S, b3) : 0;
 	const int buf1 = b1 & 1, buf3 = b3 & 1;
+	const double* osc = S->osc[buf1];
+	double* p0 = S->pos[buf1][0];
+	double* p1 = S->pos[buf1][1];
+	const double* sig = S->sig[buf3];
+	const double* c0 = S->bp[buf3][0];
+	const double* c1 = S->bp[buf3][1];
+	const double* c2 = S->bp[buf3][2];
+	const double* ta = S->tapa[buf3];
+	const double* tb = S->tapb[buf3];
+	double2* pab = S->pab[buf3];
+	double pos = r.pos, x1 = r.bp.x1, x2 = r.bp.x2, y1 = r.bp.y1, y2 = r.bp.y2;
+	double n_inc = osc[0], n_x = sig[0], n_b0 = c0[0], n_a1 = c1[0], n_a2 = c2[0], n_ta = ta[0], n_tb = tb[0];
+#pragma unroll 4
 	for (int j = 0; j < kBlock; ++j) {
-		if (j < nb1) {
-			const double inc = S->osc[buf1][j];
-			double s = r.pos + inc;
-			r.pos = (s > 511.0) ? s - 512.0 : s;
-			S->pos[buf1][0][j] = r.pos;
-			s = r.pos + inc;
-			r.pos = (s > 511.0) ? s - 512.0 : s;
-			S->pos[buf1][1][j] = r.pos;
-		}
-		if (j < nb3) {
-			const double x = S->sig[buf3][j];
-			const double y = S->bp[buf3][0][j] * (x - r.bp.x2) - S->bp[buf3][1][j] * r.bp.y1 - S->bp[buf3][2][j] * r.bp.y2;
-			r.bp.x2 = r.bp.x1; r.bp.x1 = x; r.bp.y2 = r.bp.y1; r.bp.y1 = y;
-			S->pab[buf3][j] = make_double2(S->tapa[buf3][j] * y, S->tapb[buf3][j] * y);
-		}
+		const double inc = n_inc, x = n_x, b0 = n_b0, a1 = n_a1, a2 = n_a2, tA = n_ta, tB = n_tb;
+		n_inc = osc[j + 1]; n_x = sig[j + 1]; n_b0 = c0[j + 1]; n_a1 = c1[j + 1]; n_a2 = c2[j + 1];
+		n_ta = ta[j + 1]; n_tb = tb[j + 1];          // rows are padded: index 32 is readable
+		// WavetableGlottalSource.h:196-199, 265-272 (two half-sample increments, wrap above 511)
+		double s = pos + inc;
+		pos = (s > 511.0) ? s - 512.0 : s;
+		p0[j] = pos;
+		s = pos + inc;
+		pos = (s > 511.0) ? s - 512.0 : s;
+		p1[j] = pos;
+		// BandpassFilter.h:114-122
+		const double y = b0 * (x - x2) - a1 * y1 - a2 * y2;
+		x2 = x1; x1 = x; y2 = y1; y1 = y;
+		pab[j] = make_double2(tA * y, tB * y);
 	}
+	r.pos = pos; r.bp.x1 = x1; r.bp.x2 = x2; r.bp.y1 = y1; r.bp.y2 = y2;
 }
 
 // ---- chain B (warp 3, lane = slot * 4 + filter): radiation filters + throat lowpass of block it - 5 ------
@@ -408,14 +428,9 @@ struct ChainBRegs { double x1, y1; };
 GTTS_DEV void chain_b_iteration(CtaSm* C, const KernelParamsV1& P, int lane, ChainBRegs& r)
 {
 	const int s = lane >> 2, f = lane & 3;
-	int nb = 0, b = -1;
-	SlotSm* S = nullptr;
 	if (s < kSlots && f < 3) {
-		S = &C->slot[s];
-		b = S->it - 5;
-		if (S->it >= 0 && b >= 0 && b < S->nblocks) nb = block_len(*S, b);
-	}
-	if (nb > 0) {
+		SlotSm* S = &C->slot[s];
+		const int b = S->it - 5;
 		const VoiceDev& V = P.voices[S->voice];
 		if (b == 0) { r.x1 = 0.0; r.y1 = 0.0; }
 		const double b0 = f == 0 ? V.rad_m : (f == 1 ? V.rad_n : V.throat_b0);
@@ -424,15 +439,22 @@ GTTS_DEV void chain_b_iteration(CtaSm* C, const KernelParamsV1& P, int lane, Cha
 		const double gain = f == 2 ? V.throat_gain : 1.0;
 		const double onePlusN = 1.0 + V.nasal_k[5];
 		const double* in = f == 0 ? S->endm[b & 1] : (f == 1 ? S->endn[b & 1] : S->thr[b & 3]);
-		const double* scale = S->onepk7[b % 3];
-		for (int j = 0; j < nb; ++j) {
-			double x = in[j];
-			if (f == 0) x = scale[j] * x; else if (f == 1) x = onePlusN * x;
-			const double y = b0 * x + b1 * r.x1 - a1 * r.y1;
-			r.x1 = x;
-			r.y1 = y;
-			S->rad[f][j] = y * gain;
+		const double* scale = S->onepk7[(b % 3 + 3) % 3];
+		double* out = S->rad[f];
+		double x1 = r.x1, y1 = r.y1;
+		double n_in = in[0], n_sc = scale[0];
+#pragma unroll 4
+		for (int j = 0; j < kBlock; ++j) {
+			const double raw = n_in, sc = n_sc;
+			n_in = in[j + 1]; n_sc = scale[j + 1];
+			const double m = f == 0 ? sc : onePlusN;
+			const double x = f == 2 ? raw : m * raw;
+			const double y = b0 * x + b1 * x1 - a1 * y1;
+			x1 = x;
+			y1 = y;
+			out[j] = y * gain;
 		}
+		r.x1 = x1; r.y1 = y1;
 	}
 	__syncwarp();
 	// output sum, lane = sample: (mouth + nose) + throat (VocalTractModel0.h:657-660, 441)
@@ -454,87 +476,75 @@ GTTS_DEV void chain_b_iteration(CtaSm* C, const KernelParamsV1& P, int lane, Cha
 }
 
 // ---- tube warps (0, 1): block it - 4, four utterances per warp, 8 lanes each ----------------------------
+// Same cells and wiring as stage_tube in tube_kernel.cuh, but branch-free: every lane evaluates the three
+// kinds of B cell (2-port junction, 3-way junction, open end) and selects, so that the independent
+// chains overlap; the per-sample operands are prefetched one sample ahead.  Lanes of slots without a
+// block at this stage run on dummy data: their state is reset when their block 0 arrives.
 GTTS_DEV void tube_iteration(CtaSm* C, const KernelParamsV1& P, int warp, int lane, TubeLane& t)
 {
 	const int g = lane & 7;
 	const int slot = warp * 4 + (lane >> 3);
 	const int base = lane & ~7;
 	SlotSm* S = &C->slot[slot < kSlots ? slot : 0];
-	int nb = 0, b = -1;
-	if (slot < kSlots) {
-		b = S->it - 4;
-		if (S->it >= 0 && b >= 0 && b < S->nblocks) nb = block_len(*S, b);
-	}
+	const int b = (slot < kSlots) ? S->it - 4 : -1;
 	const VoiceDev& V = P.voices[S->voice];
 	if (b == 0) { t.aT = t.aB = t.bT = t.bB = t.extra = 0.0; }
 	const double d = V.damping;
-	// lane role constants (see tube_kernel.cuh: stage_tube)
+	const bool is3 = g == 1, isEnd = (g == 4) || (g == 7), isGlot = g == 0, isN0 = g == 5;
+	const bool storesEnd = isEnd && slot < kSlots;     // the 8th group of warp 1 is a dummy: it must not store
 	const int tapA = (g >= 1 && g <= 4) ? 2 * g - 1 : -100;
 	const int tapB = (g <= 3) ? 2 * g : -100;
-	const double constA = g == 6 ? V.nasal_k[2] : (g == 7 ? V.nasal_k[4] : 0.0);
-	const double constB = g == 5 ? V.nasal_k[1] : (g == 6 ? V.nasal_k[3] : (g == 7 ? V.nasal_k[5] : 0.0));
 	const double reflB0 = g == 4 ? V.refl_b0_m : V.refl_b0_n;
 	const double reflA1 = g == 4 ? V.refl_a1_m : V.refl_a1_n;
-	const int buf = b & 1;
-	const double2* kabRow = S->kab[buf][g < 6 ? g : 0];
-	const double* extraRow = (g == 0) ? S->in[(b % 3 + 3) % 3] : &S->kab[buf][2][0].y;   // g0: input, g1: alpha upper
-	const int extraStride = (g == 0) ? 1 : 2;
-	const int* ipRow = S->ip[(b % 3 + 3) % 3];
-	double* endRow = (g == 4) ? S->endm[buf] : S->endn[buf];
-	const int nbMax = __reduce_max_sync(0xffffffffu, nb);
-	for (int j = 0; j < nbMax; ++j) {
-		const bool on = j < nb;
-		const double2 kk = kabRow[j];
-		const double2 pab = S->pab[buf][j];
-		const int ip = ipRow[j];
-		const double ex = extraRow[j * extraStride];
-		const double kA = (g == 6 || g == 7) ? constA : kk.x;
-		const double kB = (g >= 5 || g == 2) ? constB : kk.y;
+	const int buf = b & 1, b3 = (b % 3 + 3) % 3;
+	const double2* kabRow = S->kab[buf][g];
+	const double2* pabRow = S->pab[buf];
+	const double* extraRow = isGlot ? S->in[b3] : S->au[buf];       // g0: tube input; g1: alpha upper
+	const int* ipRow = S->ip[b3];
+	double* endRow = (g == 7) ? S->endn[buf] : S->endm[buf];
+	const int srcPrev = base + ((g + 7) & 7), srcNext = base + ((g + 1) & 7), srcLink = base + (is3 ? 5 : 1);
+	double aT = t.aT, aB = t.aB, bT = t.bT, bB = t.bB, extra = t.extra;
+	double2 n_kk = kabRow[0], n_pab = pabRow[0];
+	double n_ex = extraRow[0];
+	int n_ip = ipRow[0];
+#pragma unroll 2
+	for (int j = 0; j < kBlock; ++j) {
+		const double2 kk = n_kk, pab = n_pab;
+		const double ex = n_ex;
+		const int ip = n_ip;
+		n_kk = kabRow[j + 1]; n_pab = pabRow[j + 1]; n_ex = extraRow[j + 1];
+		n_ip = ipRow[(j + 1) & 31];
 		const double tfA = (tapA == ip) ? pab.x : ((tapA == ip + 1) ? pab.y : 0.0);
 		const double tfB = (tapB == ip) ? pab.x : ((tapB == ip + 1) ? pab.y : 0.0);
-
-		const double dlA = kA * (t.aT - t.aB);
-		const double aTo = ((t.aT + dlA) * d) + tfA;
-		const double aBo = (t.aB + dlA) * d;
-
-		double bTo, bBo, linkOut = aBo, newExtra = t.extra;
-		if (g == 1) {
-			const double aL = kk.y, aU = ex;
-			const double jp = (aL * t.bT) + (aL * t.bB) + (aU * t.extra);
-			bBo = (jp - t.bT) * d;
-			bTo = ((jp - t.bB) * d) + tfB;
-			linkOut = (jp - t.extra) * d;
-		} else if (g == 4 || g == 7) {
-			if (on) endRow[j] = t.bT;
-			const double y = reflB0 * (kB * t.bT) - reflA1 * t.extra;
-			newExtra = y;
-			bBo = d * y;
-			bTo = 0.0;
-		} else {
-			const double dlB = kB * (t.bT - t.bB);
-			bTo = ((t.bT + dlB) * d) + tfB;
-			bBo = (t.bB + dlB) * d;
-		}
-		const double fromPrev = shfl_d(bTo, base + ((g + 7) & 7), 32);
-		const double fromNext = shfl_d(aBo, base + ((g + 1) & 7), 32);
-		const double link = shfl_d(linkOut, base + ((g == 1) ? 5 : 1), 32);
-		double nextAT = fromPrev;
-		if (g == 0) {
-			nextAT = (t.extra * d) + ex;
-			newExtra = aBo;
-		} else if (g == 5) {
-			nextAT = link;
-		} else if (g == 1) {
-			newExtra = link;
-		}
-		if (on) {
-			t.aT = nextAT;
-			t.aB = bBo;
-			t.bT = aTo;
-			t.bB = fromNext;
-			t.extra = newExtra;
-		}
+		// cell A: 2-port junction
+		const double dlA = kk.x * (aT - aB);
+		const double aTo = ((aT + dlA) * d) + tfA;
+		const double aBo = (aB + dlA) * d;
+		// cell B, 2-port junction
+		const double dlB = kk.y * (bT - bB);
+		const double tU = bT + dlB, tW = bB + dlB;
+		// cell B, 3-way junction (lane 1): bT = T[S4], bB = B[S5], extra = NB[N1]; kk.y = alpha, ex = alpha upper
+		const double jp = (kk.y * bT) + (kk.y * bB) + (ex * extra);
+		const double pU = jp - bB, pW = jp - bT, pX = jp - extra;
+		// cell B, open end (lanes 4, 7): reflection lowpass on k * T
+		const double y = reflB0 * (kk.y * bT) - reflA1 * extra;
+		if (storesEnd) endRow[j] = bT;
+		const double U = is3 ? pU : tU;
+		const double W = is3 ? pW : (isEnd ? y : tW);
+		const double bTo = (U * d) + tfB;
+		const double bBo = W * d;
+		const double linkOut = is3 ? pX * d : aBo;
+		const double fromPrev = shfl_d(bTo, srcPrev, 32);
+		const double fromNext = shfl_d(aBo, srcNext, 32);
+		const double link = shfl_d(linkOut, srcLink, 32);
+		const double glot = (extra * d) + ex;          // T[S1] = B[S1] d + input (lane 0)
+		extra = isGlot ? aBo : (is3 ? link : (isEnd ? y : extra));
+		aT = isGlot ? glot : (isN0 ? link : fromPrev);
+		aB = bBo;
+		bT = aTo;
+		bB = fromNext;
 	}
+	t.aT = aT; t.aB = aB; t.bT = bT; t.bB = bB; t.extra = extra;
 }
 
 // ---- slot bookkeeping (between the two barriers; warp 2, lane = slot) -----------------------------------

@@ -17,7 +17,7 @@
 #include <vector>
 #include <ucontext.h>
 
-struct double2 { double x, y; };
+struct alignas(16) double2 { double x, y; };
 struct float4 { float x, y, z, w; };
 struct float2 { float x, y; };
 
