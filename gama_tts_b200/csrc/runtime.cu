@@ -128,10 +128,34 @@ int launchBatch(gtts_batch* b, const float* dFrames, float* dOut, cudaStream_t s
 		Q.src_tab = b->h->d_src_tab;
 		Q.queue = b->d_queue;
 		Q.n_utt = static_cast<int32_t>(nUtt);
+		Q.prof = nullptr;
 		const int64_t ctasWanted = (nUtt + v1::kSlots - 1) / v1::kSlots;
 		const int grid = static_cast<int>(std::min<int64_t>(ctasWanted, b->h->sms));
+		const bool profile = std::getenv("GTTS_PROFILE") != nullptr;
+		long long* dProf = nullptr;
+		if (profile) {
+			GTTS_CUDA(cudaMalloc(&dProf, sizeof(long long) * grid * (v1::kWarps + 1)));
+			GTTS_CUDA(cudaMemsetAsync(dProf, 0, sizeof(long long) * grid * (v1::kWarps + 1), stream));
+			Q.prof = dProf;
+		}
 		v1::tube_kernel_v1<<<grid, v1::kThreads, v1::smem_bytes(), stream>>>(Q);
 		GTTS_CUDA(cudaGetLastError());
+		if (profile) {
+			// debugging aid: busy cycles per warp role and iteration, averaged over the CTAs
+			std::vector<long long> hp(static_cast<size_t>(grid) * (v1::kWarps + 1));
+			GTTS_CUDA(cudaStreamSynchronize(stream));
+			GTTS_CUDA(cudaMemcpy(hp.data(), dProf, sizeof(long long) * hp.size(), cudaMemcpyDeviceToHost));
+			cudaFree(dProf);
+			double sum[v1::kWarps] = {0};
+			double iters = 0;
+			for (int c = 0; c < grid; ++c) {
+				for (int w = 0; w < v1::kWarps; ++w) sum[w] += static_cast<double>(hp[static_cast<size_t>(c) * (v1::kWarps + 1) + w]);
+				iters += static_cast<double>(hp[static_cast<size_t>(c) * (v1::kWarps + 1) + v1::kWarps]);
+			}
+			std::fprintf(stderr, "[gtts profile] grid %d, iterations per CTA %.0f; busy cycles per iteration by warp:", grid, iters / grid);
+			for (int w = 0; w < v1::kWarps; ++w) std::fprintf(stderr, " %d:%.0f", w, sum[w] / (iters > 0 ? iters : 1));
+			std::fprintf(stderr, "\n");
+		}
 		b->last_kernel = "tube_kernel_v1";
 	} else {
 		const int64_t ctasWanted = (nUtt + kWarpsPerCta - 1) / kWarpsPerCta;

@@ -86,7 +86,14 @@ struct KernelParamsV1 {
 	const double2* src_tab;
 	int32_t* queue;
 	int32_t n_utt;
+	long long* prof;              // optional [grid][kWarps + 1]: busy cycles per warp + iteration count (GTTS_PROFILE=1)
 };
+
+#ifndef GTTS_EMU
+#define GTTS_CLOCK() clock64()
+#else
+#define GTTS_CLOCK() 0ll
+#endif
 
 GTTS_DEV int block_len(const SlotSm& s, int b)
 {
@@ -596,7 +603,9 @@ GTTS_DEV void tube_v1_cta_body(const KernelParamsV1& P, unsigned char* smem, int
 	ChainBRegs cb = {0.0, 0.0};
 	HelperRegs hr = {0.f, 0.f, 0, 0, 0.7892347, 0.0};
 
+	long long busy = 0, iters = 0;
 	while (C->live) {
+		const long long tStart = GTTS_CLOCK();
 		if (warp < kTubeWarps) {
 			tube_iteration(C, P, warp, lane, tl);
 		} else if (warp == kChainAWarp) {
@@ -618,10 +627,18 @@ GTTS_DEV void tube_v1_cta_body(const KernelParamsV1& P, unsigned char* smem, int
 				else coef_task(C, S, P, lane, warp - kPool0);
 			}
 		}
+		busy += GTTS_CLOCK() - tStart;
+		iters += 1;
 		__syncthreads();
 		if (warp == kChainAWarp) schedule_slots(C, P, lane);
 		__syncthreads();
 	}
+#ifndef GTTS_EMU
+	if (P.prof != nullptr && lane == 0) {
+		P.prof[(size_t) blockIdx.x * (kWarps + 1) + warp] = busy;
+		if (warp == 0) P.prof[(size_t) blockIdx.x * (kWarps + 1) + kWarps] = iters;
+	}
+#endif
 }
 
 #ifndef GTTS_EMU
