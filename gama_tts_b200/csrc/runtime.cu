@@ -129,6 +129,8 @@ int launchBatch(gtts_batch* b, const float* dFrames, float* dOut, cudaStream_t s
 		Q.queue = b->d_queue;
 		Q.n_utt = static_cast<int32_t>(nUtt);
 		Q.prof = nullptr;
+		Q.debug_skip = 0;
+		if (const char* dbg = std::getenv("GTTS_DEBUG_SKIP")) Q.debug_skip = std::atoi(dbg);   // experiments only: wrong output
 		const int64_t ctasWanted = (nUtt + v1::kSlots - 1) / v1::kSlots;
 		const int grid = static_cast<int>(std::min<int64_t>(ctasWanted, b->h->sms));
 		const bool profile = std::getenv("GTTS_PROFILE") != nullptr;

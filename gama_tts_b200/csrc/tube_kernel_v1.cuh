@@ -53,7 +53,7 @@ struct SlotSm {
 	double endm[2][kRow], endn[2][kRow];
 	double rad[3][kRow];          // mouth radiation, nose radiation, throat outputs of one block
 	double ve[kVRing], vo[kVRing];
-	double xring[kSrcRing];
+	double xring[2 * kSrcRing];   // tube output ring, every sample stored twice (i and i + 128): any 26-sample window is contiguous
 	float  cur[kBlock][8];        // slot helper scratch: parameters 0..6 of the block being converted
 	int    ip[3][kBlock];
 	// coefficient-walk cursor (parameters 7..15), advanced by whichever pool warp runs the task
@@ -71,7 +71,7 @@ static_assert(sizeof(SlotSm) % 128 == 16, "slot stride should be 16 mod 128 byte
 struct CtaSm {
 	double2 tab[kSrcFilterLen];
 	SlotSm slot[kSlots];
-	float  pscratch[kPoolWarps][kBlock][10];   // pool scratch: parameters 7..15 of one block
+	float  pscratch[kSlots][kBlock][10];      // per-slot scratch of the coefficient task: parameters 7..15 of one block
 	int    task_counter;
 	int    live;                  // number of slots with work
 };
@@ -86,6 +86,7 @@ struct KernelParamsV1 {
 	const double2* src_tab;
 	int32_t* queue;
 	int32_t n_utt;
+	int32_t debug_skip;           // experiments only (GTTS_DEBUG_SKIP): bit0 no SRC, bit1 no coef task, bit2 no helper, bit3 no chain A, bit4 no chain B, bit5 no tube
 	long long* prof;              // optional [grid][kWarps + 1]: busy cycles per warp + iteration count (GTTS_PROFILE=1)
 };
 
@@ -165,7 +166,7 @@ GTTS_DEV void helper_iteration(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int
 	if (it == 0) {
 		// new utterance: clear the rings, reset cursors and the noise generator
 		for (int i = lane; i < kVRing; i += 32) { S->ve[i] = 0.0; S->vo[i] = 0.0; }
-		for (int i = lane; i < kSrcRing; i += 32) S->xring[i] = 0.0;
+		for (int i = lane; i < 2 * kSrcRing; i += 32) S->xring[i] = 0.0;
 		if (lane < 7) cursor_init(frames, nFrames, S->U.inv_steps, lane, h.cur, h.delta);
 		h.off = 0; h.frame = 0;
 		h.seed = 0.7892347; h.noise_x1 = 0.0;
@@ -286,14 +287,14 @@ GTTS_DEV void helper_iteration(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int
 }
 
 // ---- pool task: junction coefficients of block b = it - 3 (VocalTractModel0.h:484-512, 698-716) ---------
-GTTS_DEV void coef_task(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int lane, int poolWarp)
+GTTS_DEV void coef_task(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int lane, int slotIndex)
 {
 	const int b = S->it - 3;
 	if (S->it < 0 || b < 0 || b >= S->nblocks) return;
 	const VoiceDev& V = P.voices[S->voice];
 	const float* frames = P.frames + S->U.frame_begin * kNumParams;
 	const int nb = block_len(*S, b);
-	float (*scr)[10] = C->pscratch[poolWarp];
+	float (*scr)[10] = C->pscratch[slotIndex];
 	{
 		float cur = 0.f, delta = 0.f;
 		int off = S->coff, frame = S->cframe;
@@ -347,33 +348,49 @@ GTTS_DEV void src_task(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int lane)
 	if (b == S->nblocks - 1) k1 = S->U.n_out;          // flush: chain B appended the 26 zeros
 	if (k1 > S->U.n_out) k1 = S->U.n_out;
 	float* out = P.out + S->U.out_begin;
-	for (long long k = k0 + lane; k < k1; k += 32) {
-		const unsigned long long t = (unsigned long long) k * inc;
-		const int e = (int) (t >> 16);
-		const unsigned f = (unsigned) (t & 0xFFFFu);
-		double acc = 0.0;
-		{
-			const double interp = (double) (f & 0xFFu) / 256;
-			const unsigned L = f >> 8;
+	// Up to 96 outputs per block (ratio < 3): each lane carries three independent accumulator chains
+	// (outputs k, k + 32, k + 64) so that the 52 dependent multiply-adds of one output overlap with the
+	// other two; every chain still sums its own taps in the reference's order (left wing, then right).
+	for (long long kb = k0; kb < k1; kb += 96) {
+		double acc[3] = {0.0, 0.0, 0.0};
+		double interpL[3], interpR[3];
+		const double2* tabL[3];
+		const double2* tabR[3];
+		const double* xw[3];
+		long long kk[3];
 #pragma unroll
-			for (int j = 0; j < kSrcZeroCrossings; ++j) {
-				const double2 c = C->tab[L + 256 * j];
-				const double x = S->xring[(e - 13 - j) & (kSrcRing - 1)];
-				acc += (x * (c.x + (c.y * interp)));
-			}
-		}
-		{
+		for (int o = 0; o < 3; ++o) {
+			kk[o] = kb + lane + 32 * o;
+			const unsigned long long t = (unsigned long long) kk[o] * inc;
+			const int e = (int) (t >> 16);
+			const unsigned f = (unsigned) (t & 0xFFFFu);
 			const unsigned gph = (~f) & 0xFFFFu;
-			const double interp = (double) (gph & 0xFFu) / 256;
-			const unsigned L = gph >> 8;
+			interpL[o] = (double) (f & 0xFFu) / 256;
+			interpR[o] = (double) (gph & 0xFFu) / 256;
+			tabL[o] = C->tab + (f >> 8);
+			tabR[o] = C->tab + (gph >> 8);
+			xw[o] = S->xring + ((e - 25) & (kSrcRing - 1));      // window [e-25, e], contiguous in the doubled ring
+		}
 #pragma unroll
-			for (int j = 0; j < kSrcZeroCrossings; ++j) {
-				const double2 c = C->tab[L + 256 * j];
-				const double x = S->xring[(e - 12 + j) & (kSrcRing - 1)];
-				acc += (x * (c.x + (c.y * interp)));
+		for (int j = 0; j < kSrcZeroCrossings; ++j) {
+#pragma unroll
+			for (int o = 0; o < 3; ++o) {
+				const double2 c = tabL[o][256 * j];
+				const double x = xw[o][12 - j];                     // x[e - 13 - j]
+				acc[o] += (x * (c.x + (c.y * interpL[o])));
 			}
 		}
-		out[k] = (float) acc;
+#pragma unroll
+		for (int j = 0; j < kSrcZeroCrossings; ++j) {
+#pragma unroll
+			for (int o = 0; o < 3; ++o) {
+				const double2 c = tabR[o][256 * j];
+				const double x = xw[o][13 + j];                     // x[e - 12 + j]
+				acc[o] += (x * (c.x + (c.y * interpR[o])));
+			}
+		}
+#pragma unroll
+		for (int o = 0; o < 3; ++o) if (kk[o] < k1) out[kk[o]] = (float) acc[o];
 	}
 }
 
@@ -404,23 +421,37 @@ GTTS_DEV void chain_a_iteration(CtaSm* C, const KernelParamsV1& P, int lane, Cha
 	const double* tb = S->tapb[buf3];
 	double2* pab = S->pab[buf3];
 	double pos = r.pos, x1 = r.bp.x1, x2 = r.bp.x2, y1 = r.bp.y1, y2 = r.bp.y2;
-	double n_inc = osc[0], n_x = sig[0], n_b0 = c0[0], n_a1 = c1[0], n_a2 = c2[0], n_ta = ta[0], n_tb = tb[0];
-#pragma unroll 4
-	for (int j = 0; j < kBlock; ++j) {
-		const double inc = n_inc, x = n_x, b0 = n_b0, a1 = n_a1, a2 = n_a2, tA = n_ta, tB = n_tb;
-		n_inc = osc[j + 1]; n_x = sig[j + 1]; n_b0 = c0[j + 1]; n_a1 = c1[j + 1]; n_a2 = c2[j + 1];
-		n_ta = ta[j + 1]; n_tb = tb[j + 1];          // rows are padded: index 32 is readable
-		// WavetableGlottalSource.h:196-199, 265-272 (two half-sample increments, wrap above 511)
-		double s = pos + inc;
-		pos = (s > 511.0) ? s - 512.0 : s;
-		p0[j] = pos;
-		s = pos + inc;
-		pos = (s > 511.0) ? s - 512.0 : s;
-		p1[j] = pos;
-		// BandpassFilter.h:114-122
-		const double y = b0 * (x - x2) - a1 * y1 - a2 * y2;
-		x2 = x1; x1 = x; y2 = y1; y1 = y;
-		pab[j] = make_double2(tA * y, tB * y);
+	// chunks of 4 samples: all operands of a chunk are loaded into registers before the two recurrences
+	// are stepped, so that shared-memory latency is paid once per chunk instead of once per sample
+	for (int j0 = 0; j0 < kBlock; j0 += 4) {
+		double inc[4], x[4], b0[4], a1[4], a2[4], tA[4], tB[4];
+#pragma unroll
+		for (int q = 0; q < 4; ++q) {
+			inc[q] = osc[j0 + q]; x[q] = sig[j0 + q]; b0[q] = c0[j0 + q]; a1[q] = c1[j0 + q]; a2[q] = c2[j0 + q];
+			tA[q] = ta[j0 + q]; tB[q] = tb[j0 + q];
+		}
+		double o0[4], o1[4], oa[4], ob[4];
+#pragma unroll
+		for (int q = 0; q < 4; ++q) {
+			// WavetableGlottalSource.h:196-199, 265-272 (two half-sample increments, wrap above 511)
+			double s = pos + inc[q];
+			pos = (s > 511.0) ? s - 512.0 : s;
+			o0[q] = pos;
+			s = pos + inc[q];
+			pos = (s > 511.0) ? s - 512.0 : s;
+			o1[q] = pos;
+			// BandpassFilter.h:114-122
+			const double y = b0[q] * (x[q] - x2) - a1[q] * y1 - a2[q] * y2;
+			x2 = x1; x1 = x[q]; y2 = y1; y1 = y;
+			oa[q] = tA[q] * y;
+			ob[q] = tB[q] * y;
+		}
+#pragma unroll
+		for (int q = 0; q < 4; ++q) {
+			p0[j0 + q] = o0[q];
+			p1[j0 + q] = o1[q];
+			pab[j0 + q] = make_double2(oa[q], ob[q]);
+		}
 	}
 	r.pos = pos; r.bp.x1 = x1; r.bp.x2 = x2; r.bp.y1 = y1; r.bp.y2 = y2;
 }
@@ -449,17 +480,21 @@ GTTS_DEV void chain_b_iteration(CtaSm* C, const KernelParamsV1& P, int lane, Cha
 		const double* scale = S->onepk7[(b % 3 + 3) % 3];
 		double* out = S->rad[f];
 		double x1 = r.x1, y1 = r.y1;
-		double n_in = in[0], n_sc = scale[0];
-#pragma unroll 4
-		for (int j = 0; j < kBlock; ++j) {
-			const double raw = n_in, sc = n_sc;
-			n_in = in[j + 1]; n_sc = scale[j + 1];
-			const double m = f == 0 ? sc : onePlusN;
-			const double x = f == 2 ? raw : m * raw;
-			const double y = b0 * x + b1 * x1 - a1 * y1;
-			x1 = x;
-			y1 = y;
-			out[j] = y * gain;
+		for (int j0 = 0; j0 < kBlock; j0 += 8) {
+			double raw[8], sc[8], o[8];
+#pragma unroll
+			for (int q = 0; q < 8; ++q) { raw[q] = in[j0 + q]; sc[q] = scale[j0 + q]; }
+#pragma unroll
+			for (int q = 0; q < 8; ++q) {
+				const double m = f == 0 ? sc[q] : onePlusN;
+				const double x = f == 2 ? raw[q] : m * raw[q];
+				const double y = b0 * x + b1 * x1 - a1 * y1;
+				x1 = x;
+				y1 = y;
+				o[q] = y * gain;
+			}
+#pragma unroll
+			for (int q = 0; q < 8; ++q) out[j0 + q] = o[q];
 		}
 		r.x1 = x1; r.y1 = y1;
 	}
@@ -473,11 +508,15 @@ GTTS_DEV void chain_b_iteration(CtaSm* C, const KernelParamsV1& P, int lane, Cha
 		const long long n0 = (long long) qb * kBlock;
 		if (lane < qn) {
 			const int idx = (int) ((n0 + lane) & (kSrcRing - 1));
-			Q->xring[idx] = (Q->rad[0][lane] + Q->rad[1][lane]) + Q->rad[2][lane];
+			const double v = (Q->rad[0][lane] + Q->rad[1][lane]) + Q->rad[2][lane];
+			Q->xring[idx] = v;
+			Q->xring[idx + kSrcRing] = v;
 		}
 		if (qb == Q->nblocks - 1 && lane < 2 * kSrcZeroCrossings) {
 			// flushBuffer(): 26 zeros after the last input (SampleRateConverter.h:462-471)
-			Q->xring[(Q->U.n_internal + lane) & (kSrcRing - 1)] = 0.0;
+			const int idx = (int) ((Q->U.n_internal + lane) & (kSrcRing - 1));
+			Q->xring[idx] = 0.0;
+			Q->xring[idx + kSrcRing] = 0.0;
 		}
 	}
 }
@@ -511,45 +550,50 @@ GTTS_DEV void tube_iteration(CtaSm* C, const KernelParamsV1& P, int warp, int la
 	double* endRow = (g == 7) ? S->endn[buf] : S->endm[buf];
 	const int srcPrev = base + ((g + 7) & 7), srcNext = base + ((g + 1) & 7), srcLink = base + (is3 ? 5 : 1);
 	double aT = t.aT, aB = t.aB, bT = t.bT, bB = t.bB, extra = t.extra;
-	double2 n_kk = kabRow[0], n_pab = pabRow[0];
-	double n_ex = extraRow[0];
-	int n_ip = ipRow[0];
-#pragma unroll 2
-	for (int j = 0; j < kBlock; ++j) {
-		const double2 kk = n_kk, pab = n_pab;
-		const double ex = n_ex;
-		const int ip = n_ip;
-		n_kk = kabRow[j + 1]; n_pab = pabRow[j + 1]; n_ex = extraRow[j + 1];
-		n_ip = ipRow[(j + 1) & 31];
-		const double tfA = (tapA == ip) ? pab.x : ((tapA == ip + 1) ? pab.y : 0.0);
-		const double tfB = (tapB == ip) ? pab.x : ((tapB == ip + 1) ? pab.y : 0.0);
-		// cell A: 2-port junction
-		const double dlA = kk.x * (aT - aB);
-		const double aTo = ((aT + dlA) * d) + tfA;
-		const double aBo = (aB + dlA) * d;
-		// cell B, 2-port junction
-		const double dlB = kk.y * (bT - bB);
-		const double tU = bT + dlB, tW = bB + dlB;
-		// cell B, 3-way junction (lane 1): bT = T[S4], bB = B[S5], extra = NB[N1]; kk.y = alpha, ex = alpha upper
-		const double jp = (kk.y * bT) + (kk.y * bB) + (ex * extra);
-		const double pU = jp - bB, pW = jp - bT, pX = jp - extra;
-		// cell B, open end (lanes 4, 7): reflection lowpass on k * T
-		const double y = reflB0 * (kk.y * bT) - reflA1 * extra;
-		if (storesEnd) endRow[j] = bT;
-		const double U = is3 ? pU : tU;
-		const double W = is3 ? pW : (isEnd ? y : tW);
-		const double bTo = (U * d) + tfB;
-		const double bBo = W * d;
-		const double linkOut = is3 ? pX * d : aBo;
-		const double fromPrev = shfl_d(bTo, srcPrev, 32);
-		const double fromNext = shfl_d(aBo, srcNext, 32);
-		const double link = shfl_d(linkOut, srcLink, 32);
-		const double glot = (extra * d) + ex;          // T[S1] = B[S1] d + input (lane 0)
-		extra = isGlot ? aBo : (is3 ? link : (isEnd ? y : extra));
-		aT = isGlot ? glot : (isN0 ? link : fromPrev);
-		aB = bBo;
-		bT = aTo;
-		bB = fromNext;
+	for (int j0 = 0; j0 < kBlock; j0 += 4) {
+		// operands of 4 samples into registers first (one shared-memory latency per chunk)
+		double2 kkv[4], pabv[4];
+		double exv[4];
+		int ipv[4];
+#pragma unroll
+		for (int q = 0; q < 4; ++q) {
+			kkv[q] = kabRow[j0 + q]; pabv[q] = pabRow[j0 + q]; exv[q] = extraRow[j0 + q]; ipv[q] = ipRow[j0 + q];
+		}
+#pragma unroll
+		for (int q = 0; q < 4; ++q) {
+			const double2 kk = kkv[q], pab = pabv[q];
+			const double ex = exv[q];
+			const int ip = ipv[q];
+			const double tfA = (tapA == ip) ? pab.x : ((tapA == ip + 1) ? pab.y : 0.0);
+			const double tfB = (tapB == ip) ? pab.x : ((tapB == ip + 1) ? pab.y : 0.0);
+			// cell A: 2-port junction
+			const double dlA = kk.x * (aT - aB);
+			const double aTo = ((aT + dlA) * d) + tfA;
+			const double aBo = (aB + dlA) * d;
+			// cell B, 2-port junction
+			const double dlB = kk.y * (bT - bB);
+			const double tU = bT + dlB, tW = bB + dlB;
+			// cell B, 3-way junction (lane 1): bT = T[S4], bB = B[S5], extra = NB[N1]; kk.y = alpha, ex = alpha upper
+			const double jp = (kk.y * bT) + (kk.y * bB) + (ex * extra);
+			const double pU = jp - bB, pW = jp - bT, pX = jp - extra;
+			// cell B, open end (lanes 4, 7): reflection lowpass on k * T
+			const double y = reflB0 * (kk.y * bT) - reflA1 * extra;
+			if (storesEnd) endRow[j0 + q] = bT;
+			const double U = is3 ? pU : tU;
+			const double W = is3 ? pW : (isEnd ? y : tW);
+			const double bTo = (U * d) + tfB;
+			const double bBo = W * d;
+			const double linkOut = is3 ? pX * d : aBo;
+			const double fromPrev = shfl_d(bTo, srcPrev, 32);
+			const double fromNext = shfl_d(aBo, srcNext, 32);
+			const double link = shfl_d(linkOut, srcLink, 32);
+			const double glot = (extra * d) + ex;          // T[S1] = B[S1] d + input (lane 0)
+			extra = isGlot ? aBo : (is3 ? link : (isEnd ? y : extra));
+			aT = isGlot ? glot : (isN0 ? link : fromPrev);
+			aB = bBo;
+			bT = aTo;
+			bB = fromNext;
+		}
 	}
 	t.aT = aT; t.aB = aB; t.bT = bT; t.bB = bB; t.extra = extra;
 }
@@ -606,25 +650,28 @@ GTTS_DEV void tube_v1_cta_body(const KernelParamsV1& P, unsigned char* smem, int
 	long long busy = 0, iters = 0;
 	while (C->live) {
 		const long long tStart = GTTS_CLOCK();
+		const int skip = P.debug_skip;
 		if (warp < kTubeWarps) {
-			tube_iteration(C, P, warp, lane, tl);
-		} else if (warp == kChainAWarp) {
-			chain_a_iteration(C, P, lane, ca);
-		} else if (warp == kChainBWarp) {
-			chain_b_iteration(C, P, lane, cb);
-		} else if (warp < kPool0) {
-			SlotSm* S = &C->slot[warp - kHelper0];
-			helper_iteration(C, S, P, lane, hr);
+			if (!(skip & 32)) tube_iteration(C, P, warp, lane, tl);
 		} else {
-			// pool: 2 tasks per slot (SRC first: it is the longer one), pulled from a shared counter
+			if (warp == kChainAWarp) {
+				if (!(skip & 8)) chain_a_iteration(C, P, lane, ca);
+			} else if (warp == kChainBWarp) {
+				if (!(skip & 16)) chain_b_iteration(C, P, lane, cb);
+			} else if (warp < kPool0) {
+				SlotSm* S = &C->slot[warp - kHelper0];
+				if (!(skip & 4)) helper_iteration(C, S, P, lane, hr);
+			}
+			// task queue: 2 tasks per slot (SRC first: it is the longer one).  Every warp that is done with
+			// its fixed role helps, which balances the load whatever the mix of voices and block phases.
 			for (;;) {
 				int task = 0;
 				if (lane == 0) task = atomicAdd(&C->task_counter, 1);
 				task = __shfl_sync(0xffffffffu, task, 0, 32);
 				if (task >= 2 * kSlots) break;
 				SlotSm* S = &C->slot[task % kSlots];
-				if (task < kSlots) src_task(C, S, P, lane);
-				else coef_task(C, S, P, lane, warp - kPool0);
+				if (task < kSlots) { if (!(skip & 1)) src_task(C, S, P, lane); }
+				else if (!(skip & 2)) coef_task(C, S, P, lane, task % kSlots);
 			}
 		}
 		busy += GTTS_CLOCK() - tStart;

@@ -108,6 +108,7 @@ extern "C" int emu_batch_v1(const gtts_voice_config* voices, int n_voices, const
 	P.queue = &queue;
 	P.n_utt = static_cast<int32_t>(n_utt);
 	P.prof = nullptr;
+	P.debug_skip = 0;
 
 	std::vector<unsigned char> smem(v1::smem_bytes() + 64);
 	unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem.data()) + 15) & ~uintptr_t(15));
