@@ -74,6 +74,9 @@ struct CtaSm {
 	float  pscratch[kSlots][kBlock][10];      // per-slot scratch of the coefficient task: parameters 7..15 of one block
 	int    task_counter;
 	int    live;                  // number of slots with work
+	int    src_shared;            // 1: every slot in the SRC stage is at the same block of an equally long utterance of the same rate
+	int    src_mask;              // slots with a block in the SRC stage
+	int    src_tasks;             // SRC tasks in the queue this iteration
 };
 
 struct KernelParamsV1 {
@@ -394,6 +397,61 @@ GTTS_DEV void src_task(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int lane)
 	}
 }
 
+// ---- pool task: SRC of 32 outputs for ALL slots at once (slots aligned: same rate, same block) ---------
+// When the slots step equally long utterances of one voice in lockstep (the batch case), output k of
+// every slot has the same phase, hence the same 26 interpolated coefficients h + deltaH * frac: they are
+// fetched and formed once and applied to each slot's own window.  This divides the coefficient traffic
+// (the dominant shared-memory load of the whole kernel) by the number of slots; each slot's sum still
+// runs over its own taps in the reference's order.
+GTTS_DEV void src_shared_task(CtaSm* C, const KernelParamsV1& P, int lane, int pass)
+{
+	const int mask = C->src_mask;
+	int ref = 0;
+	while (!((mask >> ref) & 1)) ++ref;
+	const SlotSm* R = &C->slot[ref];
+	const int b = R->it - kStages;
+	const VoiceDev& V = P.voices[R->voice];
+	const long long nStart = (long long) b * kBlock;
+	const long long nEnd = nStart + block_len(*R, b);
+	const unsigned inc = V.src_inc;
+	const long long k0 = (long long) ((((unsigned long long) nStart << 16) + inc - 1) / inc);
+	long long k1 = (long long) ((((unsigned long long) nEnd << 16) + inc - 1) / inc);
+	if (b == R->nblocks - 1) k1 = R->U.n_out;
+	if (k1 > R->U.n_out) k1 = R->U.n_out;
+	const long long k = k0 + 32ll * pass + lane;
+	const unsigned long long t = (unsigned long long) k * inc;
+	const int e = (int) (t >> 16);
+	const unsigned f = (unsigned) (t & 0xFFFFu);
+	const unsigned gph = (~f) & 0xFFFFu;
+	const double interpL = (double) (f & 0xFFu) / 256, interpR = (double) (gph & 0xFFu) / 256;
+	const double2* tabL = C->tab + (f >> 8);
+	const double2* tabR = C->tab + (gph >> 8);
+	const int woff = (e - 25) & (kSrcRing - 1);
+	double acc[kSlots];
+#pragma unroll
+	for (int q = 0; q < kSlots; ++q) acc[q] = 0.0;
+#pragma unroll
+	for (int j = 0; j < kSrcZeroCrossings; ++j) {
+		const double2 c = tabL[256 * j];
+		const double cc = c.x + (c.y * interpL);
+#pragma unroll
+		for (int q = 0; q < kSlots; ++q) acc[q] += (C->slot[q].xring[woff + 12 - j] * cc);
+	}
+#pragma unroll
+	for (int j = 0; j < kSrcZeroCrossings; ++j) {
+		const double2 c = tabR[256 * j];
+		const double cc = c.x + (c.y * interpR);
+#pragma unroll
+		for (int q = 0; q < kSlots; ++q) acc[q] += (C->slot[q].xring[woff + 13 + j] * cc);
+	}
+	if (k < k1) {
+#pragma unroll
+		for (int q = 0; q < kSlots; ++q) {
+			if ((mask >> q) & 1) P.out[C->slot[q].U.out_begin + k] = (float) acc[q];
+		}
+	}
+}
+
 // ---- chain A (warp 2, lane = slot): oscillator phase (block it-1), frication bandpass (block it-3) ------
 // Both recurrences are stepped in one loop so that their latencies overlap; the operands of step j+1
 // are loaded while step j computes.  Lanes whose slot has no such block run on dummy data (their
@@ -628,7 +686,45 @@ GTTS_DEV void schedule_slots(CtaSm* C, const KernelParamsV1& P, int lane)
 		alive = S->it >= 0;
 	}
 	const unsigned any = __ballot_sync(0xffffffffu, alive);
-	if (lane == 0) { C->live = any != 0; C->task_counter = 0; }
+	// SRC stage alignment: all slots that have a block at it - 6 are at the same block of equally long
+	// utterances with the same SRC increment -> one shared SRC task per 32 outputs
+	int valid = 0, it = 0;
+	long long nInternal = 0;
+	unsigned inc = 0;
+	if (lane < kSlots) {
+		const SlotSm* S = &C->slot[lane];
+		it = S->it;
+		valid = it >= 0 && it - kStages >= 0 && it - kStages < S->nblocks;
+		if (valid) { nInternal = S->U.n_internal; inc = P.voices[S->voice].src_inc; }
+	}
+	const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+	int refLane = 0;
+	while (refLane < 31 && !((vmask >> refLane) & 1)) ++refLane;
+	const int itRef = __shfl_sync(0xffffffffu, it, refLane, 32);
+	const long long nRef = __shfl_sync(0xffffffffu, nInternal, refLane, 32);
+	const unsigned incRef = __shfl_sync(0xffffffffu, inc, refLane, 32);
+	const int same = !valid || (it == itRef && nInternal == nRef && inc == incRef);
+	const unsigned allSame = __ballot_sync(0xffffffffu, same) == 0xffffffffu;
+	if (lane == 0) {
+		C->live = any != 0;
+		C->task_counter = 0;
+		C->src_mask = (int) vmask;
+		const int nValid = __popc(vmask);
+		C->src_shared = (allSame && nValid >= 2) ? 1 : 0;
+		int nTasks = kSlots;
+		if (C->src_shared) {
+			const SlotSm* R = &C->slot[refLane];
+			const int b = R->it - kStages;
+			const long long nStart = (long long) b * kBlock;
+			const long long nEnd = nStart + block_len(*R, b);
+			const long long k0 = (long long) ((((unsigned long long) nStart << 16) + incRef - 1) / incRef);
+			long long k1 = (long long) ((((unsigned long long) nEnd << 16) + incRef - 1) / incRef);
+			if (b == R->nblocks - 1) k1 = R->U.n_out;
+			if (k1 > R->U.n_out) k1 = R->U.n_out;
+			nTasks = (int) ((k1 - k0 + 31) / 32);
+		}
+		C->src_tasks = nTasks;
+	}
 }
 
 GTTS_DEV void tube_v1_cta_body(const KernelParamsV1& P, unsigned char* smem, int tid)
@@ -637,7 +733,7 @@ GTTS_DEV void tube_v1_cta_body(const KernelParamsV1& P, unsigned char* smem, int
 	const int warp = tid >> 5, lane = tid & 31;
 	for (int i = tid; i < kSrcFilterLen; i += kThreads) C->tab[i] = P.src_tab[i];
 	if (tid < kSlots) { C->slot[tid].it = -1; C->slot[tid].voice = 0; C->slot[tid].nblocks = 0; }
-	if (tid == 0) { C->live = 0; C->task_counter = 0; }
+	if (tid == 0) { C->live = 0; C->task_counter = 0; C->src_shared = 0; C->src_mask = 0; C->src_tasks = kSlots; }
 	__syncthreads();
 	if (warp == kChainAWarp) schedule_slots(C, P, lane);
 	__syncthreads();
@@ -668,10 +764,16 @@ GTTS_DEV void tube_v1_cta_body(const KernelParamsV1& P, unsigned char* smem, int
 				int task = 0;
 				if (lane == 0) task = atomicAdd(&C->task_counter, 1);
 				task = __shfl_sync(0xffffffffu, task, 0, 32);
-				if (task >= 2 * kSlots) break;
-				SlotSm* S = &C->slot[task % kSlots];
-				if (task < kSlots) { if (!(skip & 1)) src_task(C, S, P, lane); }
-				else if (!(skip & 2)) coef_task(C, S, P, lane, task % kSlots);
+				const int nSrc = C->src_tasks;
+				if (task >= nSrc + kSlots) break;
+				if (task < nSrc) {
+					if (!(skip & 1)) {
+						if (C->src_shared) src_shared_task(C, P, lane, task);
+						else src_task(C, &C->slot[task], P, lane);
+					}
+				} else if (!(skip & 2)) {
+					coef_task(C, &C->slot[task - nSrc], P, lane, task - nSrc);
+				}
 			}
 		}
 		busy += GTTS_CLOCK() - tStart;

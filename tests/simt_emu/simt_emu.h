@@ -188,6 +188,7 @@ inline unsigned __ballot_sync(unsigned mask, int pred)
 	for (int l = 0; l < 32; ++l) if ((mask >> l) & 1) { if (__shfl_sync(mask, pred, l, 32)) r |= 1u << l; }
 	return r;
 }
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline float __fadd_rn(float a, float b) { return a + b; }
 inline float __fsub_rn(float a, float b) { return a - b; }
 inline float __fmul_rn(float a, float b) { return a * b; }

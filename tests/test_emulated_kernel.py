@@ -110,3 +110,11 @@ def test_emulated_pipelined_kernel_control_rates(emu_v1, oracle):
     for period in (1, 2, 3, 4):
         out = emu_v1([v], [0], [tr], rate=1000.0 / period)[0]
         assert np.array_equal(out, oracle.synthesize(v, tr, control_rate=1000.0 / period))
+
+
+def test_emulated_pipelined_kernel_aligned_batch(emu_v1, oracle):
+    # equally long utterances of one voice step in lockstep: the slot-shared SRC task is used
+    v = default_voice("male")
+    tracks = [T.synthetic_track(50 + i, 12) for i in range(9)] + [T.synthetic_track(70, 5)]
+    for tr, out in zip(tracks, emu_v1([v], [0] * 10, tracks)):
+        assert np.array_equal(out, oracle.synthesize(v, tr))
