@@ -59,12 +59,16 @@ struct SlotSm {
 	// coefficient-walk cursor (parameters 7..15), advanced by whichever pool warp runs the task
 	float  ccur[9], cdelta[9];
 	int    cframe, coff;
-	// descriptor
-	UttDesc U;
-	int     it;                   // iteration counter of the current utterance; -1: idle
-	int     nblocks;
-	int     voice;
-	int     pad_[9];              // slot stride = 16 mod 128 bytes: the 7 slots start in different banks
+	// control block, double-buffered by iteration parity: the scheduler lane writes ctl[p ^ 1] while the
+	// roles read ctl[p], so that one CTA barrier per iteration is enough
+	struct Ctl {
+		UttDesc U;
+		int it;                   // iteration counter of the current utterance; -1: idle
+		int nblocks;
+		int voice;
+		int pad;
+	} ctl[2];
+	int     pad_[20];              // slot stride = 16 mod 128 bytes: the 7 slots start in different banks
 };
 static_assert(sizeof(SlotSm) % 128 == 16, "slot stride should be 16 mod 128 bytes (bank spreading); adjust pad_");
 
@@ -72,11 +76,13 @@ struct CtaSm {
 	double2 tab[kSrcFilterLen];
 	SlotSm slot[kSlots];
 	float  pscratch[kSlots][kBlock][10];      // per-slot scratch of the coefficient task: parameters 7..15 of one block
-	int    task_counter;
-	int    live;                  // number of slots with work
-	int    src_shared;            // 1: every slot in the SRC stage is at the same block of an equally long utterance of the same rate
-	int    src_mask;              // slots with a block in the SRC stage
-	int    src_tasks;             // SRC tasks in the queue this iteration
+	struct Sched {
+		int live;                 // some slot has work
+		int src_shared;           // 1: every slot in the SRC stage is at the same block of an equally long utterance of the same rate
+		int src_mask;             // slots with a block in the SRC stage
+		int src_tasks;            // SRC tasks this iteration
+		long long src_k0, src_k1; // output range of the shared SRC tasks
+	} sched[2];
 };
 
 struct KernelParamsV1 {
@@ -99,9 +105,20 @@ struct KernelParamsV1 {
 #define GTTS_CLOCK() 0ll
 #endif
 
-GTTS_DEV int block_len(const SlotSm& s, int b)
+// ceil((n << 16) / inc): number of outputs whose right wing ends before input n (SampleRateConverter.h:
+// 295-361 as a closed form).  Double division plus an integer correction instead of a 64-bit divide.
+GTTS_DEV long long outputs_before(long long n, unsigned inc)
 {
-	const long long left = s.U.n_internal - (long long) b * kBlock;
+	const unsigned long long num = (unsigned long long) n << 16;
+	long long q = (long long) ((double) num / (double) inc);
+	while ((unsigned long long) q * inc < num) ++q;
+	while (q > 0 && (unsigned long long) (q - 1) * inc >= num) --q;
+	return q;
+}
+
+GTTS_DEV int block_len(const SlotSm::Ctl& k, int b)
+{
+	const long long left = k.U.n_internal - (long long) b * kBlock;
 	return left < kBlock ? (int) left : kBlock;
 }
 
@@ -159,47 +176,48 @@ struct HelperRegs {
 	double seed, noise_x1;
 };
 
-GTTS_DEV void helper_iteration(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int lane, HelperRegs& h)
+GTTS_DEV void helper_iteration(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int lane, HelperRegs& h, int p)
 {
-	const int it = S->it;
+	const SlotSm::Ctl& K = S->ctl[p];
+	const int it = K.it;
 	if (it < 0) return;
-	const VoiceDev& V = P.voices[S->voice];
-	const float* frames = P.frames + S->U.frame_begin * kNumParams;
-	const long long nFrames = S->U.n_frames;
+	const VoiceDev& V = P.voices[K.voice];
+	const float* frames = P.frames + K.U.frame_begin * kNumParams;
+	const long long nFrames = K.U.n_frames;
 	if (it == 0) {
 		// new utterance: clear the rings, reset cursors and the noise generator
 		for (int i = lane; i < kVRing; i += 32) { S->ve[i] = 0.0; S->vo[i] = 0.0; }
 		for (int i = lane; i < 2 * kSrcRing; i += 32) S->xring[i] = 0.0;
-		if (lane < 7) cursor_init(frames, nFrames, S->U.inv_steps, lane, h.cur, h.delta);
+		if (lane < 7) cursor_init(frames, nFrames, K.U.inv_steps, lane, h.cur, h.delta);
 		h.off = 0; h.frame = 0;
 		h.seed = 0.7892347; h.noise_x1 = 0.0;
 		if (lane < 9) {
 			float c, d;
-			cursor_init(frames, nFrames, S->U.inv_steps, 7 + lane, c, d);
+			cursor_init(frames, nFrames, K.U.inv_steps, 7 + lane, c, d);
 			S->ccur[lane] = c; S->cdelta[lane] = d;
 		}
 		if (lane == 0) { S->cframe = 0; S->coff = 0; }
 		__syncwarp();
 	}
 	const int b0 = it, b2 = it - 2;
-	const bool do0 = b0 < S->nblocks, do2 = b2 >= 0 && b2 < S->nblocks;
+	const bool do0 = b0 < K.nblocks, do2 = b2 >= 0 && b2 < K.nblocks;
 	// one walk loop serves both cursors: lane 0 (block b0), lanes 1..6 (block b2)
 	{
 		const bool mine = (lane == 0) ? do0 : (lane < 7 && do2);
-		const int nb = (lane == 0) ? block_len(*S, b0) : block_len(*S, b2);
-		walk_block(frames, nFrames, S->U.steps, S->U.inv_steps, lane, nb, h.cur, h.delta, h.off, h.frame,
+		const int nb = (lane == 0) ? block_len(K, b0) : block_len(K, b2);
+		walk_block(frames, nFrames, K.U.steps, K.U.inv_steps, lane, nb, h.cur, h.delta, h.off, h.frame,
 				&S->cur[0][lane], 8, mine);
 	}
 	__syncwarp();
 	if (do0) {
-		const int nb = block_len(*S, b0);
+		const int nb = block_len(K, b0);
 		if (lane < nb) {
 			const double f0 = 220.0 * gtts_exp2(((double) S->cur[lane][0] + 3.0) * (1.0 / 12.0));
 			S->osc[b0 & 1][lane] = (f0 / 2.0) * V.basic_inc;
 		}
 	}
 	if (do2) {
-		const int nb = block_len(*S, b2);
+		const int nb = block_len(K, b2);
 		const int buf = b2 & 1;
 		const long long n0 = (long long) b2 * kBlock;
 		double ax = 0.0, ah1 = 0.0;
@@ -227,7 +245,7 @@ GTTS_DEV void helper_iteration(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int
 		const double lp = stage_noise(lane, nb, h.seed, h.noise_x1);
 		// wavetable lookup of both half samples (WavetableGlottalSource.h:212-228)
 		if (lane < nb) {
-			const double* table = P.tables + (size_t) S->voice * kTableLen;
+			const double* table = P.tables + (size_t) K.voice * kTableLen;
 			const bool dynamic = (V.waveform == 0) && (V.tn_delta != 0.0);
 			double nd2 = 0.0, inv = 0.0;
 			if (dynamic) {
@@ -290,20 +308,21 @@ GTTS_DEV void helper_iteration(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int
 }
 
 // ---- pool task: junction coefficients of block b = it - 3 (VocalTractModel0.h:484-512, 698-716) ---------
-GTTS_DEV void coef_task(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int lane, int slotIndex)
+GTTS_DEV void coef_task(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int lane, int slotIndex, int p)
 {
-	const int b = S->it - 3;
-	if (S->it < 0 || b < 0 || b >= S->nblocks) return;
-	const VoiceDev& V = P.voices[S->voice];
-	const float* frames = P.frames + S->U.frame_begin * kNumParams;
-	const int nb = block_len(*S, b);
+	const SlotSm::Ctl& K = S->ctl[p];
+	const int b = K.it - 3;
+	if (K.it < 0 || b < 0 || b >= K.nblocks) return;
+	const VoiceDev& V = P.voices[K.voice];
+	const float* frames = P.frames + K.U.frame_begin * kNumParams;
+	const int nb = block_len(K, b);
 	float (*scr)[10] = C->pscratch[slotIndex];
 	{
 		float cur = 0.f, delta = 0.f;
 		int off = S->coff, frame = S->cframe;
 		if (lane < 9) { cur = S->ccur[lane]; delta = S->cdelta[lane]; }
 		__syncwarp();
-		walk_block(frames, S->U.n_frames, S->U.steps, S->U.inv_steps, 7 + lane, nb, cur, delta, off, frame,
+		walk_block(frames, K.U.n_frames, K.U.steps, K.U.inv_steps, 7 + lane, nb, cur, delta, off, frame,
 				&scr[0][lane], 10, lane < 9);
 		if (lane < 9) { S->ccur[lane] = cur; S->cdelta[lane] = delta; }
 		if (lane == 0) { S->coff = off; S->cframe = frame; }
@@ -338,19 +357,20 @@ GTTS_DEV void coef_task(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int lane, 
 }
 
 // ---- pool task: sample-rate conversion of the outputs that block b = it - 6 completes ---------------
-GTTS_DEV void src_task(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int lane)
+GTTS_DEV void src_task(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int lane, int p)
 {
-	const int b = S->it - kStages;
-	if (S->it < 0 || b < 0 || b >= S->nblocks) return;
-	const VoiceDev& V = P.voices[S->voice];
+	const SlotSm::Ctl& K = S->ctl[p];
+	const int b = K.it - kStages;
+	if (K.it < 0 || b < 0 || b >= K.nblocks) return;
+	const VoiceDev& V = P.voices[K.voice];
 	const long long nStart = (long long) b * kBlock;
-	const long long nEnd = nStart + block_len(*S, b);
+	const long long nEnd = nStart + block_len(K, b);
 	const unsigned inc = V.src_inc;
-	long long k0 = (long long) ((((unsigned long long) nStart << 16) + inc - 1) / inc);
-	long long k1 = (long long) ((((unsigned long long) nEnd << 16) + inc - 1) / inc);
-	if (b == S->nblocks - 1) k1 = S->U.n_out;          // flush: chain B appended the 26 zeros
-	if (k1 > S->U.n_out) k1 = S->U.n_out;
-	float* out = P.out + S->U.out_begin;
+	long long k0 = outputs_before(nStart, inc);
+	long long k1 = outputs_before(nEnd, inc);
+	if (b == K.nblocks - 1) k1 = K.U.n_out;          // flush: chain B appended the 26 zeros
+	if (k1 > K.U.n_out) k1 = K.U.n_out;
+	float* out = P.out + K.U.out_begin;
 	// Up to 96 outputs per block (ratio < 3): each lane carries three independent accumulator chains
 	// (outputs k, k + 32, k + 64) so that the 52 dependent multiply-adds of one output overlap with the
 	// other two; every chain still sums its own taps in the reference's order (left wing, then right).
@@ -403,21 +423,13 @@ GTTS_DEV void src_task(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int lane)
 // fetched and formed once and applied to each slot's own window.  This divides the coefficient traffic
 // (the dominant shared-memory load of the whole kernel) by the number of slots; each slot's sum still
 // runs over its own taps in the reference's order.
-GTTS_DEV void src_shared_task(CtaSm* C, const KernelParamsV1& P, int lane, int pass)
+GTTS_DEV void src_shared_task(CtaSm* C, const KernelParamsV1& P, int lane, int pass, int p)
 {
-	const int mask = C->src_mask;
+	const int mask = C->sched[p].src_mask;
 	int ref = 0;
 	while (!((mask >> ref) & 1)) ++ref;
-	const SlotSm* R = &C->slot[ref];
-	const int b = R->it - kStages;
-	const VoiceDev& V = P.voices[R->voice];
-	const long long nStart = (long long) b * kBlock;
-	const long long nEnd = nStart + block_len(*R, b);
-	const unsigned inc = V.src_inc;
-	const long long k0 = (long long) ((((unsigned long long) nStart << 16) + inc - 1) / inc);
-	long long k1 = (long long) ((((unsigned long long) nEnd << 16) + inc - 1) / inc);
-	if (b == R->nblocks - 1) k1 = R->U.n_out;
-	if (k1 > R->U.n_out) k1 = R->U.n_out;
+	const unsigned inc = P.voices[C->slot[ref].ctl[p].voice].src_inc;
+	const long long k0 = C->sched[p].src_k0, k1 = C->sched[p].src_k1;
 	const long long k = k0 + 32ll * pass + lane;
 	const unsigned long long t = (unsigned long long) k * inc;
 	const int e = (int) (t >> 16);
@@ -447,7 +459,7 @@ GTTS_DEV void src_shared_task(CtaSm* C, const KernelParamsV1& P, int lane, int p
 	if (k < k1) {
 #pragma unroll
 		for (int q = 0; q < kSlots; ++q) {
-			if ((mask >> q) & 1) P.out[C->slot[q].U.out_begin + k] = (float) acc[q];
+			if ((mask >> q) & 1) P.out[C->slot[q].ctl[p].U.out_begin + k] = (float) acc[q];
 		}
 	}
 }
@@ -458,12 +470,13 @@ GTTS_DEV void src_shared_task(CtaSm* C, const KernelParamsV1& P, int lane, int p
 // results are never read), which keeps the loop free of divergent branches.
 struct ChainARegs { double pos; BandpassState bp; };
 
-GTTS_DEV void chain_a_iteration(CtaSm* C, const KernelParamsV1& P, int lane, ChainARegs& r)
+GTTS_DEV void chain_a_iteration(CtaSm* C, const KernelParamsV1& P, int lane, ChainARegs& r, int p)
 {
 	(void) P;
 	if (lane >= kSlots) return;
 	SlotSm* S = &C->slot[lane];
-	const int it = S->it;
+	const SlotSm::Ctl& K = S->ctl[p];
+	const int it = K.it;
 	const int b1 = it - 1, b3 = it - 3;
 	if (b1 == 0) r.pos = 0.0;
 	if (b3 == 0) { r.bp.x1 = r.bp.x2 = r.bp.y1 = r.bp.y2 = 0.0; }
@@ -521,13 +534,14 @@ GTTS_DEV void chain_a_iteration(CtaSm* C, const KernelParamsV1& P, int lane, Cha
 //   f = 2 throat lowpass (b0, b1 = 0, a1, gain = throat gain) on pulse * 0.125   (Throat.h:80-85)
 struct ChainBRegs { double x1, y1; };
 
-GTTS_DEV void chain_b_iteration(CtaSm* C, const KernelParamsV1& P, int lane, ChainBRegs& r)
+GTTS_DEV void chain_b_iteration(CtaSm* C, const KernelParamsV1& P, int lane, ChainBRegs& r, int p)
 {
 	const int s = lane >> 2, f = lane & 3;
 	if (s < kSlots && f < 3) {
 		SlotSm* S = &C->slot[s];
-		const int b = S->it - 5;
-		const VoiceDev& V = P.voices[S->voice];
+		const SlotSm::Ctl& K = S->ctl[p];
+		const int b = K.it - 5;
+		const VoiceDev& V = P.voices[K.voice];
 		if (b == 0) { r.x1 = 0.0; r.y1 = 0.0; }
 		const double b0 = f == 0 ? V.rad_m : (f == 1 ? V.rad_n : V.throat_b0);
 		const double b1 = f == 0 ? -V.rad_m : (f == 1 ? -V.rad_n : 0.0);
@@ -560,9 +574,10 @@ GTTS_DEV void chain_b_iteration(CtaSm* C, const KernelParamsV1& P, int lane, Cha
 	// output sum, lane = sample: (mouth + nose) + throat (VocalTractModel0.h:657-660, 441)
 	for (int q = 0; q < kSlots; ++q) {
 		SlotSm* Q = &C->slot[q];
-		const int qb = Q->it - 5;
-		if (Q->it < 0 || qb < 0 || qb >= Q->nblocks) continue;
-		const int qn = block_len(*Q, qb);
+		const SlotSm::Ctl& QK = Q->ctl[p];
+		const int qb = QK.it - 5;
+		if (QK.it < 0 || qb < 0 || qb >= QK.nblocks) continue;
+		const int qn = block_len(QK, qb);
 		const long long n0 = (long long) qb * kBlock;
 		if (lane < qn) {
 			const int idx = (int) ((n0 + lane) & (kSrcRing - 1));
@@ -570,9 +585,9 @@ GTTS_DEV void chain_b_iteration(CtaSm* C, const KernelParamsV1& P, int lane, Cha
 			Q->xring[idx] = v;
 			Q->xring[idx + kSrcRing] = v;
 		}
-		if (qb == Q->nblocks - 1 && lane < 2 * kSrcZeroCrossings) {
+		if (qb == QK.nblocks - 1 && lane < 2 * kSrcZeroCrossings) {
 			// flushBuffer(): 26 zeros after the last input (SampleRateConverter.h:462-471)
-			const int idx = (int) ((Q->U.n_internal + lane) & (kSrcRing - 1));
+			const int idx = (int) ((QK.U.n_internal + lane) & (kSrcRing - 1));
 			Q->xring[idx] = 0.0;
 			Q->xring[idx + kSrcRing] = 0.0;
 		}
@@ -584,14 +599,15 @@ GTTS_DEV void chain_b_iteration(CtaSm* C, const KernelParamsV1& P, int lane, Cha
 // kinds of B cell (2-port junction, 3-way junction, open end) and selects, so that the independent
 // chains overlap; the per-sample operands are prefetched one sample ahead.  Lanes of slots without a
 // block at this stage run on dummy data: their state is reset when their block 0 arrives.
-GTTS_DEV void tube_iteration(CtaSm* C, const KernelParamsV1& P, int warp, int lane, TubeLane& t)
+GTTS_DEV void tube_iteration(CtaSm* C, const KernelParamsV1& P, int warp, int lane, TubeLane& t, int p)
 {
 	const int g = lane & 7;
 	const int slot = warp * 4 + (lane >> 3);
 	const int base = lane & ~7;
 	SlotSm* S = &C->slot[slot < kSlots ? slot : 0];
-	const int b = (slot < kSlots) ? S->it - 4 : -1;
-	const VoiceDev& V = P.voices[S->voice];
+	const SlotSm::Ctl& K = S->ctl[p];
+	const int b = (slot < kSlots) ? K.it - 4 : -1;
+	const VoiceDev& V = P.voices[K.voice];
 	if (b == 0) { t.aT = t.aB = t.bT = t.bB = t.extra = 0.0; }
 	const double d = V.damping;
 	const bool is3 = g == 1, isEnd = (g == 4) || (g == 7), isGlot = g == 0, isN0 = g == 5;
@@ -656,74 +672,77 @@ GTTS_DEV void tube_iteration(CtaSm* C, const KernelParamsV1& P, int warp, int la
 	t.aT = aT; t.aB = aB; t.bT = bT; t.bB = bB; t.extra = extra;
 }
 
-// ---- slot bookkeeping (between the two barriers; warp 2, lane = slot) -----------------------------------
-GTTS_DEV void schedule_slots(CtaSm* C, const KernelParamsV1& P, int lane)
+// ---- slot bookkeeping for the NEXT iteration (chain A warp, lane = slot, after its chain work) ----------
+// Reads ctl[p] / writes ctl[p ^ 1] and sched[p ^ 1]; everybody switches to p ^ 1 after the barrier.
+GTTS_DEV void schedule_slots(CtaSm* C, const KernelParamsV1& P, int lane, int p, bool first)
 {
-	int alive = 0;
+	const int q = p ^ 1;
+	int alive = 0, valid = 0, it = -1;
+	long long nInternal = 0;
+	unsigned inc = 0;
 	if (lane < kSlots) {
 		SlotSm* S = &C->slot[lane];
-		if (S->it >= 0) {
-			S->it += 1;
-			if (S->it > S->nblocks - 1 + kStages) S->it = -1;      // every stage has seen every block
+		const SlotSm::Ctl& K = S->ctl[p];
+		SlotSm::Ctl& N = S->ctl[q];
+		it = first ? -1 : K.it;
+		if (it >= 0) {
+			it += 1;
+			if (it > K.nblocks - 1 + kStages) it = -1;          // every stage has seen every block
 		}
-		if (S->it < 0) {
+		if (it >= 0) {
+			N.U = K.U; N.nblocks = K.nblocks; N.voice = K.voice; N.it = it;
+		} else {
+			N.it = -1; N.nblocks = 0; N.voice = first ? 0 : K.voice; N.U = K.U;
 			for (;;) {
-				const int q = atomicAdd(P.queue, 1);
-				if (q >= P.n_utt) break;
-				const UttDesc U = P.utts[P.order[q]];
+				const int u = atomicAdd(P.queue, 1);
+				if (u >= P.n_utt) break;
+				const UttDesc U = P.utts[P.order[u]];
 				if (U.n_internal == 0) {
 					// no input at all: finishSynthesis() alone converts the 26 flush zeros into zeros
 					for (long long k = 0; k < U.n_out; ++k) P.out[U.out_begin + k] = 0.0f;
 					continue;
 				}
-				S->U = U;
-				S->voice = U.voice;
-				S->nblocks = (int) ((U.n_internal + kBlock - 1) / kBlock);
-				S->it = 0;
+				N.U = U;
+				N.voice = U.voice;
+				N.nblocks = (int) ((U.n_internal + kBlock - 1) / kBlock);
+				N.it = 0;
+				it = 0;
 				break;
 			}
 		}
-		alive = S->it >= 0;
+		alive = it >= 0;
+		valid = it >= 0 && it - kStages >= 0 && it - kStages < N.nblocks;
+		if (valid) { nInternal = N.U.n_internal; inc = P.voices[N.voice].src_inc; }
 	}
 	const unsigned any = __ballot_sync(0xffffffffu, alive);
 	// SRC stage alignment: all slots that have a block at it - 6 are at the same block of equally long
 	// utterances with the same SRC increment -> one shared SRC task per 32 outputs
-	int valid = 0, it = 0;
-	long long nInternal = 0;
-	unsigned inc = 0;
-	if (lane < kSlots) {
-		const SlotSm* S = &C->slot[lane];
-		it = S->it;
-		valid = it >= 0 && it - kStages >= 0 && it - kStages < S->nblocks;
-		if (valid) { nInternal = S->U.n_internal; inc = P.voices[S->voice].src_inc; }
-	}
 	const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-	int refLane = 0;
-	while (refLane < 31 && !((vmask >> refLane) & 1)) ++refLane;
+	const int refLane = vmask ? __ffs((int) vmask) - 1 : 0;
 	const int itRef = __shfl_sync(0xffffffffu, it, refLane, 32);
 	const long long nRef = __shfl_sync(0xffffffffu, nInternal, refLane, 32);
 	const unsigned incRef = __shfl_sync(0xffffffffu, inc, refLane, 32);
 	const int same = !valid || (it == itRef && nInternal == nRef && inc == incRef);
-	const unsigned allSame = __ballot_sync(0xffffffffu, same) == 0xffffffffu;
+	const bool allSame = __ballot_sync(0xffffffffu, same) == 0xffffffffu;
 	if (lane == 0) {
-		C->live = any != 0;
-		C->task_counter = 0;
-		C->src_mask = (int) vmask;
-		const int nValid = __popc(vmask);
-		C->src_shared = (allSame && nValid >= 2) ? 1 : 0;
-		int nTasks = kSlots;
-		if (C->src_shared) {
-			const SlotSm* R = &C->slot[refLane];
-			const int b = R->it - kStages;
+		CtaSm::Sched& D = C->sched[q];
+		D.live = any != 0;
+		D.src_mask = (int) vmask;
+		D.src_shared = (allSame && __popc(vmask) >= 2) ? 1 : 0;
+		D.src_tasks = kSlots;
+		if (D.src_shared) {
+			const SlotSm::Ctl& RK = C->slot[refLane].ctl[q];
+			const int b = RK.it - kStages;
 			const long long nStart = (long long) b * kBlock;
-			const long long nEnd = nStart + block_len(*R, b);
-			const long long k0 = (long long) ((((unsigned long long) nStart << 16) + incRef - 1) / incRef);
-			long long k1 = (long long) ((((unsigned long long) nEnd << 16) + incRef - 1) / incRef);
-			if (b == R->nblocks - 1) k1 = R->U.n_out;
-			if (k1 > R->U.n_out) k1 = R->U.n_out;
-			nTasks = (int) ((k1 - k0 + 31) / 32);
+			const long long nEnd = nStart + block_len(RK, b);
+			const long long k0 = outputs_before(nStart, incRef);
+			long long k1 = outputs_before(nEnd, incRef);
+			if (b == RK.nblocks - 1) k1 = RK.U.n_out;
+			if (k1 > RK.U.n_out) k1 = RK.U.n_out;
+			D.src_k0 = k0;
+			D.src_k1 = k1;
+			D.src_tasks = (int) ((k1 - k0 + 31) / 32);
 		}
-		C->src_tasks = nTasks;
 	}
 }
 
@@ -732,55 +751,60 @@ GTTS_DEV void tube_v1_cta_body(const KernelParamsV1& P, unsigned char* smem, int
 	CtaSm* C = reinterpret_cast<CtaSm*>(smem);
 	const int warp = tid >> 5, lane = tid & 31;
 	for (int i = tid; i < kSrcFilterLen; i += kThreads) C->tab[i] = P.src_tab[i];
-	if (tid < kSlots) { C->slot[tid].it = -1; C->slot[tid].voice = 0; C->slot[tid].nblocks = 0; }
-	if (tid == 0) { C->live = 0; C->task_counter = 0; C->src_shared = 0; C->src_mask = 0; C->src_tasks = kSlots; }
+	if (tid < kSlots) {
+		for (int b = 0; b < 2; ++b) { C->slot[tid].ctl[b].it = -1; C->slot[tid].ctl[b].voice = 0; C->slot[tid].ctl[b].nblocks = 0; }
+	}
 	__syncthreads();
-	if (warp == kChainAWarp) schedule_slots(C, P, lane);
+	int p = 1;
+	if (warp == kChainAWarp) schedule_slots(C, P, lane, p, true);      // fills ctl[0] / sched[0]
 	__syncthreads();
+	p = 0;
 
 	TubeLane tl = {0.0, 0.0, 0.0, 0.0, 0.0};
 	ChainARegs ca = {0.0, {0.0, 0.0, 0.0, 0.0}};
 	ChainBRegs cb = {0.0, 0.0};
 	HelperRegs hr = {0.f, 0.f, 0, 0, 0.7892347, 0.0};
 
+	// Task workers besides the seven slot helpers: pool warps first, then the two chain warps.  Task t of an
+	// iteration (SRC tasks, then one coefficient task per slot) goes to worker t mod 7; no atomics.
+	const int worker = warp >= kPool0 ? warp - kPool0 : (warp == kChainBWarp ? kPoolWarps : (warp == kChainAWarp ? kPoolWarps + 1 : -1));
+	const int nWorkers = kPoolWarps + 2;
+
 	long long busy = 0, iters = 0;
-	while (C->live) {
+	while (C->sched[p].live) {
 		const long long tStart = GTTS_CLOCK();
 		const int skip = P.debug_skip;
 		if (warp < kTubeWarps) {
-			if (!(skip & 32)) tube_iteration(C, P, warp, lane, tl);
+			if (!(skip & 32)) tube_iteration(C, P, warp, lane, tl, p);
 		} else {
 			if (warp == kChainAWarp) {
-				if (!(skip & 8)) chain_a_iteration(C, P, lane, ca);
+				if (!(skip & 8)) chain_a_iteration(C, P, lane, ca, p);
+				schedule_slots(C, P, lane, p, false);
 			} else if (warp == kChainBWarp) {
-				if (!(skip & 16)) chain_b_iteration(C, P, lane, cb);
+				if (!(skip & 16)) chain_b_iteration(C, P, lane, cb, p);
 			} else if (warp < kPool0) {
 				SlotSm* S = &C->slot[warp - kHelper0];
-				if (!(skip & 4)) helper_iteration(C, S, P, lane, hr);
+				if (!(skip & 4)) helper_iteration(C, S, P, lane, hr, p);
 			}
-			// task queue: 2 tasks per slot (SRC first: it is the longer one).  Every warp that is done with
-			// its fixed role helps, which balances the load whatever the mix of voices and block phases.
-			for (;;) {
-				int task = 0;
-				if (lane == 0) task = atomicAdd(&C->task_counter, 1);
-				task = __shfl_sync(0xffffffffu, task, 0, 32);
-				const int nSrc = C->src_tasks;
-				if (task >= nSrc + kSlots) break;
-				if (task < nSrc) {
-					if (!(skip & 1)) {
-						if (C->src_shared) src_shared_task(C, P, lane, task);
-						else src_task(C, &C->slot[task], P, lane);
+			if (worker >= 0) {
+				const int nSrc = C->sched[p].src_tasks;
+				const bool shared = C->sched[p].src_shared != 0;
+				for (int task = worker; task < nSrc + kSlots; task += nWorkers) {
+					if (task < nSrc) {
+						if (!(skip & 1)) {
+							if (shared) src_shared_task(C, P, lane, task, p);
+							else src_task(C, &C->slot[task], P, lane, p);
+						}
+					} else if (!(skip & 2)) {
+						coef_task(C, &C->slot[task - nSrc], P, lane, task - nSrc, p);
 					}
-				} else if (!(skip & 2)) {
-					coef_task(C, &C->slot[task - nSrc], P, lane, task - nSrc);
 				}
 			}
 		}
 		busy += GTTS_CLOCK() - tStart;
 		iters += 1;
 		__syncthreads();
-		if (warp == kChainAWarp) schedule_slots(C, P, lane);
-		__syncthreads();
+		p ^= 1;
 	}
 #ifndef GTTS_EMU
 	if (P.prof != nullptr && lane == 0) {
