@@ -765,10 +765,10 @@ GTTS_DEV void tube_v1_cta_body(const KernelParamsV1& P, unsigned char* smem, int
 	ChainBRegs cb = {0.0, 0.0};
 	HelperRegs hr = {0.f, 0.f, 0, 0, 0.7892347, 0.0};
 
-	// Task workers besides the seven slot helpers: pool warps first, then the two chain warps.  Task t of an
-	// iteration (SRC tasks, then one coefficient task per slot) goes to worker t mod 7; no atomics.
-	const int worker = warp >= kPool0 ? warp - kPool0 : (warp == kChainBWarp ? kPoolWarps : (warp == kChainAWarp ? kPoolWarps + 1 : -1));
-	const int nWorkers = kPoolWarps + 2;
+	// Task workers: the pool warps and chain B (chain A also does the slot bookkeeping and takes no task).
+	// Task t of an iteration (SRC tasks, then one coefficient task per slot) goes to worker t mod 6; no atomics.
+	const int worker = warp >= kPool0 ? warp - kPool0 : (warp == kChainBWarp ? kPoolWarps : -1);
+	const int nWorkers = kPoolWarps + 1;
 
 	long long busy = 0, iters = 0;
 	while (C->sched[p].live) {
