@@ -415,16 +415,34 @@ int gtts_batch_run_host(gtts_batch* b, const float* h_frames, float* h_out)
 		GTTS_CUDA(cudaMalloc(&b->d_frames, sizeof(float) * kNumParams * nFrames));
 		b->cap_frames = nFrames;
 	}
-	if (nOut > b->cap_out) {
+	// Output path.  Pinned (page-locked) host memory is device-accessible under UVA: the kernel then
+	// stores the float32 audio straight into the caller's buffer over PCIe while it computes, so the
+	// device->host transfer overlaps the synthesis instead of following it.  Pageable buffers are
+	// staged through device memory and copied afterwards.  GTTS_HOST_OUTPUT=staged forces staging.
+	float* dOut = nullptr;
+	bool zeroCopy = false;
+	if (nOut > 0) {
+		cudaPointerAttributes attr;
+		const char* env = std::getenv("GTTS_HOST_OUTPUT");
+		const bool allow = !(env && std::strcmp(env, "staged") == 0);
+		if (allow && cudaPointerGetAttributes(&attr, h_out) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer) {
+			dOut = static_cast<float*>(attr.devicePointer);
+			zeroCopy = true;
+		} else {
+			cudaGetLastError();     // clear the error a pageable pointer may have left
+		}
+	}
+	if (!zeroCopy && nOut > b->cap_out) {
 		if (b->d_out) cudaFree(b->d_out);
 		b->d_out = nullptr; b->cap_out = 0;
 		GTTS_CUDA(cudaMalloc(&b->d_out, sizeof(float) * nOut));
 		b->cap_out = nOut;
 	}
+	if (!zeroCopy) dOut = b->d_out;
 	if (nFrames > 0) GTTS_CUDA(cudaMemcpyAsync(b->d_frames, h_frames, sizeof(float) * kNumParams * nFrames, cudaMemcpyHostToDevice, b->stream));
-	const int rc = launchBatch(b, b->d_frames, b->d_out, b->stream);
+	const int rc = launchBatch(b, b->d_frames, dOut, b->stream);
 	if (rc != GTTS_OK) return rc;
-	if (nOut > 0) GTTS_CUDA(cudaMemcpyAsync(h_out, b->d_out, sizeof(float) * nOut, cudaMemcpyDeviceToHost, b->stream));
+	if (!zeroCopy && nOut > 0) GTTS_CUDA(cudaMemcpyAsync(h_out, b->d_out, sizeof(float) * nOut, cudaMemcpyDeviceToHost, b->stream));
 	GTTS_CUDA(cudaStreamSynchronize(b->stream));
 	return GTTS_OK;
 }

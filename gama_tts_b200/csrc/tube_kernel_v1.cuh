@@ -56,6 +56,7 @@ struct SlotSm {
 	double xring[2 * kSrcRing];   // tube output ring, every sample stored twice (i and i + 128): any 26-sample window is contiguous
 	float  cur[kBlock][8];        // slot helper scratch: parameters 0..6 of the block being converted
 	int    ip[3][kBlock];
+	int    fric[2];               // block has frication (some tap * bandpassed noise != 0), per pab buffer
 	// coefficient-walk cursor (parameters 7..15), advanced by whichever pool warp runs the task
 	float  ccur[9], cdelta[9];
 	int    cframe, coff;
@@ -68,7 +69,7 @@ struct SlotSm {
 		int voice;
 		int pad;
 	} ctl[2];
-	int     pad_[20];              // slot stride = 16 mod 128 bytes: the 7 slots start in different banks
+	int     pad_[16];              // slot stride = 16 mod 128 bytes: the 7 slots start in different banks
 };
 static_assert(sizeof(SlotSm) % 128 == 16, "slot stride should be 16 mod 128 bytes (bank spreading); adjust pad_");
 
@@ -219,8 +220,7 @@ GTTS_DEV void helper_iteration(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int
 	if (do2) {
 		const int nb = block_len(K, b2);
 		const int buf = b2 & 1;
-		const long long n0 = (long long) b2 * kBlock;
-		double ax = 0.0, ah1 = 0.0;
+			double ax = 0.0, ah1 = 0.0;
 		if (lane < nb) {
 			const float* p = S->cur[lane];
 			ax = amp60((double) p[1]);
@@ -274,20 +274,32 @@ GTTS_DEV void helper_iteration(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int
 				}
 				v[s] = tl + ((pos - (double) lo) * (tu - tl));
 			}
-			const int slot = (int) ((n0 + lane) & (kVRing - 1));
-			S->ve[slot] = v[0];
-			S->vo[slot] = v[1];
+			// linear window: [0, 24) = the last 24 samples of the previous blocks, [24, 56) = this block
+			S->ve[24 + lane] = v[0];
+			S->vo[24 + lane] = v[1];
 		}
 		__syncwarp();
-		if (lane < nb) {
-			const long long n = n0 + lane;
+		double firOut = 0.0;
+		{
+			// y = sum_i c[i] x2[2n+1-i]: i even -> odd phase of sample n - i/2, i odd -> even phase of n - (i-1)/2
+			const double* pe = S->ve + 24 + lane;
+			const double* po = S->vo + 24 + lane;
 			double acc = 0.0;
 #pragma unroll
 			for (int i = 0; i < kFirTaps; ++i) {
-				const int idx = (int) ((n - ((i & 1) ? (i - 1) / 2 : i / 2)) & (kVRing - 1));
-				const double x = (i & 1) ? S->ve[idx] : S->vo[idx];
+				const double x = (i & 1) ? pe[-((i - 1) / 2)] : po[-(i / 2)];
 				acc += x * c_fir[i];
 			}
+			firOut = acc;
+		}
+		__syncwarp();
+		if (lane < 24) {
+			// slide the window: the last 24 samples become the history of the next block
+			S->ve[lane] = S->ve[32 + lane];      // source [32, 56) and destination [0, 24) do not overlap
+			S->vo[lane] = S->vo[32 + lane];
+		}
+		if (lane < nb) {
+			const double acc = firOut;
 			double pulse = acc;
 			const double pn = lp * pulse;
 			pulse = ax * ((pulse * V.one_minus_breath) + (pn * V.breath));
@@ -492,6 +504,7 @@ GTTS_DEV void chain_a_iteration(CtaSm* C, const KernelParamsV1& P, int lane, Cha
 	const double* tb = S->tapb[buf3];
 	double2* pab = S->pab[buf3];
 	double pos = r.pos, x1 = r.bp.x1, x2 = r.bp.x2, y1 = r.bp.y1, y2 = r.bp.y2;
+	bool anyFric = false;
 	// chunks of 4 samples: all operands of a chunk are loaded into registers before the two recurrences
 	// are stepped, so that shared-memory latency is paid once per chunk instead of once per sample
 	for (int j0 = 0; j0 < kBlock; j0 += 4) {
@@ -516,6 +529,7 @@ GTTS_DEV void chain_a_iteration(CtaSm* C, const KernelParamsV1& P, int lane, Cha
 			x2 = x1; x1 = x[q]; y2 = y1; y1 = y;
 			oa[q] = tA[q] * y;
 			ob[q] = tB[q] * y;
+			anyFric = anyFric || oa[q] != 0.0 || ob[q] != 0.0;
 		}
 #pragma unroll
 		for (int q = 0; q < 4; ++q) {
@@ -524,6 +538,7 @@ GTTS_DEV void chain_a_iteration(CtaSm* C, const KernelParamsV1& P, int lane, Cha
 			pab[j0 + q] = make_double2(oa[q], ob[q]);
 		}
 	}
+	S->fric[buf3] = anyFric ? 1 : 0;
 	r.pos = pos; r.bp.x1 = x1; r.bp.x2 = x2; r.bp.y1 = y1; r.bp.y2 = y2;
 }
 
@@ -599,7 +614,8 @@ GTTS_DEV void chain_b_iteration(CtaSm* C, const KernelParamsV1& P, int lane, Cha
 // kinds of B cell (2-port junction, 3-way junction, open end) and selects, so that the independent
 // chains overlap; the per-sample operands are prefetched one sample ahead.  Lanes of slots without a
 // block at this stage run on dummy data: their state is reset when their block 0 arrives.
-GTTS_DEV void tube_iteration(CtaSm* C, const KernelParamsV1& P, int warp, int lane, TubeLane& t, int p)
+template<bool kFric>
+GTTS_DEV void tube_iteration_impl(CtaSm* C, const KernelParamsV1& P, int warp, int lane, TubeLane& t, int p)
 {
 	const int g = lane & 7;
 	const int slot = warp * 4 + (lane >> 3);
@@ -631,15 +647,22 @@ GTTS_DEV void tube_iteration(CtaSm* C, const KernelParamsV1& P, int warp, int la
 		int ipv[4];
 #pragma unroll
 		for (int q = 0; q < 4; ++q) {
-			kkv[q] = kabRow[j0 + q]; pabv[q] = pabRow[j0 + q]; exv[q] = extraRow[j0 + q]; ipv[q] = ipRow[j0 + q];
+			kkv[q] = kabRow[j0 + q]; exv[q] = extraRow[j0 + q];
+			if (kFric) { pabv[q] = pabRow[j0 + q]; ipv[q] = ipRow[j0 + q]; }
 		}
 #pragma unroll
 		for (int q = 0; q < 4; ++q) {
-			const double2 kk = kkv[q], pab = pabv[q];
+			const double2 kk = kkv[q];
 			const double ex = exv[q];
-			const int ip = ipv[q];
-			const double tfA = (tapA == ip) ? pab.x : ((tapA == ip + 1) ? pab.y : 0.0);
-			const double tfB = (tapB == ip) ? pab.x : ((tapB == ip + 1) ? pab.y : 0.0);
+			// frication injected at taps ip, ip+1; a block without frication in any of the warp's slots
+			// (the common case) skips the selection: the reference adds tap * 0 = 0 there
+			double tfA = 0.0, tfB = 0.0;
+			if (kFric) {
+				const double2 pab = pabv[q];
+				const int ip = ipv[q];
+				tfA = (tapA == ip) ? pab.x : ((tapA == ip + 1) ? pab.y : 0.0);
+				tfB = (tapB == ip) ? pab.x : ((tapB == ip + 1) ? pab.y : 0.0);
+			}
 			// cell A: 2-port junction
 			const double dlA = kk.x * (aT - aB);
 			const double aTo = ((aT + dlA) * d) + tfA;
@@ -670,6 +693,19 @@ GTTS_DEV void tube_iteration(CtaSm* C, const KernelParamsV1& P, int warp, int la
 		}
 	}
 	t.aT = aT; t.aB = aB; t.bT = bT; t.bB = bB; t.extra = extra;
+}
+
+GTTS_DEV void tube_iteration(CtaSm* C, const KernelParamsV1& P, int warp, int lane, TubeLane& t, int p)
+{
+	const int slot = warp * 4 + (lane >> 3);
+	int fric = 0;
+	if (slot < kSlots) {
+		const SlotSm* S = &C->slot[slot];
+		const int b = S->ctl[p].it - 4;
+		if (S->ctl[p].it >= 0 && b >= 0 && b < S->ctl[p].nblocks) fric = S->fric[b & 1];
+	}
+	if (__any_sync(0xffffffffu, fric != 0)) tube_iteration_impl<true>(C, P, warp, lane, t, p);
+	else tube_iteration_impl<false>(C, P, warp, lane, t, p);
 }
 
 // ---- slot bookkeeping for the NEXT iteration (chain A warp, lane = slot, after its chain work) ----------
@@ -756,7 +792,7 @@ GTTS_DEV void tube_v1_cta_body(const KernelParamsV1& P, unsigned char* smem, int
 	}
 	__syncthreads();
 	int p = 1;
-	if (warp == kChainAWarp) schedule_slots(C, P, lane, p, true);      // fills ctl[0] / sched[0]
+	if (warp == 4) schedule_slots(C, P, lane, p, true);      // chain A warp fills ctl[0] / sched[0]
 	__syncthreads();
 	p = 0;
 
@@ -765,25 +801,34 @@ GTTS_DEV void tube_v1_cta_body(const KernelParamsV1& P, unsigned char* smem, int
 	ChainBRegs cb = {0.0, 0.0};
 	HelperRegs hr = {0.f, 0.f, 0, 0, 0.7892347, 0.0};
 
-	// Task workers: the pool warps and chain B (chain A also does the slot bookkeeping and takes no task).
+	// Warp roles by scheduler partition (warp id % 4 selects the SM sub-partition): the two tube warps sit
+	// on partitions 0 and 1 together with the light chain warps and task workers; the seven slot helpers
+	// (the heaviest issue load) fill partitions 2 and 3.
+	//   partition 0: 0 tube, 4 chain A, 8 worker, 12 worker      partition 2: 2, 6, 10, 14 helpers (slots 0-3)
+	//   partition 1: 1 tube, 5 chain B, 9 worker, 13 worker      partition 3: 3, 7, 11 helpers (slots 4-6), 15 worker
+	const bool isTube = warp < kTubeWarps;
+	const bool isChainA = warp == 4, isChainB = warp == 5;
+	const bool isHelper = (warp & 3) >= 2 && warp != 15;
+	const int helperSlot = (warp & 3) == 2 ? (warp >> 2) : 4 + (warp >> 2);
+	// Task workers: five pool warps and chain B (chain A also does the slot bookkeeping and takes no task).
 	// Task t of an iteration (SRC tasks, then one coefficient task per slot) goes to worker t mod 6; no atomics.
-	const int worker = warp >= kPool0 ? warp - kPool0 : (warp == kChainBWarp ? kPoolWarps : -1);
-	const int nWorkers = kPoolWarps + 1;
+	const int worker = warp == 8 ? 0 : warp == 12 ? 1 : warp == 9 ? 2 : warp == 13 ? 3 : warp == 15 ? 4 : (isChainB ? 5 : -1);
+	const int nWorkers = 6;
 
 	long long busy = 0, iters = 0;
 	while (C->sched[p].live) {
 		const long long tStart = GTTS_CLOCK();
 		const int skip = P.debug_skip;
-		if (warp < kTubeWarps) {
+		if (isTube) {
 			if (!(skip & 32)) tube_iteration(C, P, warp, lane, tl, p);
 		} else {
-			if (warp == kChainAWarp) {
+			if (isChainA) {
 				if (!(skip & 8)) chain_a_iteration(C, P, lane, ca, p);
 				schedule_slots(C, P, lane, p, false);
-			} else if (warp == kChainBWarp) {
+			} else if (isChainB) {
 				if (!(skip & 16)) chain_b_iteration(C, P, lane, cb, p);
-			} else if (warp < kPool0) {
-				SlotSm* S = &C->slot[warp - kHelper0];
+			} else if (isHelper) {
+				SlotSm* S = &C->slot[helperSlot];
 				if (!(skip & 4)) helper_iteration(C, S, P, lane, hr, p);
 			}
 			if (worker >= 0) {

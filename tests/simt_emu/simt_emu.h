@@ -188,6 +188,7 @@ inline unsigned __ballot_sync(unsigned mask, int pred)
 	for (int l = 0; l < 32; ++l) if ((mask >> l) & 1) { if (__shfl_sync(mask, pred, l, 32)) r |= 1u << l; }
 	return r;
 }
+inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __ffs(int v) { return __builtin_ffs(v); }
 inline float __fadd_rn(float a, float b) { return a + b; }

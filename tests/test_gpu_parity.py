@@ -186,3 +186,19 @@ def test_both_kernels_agree(synth, monkeypatch):
     for x, y in zip(a, b):
         assert len(x) == len(y)
         assert full_scale_error(x, y) <= 1e-7
+
+
+def test_pinned_host_output_is_written_directly(synth):
+    # pinned host buffers are device-accessible: the kernel stores the audio straight into them
+    # (device->host transfer overlapped with the synthesis); result must equal the staged path
+    import torch
+    v = default_voice("male")
+    tracks = [T.synthetic_track(900 + i, 37 + i) for i in range(12)]
+    frames, fo = g.pack_tracks(tracks)
+    b = synth.prepare(v, fo)
+    staged = b.run_host(frames)                              # pageable numpy buffers -> staged copy
+    h_frames = torch.from_numpy(frames).pin_memory()
+    h_out = torch.zeros(b.n_out_total, dtype=torch.float32).pin_memory()
+    b.run_host_ptr(h_frames.data_ptr(), h_out.data_ptr())
+    assert np.array_equal(h_out.numpy(), staged)
+    b.close()
