@@ -141,6 +141,7 @@ GTTS_DEV void walk_block(const float* frames, long long nFrames, int steps, floa
 			nxt1 = (f1 + 1 < nFrames) ? frames[(f1 + 1) * kNumParams + param] : nxt0;
 		}
 		int j = 0;
+#pragma unroll 4
 		for (; j < first; ++j) { out[j * outStride] = cur; cur = __fadd_rn(cur, delta); }
 		off += first;
 		if (off == steps) {
@@ -285,7 +286,7 @@ GTTS_DEV void helper_iteration(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int
 			const double* pe = S->ve + 24 + lane;
 			const double* po = S->vo + 24 + lane;
 			double acc = 0.0;
-#pragma unroll
+#pragma unroll 7
 			for (int i = 0; i < kFirTaps; ++i) {
 				const double x = (i & 1) ? pe[-((i - 1) / 2)] : po[-(i / 2)];
 				acc += x * c_fir[i];
@@ -406,7 +407,7 @@ GTTS_DEV void src_task(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int lane, i
 			tabR[o] = C->tab + (gph >> 8);
 			xw[o] = S->xring + ((e - 25) & (kSrcRing - 1));      // window [e-25, e], contiguous in the doubled ring
 		}
-#pragma unroll
+#pragma unroll 1
 		for (int j = 0; j < kSrcZeroCrossings; ++j) {
 #pragma unroll
 			for (int o = 0; o < 3; ++o) {
@@ -415,7 +416,7 @@ GTTS_DEV void src_task(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int lane, i
 				acc[o] += (x * (c.x + (c.y * interpL[o])));
 			}
 		}
-#pragma unroll
+#pragma unroll 1
 		for (int j = 0; j < kSrcZeroCrossings; ++j) {
 #pragma unroll
 			for (int o = 0; o < 3; ++o) {
@@ -454,14 +455,14 @@ GTTS_DEV void src_shared_task(CtaSm* C, const KernelParamsV1& P, int lane, int p
 	double acc[kSlots];
 #pragma unroll
 	for (int q = 0; q < kSlots; ++q) acc[q] = 0.0;
-#pragma unroll
+#pragma unroll 1
 	for (int j = 0; j < kSrcZeroCrossings; ++j) {
 		const double2 c = tabL[256 * j];
 		const double cc = c.x + (c.y * interpL);
 #pragma unroll
 		for (int q = 0; q < kSlots; ++q) acc[q] += (C->slot[q].xring[woff + 12 - j] * cc);
 	}
-#pragma unroll
+#pragma unroll 1
 	for (int j = 0; j < kSrcZeroCrossings; ++j) {
 		const double2 c = tabR[256 * j];
 		const double cc = c.x + (c.y * interpR);

@@ -165,6 +165,7 @@ inline void run_cta(int nthreads, std::function<void(int)> body, size_t stackByt
 
 // ---- the CUDA surface the kernel source uses ---------------------------------------------------------
 #define GTTS_DEV static inline
+#define GTTS_DEV_NOINLINE static inline
 #define GTTS_CONST
 #define __syncwarp(...) simt::syncwarp(0xffffffffu)
 #define __syncthreads() simt::cta_barrier(0, simt::g_cta->nthreads)
