@@ -69,4 +69,17 @@ void lcgMultipliers(unsigned long long* out32)
 	}
 }
 
+unsigned long long lcgInitialState()
+{
+	const unsigned long long mask = (1ull << 44) - 1;
+	const double seed0 = 0.7892347;
+	const double product = seed0 * 377.0;                                  // one IEEE multiplication, as in the reference
+	const double s1d = product - static_cast<double>(static_cast<int>(product));
+	const unsigned long long s1 = static_cast<unsigned long long>(s1d * 17592186044416.0);    // exact: s1d is on the 2^-44 grid
+	// inverse of 377 modulo 2^44 by Newton iteration (377 is odd)
+	unsigned long long inv = 377;
+	for (int i = 0; i < 6; ++i) inv = (inv * (2 - 377 * inv)) & mask;
+	return (s1 * inv) & mask;
+}
+
 } // namespace gtts

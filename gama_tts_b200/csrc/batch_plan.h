@@ -28,6 +28,9 @@ std::string planBatch(const gtts_voice_config* voices, int32_t nVoices, const in
 // 377^(j+1) mod 2^44, j = 0..31: jump-ahead multipliers of the noise generator
 // (reference NoiseSource.h:40-44 is exactly this LCG on the 2^-44 grid).
 void lcgMultipliers(unsigned long long* out32);
+// The state s0 with 377 * s0 = s1 (mod 2^44), s1 = frac(0.7892347 * 377) * 2^44 being the reference's first
+// seed after reset (exactly on the grid): lane j of the first block then gets s0 * 377^(j+1) like any other block.
+unsigned long long lcgInitialState();
 
 } // namespace gtts
 #endif

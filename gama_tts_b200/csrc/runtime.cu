@@ -129,6 +129,7 @@ int launchBatch(gtts_batch* b, const float* dFrames, float* dOut, cudaStream_t s
 		Q.queue = b->d_queue;
 		Q.n_utt = static_cast<int32_t>(nUtt);
 		Q.prof = nullptr;
+		Q.prof_sections = nullptr;
 		Q.debug_skip = 0;
 		if (const char* dbg = std::getenv("GTTS_DEBUG_SKIP")) Q.debug_skip = std::atoi(dbg);   // experiments only: wrong output
 		const int64_t ctasWanted = (nUtt + v1::kSlots - 1) / v1::kSlots;
@@ -139,6 +140,10 @@ int launchBatch(gtts_batch* b, const float* dFrames, float* dOut, cudaStream_t s
 			GTTS_CUDA(cudaMalloc(&dProf, sizeof(long long) * grid * (v1::kWarps + 1)));
 			GTTS_CUDA(cudaMemsetAsync(dProf, 0, sizeof(long long) * grid * (v1::kWarps + 1), stream));
 			Q.prof = dProf;
+			long long* dSec = nullptr;
+			GTTS_CUDA(cudaMalloc(&dSec, sizeof(long long) * grid * 6));
+			GTTS_CUDA(cudaMemsetAsync(dSec, 0, sizeof(long long) * grid * 6, stream));
+			Q.prof_sections = dSec;
 		}
 		v1::tube_kernel_v1<<<grid, v1::kThreads, v1::smem_bytes(), stream>>>(Q);
 		GTTS_CUDA(cudaGetLastError());
@@ -156,6 +161,17 @@ int launchBatch(gtts_batch* b, const float* dFrames, float* dOut, cudaStream_t s
 			}
 			std::fprintf(stderr, "[gtts profile] grid %d, iterations per CTA %.0f; busy cycles per iteration by warp:", grid, iters / grid);
 			for (int w = 0; w < v1::kWarps; ++w) std::fprintf(stderr, " %d:%.0f", w, sum[w] / (iters > 0 ? iters : 1));
+			std::fprintf(stderr, "\n");
+			std::vector<long long> hs(static_cast<size_t>(grid) * 6);
+			GTTS_CUDA(cudaMemcpy(hs.data(), Q.prof_sections, sizeof(long long) * hs.size(), cudaMemcpyDeviceToHost));
+			cudaFree(Q.prof_sections);
+			const char* names[6] = {"walk", "convert", "noise", "lookup", "fir", "mix"};
+			std::fprintf(stderr, "[gtts profile] helper sections (cycles per iteration):");
+			for (int q = 0; q < 6; ++q) {
+				double t = 0;
+				for (int c = 0; c < grid; ++c) t += static_cast<double>(hs[static_cast<size_t>(c) * 6 + q]);
+				std::fprintf(stderr, " %s:%.0f", names[q], t / (iters > 0 ? iters : 1));
+			}
 			std::fprintf(stderr, "\n");
 		}
 		b->last_kernel = "tube_kernel_v1";
@@ -300,6 +316,7 @@ int gtts_create(int32_t device, gtts_handle** handle_out)
 	std::copy(taps.begin(), taps.end(), fir);
 	unsigned long long lcg[kBlock];
 	lcgMultipliers(lcg);
+	const unsigned long long lcgInit = lcgInitialState();
 	std::vector<double> hh(kSrcFilterLen), dh(kSrcFilterLen);
 	buildSrcTables(hh.data(), dh.data());
 	std::vector<double2> tab(kSrcFilterLen);
@@ -307,6 +324,7 @@ int gtts_create(int32_t device, gtts_handle** handle_out)
 	cudaError_t ce;
 	if ((ce = cudaMemcpyToSymbol(c_fir, fir, sizeof fir)) != cudaSuccess ||
 	    (ce = cudaMemcpyToSymbol(c_lcg, lcg, sizeof lcg)) != cudaSuccess ||
+	    (ce = cudaMemcpyToSymbol(c_lcg_init, &lcgInit, sizeof lcgInit)) != cudaSuccess ||
 	    (ce = cudaMalloc(&h->d_src_tab, sizeof(double2) * kSrcFilterLen)) != cudaSuccess ||
 	    (ce = cudaMemcpy(h->d_src_tab, tab.data(), sizeof(double2) * kSrcFilterLen, cudaMemcpyHostToDevice)) != cudaSuccess ||
 	    (ce = cudaFuncSetAttribute(tube_kernel_v0<kWarpsPerCta>, cudaFuncAttributeMaxDynamicSharedMemorySize,

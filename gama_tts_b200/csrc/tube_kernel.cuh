@@ -84,9 +84,11 @@ struct KernelParams {
 #ifndef GTTS_EMU
 GTTS_CONST double c_fir[kFirMaxTaps];
 GTTS_CONST unsigned long long c_lcg[kBlock];       // 377^(j+1) mod 2^44
+GTTS_CONST unsigned long long c_lcg_init;          // state s with 377 s = (first seed after 0.7892347) on the 2^-44 grid
 #else
 extern double c_fir[kFirMaxTaps];
 extern unsigned long long c_lcg[kBlock];
+extern unsigned long long c_lcg_init;
 #endif
 
 // ---- small helpers ---------------------------------------------------------------------------------

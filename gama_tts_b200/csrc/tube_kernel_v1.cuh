@@ -97,6 +97,7 @@ struct KernelParamsV1 {
 	int32_t* queue;
 	int32_t n_utt;
 	int32_t debug_skip;           // experiments only (GTTS_DEBUG_SKIP): bit0 no SRC, bit1 no coef task, bit2 no helper, bit3 no chain A, bit4 no chain B, bit5 no tube
+	long long* prof_sections;     // optional [grid][6]: helper warp 4's cycles per section
 	long long* prof;              // optional [grid][kWarps + 1]: busy cycles per warp + iteration count (GTTS_PROFILE=1)
 };
 
@@ -130,36 +131,33 @@ GTTS_DEV int block_len(const SlotSm::Ctl& k, int b)
 GTTS_DEV void walk_block(const float* frames, long long nFrames, int steps, float invSteps, int param,
 			int nb, float& cur, float& delta, int& off, int& frame, float* out, int outStride, bool active)
 {
+	// `first` samples of the block still belong to the current control period; the period ends inside
+	// (or exactly at the end of) this block iff off + first == steps.  The next frame pair is fetched
+	// up front, the 32 steps are straight-line code: store, sequential float add, and a predicated
+	// restart from the next frame value at step `first` (the reference restarts from the frame value,
+	// not from the accumulated one: Controller.cpp:297-300).
+	const int first = (steps - off) < nb ? (steps - off) : nb;
+	const bool reaches = active && (off + first == steps);
+	float nxt0 = cur, nxt1 = cur;
+	if (reaches && frame + 1 < nFrames) {
+		const long long f1 = frame + 1;
+		nxt0 = frames[f1 * kNumParams + param];
+		nxt1 = (f1 + 1 < nFrames) ? frames[(f1 + 1) * kNumParams + param] : nxt0;
+	}
+	const float d2 = __fmul_rn(__fsub_rn(nxt1, nxt0), invSteps);
+	const int restart = reaches ? first : -1;
+	float c = cur, d = delta;
+#pragma unroll
+	for (int j = 0; j < kBlock; ++j) {
+		if (j == restart) { c = nxt0; d = d2; }
+		if (active) out[j * outStride] = c;
+		c = __fadd_rn(c, d);
+	}
+	if (restart == kBlock) { c = nxt0; d = d2; }
 	if (active) {
-		const int first = (steps - off) < nb ? (steps - off) : nb;
-		// prefetch the next frame pair in case the boundary falls inside this block
-		float nxt0 = 0.f, nxt1 = 0.f;
-		const bool crosses = first < nb;
-		if (crosses) {
-			const long long f1 = frame + 1;
-			nxt0 = frames[f1 * kNumParams + param];
-			nxt1 = (f1 + 1 < nFrames) ? frames[(f1 + 1) * kNumParams + param] : nxt0;
-		}
-		int j = 0;
-#pragma unroll 4
-		for (; j < first; ++j) { out[j * outStride] = cur; cur = __fadd_rn(cur, delta); }
-		off += first;
-		if (off == steps) {
-			off = 0;
-			frame += 1;
-			if (crosses) {
-				cur = nxt0;
-				delta = __fmul_rn(__fsub_rn(nxt1, nxt0), invSteps);
-				for (; j < nb; ++j) { out[j * outStride] = cur; cur = __fadd_rn(cur, delta); }
-				off = nb - first;
-			} else if (frame < nFrames) {
-				// boundary exactly at the end of the block: start the next frame
-				const float a = frames[(long long) frame * kNumParams + param];
-				const float b = (frame + 1 < nFrames) ? frames[(long long) (frame + 1) * kNumParams + param] : a;
-				cur = a;
-				delta = __fmul_rn(__fsub_rn(b, a), invSteps);
-			}
-		}
+		cur = c;
+		delta = d;
+		if (reaches) { frame += 1; off = nb - first; } else { off += nb; }
 	}
 }
 
@@ -173,9 +171,15 @@ GTTS_DEV void cursor_init(const float* frames, long long nFrames, float invSteps
 
 // ---- slot helper (warp 4 + s): stages at it = b and it = b + 2 ------------------------------------------
 struct HelperRegs {
+	long long sec[6];             // profiling: cycles per section (walk, convert, noise, lookup, FIR, mix)
 	float cur, delta;             // lane 0: parameter 0 (block it); lanes 1..6: parameters 1..6 (block it - 2)
 	int off, frame;
-	double seed, noise_x1;
+	unsigned long long lcg;       // noise generator state on the 2^-44 grid: next samples are lcg * 377^(j+1) mod 2^44
+	double noise_x1;
+	// conversions of the previous block, re-used while the parameter does not change (the reference
+	// caches the same way: BandpassFilter.h:93, WavetableGlottalSource.h:164)
+	float c_p1, c_p2, c_p3, c_p5, c_p6;
+	double c_ax, c_ah1, c_fa, c_a2, c_a1, c_b0;
 };
 
 GTTS_DEV void helper_iteration(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int lane, HelperRegs& h, int p)
@@ -192,7 +196,8 @@ GTTS_DEV void helper_iteration(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int
 		for (int i = lane; i < 2 * kSrcRing; i += 32) S->xring[i] = 0.0;
 		if (lane < 7) cursor_init(frames, nFrames, K.U.inv_steps, lane, h.cur, h.delta);
 		h.off = 0; h.frame = 0;
-		h.seed = 0.7892347; h.noise_x1 = 0.0;
+		h.lcg = c_lcg_init; h.noise_x1 = 0.0;
+		h.c_p1 = h.c_p2 = h.c_p3 = h.c_p5 = h.c_p6 = __int_as_float(0x7fc00000);     // NaN: nothing cached
 		if (lane < 9) {
 			float c, d;
 			cursor_init(frames, nFrames, K.U.inv_steps, 7 + lane, c, d);
@@ -203,6 +208,7 @@ GTTS_DEV void helper_iteration(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int
 	}
 	const int b0 = it, b2 = it - 2;
 	const bool do0 = b0 < K.nblocks, do2 = b2 >= 0 && b2 < K.nblocks;
+	long long tq = GTTS_CLOCK();
 	// one walk loop serves both cursors: lane 0 (block b0), lanes 1..6 (block b2)
 	{
 		const bool mine = (lane == 0) ? do0 : (lane < 7 && do2);
@@ -211,6 +217,7 @@ GTTS_DEV void helper_iteration(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int
 				&S->cur[0][lane], 8, mine);
 	}
 	__syncwarp();
+	{ const long long tn = GTTS_CLOCK(); h.sec[0] += tn - tq; tq = tn; }
 	if (do0) {
 		const int nb = block_len(K, b0);
 		if (lane < nb) {
@@ -221,29 +228,73 @@ GTTS_DEV void helper_iteration(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int
 	if (do2) {
 		const int nb = block_len(K, b2);
 		const int buf = b2 & 1;
-			double ax = 0.0, ah1 = 0.0;
-		if (lane < nb) {
-			const float* p = S->cur[lane];
-			ax = amp60((double) p[1]);
-			ah1 = amp60((double) p[2]);
-			const double fa = amp60((double) p[3]);
+		double ax = 0.0, ah1 = 0.0;
+		{
+			const bool live = lane < nb;
+			const float* p = S->cur[lane < nb ? lane : 0];
+			const float p1 = p[1], p2 = p[2], p3 = p[3], p5 = p[5], p6 = p[6];
+			const int last = nb - 1;
+			// glottal and aspiration amplitudes, frication amplitude (VTMUtil.h:50-67)
+			if (__all_sync(0xffffffffu, !live || p1 == h.c_p1)) {
+				ax = h.c_ax;
+			} else {
+				ax = amp60((double) p1);
+				h.c_p1 = __shfl_sync(0xffffffffu, p1, last, 32); h.c_ax = shfl_d(ax, last, 32);
+			}
+			if (__all_sync(0xffffffffu, !live || p2 == h.c_p2)) {
+				ah1 = h.c_ah1;
+			} else {
+				ah1 = amp60((double) p2);
+				h.c_p2 = __shfl_sync(0xffffffffu, p2, last, 32); h.c_ah1 = shfl_d(ah1, last, 32);
+			}
+			double fa;
+			if (__all_sync(0xffffffffu, !live || p3 == h.c_p3)) {
+				fa = h.c_fa;
+			} else {
+				fa = amp60((double) p3);
+				h.c_p3 = __shfl_sync(0xffffffffu, p3, last, 32); h.c_fa = shfl_d(fa, last, 32);
+			}
 			const double fpos = (double) p[4];
 			int ip = (int) fpos;
 			const double comp = fpos - ip;
 			double ta = (1.0 - comp) * fa, tb = comp * fa;
 			if (ip < 0 || ip > 7) { ta = 0.0; tb = 0.0; ip = -50; }
-			S->tapa[buf][lane] = ta;
-			S->tapb[buf][lane] = tb;
-			S->ip[b2 % 3][lane] = ip;
-			const double pi = 3.14159265358979323846;
-			const double tv = tan(pi * (double) p[6] * V.Ts);
-			const double cv = cos(2.0 * pi * (double) p[5] * V.Ts);
-			const double a2 = (1.0 - tv) / (1.0 + tv);
-			S->bp[buf][2][lane] = a2;
-			S->bp[buf][1][lane] = -(1.0 + a2) * cv;
-			S->bp[buf][0][lane] = 0.5 - 0.5 * a2;
+			// bandpass coefficients (BandpassFilter.h:91-110)
+			double a2, a1, b0;
+			if (__all_sync(0xffffffffu, !live || (p5 == h.c_p5 && p6 == h.c_p6))) {
+				a2 = h.c_a2; a1 = h.c_a1; b0 = h.c_b0;
+			} else {
+				const double pi = 3.14159265358979323846;
+				const double tv = tan(pi * (double) p6 * V.Ts);
+				const double cv = cos(2.0 * pi * (double) p5 * V.Ts);
+				a2 = (1.0 - tv) / (1.0 + tv);
+				a1 = -(1.0 + a2) * cv;
+				b0 = 0.5 - 0.5 * a2;
+				h.c_p5 = __shfl_sync(0xffffffffu, p5, last, 32); h.c_p6 = __shfl_sync(0xffffffffu, p6, last, 32);
+				h.c_a2 = shfl_d(a2, last, 32); h.c_a1 = shfl_d(a1, last, 32); h.c_b0 = shfl_d(b0, last, 32);
+			}
+			if (live) {
+				S->tapa[buf][lane] = ta;
+				S->tapb[buf][lane] = tb;
+				S->ip[b2 % 3][lane] = ip;
+				S->bp[buf][2][lane] = a2;
+				S->bp[buf][1][lane] = a1;
+				S->bp[buf][0][lane] = b0;
+			}
 		}
-		const double lp = stage_noise(lane, nb, h.seed, h.noise_x1);
+		{ const long long tn = GTTS_CLOCK(); h.sec[1] += tn - tq; tq = tn; }
+		// noise (NoiseSource.h:40-44 as the integer LCG it is, NoiseFilter.h:63-68)
+		double lp;
+		{
+			const unsigned long long sj = (h.lcg * c_lcg[lane]) & ((1ull << 44) - 1);
+			const double n = (double) (long long) sj * (1.0 / 17592186044416.0) - 0.5;
+			double prev = shfl_d(n, (lane + 31) & 31, 32);
+			if (lane == 0) prev = h.noise_x1;
+			h.noise_x1 = shfl_d(n, nb - 1, 32);
+			h.lcg = __shfl_sync(0xffffffffu, sj, nb - 1, 32);
+			lp = n + prev;
+		}
+		{ const long long tn = GTTS_CLOCK(); h.sec[2] += tn - tq; tq = tn; }
 		// wavetable lookup of both half samples (WavetableGlottalSource.h:212-228)
 		if (lane < nb) {
 			const double* table = P.tables + (size_t) K.voice * kTableLen;
@@ -280,20 +331,36 @@ GTTS_DEV void helper_iteration(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int
 			S->vo[24 + lane] = v[1];
 		}
 		__syncwarp();
+		{ const long long tn = GTTS_CLOCK(); h.sec[3] += tn - tq; tq = tn; }
 		double firOut = 0.0;
 		{
-			// y = sum_i c[i] x2[2n+1-i]: i even -> odd phase of sample n - i/2, i odd -> even phase of n - (i-1)/2
+			// y = sum_i c[i] x2[2n+1-i], i ascending: taps 2m and 2m+1 read the odd and the even phase of
+			// sample n - m (m = 0..23), tap 48 the odd phase of n - 24.  Groups of 4 pairs, the next group
+			// is loaded while the current one is accumulated.
 			const double* pe = S->ve + 24 + lane;
 			const double* po = S->vo + 24 + lane;
 			double acc = 0.0;
-#pragma unroll 7
-			for (int i = 0; i < kFirTaps; ++i) {
-				const double x = (i & 1) ? pe[-((i - 1) / 2)] : po[-(i / 2)];
-				acc += x * c_fir[i];
+			double xo[4], xe[4];
+#pragma unroll
+			for (int q = 0; q < 4; ++q) { xo[q] = po[-q]; xe[q] = pe[-q]; }
+#pragma unroll 1
+			for (int m0 = 0; m0 < 24; m0 += 4) {
+				double no[4], ne[4];
+#pragma unroll
+				for (int q = 0; q < 4; ++q) { no[q] = po[-(m0 + 4 + q)]; ne[q] = (m0 + 4 + q <= 23) ? pe[-(m0 + 4 + q)] : 0.0; }
+#pragma unroll
+				for (int q = 0; q < 4; ++q) {
+					acc += xo[q] * c_fir[2 * (m0 + q)];
+					acc += xe[q] * c_fir[2 * (m0 + q) + 1];
+				}
+#pragma unroll
+				for (int q = 0; q < 4; ++q) { xo[q] = no[q]; xe[q] = ne[q]; }
 			}
+			acc += xo[0] * c_fir[48];
 			firOut = acc;
 		}
 		__syncwarp();
+		{ const long long tn = GTTS_CLOCK(); h.sec[4] += tn - tq; tq = tn; }
 		if (lane < 24) {
 			// slide the window: the last 24 samples become the history of the next block
 			S->ve[lane] = S->ve[32 + lane];      // source [32, 56) and destination [0, 24) do not overlap
@@ -316,6 +383,7 @@ GTTS_DEV void helper_iteration(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int
 			S->in[b2 % 3][lane] = (pulse + (ah1 * sig)) * 0.125;
 			S->thr[b2 & 3][lane] = pulse * 0.125;
 		}
+		{ const long long tn = GTTS_CLOCK(); h.sec[5] += tn - tq; tq = tn; }
 	}
 	(void) C;
 }
@@ -800,7 +868,7 @@ GTTS_DEV void tube_v1_cta_body(const KernelParamsV1& P, unsigned char* smem, int
 	TubeLane tl = {0.0, 0.0, 0.0, 0.0, 0.0};
 	ChainARegs ca = {0.0, {0.0, 0.0, 0.0, 0.0}};
 	ChainBRegs cb = {0.0, 0.0};
-	HelperRegs hr = {0.f, 0.f, 0, 0, 0.7892347, 0.0};
+	HelperRegs hr = {};
 
 	// Warp roles.  warp id % 4 selects the SM sub-partition; this assignment spreads the heavy issuers
 	// (7 slot helpers, 5 task workers) evenly over the four partitions next to one light warp each
@@ -856,6 +924,9 @@ GTTS_DEV void tube_v1_cta_body(const KernelParamsV1& P, unsigned char* smem, int
 	if (P.prof != nullptr && lane == 0) {
 		P.prof[(size_t) blockIdx.x * (kWarps + 1) + warp] = busy;
 		if (warp == 0) P.prof[(size_t) blockIdx.x * (kWarps + 1) + kWarps] = iters;
+		if (warp == kHelper0 && P.prof_sections != nullptr) {
+			for (int q = 0; q < 6; ++q) P.prof_sections[(size_t) blockIdx.x * 6 + q] = hr.sec[q];
+		}
 	}
 #endif
 }

@@ -6,6 +6,7 @@
 namespace gtts {
 double c_fir[64];
 unsigned long long c_lcg[32];
+unsigned long long c_lcg_init;
 }
 #include "../../gama_tts_b200/csrc/tube_kernel.cuh"
 #include "../../gama_tts_b200/csrc/batch_plan.h"
@@ -89,6 +90,7 @@ extern "C" int emu_batch_v1(const gtts_voice_config* voices, int n_voices, const
 	std::memset(c_fir, 0, sizeof c_fir);
 	for (size_t i = 0; i < taps.size(); ++i) c_fir[i] = taps[i];
 	lcgMultipliers(c_lcg);
+	c_lcg_init = lcgInitialState();
 	std::vector<double> h(kSrcFilterLen), dh(kSrcFilterLen);
 	buildSrcTables(h.data(), dh.data());
 	std::vector<double2> tab(kSrcFilterLen);
@@ -108,6 +110,7 @@ extern "C" int emu_batch_v1(const gtts_voice_config* voices, int n_voices, const
 	P.queue = &queue;
 	P.n_utt = static_cast<int32_t>(n_utt);
 	P.prof = nullptr;
+	P.prof_sections = nullptr;
 	P.debug_skip = 0;
 
 	std::vector<unsigned char> smem(v1::smem_bytes() + 64);

@@ -189,6 +189,8 @@ inline unsigned __ballot_sync(unsigned mask, int pred)
 	for (int l = 0; l < 32; ++l) if ((mask >> l) & 1) { if (__shfl_sync(mask, pred, l, 32)) r |= 1u << l; }
 	return r;
 }
+inline int __all_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) == mask; }
+inline float __int_as_float(int v) { float f; std::memcpy(&f, &v, 4); return f; }
 inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __ffs(int v) { return __builtin_ffs(v); }
