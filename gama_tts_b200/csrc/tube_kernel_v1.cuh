@@ -147,13 +147,22 @@ GTTS_DEV void walk_block(const float* frames, long long nFrames, int steps, floa
 	const float d2 = __fmul_rn(__fsub_rn(nxt1, nxt0), invSteps);
 	const int restart = reaches ? first : -1;
 	float c = cur, d = delta;
+	if (!__any_sync(0xffffffffu, reaches)) {
+		// no control-period boundary in this block (the common case): store + add, 32 times
 #pragma unroll
-	for (int j = 0; j < kBlock; ++j) {
-		if (j == restart) { c = nxt0; d = d2; }
-		if (active) out[j * outStride] = c;
-		c = __fadd_rn(c, d);
+		for (int j = 0; j < kBlock; ++j) {
+			if (active) out[j * outStride] = c;
+			c = __fadd_rn(c, d);
+		}
+	} else {
+#pragma unroll 4
+		for (int j = 0; j < kBlock; ++j) {
+			if (j == restart) { c = nxt0; d = d2; }
+			if (active) out[j * outStride] = c;
+			c = __fadd_rn(c, d);
+		}
+		if (restart == kBlock) { c = nxt0; d = d2; }
 	}
-	if (restart == kBlock) { c = nxt0; d = d2; }
 	if (active) {
 		cur = c;
 		delta = d;
@@ -174,6 +183,7 @@ struct HelperRegs {
 	long long sec[6];             // profiling: cycles per section (walk, convert, noise, lookup, FIR, mix)
 	float cur, delta;             // lane 0: parameter 0 (block it); lanes 1..6: parameters 1..6 (block it - 2)
 	int off, frame;
+	unsigned long long mult;      // 377^(lane+1) mod 2^44, this lane's jump-ahead multiplier (loaded once)
 	unsigned long long lcg;       // noise generator state on the 2^-44 grid: next samples are lcg * 377^(j+1) mod 2^44
 	double noise_x1;
 	// conversions of the previous block, re-used while the parameter does not change (the reference
@@ -286,7 +296,7 @@ GTTS_DEV void helper_iteration(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int
 		// noise (NoiseSource.h:40-44 as the integer LCG it is, NoiseFilter.h:63-68)
 		double lp;
 		{
-			const unsigned long long sj = (h.lcg * c_lcg[lane]) & ((1ull << 44) - 1);
+			const unsigned long long sj = (h.lcg * h.mult) & ((1ull << 44) - 1);
 			const double n = (double) (long long) sj * (1.0 / 17592186044416.0) - 0.5;
 			double prev = shfl_d(n, (lane + 31) & 31, 32);
 			if (lane == 0) prev = h.noise_x1;
@@ -869,6 +879,7 @@ GTTS_DEV void tube_v1_cta_body(const KernelParamsV1& P, unsigned char* smem, int
 	ChainARegs ca = {0.0, {0.0, 0.0, 0.0, 0.0}};
 	ChainBRegs cb = {0.0, 0.0};
 	HelperRegs hr = {};
+	hr.mult = c_lcg[lane];
 
 	// Warp roles.  warp id % 4 selects the SM sub-partition; this assignment spreads the heavy issuers
 	// (7 slot helpers, 5 task workers) evenly over the four partitions next to one light warp each
