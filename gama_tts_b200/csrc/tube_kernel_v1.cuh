@@ -109,7 +109,7 @@ struct KernelParamsV1 {
 
 // ceil((n << 16) / inc): number of outputs whose right wing ends before input n (SampleRateConverter.h:
 // 295-361 as a closed form).  Double division plus an integer correction instead of a 64-bit divide.
-GTTS_DEV long long outputs_before(long long n, unsigned inc)
+GTTS_DEV_NOINLINE long long outputs_before(long long n, unsigned inc)
 {
 	const unsigned long long num = (unsigned long long) n << 16;
 	long long q = (long long) ((double) num / (double) inc);
@@ -128,14 +128,13 @@ GTTS_DEV int block_len(const SlotSm::Ctl& k, int b)
 // lane k walks parameter base + k: cur/delta/off/frame are the lane's cursor (registers or shared),
 // out[j][k] receives the value used for sample j.  Control periods are >= one block, so at most one
 // frame boundary falls inside the block.
-GTTS_DEV void walk_block(const float* frames, long long nFrames, int steps, float invSteps, int param,
+GTTS_DEV_NOINLINE void walk_block(const float* frames, long long nFrames, int steps, float invSteps, int param,
 			int nb, float& cur, float& delta, int& off, int& frame, float* out, int outStride, bool active)
 {
 	// `first` samples of the block still belong to the current control period; the period ends inside
 	// (or exactly at the end of) this block iff off + first == steps.  The next frame pair is fetched
-	// up front, the 32 steps are straight-line code: store, sequential float add, and a predicated
-	// restart from the next frame value at step `first` (the reference restarts from the frame value,
-	// not from the accumulated one: Controller.cpp:297-300).
+	// up front; at step `first` the walk restarts from the next frame value (the reference restarts
+	// from the frame value, not from the accumulated one: Controller.cpp:297-300).
 	const int first = (steps - off) < nb ? (steps - off) : nb;
 	const bool reaches = active && (off + first == steps);
 	float nxt0 = cur, nxt1 = cur;
@@ -147,22 +146,15 @@ GTTS_DEV void walk_block(const float* frames, long long nFrames, int steps, floa
 	const float d2 = __fmul_rn(__fsub_rn(nxt1, nxt0), invSteps);
 	const int restart = reaches ? first : -1;
 	float c = cur, d = delta;
-	if (!__any_sync(0xffffffffu, reaches)) {
-		// no control-period boundary in this block (the common case): store + add, 32 times
-#pragma unroll
-		for (int j = 0; j < kBlock; ++j) {
-			if (active) out[j * outStride] = c;
-			c = __fadd_rn(c, d);
-		}
-	} else {
-#pragma unroll 4
-		for (int j = 0; j < kBlock; ++j) {
-			if (j == restart) { c = nxt0; d = d2; }
-			if (active) out[j * outStride] = c;
-			c = __fadd_rn(c, d);
-		}
-		if (restart == kBlock) { c = nxt0; d = d2; }
+	float* o = out;
+#pragma unroll 2
+	for (int j = 0; j < kBlock; ++j) {
+		if (j == restart) { c = nxt0; d = d2; }
+		if (active) *o = c;
+		o += outStride;
+		c = __fadd_rn(c, d);
 	}
+	if (restart == kBlock) { c = nxt0; d = d2; }
 	if (active) {
 		cur = c;
 		delta = d;
@@ -586,6 +578,7 @@ GTTS_DEV void chain_a_iteration(CtaSm* C, const KernelParamsV1& P, int lane, Cha
 	bool anyFric = false;
 	// chunks of 4 samples: all operands of a chunk are loaded into registers before the two recurrences
 	// are stepped, so that shared-memory latency is paid once per chunk instead of once per sample
+#pragma unroll 1
 	for (int j0 = 0; j0 < kBlock; j0 += 4) {
 		double inc[4], x[4], b0[4], a1[4], a2[4], tA[4], tB[4];
 #pragma unroll
@@ -646,6 +639,7 @@ GTTS_DEV void chain_b_iteration(CtaSm* C, const KernelParamsV1& P, int lane, Cha
 		const double* scale = S->onepk7[(b % 3 + 3) % 3];
 		double* out = S->rad[f];
 		double x1 = r.x1, y1 = r.y1;
+#pragma unroll 1
 		for (int j0 = 0; j0 < kBlock; j0 += 8) {
 			double raw[8], sc[8], o[8];
 #pragma unroll
@@ -666,6 +660,7 @@ GTTS_DEV void chain_b_iteration(CtaSm* C, const KernelParamsV1& P, int lane, Cha
 	}
 	__syncwarp();
 	// output sum, lane = sample: (mouth + nose) + throat (VocalTractModel0.h:657-660, 441)
+#pragma unroll 1
 	for (int q = 0; q < kSlots; ++q) {
 		SlotSm* Q = &C->slot[q];
 		const SlotSm::Ctl& QK = Q->ctl[p];
@@ -719,6 +714,7 @@ GTTS_DEV void tube_iteration_impl(CtaSm* C, const KernelParamsV1& P, int warp, i
 	double* endRow = (g == 7) ? S->endn[buf] : S->endm[buf];
 	const int srcPrev = base + ((g + 7) & 7), srcNext = base + ((g + 1) & 7), srcLink = base + (is3 ? 5 : 1);
 	double aT = t.aT, aB = t.aB, bT = t.bT, bB = t.bB, extra = t.extra;
+#pragma unroll 1
 	for (int j0 = 0; j0 < kBlock; j0 += 4) {
 		// operands of 4 samples into registers first (one shared-memory latency per chunk)
 		double2 kkv[4], pabv[4];
@@ -783,8 +779,8 @@ GTTS_DEV void tube_iteration(CtaSm* C, const KernelParamsV1& P, int warp, int la
 		const int b = S->ctl[p].it - 4;
 		if (S->ctl[p].it >= 0 && b >= 0 && b < S->ctl[p].nblocks) fric = S->fric[b & 1];
 	}
-	if (__any_sync(0xffffffffu, fric != 0)) tube_iteration_impl<true>(C, P, warp, lane, t, p);
-	else tube_iteration_impl<false>(C, P, warp, lane, t, p);
+	(void) fric;   // both variants alternate from block to block; one copy keeps the instruction footprint small
+	tube_iteration_impl<true>(C, P, warp, lane, t, p);
 }
 
 // ---- slot bookkeeping for the NEXT iteration (chain A warp, lane = slot, after its chain work) ----------
@@ -814,6 +810,7 @@ GTTS_DEV void schedule_slots(CtaSm* C, const KernelParamsV1& P, int lane, int p,
 				const UttDesc U = P.utts[P.order[u]];
 				if (U.n_internal == 0) {
 					// no input at all: finishSynthesis() alone converts the 26 flush zeros into zeros
+#pragma unroll 1
 					for (long long k = 0; k < U.n_out; ++k) P.out[U.out_begin + k] = 0.0f;
 					continue;
 				}

@@ -1,0 +1,58 @@
+#!/usr/bin/env python
+"""Static SASS size per source function of tube_kernel_v1 (instruction-cache footprint), from
+`nvdisasm -g -c` of the cubin inside libgtts_b200.so.  No GPU needed.  python tools/sass_static.py"""
+import collections
+import glob
+import os
+import re
+import subprocess
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def func_ranges(path):
+    out, cur = [], None
+    for i, line in enumerate(open(path), 1):
+        m = re.match(r"^(?:GTTS_DEV_NOINLINE|GTTS_DEV|__global__|inline).*?\b([A-Za-z_0-9]+)\s*\(", line)
+        if m and not line.startswith(" "):
+            if cur:
+                out.append((cur[0], cur[1], i - 1))
+            cur = (m.group(1), i)
+    if cur:
+        out.append((cur[0], cur[1], 10 ** 9))
+    return out
+
+
+def main():
+    tmp = tempfile.mkdtemp()
+    so = os.path.join(ROOT, "gama_tts_b200", "csrc", "libgtts_b200.so")
+    subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, capture_output=True)
+    cubin = max(glob.glob(os.path.join(tmp, "*.cubin")), key=os.path.getsize)
+    dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout
+    ranges = {f: func_ranges(os.path.join(ROOT, "gama_tts_b200", "csrc", f)) for f in ("tube_kernel_v1.cuh", "tube_kernel.cuh")}
+    counts = collections.Counter()
+    section, key = None, "?"
+    for line in dis.splitlines():
+        m = re.match(r"\s*\.section\s+\.text\.(\S+)", line)
+        if m:
+            section = m.group(1)
+            continue
+        m = re.search(r'//## File "([^"]+)", line (\d+)', line)
+        if m:
+            f, l = os.path.basename(m.group(1)), int(m.group(2))
+            key = f
+            for name, a, b in ranges.get(f, []):
+                if a <= l <= b:
+                    key = f.replace("tube_kernel", "k").replace(".cuh", "") + ":" + name
+            continue
+        if section and "tube_kernel_v1" in section and re.match(r"\s+/\*[0-9a-f]{4,5}\*/", line):
+            counts[key] += 1
+    total = sum(counts.values())
+    print("tube_kernel_v1: %d SASS instructions, %.1f KB" % (total, total * 16 / 1024.0))
+    for k, v in counts.most_common(24):
+        print("  %-36s %5d" % (k, v))
+
+
+if __name__ == "__main__":
+    main()
