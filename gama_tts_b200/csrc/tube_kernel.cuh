@@ -95,17 +95,16 @@ extern unsigned long long c_lcg_init;
 
 GTTS_DEV double shfl_d(double v, int src, int width) { return __shfl_sync(0xffffffffu, v, src, width); }
 
-// Util::amplitude60dB (VTMUtil.h:50-67).  Not inlined: called several times per stage, and the pipelined
-// kernel is instruction-cache bound.
-GTTS_DEV_NOINLINE double amp60(double db)
+// Util::amplitude60dB (VTMUtil.h:50-67)
+GTTS_DEV double amp60(double db)
 {
 	if (db <= 0.0) return 0.0;
 	if (db == 60.0) return 1.0;
 	return gtts_exp10((db - 60.0) * (1.0 / 20.0));
 }
 
-// (a - b) / (a + b): scattering coefficient from two squared radii (not inlined, see amp60).
-GTTS_DEV_NOINLINE double kcoef(double a2, double b2) { return (a2 - b2) / (a2 + b2); }
+// (a - b) / (a + b): scattering coefficient from two squared radii.
+GTTS_DEV double kcoef(double a2, double b2) { return (a2 - b2) / (a2 + b2); }
 
 // ---- stage: float32 interpolation, lane = parameter (Controller.cpp:297-311) ----------------------------
 // Writes cur[j][k] for j < nb and advances the running value by nb sequential float additions.

@@ -128,7 +128,7 @@ GTTS_DEV int block_len(const SlotSm::Ctl& k, int b)
 // lane k walks parameter base + k: cur/delta/off/frame are the lane's cursor (registers or shared),
 // out[j][k] receives the value used for sample j.  Control periods are >= one block, so at most one
 // frame boundary falls inside the block.
-GTTS_DEV_NOINLINE void walk_block(const float* frames, long long nFrames, int steps, float invSteps, int param,
+GTTS_DEV void walk_block(const float* frames, long long nFrames, int steps, float invSteps, int param,
 			int nb, float& cur, float& delta, int& off, int& frame, float* out, int outStride, bool active)
 {
 	// `first` samples of the block still belong to the current control period; the period ends inside
@@ -235,26 +235,24 @@ GTTS_DEV void helper_iteration(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int
 			const bool live = lane < nb;
 			const float* p = S->cur[lane < nb ? lane : 0];
 			const float p1 = p[1], p2 = p[2], p3 = p[3], p5 = p[5], p6 = p[6];
-			const int last = nb - 1;
-			// glottal and aspiration amplitudes, frication amplitude (VTMUtil.h:50-67)
-			if (__all_sync(0xffffffffu, !live || p1 == h.c_p1)) {
-				ax = h.c_ax;
-			} else {
-				ax = amp60((double) p1);
-				h.c_p1 = __shfl_sync(0xffffffffu, p1, last, 32); h.c_ax = shfl_d(ax, last, 32);
-			}
-			if (__all_sync(0xffffffffu, !live || p2 == h.c_p2)) {
-				ah1 = h.c_ah1;
-			} else {
-				ah1 = amp60((double) p2);
-				h.c_p2 = __shfl_sync(0xffffffffu, p2, last, 32); h.c_ah1 = shfl_d(ah1, last, 32);
-			}
-			double fa;
-			if (__all_sync(0xffffffffu, !live || p3 == h.c_p3)) {
-				fa = h.c_fa;
-			} else {
-				fa = amp60((double) p3);
-				h.c_p3 = __shfl_sync(0xffffffffu, p3, last, 32); h.c_fa = shfl_d(fa, last, 32);
+			// glottal, aspiration and frication amplitudes (VTMUtil.h:50-67): one rolled loop over the three
+			// parameters.  A value is re-used while its parameter is uniform over the block and unchanged
+			// since the previous block (the reference caches the same way, e.g. BandpassFilter.h:93).
+			double fa = 0.0;
+#pragma unroll 1
+			for (int w = 0; w < 3; ++w) {
+				const float pw = w == 0 ? p1 : (w == 1 ? p2 : p3);
+				const float cp = w == 0 ? h.c_p1 : (w == 1 ? h.c_p2 : h.c_p3);
+				const double cv = w == 0 ? h.c_ax : (w == 1 ? h.c_ah1 : h.c_fa);
+				const float p0v = __shfl_sync(0xffffffffu, pw, 0, 32);
+				const float pe = live ? pw : p0v;
+				const bool uniform = __all_sync(0xffffffffu, pe == p0v);
+				double val;
+				if (uniform && p0v == cp) val = cv; else val = amp60((double) pe);
+				const float ncp = uniform ? p0v : __int_as_float(0x7fc00000);
+				if (w == 0) { ax = val; h.c_p1 = ncp; h.c_ax = val; }
+				else if (w == 1) { ah1 = val; h.c_p2 = ncp; h.c_ah1 = val; }
+				else { fa = val; h.c_p3 = ncp; h.c_fa = val; }
 			}
 			const double fpos = (double) p[4];
 			int ip = (int) fpos;
@@ -263,17 +261,23 @@ GTTS_DEV void helper_iteration(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int
 			if (ip < 0 || ip > 7) { ta = 0.0; tb = 0.0; ip = -50; }
 			// bandpass coefficients (BandpassFilter.h:91-110)
 			double a2, a1, b0;
-			if (__all_sync(0xffffffffu, !live || (p5 == h.c_p5 && p6 == h.c_p6))) {
-				a2 = h.c_a2; a1 = h.c_a1; b0 = h.c_b0;
-			} else {
-				const double pi = 3.14159265358979323846;
-				const double tv = tan(pi * (double) p6 * V.Ts);
-				const double cv = cos(2.0 * pi * (double) p5 * V.Ts);
-				a2 = (1.0 - tv) / (1.0 + tv);
-				a1 = -(1.0 + a2) * cv;
-				b0 = 0.5 - 0.5 * a2;
-				h.c_p5 = __shfl_sync(0xffffffffu, p5, last, 32); h.c_p6 = __shfl_sync(0xffffffffu, p6, last, 32);
-				h.c_a2 = shfl_d(a2, last, 32); h.c_a1 = shfl_d(a1, last, 32); h.c_b0 = shfl_d(b0, last, 32);
+			{
+				const float p50 = __shfl_sync(0xffffffffu, p5, 0, 32), p60 = __shfl_sync(0xffffffffu, p6, 0, 32);
+				const float e5 = live ? p5 : p50, e6 = live ? p6 : p60;
+				const bool uniform = __all_sync(0xffffffffu, e5 == p50 && e6 == p60);
+				if (uniform && p50 == h.c_p5 && p60 == h.c_p6) {
+					a2 = h.c_a2; a1 = h.c_a1; b0 = h.c_b0;
+				} else {
+					const double pi = 3.14159265358979323846;
+					const double tv = tan(pi * (double) e6 * V.Ts);
+					const double cv = cos(2.0 * pi * (double) e5 * V.Ts);
+					a2 = (1.0 - tv) / (1.0 + tv);
+					a1 = -(1.0 + a2) * cv;
+					b0 = 0.5 - 0.5 * a2;
+				}
+				h.c_p5 = uniform ? p50 : __int_as_float(0x7fc00000);
+				h.c_p6 = uniform ? p60 : __int_as_float(0x7fc00000);
+				h.c_a2 = a2; h.c_a1 = a1; h.c_b0 = b0;
 			}
 			if (live) {
 				S->tapa[buf][lane] = ta;
@@ -412,25 +416,44 @@ GTTS_DEV void coef_task(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int lane, 
 	}
 	__syncwarp();
 	if (lane < nb) {
+		// Nine scattering coefficients k = (a - b) / (a + b) in ONE rolled loop (the kernel is bound by its
+		// instruction footprint): i = 0..6 oral junctions r_i | r_{i+1}, i = 7 mouth r_8 | aperture,
+		// i = 8 velum | first nasal section.  Radii as in setAllParameters: max(r * coef, 0.01).
 		const float* p = scr[lane];
-		double r2[8];
-#pragma unroll
-		for (int i = 0; i < 8; ++i) {
-			double r = (double) p[i] * V.radius_coef[i];
-			r = r > 0.01 ? r : 0.01;
-			r2[i] = r * r;
-		}
+		const int buf = b & 1;
+		double* kabFlat = &S->kab[buf][0][0].x;         // [row][lane]{x, y} -> (row * kRow + lane) * 2 + c
 		const double vel = (double) p[8];
 		const double v2 = vel * vel;
-		const double sum = 2.0 / (r2[3] + r2[3] + v2);
-		const double k7 = kcoef(r2[7], V.ap2);
-		const int buf = b & 1;
-		S->kab[buf][0][lane] = make_double2(kcoef(r2[0], r2[1]), kcoef(r2[1], r2[2]));
-		S->kab[buf][1][lane] = make_double2(kcoef(r2[2], r2[3]), sum * r2[3]);
-		S->kab[buf][2][lane] = make_double2(kcoef(r2[3], r2[4]), 0.0);      // S6-S7 is a pure damped delay: k = 0
-		S->kab[buf][3][lane] = make_double2(kcoef(r2[4], r2[5]), kcoef(r2[5], r2[6]));
-		S->kab[buf][4][lane] = make_double2(kcoef(r2[6], r2[7]), k7);
-		S->kab[buf][5][lane] = make_double2(kcoef(v2, V.nr1_2), V.nasal_k[1]);
+		double a2, r2_3 = 0.0, k7 = 0.0;
+		{
+			double r = (double) p[0] * V.radius_coef[0];
+			r = r > 0.01 ? r : 0.01;
+			a2 = r * r;
+		}
+#pragma unroll 1
+		for (int i = 0; i < 9; ++i) {
+			double b2;
+			if (i < 7) {
+				double r = (double) p[i + 1] * V.radius_coef[i + 1];
+				r = r > 0.01 ? r : 0.01;
+				b2 = r * r;
+			} else if (i == 7) {
+				b2 = V.ap2;
+			} else {
+				a2 = v2;
+				b2 = V.nr1_2;
+			}
+			if (i == 3) r2_3 = a2;
+			const double k = kcoef(a2, b2);
+			if (i == 7) k7 = k;
+			const int dst = i <= 2 ? i : (i == 3 ? 4 : i + 2);     // (row, component) of junction i in the kab rows
+			kabFlat[((dst >> 1) * kRow + lane) * 2 + (dst & 1)] = k;
+			a2 = b2;
+		}
+		const double sum = 2.0 / (r2_3 + r2_3 + v2);
+		S->kab[buf][1][lane].y = sum * r2_3;                   // alpha left == alpha right (lane 1 of the tube)
+		S->kab[buf][2][lane].y = 0.0;                          // S6-S7 is a pure damped delay: k = 0
+		S->kab[buf][5][lane].y = V.nasal_k[1];
 		S->kab[buf][6][lane] = make_double2(V.nasal_k[2], V.nasal_k[3]);
 		S->kab[buf][7][lane] = make_double2(V.nasal_k[4], V.nasal_k[5]);
 		S->au[buf][lane] = sum * v2;
