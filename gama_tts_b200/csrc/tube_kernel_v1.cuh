@@ -54,12 +54,12 @@ struct SlotSm {
 	double rad[3][kRow];          // mouth radiation, nose radiation, throat outputs of one block
 	double ve[kVRing], vo[kVRing];
 	double xring[2 * kSrcRing];   // tube output ring, every sample stored twice (i and i + 128): any 26-sample window is contiguous
-	float  cur[kBlock][8];        // slot helper scratch: parameters 0..6 of the block being converted
+	float  cur[kBlock][7];        // slot helper scratch: parameters 0..6 of the block being converted
 	int    ip[3][kBlock];
 	VoiceDev V;                   // the slot's voice constants (copied from global memory when an utterance starts)
 	int    fric[2];               // block has frication (some tap * bandpassed noise != 0), per pab buffer
 	// coefficient-walk cursor (parameters 7..15), advanced by whichever pool warp runs the task
-	float  ccur[9], cdelta[9];
+	float  ccur[9], cdelta[9], cfn1[9], cfn2[9];
 	int    cframe, coff;
 	// control block, double-buffered by iteration parity: the scheduler lane writes ctl[p ^ 1] while the
 	// roles read ctl[p], so that one CTA barrier per iteration is enough
@@ -70,7 +70,7 @@ struct SlotSm {
 		int voice;
 		int pad;
 	} ctl[2];
-	int     pad_[2];              // slot stride = 16 mod 128 bytes: the 7 slots start in different banks
+	int     pad_[16];              // slot stride = 16 mod 128 bytes: the 7 slots start in different banks
 };
 static_assert(sizeof(SlotSm) % 128 == 16, "slot stride should be 16 mod 128 bytes (bank spreading); adjust pad_");
 
@@ -129,22 +129,23 @@ GTTS_DEV int block_len(const SlotSm::Ctl& k, int b)
 // lane k walks parameter base + k: cur/delta/off/frame are the lane's cursor (registers or shared),
 // out[j][k] receives the value used for sample j.  Control periods are >= one block, so at most one
 // frame boundary falls inside the block.
+// The cursor carries the next two frame values (fn1 = frame[f+1], fn2 = frame[f+2], clamped to the last
+// frame): they are fetched from global memory one control period ahead, so no load sits on the walk.
 GTTS_DEV void walk_block(const float* frames, long long nFrames, int steps, float invSteps, int param,
-			int nb, float& cur, float& delta, int& off, int& frame, float* out, int outStride, bool active)
+			int nb, float& cur, float& delta, float& fn1, float& fn2, int& off, int& frame,
+			float* out, int outStride, bool active)
 {
 	// `first` samples of the block still belong to the current control period; the period ends inside
-	// (or exactly at the end of) this block iff off + first == steps.  The next frame pair is fetched
-	// up front; at step `first` the walk restarts from the next frame value (the reference restarts
-	// from the frame value, not from the accumulated one: Controller.cpp:297-300).
+	// (or exactly at the end of) this block iff off + first == steps.  At step `first` the walk restarts
+	// from the next frame value (the reference restarts from the frame value, not from the accumulated
+	// one: Controller.cpp:297-300).
 	const int first = (steps - off) < nb ? (steps - off) : nb;
 	const bool reaches = active && (off + first == steps);
-	float nxt0 = cur, nxt1 = cur;
-	if (reaches && frame + 1 < nFrames) {
-		const long long f1 = frame + 1;
-		nxt0 = frames[f1 * kNumParams + param];
-		nxt1 = (f1 + 1 < nFrames) ? frames[(f1 + 1) * kNumParams + param] : nxt0;
-	}
-	const float d2 = __fmul_rn(__fsub_rn(nxt1, nxt0), invSteps);
+	const float nxt0 = fn1;
+	const float d2 = __fmul_rn(__fsub_rn(fn2, fn1), invSteps);
+	// refill for the boundary after this one: frame[f+3] (needed a whole control period from now)
+	float refill = fn2;
+	if (reaches && (long long) frame + 3 < nFrames) refill = frames[((long long) frame + 3) * kNumParams + param];
 	const int restart = reaches ? first : -1;
 	float c = cur, d = delta;
 	float* o = out;
@@ -159,22 +160,27 @@ GTTS_DEV void walk_block(const float* frames, long long nFrames, int steps, floa
 	if (active) {
 		cur = c;
 		delta = d;
-		if (reaches) { frame += 1; off = nb - first; } else { off += nb; }
+		if (reaches) { frame += 1; off = nb - first; fn1 = fn2; fn2 = refill; } else { off += nb; }
 	}
 }
 
-GTTS_DEV void cursor_init(const float* frames, long long nFrames, float invSteps, int param, float& cur, float& delta)
+GTTS_DEV void cursor_init(const float* frames, long long nFrames, float invSteps, int param,
+			float& cur, float& delta, float& fn1, float& fn2)
 {
 	const float a = frames[param];
 	const float b = (nFrames > 1) ? frames[kNumParams + param] : a;
+	const float c = (nFrames > 2) ? frames[2 * kNumParams + param] : b;
 	cur = a;
 	delta = __fmul_rn(__fsub_rn(b, a), invSteps);
+	fn1 = b;
+	fn2 = c;
 }
 
 // ---- slot helper (warp 4 + s): stages at it = b and it = b + 2 ------------------------------------------
 struct HelperRegs {
 	long long sec[6];             // profiling: cycles per section (walk, convert, noise, lookup, FIR, mix)
 	float cur, delta;             // lane 0: parameter 0 (block it); lanes 1..6: parameters 1..6 (block it - 2)
+	float fn1, fn2;               // next two frame values of the lane's parameter (prefetched)
 	int off, frame;
 	unsigned long long mult;      // 377^(lane+1) mod 2^44, this lane's jump-ahead multiplier (loaded once)
 	unsigned long long lcg;       // noise generator state on the 2^-44 grid: next samples are lcg * 377^(j+1) mod 2^44
@@ -203,14 +209,14 @@ GTTS_DEV void helper_iteration(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int
 		// new utterance: clear the rings, reset cursors and the noise generator
 		for (int i = lane; i < kVRing; i += 32) { S->ve[i] = 0.0; S->vo[i] = 0.0; }
 		for (int i = lane; i < 2 * kSrcRing; i += 32) S->xring[i] = 0.0;
-		if (lane < 7) cursor_init(frames, nFrames, K.U.inv_steps, lane, h.cur, h.delta);
+		if (lane < 7) cursor_init(frames, nFrames, K.U.inv_steps, lane, h.cur, h.delta, h.fn1, h.fn2);
 		h.off = 0; h.frame = 0;
 		h.lcg = c_lcg_init; h.noise_x1 = 0.0;
 		h.c_p1 = h.c_p2 = h.c_p3 = h.c_p5 = h.c_p6 = __int_as_float(0x7fc00000);     // NaN: nothing cached
 		if (lane < 9) {
-			float c, d;
-			cursor_init(frames, nFrames, K.U.inv_steps, 7 + lane, c, d);
-			S->ccur[lane] = c; S->cdelta[lane] = d;
+			float c, d, f1, f2;
+			cursor_init(frames, nFrames, K.U.inv_steps, 7 + lane, c, d, f1, f2);
+			S->ccur[lane] = c; S->cdelta[lane] = d; S->cfn1[lane] = f1; S->cfn2[lane] = f2;
 		}
 		if (lane == 0) { S->cframe = 0; S->coff = 0; }
 		__syncwarp();
@@ -222,8 +228,8 @@ GTTS_DEV void helper_iteration(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int
 	{
 		const bool mine = (lane == 0) ? do0 : (lane < 7 && do2);
 		const int nb = (lane == 0) ? block_len(K, b0) : block_len(K, b2);
-		walk_block(frames, nFrames, K.U.steps, K.U.inv_steps, lane, nb, h.cur, h.delta, h.off, h.frame,
-				&S->cur[0][lane], 8, mine);
+		walk_block(frames, nFrames, K.U.steps, K.U.inv_steps, lane, nb, h.cur, h.delta, h.fn1, h.fn2, h.off, h.frame,
+				&S->cur[0][lane < 7 ? lane : 0], 7, mine);
 	}
 	__syncwarp();
 	{ const long long tn = GTTS_CLOCK(); h.sec[0] += tn - tq; tq = tn; }
@@ -412,13 +418,13 @@ GTTS_DEV void coef_task(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int lane, 
 	const int nb = block_len(K, b);
 	float (*scr)[9] = C->pscratch[slotIndex];
 	{
-		float cur = 0.f, delta = 0.f;
+		float cur = 0.f, delta = 0.f, f1 = 0.f, f2 = 0.f;
 		int off = S->coff, frame = S->cframe;
-		if (lane < 9) { cur = S->ccur[lane]; delta = S->cdelta[lane]; }
+		if (lane < 9) { cur = S->ccur[lane]; delta = S->cdelta[lane]; f1 = S->cfn1[lane]; f2 = S->cfn2[lane]; }
 		__syncwarp();
-		walk_block(frames, K.U.n_frames, K.U.steps, K.U.inv_steps, 7 + lane, nb, cur, delta, off, frame,
+		walk_block(frames, K.U.n_frames, K.U.steps, K.U.inv_steps, 7 + lane, nb, cur, delta, f1, f2, off, frame,
 				&scr[0][lane], 9, lane < 9);
-		if (lane < 9) { S->ccur[lane] = cur; S->cdelta[lane] = delta; }
+		if (lane < 9) { S->ccur[lane] = cur; S->cdelta[lane] = delta; S->cfn1[lane] = f1; S->cfn2[lane] = f2; }
 		if (lane == 0) { S->coff = off; S->cframe = frame; }
 	}
 	__syncwarp();
