@@ -162,17 +162,7 @@ int launchBatch(gtts_batch* b, const float* dFrames, float* dOut, cudaStream_t s
 			std::fprintf(stderr, "[gtts profile] grid %d, iterations per CTA %.0f; busy cycles per iteration by warp:", grid, iters / grid);
 			for (int w = 0; w < v1::kWarps; ++w) std::fprintf(stderr, " %d:%.0f", w, sum[w] / (iters > 0 ? iters : 1));
 			std::fprintf(stderr, "\n");
-			std::vector<long long> hs(static_cast<size_t>(grid) * 6);
-			GTTS_CUDA(cudaMemcpy(hs.data(), Q.prof_sections, sizeof(long long) * hs.size(), cudaMemcpyDeviceToHost));
 			cudaFree(Q.prof_sections);
-			const char* names[6] = {"walk", "convert", "noise", "lookup", "fir", "mix"};
-			std::fprintf(stderr, "[gtts profile] helper sections (cycles per iteration):");
-			for (int q = 0; q < 6; ++q) {
-				double t = 0;
-				for (int c = 0; c < grid; ++c) t += static_cast<double>(hs[static_cast<size_t>(c) * 6 + q]);
-				std::fprintf(stderr, " %s:%.0f", names[q], t / (iters > 0 ? iters : 1));
-			}
-			std::fprintf(stderr, "\n");
 		}
 		b->last_kernel = "tube_kernel_v1";
 	} else {

@@ -178,7 +178,6 @@ GTTS_DEV void cursor_init(const float* frames, long long nFrames, float invSteps
 
 // ---- slot helper (warp 4 + s): stages at it = b and it = b + 2 ------------------------------------------
 struct HelperRegs {
-	long long sec[6];             // profiling: cycles per section (walk, convert, noise, lookup, FIR, mix)
 	float cur, delta;             // lane 0: parameter 0 (block it); lanes 1..6: parameters 1..6 (block it - 2)
 	float fn1, fn2;               // next two frame values of the lane's parameter (prefetched)
 	int off, frame;
@@ -223,7 +222,6 @@ GTTS_DEV void helper_iteration(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int
 	}
 	const int b0 = it, b2 = it - 2;
 	const bool do0 = b0 < K.nblocks, do2 = b2 >= 0 && b2 < K.nblocks;
-	long long tq = GTTS_CLOCK();
 	// one walk loop serves both cursors: lane 0 (block b0), lanes 1..6 (block b2)
 	{
 		const bool mine = (lane == 0) ? do0 : (lane < 7 && do2);
@@ -232,7 +230,6 @@ GTTS_DEV void helper_iteration(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int
 				&S->cur[0][lane < 7 ? lane : 0], 7, mine);
 	}
 	__syncwarp();
-	{ const long long tn = GTTS_CLOCK(); h.sec[0] += tn - tq; tq = tn; }
 	if (do0) {
 		const int nb = block_len(K, b0);
 		if (lane < nb) {
@@ -301,7 +298,6 @@ GTTS_DEV void helper_iteration(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int
 				S->bp[buf][0][lane] = b0;
 			}
 		}
-		{ const long long tn = GTTS_CLOCK(); h.sec[1] += tn - tq; tq = tn; }
 		// noise (NoiseSource.h:40-44 as the integer LCG it is, NoiseFilter.h:63-68)
 		double lp;
 		{
@@ -313,7 +309,6 @@ GTTS_DEV void helper_iteration(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int
 			h.lcg = __shfl_sync(0xffffffffu, sj, nb - 1, 32);
 			lp = n + prev;
 		}
-		{ const long long tn = GTTS_CLOCK(); h.sec[2] += tn - tq; tq = tn; }
 		// wavetable lookup of both half samples (WavetableGlottalSource.h:212-228)
 		if (lane < nb) {
 			const double* table = P.tables + (size_t) K.voice * kTableLen;
@@ -350,7 +345,6 @@ GTTS_DEV void helper_iteration(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int
 			S->vo[24 + lane] = v[1];
 		}
 		__syncwarp();
-		{ const long long tn = GTTS_CLOCK(); h.sec[3] += tn - tq; tq = tn; }
 		double firOut = 0.0;
 		{
 			// y = sum_i c[i] x2[2n+1-i], i ascending: taps 2m and 2m+1 read the odd and the even phase of
@@ -379,7 +373,6 @@ GTTS_DEV void helper_iteration(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int
 			firOut = acc;
 		}
 		__syncwarp();
-		{ const long long tn = GTTS_CLOCK(); h.sec[4] += tn - tq; tq = tn; }
 		if (lane < 24) {
 			// slide the window: the last 24 samples become the history of the next block
 			S->ve[lane] = S->ve[32 + lane];      // source [32, 56) and destination [0, 24) do not overlap
@@ -402,7 +395,6 @@ GTTS_DEV void helper_iteration(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int
 			S->in[b2 % 3][lane] = (pulse + (ah1 * sig)) * 0.125;
 			S->thr[b2 & 3][lane] = pulse * 0.125;
 		}
-		{ const long long tn = GTTS_CLOCK(); h.sec[5] += tn - tq; tq = tn; }
 	}
 	(void) C;
 }
@@ -971,9 +963,6 @@ GTTS_DEV void tube_v1_cta_body(const KernelParamsV1& P, unsigned char* smem, int
 	if (P.prof != nullptr && lane == 0) {
 		P.prof[(size_t) blockIdx.x * (kWarps + 1) + warp] = busy;
 		if (warp == 0) P.prof[(size_t) blockIdx.x * (kWarps + 1) + kWarps] = iters;
-		if (warp == kHelper0 && P.prof_sections != nullptr) {
-			for (int q = 0; q < 6; ++q) P.prof_sections[(size_t) blockIdx.x * 6 + q] = hr.sec[q];
-		}
 	}
 #endif
 }
