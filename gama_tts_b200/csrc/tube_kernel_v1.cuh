@@ -435,7 +435,7 @@ GTTS_DEV void coef_task(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int lane, 
 			r = r > 0.01 ? r : 0.01;
 			a2 = r * r;
 		}
-#pragma unroll 1
+#pragma unroll 3
 		for (int i = 0; i < 9; ++i) {
 			double b2;
 			if (i < 7) {
@@ -918,10 +918,10 @@ GTTS_DEV void tube_v1_cta_body(const KernelParamsV1& P, unsigned char* smem, int
 	const bool isChainA = warp == kChainAWarp, isChainB = warp == kChainBWarp;
 	const bool isHelper = warp >= kHelper0 && warp < kPool0;
 	const int helperSlot = warp - kHelper0;
-	// Task workers: five pool warps and chain B (chain A also does the slot bookkeeping and takes no task).
-	// Task t of an iteration (SRC tasks, then one coefficient task per slot) goes to worker t mod 6; no atomics.
-	const int worker = warp >= kPool0 ? warp - kPool0 : (isChainB ? kPoolWarps : -1);
-	const int nWorkers = kPoolWarps + 1;
+	// Task workers: five pool warps, chain B and chain A (after its chain work and the slot bookkeeping).
+	// Task t of an iteration (SRC tasks, then one coefficient task per slot) goes to worker t mod 7; no atomics.
+	const int worker = warp >= kPool0 ? warp - kPool0 : (isChainB ? kPoolWarps : (isChainA ? kPoolWarps + 1 : -1));
+	const int nWorkers = kPoolWarps + 2;
 
 	long long busy = 0, iters = 0;
 	while (C->sched[p].live) {
