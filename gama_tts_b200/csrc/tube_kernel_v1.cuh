@@ -60,6 +60,7 @@ struct SlotSm {
 	int    fric[2];               // block has frication (some tap * bandpassed noise != 0), per pab buffer
 	// coefficient-walk cursor (parameters 7..15), advanced by whichever pool warp runs the task
 	float  ccur[9], cdelta[9], cfn1[9], cfn2[9];
+	float  ckey[9];               // parameters 7..15 at the last sample of the previous block (NaN: none)
 	int    cframe, coff;
 	// control block, double-buffered by iteration parity: the scheduler lane writes ctl[p ^ 1] while the
 	// roles read ctl[p], so that one CTA barrier per iteration is enough
@@ -70,7 +71,7 @@ struct SlotSm {
 		int voice;
 		int pad;
 	} ctl[2];
-	int     pad_[16];              // slot stride = 16 mod 128 bytes: the 7 slots start in different banks
+	int     pad_[7];              // slot stride = 16 mod 128 bytes: the 7 slots start in different banks
 };
 static_assert(sizeof(SlotSm) % 128 == 16, "slot stride should be 16 mod 128 bytes (bank spreading); adjust pad_");
 
@@ -148,15 +149,25 @@ GTTS_DEV void walk_block(const float* frames, long long nFrames, int steps, floa
 	if (reaches && (long long) frame + 3 < nFrames) refill = frames[((long long) frame + 3) * kNumParams + param];
 	const int restart = reaches ? first : -1;
 	float c = cur, d = delta;
-	float* o = out;
+	float* o = active ? out : nullptr;
+	if (!__any_sync(0xffffffffu, reaches)) {
+		// no control-period boundary for any lane in this block (about half of the blocks): store + add
+		if (o != nullptr) {
+#pragma unroll 8
+			for (int j = 0; j < kBlock; ++j) {
+				o[j * outStride] = c;
+				c = __fadd_rn(c, d);
+			}
+		}
+	} else {
 #pragma unroll 2
-	for (int j = 0; j < kBlock; ++j) {
-		if (j == restart) { c = nxt0; d = d2; }
-		if (active) *o = c;
-		o += outStride;
-		c = __fadd_rn(c, d);
+		for (int j = 0; j < kBlock; ++j) {
+			if (j == restart) { c = nxt0; d = d2; }
+			if (o != nullptr) o[j * outStride] = c;
+			c = __fadd_rn(c, d);
+		}
+		if (restart == kBlock) { c = nxt0; d = d2; }
 	}
-	if (restart == kBlock) { c = nxt0; d = d2; }
 	if (active) {
 		cur = c;
 		delta = d;
@@ -353,23 +364,12 @@ GTTS_DEV void helper_iteration(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int
 			const double* pe = S->ve + 24 + lane;
 			const double* po = S->vo + 24 + lane;
 			double acc = 0.0;
-			double xo[4], xe[4];
 #pragma unroll
-			for (int q = 0; q < 4; ++q) { xo[q] = po[-q]; xe[q] = pe[-q]; }
-#pragma unroll 1
-			for (int m0 = 0; m0 < 24; m0 += 4) {
-				double no[4], ne[4];
-#pragma unroll
-				for (int q = 0; q < 4; ++q) { no[q] = po[-(m0 + 4 + q)]; ne[q] = (m0 + 4 + q <= 23) ? pe[-(m0 + 4 + q)] : 0.0; }
-#pragma unroll
-				for (int q = 0; q < 4; ++q) {
-					acc += xo[q] * c_fir[2 * (m0 + q)];
-					acc += xe[q] * c_fir[2 * (m0 + q) + 1];
-				}
-#pragma unroll
-				for (int q = 0; q < 4; ++q) { xo[q] = no[q]; xe[q] = ne[q]; }
+			for (int m = 0; m < 24; ++m) {
+				acc += po[-m] * c_fir[2 * m];
+				acc += pe[-m] * c_fir[2 * m + 1];
 			}
-			acc += xo[0] * c_fir[48];
+			acc += po[-24] * c_fir[48];
 			firOut = acc;
 		}
 		__syncwarp();
@@ -420,7 +420,30 @@ GTTS_DEV void coef_task(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int lane, 
 		if (lane == 0) { S->coff = off; S->cframe = frame; }
 	}
 	__syncwarp();
+	// Radii and velum unchanged since the last sample of the previous block (a held posture): the
+	// coefficients are the previous block's last row, copied instead of recomputed (9 divisions saved).
+	const int buf0 = b & 1;
+	bool same = lane >= nb;
 	if (lane < nb) {
+		const float* q = scr[lane];
+		same = true;
+#pragma unroll
+		for (int i = 0; i < 9; ++i) same = same && (q[i] == S->ckey[i]);
+	}
+	const bool reuse = b > 0 && __all_sync(0xffffffffu, same);
+	__syncwarp();
+	if (lane == kBlock - 1) {
+#pragma unroll
+		for (int i = 0; i < 9; ++i) S->ckey[i] = (nb == kBlock) ? scr[lane][i] : __int_as_float(0x7fc00000);
+	}
+	if (reuse) {
+		if (lane < nb) {
+#pragma unroll
+			for (int r = 0; r < 8; ++r) S->kab[buf0][r][lane] = S->kab[buf0 ^ 1][r][kBlock - 1];
+			S->au[buf0][lane] = S->au[buf0 ^ 1][kBlock - 1];
+			S->onepk7[b % 3][lane] = S->onepk7[(b + 2) % 3][kBlock - 1];
+		}
+	} else if (lane < nb) {
 		// Nine scattering coefficients k = (a - b) / (a + b) in ONE rolled loop (the kernel is bound by its
 		// instruction footprint): i = 0..6 oral junctions r_i | r_{i+1}, i = 7 mouth r_8 | aperture,
 		// i = 8 velum | first nasal section.  Radii as in setAllParameters: max(r * coef, 0.01).
