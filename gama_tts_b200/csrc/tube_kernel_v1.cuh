@@ -26,13 +26,13 @@ namespace v1 {
 
 enum {
 	kSlots = 7,
-	kWarps = 16,
+	kWarps = 24,
 	kThreads = kWarps * 32,
 	kTubeWarps = 2,
 	kChainAWarp = 2,
 	kChainBWarp = 3,
 	kHelper0 = 4,                 // warps 4..10: slot helpers
-	kPool0 = kHelper0 + kSlots,   // warps 11..15: pool
+	kPool0 = kHelper0 + kSlots,   // warps 11..23: task workers
 	kPoolWarps = kWarps - kPool0,
 	kStages = 6,                  // last stage (SRC) runs at it = b + 6
 	kRow = 33,
@@ -909,85 +909,85 @@ GTTS_DEV void schedule_slots(CtaSm* C, const KernelParamsV1& P, int lane, int p,
 	}
 }
 
-GTTS_DEV void tube_v1_cta_body(const KernelParamsV1& P, unsigned char* smem, int tid)
+// One task of the per-iteration task list: SRC tasks first, then one coefficient task per slot.
+GTTS_DEV void run_task(CtaSm* C, const KernelParamsV1& P, int lane, int task, int p)
 {
-	CtaSm* C = reinterpret_cast<CtaSm*>(smem);
-	// Role index = 15 - hardware warp id: the warp scheduler of a sub-partition favours the highest warp id
-	// among its eligible warps, so the latency-critical roles (tube, then the chains) get the highest ids
-	// and the throughput roles (helpers, task workers) the lowest.
-	const int warp = (kWarps - 1) - (tid >> 5), lane = tid & 31;
-	for (int i = tid; i < kSrcFilterLen; i += kThreads) C->tab[i] = P.src_tab[i];
-	if (tid < kSlots) {
-		for (int b = 0; b < 2; ++b) { C->slot[tid].ctl[b].it = -1; C->slot[tid].ctl[b].voice = 0; C->slot[tid].ctl[b].nblocks = 0; }
-	}
-	__syncthreads();
-	int p = 1;
-	if (warp == kChainAWarp) schedule_slots(C, P, lane, p, true);      // fills ctl[0] / sched[0]
-	__syncthreads();
-	p = 0;
-
-	TubeLane tl = {0.0, 0.0, 0.0, 0.0, 0.0};
-	ChainARegs ca = {0.0, {0.0, 0.0, 0.0, 0.0}};
-	ChainBRegs cb = {0.0, 0.0};
-	HelperRegs hr = {};
-	hr.mult = c_lcg[lane];
-
-	// Warp roles.  warp id % 4 selects the SM sub-partition; this assignment spreads the heavy issuers
-	// (7 slot helpers, 5 task workers) evenly over the four partitions next to one light warp each
-	// (measured: packing the helpers on two partitions is 13 % slower).
-	//   partition 0: 0 tube, 4 helper, 8 helper, 12 worker      partition 2: 2 chain A, 6 helper, 10 helper, 14 worker
-	//   partition 1: 1 tube, 5 helper, 9 helper, 13 worker      partition 3: 3 chain B, 7 helper, 11 worker, 15 worker
-	const bool isTube = warp < kTubeWarps;
-	const bool isChainA = warp == kChainAWarp, isChainB = warp == kChainBWarp;
-	const bool isHelper = warp >= kHelper0 && warp < kPool0;
-	const int helperSlot = warp - kHelper0;
-	// Task workers: five pool warps, chain B and chain A (after its chain work and the slot bookkeeping).
-	// Task t of an iteration (SRC tasks, then one coefficient task per slot) goes to worker t mod 7; no atomics.
-	const int worker = warp >= kPool0 ? warp - kPool0 : (isChainB ? kPoolWarps : (isChainA ? kPoolWarps + 1 : -1));
-	const int nWorkers = kPoolWarps + 2;
-
-	long long busy = 0, iters = 0;
-	while (C->sched[p].live) {
-		const long long tStart = GTTS_CLOCK();
-		const int skip = P.debug_skip;
-		if (isTube) {
-			if (!(skip & 32)) tube_iteration(C, P, warp, lane, tl, p);
-		} else {
-			if (isChainA) {
-				if (!(skip & 8)) chain_a_iteration(C, P, lane, ca, p);
-				schedule_slots(C, P, lane, p, false);
-			} else if (isChainB) {
-				if (!(skip & 16)) chain_b_iteration(C, P, lane, cb, p);
-			} else if (isHelper) {
-				SlotSm* S = &C->slot[helperSlot];
-				if (!(skip & 4)) helper_iteration(C, S, P, lane, hr, p);
-			}
-			if (worker >= 0) {
-				const int nSrc = C->sched[p].src_tasks;
-				const bool shared = C->sched[p].src_shared != 0;
-				for (int task = worker; task < nSrc + kSlots; task += nWorkers) {
-					if (task < nSrc) {
-						if (!(skip & 1)) {
-							if (shared) src_shared_task(C, P, lane, task, p);
-							else src_task(C, &C->slot[task], P, lane, p);
-						}
-					} else if (!(skip & 2)) {
-						coef_task(C, &C->slot[task - nSrc], P, lane, task - nSrc, p);
-					}
-				}
-			}
+	const int skip = P.debug_skip;
+	const int nSrc = C->sched[p].src_tasks;
+	if (task < nSrc) {
+		if (!(skip & 1)) {
+			if (C->sched[p].src_shared) src_shared_task(C, P, lane, task, p);
+			else src_task(C, &C->slot[task], P, lane, p);
 		}
-		busy += GTTS_CLOCK() - tStart;
-		iters += 1;
-		__syncthreads();
-		p ^= 1;
+	} else if (task < nSrc + kSlots) {
+		if (!(skip & 2)) coef_task(C, &C->slot[task - nSrc], P, lane, task - nSrc, p);
 	}
+}
+
+// Every role runs its OWN iteration loop (one CTA barrier per iteration each), so that a warp keeps only
+// its own role's state in registers: ~80 registers per thread instead of 128, which is what lets 24 warps
+// share the register file.
+#define GTTS_ROLE_LOOP(BODY)                                                     \
+	{                                                                            \
+		int p = 0;                                                               \
+		long long busy = 0, iters = 0;                                           \
+		while (C->sched[p].live) {                                               \
+			const long long tStart = GTTS_CLOCK();                               \
+			BODY                                                                 \
+			busy += GTTS_CLOCK() - tStart;                                       \
+			iters += 1;                                                          \
+			__syncthreads();                                                     \
+			p ^= 1;                                                              \
+		}                                                                        \
+		role_profile(P, warp, lane, busy, iters);                                \
+	}
+
+GTTS_DEV void role_profile(const KernelParamsV1& P, int warp, int lane, long long busy, long long iters)
+{
 #ifndef GTTS_EMU
 	if (P.prof != nullptr && lane == 0) {
 		P.prof[(size_t) blockIdx.x * (kWarps + 1) + warp] = busy;
 		if (warp == 0) P.prof[(size_t) blockIdx.x * (kWarps + 1) + kWarps] = iters;
 	}
+#else
+	(void) P; (void) warp; (void) lane; (void) busy; (void) iters;
 #endif
+}
+
+GTTS_DEV void tube_v1_cta_body(const KernelParamsV1& P, unsigned char* smem, int tid)
+{
+	CtaSm* C = reinterpret_cast<CtaSm*>(smem);
+	const int warp = tid >> 5, lane = tid & 31;
+	for (int i = tid; i < kSrcFilterLen; i += kThreads) C->tab[i] = P.src_tab[i];
+	if (tid < kSlots) {
+		for (int b = 0; b < 2; ++b) { C->slot[tid].ctl[b].it = -1; C->slot[tid].ctl[b].voice = 0; C->slot[tid].ctl[b].nblocks = 0; }
+	}
+	__syncthreads();
+	if (warp == kChainAWarp) schedule_slots(C, P, lane, 1, true);      // fills ctl[0] / sched[0]
+	__syncthreads();
+
+	// Warp roles (warp id % 4 selects the SM sub-partition; the heavy issuers are spread evenly):
+	//   0-1 tube, 2 chain A (+ slot bookkeeping), 3 chain B, 4-10 slot helpers, 11-23 task workers.
+	// Task t of an iteration goes to worker t mod 13: with at most 10-14 tasks nearly every worker has one.
+	const int skip = P.debug_skip;
+	if (warp < kTubeWarps) {
+		TubeLane tl = {0.0, 0.0, 0.0, 0.0, 0.0};
+		GTTS_ROLE_LOOP(if (!(skip & 32)) tube_iteration(C, P, warp, lane, tl, p);)
+	} else if (warp == kChainAWarp) {
+		ChainARegs ca = {0.0, {0.0, 0.0, 0.0, 0.0}};
+		GTTS_ROLE_LOOP(if (!(skip & 8)) chain_a_iteration(C, P, lane, ca, p); schedule_slots(C, P, lane, p, false);)
+	} else if (warp == kChainBWarp) {
+		ChainBRegs cb = {0.0, 0.0};
+		GTTS_ROLE_LOOP(if (!(skip & 16)) chain_b_iteration(C, P, lane, cb, p);)
+	} else if (warp < kPool0) {
+		HelperRegs hr = {};
+		hr.mult = c_lcg[lane];
+		SlotSm* S = &C->slot[warp - kHelper0];
+		GTTS_ROLE_LOOP(if (!(skip & 4)) helper_iteration(C, S, P, lane, hr, p);)
+	} else {
+		const int worker = warp - kPool0;
+		GTTS_ROLE_LOOP(for (int task = worker; task < C->sched[p].src_tasks + kSlots; task += kPoolWarps) run_task(C, P, lane, task, p);)
+	}
 }
 
 #ifndef GTTS_EMU
