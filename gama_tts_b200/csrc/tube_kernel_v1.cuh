@@ -749,7 +749,7 @@ GTTS_DEV void tube_iteration_impl(CtaSm* C, const KernelParamsV1& P, int warp, i
 	const SlotSm::Ctl& K = S->ctl[p];
 	const int b = (slot < kSlots) ? K.it - 4 : -1;
 	const VoiceDev& V = S->V;
-	if (b == 0) { t.aT = t.aB = t.bT = t.bB = t.extra = 0.0; }
+	if (b == 0) { t.aT = t.aB = t.bT = t.bB = t.extra = t.nb0 = t.y1 = 0.0; }
 	const double d = V.damping;
 	const bool is3 = g == 1, isEnd = (g == 4) || (g == 7), isGlot = g == 0, isN0 = g == 5;
 	const bool storesEnd = isEnd && slot < kSlots;     // the 8th group of warp 1 is a dummy: it must not store
@@ -764,7 +764,10 @@ GTTS_DEV void tube_iteration_impl(CtaSm* C, const KernelParamsV1& P, int warp, i
 	const int* ipRow = S->ip[b3];
 	double* endRow = (g == 7) ? S->endn[buf] : S->endm[buf];
 	const int srcPrev = base + ((g + 7) & 7), srcNext = base + ((g + 1) & 7), srcLink = base + (is3 ? 5 : 1);
-	double aT = t.aT, aB = t.aB, bT = t.bT, bB = t.bB, extra = t.extra;
+	// gB = B[S1] (used by lane 0), nb0 = NB[N1] (lane 1), y1 = reflection filter state (lanes 4, 7): every
+	// lane updates all three unconditionally (values on the other lanes are never used), which saves the
+	// per-sample role selects
+	double aT = t.aT, aB = t.aB, bT = t.bT, bB = t.bB, gB = t.extra, nb0 = t.nb0, y1 = t.y1;
 #pragma unroll 1
 	for (int j0 = 0; j0 < kBlock; j0 += 4) {
 		// operands of 4 samples into registers first (one shared-memory latency per chunk)
@@ -797,10 +800,10 @@ GTTS_DEV void tube_iteration_impl(CtaSm* C, const KernelParamsV1& P, int warp, i
 			const double dlB = kk.y * (bT - bB);
 			const double tU = bT + dlB, tW = bB + dlB;
 			// cell B, 3-way junction (lane 1): bT = T[S4], bB = B[S5], extra = NB[N1]; kk.y = alpha, ex = alpha upper
-			const double jp = (kk.y * bT) + (kk.y * bB) + (ex * extra);
-			const double pU = jp - bB, pW = jp - bT, pX = jp - extra;
+			const double jp = (kk.y * bT) + (kk.y * bB) + (ex * nb0);
+			const double pU = jp - bB, pW = jp - bT, pX = jp - nb0;
 			// cell B, open end (lanes 4, 7): reflection lowpass on k * T
-			const double y = reflB0 * (kk.y * bT) - reflA1 * extra;
+			const double y = reflB0 * (kk.y * bT) - reflA1 * y1;
 			if (storesEnd) endRow[j0 + q] = bT;
 			const double U = is3 ? pU : tU;
 			const double W = is3 ? pW : (isEnd ? y : tW);
@@ -810,15 +813,17 @@ GTTS_DEV void tube_iteration_impl(CtaSm* C, const KernelParamsV1& P, int warp, i
 			const double fromPrev = shfl_d(bTo, srcPrev, 32);
 			const double fromNext = shfl_d(aBo, srcNext, 32);
 			const double link = shfl_d(linkOut, srcLink, 32);
-			const double glot = (extra * d) + ex;          // T[S1] = B[S1] d + input (lane 0)
-			extra = isGlot ? aBo : (is3 ? link : (isEnd ? y : extra));
+			const double glot = (gB * d) + ex;             // T[S1] = B[S1] d + input (lane 0)
+			gB = aBo;
+			nb0 = link;
+			y1 = y;
 			aT = isGlot ? glot : (isN0 ? link : fromPrev);
 			aB = bBo;
 			bT = aTo;
 			bB = fromNext;
 		}
 	}
-	t.aT = aT; t.aB = aB; t.bT = bT; t.bB = bB; t.extra = extra;
+	t.aT = aT; t.aB = aB; t.bT = bT; t.bB = bB; t.extra = gB; t.nb0 = nb0; t.y1 = y1;
 }
 
 GTTS_DEV void tube_iteration(CtaSm* C, const KernelParamsV1& P, int warp, int lane, TubeLane& t, int p)
@@ -830,8 +835,8 @@ GTTS_DEV void tube_iteration(CtaSm* C, const KernelParamsV1& P, int warp, int la
 		const int b = S->ctl[p].it - 4;
 		if (S->ctl[p].it >= 0 && b >= 0 && b < S->ctl[p].nblocks) fric = S->fric[b & 1];
 	}
-	(void) fric;   // both variants alternate from block to block; one copy keeps the instruction footprint small
-	tube_iteration_impl<true>(C, P, warp, lane, t, p);
+	if (__any_sync(0xffffffffu, fric != 0)) tube_iteration_impl<true>(C, P, warp, lane, t, p);
+	else tube_iteration_impl<false>(C, P, warp, lane, t, p);
 }
 
 // ---- slot bookkeeping for the NEXT iteration (chain A warp, lane = slot, after its chain work) ----------
@@ -971,7 +976,7 @@ GTTS_DEV void tube_v1_cta_body(const KernelParamsV1& P, unsigned char* smem, int
 	// Task t of an iteration goes to worker t mod 13: with at most 10-14 tasks nearly every worker has one.
 	const int skip = P.debug_skip;
 	if (warp < kTubeWarps) {
-		TubeLane tl = {0.0, 0.0, 0.0, 0.0, 0.0};
+		TubeLane tl = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 		GTTS_ROLE_LOOP(if (!(skip & 32)) tube_iteration(C, P, warp, lane, tl, p);)
 	} else if (warp == kChainAWarp) {
 		ChainARegs ca = {0.0, {0.0, 0.0, 0.0, 0.0}};
