@@ -835,8 +835,14 @@ GTTS_DEV void tube_iteration(CtaSm* C, const KernelParamsV1& P, int warp, int la
 		const int b = S->ctl[p].it - 4;
 		if (S->ctl[p].it >= 0 && b >= 0 && b < S->ctl[p].nblocks) fric = S->fric[b & 1];
 	}
+#ifdef GTTS_TUBE_TWO_VARIANTS
+	// Measured on B200: the second copy of the loop costs 10 % of the whole kernel (instruction-cache
+	// footprint), far more than the frication-free variant saves.
 	if (__any_sync(0xffffffffu, fric != 0)) tube_iteration_impl<true>(C, P, warp, lane, t, p);
 	else tube_iteration_impl<false>(C, P, warp, lane, t, p);
+#else
+	tube_iteration_impl<true>(C, P, warp, lane, t, p);
+#endif
 }
 
 // ---- slot bookkeeping for the NEXT iteration (chain A warp, lane = slot, after its chain work) ----------

@@ -6,6 +6,7 @@ import glob
 import os
 import re
 import subprocess
+import sys
 import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -32,6 +33,8 @@ def main():
     dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout
     ranges = {f: func_ranges(os.path.join(ROOT, "gama_tts_b200", "csrc", f)) for f in ("tube_kernel_v1.cuh", "tube_kernel.cuh")}
     counts = collections.Counter()
+    lines = collections.Counter()
+    lkey = None
     section, key = None, "?"
     for line in dis.splitlines():
         m = re.match(r"\s*\.section\s+\.text\.(\S+)", line)
@@ -42,16 +45,27 @@ def main():
         if m:
             f, l = os.path.basename(m.group(1)), int(m.group(2))
             key = f
+            lkey = (f, l)
             for name, a, b in ranges.get(f, []):
                 if a <= l <= b:
                     key = f.replace("tube_kernel", "k").replace(".cuh", "") + ":" + name
             continue
         if section and "tube_kernel_v1" in section and re.match(r"\s+/\*[0-9a-f]{4,5}\*/", line):
             counts[key] += 1
+            lines[lkey] += 1
     total = sum(counts.values())
     print("tube_kernel_v1: %d SASS instructions, %.1f KB" % (total, total * 16 / 1024.0))
     for k, v in counts.most_common(24):
         print("  %-36s %5d" % (k, v))
+    if "--lines" in sys.argv:
+        src = {}
+        print("--- top source lines by static SASS instructions")
+        for (f, l), v in lines.most_common(60):
+            path = os.path.join(ROOT, "gama_tts_b200", "csrc", f)
+            if f not in src:
+                src[f] = open(path).read().splitlines() if os.path.exists(path) else []
+            text = src[f][l - 1].strip() if 0 < l <= len(src[f]) else ""
+            print("  %4d  %s:%d  %s" % (v, f.replace("tube_kernel", "k"), l, text[:110]))
 
 
 if __name__ == "__main__":
