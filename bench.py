@@ -213,10 +213,11 @@ def main():
     fo = np.arange(N_UTT + 1, dtype=np.int64) * N_FRAMES
     synth = g.TubeSynthesizer(local_rank)
     batch = synth.prepare(voice, fo)
-    n_out = batch.n_out_total
+    n_out = batch.n_out_total                 # buffer size: every utterance starts on a 32-sample row
+    n_samples = batch.n_samples_total         # audio samples produced
     n_internal = int(batch.n_internal.sum())
-    audio_seconds = n_out / voice["output_rate"]
-    flops_per_launch = FLOP_PER_INTERNAL * n_internal + FLOP_PER_OUTPUT * n_out
+    audio_seconds = n_samples / voice["output_rate"]
+    flops_per_launch = FLOP_PER_INTERNAL * n_internal + FLOP_PER_OUTPUT * n_samples
 
     h_frames = torch.from_numpy(frames_np).pin_memory()
     h_out = torch.empty(n_out, dtype=torch.float32).pin_memory()
@@ -281,12 +282,12 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(),
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": int(frames_np.nbytes), "d2h_bytes_per_step": int(n_out * 4)},
+                    "h2d_bytes_per_step": int(frames_np.nbytes), "d2h_bytes_per_step": int(n_samples * 4)},
             "gpu_launches": launches,
             "roofline": {"bound": "fp64_fma", "achieved": achieved_tflops, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved_tflops / peak, "traffic": None, "peak_source": peak_src,
                          "flops_per_launch": flops_per_launch,
-                         "hbm_bytes_per_launch_algorithmic": int(frames_np.nbytes + n_out * 4)},
+                         "hbm_bytes_per_launch_algorithmic": int(frames_np.nbytes + n_samples * 4)},
             "clocks": clocks,
             "kernel": json.loads(synth.describe()),
             "checksum": checksum,

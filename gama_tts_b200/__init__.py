@@ -92,7 +92,11 @@ class Batch:
         self.n_internal = np.zeros(max(self.n_utt, 1), np.int64)
         check(self._lib.gtts_batch_layout(self._h, self.out_offsets.ctypes.data, self.n_internal.ctypes.data))
         self.n_internal = self.n_internal[:self.n_utt]
-        self.n_out_total = int(self.out_offsets[-1])
+        self.n_out = np.zeros(max(self.n_utt, 1), np.int64)
+        check(self._lib.gtts_batch_lengths(self._h, self.n_out.ctypes.data))
+        self.n_out = self.n_out[:self.n_utt]
+        self.n_out_total = int(self.out_offsets[-1])     # size of the output buffer (utterances start on 32-sample rows)
+        self.n_samples_total = int(self.n_out.sum())     # audio samples produced
         self.n_frames_total = int(fo[-1]) if len(fo) else 0
 
     def run_device(self, d_frames_ptr, d_out_ptr, stream_ptr=0):
@@ -115,7 +119,7 @@ class Batch:
         return n.value
 
     def split(self, packed):
-        return [packed[self.out_offsets[u]:self.out_offsets[u + 1]] for u in range(self.n_utt)]
+        return [packed[self.out_offsets[u]:self.out_offsets[u] + self.n_out[u]] for u in range(self.n_utt)]
 
     def close(self):
         if self._h:

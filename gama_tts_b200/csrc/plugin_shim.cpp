@@ -146,13 +146,16 @@ void B200VocalTractModel::finishSynthesis() noexcept
 			return;
 		}
 		int64_t outOffsets[2] = {0, 0};
+		int64_t nOut = 0;
 		gtts_batch_layout(batch, outOffsets, nullptr);
+		gtts_batch_lengths(batch, &nOut);
 		const size_t base = outputBuffer_.size();
-		outputBuffer_.resize(base + static_cast<size_t>(outOffsets[1]));
+		outputBuffer_.resize(base + static_cast<size_t>(outOffsets[1]));     // the layout is padded to whole rows
 		if (gtts_batch_run_host(batch, recorded_.data(), outputBuffer_.data() + base) != GTTS_OK) {
 			std::fprintf(stderr, "[gtts_plugin] %s\n", gtts_last_error());
-			outputBuffer_.resize(base);
+			nOut = 0;
 		}
+		outputBuffer_.resize(base + static_cast<size_t>(nOut));
 		gtts_batch_free(batch);
 		recorded_.clear();
 	} catch (...) {

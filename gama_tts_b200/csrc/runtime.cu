@@ -409,6 +409,13 @@ int gtts_batch_run_device(gtts_batch* b, const float* d_frames, float* d_out, vo
 	return launchBatch(b, d_frames, d_out, static_cast<cudaStream_t>(cuda_stream));
 }
 
+int gtts_batch_lengths(const gtts_batch* b, int64_t* n_out)
+{
+	if (!b || !n_out) return fail(GTTS_ERR_INVALID, "null argument");
+	for (size_t u = 0; u < b->plan.utts.size(); ++u) n_out[u] = b->plan.utts[u].n_out;
+	return GTTS_OK;
+}
+
 int gtts_batch_run_host(gtts_batch* b, const float* h_frames, float* h_out)
 {
 	if (!b) return fail(GTTS_ERR_INVALID, "null batch");
@@ -417,11 +424,28 @@ int gtts_batch_run_host(gtts_batch* b, const float* h_frames, float* h_out)
 	if ((nFrames > 0 && !h_frames) || (nOut > 0 && !h_out)) return fail(GTTS_ERR_INVALID, "null host buffer");
 	GTTS_CUDA(cudaSetDevice(b->h->device));
 	if (!b->stream) GTTS_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
-	if (nFrames > b->cap_frames) {
-		if (b->d_frames) cudaFree(b->d_frames);
-		b->d_frames = nullptr; b->cap_frames = 0;
-		GTTS_CUDA(cudaMalloc(&b->d_frames, sizeof(float) * kNumParams * nFrames));
-		b->cap_frames = nFrames;
+	// Input path.  The kernels read every track value exactly once, one control period before it is needed
+	// (walk_block), so pinned host frames are read in place over PCIe (measured: no slowdown against
+	// device-resident frames, and the serial 3 ms host->device copy of BASELINE config 2 disappears).
+	// Pageable frames are copied to the device first.  GTTS_HOST_INPUT=staged forces the copy.
+	const float* dFrames = nullptr;
+	if (nFrames > 0) {
+		cudaPointerAttributes attr;
+		const char* env = std::getenv("GTTS_HOST_INPUT");
+		const bool allow = !(env && std::strcmp(env, "staged") == 0);
+		if (allow && cudaPointerGetAttributes(&attr, h_frames) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer) {
+			dFrames = static_cast<const float*>(attr.devicePointer);
+		} else {
+			cudaGetLastError();
+			if (nFrames > b->cap_frames) {
+				if (b->d_frames) cudaFree(b->d_frames);
+				b->d_frames = nullptr; b->cap_frames = 0;
+				GTTS_CUDA(cudaMalloc(&b->d_frames, sizeof(float) * kNumParams * nFrames));
+				b->cap_frames = nFrames;
+			}
+			GTTS_CUDA(cudaMemcpyAsync(b->d_frames, h_frames, sizeof(float) * kNumParams * nFrames, cudaMemcpyHostToDevice, b->stream));
+			dFrames = b->d_frames;
+		}
 	}
 	// Output path.  Pinned (page-locked) host memory is device-accessible under UVA: the kernel then
 	// stores the float32 audio straight into the caller's buffer over PCIe while it computes, so the
@@ -447,8 +471,7 @@ int gtts_batch_run_host(gtts_batch* b, const float* h_frames, float* h_out)
 		b->cap_out = nOut;
 	}
 	if (!zeroCopy) dOut = b->d_out;
-	if (nFrames > 0) GTTS_CUDA(cudaMemcpyAsync(b->d_frames, h_frames, sizeof(float) * kNumParams * nFrames, cudaMemcpyHostToDevice, b->stream));
-	const int rc = launchBatch(b, b->d_frames, dOut, b->stream);
+	const int rc = launchBatch(b, dFrames, dOut, b->stream);
 	if (rc != GTTS_OK) return rc;
 	if (!zeroCopy && nOut > 0) GTTS_CUDA(cudaMemcpyAsync(h_out, b->d_out, sizeof(float) * nOut, cudaMemcpyDeviceToHost, b->stream));
 	GTTS_CUDA(cudaStreamSynchronize(b->stream));

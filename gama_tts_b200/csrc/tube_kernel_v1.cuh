@@ -21,8 +21,24 @@
 
 #include "tube_kernel.cuh"
 
+// Unrolling knobs: the kernel is sensitive to its instruction-cache footprint (tools/ab_build.sh NAME -D...)
+#ifndef GTTS_FIR_UNROLL
+#define GTTS_FIR_UNROLL 4
+#endif
+#ifndef GTTS_COEF_UNROLL
+#define GTTS_COEF_UNROLL 1
+#endif
+#ifndef GTTS_ROLE_MAP
+#define GTTS_ROLE_MAP 0
+#endif
+#ifndef GTTS_CHAINB_CHUNK
+#define GTTS_CHAINB_CHUNK 8
+#endif
+
 namespace gtts {
 namespace v1 {
+
+constexpr int kFirUnroll = GTTS_FIR_UNROLL, kCoefUnroll = GTTS_COEF_UNROLL;
 
 enum {
 	kSlots = 7,
@@ -33,7 +49,11 @@ enum {
 	kChainBWarp = 3,
 	kHelper0 = 4,                 // warps 4..10: slot helpers
 	kPool0 = kHelper0 + kSlots,   // warps 11..23: task workers
+#if GTTS_ROLE_MAP == 1
+	kPoolWarps = kWarps - kPool0 - 2,   // two warp slots of the tube's sub-partition stay idle
+#else
 	kPoolWarps = kWarps - kPool0,
+#endif
 	kStages = 6,                  // last stage (SRC) runs at it = b + 6
 	kRow = 33,
 };
@@ -79,12 +99,14 @@ struct CtaSm {
 	double2 tab[kSrcFilterLen];
 	SlotSm slot[kSlots];
 	float  pscratch[kSlots][kBlock][9];       // per-slot scratch of the coefficient task: parameters 7..15 of one block
+	double zeros[kBlock];                     // operand row of the tube lanes that take no per-sample input
 	struct Sched {
 		int live;                 // some slot has work
 		int src_shared;           // 1: every slot in the SRC stage is at the same block of an equally long utterance of the same rate
 		int src_mask;             // slots with a block in the SRC stage
 		int src_tasks;            // SRC tasks this iteration
-		long long src_k0, src_k1; // output range of the shared SRC tasks
+		long long src_k0, src_k1; // shared SRC tasks: first output of the first row, end of the range
+		long long src_k0w;        // first output to write (>= src_k0: the first row of an unaligned utterance is partial)
 	} sched[2];
 };
 
@@ -150,23 +172,25 @@ GTTS_DEV void walk_block(const float* frames, long long nFrames, int steps, floa
 	const int restart = reaches ? first : -1;
 	float c = cur, d = delta;
 	float* o = active ? out : nullptr;
-	if (!__any_sync(0xffffffffu, reaches)) {
-		// no control-period boundary for any lane in this block (about half of the blocks): store + add
+	// The lanes of one call belong to at most two groups with a common cursor offset (lane 0 | lanes 1..):
+	// their restart points split the block into at most three segments that are walked without a per-sample
+	// test (store + add); a lane reloads (c, d) when a segment ends on its own restart point.
+	const int mine = reaches ? first : kBlock;
+	const int ra = __shfl_sync(0xffffffffu, mine, 0), rb = __shfl_sync(0xffffffffu, mine, 1);
+	const int s0 = ra < rb ? ra : rb, s1 = ra < rb ? rb : ra;
+	int j = 0;
+#pragma unroll 1
+	for (int seg = 0; seg < 3; ++seg) {
+		const int end = seg == 0 ? s0 : (seg == 1 ? s1 : kBlock);
 		if (o != nullptr) {
-#pragma unroll 8
-			for (int j = 0; j < kBlock; ++j) {
-				o[j * outStride] = c;
+#pragma unroll 4
+			for (int jj = j; jj < end; ++jj) {
+				o[jj * outStride] = c;
 				c = __fadd_rn(c, d);
 			}
 		}
-	} else {
-#pragma unroll 2
-		for (int j = 0; j < kBlock; ++j) {
-			if (j == restart) { c = nxt0; d = d2; }
-			if (o != nullptr) o[j * outStride] = c;
-			c = __fadd_rn(c, d);
-		}
-		if (restart == kBlock) { c = nxt0; d = d2; }
+		j = end;
+		if (j == restart) { c = nxt0; d = d2; }
 	}
 	if (active) {
 		cur = c;
@@ -364,7 +388,7 @@ GTTS_DEV void helper_iteration(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int
 			const double* pe = S->ve + 24 + lane;
 			const double* po = S->vo + 24 + lane;
 			double acc = 0.0;
-#pragma unroll
+#pragma unroll kFirUnroll
 			for (int m = 0; m < 24; ++m) {
 				acc += po[-m] * c_fir[2 * m];
 				acc += pe[-m] * c_fir[2 * m + 1];
@@ -458,7 +482,7 @@ GTTS_DEV void coef_task(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int lane, 
 			r = r > 0.01 ? r : 0.01;
 			a2 = r * r;
 		}
-#pragma unroll 3
+#pragma unroll kCoefUnroll
 		for (int i = 0; i < 9; ++i) {
 			double b2;
 			if (i < 7) {
@@ -475,19 +499,46 @@ GTTS_DEV void coef_task(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int lane, 
 			const double k = kcoef(a2, b2);
 			if (i == 7) k7 = k;
 			const int dst = i <= 2 ? i : (i == 3 ? 4 : i + 2);     // (row, component) of junction i in the kab rows
-			kabFlat[((dst >> 1) * kRow + lane) * 2 + (dst & 1)] = k;
+			kabFlat[((dst >> 1) * kRow + lane) * 2 + (dst & 1)] = (i == 7) ? k * V.refl_b0_m : k;   // mouth end: b0 folded in (tube_iteration)
 			a2 = b2;
 		}
 		const double sum = 2.0 / (r2_3 + r2_3 + v2);
-		S->kab[buf][1][lane].y = sum * r2_3;                   // alpha left == alpha right (lane 1 of the tube)
+		S->kab[buf][1][lane].y = (sum * r2_3) - 1.0;           // alpha left == alpha right, stored as alpha - 1 (tube_iteration)
 		S->kab[buf][2][lane].y = 0.0;                          // S6-S7 is a pure damped delay: k = 0
 		S->kab[buf][5][lane].y = V.nasal_k[1];
 		S->kab[buf][6][lane] = make_double2(V.nasal_k[2], V.nasal_k[3]);
-		S->kab[buf][7][lane] = make_double2(V.nasal_k[4], V.nasal_k[5]);
+		S->kab[buf][7][lane] = make_double2(V.nasal_k[4], V.nasal_k[5] * V.refl_b0_n);   // nose end: b0 folded in
 		S->au[buf][lane] = sum * v2;
 		S->onepk7[b % 3][lane] = 1.0 + k7;
 	}
 	__syncwarp();
+}
+
+// ---- output rows of the SRC stage --------------------------------------------------------------------
+// Block b completes the outputs [outputs_before(32 b), outputs_before(32 (b + 1))).  The SRC tasks write
+// whole 128-byte rows instead: every block but the last stops at the last row boundary (an absolute
+// multiple of 32 samples in the output buffer) and leaves the remainder to the next block, whose window
+// still holds the inputs (the ring keeps 128: 57 back + 64 ahead being written).  Row-aligned 128-byte stores are what lets the kernel write
+// straight into pinned host memory at PCIe rate (52.7 GB/s measured against 30 GB/s for unaligned rows,
+// tools/microbench/zerocopy_store.cu); in device memory they halve the written sectors' partial writes.
+GTTS_DEV void src_range(const SlotSm::Ctl& K, int b, unsigned inc, long long& k0, long long& k1)
+{
+	const long long nStart = (long long) b * kBlock;
+	const long long nEnd = nStart + block_len(K, b);
+	const long long a = K.U.out_begin & 31;        // 0 with the planner's padded layout
+	// The boundary between the last two blocks stays exact: the 26 flush zeros that chain B appends after the
+	// last block would otherwise reach, around the 128-entry ring, the oldest inputs of the deferred outputs.
+	const long long e0 = outputs_before(nStart, inc);
+	k0 = (b == 0) ? 0 : (b == K.nblocks - 2 ? e0 : ((e0 + a) & ~31ll) - a);
+	if (b == K.nblocks - 1) {
+		k1 = K.U.n_out;                             // flush: chain B appended the 26 zeros
+	} else {
+		const long long e1 = outputs_before(nEnd, inc);
+		k1 = (b == K.nblocks - 3) ? e1 : ((e1 + a) & ~31ll) - a;
+		if (k1 > K.U.n_out) k1 = K.U.n_out;
+	}
+	if (k0 < 0) k0 = 0;
+	if (k1 < k0) k1 = k0;
 }
 
 // ---- pool task: sample-rate conversion of the outputs that block b = it - 6 completes ---------------
@@ -497,18 +548,16 @@ GTTS_DEV void src_task(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int lane, i
 	const int b = K.it - kStages;
 	if (K.it < 0 || b < 0 || b >= K.nblocks) return;
 	const VoiceDev& V = S->V;
-	const long long nStart = (long long) b * kBlock;
-	const long long nEnd = nStart + block_len(K, b);
 	const unsigned inc = V.src_inc;
-	long long k0 = outputs_before(nStart, inc);
-	long long k1 = outputs_before(nEnd, inc);
-	if (b == K.nblocks - 1) k1 = K.U.n_out;          // flush: chain B appended the 26 zeros
-	if (k1 > K.U.n_out) k1 = K.U.n_out;
+	long long k0, k1;
+	src_range(K, b, inc, k0, k1);
+	// rows start on absolute multiples of 32 samples: lane = (out_begin + k) mod 32
+	const long long kRow0 = ((k0 + (K.U.out_begin & 31)) & ~31ll) - (K.U.out_begin & 31);
 	float* out = P.out + K.U.out_begin;
 	// Up to 96 outputs per block (ratio < 3): each lane carries three independent accumulator chains
 	// (outputs k, k + 32, k + 64) so that the 52 dependent multiply-adds of one output overlap with the
 	// other two; every chain still sums its own taps in the reference's order (left wing, then right).
-	for (long long kb = k0; kb < k1; kb += 96) {
+	for (long long kb = kRow0; kb < k1; kb += 96) {
 		double acc[3] = {0.0, 0.0, 0.0};
 		double interpL[3], interpR[3];
 		const double2* tabL[3];
@@ -518,7 +567,7 @@ GTTS_DEV void src_task(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int lane, i
 #pragma unroll
 		for (int o = 0; o < 3; ++o) {
 			kk[o] = kb + lane + 32 * o;
-			const unsigned long long t = (unsigned long long) kk[o] * inc;
+			const unsigned long long t = (unsigned long long) (kk[o] < 0 ? 0 : kk[o]) * inc;
 			const int e = (int) (t >> 16);
 			const unsigned f = (unsigned) (t & 0xFFFFu);
 			const unsigned gph = (~f) & 0xFFFFu;
@@ -547,7 +596,7 @@ GTTS_DEV void src_task(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int lane, i
 			}
 		}
 #pragma unroll
-		for (int o = 0; o < 3; ++o) if (kk[o] < k1) out[kk[o]] = (float) acc[o];
+		for (int o = 0; o < 3; ++o) if (kk[o] >= k0 && kk[o] < k1) out[kk[o]] = (float) acc[o];
 	}
 }
 
@@ -563,9 +612,10 @@ GTTS_DEV void src_shared_task(CtaSm* C, const KernelParamsV1& P, int lane, int p
 	int ref = 0;
 	while (!((mask >> ref) & 1)) ++ref;
 	const unsigned inc = C->slot[ref].V.src_inc;
-	const long long k0 = C->sched[p].src_k0, k1 = C->sched[p].src_k1;
+	// src_k0 is the first output of the first ROW (it may lie before the first output to write, k0w)
+	const long long k0 = C->sched[p].src_k0, k1 = C->sched[p].src_k1, k0w = C->sched[p].src_k0w;
 	const long long k = k0 + 32ll * pass + lane;
-	const unsigned long long t = (unsigned long long) k * inc;
+	const unsigned long long t = (unsigned long long) (k < 0 ? 0 : k) * inc;
 	const int e = (int) (t >> 16);
 	const unsigned f = (unsigned) (t & 0xFFFFu);
 	const unsigned gph = (~f) & 0xFFFFu;
@@ -590,7 +640,7 @@ GTTS_DEV void src_shared_task(CtaSm* C, const KernelParamsV1& P, int lane, int p
 #pragma unroll
 		for (int q = 0; q < kSlots; ++q) acc[q] += (C->slot[q].xring[woff + 13 + j] * cc);
 	}
-	if (k < k1) {
+	if (k >= k0w && k < k1) {
 #pragma unroll
 		for (int q = 0; q < kSlots; ++q) {
 			if ((mask >> q) & 1) P.out[C->slot[q].ctl[p].U.out_begin + k] = (float) acc[q];
@@ -691,12 +741,12 @@ GTTS_DEV void chain_b_iteration(CtaSm* C, const KernelParamsV1& P, int lane, Cha
 		double* out = S->rad[f];
 		double x1 = r.x1, y1 = r.y1;
 #pragma unroll 1
-		for (int j0 = 0; j0 < kBlock; j0 += 8) {
-			double raw[8], sc[8], o[8];
+		for (int j0 = 0; j0 < kBlock; j0 += GTTS_CHAINB_CHUNK) {
+			double raw[GTTS_CHAINB_CHUNK], sc[GTTS_CHAINB_CHUNK], o[GTTS_CHAINB_CHUNK];
 #pragma unroll
-			for (int q = 0; q < 8; ++q) { raw[q] = in[j0 + q]; sc[q] = scale[j0 + q]; }
+			for (int q = 0; q < GTTS_CHAINB_CHUNK; ++q) { raw[q] = in[j0 + q]; sc[q] = scale[j0 + q]; }
 #pragma unroll
-			for (int q = 0; q < 8; ++q) {
+			for (int q = 0; q < GTTS_CHAINB_CHUNK; ++q) {
 				const double m = f == 0 ? sc[q] : onePlusN;
 				const double x = f == 2 ? raw[q] : m * raw[q];
 				const double y = b0 * x + b1 * x1 - a1 * y1;
@@ -705,7 +755,7 @@ GTTS_DEV void chain_b_iteration(CtaSm* C, const KernelParamsV1& P, int lane, Cha
 				o[q] = y * gain;
 			}
 #pragma unroll
-			for (int q = 0; q < 8; ++q) out[j0 + q] = o[q];
+			for (int q = 0; q < GTTS_CHAINB_CHUNK; ++q) out[j0 + q] = o[q];
 		}
 		r.x1 = x1; r.y1 = y1;
 	}
@@ -735,12 +785,22 @@ GTTS_DEV void chain_b_iteration(CtaSm* C, const KernelParamsV1& P, int lane, Cha
 }
 
 // ---- tube warps (0, 1): block it - 4, four utterances per warp, 8 lanes each ----------------------------
-// Same cells and wiring as stage_tube in tube_kernel.cuh, but branch-free: every lane evaluates the three
-// kinds of B cell (2-port junction, 3-way junction, open end) and selects, so that the independent
-// chains overlap; the per-sample operands are prefetched one sample ahead.  Lanes of slots without a
-// block at this stage run on dummy data: their state is reset when their block 0 arrives.
-template<bool kFric>
-GTTS_DEV void tube_iteration_impl(CtaSm* C, const KernelParamsV1& P, int warp, int lane, TubeLane& t, int p)
+// Same cells and wiring as stage_tube in tube_kernel.cuh: lane g of a group owns cells A and B,
+//   g0: S1 S2 | g1: S3 S4 -> 3-way junction | g2: S5 S6 | g3: S7 S8 | g4: S9 S10 -> mouth | g5: N1 N2 | g6: N3 N4 | g7: N5 N6 -> nose
+// The loop is bound by issue slots and a 64-bit select costs two (FSEL x 2) on top of the arithmetic it
+// chooses between, so the three kinds of B cell are ONE formula with per-lane constants instead:
+//   dl = e3 nb0 + k (bT + sigma bB)      U = bT + dl      W = cA aB + (cW bB + dl)
+//   2-port junction   sigma = -1, cW = 1, cA = 0, e3 = 0:  dl = k (bT - bB)               (VocalTractModel0.h:575-600)
+//   3-way junction    sigma = +1, cW = 1, cA = 0, e3 = alpha upper, k = alpha - 1 (stored so by coef_task):
+//                     dl = jp - bT - bB with jp = alpha (bT + bB) + alpha_u nb0, U = jp - bB, W = jp - bT,
+//                     and the wave into the nose X = jp - nb0 = U + bB - nb0                  (:602-617)
+//   open end          sigma = 0, cW = 0, cA = -a1 / d, k = b0 k_end (stored so): W = b0 (k T) - a1 y1 is the
+//                     reflection lowpass, whose state y1 is the lane's aB / d (aB = W d of the last sample)  (:619-630)
+// and the input of cell A is mL link + mP fromPrev + mG B[S1] + input with 0 / 1 / d masks (input = 0 off lane 0).
+// Per-sample operands are prefetched four samples at a time; frication taps cost nothing in blocks
+// without frication (warp-uniform branch).  Lanes of slots without a block at this stage run on dummy
+// data: their state is reset when their block 0 arrives.
+GTTS_DEV void tube_iteration(CtaSm* C, const KernelParamsV1& P, int warp, int lane, TubeLane& t, int p)
 {
 	const int g = lane & 7;
 	const int slot = warp * 4 + (lane >> 3);
@@ -748,101 +808,76 @@ GTTS_DEV void tube_iteration_impl(CtaSm* C, const KernelParamsV1& P, int warp, i
 	SlotSm* S = &C->slot[slot < kSlots ? slot : 0];
 	const SlotSm::Ctl& K = S->ctl[p];
 	const int b = (slot < kSlots) ? K.it - 4 : -1;
+	const bool hasBlock = slot < kSlots && K.it >= 0 && b >= 0 && b < K.nblocks;
+	const int buf = b & 1, b3 = (b % 3 + 3) % 3;
+	const bool fricBlock = __any_sync(0xffffffffu, hasBlock && S->fric[buf] != 0);
 	const VoiceDev& V = S->V;
 	if (b == 0) { t.aT = t.aB = t.bT = t.bB = t.extra = t.nb0 = t.y1 = 0.0; }
 	const double d = V.damping;
-	const bool is3 = g == 1, isEnd = (g == 4) || (g == 7), isGlot = g == 0, isN0 = g == 5;
+	const bool is3 = g == 1, isEnd = (g == 4) || (g == 7);
 	const bool storesEnd = isEnd && slot < kSlots;     // the 8th group of warp 1 is a dummy: it must not store
+	const double sigma = is3 ? 1.0 : (isEnd ? 0.0 : -1.0);
+	const double cW = isEnd ? 0.0 : 1.0;
+	const double cA = isEnd ? -(g == 4 ? V.refl_a1_m : V.refl_a1_n) / d : 0.0;
+	const double mP = (g == 0 || g == 5) ? 0.0 : 1.0, mL = (g == 5) ? 1.0 : 0.0, mG = (g == 0) ? d : 0.0;
 	const int tapA = (g >= 1 && g <= 4) ? 2 * g - 1 : -100;
 	const int tapB = (g <= 3) ? 2 * g : -100;
-	const double reflB0 = g == 4 ? V.refl_b0_m : V.refl_b0_n;
-	const double reflA1 = g == 4 ? V.refl_a1_m : V.refl_a1_n;
-	const int buf = b & 1, b3 = (b % 3 + 3) % 3;
 	const double2* kabRow = S->kab[buf][g];
 	const double2* pabRow = S->pab[buf];
-	const double* extraRow = isGlot ? S->in[b3] : S->au[buf];       // g0: tube input; g1: alpha upper
+	const double* e3Row = is3 ? S->au[buf] : C->zeros;
+	const double* inRow = (g == 0) ? S->in[b3] : C->zeros;
 	const int* ipRow = S->ip[b3];
 	double* endRow = (g == 7) ? S->endn[buf] : S->endm[buf];
 	const int srcPrev = base + ((g + 7) & 7), srcNext = base + ((g + 1) & 7), srcLink = base + (is3 ? 5 : 1);
-	// gB = B[S1] (used by lane 0), nb0 = NB[N1] (lane 1), y1 = reflection filter state (lanes 4, 7): every
-	// lane updates all three unconditionally (values on the other lanes are never used), which saves the
-	// per-sample role selects
-	double aT = t.aT, aB = t.aB, bT = t.bT, bB = t.bB, gB = t.extra, nb0 = t.nb0, y1 = t.y1;
+	// gB = B[S1] (used by lane 0), nb0 = NB[N1] (lane 1): every lane updates both unconditionally
+	double aT = t.aT, aB = t.aB, bT = t.bT, bB = t.bB, gB = t.extra, nb0 = t.nb0;
 #pragma unroll 1
 	for (int j0 = 0; j0 < kBlock; j0 += 4) {
-		// operands of 4 samples into registers first (one shared-memory latency per chunk)
-		double2 kkv[4], pabv[4];
-		double exv[4];
-		int ipv[4];
+		double2 kkv[4];
+		double e3v[4], inv[4], tfA[4], tfB[4];
 #pragma unroll
 		for (int q = 0; q < 4; ++q) {
-			kkv[q] = kabRow[j0 + q]; exv[q] = extraRow[j0 + q];
-			if (kFric) { pabv[q] = pabRow[j0 + q]; ipv[q] = ipRow[j0 + q]; }
+			kkv[q] = kabRow[j0 + q]; e3v[q] = e3Row[j0 + q]; inv[q] = inRow[j0 + q];
+			tfA[q] = 0.0; tfB[q] = 0.0;
+		}
+		if (fricBlock) {
+			// frication injected at taps ip, ip + 1 (the reference adds tap * 0 = 0 everywhere else)
+#pragma unroll
+			for (int q = 0; q < 4; ++q) {
+				const double2 pab = pabRow[j0 + q];
+				const int ip = ipRow[j0 + q];
+				tfA[q] = (tapA == ip) ? pab.x : ((tapA == ip + 1) ? pab.y : 0.0);
+				tfB[q] = (tapB == ip) ? pab.x : ((tapB == ip + 1) ? pab.y : 0.0);
+			}
 		}
 #pragma unroll
 		for (int q = 0; q < 4; ++q) {
 			const double2 kk = kkv[q];
-			const double ex = exv[q];
-			// frication injected at taps ip, ip+1; a block without frication in any of the warp's slots
-			// (the common case) skips the selection: the reference adds tap * 0 = 0 there
-			double tfA = 0.0, tfB = 0.0;
-			if (kFric) {
-				const double2 pab = pabv[q];
-				const int ip = ipv[q];
-				tfA = (tapA == ip) ? pab.x : ((tapA == ip + 1) ? pab.y : 0.0);
-				tfB = (tapB == ip) ? pab.x : ((tapB == ip + 1) ? pab.y : 0.0);
-			}
 			// cell A: 2-port junction
 			const double dlA = kk.x * (aT - aB);
-			const double aTo = ((aT + dlA) * d) + tfA;
+			const double aTo = ((aT + dlA) * d) + tfA[q];
 			const double aBo = (aB + dlA) * d;
-			// cell B, 2-port junction
-			const double dlB = kk.y * (bT - bB);
-			const double tU = bT + dlB, tW = bB + dlB;
-			// cell B, 3-way junction (lane 1): bT = T[S4], bB = B[S5], extra = NB[N1]; kk.y = alpha, ex = alpha upper
-			const double jp = (kk.y * bT) + (kk.y * bB) + (ex * nb0);
-			const double pU = jp - bB, pW = jp - bT, pX = jp - nb0;
-			// cell B, open end (lanes 4, 7): reflection lowpass on k * T
-			const double y = reflB0 * (kk.y * bT) - reflA1 * y1;
+			// cell B: unified junction
+			const double dl = (e3v[q] * nb0) + (kk.y * ((sigma * bB) + bT));
+			const double U = bT + dl;
+			const double W = (cA * aB) + ((cW * bB) + dl);
+			const double X = (U + bB) - nb0;
 			if (storesEnd) endRow[j0 + q] = bT;
-			const double U = is3 ? pU : tU;
-			const double W = is3 ? pW : (isEnd ? y : tW);
-			const double bTo = (U * d) + tfB;
+			const double bTo = (U * d) + tfB[q];
 			const double bBo = W * d;
-			const double linkOut = is3 ? pX * d : aBo;
+			const double linkOut = is3 ? X * d : aBo;
 			const double fromPrev = shfl_d(bTo, srcPrev, 32);
 			const double fromNext = shfl_d(aBo, srcNext, 32);
 			const double link = shfl_d(linkOut, srcLink, 32);
-			const double glot = (gB * d) + ex;             // T[S1] = B[S1] d + input (lane 0)
+			aT = (mL * link) + ((mP * fromPrev) + ((mG * gB) + inv[q]));
 			gB = aBo;
 			nb0 = link;
-			y1 = y;
-			aT = isGlot ? glot : (isN0 ? link : fromPrev);
 			aB = bBo;
 			bT = aTo;
 			bB = fromNext;
 		}
 	}
-	t.aT = aT; t.aB = aB; t.bT = bT; t.bB = bB; t.extra = gB; t.nb0 = nb0; t.y1 = y1;
-}
-
-GTTS_DEV void tube_iteration(CtaSm* C, const KernelParamsV1& P, int warp, int lane, TubeLane& t, int p)
-{
-	const int slot = warp * 4 + (lane >> 3);
-	int fric = 0;
-	if (slot < kSlots) {
-		const SlotSm* S = &C->slot[slot];
-		const int b = S->ctl[p].it - 4;
-		if (S->ctl[p].it >= 0 && b >= 0 && b < S->ctl[p].nblocks) fric = S->fric[b & 1];
-	}
-#ifdef GTTS_TUBE_TWO_VARIANTS
-	// Measured on B200: the second copy of the loop costs 10 % of the whole kernel (instruction-cache
-	// footprint), far more than the frication-free variant saves.
-	if (__any_sync(0xffffffffu, fric != 0)) tube_iteration_impl<true>(C, P, warp, lane, t, p);
-	else tube_iteration_impl<false>(C, P, warp, lane, t, p);
-#else
-	tube_iteration_impl<true>(C, P, warp, lane, t, p);
-#endif
+	t.aT = aT; t.aB = aB; t.bT = bT; t.bB = bB; t.extra = gB; t.nb0 = nb0;
 }
 
 // ---- slot bookkeeping for the NEXT iteration (chain A warp, lane = slot, after its chain work) ----------
@@ -853,6 +888,7 @@ GTTS_DEV void schedule_slots(CtaSm* C, const KernelParamsV1& P, int lane, int p,
 	int alive = 0, valid = 0, it = -1;
 	long long nInternal = 0;
 	unsigned inc = 0;
+	int phase = 0;
 	if (lane < kSlots) {
 		SlotSm* S = &C->slot[lane];
 		const SlotSm::Ctl& K = S->ctl[p];
@@ -886,7 +922,7 @@ GTTS_DEV void schedule_slots(CtaSm* C, const KernelParamsV1& P, int lane, int p,
 		}
 		alive = it >= 0;
 		valid = it >= 0 && it - kStages >= 0 && it - kStages < N.nblocks;
-		if (valid) { nInternal = N.U.n_internal; inc = P.voices[N.voice].src_inc; }
+		if (valid) { nInternal = N.U.n_internal; inc = P.voices[N.voice].src_inc; phase = (int) (N.U.out_begin & 31); }
 	}
 	const unsigned any = __ballot_sync(0xffffffffu, alive);
 	// SRC stage alignment: all slots that have a block at it - 6 are at the same block of equally long
@@ -896,7 +932,8 @@ GTTS_DEV void schedule_slots(CtaSm* C, const KernelParamsV1& P, int lane, int p,
 	const int itRef = __shfl_sync(0xffffffffu, it, refLane, 32);
 	const long long nRef = __shfl_sync(0xffffffffu, nInternal, refLane, 32);
 	const unsigned incRef = __shfl_sync(0xffffffffu, inc, refLane, 32);
-	const int same = !valid || (it == itRef && nInternal == nRef && inc == incRef);
+	const int phaseRef = __shfl_sync(0xffffffffu, phase, refLane, 32);
+	const int same = !valid || (it == itRef && nInternal == nRef && inc == incRef && phase == phaseRef);
 	const bool allSame = __ballot_sync(0xffffffffu, same) == 0xffffffffu;
 	if (lane == 0) {
 		CtaSm::Sched& D = C->sched[q];
@@ -906,13 +943,11 @@ GTTS_DEV void schedule_slots(CtaSm* C, const KernelParamsV1& P, int lane, int p,
 		D.src_tasks = kSlots;
 		if (D.src_shared) {
 			const SlotSm::Ctl& RK = C->slot[refLane].ctl[q];
-			const int b = RK.it - kStages;
-			const long long nStart = (long long) b * kBlock;
-			const long long nEnd = nStart + block_len(RK, b);
-			const long long k0 = outputs_before(nStart, incRef);
-			long long k1 = outputs_before(nEnd, incRef);
-			if (b == RK.nblocks - 1) k1 = RK.U.n_out;
-			if (k1 > RK.U.n_out) k1 = RK.U.n_out;
+			long long k0, k1;
+			src_range(RK, RK.it - kStages, incRef, k0, k1);
+			const long long a = RK.U.out_begin & 31;
+			D.src_k0w = k0;
+			k0 = ((k0 + a) & ~31ll) - a;
 			D.src_k0 = k0;
 			D.src_k1 = k1;
 			D.src_tasks = (int) ((k1 - k0 + 31) / 32);
@@ -957,7 +992,7 @@ GTTS_DEV void role_profile(const KernelParamsV1& P, int warp, int lane, long lon
 {
 #ifndef GTTS_EMU
 	if (P.prof != nullptr && lane == 0) {
-		P.prof[(size_t) blockIdx.x * (kWarps + 1) + warp] = busy;
+		P.prof[(size_t) blockIdx.x * (kWarps + 1) + (warp >= 100 ? warp - 82 : warp)] = busy;   // idle roles 104, 105 -> 22, 23
 		if (warp == 0) P.prof[(size_t) blockIdx.x * (kWarps + 1) + kWarps] = iters;
 	}
 #else
@@ -968,8 +1003,18 @@ GTTS_DEV void role_profile(const KernelParamsV1& P, int warp, int lane, long lon
 GTTS_DEV void tube_v1_cta_body(const KernelParamsV1& P, unsigned char* smem, int tid)
 {
 	CtaSm* C = reinterpret_cast<CtaSm*>(smem);
-	const int warp = tid >> 5, lane = tid & 31;
+	const int lane = tid & 31;
+#if GTTS_ROLE_MAP == 1
+	// Hardware warp w runs on SM sub-partition w % 4.  Sub-partition 0 takes the four latency-bound
+	// single warps (tube 0, tube 1, chain A, chain B) and two idle warps, so that the warps on the critical
+	// path of an iteration do not queue for issue slots behind the throughput-bound helpers and workers.
+	const int hw = tid >> 5;
+	const int warp = (hw & 3) == 0 ? ((hw >> 2) < 4 ? (hw >> 2) : 100 + (hw >> 2)) : 4 + (hw >> 2) * 3 + (hw & 3) - 1;
+#else
+	const int warp = tid >> 5;
+#endif
 	for (int i = tid; i < kSrcFilterLen; i += kThreads) C->tab[i] = P.src_tab[i];
+	if (tid < kBlock) C->zeros[tid] = 0.0;
 	if (tid < kSlots) {
 		for (int b = 0; b < 2; ++b) { C->slot[tid].ctl[b].it = -1; C->slot[tid].ctl[b].voice = 0; C->slot[tid].ctl[b].nblocks = 0; }
 	}
@@ -990,6 +1035,8 @@ GTTS_DEV void tube_v1_cta_body(const KernelParamsV1& P, unsigned char* smem, int
 	} else if (warp == kChainBWarp) {
 		ChainBRegs cb = {0.0, 0.0};
 		GTTS_ROLE_LOOP(if (!(skip & 16)) chain_b_iteration(C, P, lane, cb, p);)
+	} else if (warp >= 100) {
+		GTTS_ROLE_LOOP(;)
 	} else if (warp < kPool0) {
 		HelperRegs hr = {};
 		hr.mult = c_lcg[lane];

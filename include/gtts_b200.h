@@ -122,8 +122,14 @@ int gtts_probe_fp64_peak(gtts_handle* handle, double* tflops_out);
 int gtts_batch_prepare(gtts_handle* handle, const gtts_voice_config* voices, int32_t n_voices,
 			const int32_t* voice_index, double control_rate, const int32_t* steps_override,
 			const int64_t* frame_offsets, int64_t n_utt, gtts_batch** batch_out);
-/* out_offsets[n_utt+1] (in float32 samples) of the packed output; n_internal[n_utt] may be NULL. */
+/* Layout of the output buffer, in float32 samples: utterance u occupies [out_offsets[u], out_offsets[u] +
+ * n_out[u]); out_offsets[n_utt] is the size of the whole buffer.  Every utterance starts on a multiple of
+ * 32 samples (128 bytes) so that the kernel writes whole aligned rows -- this is what lets it store straight
+ * into pinned host memory at PCIe rate; the up to 31 samples between two utterances are never written.
+ * n_internal[n_utt] (samples at the tube's internal rate) may be NULL. */
 int gtts_batch_layout(const gtts_batch* batch, int64_t* out_offsets, int64_t* n_internal);
+/* n_out[n_utt]: output samples of each utterance (== gtts_output_length of its voice, steps and frames). */
+int gtts_batch_lengths(const gtts_batch* batch, int64_t* n_out);
 /* Runs the batch on DEVICE buffers, asynchronously on `cuda_stream` (a cudaStream_t, may be NULL):
  * d_frames float32 [n_frames_total][16], d_out float32 [out_offsets[n_utt]]. */
 int gtts_batch_run_device(gtts_batch* batch, const float* d_frames, float* d_out, void* cuda_stream);

@@ -27,7 +27,7 @@ extern "C" const char* emu_last_error() { return g_err.c_str(); }
 // Same planning code as the product host runtime, kernel body run CTA by CTA on fibers.
 extern "C" int emu_batch(const gtts_voice_config* voices, int n_voices, const int* voice_index, double control_rate,
 			const int* steps_override, const float* frames, const long long* frame_offsets, long long n_utt,
-			float* out, long long* out_offsets, int warps_per_cta, int n_ctas)
+			float* out, long long* out_offsets, long long* out_lengths, int warps_per_cta, int n_ctas)
 {
 	using namespace gtts;
 	BatchPlan plan;
@@ -36,6 +36,7 @@ extern "C" int emu_batch(const gtts_voice_config* voices, int n_voices, const in
 			reinterpret_cast<const int64_t*>(frame_offsets), n_utt, plan, &err);
 	if (err) return err;
 	for (long long u = 0; u <= n_utt; ++u) out_offsets[u] = plan.out_offsets[u];
+	for (long long u = 0; u < n_utt; ++u) out_lengths[u] = plan.utts[u].n_out;
 	if (!out) return 0;
 
 	std::vector<double> taps = designGlottalFir();
@@ -73,7 +74,7 @@ extern "C" int emu_batch(const gtts_voice_config* voices, int n_voices, const in
 
 extern "C" int emu_batch_v1(const gtts_voice_config* voices, int n_voices, const int* voice_index, double control_rate,
 			const int* steps_override, const float* frames, const long long* frame_offsets, long long n_utt,
-			float* out, long long* out_offsets, int n_ctas)
+			float* out, long long* out_offsets, long long* out_lengths, int n_ctas)
 {
 	using namespace gtts;
 	BatchPlan plan;
@@ -82,6 +83,7 @@ extern "C" int emu_batch_v1(const gtts_voice_config* voices, int n_voices, const
 			reinterpret_cast<const int64_t*>(frame_offsets), n_utt, plan, &err);
 	if (err) return err;
 	for (long long u = 0; u <= n_utt; ++u) out_offsets[u] = plan.out_offsets[u];
+	for (long long u = 0; u < n_utt; ++u) out_lengths[u] = plan.utts[u].n_out;
 	if (!out) return 0;
 	for (const UttDesc& d : plan.utts) {
 		if (d.steps < kBlock) { g_err = "v1 needs control periods of at least one block"; return GTTS_ERR_UNSUPPORTED; }

@@ -25,7 +25,7 @@ def emu():
     L = C.CDLL(os.path.join(HERE, "simt_emu", "libemu_tube.so"))
     L.emu_last_error.restype = C.c_char_p
     L.emu_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
-                            C.c_longlong, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+                            C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
 
     def run(voices, vidx, tracks, warps=4, ctas=1, rate=250.0, steps=None):
         va = voice_array(voices)
@@ -33,12 +33,13 @@ def emu():
         vi = np.ascontiguousarray(vidx, np.int32)
         so = None if steps is None else np.ascontiguousarray(steps, np.int32)
         oo = np.zeros(len(tracks) + 1, np.int64)
+        ol = np.zeros(len(tracks) + 1, np.int64)
         args = [va, len(voices), vi.ctypes.data, rate, None if so is None else so.ctypes.data, frames.ctypes.data,
                 fo.ctypes.data, len(tracks)]
-        assert L.emu_batch(*args, None, oo.ctypes.data, warps, ctas) == 0, L.emu_last_error()
+        assert L.emu_batch(*args, None, oo.ctypes.data, ol.ctypes.data, warps, ctas) == 0, L.emu_last_error()
         out = np.zeros(int(oo[-1]), np.float32)
-        assert L.emu_batch(*args, out.ctypes.data, oo.ctypes.data, warps, ctas) == 0
-        return [out[oo[i]:oo[i + 1]] for i in range(len(tracks))]
+        assert L.emu_batch(*args, out.ctypes.data, oo.ctypes.data, ol.ctypes.data, warps, ctas) == 0
+        return [out[oo[i]:oo[i] + ol[i]] for i in range(len(tracks))]
     return run
 
 
@@ -71,18 +72,19 @@ def emu_v1():
     L = C.CDLL(os.path.join(HERE, "simt_emu", "libemu_tube.so"))
     L.emu_last_error.restype = C.c_char_p
     L.emu_batch_v1.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
-                               C.c_longlong, C.c_void_p, C.c_void_p, C.c_int]
+                               C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
 
     def run(voices, vidx, tracks, ctas=1, rate=250.0):
         va = voice_array(voices)
         frames, fo = pack_tracks(tracks)
         vi = np.ascontiguousarray(vidx, np.int32)
         oo = np.zeros(len(tracks) + 1, np.int64)
+        ol = np.zeros(len(tracks) + 1, np.int64)
         args = [va, len(voices), vi.ctypes.data, rate, None, frames.ctypes.data, fo.ctypes.data, len(tracks)]
-        assert L.emu_batch_v1(*args, None, oo.ctypes.data, ctas) == 0, L.emu_last_error()
+        assert L.emu_batch_v1(*args, None, oo.ctypes.data, ol.ctypes.data, ctas) == 0, L.emu_last_error()
         out = np.full(int(oo[-1]), np.nan, np.float32)
-        assert L.emu_batch_v1(*args, out.ctypes.data, oo.ctypes.data, ctas) == 0, L.emu_last_error()
-        return [out[oo[i]:oo[i + 1]] for i in range(len(tracks))]
+        assert L.emu_batch_v1(*args, out.ctypes.data, oo.ctypes.data, ol.ctypes.data, ctas) == 0, L.emu_last_error()
+        return [out[oo[i]:oo[i] + ol[i]] for i in range(len(tracks))]
     return run
 
 

@@ -58,7 +58,7 @@ def main():
     e1.record(s)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    audio = b.n_out_total / 48000.0
+    audio = b.n_samples_total / 48000.0
     out["config3_like"] = {"utterances": U, "frames_total": int(fo[-1]), "audio_seconds": audio, "ms": ms,
                            "audio_s_per_s": audio / (ms * 1e-3), "prepare_s": prep,
                            "internal_samples": int(b.n_internal.sum()),

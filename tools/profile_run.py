@@ -41,7 +41,7 @@ def main():
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
         print("launch %d: %.3f ms  (%.1f ns per internal sample per utterance, %.0f audio-s/s)" %
-              (r, ms, ms * 1e6 / (args.frames * 80), b.n_out_total / 48000.0 / (ms * 1e-3)))
+              (r, ms, ms * 1e6 / (args.frames * 80), b.n_samples_total / 48000.0 / (ms * 1e-3)))
     print("checksum", float(d_out[::997].double().abs().sum()))
 
 
