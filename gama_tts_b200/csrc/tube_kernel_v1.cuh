@@ -40,6 +40,14 @@ namespace v1 {
 
 constexpr int kFirUnroll = GTTS_FIR_UNROLL, kCoefUnroll = GTTS_COEF_UNROLL;
 
+// keeps the first use of a register inside the branch it is written in (the compiler would otherwise hoist
+// cheap arithmetic on it above the branch)
+#ifndef GTTS_EMU
+#define GTTS_KEEP_IN_BRANCH(x) asm volatile("" : "+f"(x))
+#else
+#define GTTS_KEEP_IN_BRANCH(x) ((void) 0)
+#endif
+
 enum {
 	kSlots = 7,
 	kWarps = 24,
@@ -78,10 +86,7 @@ struct SlotSm {
 	int    ip[3][kBlock];
 	VoiceDev V;                   // the slot's voice constants (copied from global memory when an utterance starts)
 	int    fric[2];               // block has frication (some tap * bandpassed noise != 0), per pab buffer
-	// coefficient-walk cursor (parameters 7..15), advanced by whichever pool warp runs the task
-	float  ccur[9], cdelta[9], cfn1[9], cfn2[9];
 	float  ckey[9];               // parameters 7..15 at the last sample of the previous block (NaN: none)
-	int    cframe, coff;
 	// control block, double-buffered by iteration parity: the scheduler lane writes ctl[p ^ 1] while the
 	// roles read ctl[p], so that one CTA barrier per iteration is enough
 	struct Ctl {
@@ -91,7 +96,7 @@ struct SlotSm {
 		int voice;
 		int pad;
 	} ctl[2];
-	int     pad_[7];              // slot stride = 16 mod 128 bytes: the 7 slots start in different banks
+	int     pad_[13];              // slot stride = 16 mod 128 bytes: the 7 slots start in different banks
 };
 static_assert(sizeof(SlotSm) % 128 == 16, "slot stride should be 16 mod 128 bytes (bank spreading); adjust pad_");
 
@@ -164,11 +169,6 @@ GTTS_DEV void walk_block(const float* frames, long long nFrames, int steps, floa
 	// one: Controller.cpp:297-300).
 	const int first = (steps - off) < nb ? (steps - off) : nb;
 	const bool reaches = active && (off + first == steps);
-	const float nxt0 = fn1;
-	const float d2 = __fmul_rn(__fsub_rn(fn2, fn1), invSteps);
-	// refill for the boundary after this one: frame[f+3] (needed a whole control period from now)
-	float refill = fn2;
-	if (reaches && (long long) frame + 3 < nFrames) refill = frames[((long long) frame + 3) * kNumParams + param];
 	const int restart = reaches ? first : -1;
 	float c = cur, d = delta;
 	float* o = active ? out : nullptr;
@@ -190,12 +190,25 @@ GTTS_DEV void walk_block(const float* frames, long long nFrames, int steps, floa
 			}
 		}
 		j = end;
-		if (j == restart) { c = nxt0; d = d2; }
+		if (j == restart) {
+			// fn2 was fetched one control period ago; it must not be touched on any other path, so that a
+			// fetch still in flight (pinned host memory: microseconds over PCIe) never stalls the walk
+			GTTS_KEEP_IN_BRANCH(fn2);
+			c = fn1;
+			d = __fmul_rn(__fsub_rn(fn2, fn1), invSteps);
+		}
 	}
 	if (active) {
 		cur = c;
 		delta = d;
-		if (reaches) { frame += 1; off = nb - first; fn1 = fn2; fn2 = refill; } else { off += nb; }
+		if (reaches) {
+			frame += 1; off = nb - first; fn1 = fn2;
+			// refill for the boundary after the next one: frame[f+3], needed a whole control period from now;
+			// loaded straight into the cursor register, which nothing reads before that boundary
+			if ((long long) frame + 2 < nFrames) fn2 = frames[((long long) frame + 2) * kNumParams + param];
+		} else {
+			off += nb;
+		}
 	}
 }
 
@@ -247,12 +260,6 @@ GTTS_DEV void helper_iteration(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int
 		h.off = 0; h.frame = 0;
 		h.lcg = c_lcg_init; h.noise_x1 = 0.0;
 		h.c_p1 = h.c_p2 = h.c_p3 = h.c_p5 = h.c_p6 = __int_as_float(0x7fc00000);     // NaN: nothing cached
-		if (lane < 9) {
-			float c, d, f1, f2;
-			cursor_init(frames, nFrames, K.U.inv_steps, 7 + lane, c, d, f1, f2);
-			S->ccur[lane] = c; S->cdelta[lane] = d; S->cfn1[lane] = f1; S->cfn2[lane] = f2;
-		}
-		if (lane == 0) { S->cframe = 0; S->coff = 0; }
 		__syncwarp();
 	}
 	const int b0 = it, b2 = it - 2;
@@ -424,7 +431,11 @@ GTTS_DEV void helper_iteration(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int
 }
 
 // ---- pool task: junction coefficients of block b = it - 3 (VocalTractModel0.h:484-512, 698-716) ---------
-GTTS_DEV void coef_task(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int lane, int slotIndex, int p)
+// The walk cursor of parameters 7..15 (lanes 0..8) lives in the registers of pool worker `slotIndex`, which runs
+// this slot's task in every iteration (tasks 0..6 of the list are the coefficient tasks).
+struct CoefRegs { float cur, delta, fn1, fn2; int off, frame; };
+
+GTTS_DEV void coef_task(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int lane, int slotIndex, int p, CoefRegs& r)
 {
 	const SlotSm::Ctl& K = S->ctl[p];
 	const int b = K.it - 3;
@@ -433,16 +444,13 @@ GTTS_DEV void coef_task(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int lane, 
 	const float* frames = P.frames + K.U.frame_begin * kNumParams;
 	const int nb = block_len(K, b);
 	float (*scr)[9] = C->pscratch[slotIndex];
-	{
-		float cur = 0.f, delta = 0.f, f1 = 0.f, f2 = 0.f;
-		int off = S->coff, frame = S->cframe;
-		if (lane < 9) { cur = S->ccur[lane]; delta = S->cdelta[lane]; f1 = S->cfn1[lane]; f2 = S->cfn2[lane]; }
-		__syncwarp();
-		walk_block(frames, K.U.n_frames, K.U.steps, K.U.inv_steps, 7 + lane, nb, cur, delta, f1, f2, off, frame,
-				&scr[0][lane], 9, lane < 9);
-		if (lane < 9) { S->ccur[lane] = cur; S->cdelta[lane] = delta; S->cfn1[lane] = f1; S->cfn2[lane] = f2; }
-		if (lane == 0) { S->coff = off; S->cframe = frame; }
+	if (b == 0) {
+		r.cur = r.delta = r.fn1 = r.fn2 = 0.f;
+		if (lane < 9) cursor_init(frames, K.U.n_frames, K.U.inv_steps, 7 + lane, r.cur, r.delta, r.fn1, r.fn2);
+		r.off = 0; r.frame = 0;
 	}
+	walk_block(frames, K.U.n_frames, K.U.steps, K.U.inv_steps, 7 + lane, nb, r.cur, r.delta, r.fn1, r.fn2, r.off, r.frame,
+			&scr[0][lane], 9, lane < 9);
 	__syncwarp();
 	// Radii and velum unchanged since the last sample of the previous block (a held posture): the
 	// coefficients are the previous block's last row, copied instead of recomputed (9 divisions saved).
@@ -955,18 +963,18 @@ GTTS_DEV void schedule_slots(CtaSm* C, const KernelParamsV1& P, int lane, int p,
 	}
 }
 
-// One task of the per-iteration task list: SRC tasks first, then one coefficient task per slot.
-GTTS_DEV void run_task(CtaSm* C, const KernelParamsV1& P, int lane, int task, int p)
+// One task of the per-iteration task list: the coefficient task of every slot first (task t runs on worker t in
+// every iteration, which is what lets its cursor stay in registers), then the SRC tasks.
+GTTS_DEV void run_task(CtaSm* C, const KernelParamsV1& P, int lane, int task, int p, CoefRegs& cr)
 {
 	const int skip = P.debug_skip;
-	const int nSrc = C->sched[p].src_tasks;
-	if (task < nSrc) {
+	if (task < kSlots) {
+		if (!(skip & 2)) coef_task(C, &C->slot[task], P, lane, task, p, cr);
+	} else if (task < kSlots + C->sched[p].src_tasks) {
 		if (!(skip & 1)) {
-			if (C->sched[p].src_shared) src_shared_task(C, P, lane, task, p);
-			else src_task(C, &C->slot[task], P, lane, p);
+			if (C->sched[p].src_shared) src_shared_task(C, P, lane, task - kSlots, p);
+			else src_task(C, &C->slot[task - kSlots], P, lane, p);
 		}
-	} else if (task < nSrc + kSlots) {
-		if (!(skip & 2)) coef_task(C, &C->slot[task - nSrc], P, lane, task - nSrc, p);
 	}
 }
 
@@ -1044,7 +1052,8 @@ GTTS_DEV void tube_v1_cta_body(const KernelParamsV1& P, unsigned char* smem, int
 		GTTS_ROLE_LOOP(if (!(skip & 4)) helper_iteration(C, S, P, lane, hr, p);)
 	} else {
 		const int worker = warp - kPool0;
-		GTTS_ROLE_LOOP(for (int task = worker; task < C->sched[p].src_tasks + kSlots; task += kPoolWarps) run_task(C, P, lane, task, p);)
+		CoefRegs cr = {0.f, 0.f, 0.f, 0.f, 0, 0};
+		GTTS_ROLE_LOOP(for (int task = worker; task < C->sched[p].src_tasks + kSlots; task += kPoolWarps) run_task(C, P, lane, task, p, cr);)
 	}
 }
 
