@@ -12,7 +12,7 @@
 //   it = b+5   chain B       radiation filters (serial, lane = slot x filter) + output sum
 //   it = b+6   pool          windowed-sinc sample-rate conversion, lane = output sample, coalesced stores
 //
-// Warps: 0-1 tube (slots 0-3 / 4-6), 2 chain A, 3 chain B, 4-10 slot helpers, 11-15 pool (dynamic
+// Warps: 0-3 tube (two slots each), 4 chain A, 5 chain B, 6-12 slot helpers, 13-23 pool (dynamic
 // task queue in shared memory).  Two CTA barriers per iteration (work | slot bookkeeping).
 // The per-sample arithmetic is the same as in tube_kernel.cuh (v0), which stays as the general
 // kernel for streaming / resumed utterances and control periods shorter than one block.
@@ -27,9 +27,6 @@
 #endif
 #ifndef GTTS_COEF_UNROLL
 #define GTTS_COEF_UNROLL 1
-#endif
-#ifndef GTTS_ROLE_MAP
-#define GTTS_ROLE_MAP 0
 #endif
 #ifndef GTTS_CHAINB_CHUNK
 #define GTTS_CHAINB_CHUNK 8
@@ -52,16 +49,13 @@ enum {
 	kSlots = 7,
 	kWarps = 24,
 	kThreads = kWarps * 32,
-	kTubeWarps = 2,
-	kChainAWarp = 2,
-	kChainBWarp = 3,
-	kHelper0 = 4,                 // warps 4..10: slot helpers
-	kPool0 = kHelper0 + kSlots,   // warps 11..23: task workers
-#if GTTS_ROLE_MAP == 1
-	kPoolWarps = kWarps - kPool0 - 2,   // two warp slots of the tube's sub-partition stay idle
-#else
+	kTubeLanes = 16,              // one cell per lane
+	kTubeWarps = (kSlots * kTubeLanes + 31) / 32,
+	kChainAWarp = kTubeWarps,
+	kChainBWarp = kTubeWarps + 1,
+	kHelper0 = kTubeWarps + 2,    // one helper warp per slot
+	kPool0 = kHelper0 + kSlots,   // the rest: task workers
 	kPoolWarps = kWarps - kPool0,
-#endif
 	kStages = 6,                  // last stage (SRC) runs at it = b + 6
 	kRow = 33,
 };
@@ -484,6 +478,7 @@ GTTS_DEV void coef_task(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int lane, 
 		double* kabFlat = &S->kab[buf][0][0].x;         // [row][lane]{x, y} -> (row * kRow + lane) * 2 + c
 		const double vel = (double) p[8];
 		const double v2 = vel * vel;
+		const double dmp = V.damping;
 		double a2, r2_3 = 0.0, k7 = 0.0;
 		{
 			double r = (double) p[0] * V.radius_coef[0];
@@ -507,16 +502,16 @@ GTTS_DEV void coef_task(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int lane, 
 			const double k = kcoef(a2, b2);
 			if (i == 7) k7 = k;
 			const int dst = i <= 2 ? i : (i == 3 ? 4 : i + 2);     // (row, component) of junction i in the kab rows
-			kabFlat[((dst >> 1) * kRow + lane) * 2 + (dst & 1)] = (i == 7) ? k * V.refl_b0_m : k;   // mouth end: b0 folded in (tube_iteration)
+			kabFlat[((dst >> 1) * kRow + lane) * 2 + (dst & 1)] = ((i == 7) ? k * V.refl_b0_m : k) * dmp;   // damping (and the mouth end's b0) folded in: tube_iteration
 			a2 = b2;
 		}
 		const double sum = 2.0 / (r2_3 + r2_3 + v2);
-		S->kab[buf][1][lane].y = (sum * r2_3) - 1.0;           // alpha left == alpha right, stored as alpha - 1 (tube_iteration)
+		S->kab[buf][1][lane].y = ((sum * r2_3) - 1.0) * dmp;   // alpha left == alpha right, stored as (alpha - 1) d (tube_iteration)
 		S->kab[buf][2][lane].y = 0.0;                          // S6-S7 is a pure damped delay: k = 0
-		S->kab[buf][5][lane].y = V.nasal_k[1];
-		S->kab[buf][6][lane] = make_double2(V.nasal_k[2], V.nasal_k[3]);
-		S->kab[buf][7][lane] = make_double2(V.nasal_k[4], V.nasal_k[5] * V.refl_b0_n);   // nose end: b0 folded in
-		S->au[buf][lane] = sum * v2;
+		S->kab[buf][5][lane].y = V.nasal_k[1] * dmp;
+		S->kab[buf][6][lane] = make_double2(V.nasal_k[2] * dmp, V.nasal_k[3] * dmp);
+		S->kab[buf][7][lane] = make_double2(V.nasal_k[4] * dmp, (V.nasal_k[5] * V.refl_b0_n) * dmp);   // nose end: b0 folded in
+		S->au[buf][lane] = (sum * v2) * dmp;
 		S->onepk7[b % 3][lane] = 1.0 + k7;
 	}
 	__syncwarp();
@@ -792,27 +787,34 @@ GTTS_DEV void chain_b_iteration(CtaSm* C, const KernelParamsV1& P, int lane, Cha
 	}
 }
 
-// ---- tube warps (0, 1): block it - 4, four utterances per warp, 8 lanes each ----------------------------
-// Same cells and wiring as stage_tube in tube_kernel.cuh: lane g of a group owns cells A and B,
-//   g0: S1 S2 | g1: S3 S4 -> 3-way junction | g2: S5 S6 | g3: S7 S8 | g4: S9 S10 -> mouth | g5: N1 N2 | g6: N3 N4 | g7: N5 N6 -> nose
-// The loop is bound by issue slots and a 64-bit select costs two (FSEL x 2) on top of the arithmetic it
-// chooses between, so the three kinds of B cell are ONE formula with per-lane constants instead:
-//   dl = e3 nb0 + k (bT + sigma bB)      U = bT + dl      W = cA aB + (cW bB + dl)
-//   2-port junction   sigma = -1, cW = 1, cA = 0, e3 = 0:  dl = k (bT - bB)               (VocalTractModel0.h:575-600)
-//   3-way junction    sigma = +1, cW = 1, cA = 0, e3 = alpha upper, k = alpha - 1 (stored so by coef_task):
-//                     dl = jp - bT - bB with jp = alpha (bT + bB) + alpha_u nb0, U = jp - bB, W = jp - bT,
-//                     and the wave into the nose X = jp - nb0 = U + bB - nb0                  (:602-617)
-//   open end          sigma = 0, cW = 0, cA = -a1 / d, k = b0 k_end (stored so): W = b0 (k T) - a1 y1 is the
-//                     reflection lowpass, whose state y1 is the lane's aB / d (aB = W d of the last sample)  (:619-630)
-// and the input of cell A is mL link + mP fromPrev + mG B[S1] + input with 0 / 1 / d masks (input = 0 off lane 0).
-// Per-sample operands are prefetched four samples at a time; frication taps cost nothing in blocks
-// without frication (warp-uniform branch).  Lanes of slots without a block at this stage run on dummy
-// data: their state is reset when their block 0 arrives.
+// ---- tube warps: block it - 4, one cell per lane, 16 lanes per utterance, two utterances per warp ---------
+// Cells (same wiring as stage_tube in tube_kernel.cuh): u = 0..9 oral S1..S10 (u = 3: the 3-way junction after
+// S4, u = 9: mouth end), u = 10..15 nasal N1..N6 (u = 15: nose end).  The forward wave goes u -> u + 1, the
+// backward wave u + 1 -> u, the velum branch links u = 3 <-> u = 10: three 64-bit shuffles per sample.
+//
+// The loop is one dependent chain per sample (shuffle -> T -> outputs -> shuffle); a single warp issues in
+// order, so both the length of that chain and the number of instructions around it set the iteration time of
+// the whole CTA.  Hence (measured steps in DESIGN.md section 4.4):
+//  * the three kinds of cell are ONE formula with per-lane constants -- a 64-bit select costs two issue slots on
+//    top of the arithmetic it chooses between:
+//        dl = e3 nb + k (T + sigma Bn)      Tout = (T + dl) d + tap      Bout = (cA last + cW Bn + dl) d
+//      2-port junction  sigma = -1, cW = 1, cA = 0, e3 = 0: dl = k (T - Bn)                (VocalTractModel0.h:575-600)
+//      3-way junction   sigma = +1, cW = 1, e3 = alpha_u, k = alpha - 1: dl = jp - T - Bn with
+//                       jp = alpha (T + Bn) + alpha_u nb; Tout = (jp - Bn) d, Bout = (jp - T) d, and the wave into
+//                       the nose (jp - nb) d = (T + dl + Bn - nb) d                           (:602-617)
+//      open end         sigma = 0, cW = 0, cA = -a1 / d, k = b0 k_end: Bout / d = b0 (k T) - a1 y1 is the reflection
+//                       lowpass, whose state y1 is last / d (last = the lane's own Bout of the previous sample)  (:619-630)
+//  * damping is folded into the coefficients (the coefficient task stores k d and alpha_u d), so that every output is
+//    two dependent FMAs behind T:  out = kd ts + (d T + early), ts = T + sigma Bn, `early` known before T is;
+//  * the input of the cell is mP fromPrev + mL link + (mG last + input) with 0 / 1 / d masks (input = 0 off lane 0);
+//  * per-sample operands are prefetched four samples at a time, frication taps sit behind a warp-uniform branch.
+// Lanes of slots without a block at this stage run on dummy data: their state is reset when their block 0 arrives.
 GTTS_DEV void tube_iteration(CtaSm* C, const KernelParamsV1& P, int warp, int lane, TubeLane& t, int p)
 {
-	const int g = lane & 7;
-	const int slot = warp * 4 + (lane >> 3);
-	const int base = lane & ~7;
+	(void) P;
+	const int u = lane & 15;
+	const int slot = warp * 2 + (lane >> 4);
+	const int base = lane & ~15;
 	SlotSm* S = &C->slot[slot < kSlots ? slot : 0];
 	const SlotSm::Ctl& K = S->ctl[p];
 	const int b = (slot < kSlots) ? K.it - 4 : -1;
@@ -822,31 +824,30 @@ GTTS_DEV void tube_iteration(CtaSm* C, const KernelParamsV1& P, int warp, int la
 	const VoiceDev& V = S->V;
 	if (b == 0) { t.aT = t.aB = t.bT = t.bB = t.extra = t.nb0 = t.y1 = 0.0; }
 	const double d = V.damping;
-	const bool is3 = g == 1, isEnd = (g == 4) || (g == 7);
-	const bool storesEnd = isEnd && slot < kSlots;     // the 8th group of warp 1 is a dummy: it must not store
+	const bool is3 = u == 3, isEnd = (u == 9) || (u == 15);
+	const bool storesEnd = isEnd && slot < kSlots;     // the second group of the last warp is a dummy: it must not store
 	const double sigma = is3 ? 1.0 : (isEnd ? 0.0 : -1.0);
-	const double cW = isEnd ? 0.0 : 1.0;
-	const double cA = isEnd ? -(g == 4 ? V.refl_a1_m : V.refl_a1_n) / d : 0.0;
-	const double mP = (g == 0 || g == 5) ? 0.0 : 1.0, mL = (g == 5) ? 1.0 : 0.0, mG = (g == 0) ? d : 0.0;
-	const int tapA = (g >= 1 && g <= 4) ? 2 * g - 1 : -100;
-	const int tapB = (g <= 3) ? 2 * g : -100;
-	const double2* kabRow = S->kab[buf][g];
+	const double cWd = isEnd ? 0.0 : d;
+	const double cAd = isEnd ? -(u == 9 ? V.refl_a1_m : V.refl_a1_n) : 0.0;
+	const double mP = (u == 0 || u == 10) ? 0.0 : 1.0, mL = (u == 10) ? 1.0 : 0.0, mG = (u == 0) ? d : 0.0;
+	const int tap = (u >= 1 && u <= 8) ? u - 1 : -100;
+	const double* kRowp = &S->kab[buf][u >> 1][0].x + (u & 1);     // component u & 1 of the pair row, stride 2 doubles
 	const double2* pabRow = S->pab[buf];
 	const double* e3Row = is3 ? S->au[buf] : C->zeros;
-	const double* inRow = (g == 0) ? S->in[b3] : C->zeros;
+	const double* inRow = (u == 0) ? S->in[b3] : C->zeros;
 	const int* ipRow = S->ip[b3];
-	double* endRow = (g == 7) ? S->endn[buf] : S->endm[buf];
-	const int srcPrev = base + ((g + 7) & 7), srcNext = base + ((g + 1) & 7), srcLink = base + (is3 ? 5 : 1);
-	// gB = B[S1] (used by lane 0), nb0 = NB[N1] (lane 1): every lane updates both unconditionally
-	double aT = t.aT, aB = t.aB, bT = t.bT, bB = t.bB, gB = t.extra, nb0 = t.nb0;
+	double* endRow = (u == 15) ? S->endn[buf] : S->endm[buf];
+	const int srcPrev = base + ((u + 15) & 15), srcNext = base + ((u + 1) & 15), srcLink = base + (is3 ? 10 : 3);
+	// T = forward wave into the cell, Bn = backward wave from the next cell, nb = wave on the velum link,
+	// last = the cell's own backward output of the previous sample (glottis reflection, end-filter state)
+	double T = t.aT, Bn = t.aB, nb = t.nb0, last = t.extra;
 #pragma unroll 1
 	for (int j0 = 0; j0 < kBlock; j0 += 4) {
-		double2 kkv[4];
-		double e3v[4], inv[4], tfA[4], tfB[4];
+		double kv[4], e3v[4], inv[4], tf[4];
 #pragma unroll
 		for (int q = 0; q < 4; ++q) {
-			kkv[q] = kabRow[j0 + q]; e3v[q] = e3Row[j0 + q]; inv[q] = inRow[j0 + q];
-			tfA[q] = 0.0; tfB[q] = 0.0;
+			kv[q] = kRowp[2 * (j0 + q)]; e3v[q] = e3Row[j0 + q]; inv[q] = inRow[j0 + q];
+			tf[q] = 0.0;
 		}
 		if (fricBlock) {
 			// frication injected at taps ip, ip + 1 (the reference adds tap * 0 = 0 everywhere else)
@@ -854,38 +855,35 @@ GTTS_DEV void tube_iteration(CtaSm* C, const KernelParamsV1& P, int warp, int la
 			for (int q = 0; q < 4; ++q) {
 				const double2 pab = pabRow[j0 + q];
 				const int ip = ipRow[j0 + q];
-				tfA[q] = (tapA == ip) ? pab.x : ((tapA == ip + 1) ? pab.y : 0.0);
-				tfB[q] = (tapB == ip) ? pab.x : ((tapB == ip + 1) ? pab.y : 0.0);
+				tf[q] = (tap == ip) ? pab.x : ((tap == ip + 1) ? pab.y : 0.0);
 			}
 		}
 #pragma unroll
 		for (int q = 0; q < 4; ++q) {
-			const double2 kk = kkv[q];
-			// cell A: 2-port junction
-			const double dlA = kk.x * (aT - aB);
-			const double aTo = ((aT + dlA) * d) + tfA[q];
-			const double aBo = (aB + dlA) * d;
-			// cell B: unified junction
-			const double dl = (e3v[q] * nb0) + (kk.y * ((sigma * bB) + bT));
-			const double U = bT + dl;
-			const double W = (cA * aB) + ((cW * bB) + dl);
-			const double X = (U + bB) - nb0;
-			if (storesEnd) endRow[j0 + q] = bT;
-			const double bTo = (U * d) + tfB[q];
-			const double bBo = W * d;
-			const double linkOut = is3 ? X * d : aBo;
-			const double fromPrev = shfl_d(bTo, srcPrev, 32);
-			const double fromNext = shfl_d(aBo, srcNext, 32);
+			// known before T: everything that depends only on the neighbours' waves and the lane's own state
+			const double e = e3v[q] * nb;                            // alpha_u d NB[N1] (3-way junction only)
+			const double pre = (mG * last) + inv[q];                 // glottis: T[S1] = B[S1] d + input, B[S1] of the previous sample
+			const double eB = (cAd * last) + ((cWd * Bn) + e);
+			const double eT = e + tf[q];
+			const double eX = e + (d * (Bn - nb));
+			// behind T: two dependent FMAs per output
+			const double ts = (sigma * Bn) + T;
+			const double dT = d * T;
+			if (storesEnd) endRow[j0 + q] = T;
+			const double Tout = (kv[q] * ts) + (dT + eT);
+			const double Bout = (kv[q] * ts) + eB;
+			const double Xd = (kv[q] * ts) + (dT + eX);
+			const double linkOut = is3 ? Xd : Bout;
+			const double fromPrev = shfl_d(Tout, srcPrev, 32);
+			const double fromNext = shfl_d(Bout, srcNext, 32);
 			const double link = shfl_d(linkOut, srcLink, 32);
-			aT = (mL * link) + ((mP * fromPrev) + ((mG * gB) + inv[q]));
-			gB = aBo;
-			nb0 = link;
-			aB = bBo;
-			bT = aTo;
-			bB = fromNext;
+			last = Bout;
+			T = (mP * fromPrev) + ((mL * link) + pre);
+			Bn = fromNext;
+			nb = link;
 		}
 	}
-	t.aT = aT; t.aB = aB; t.bT = bT; t.bB = bB; t.extra = gB; t.nb0 = nb0;
+	t.aT = T; t.aB = Bn; t.nb0 = nb; t.extra = last;
 }
 
 // ---- slot bookkeeping for the NEXT iteration (chain A warp, lane = slot, after its chain work) ----------
@@ -1000,7 +998,7 @@ GTTS_DEV void role_profile(const KernelParamsV1& P, int warp, int lane, long lon
 {
 #ifndef GTTS_EMU
 	if (P.prof != nullptr && lane == 0) {
-		P.prof[(size_t) blockIdx.x * (kWarps + 1) + (warp >= 100 ? warp - 82 : warp)] = busy;   // idle roles 104, 105 -> 22, 23
+		P.prof[(size_t) blockIdx.x * (kWarps + 1) + warp] = busy;
 		if (warp == 0) P.prof[(size_t) blockIdx.x * (kWarps + 1) + kWarps] = iters;
 	}
 #else
@@ -1012,15 +1010,7 @@ GTTS_DEV void tube_v1_cta_body(const KernelParamsV1& P, unsigned char* smem, int
 {
 	CtaSm* C = reinterpret_cast<CtaSm*>(smem);
 	const int lane = tid & 31;
-#if GTTS_ROLE_MAP == 1
-	// Hardware warp w runs on SM sub-partition w % 4.  Sub-partition 0 takes the four latency-bound
-	// single warps (tube 0, tube 1, chain A, chain B) and two idle warps, so that the warps on the critical
-	// path of an iteration do not queue for issue slots behind the throughput-bound helpers and workers.
-	const int hw = tid >> 5;
-	const int warp = (hw & 3) == 0 ? ((hw >> 2) < 4 ? (hw >> 2) : 100 + (hw >> 2)) : 4 + (hw >> 2) * 3 + (hw & 3) - 1;
-#else
 	const int warp = tid >> 5;
-#endif
 	for (int i = tid; i < kSrcFilterLen; i += kThreads) C->tab[i] = P.src_tab[i];
 	if (tid < kBlock) C->zeros[tid] = 0.0;
 	if (tid < kSlots) {
@@ -1031,8 +1021,8 @@ GTTS_DEV void tube_v1_cta_body(const KernelParamsV1& P, unsigned char* smem, int
 	__syncthreads();
 
 	// Warp roles (warp id % 4 selects the SM sub-partition; the heavy issuers are spread evenly):
-	//   0-1 tube, 2 chain A (+ slot bookkeeping), 3 chain B, 4-10 slot helpers, 11-23 task workers.
-	// Task t of an iteration goes to worker t mod 13: with at most 10-14 tasks nearly every worker has one.
+	//   0-3 tube, 4 chain A (+ slot bookkeeping), 5 chain B, 6-12 slot helpers, 13-23 task workers.
+	// Task t of an iteration goes to worker t mod 11: with 9-14 tasks nearly every worker has one.
 	const int skip = P.debug_skip;
 	if (warp < kTubeWarps) {
 		TubeLane tl = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
@@ -1043,8 +1033,6 @@ GTTS_DEV void tube_v1_cta_body(const KernelParamsV1& P, unsigned char* smem, int
 	} else if (warp == kChainBWarp) {
 		ChainBRegs cb = {0.0, 0.0};
 		GTTS_ROLE_LOOP(if (!(skip & 16)) chain_b_iteration(C, P, lane, cb, p);)
-	} else if (warp >= 100) {
-		GTTS_ROLE_LOOP(;)
 	} else if (warp < kPool0) {
 		HelperRegs hr = {};
 		hr.mult = c_lcg[lane];

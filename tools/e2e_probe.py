@@ -18,8 +18,12 @@ def main():
     ap.add_argument("--utts", type=int, default=1024)
     ap.add_argument("--frames", type=int, default=2500)
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--lib", default=None, help="time another build of the library (tools/ab_build.sh)")
     args = ap.parse_args()
     import torch
+    if args.lib:
+        from gama_tts_b200 import capi
+        capi.LIB_PATH = os.path.abspath(args.lib)
     import gama_tts_b200 as g
     from gama_tts_b200 import tracks as T
     from gama_tts_b200.voices import default_voice
