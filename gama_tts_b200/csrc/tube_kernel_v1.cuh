@@ -165,32 +165,40 @@ GTTS_DEV void walk_block(const float* frames, long long nFrames, int steps, floa
 	const bool reaches = active && (off + first == steps);
 	const int restart = reaches ? first : -1;
 	float c = cur, d = delta;
-	float* o = active ? out : nullptr;
-	// The lanes of one call belong to at most two groups with a common cursor offset (lane 0 | lanes 1..):
-	// their restart points split the block into at most three segments that are walked without a per-sample
-	// test (store + add); a lane reloads (c, d) when a segment ends on its own restart point.
-	const int mine = reaches ? first : kBlock;
+	// The lanes of one call belong to at most two groups with a common cursor offset (lane 0 | lanes 1..), so
+	// at most two chunks of four samples contain a restart point: only those test every sample (warp-uniform
+	// branch), the others are four stores and four adds.  A lane restarts from the next frame value; fn2 was
+	// fetched one control period ago and is not touched on any other path, so that a fetch still in flight
+	// (pinned host memory: microseconds over PCIe) never stalls the walk.
+	const int mine = reaches ? first : 2 * kBlock;
 	const int ra = __shfl_sync(0xffffffffu, mine, 0), rb = __shfl_sync(0xffffffffu, mine, 1);
-	const int s0 = ra < rb ? ra : rb, s1 = ra < rb ? rb : ra;
-	int j = 0;
+	float* o = out;
 #pragma unroll 1
-	for (int seg = 0; seg < 3; ++seg) {
-		const int end = seg == 0 ? s0 : (seg == 1 ? s1 : kBlock);
-		if (o != nullptr) {
-#pragma unroll 4
-			for (int jj = j; jj < end; ++jj) {
-				o[jj * outStride] = c;
+	for (int j0 = 0; j0 < kBlock; j0 += 4) {
+		if ((unsigned) (ra - j0) >= 4u && (unsigned) (rb - j0) >= 4u) {
+#pragma unroll
+			for (int q = 0; q < 4; ++q) {
+				if (active) o[q * outStride] = c;
+				c = __fadd_rn(c, d);
+			}
+		} else {
+#pragma unroll
+			for (int q = 0; q < 4; ++q) {
+				if (j0 + q == restart) {
+					GTTS_KEEP_IN_BRANCH(fn2);
+					c = fn1;
+					d = __fmul_rn(__fsub_rn(fn2, fn1), invSteps);
+				}
+				if (active) o[q * outStride] = c;
 				c = __fadd_rn(c, d);
 			}
 		}
-		j = end;
-		if (j == restart) {
-			// fn2 was fetched one control period ago; it must not be touched on any other path, so that a
-			// fetch still in flight (pinned host memory: microseconds over PCIe) never stalls the walk
-			GTTS_KEEP_IN_BRANCH(fn2);
-			c = fn1;
-			d = __fmul_rn(__fsub_rn(fn2, fn1), invSteps);
-		}
+		o += 4 * outStride;
+	}
+	if (restart == kBlock) {
+		GTTS_KEEP_IN_BRANCH(fn2);
+		c = fn1;
+		d = __fmul_rn(__fsub_rn(fn2, fn1), invSteps);
 	}
 	if (active) {
 		cur = c;
@@ -1010,7 +1018,14 @@ GTTS_DEV void tube_v1_cta_body(const KernelParamsV1& P, unsigned char* smem, int
 {
 	CtaSm* C = reinterpret_cast<CtaSm*>(smem);
 	const int lane = tid & 31;
-	const int warp = tid >> 5;
+#ifndef GTTS_CHAIN_A_HW
+#define GTTS_CHAIN_A_HW 23
+#endif
+	// Hardware warp w runs on SM sub-partition w % 4 and the roles slow each other down through its issue
+	// slots and FP64 pipe: chain A trades places with another role so that the sub-partitions are evenly loaded
+	// (measured: chain A on the sub-partition of the idle worker +2.4 %).
+	const int hw = tid >> 5;
+	const int warp = hw == kChainAWarp ? GTTS_CHAIN_A_HW : (hw == GTTS_CHAIN_A_HW ? kChainAWarp : hw);
 	for (int i = tid; i < kSrcFilterLen; i += kThreads) C->tab[i] = P.src_tab[i];
 	if (tid < kBlock) C->zeros[tid] = 0.0;
 	if (tid < kSlots) {
