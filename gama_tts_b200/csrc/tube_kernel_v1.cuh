@@ -53,7 +53,8 @@ enum {
 	kTubeWarps = (kSlots * kTubeLanes + 31) / 32,
 	kChainAWarp = kTubeWarps,
 	kChainBWarp = kTubeWarps + 1,
-	kHelper0 = kTubeWarps + 2,    // one helper warp per slot
+	kChainA2Warp = kTubeWarps + 2,
+	kHelper0 = kTubeWarps + 3,    // one helper warp per slot
 	kPool0 = kHelper0 + kSlots,   // the rest: task workers
 	kPoolWarps = kWarps - kPool0,
 	kStages = 6,                  // last stage (SRC) runs at it = b + 6
@@ -292,21 +293,23 @@ GTTS_DEV void helper_iteration(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int
 			// glottal, aspiration and frication amplitudes (VTMUtil.h:50-67): one rolled loop over the three
 			// parameters.  A value is re-used while its parameter is uniform over the block and unchanged
 			// since the previous block (the reference caches the same way, e.g. BandpassFilter.h:93).
+			// All three are converted in ONE straight-line region when any of them has to be (three independent
+			// exp10 chains overlap; one after the other they were a quarter of the helper's time).
 			double fa = 0.0;
-#pragma unroll 1
-			for (int w = 0; w < 3; ++w) {
-				const float pw = w == 0 ? p1 : (w == 1 ? p2 : p3);
-				const float cp = w == 0 ? h.c_p1 : (w == 1 ? h.c_p2 : h.c_p3);
-				const double cv = w == 0 ? h.c_ax : (w == 1 ? h.c_ah1 : h.c_fa);
-				const float p0v = __shfl_sync(0xffffffffu, pw, 0, 32);
-				const float pe = live ? pw : p0v;
-				const bool uniform = __all_sync(0xffffffffu, pe == p0v);
-				double val;
-				if (uniform && p0v == cp) val = cv; else val = amp60((double) pe);
-				const float ncp = uniform ? p0v : __int_as_float(0x7fc00000);
-				if (w == 0) { ax = val; h.c_p1 = ncp; h.c_ax = val; }
-				else if (w == 1) { ah1 = val; h.c_p2 = ncp; h.c_ah1 = val; }
-				else { fa = val; h.c_p3 = ncp; h.c_fa = val; }
+			{
+				const float q1 = __shfl_sync(0xffffffffu, p1, 0, 32), q2 = __shfl_sync(0xffffffffu, p2, 0, 32);
+				const float q3 = __shfl_sync(0xffffffffu, p3, 0, 32);
+				const float e1 = live ? p1 : q1, e2 = live ? p2 : q2, e3 = live ? p3 : q3;
+				const bool u1 = __all_sync(0xffffffffu, e1 == q1), u2 = __all_sync(0xffffffffu, e2 == q2);
+				const bool u3 = __all_sync(0xffffffffu, e3 == q3);
+				if (u1 && u2 && u3 && q1 == h.c_p1 && q2 == h.c_p2 && q3 == h.c_p3) {
+					ax = h.c_ax; ah1 = h.c_ah1; fa = h.c_fa;
+				} else {
+					ax = amp60((double) e1); ah1 = amp60((double) e2); fa = amp60((double) e3);
+				}
+				const float nan = __int_as_float(0x7fc00000);
+				h.c_p1 = u1 ? q1 : nan; h.c_p2 = u2 ? q2 : nan; h.c_p3 = u3 ? q3 : nan;
+				h.c_ax = ax; h.c_ah1 = ah1; h.c_fa = fa;
 			}
 			const double fpos = (double) p[4];
 			int ip = (int) fpos;
@@ -396,14 +399,27 @@ GTTS_DEV void helper_iteration(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int
 			// is loaded while the current one is accumulated.
 			const double* pe = S->ve + 24 + lane;
 			const double* po = S->vo + 24 + lane;
-			double acc = 0.0;
+#ifndef GTTS_EMU
+			// two accumulator chains (odd-phase taps | even-phase taps): 25 dependent multiply-adds instead of 49
+			double accO = 0.0, accE = 0.0;
 #pragma unroll kFirUnroll
+			for (int m = 0; m < 24; ++m) {
+				accO += po[-m] * c_fir[2 * m];
+				accE += pe[-m] * c_fir[2 * m + 1];
+			}
+			accO += po[-24] * c_fir[48];
+			firOut = accO + accE;
+#else
+			// CPU emulation (tests/simt_emu): the reference's single ascending sum, so that the emulated kernel
+			// stays bit-identical to the oracle
+			double acc = 0.0;
 			for (int m = 0; m < 24; ++m) {
 				acc += po[-m] * c_fir[2 * m];
 				acc += pe[-m] * c_fir[2 * m + 1];
 			}
 			acc += po[-24] * c_fir[48];
 			firOut = acc;
+#endif
 		}
 		__syncwarp();
 		if (lane < 24) {
@@ -663,22 +679,54 @@ GTTS_DEV void src_shared_task(CtaSm* C, const KernelParamsV1& P, int lane, int p
 // Both recurrences are stepped in one loop so that their latencies overlap; the operands of step j+1
 // are loaded while step j computes.  Lanes whose slot has no such block run on dummy data (their
 // results are never read), which keeps the loop free of divergent branches.
-struct ChainARegs { double pos; BandpassState bp; };
+struct ChainARegs { double pos; };
+struct ChainA2Regs { BandpassState bp; };
 
+// chain A, lane = slot: oscillator phase of block it - 1 (WavetableGlottalSource.h:196-199, 265-272: two
+// half-sample increments per sample, wrap above 511).  42 dependent cycles per sample; the operands of a chunk
+// of 8 samples are loaded before it is stepped.
 GTTS_DEV void chain_a_iteration(CtaSm* C, const KernelParamsV1& P, int lane, ChainARegs& r, int p)
 {
 	(void) P;
 	if (lane >= kSlots) return;
 	SlotSm* S = &C->slot[lane];
-	const SlotSm::Ctl& K = S->ctl[p];
-	const int it = K.it;
-	const int b1 = it - 1, b3 = it - 3;
+	const int b1 = S->ctl[p].it - 1;
 	if (b1 == 0) r.pos = 0.0;
-	if (b3 == 0) { r.bp.x1 = r.bp.x2 = r.bp.y1 = r.bp.y2 = 0.0; }
-	const int buf1 = b1 & 1, buf3 = b3 & 1;
+	const int buf1 = b1 & 1;
 	const double* osc = S->osc[buf1];
 	double* p0 = S->pos[buf1][0];
 	double* p1 = S->pos[buf1][1];
+	double pos = r.pos;
+#pragma unroll 1
+	for (int j0 = 0; j0 < kBlock; j0 += 8) {
+		double inc[8], o0[8], o1[8];
+#pragma unroll
+		for (int q = 0; q < 8; ++q) inc[q] = osc[j0 + q];
+#pragma unroll
+		for (int q = 0; q < 8; ++q) {
+			double s = pos + inc[q];
+			pos = (s > 511.0) ? s - 512.0 : s;
+			o0[q] = pos;
+			s = pos + inc[q];
+			pos = (s > 511.0) ? s - 512.0 : s;
+			o1[q] = pos;
+		}
+#pragma unroll
+		for (int q = 0; q < 8; ++q) { p0[j0 + q] = o0[q]; p1[j0 + q] = o1[q]; }
+	}
+	r.pos = pos;
+}
+
+// chain A2, lane = slot: frication bandpass of block it - 3 (BandpassFilter.h:114-122) and the two tap signals.
+// Lanes whose slot has no such block run on dummy data (their results are never read).
+GTTS_DEV void chain_a2_iteration(CtaSm* C, const KernelParamsV1& P, int lane, ChainA2Regs& r, int p)
+{
+	(void) P;
+	if (lane >= kSlots) return;
+	SlotSm* S = &C->slot[lane];
+	const int b3 = S->ctl[p].it - 3;
+	if (b3 == 0) { r.bp.x1 = r.bp.x2 = r.bp.y1 = r.bp.y2 = 0.0; }
+	const int buf3 = b3 & 1;
 	const double* sig = S->sig[buf3];
 	const double* c0 = S->bp[buf3][0];
 	const double* c1 = S->bp[buf3][1];
@@ -686,29 +734,18 @@ GTTS_DEV void chain_a_iteration(CtaSm* C, const KernelParamsV1& P, int lane, Cha
 	const double* ta = S->tapa[buf3];
 	const double* tb = S->tapb[buf3];
 	double2* pab = S->pab[buf3];
-	double pos = r.pos, x1 = r.bp.x1, x2 = r.bp.x2, y1 = r.bp.y1, y2 = r.bp.y2;
+	double x1 = r.bp.x1, x2 = r.bp.x2, y1 = r.bp.y1, y2 = r.bp.y2;
 	bool anyFric = false;
-	// chunks of 4 samples: all operands of a chunk are loaded into registers before the two recurrences
-	// are stepped, so that shared-memory latency is paid once per chunk instead of once per sample
 #pragma unroll 1
 	for (int j0 = 0; j0 < kBlock; j0 += 4) {
-		double inc[4], x[4], b0[4], a1[4], a2[4], tA[4], tB[4];
+		double x[4], b0[4], a1[4], a2[4], tA[4], tB[4], oa[4], ob[4];
 #pragma unroll
 		for (int q = 0; q < 4; ++q) {
-			inc[q] = osc[j0 + q]; x[q] = sig[j0 + q]; b0[q] = c0[j0 + q]; a1[q] = c1[j0 + q]; a2[q] = c2[j0 + q];
+			x[q] = sig[j0 + q]; b0[q] = c0[j0 + q]; a1[q] = c1[j0 + q]; a2[q] = c2[j0 + q];
 			tA[q] = ta[j0 + q]; tB[q] = tb[j0 + q];
 		}
-		double o0[4], o1[4], oa[4], ob[4];
 #pragma unroll
 		for (int q = 0; q < 4; ++q) {
-			// WavetableGlottalSource.h:196-199, 265-272 (two half-sample increments, wrap above 511)
-			double s = pos + inc[q];
-			pos = (s > 511.0) ? s - 512.0 : s;
-			o0[q] = pos;
-			s = pos + inc[q];
-			pos = (s > 511.0) ? s - 512.0 : s;
-			o1[q] = pos;
-			// BandpassFilter.h:114-122
 			const double y = b0[q] * (x[q] - x2) - a1[q] * y1 - a2[q] * y2;
 			x2 = x1; x1 = x[q]; y2 = y1; y1 = y;
 			oa[q] = tA[q] * y;
@@ -716,14 +753,10 @@ GTTS_DEV void chain_a_iteration(CtaSm* C, const KernelParamsV1& P, int lane, Cha
 			anyFric = anyFric || oa[q] != 0.0 || ob[q] != 0.0;
 		}
 #pragma unroll
-		for (int q = 0; q < 4; ++q) {
-			p0[j0 + q] = o0[q];
-			p1[j0 + q] = o1[q];
-			pab[j0 + q] = make_double2(oa[q], ob[q]);
-		}
+		for (int q = 0; q < 4; ++q) pab[j0 + q] = make_double2(oa[q], ob[q]);
 	}
 	S->fric[buf3] = anyFric ? 1 : 0;
-	r.pos = pos; r.bp.x1 = x1; r.bp.x2 = x2; r.bp.y1 = y1; r.bp.y2 = y2;
+	r.bp.x1 = x1; r.bp.x2 = x2; r.bp.y1 = y1; r.bp.y2 = y2;
 }
 
 // ---- chain B (warp 3, lane = slot * 4 + filter): radiation filters + throat lowpass of block it - 5 ------
@@ -1043,8 +1076,11 @@ GTTS_DEV void tube_v1_cta_body(const KernelParamsV1& P, unsigned char* smem, int
 		TubeLane tl = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 		GTTS_ROLE_LOOP(if (!(skip & 32)) tube_iteration(C, P, warp, lane, tl, p);)
 	} else if (warp == kChainAWarp) {
-		ChainARegs ca = {0.0, {0.0, 0.0, 0.0, 0.0}};
+		ChainARegs ca = {0.0};
 		GTTS_ROLE_LOOP(if (!(skip & 8)) chain_a_iteration(C, P, lane, ca, p); schedule_slots(C, P, lane, p, false);)
+	} else if (warp == kChainA2Warp) {
+		ChainA2Regs ca2 = {{0.0, 0.0, 0.0, 0.0}};
+		GTTS_ROLE_LOOP(if (!(skip & 8)) chain_a2_iteration(C, P, lane, ca2, p);)
 	} else if (warp == kChainBWarp) {
 		ChainBRegs cb = {0.0, 0.0};
 		GTTS_ROLE_LOOP(if (!(skip & 16)) chain_b_iteration(C, P, lane, cb, p);)
