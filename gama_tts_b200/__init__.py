@@ -194,6 +194,13 @@ class TubeSynthesizer:
         check(self._lib.gtts_probe_fp64_peak(self._h, C.byref(t)))
         return t.value
 
+    def probe_exp(self, x):
+        """The kernels' 2^x and 10^x evaluated on the device (test hook)."""
+        x = np.ascontiguousarray(x, np.float64)
+        e2, e10 = np.empty_like(x), np.empty_like(x)
+        check(self._lib.gtts_probe_exp(self._h, x.ctypes.data, len(x), e2.ctypes.data, e10.ctypes.data))
+        return e2, e10
+
     def prepare(self, voice_or_voices, frame_offsets, voice_index=None, control_rate=voices.DEFAULT_CONTROL_RATE,
                 steps_override=None):
         vl = [voice_or_voices] if isinstance(voice_or_voices, dict) else list(voice_or_voices)

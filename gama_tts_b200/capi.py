@@ -53,7 +53,7 @@ def voice_array(voices):
 EXPORTS = [
     "gtts_last_error", "gtts_abi_version", "gtts_voice_internal_rate", "gtts_voice_control_steps",
     "gtts_output_length", "gtts_shard_plan", "gtts_probe_fir_taps", "gtts_probe_src_tables",
-    "gtts_probe_voice_constants", "gtts_probe_fp64_peak", "gtts_create", "gtts_destroy", "gtts_describe", "gtts_batch_prepare",
+    "gtts_probe_voice_constants", "gtts_probe_fp64_peak", "gtts_probe_exp", "gtts_create", "gtts_destroy", "gtts_describe", "gtts_batch_prepare",
     "gtts_batch_layout", "gtts_batch_lengths", "gtts_batch_run_device", "gtts_batch_run_host", "gtts_batch_last_launches",
     "gtts_batch_free", "gtts_batch_synthesize", "gtts_stream_open", "gtts_stream_push_frames",
     "gtts_stream_finish", "gtts_stream_reset", "gtts_stream_close",
@@ -84,6 +84,7 @@ def load():
     L.gtts_probe_src_tables.argtypes = [vp, vp]
     L.gtts_probe_voice_constants.argtypes = [PV, vp, i32, C.POINTER(i32)]
     L.gtts_probe_fp64_peak.argtypes = [vp, C.POINTER(dbl)]
+    L.gtts_probe_exp.argtypes = [vp, vp, i32, vp, vp]
     L.gtts_create.argtypes = [i32, C.POINTER(vp)]
     L.gtts_destroy.argtypes = [vp]
     L.gtts_destroy.restype = None

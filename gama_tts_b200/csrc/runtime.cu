@@ -347,6 +347,33 @@ void gtts_destroy(gtts_handle* h)
 
 const char* gtts_describe(gtts_handle* h) { return h ? h->description.c_str() : "{}"; }
 
+namespace {
+__global__ void probe_exp_kernel(const double* x, int n, double* out2, double* out10)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) { out2[i] = gtts_exp2(x[i]); out10[i] = gtts_exp10(x[i]); }
+}
+} // namespace
+
+int gtts_probe_exp(gtts_handle* h, const double* x, int32_t n, double* exp2_out, double* exp10_out)
+{
+	if (!h || !x || !exp2_out || !exp10_out || n < 0) return fail(GTTS_ERR_INVALID, "bad argument");
+	if (n == 0) return GTTS_OK;
+	GTTS_CUDA(cudaSetDevice(h->device));
+	double* d = nullptr;
+	GTTS_CUDA(cudaMalloc(&d, sizeof(double) * 3 * n));
+	cudaError_t e = cudaMemcpy(d, x, sizeof(double) * n, cudaMemcpyHostToDevice);
+	if (e == cudaSuccess) {
+		probe_exp_kernel<<<(n + 255) / 256, 256>>>(d, n, d + n, d + 2 * (size_t) n);
+		e = cudaGetLastError();
+	}
+	if (e == cudaSuccess) e = cudaMemcpy(exp2_out, d + n, sizeof(double) * n, cudaMemcpyDeviceToHost);
+	if (e == cudaSuccess) e = cudaMemcpy(exp10_out, d + 2 * (size_t) n, sizeof(double) * n, cudaMemcpyDeviceToHost);
+	cudaFree(d);
+	if (e != cudaSuccess) return failCuda(e, "gtts_probe_exp");
+	return GTTS_OK;
+}
+
 int gtts_probe_fp64_peak(gtts_handle* h, double* tflops_out)
 {
 	if (!h || !tflops_out) return fail(GTTS_ERR_INVALID, "null argument");

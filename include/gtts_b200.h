@@ -110,6 +110,9 @@ const char* gtts_describe(gtts_handle* handle);
 /* Measures this GPU's FP64 FMA-pipe peak (TFLOP/s) with a register-resident DFMA kernel (~30 ms):
  * the roofline denominator of this path (MEASURED_PEAKS.json only carries HBM and bf16 figures). */
 int gtts_probe_fp64_peak(gtts_handle* handle, double* tflops_out);
+/* Test hook: the kernels' 2^x and 10^x (the reference's pow(2, .) / pow(10, .) in VTMUtil.h:50-84, valid for |x| < 16)
+ * evaluated on the device for x[n] (host arrays). */
+int gtts_probe_exp(gtts_handle* handle, const double* x, int32_t n, double* exp2_out, double* exp10_out);
 
 /* Plans a batch of n_utt utterances.
  *   voices[n_voices]        voice table; voice_index[u] selects one (NULL: every utterance uses voices[0])

@@ -211,3 +211,17 @@ def test_pinned_host_output_is_written_directly(synth):
         gaps[b.out_offsets[u]:b.out_offsets[u] + b.n_out[u]] = False
     assert not h_out.numpy()[gaps].any()
     b.close()
+
+
+def test_device_exp2_exp10_match_libm(synth):
+    # the kernels' branch-free 2^x / 10^x (tube_kernel.cuh) against libm over the ranges the path uses:
+    # (pitch + 3) / 12 with pitch in [-30, 30] semitones, (dB - 60) / 20 with dB in (0, 100]
+    rng = np.random.Generator(np.random.PCG64(11))
+    x = np.concatenate([rng.uniform(-16.0, 16.0, 200000), np.linspace(-3.0, 2.0, 100001),
+                        np.array([0.0, -0.0, 1.0, -1.0, 0.5, -0.5, 1e-300, -3.0, 15.999, -15.999])])
+    e2, e10 = synth.probe_exp(x)
+    r2, r10 = np.exp2(x), np.power(10.0, x)
+    ulp2 = np.abs(e2 - r2) / np.spacing(r2)
+    ulp10 = np.abs(e10 - r10) / np.spacing(r10)
+    assert ulp2.max() <= 2.0, ulp2.max()
+    assert ulp10.max() <= 2.0, ulp10.max()
