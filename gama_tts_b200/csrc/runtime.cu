@@ -137,8 +137,8 @@ int launchBatch(gtts_batch* b, const float* dFrames, float* dOut, cudaStream_t s
 		const bool profile = std::getenv("GTTS_PROFILE") != nullptr;
 		long long* dProf = nullptr;
 		if (profile) {
-			GTTS_CUDA(cudaMalloc(&dProf, sizeof(long long) * grid * (v1::kWarps + 1)));
-			GTTS_CUDA(cudaMemsetAsync(dProf, 0, sizeof(long long) * grid * (v1::kWarps + 1), stream));
+			GTTS_CUDA(cudaMalloc(&dProf, sizeof(long long) * grid * (2 * v1::kWarps + 1)));
+			GTTS_CUDA(cudaMemsetAsync(dProf, 0, sizeof(long long) * grid * (2 * v1::kWarps + 1), stream));
 			Q.prof = dProf;
 			long long* dSec = nullptr;
 			GTTS_CUDA(cudaMalloc(&dSec, sizeof(long long) * grid * 6));
@@ -149,18 +149,24 @@ int launchBatch(gtts_batch* b, const float* dFrames, float* dOut, cudaStream_t s
 		GTTS_CUDA(cudaGetLastError());
 		if (profile) {
 			// debugging aid: busy cycles per warp role and iteration, averaged over the CTAs
-			std::vector<long long> hp(static_cast<size_t>(grid) * (v1::kWarps + 1));
+			const size_t rowLen = 2 * v1::kWarps + 1;
+			std::vector<long long> hp(static_cast<size_t>(grid) * rowLen);
 			GTTS_CUDA(cudaStreamSynchronize(stream));
 			GTTS_CUDA(cudaMemcpy(hp.data(), dProf, sizeof(long long) * hp.size(), cudaMemcpyDeviceToHost));
 			cudaFree(dProf);
-			double sum[v1::kWarps] = {0};
+			double sum[v1::kWarps] = {0}, last[v1::kWarps] = {0};
 			double iters = 0;
 			for (int c = 0; c < grid; ++c) {
-				for (int w = 0; w < v1::kWarps; ++w) sum[w] += static_cast<double>(hp[static_cast<size_t>(c) * (v1::kWarps + 1) + w]);
-				iters += static_cast<double>(hp[static_cast<size_t>(c) * (v1::kWarps + 1) + v1::kWarps]);
+				for (int w = 0; w < v1::kWarps; ++w) {
+					sum[w] += static_cast<double>(hp[static_cast<size_t>(c) * rowLen + w]);
+					last[w] += static_cast<double>(hp[static_cast<size_t>(c) * rowLen + v1::kWarps + 1 + w]);
+				}
+				iters += static_cast<double>(hp[static_cast<size_t>(c) * rowLen + v1::kWarps]);
 			}
 			std::fprintf(stderr, "[gtts profile] grid %d, iterations per CTA %.0f; busy cycles per iteration by warp:", grid, iters / grid);
 			for (int w = 0; w < v1::kWarps; ++w) std::fprintf(stderr, " %d:%.0f", w, sum[w] / (iters > 0 ? iters : 1));
+			std::fprintf(stderr, "\n[gtts profile] share of iterations in which the role reached the barrier last (%%):");
+			for (int w = 0; w < v1::kWarps; ++w) std::fprintf(stderr, " %d:%.0f", w, 100.0 * last[w] / (iters > 0 ? iters : 1));
 			std::fprintf(stderr, "\n");
 			cudaFree(Q.prof_sections);
 		}

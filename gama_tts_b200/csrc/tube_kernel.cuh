@@ -145,6 +145,25 @@ GTTS_DEV double amp60(double db)
 // (a - b) / (a + b): scattering coefficient from two squared radii.
 GTTS_DEV double kcoef(double a2, double b2) { return (a2 - b2) / (a2 + b2); }
 
+// a / b for well-scaled operands (squared radii: 1e-4 .. 1e2), branch-free: hardware reciprocal estimate, two
+// Newton steps, one residual correction -- 8 instructions without the special-case path of the IEEE division, so
+// that the ten divisions of a sample overlap instead of running one after the other.  Within 1 ulp of a / b.
+GTTS_DEV double div_fast(double a, double b)
+{
+#ifndef GTTS_EMU
+	double r;
+	asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+	double e = fma(-b, r, 1.0);
+	r = fma(r, e, r);
+	e = fma(-b, r, 1.0);
+	r = fma(r, e, r);
+	const double q = a * r;
+	return fma(fma(-b, q, a), r, q);
+#else
+	return a / b;
+#endif
+}
+
 // ---- stage: float32 interpolation, lane = parameter (Controller.cpp:297-311) ----------------------------
 // Writes cur[j][k] for j < nb and advances the running value by nb sequential float additions.
 GTTS_DEV void stage_interp(WarpSm* S, int lane, int nb, float& cur, float delta)

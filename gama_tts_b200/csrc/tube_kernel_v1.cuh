@@ -26,7 +26,7 @@
 #define GTTS_FIR_UNROLL 4
 #endif
 #ifndef GTTS_COEF_UNROLL
-#define GTTS_COEF_UNROLL 1
+#define GTTS_COEF_UNROLL 9
 #endif
 #ifndef GTTS_CHAINB_CHUNK
 #define GTTS_CHAINB_CHUNK 8
@@ -99,7 +99,6 @@ struct CtaSm {
 	double2 tab[kSrcFilterLen];
 	SlotSm slot[kSlots];
 	float  pscratch[kSlots][kBlock][9];       // per-slot scratch of the coefficient task: parameters 7..15 of one block
-	double zeros[kBlock];                     // operand row of the tube lanes that take no per-sample input
 	struct Sched {
 		int live;                 // some slot has work
 		int src_shared;           // 1: every slot in the SRC stage is at the same block of an equally long utterance of the same rate
@@ -127,8 +126,11 @@ struct KernelParamsV1 {
 
 #ifndef GTTS_EMU
 #define GTTS_CLOCK() clock64()
+// clock read that cannot be scheduled before `dep` (a value loaded after a barrier) is available
+#define GTTS_CLOCK_AFTER(t, dep) asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) : "r"(dep) : "memory")
 #else
 #define GTTS_CLOCK() 0ll
+#define GTTS_CLOCK_AFTER(t, dep) ((t) = 0)
 #endif
 
 // ceil((n << 16) / inc): number of outputs whose right wing ends before input n (SampleRateConverter.h:
@@ -523,13 +525,13 @@ GTTS_DEV void coef_task(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int lane, 
 				b2 = V.nr1_2;
 			}
 			if (i == 3) r2_3 = a2;
-			const double k = kcoef(a2, b2);
+			const double k = div_fast(a2 - b2, a2 + b2);
 			if (i == 7) k7 = k;
 			const int dst = i <= 2 ? i : (i == 3 ? 4 : i + 2);     // (row, component) of junction i in the kab rows
 			kabFlat[((dst >> 1) * kRow + lane) * 2 + (dst & 1)] = ((i == 7) ? k * V.refl_b0_m : k) * dmp;   // damping (and the mouth end's b0) folded in: tube_iteration
 			a2 = b2;
 		}
-		const double sum = 2.0 / (r2_3 + r2_3 + v2);
+		const double sum = div_fast(2.0, r2_3 + r2_3 + v2);
 		S->kab[buf][1][lane].y = ((sum * r2_3) - 1.0) * dmp;   // alpha left == alpha right, stored as (alpha - 1) d (tube_iteration)
 		S->kab[buf][2][lane].y = 0.0;                          // S6-S7 is a pure damped delay: k = 0
 		S->kab[buf][5][lane].y = V.nasal_k[1] * dmp;
@@ -853,9 +855,13 @@ GTTS_DEV void chain_b_iteration(CtaSm* C, const KernelParamsV1& P, int lane, Cha
 GTTS_DEV void tube_iteration(CtaSm* C, const KernelParamsV1& P, int warp, int lane, TubeLane& t, int p)
 {
 	(void) P;
-	const int u = lane & 15;
-	const int slot = warp * 2 + (lane >> 4);
-	const int base = lane & ~15;
+	// lane = 2 u + s: cell u of the warp's slot s.  The two slots are interleaved so that the few lanes that load
+	// or store something of their own (u = 0, 3, 9, 15) sit in the same half-warp for both slots: a 64-bit
+	// shared-memory access costs one wavefront per half-warp with an active lane, and the shared-memory pipe
+	// (71 % busy) is what the loop's shuffles queue behind.
+	const int u = lane >> 1;
+	const int sbit = lane & 1;
+	const int slot = warp + kTubeWarps * sbit;         // slots w and w + 4: their rows are 64 bytes (16 banks) apart modulo 128
 	SlotSm* S = &C->slot[slot < kSlots ? slot : 0];
 	const SlotSm::Ctl& K = S->ctl[p];
 	const int b = (slot < kSlots) ? K.it - 4 : -1;
@@ -874,20 +880,25 @@ GTTS_DEV void tube_iteration(CtaSm* C, const KernelParamsV1& P, int warp, int la
 	const int tap = (u >= 1 && u <= 8) ? u - 1 : -100;
 	const double* kRowp = &S->kab[buf][u >> 1][0].x + (u & 1);     // component u & 1 of the pair row, stride 2 doubles
 	const double2* pabRow = S->pab[buf];
-	const double* e3Row = is3 ? S->au[buf] : C->zeros;
-	const double* inRow = (u == 0) ? S->in[b3] : C->zeros;
+	const bool isGlot = u == 0;
+	const double* e3Row = S->au[buf];                  // read by lane u = 3 only
+	const double* inRow = S->in[b3];                   // read by lane u = 0 only
 	const int* ipRow = S->ip[b3];
 	double* endRow = (u == 15) ? S->endn[buf] : S->endm[buf];
-	const int srcPrev = base + ((u + 15) & 15), srcNext = base + ((u + 1) & 15), srcLink = base + (is3 ? 10 : 3);
+	const int srcPrev = 2 * ((u + 15) & 15) + sbit, srcNext = 2 * ((u + 1) & 15) + sbit, srcLink = 2 * (is3 ? 10 : 3) + sbit;
 	// T = forward wave into the cell, Bn = backward wave from the next cell, nb = wave on the velum link,
 	// last = the cell's own backward output of the previous sample (glottis reflection, end-filter state)
 	double T = t.aT, Bn = t.aB, nb = t.nb0, last = t.extra;
+	// alpha_u d (lane u = 3) and the glottal input (lane u = 0): zero on every other lane, loaded under predicate
+	double e3v[4] = {0.0, 0.0, 0.0, 0.0}, inv[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 1
 	for (int j0 = 0; j0 < kBlock; j0 += 4) {
-		double kv[4], e3v[4], inv[4], tf[4];
+		double kv[4], tf[4];
 #pragma unroll
 		for (int q = 0; q < 4; ++q) {
-			kv[q] = kRowp[2 * (j0 + q)]; e3v[q] = e3Row[j0 + q]; inv[q] = inRow[j0 + q];
+			kv[q] = kRowp[2 * (j0 + q)];
+			if (is3) e3v[q] = e3Row[j0 + q];
+			if (isGlot) inv[q] = inRow[j0 + q];
 			tf[q] = 0.0;
 		}
 		if (fricBlock) {
@@ -1023,27 +1034,37 @@ GTTS_DEV void run_task(CtaSm* C, const KernelParamsV1& P, int lane, int task, in
 #define GTTS_ROLE_LOOP(BODY)                                                     \
 	{                                                                            \
 		int p = 0;                                                               \
-		long long busy = 0, iters = 0;                                           \
-		while (C->sched[p].live) {                                               \
+		long long busy = 0, iters = 0, lastIn = 0;                               \
+		int live = C->sched[0].live;                                             \
+		while (live) {                                                           \
 			const long long tStart = GTTS_CLOCK();                               \
 			BODY                                                                 \
-			busy += GTTS_CLOCK() - tStart;                                       \
+			const long long tEnd = GTTS_CLOCK();                                 \
+			busy += tEnd - tStart;                                               \
 			iters += 1;                                                          \
 			__syncthreads();                                                     \
 			p ^= 1;                                                              \
+			live = C->sched[p].live;                                             \
+			long long tRel;                                                      \
+			GTTS_CLOCK_AFTER(tRel, live);                                        \
+			if (tRel - tEnd < 300) lastIn += 1;                                  \
 		}                                                                        \
-		role_profile(P, warp, lane, busy, iters);                                \
+		role_profile(P, warp, lane, busy, iters, lastIn);                        \
 	}
 
-GTTS_DEV void role_profile(const KernelParamsV1& P, int warp, int lane, long long busy, long long iters)
+// GTTS_PROFILE=1: per CTA [0, kWarps) busy cycles of every role, [kWarps] iterations, then per role the number of
+// iterations in which it was among the last to reach the barrier (it waited less than 200 cycles there)
+GTTS_DEV void role_profile(const KernelParamsV1& P, int warp, int lane, long long busy, long long iters, long long lastIn)
 {
 #ifndef GTTS_EMU
 	if (P.prof != nullptr && lane == 0) {
-		P.prof[(size_t) blockIdx.x * (kWarps + 1) + warp] = busy;
-		if (warp == 0) P.prof[(size_t) blockIdx.x * (kWarps + 1) + kWarps] = iters;
+		long long* row = P.prof + (size_t) blockIdx.x * (2 * kWarps + 1);
+		row[warp] = busy;
+		row[kWarps + 1 + warp] = lastIn;
+		if (warp == 0) row[kWarps] = iters;
 	}
 #else
-	(void) P; (void) warp; (void) lane; (void) busy; (void) iters;
+	(void) P; (void) warp; (void) lane; (void) busy; (void) iters; (void) lastIn;
 #endif
 }
 
@@ -1060,7 +1081,6 @@ GTTS_DEV void tube_v1_cta_body(const KernelParamsV1& P, unsigned char* smem, int
 	const int hw = tid >> 5;
 	const int warp = hw == kChainAWarp ? GTTS_CHAIN_A_HW : (hw == GTTS_CHAIN_A_HW ? kChainAWarp : hw);
 	for (int i = tid; i < kSrcFilterLen; i += kThreads) C->tab[i] = P.src_tab[i];
-	if (tid < kBlock) C->zeros[tid] = 0.0;
 	if (tid < kSlots) {
 		for (int b = 0; b < 2; ++b) { C->slot[tid].ctl[b].it = -1; C->slot[tid].ctl[b].voice = 0; C->slot[tid].ctl[b].nblocks = 0; }
 	}
