@@ -50,6 +50,7 @@ enum {
 	kWarps = 24,
 	kThreads = kWarps * 32,
 	kTubeLanes = 16,              // one cell per lane
+	kParamRow = 36,               // floats per walked-parameter row: 16-byte aligned, rows 4 banks apart (float4 stores by 7-9 lanes)
 	kTubeWarps = (kSlots * kTubeLanes + 31) / 32,
 	kChainAWarp = kTubeWarps,
 	kChainBWarp = kTubeWarps + 1,
@@ -77,8 +78,8 @@ struct SlotSm {
 	double rad[3][kRow];          // mouth radiation, nose radiation, throat outputs of one block
 	double ve[kVRing], vo[kVRing];
 	double xring[2 * kSrcRing];   // tube output ring, every sample stored twice (i and i + 128): any 26-sample window is contiguous
-	float  cur[kBlock][7];        // slot helper scratch: parameters 0..6 of the block being converted
-	int    ip[3][kBlock];
+	alignas(16) float cur[7][kParamRow];     // slot helper scratch: parameters 0..6 of the block being converted, [parameter][sample]
+	signed char ip[3][kBlock];    // integer part of the frication position (-50: none)
 	VoiceDev V;                   // the slot's voice constants (copied from global memory when an utterance starts)
 	int    fric[2];               // block has frication (some tap * bandpassed noise != 0), per pab buffer
 	float  ckey[9];               // parameters 7..15 at the last sample of the previous block (NaN: none)
@@ -91,14 +92,14 @@ struct SlotSm {
 		int voice;
 		int pad;
 	} ctl[2];
-	int     pad_[13];              // slot stride = 16 mod 128 bytes: the 7 slots start in different banks
+	int     pad_[25];              // slot stride = 16 mod 128 bytes: the 7 slots start in different banks
 };
 static_assert(sizeof(SlotSm) % 128 == 16, "slot stride should be 16 mod 128 bytes (bank spreading); adjust pad_");
 
 struct CtaSm {
 	double2 tab[kSrcFilterLen];
 	SlotSm slot[kSlots];
-	float  pscratch[kSlots][kBlock][9];       // per-slot scratch of the coefficient task: parameters 7..15 of one block
+	float  pscratch[kSlots][9][kParamRow];    // per-slot scratch of the coefficient task: parameters 7..15 of one block, [parameter][sample]
 	struct Sched {
 		int live;                 // some slot has work
 		int src_shared;           // 1: every slot in the SRC stage is at the same block of an equally long utterance of the same rate
@@ -152,13 +153,13 @@ GTTS_DEV int block_len(const SlotSm::Ctl& k, int b)
 
 // ---- float32 walk of a group of parameters over one block (Controller.cpp:297-311) -----------------
 // lane k walks parameter base + k: cur/delta/off/frame are the lane's cursor (registers or shared),
-// out[j][k] receives the value used for sample j.  Control periods are >= one block, so at most one
+// out[j] (the lane's own row of kParamRow floats, 16-byte aligned) receives the value used for sample j.  Control periods are >= one block, so at most one
 // frame boundary falls inside the block.
 // The cursor carries the next two frame values (fn1 = frame[f+1], fn2 = frame[f+2], clamped to the last
 // frame): they are fetched from global memory one control period ahead, so no load sits on the walk.
 GTTS_DEV void walk_block(const float* frames, long long nFrames, int steps, float invSteps, int param,
 			int nb, float& cur, float& delta, float& fn1, float& fn2, int& off, int& frame,
-			float* out, int outStride, bool active)
+			float* out, bool active)
 {
 	// `first` samples of the block still belong to the current control period; the period ends inside
 	// (or exactly at the end of) this block iff off + first == steps.  At step `first` the walk restarts
@@ -175,13 +176,14 @@ GTTS_DEV void walk_block(const float* frames, long long nFrames, int steps, floa
 	// (pinned host memory: microseconds over PCIe) never stalls the walk.
 	const int mine = reaches ? first : 2 * kBlock;
 	const int ra = __shfl_sync(0xffffffffu, mine, 0), rb = __shfl_sync(0xffffffffu, mine, 1);
-	float* o = out;
+	float4* o = reinterpret_cast<float4*>(out);
 #pragma unroll 1
 	for (int j0 = 0; j0 < kBlock; j0 += 4) {
+		float v[4];
 		if ((unsigned) (ra - j0) >= 4u && (unsigned) (rb - j0) >= 4u) {
 #pragma unroll
 			for (int q = 0; q < 4; ++q) {
-				if (active) o[q * outStride] = c;
+				v[q] = c;
 				c = __fadd_rn(c, d);
 			}
 		} else {
@@ -192,11 +194,12 @@ GTTS_DEV void walk_block(const float* frames, long long nFrames, int steps, floa
 					c = fn1;
 					d = __fmul_rn(__fsub_rn(fn2, fn1), invSteps);
 				}
-				if (active) o[q * outStride] = c;
+				v[q] = c;
 				c = __fadd_rn(c, d);
 			}
 		}
-		o += 4 * outStride;
+		if (active) *o = make_float4(v[0], v[1], v[2], v[3]);      // one 16-byte store per four samples
+		o += 1;
 	}
 	if (restart == kBlock) {
 		GTTS_KEEP_IN_BRANCH(fn2);
@@ -274,13 +277,13 @@ GTTS_DEV void helper_iteration(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int
 		const bool mine = (lane == 0) ? do0 : (lane < 7 && do2);
 		const int nb = (lane == 0) ? block_len(K, b0) : block_len(K, b2);
 		walk_block(frames, nFrames, K.U.steps, K.U.inv_steps, lane, nb, h.cur, h.delta, h.fn1, h.fn2, h.off, h.frame,
-				&S->cur[0][lane < 7 ? lane : 0], 7, mine);
+				S->cur[lane < 7 ? lane : 0], mine);
 	}
 	__syncwarp();
 	if (do0) {
 		const int nb = block_len(K, b0);
 		if (lane < nb) {
-			const double f0 = 220.0 * gtts_exp2(((double) S->cur[lane][0] + 3.0) * (1.0 / 12.0));
+			const double f0 = 220.0 * gtts_exp2(((double) S->cur[0][lane] + 3.0) * (1.0 / 12.0));
 			S->osc[b0 & 1][lane] = (f0 / 2.0) * V.basic_inc;
 		}
 	}
@@ -290,8 +293,8 @@ GTTS_DEV void helper_iteration(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int
 		double ax = 0.0, ah1 = 0.0;
 		{
 			const bool live = lane < nb;
-			const float* p = S->cur[lane < nb ? lane : 0];
-			const float p1 = p[1], p2 = p[2], p3 = p[3], p5 = p[5], p6 = p[6];
+			const int col = lane < nb ? lane : 0;
+			const float p1 = S->cur[1][col], p2 = S->cur[2][col], p3 = S->cur[3][col], p5 = S->cur[5][col], p6 = S->cur[6][col];
 			// glottal, aspiration and frication amplitudes (VTMUtil.h:50-67): one rolled loop over the three
 			// parameters.  A value is re-used while its parameter is uniform over the block and unchanged
 			// since the previous block (the reference caches the same way, e.g. BandpassFilter.h:93).
@@ -313,7 +316,7 @@ GTTS_DEV void helper_iteration(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int
 				h.c_p1 = u1 ? q1 : nan; h.c_p2 = u2 ? q2 : nan; h.c_p3 = u3 ? q3 : nan;
 				h.c_ax = ax; h.c_ah1 = ah1; h.c_fa = fa;
 			}
-			const double fpos = (double) p[4];
+			const double fpos = (double) S->cur[4][col];
 			int ip = (int) fpos;
 			const double comp = fpos - ip;
 			double ta = (1.0 - comp) * fa, tb = comp * fa;
@@ -341,7 +344,7 @@ GTTS_DEV void helper_iteration(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int
 			if (live) {
 				S->tapa[buf][lane] = ta;
 				S->tapb[buf][lane] = tb;
-				S->ip[b2 % 3][lane] = ip;
+				S->ip[b2 % 3][lane] = (signed char) ip;
 				S->bp[buf][2][lane] = a2;
 				S->bp[buf][1][lane] = a1;
 				S->bp[buf][0][lane] = b0;
@@ -463,30 +466,29 @@ GTTS_DEV void coef_task(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int lane, 
 	const VoiceDev& V = S->V;
 	const float* frames = P.frames + K.U.frame_begin * kNumParams;
 	const int nb = block_len(K, b);
-	float (*scr)[9] = C->pscratch[slotIndex];
+	float (*scr)[kParamRow] = C->pscratch[slotIndex];
 	if (b == 0) {
 		r.cur = r.delta = r.fn1 = r.fn2 = 0.f;
 		if (lane < 9) cursor_init(frames, K.U.n_frames, K.U.inv_steps, 7 + lane, r.cur, r.delta, r.fn1, r.fn2);
 		r.off = 0; r.frame = 0;
 	}
 	walk_block(frames, K.U.n_frames, K.U.steps, K.U.inv_steps, 7 + lane, nb, r.cur, r.delta, r.fn1, r.fn2, r.off, r.frame,
-			&scr[0][lane], 9, lane < 9);
+			scr[lane < 9 ? lane : 0], lane < 9);
 	__syncwarp();
 	// Radii and velum unchanged since the last sample of the previous block (a held posture): the
 	// coefficients are the previous block's last row, copied instead of recomputed (9 divisions saved).
 	const int buf0 = b & 1;
 	bool same = lane >= nb;
 	if (lane < nb) {
-		const float* q = scr[lane];
 		same = true;
 #pragma unroll
-		for (int i = 0; i < 9; ++i) same = same && (q[i] == S->ckey[i]);
+		for (int i = 0; i < 9; ++i) same = same && (scr[i][lane] == S->ckey[i]);
 	}
 	const bool reuse = b > 0 && __all_sync(0xffffffffu, same);
 	__syncwarp();
 	if (lane == kBlock - 1) {
 #pragma unroll
-		for (int i = 0; i < 9; ++i) S->ckey[i] = (nb == kBlock) ? scr[lane][i] : __int_as_float(0x7fc00000);
+		for (int i = 0; i < 9; ++i) S->ckey[i] = (nb == kBlock) ? scr[i][lane] : __int_as_float(0x7fc00000);
 	}
 	if (reuse) {
 		if (lane < nb) {
@@ -499,15 +501,14 @@ GTTS_DEV void coef_task(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int lane, 
 		// Nine scattering coefficients k = (a - b) / (a + b) in ONE rolled loop (the kernel is bound by its
 		// instruction footprint): i = 0..6 oral junctions r_i | r_{i+1}, i = 7 mouth r_8 | aperture,
 		// i = 8 velum | first nasal section.  Radii as in setAllParameters: max(r * coef, 0.01).
-		const float* p = scr[lane];
 		const int buf = b & 1;
 		double* kabFlat = &S->kab[buf][0][0].x;         // [row][lane]{x, y} -> (row * kRow + lane) * 2 + c
-		const double vel = (double) p[8];
+		const double vel = (double) scr[8][lane];
 		const double v2 = vel * vel;
 		const double dmp = V.damping;
 		double a2, r2_3 = 0.0, k7 = 0.0;
 		{
-			double r = (double) p[0] * V.radius_coef[0];
+			double r = (double) scr[0][lane] * V.radius_coef[0];
 			r = r > 0.01 ? r : 0.01;
 			a2 = r * r;
 		}
@@ -515,7 +516,7 @@ GTTS_DEV void coef_task(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int lane, 
 		for (int i = 0; i < 9; ++i) {
 			double b2;
 			if (i < 7) {
-				double r = (double) p[i + 1] * V.radius_coef[i + 1];
+				double r = (double) scr[i + 1][lane] * V.radius_coef[i + 1];
 				r = r > 0.01 ? r : 0.01;
 				b2 = r * r;
 			} else if (i == 7) {
@@ -883,7 +884,7 @@ GTTS_DEV void tube_iteration(CtaSm* C, const KernelParamsV1& P, int warp, int la
 	const bool isGlot = u == 0;
 	const double* e3Row = S->au[buf];                  // read by lane u = 3 only
 	const double* inRow = S->in[b3];                   // read by lane u = 0 only
-	const int* ipRow = S->ip[b3];
+	const signed char* ipRow = S->ip[b3];
 	double* endRow = (u == 15) ? S->endn[buf] : S->endm[buf];
 	const int srcPrev = 2 * ((u + 15) & 15) + sbit, srcNext = 2 * ((u + 1) & 15) + sbit, srcLink = 2 * (is3 ? 10 : 3) + sbit;
 	// T = forward wave into the cell, Bn = backward wave from the next cell, nb = wave on the velum link,

@@ -18,7 +18,7 @@
 #include <ucontext.h>
 
 struct alignas(16) double2 { double x, y; };
-struct float4 { float x, y, z, w; };
+struct alignas(16) float4 { float x, y, z, w; };
 struct float2 { float x, y; };
 
 namespace simt {
@@ -177,6 +177,7 @@ template<class T> inline T __shfl_sync(unsigned mask, T v, int src, int width = 
 }
 inline int atomicAdd(int* p, int v) { const int old = *p; *p += v; return old; }
 inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
+inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 inline int __reduce_max_sync(unsigned mask, int v)
 {
 	int m = v;
