@@ -64,6 +64,17 @@ def make_tracks(rank, n_utt, n_frames):
     return a
 
 
+def measured_traffic():
+    """DRAM bytes per launch of the dominant kernel on this workload, from the committed ncu capture (or None)."""
+    path = os.path.join(ROOT, "profiles", "ncu_r01_traffic_bench.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        return int(d["dram_bytes_read"]) + int(d["dram_bytes_write"])
+    except (OSError, ValueError, KeyError):
+        return None
+
+
 class ClockSampler:
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -285,7 +296,7 @@ def main():
                     "h2d_bytes_per_step": int(frames_np.nbytes), "d2h_bytes_per_step": int(n_samples * 4)},
             "gpu_launches": launches,
             "roofline": {"bound": "fp64_fma", "achieved": achieved_tflops, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved_tflops / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved_tflops / peak, "traffic": measured_traffic(), "peak_source": peak_src,
                          "flops_per_launch": flops_per_launch,
                          "hbm_bytes_per_launch_algorithmic": int(frames_np.nbytes + n_samples * 4)},
             "clocks": clocks,
