@@ -129,7 +129,6 @@ int launchBatch(gtts_batch* b, const float* dFrames, float* dOut, cudaStream_t s
 		Q.queue = b->d_queue;
 		Q.n_utt = static_cast<int32_t>(nUtt);
 		Q.prof = nullptr;
-		Q.prof_sections = nullptr;
 		Q.debug_skip = 0;
 		if (const char* dbg = std::getenv("GTTS_DEBUG_SKIP")) Q.debug_skip = std::atoi(dbg);   // experiments only: wrong output
 		const int64_t ctasWanted = (nUtt + v1::kSlots - 1) / v1::kSlots;
@@ -140,10 +139,6 @@ int launchBatch(gtts_batch* b, const float* dFrames, float* dOut, cudaStream_t s
 			GTTS_CUDA(cudaMalloc(&dProf, sizeof(long long) * grid * (2 * v1::kWarps + 1)));
 			GTTS_CUDA(cudaMemsetAsync(dProf, 0, sizeof(long long) * grid * (2 * v1::kWarps + 1), stream));
 			Q.prof = dProf;
-			long long* dSec = nullptr;
-			GTTS_CUDA(cudaMalloc(&dSec, sizeof(long long) * grid * 6));
-			GTTS_CUDA(cudaMemsetAsync(dSec, 0, sizeof(long long) * grid * 6, stream));
-			Q.prof_sections = dSec;
 		}
 		v1::tube_kernel_v1<<<grid, v1::kThreads, v1::smem_bytes(), stream>>>(Q);
 		GTTS_CUDA(cudaGetLastError());
@@ -168,7 +163,6 @@ int launchBatch(gtts_batch* b, const float* dFrames, float* dOut, cudaStream_t s
 			std::fprintf(stderr, "\n[gtts profile] share of iterations in which the role reached the barrier last (%%):");
 			for (int w = 0; w < v1::kWarps; ++w) std::fprintf(stderr, " %d:%.0f", w, 100.0 * last[w] / (iters > 0 ? iters : 1));
 			std::fprintf(stderr, "\n");
-			cudaFree(Q.prof_sections);
 		}
 		b->last_kernel = "tube_kernel_v1";
 	} else {

@@ -389,7 +389,6 @@ GTTS_DEV void stage_bandpass(WarpSm* S, int lane, int nb, BandpassState& b)
 struct TubeLane {
 	double aT, aB, bT, bB;      // inputs of cell A and cell B (state of the previous sample)
 	double extra;               // g0: B[S1] (glottis end), g1: NB[N1] (velum branch), g4/g7: reflection y1
-	double nb0, y1;             // pipelined kernel only: NB[N1] and reflection state in their own registers
 };
 
 struct TubeRole {
@@ -585,7 +584,7 @@ GTTS_DEV void run_utterance(WarpSm* S, const double2* tab, const KernelParams& P
 	// state
 	double seed = 0.7892347, noiseX1 = 0.0, pos = 0.0;
 	BandpassState bp = {0.0, 0.0, 0.0, 0.0};
-	TubeLane tl = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+	TubeLane tl = {0.0, 0.0, 0.0, 0.0, 0.0};
 	PostState ps = {0.0, 0.0};
 	long long nDone = 0, kDone = 0;
 	const TubeRole role = tube_role(V, lane);

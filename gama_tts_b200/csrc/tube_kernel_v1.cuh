@@ -3,19 +3,23 @@
 // whose stages run concurrently on different warps and different blocks:
 //
 //   it = b     slot helper   float32 walk of parameter 0 -> f0 -> oscillator increments        (lane = sample)
-//   it = b+1   chain A       oscillator phase recurrence (serial, lane = slot)
+//   it = b+1   chain A       oscillator phase recurrence (serial, lane = slot) + slot bookkeeping
 //   it = b+2   slot helper   float32 walk of parameters 1..6 -> amplitudes, frication taps, bandpass
 //                            coefficients; noise (LCG jump); wavetable lookup; 49-tap FIR; mixing   (lane = sample)
-//   it = b+3   chain A       frication bandpass biquad + throat lowpass (serial, lane = slot)
-//              pool          float32 walk of parameters 7..15 -> junction coefficients            (lane = sample)
-//   it = b+4   tube warps    the waveguide itself: 8 lanes per utterance, waves in registers, shuffles
-//   it = b+5   chain B       radiation filters (serial, lane = slot x filter) + output sum
-//   it = b+6   pool          windowed-sinc sample-rate conversion, lane = output sample, coalesced stores
+//   it = b+3   chain A2      frication bandpass biquad + tap signals (serial, lane = slot)
+//              task worker   float32 walk of parameters 7..15 -> junction coefficients            (lane = sample)
+//   it = b+4   tube warps    the waveguide itself: one cell per lane, 16 lanes per utterance, waves in registers,
+//                            three shuffles per sample
+//   it = b+5   chain B       radiation filters + throat lowpass (serial, lane = slot x filter) + output sum
+//   it = b+6   task worker   windowed-sinc sample-rate conversion, lane = output sample, whole 128-byte rows
 //
-// Warps: 0-3 tube (two slots each), 4 chain A, 5 chain B, 6-12 slot helpers, 13-23 pool (dynamic
-// task queue in shared memory).  Two CTA barriers per iteration (work | slot bookkeeping).
-// The per-sample arithmetic is the same as in tube_kernel.cuh (v0), which stays as the general
-// kernel for streaming / resumed utterances and control periods shorter than one block.
+// Warps: 0-3 tube (two slots each), 4 chain A, 5 chain B, 6 chain A2, 7-13 slot helpers, 14-23 task workers
+// (static task list per iteration).  One CTA barrier per iteration: the slot control block and the task list
+// are double-buffered by iteration parity.  Every role has its own loop, so a warp keeps only its own state
+// in registers (80 per thread).
+// The per-sample arithmetic follows tube_kernel.cuh (v0), which stays as the general kernel for streaming /
+// resumed utterances and control periods shorter than one block.  DESIGN.md section 4 has the measurements
+// behind the choices made here.
 #ifndef GTTS_TUBE_KERNEL_V1_CUH_
 #define GTTS_TUBE_KERNEL_V1_CUH_
 
@@ -121,7 +125,6 @@ struct KernelParamsV1 {
 	int32_t* queue;
 	int32_t n_utt;
 	int32_t debug_skip;           // experiments only (GTTS_DEBUG_SKIP): bit0 no SRC, bit1 no coef task, bit2 no helper, bit3 no chain A, bit4 no chain B, bit5 no tube
-	long long* prof_sections;     // optional [grid][6]: helper warp 4's cycles per section
 	long long* prof;              // optional [grid][kWarps + 1]: busy cycles per warp + iteration count (GTTS_PROFILE=1)
 };
 
@@ -853,7 +856,9 @@ GTTS_DEV void chain_b_iteration(CtaSm* C, const KernelParamsV1& P, int lane, Cha
 //  * the input of the cell is mP fromPrev + mL link + (mG last + input) with 0 / 1 / d masks (input = 0 off lane 0);
 //  * per-sample operands are prefetched four samples at a time, frication taps sit behind a warp-uniform branch.
 // Lanes of slots without a block at this stage run on dummy data: their state is reset when their block 0 arrives.
-GTTS_DEV void tube_iteration(CtaSm* C, const KernelParamsV1& P, int warp, int lane, TubeLane& t, int p)
+struct TubeCell { double T, Bn, nb, last; };      // state of a tube lane between blocks (see tube_iteration)
+
+GTTS_DEV void tube_iteration(CtaSm* C, const KernelParamsV1& P, int warp, int lane, TubeCell& t, int p)
 {
 	(void) P;
 	// lane = 2 u + s: cell u of the warp's slot s.  The two slots are interleaved so that the few lanes that load
@@ -870,7 +875,7 @@ GTTS_DEV void tube_iteration(CtaSm* C, const KernelParamsV1& P, int warp, int la
 	const int buf = b & 1, b3 = (b % 3 + 3) % 3;
 	const bool fricBlock = __any_sync(0xffffffffu, hasBlock && S->fric[buf] != 0);
 	const VoiceDev& V = S->V;
-	if (b == 0) { t.aT = t.aB = t.bT = t.bB = t.extra = t.nb0 = t.y1 = 0.0; }
+	if (b == 0) { t.T = t.Bn = t.nb = t.last = 0.0; }
 	const double d = V.damping;
 	const bool is3 = u == 3, isEnd = (u == 9) || (u == 15);
 	const bool storesEnd = isEnd && slot < kSlots;     // the second group of the last warp is a dummy: it must not store
@@ -889,7 +894,7 @@ GTTS_DEV void tube_iteration(CtaSm* C, const KernelParamsV1& P, int warp, int la
 	const int srcPrev = 2 * ((u + 15) & 15) + sbit, srcNext = 2 * ((u + 1) & 15) + sbit, srcLink = 2 * (is3 ? 10 : 3) + sbit;
 	// T = forward wave into the cell, Bn = backward wave from the next cell, nb = wave on the velum link,
 	// last = the cell's own backward output of the previous sample (glottis reflection, end-filter state)
-	double T = t.aT, Bn = t.aB, nb = t.nb0, last = t.extra;
+	double T = t.T, Bn = t.Bn, nb = t.nb, last = t.last;
 	// alpha_u d (lane u = 3) and the glottal input (lane u = 0): zero on every other lane, loaded under predicate
 	double e3v[4] = {0.0, 0.0, 0.0, 0.0}, inv[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 1
@@ -936,7 +941,7 @@ GTTS_DEV void tube_iteration(CtaSm* C, const KernelParamsV1& P, int warp, int la
 			nb = link;
 		}
 	}
-	t.aT = T; t.aB = Bn; t.nb0 = nb; t.extra = last;
+	t.T = T; t.Bn = Bn; t.nb = nb; t.last = last;
 }
 
 // ---- slot bookkeeping for the NEXT iteration (chain A warp, lane = slot, after its chain work) ----------
@@ -1094,7 +1099,7 @@ GTTS_DEV void tube_v1_cta_body(const KernelParamsV1& P, unsigned char* smem, int
 	// Task t of an iteration goes to worker t mod 11: with 9-14 tasks nearly every worker has one.
 	const int skip = P.debug_skip;
 	if (warp < kTubeWarps) {
-		TubeLane tl = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+		TubeCell tl = {0.0, 0.0, 0.0, 0.0};
 		GTTS_ROLE_LOOP(if (!(skip & 32)) tube_iteration(C, P, warp, lane, tl, p);)
 	} else if (warp == kChainAWarp) {
 		ChainARegs ca = {0.0};

@@ -82,6 +82,16 @@ extern "C" int emu_batch_v1(const gtts_voice_config* voices, int n_voices, const
 	g_err = planBatch(voices, n_voices, voice_index, control_rate, steps_override,
 			reinterpret_cast<const int64_t*>(frame_offsets), n_utt, plan, &err);
 	if (err) return err;
+	// EMU_OUT_SHIFT=s (tests only): utterance u starts s + 7 u samples (mod 32) off its 32-sample row, which the
+	// planner never produces -- exercises the partial first row and the row phases of the SRC stage.
+	if (const char* sh = std::getenv("EMU_OUT_SHIFT")) {
+		const long long shift = std::atoll(sh);
+		for (long long u = 0; u < n_utt; ++u) {
+			plan.out_offsets[u] += 64 * u + ((7 * u + shift) & 31);
+			plan.utts[u].out_begin = plan.out_offsets[u];
+		}
+		plan.out_offsets[n_utt] += 64 * n_utt + 32;
+	}
 	for (long long u = 0; u <= n_utt; ++u) out_offsets[u] = plan.out_offsets[u];
 	for (long long u = 0; u < n_utt; ++u) out_lengths[u] = plan.utts[u].n_out;
 	if (!out) return 0;
@@ -112,7 +122,6 @@ extern "C" int emu_batch_v1(const gtts_voice_config* voices, int n_voices, const
 	P.queue = &queue;
 	P.n_utt = static_cast<int32_t>(n_utt);
 	P.prof = nullptr;
-	P.prof_sections = nullptr;
 	P.debug_skip = 0;
 
 	std::vector<unsigned char> smem(v1::smem_bytes() + 64);
