@@ -158,6 +158,9 @@ int launchBatch(gtts_batch* b, const float* dFrames, float* dOut, cudaStream_t s
 				}
 				iters += static_cast<double>(hp[static_cast<size_t>(c) * rowLen + v1::kWarps]);
 			}
+#ifndef GTTS_ROLE_PROFILE
+			std::fprintf(stderr, "[gtts profile] this build has no per-role counters: rebuild with -DGTTS_ROLE_PROFILE (tools/ab_build.sh)\n");
+#endif
 			std::fprintf(stderr, "[gtts profile] grid %d, iterations per CTA %.0f; busy cycles per iteration by warp:", grid, iters / grid);
 			for (int w = 0; w < v1::kWarps; ++w) std::fprintf(stderr, " %d:%.0f", w, sum[w] / (iters > 0 ? iters : 1));
 			std::fprintf(stderr, "\n[gtts profile] share of iterations in which the role reached the barrier last (%%):");

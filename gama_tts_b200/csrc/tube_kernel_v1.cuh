@@ -32,8 +32,11 @@
 #ifndef GTTS_COEF_UNROLL
 #define GTTS_COEF_UNROLL 9
 #endif
+#ifndef GTTS_CHAINA_CHUNK
+#define GTTS_CHAINA_CHUNK 4
+#endif
 #ifndef GTTS_CHAINB_CHUNK
-#define GTTS_CHAINB_CHUNK 8
+#define GTTS_CHAINB_CHUNK 4
 #endif
 
 namespace gtts {
@@ -94,9 +97,15 @@ struct SlotSm {
 		int it;                   // iteration counter of the current utterance; -1: idle
 		int nblocks;
 		int voice;
-		int pad;
+		int last_len;             // samples in the last block
+		// output rows of the block that is in the SRC stage this iteration (see src_rows), and the running
+		// count they are derived from: outputs_before(32 b') = ceil(32 b' 65536 / inc) for the next SRC block b',
+		// kept as quotient / remainder of (32 b' 65536 + inc - 1) / inc and advanced by (eQ, eR) per block
+		long long src_k0, src_k1;
+		long long eq;
+		unsigned erem, eQ, eR, inc;
 	} ctl[2];
-	int     pad_[25];              // slot stride = 16 mod 128 bytes: the 7 slots start in different banks
+	int     pad_[5];              // slot stride = 16 mod 128 bytes: the 7 slots start in different banks
 };
 static_assert(sizeof(SlotSm) % 128 == 16, "slot stride should be 16 mod 128 bytes (bank spreading); adjust pad_");
 
@@ -137,21 +146,9 @@ struct KernelParamsV1 {
 #define GTTS_CLOCK_AFTER(t, dep) ((t) = 0)
 #endif
 
-// ceil((n << 16) / inc): number of outputs whose right wing ends before input n (SampleRateConverter.h:
-// 295-361 as a closed form).  Double division plus an integer correction instead of a 64-bit divide.
-GTTS_DEV_NOINLINE long long outputs_before(long long n, unsigned inc)
-{
-	const unsigned long long num = (unsigned long long) n << 16;
-	long long q = (long long) ((double) num / (double) inc);
-	while ((unsigned long long) q * inc < num) ++q;
-	while (q > 0 && (unsigned long long) (q - 1) * inc >= num) --q;
-	return q;
-}
-
 GTTS_DEV int block_len(const SlotSm::Ctl& k, int b)
 {
-	const long long left = k.U.n_internal - (long long) b * kBlock;
-	return left < kBlock ? (int) left : kBlock;
+	return b == k.nblocks - 1 ? k.last_len : kBlock;
 }
 
 // ---- float32 walk of a group of parameters over one block (Controller.cpp:297-311) -----------------
@@ -548,30 +545,30 @@ GTTS_DEV void coef_task(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int lane, 
 }
 
 // ---- output rows of the SRC stage --------------------------------------------------------------------
-// Block b completes the outputs [outputs_before(32 b), outputs_before(32 (b + 1))).  The SRC tasks write
-// whole 128-byte rows instead: every block but the last stops at the last row boundary (an absolute
-// multiple of 32 samples in the output buffer) and leaves the remainder to the next block, whose window
-// still holds the inputs (the ring keeps 128: 57 back + 64 ahead being written).  Row-aligned 128-byte stores are what lets the kernel write
-// straight into pinned host memory at PCIe rate (52.7 GB/s measured against 30 GB/s for unaligned rows,
-// tools/microbench/zerocopy_store.cu); in device memory they halve the written sectors' partial writes.
-GTTS_DEV void src_range(const SlotSm::Ctl& K, int b, unsigned inc, long long& k0, long long& k1)
+// Block b completes the outputs [e(b), e(b + 1)), e(b) = ceil(32 b 65536 / inc) (closed form of
+// SampleRateConverter.h:295-361).  The SRC tasks write whole 128-byte rows instead: every block but the last
+// stops at the last row boundary (an absolute multiple of 32 samples in the output buffer) and leaves the
+// remainder to the next block, whose window still holds the inputs (the ring keeps 128: 57 back + 64 ahead
+// being written).  Row-aligned 128-byte stores are what lets the kernel write straight into pinned host memory
+// at PCIe rate (52.7 GB/s measured against 30 GB/s for unaligned rows, tools/microbench/zerocopy_store.cu).
+// The boundary between the last two blocks stays exact: the 26 flush zeros that chain B appends after the last
+// block would otherwise reach, around the ring, the oldest inputs of the deferred outputs.
+// Called by the scheduler lane of the slot for the block that enters the SRC stage; e0 = e(b), e1 = e(b + 1).
+GTTS_DEV void src_rows(SlotSm::Ctl& N, int b, long long e0, long long e1)
 {
-	const long long nStart = (long long) b * kBlock;
-	const long long nEnd = nStart + block_len(K, b);
-	const long long a = K.U.out_begin & 31;        // 0 with the planner's padded layout
-	// The boundary between the last two blocks stays exact: the 26 flush zeros that chain B appends after the
-	// last block would otherwise reach, around the 128-entry ring, the oldest inputs of the deferred outputs.
-	const long long e0 = outputs_before(nStart, inc);
-	k0 = (b == 0) ? 0 : (b == K.nblocks - 2 ? e0 : ((e0 + a) & ~31ll) - a);
-	if (b == K.nblocks - 1) {
-		k1 = K.U.n_out;                             // flush: chain B appended the 26 zeros
+	const long long a = N.U.out_begin & 31;        // 0 with the planner's padded layout
+	long long k0 = (b == 0) ? 0 : (b == N.nblocks - 2 ? e0 : ((e0 + a) & ~31ll) - a);
+	long long k1;
+	if (b == N.nblocks - 1) {
+		k1 = N.U.n_out;                             // flush: chain B appended the 26 zeros
 	} else {
-		const long long e1 = outputs_before(nEnd, inc);
-		k1 = (b == K.nblocks - 3) ? e1 : ((e1 + a) & ~31ll) - a;
-		if (k1 > K.U.n_out) k1 = K.U.n_out;
+		k1 = (b == N.nblocks - 3) ? e1 : ((e1 + a) & ~31ll) - a;
+		if (k1 > N.U.n_out) k1 = N.U.n_out;
 	}
 	if (k0 < 0) k0 = 0;
 	if (k1 < k0) k1 = k0;
+	N.src_k0 = k0;
+	N.src_k1 = k1;
 }
 
 // ---- pool task: sample-rate conversion of the outputs that block b = it - 6 completes ---------------
@@ -582,8 +579,7 @@ GTTS_DEV void src_task(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int lane, i
 	if (K.it < 0 || b < 0 || b >= K.nblocks) return;
 	const VoiceDev& V = S->V;
 	const unsigned inc = V.src_inc;
-	long long k0, k1;
-	src_range(K, b, inc, k0, k1);
+	const long long k0 = K.src_k0, k1 = K.src_k1;
 	// rows start on absolute multiples of 32 samples: lane = (out_begin + k) mod 32
 	const long long kRow0 = ((k0 + (K.U.out_begin & 31)) & ~31ll) - (K.U.out_begin & 31);
 	float* out = P.out + K.U.out_begin;
@@ -690,7 +686,7 @@ struct ChainA2Regs { BandpassState bp; };
 
 // chain A, lane = slot: oscillator phase of block it - 1 (WavetableGlottalSource.h:196-199, 265-272: two
 // half-sample increments per sample, wrap above 511).  42 dependent cycles per sample; the operands of a chunk
-// of 8 samples are loaded before it is stepped.
+// of samples are loaded before it is stepped.
 GTTS_DEV void chain_a_iteration(CtaSm* C, const KernelParamsV1& P, int lane, ChainARegs& r, int p)
 {
 	(void) P;
@@ -704,12 +700,12 @@ GTTS_DEV void chain_a_iteration(CtaSm* C, const KernelParamsV1& P, int lane, Cha
 	double* p1 = S->pos[buf1][1];
 	double pos = r.pos;
 #pragma unroll 1
-	for (int j0 = 0; j0 < kBlock; j0 += 8) {
-		double inc[8], o0[8], o1[8];
+	for (int j0 = 0; j0 < kBlock; j0 += GTTS_CHAINA_CHUNK) {
+		double inc[GTTS_CHAINA_CHUNK], o0[GTTS_CHAINA_CHUNK], o1[GTTS_CHAINA_CHUNK];
 #pragma unroll
-		for (int q = 0; q < 8; ++q) inc[q] = osc[j0 + q];
+		for (int q = 0; q < GTTS_CHAINA_CHUNK; ++q) inc[q] = osc[j0 + q];
 #pragma unroll
-		for (int q = 0; q < 8; ++q) {
+		for (int q = 0; q < GTTS_CHAINA_CHUNK; ++q) {
 			double s = pos + inc[q];
 			pos = (s > 511.0) ? s - 512.0 : s;
 			o0[q] = pos;
@@ -718,7 +714,7 @@ GTTS_DEV void chain_a_iteration(CtaSm* C, const KernelParamsV1& P, int lane, Cha
 			o1[q] = pos;
 		}
 #pragma unroll
-		for (int q = 0; q < 8; ++q) { p0[j0 + q] = o0[q]; p1[j0 + q] = o1[q]; }
+		for (int q = 0; q < GTTS_CHAINA_CHUNK; ++q) { p0[j0 + q] = o0[q]; p1[j0 + q] = o1[q]; }
 	}
 	r.pos = pos;
 }
@@ -963,7 +959,8 @@ GTTS_DEV void schedule_slots(CtaSm* C, const KernelParamsV1& P, int lane, int p,
 			if (it > K.nblocks - 1 + kStages) it = -1;          // every stage has seen every block
 		}
 		if (it >= 0) {
-			N.U = K.U; N.nblocks = K.nblocks; N.voice = K.voice; N.it = it;
+			N.U = K.U; N.nblocks = K.nblocks; N.voice = K.voice; N.it = it; N.last_len = K.last_len;
+			N.eq = K.eq; N.erem = K.erem; N.eQ = K.eQ; N.eR = K.eR; N.inc = K.inc;
 		} else {
 			N.it = -1; N.nblocks = 0; N.voice = first ? 0 : K.voice; N.U = K.U;
 			for (;;) {
@@ -979,14 +976,31 @@ GTTS_DEV void schedule_slots(CtaSm* C, const KernelParamsV1& P, int lane, int p,
 				N.U = U;
 				N.voice = U.voice;
 				N.nblocks = (int) ((U.n_internal + kBlock - 1) / kBlock);
+				N.last_len = (int) (U.n_internal - (long long) (N.nblocks - 1) * kBlock);
 				N.it = 0;
+				// output counter: e(0) = 0 = (0 + inc - 1) / inc, remainder inc - 1; one block adds 32 * 65536
+				const unsigned uinc = P.voices[U.voice].src_inc;
+				N.inc = uinc;
+				N.eQ = (unsigned) (kBlock << 16) / uinc;
+				N.eR = (unsigned) (kBlock << 16) % uinc;
+				N.eq = 0;
+				N.erem = uinc - 1;
 				it = 0;
 				break;
 			}
 		}
 		alive = it >= 0;
 		valid = it >= 0 && it - kStages >= 0 && it - kStages < N.nblocks;
-		if (valid) { nInternal = N.U.n_internal; inc = P.voices[N.voice].src_inc; phase = (int) (N.U.out_begin & 31); }
+		if (valid) {
+			nInternal = N.U.n_internal; inc = N.inc; phase = (int) (N.U.out_begin & 31);
+			// the block entering the SRC stage: advance the output counter by one block, derive its rows
+			const long long e0 = N.eq;
+			unsigned rem = N.erem + N.eR;
+			long long e1 = e0 + N.eQ;
+			if (rem >= inc) { rem -= inc; e1 += 1; }
+			N.eq = e1; N.erem = rem;
+			src_rows(N, it - kStages, e0, e1);
+		}
 	}
 	const unsigned any = __ballot_sync(0xffffffffu, alive);
 	// SRC stage alignment: all slots that have a block at it - 6 are at the same block of equally long
@@ -999,6 +1013,7 @@ GTTS_DEV void schedule_slots(CtaSm* C, const KernelParamsV1& P, int lane, int p,
 	const int phaseRef = __shfl_sync(0xffffffffu, phase, refLane, 32);
 	const int same = !valid || (it == itRef && nInternal == nRef && inc == incRef && phase == phaseRef);
 	const bool allSame = __ballot_sync(0xffffffffu, same) == 0xffffffffu;
+	__syncwarp();                                  // lane 0 reads what the reference slot's lane wrote into ctl[q]
 	if (lane == 0) {
 		CtaSm::Sched& D = C->sched[q];
 		D.live = any != 0;
@@ -1007,8 +1022,8 @@ GTTS_DEV void schedule_slots(CtaSm* C, const KernelParamsV1& P, int lane, int p,
 		D.src_tasks = kSlots;
 		if (D.src_shared) {
 			const SlotSm::Ctl& RK = C->slot[refLane].ctl[q];
-			long long k0, k1;
-			src_range(RK, RK.it - kStages, incRef, k0, k1);
+			long long k0 = RK.src_k0;
+			const long long k1 = RK.src_k1;
 			const long long a = RK.U.out_begin & 31;
 			D.src_k0w = k0;
 			k0 = ((k0 + a) & ~31ll) - a;
@@ -1037,6 +1052,7 @@ GTTS_DEV void run_task(CtaSm* C, const KernelParamsV1& P, int lane, int task, in
 // Every role runs its OWN iteration loop (one CTA barrier per iteration each), so that a warp keeps only
 // its own role's state in registers: ~80 registers per thread instead of 128, which is what lets 24 warps
 // share the register file.
+#ifdef GTTS_ROLE_PROFILE
 #define GTTS_ROLE_LOOP(BODY)                                                     \
 	{                                                                            \
 		int p = 0;                                                               \
@@ -1057,6 +1073,19 @@ GTTS_DEV void run_task(CtaSm* C, const KernelParamsV1& P, int lane, int task, in
 		}                                                                        \
 		role_profile(P, warp, lane, busy, iters, lastIn);                        \
 	}
+#else
+// Default build: no per-role cycle counters (they cost 2.7 % through the instruction cache alone).  Build with
+// -DGTTS_ROLE_PROFILE (tools/ab_build.sh NAME -DGTTS_ROLE_PROFILE) for GTTS_PROFILE=1 to report them.
+#define GTTS_ROLE_LOOP(BODY)                                                     \
+	{                                                                            \
+		int p = 0;                                                               \
+		while (C->sched[p].live) {                                               \
+			BODY                                                                 \
+			__syncthreads();                                                     \
+			p ^= 1;                                                              \
+		}                                                                        \
+	}
+#endif
 
 // GTTS_PROFILE=1: per CTA [0, kWarps) busy cycles of every role, [kWarps] iterations, then per role the number of
 // iterations in which it was among the last to reach the barrier (it waited less than 200 cycles there)
