@@ -30,7 +30,7 @@
 #define GTTS_FIR_UNROLL 4
 #endif
 #ifndef GTTS_COEF_UNROLL
-#define GTTS_COEF_UNROLL 9
+#define GTTS_COEF_UNROLL 1
 #endif
 #ifndef GTTS_CHAINA_CHUNK
 #define GTTS_CHAINA_CHUNK 4
