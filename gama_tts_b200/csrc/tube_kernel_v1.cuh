@@ -492,8 +492,13 @@ GTTS_DEV void coef_task(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int lane, 
 	}
 	if (reuse) {
 		if (lane < nb) {
+			// rows 6, 7 hold per-voice constants: written with blocks 0 and 1 (one per buffer), never again
 #pragma unroll
-			for (int r = 0; r < 8; ++r) S->kab[buf0][r][lane] = S->kab[buf0 ^ 1][r][kBlock - 1];
+			for (int r = 0; r < 6; ++r) S->kab[buf0][r][lane] = S->kab[buf0 ^ 1][r][kBlock - 1];
+			if (b < 2) {
+				S->kab[buf0][6][lane] = S->kab[buf0 ^ 1][6][kBlock - 1];
+				S->kab[buf0][7][lane] = S->kab[buf0 ^ 1][7][kBlock - 1];
+			}
 			S->au[buf0][lane] = S->au[buf0 ^ 1][kBlock - 1];
 			S->onepk7[b % 3][lane] = S->onepk7[(b + 2) % 3][kBlock - 1];
 		}
@@ -536,8 +541,11 @@ GTTS_DEV void coef_task(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int lane, 
 		S->kab[buf][1][lane].y = ((sum * r2_3) - 1.0) * dmp;   // alpha left == alpha right, stored as (alpha - 1) d (tube_iteration)
 		S->kab[buf][2][lane].y = 0.0;                          // S6-S7 is a pure damped delay: k = 0
 		S->kab[buf][5][lane].y = V.nasal_k[1] * dmp;
-		S->kab[buf][6][lane] = make_double2(V.nasal_k[2] * dmp, V.nasal_k[3] * dmp);
-		S->kab[buf][7][lane] = make_double2(V.nasal_k[4] * dmp, (V.nasal_k[5] * V.refl_b0_n) * dmp);   // nose end: b0 folded in
+		if (b < 2) {
+			// the fixed nasal junctions: the same in every block, so written once per buffer and utterance
+			S->kab[buf][6][lane] = make_double2(V.nasal_k[2] * dmp, V.nasal_k[3] * dmp);
+			S->kab[buf][7][lane] = make_double2(V.nasal_k[4] * dmp, (V.nasal_k[5] * V.refl_b0_n) * dmp);   // nose end: b0 folded in
+		}
 		S->au[buf][lane] = (sum * v2) * dmp;
 		S->onepk7[b % 3][lane] = 1.0 + k7;
 	}
