@@ -331,9 +331,17 @@ GTTS_DEV void helper_iteration(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int
 					a2 = h.c_a2; a1 = h.c_a1; b0 = h.c_b0;
 				} else {
 					const double pi = 3.14159265358979323846;
+#ifndef GTTS_EMU
+					// a2 = (1 - tan x) / (1 + tan x) = (cos x - sin x) / (cos x + sin x): one division
+					double sx, cx, sy, cv;
+					gtts_sincos(pi * (double) e6 * V.Ts, sx, cx);
+					gtts_sincos(2.0 * pi * (double) e5 * V.Ts, sy, cv);
+					a2 = div_fast(cx - sx, cx + sx);
+#else
 					const double tv = tan(pi * (double) e6 * V.Ts);
 					const double cv = cos(2.0 * pi * (double) e5 * V.Ts);
 					a2 = (1.0 - tv) / (1.0 + tv);
+#endif
 					a1 = -(1.0 + a2) * cv;
 					b0 = 0.5 - 0.5 * a2;
 				}
