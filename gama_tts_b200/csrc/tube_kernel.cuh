@@ -50,6 +50,15 @@ __device__ __forceinline__ double gtts_exp_core(double y)
 __device__ __forceinline__ double gtts_exp10(double x)
 {
 	const double magic = 6755399441055744.0;                     // 2^52 + 2^51: the sum's low word is rint(t)
+	// Integer x (40 dB, 20 dB: 10^-1, 10^-2) must give the correctly rounded power like the reference's pow():
+	// the amplitude feeds rint(amplitude * tnDelta) in the wavetable (WavetableGlottalSource.h:162-184), and
+	// 0.1 * 15 is a tie that one ulp decides.  Rare, so a branch: exact 10^|x| (|x| <= 22), then one division.
+	const double xi = (x + magic) - magic;
+	if (x == xi && fabs(x) <= 22.0) {
+		double p = 1.0;
+		for (int i = (int) fabs(x); i > 0; --i) p *= 10.0;
+		return x < 0.0 ? 1.0 / p : p;
+	}
 	const double tt = fma(x, 3.321928094887362, magic);
 	const int n = __double2loint(tt);
 	const double nd = tt - magic;

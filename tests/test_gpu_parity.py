@@ -225,3 +225,35 @@ def test_device_exp2_exp10_match_libm(synth):
     ulp10 = np.abs(e10 - r10) / np.spacing(r10)
     assert ulp2.max() <= 2.0, ulp2.max()
     assert ulp10.max() <= 2.0, ulp10.max()
+    # integer arguments are exact cases of the reference's pow(): 10^-1 * tnDelta can be a tie of rint()
+    # (the amplitudes use x = (dB - 60) / 20 in (-3, 0]: 10^-1 and 10^-2 must be libm's values bit for bit;
+    # further out libm's own pow() is no longer correctly rounded -- 10^-5 -- and 1 ulp is all that is asked)
+    ints = np.arange(-15.0, 16.0)
+    e2, e10 = synth.probe_exp(ints)
+    assert np.array_equal(e2, np.exp2(ints))
+    near = np.abs(ints) <= 4
+    assert np.array_equal(e10[near], np.power(10.0, ints[near]))
+    assert (np.abs(e10 - np.power(10.0, ints)) <= np.spacing(np.power(10.0, ints))).all()
+
+
+@pytest.mark.slow
+def test_config3_shape_subsample_parity(synth, oracle):
+    # BASELINE config 3 in miniature: log-uniform lengths, every utterance its own random voice (own internal
+    # rate, control steps, SRC ratio, analytic wavetable), several waves through the 7 x 148 slots.  Parity on
+    # a random subsample and the longest utterances; size-independent properties on all of them.
+    rng = np.random.Generator(np.random.PCG64(7))
+    n = 2600
+    lengths = T.config3_lengths(n, seed=7, lo=25, hi=500)
+    voices = [random_voice(rng) for _ in range(n)]
+    seeds = [T.synthetic_track(3000 + i, 500) for i in range(16)]
+    tracks = [seeds[i % 16][: int(lengths[i])] for i in range(n)]
+    outs = synth.synthesize(voices, tracks, voice_index=np.arange(n))
+    for v, tr, out in zip(voices, tracks, outs):
+        assert len(out) == g.output_length(v, len(tr))[1]
+        assert np.isfinite(out).all()
+    check = sorted(set(rng.choice(n, 48, replace=False).tolist()) | set(np.argsort(lengths)[-4:].tolist()))
+    worst = 0.0
+    for i in check:
+        ref = oracle.synthesize(voices[i], tracks[i])
+        worst = max(worst, full_scale_error(outs[i], ref))
+    assert worst <= TIGHT, worst
