@@ -693,10 +693,9 @@ GTTS_DEV void src_shared_task(CtaSm* C, const KernelParamsV1& P, int lane, int p
 	}
 }
 
-// ---- chain A (warp 2, lane = slot): oscillator phase (block it-1), frication bandpass (block it-3) ------
-// Both recurrences are stepped in one loop so that their latencies overlap; the operands of step j+1
-// are loaded while step j computes.  Lanes whose slot has no such block run on dummy data (their
-// results are never read), which keeps the loop free of divergent branches.
+// ---- chain A / chain A2 (one warp each, lane = slot): the two serial recurrences ahead of the tube -------------
+// Lanes whose slot has no such block run on dummy data (their results are never read), which keeps the loops
+// free of divergent branches.
 struct ChainARegs { double pos; };
 struct ChainA2Regs { BandpassState bp; };
 
