@@ -47,18 +47,21 @@ __device__ __forceinline__ double gtts_exp_core(double y)
 	p = fma(p, y, 1.0);
 	return p;
 }
+// 10^x for integer x, |x| <= 22: exact 10^|x|, then one IEEE division (out of line: rare)
+__device__ __noinline__ double gtts_exp10_int(double x)
+{
+	double p = 1.0;
+	for (int i = (int) fabs(x); i > 0; --i) p *= 10.0;
+	return x < 0.0 ? 1.0 / p : p;
+}
 __device__ __forceinline__ double gtts_exp10(double x)
 {
 	const double magic = 6755399441055744.0;                     // 2^52 + 2^51: the sum's low word is rint(t)
 	// Integer x (40 dB, 20 dB: 10^-1, 10^-2) must give the correctly rounded power like the reference's pow():
 	// the amplitude feeds rint(amplitude * tnDelta) in the wavetable (WavetableGlottalSource.h:162-184), and
-	// 0.1 * 15 is a tie that one ulp decides.  Rare, so a branch: exact 10^|x| (|x| <= 22), then one division.
+	// 0.1 * 15 is a tie that one ulp decides.
 	const double xi = (x + magic) - magic;
-	if (x == xi && fabs(x) <= 22.0) {
-		double p = 1.0;
-		for (int i = (int) fabs(x); i > 0; --i) p *= 10.0;
-		return x < 0.0 ? 1.0 / p : p;
-	}
+	if (x == xi && fabs(x) <= 22.0) return gtts_exp10_int(x);
 	const double tt = fma(x, 3.321928094887362, magic);
 	const int n = __double2loint(tt);
 	const double nd = tt - magic;

@@ -547,10 +547,10 @@ GTTS_DEV void coef_task(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int lane, 
 		}
 		const double sum = div_fast(2.0, r2_3 + r2_3 + v2);
 		S->kab[buf][1][lane].y = ((sum * r2_3) - 1.0) * dmp;   // alpha left == alpha right, stored as (alpha - 1) d (tube_iteration)
-		S->kab[buf][2][lane].y = 0.0;                          // S6-S7 is a pure damped delay: k = 0
-		S->kab[buf][5][lane].y = V.nasal_k[1] * dmp;
 		if (b < 2) {
-			// the fixed nasal junctions: the same in every block, so written once per buffer and utterance
+			// the fixed junctions: the same in every block, so written once per buffer and utterance
+			S->kab[buf][2][lane].y = 0.0;                      // S6-S7 is a pure damped delay: k = 0
+			S->kab[buf][5][lane].y = V.nasal_k[1] * dmp;
 			S->kab[buf][6][lane] = make_double2(V.nasal_k[2] * dmp, V.nasal_k[3] * dmp);
 			S->kab[buf][7][lane] = make_double2(V.nasal_k[4] * dmp, (V.nasal_k[5] * V.refl_b0_n) * dmp);   // nose end: b0 folded in
 		}
