@@ -257,3 +257,28 @@ def test_config3_shape_subsample_parity(synth, oracle):
         ref = oracle.synthesize(voices[i], tracks[i])
         worst = max(worst, full_scale_error(outs[i], ref))
     assert worst <= TIGHT, worst
+
+
+def test_sharded_over_gpus_equals_one_gpu(synth):
+    # BASELINE config 4: the batch partitioned by utterance over the GPUs of the box (no collective on the data
+    # path) gives, utterance by utterance, the bits of the one-GPU run.  Needs >= 2 GPUs.
+    import torch
+    from gama_tts_b200.sharding import shard_utterances, utterance_cost
+    n_gpu = torch.cuda.device_count()
+    if n_gpu < 2:
+        pytest.skip("one GPU on this box")
+    rng = np.random.Generator(np.random.PCG64(44))
+    n = 600
+    voices = [default_voice("male"), default_voice("female"), random_voice(rng)]
+    vidx = rng.integers(0, 3, n)
+    tracks = [T.synthetic_track(4400 + i, int(rng.integers(10, 200))) for i in range(n)]
+    whole = synth.synthesize(voices, tracks, voice_index=vidx)
+    cost = utterance_cost(voices, vidx, [len(t) for t in tracks])
+    shards = shard_utterances(cost, n_gpu)
+    assert sorted(np.concatenate(shards).tolist()) == list(range(n))
+    for r, idx in enumerate(shards):
+        dev = g.TubeSynthesizer(r)
+        part = dev.synthesize(voices, [tracks[i] for i in idx], voice_index=vidx[idx])
+        for i, out in zip(idx, part):
+            assert np.array_equal(out, whole[i]), (r, i)
+        dev.close()
