@@ -136,8 +136,12 @@ int gtts_batch_lengths(const gtts_batch* batch, int64_t* n_out);
 /* Runs the batch on DEVICE buffers, asynchronously on `cuda_stream` (a cudaStream_t, may be NULL):
  * d_frames float32 [n_frames_total][16], d_out float32 [out_offsets[n_utt]]. */
 int gtts_batch_run_device(gtts_batch* batch, const float* d_frames, float* d_out, void* cuda_stream);
-/* Same with HOST buffers: host->device copy of the frames, kernels, device->host copy of the audio,
- * synchronised on return.  Buffers may be pageable or pinned. */
+/* Same with HOST buffers, synchronised on return.  Pageable buffers are staged: host->device copy of the frames,
+ * kernel, device->host copy of the audio.  Pinned (page-locked, e.g. cudaHostAlloc) buffers are used in place: the
+ * kernel reads each frame over PCIe one control period ahead of its use and stores the audio straight into h_out
+ * in whole 128-byte rows while it computes, so the transfers overlap the synthesis (h_out should be 128-byte
+ * aligned, which pinned allocations are).  The samples between two utterances (see gtts_batch_layout) are not
+ * written. */
 int gtts_batch_run_host(gtts_batch* batch, const float* h_frames, float* h_out);
 /* Number of kernel launches the last run issued (for bench.py's gpu_launches claim). */
 int gtts_batch_last_launches(const gtts_batch* batch, int32_t* n_out);
