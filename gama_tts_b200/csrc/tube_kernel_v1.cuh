@@ -776,7 +776,7 @@ GTTS_DEV void chain_a2_iteration(CtaSm* C, const KernelParamsV1& P, int lane, Ch
 	r.bp.x1 = x1; r.bp.x2 = x2; r.bp.y1 = y1; r.bp.y2 = y2;
 }
 
-// ---- chain B (warp 3, lane = slot * 4 + filter): radiation filters + throat lowpass of block it - 5 ------
+// ---- chain B (one warp, lane = slot * 4 + filter): radiation filters + throat lowpass of block it - 5 ----
 // One code path for the three one-pole filters: y = b0 x + b1 x1 - a1 y1, out = y * gain
 //   f = 0 mouth radiation (b0 = A, b1 = a1 = -A, gain 1) on (1 + k7) T[S10]     (RadiationFilter.h:73-79)
 //   f = 1 nose radiation on (1 + nk5) NT[N6]
