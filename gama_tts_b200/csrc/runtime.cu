@@ -188,10 +188,11 @@ int uploadPlan(gtts_batch* b)
 	GTTS_CUDA(cudaMalloc(&b->d_utts, sizeof(UttDesc) * std::max<size_t>(p.utts.size(), 1)));
 	GTTS_CUDA(cudaMalloc(&b->d_order, sizeof(int32_t) * std::max<size_t>(p.order.size(), 1)));
 	GTTS_CUDA(cudaMalloc(&b->d_queue, sizeof(int32_t)));
-	// kernel choice: v1 (pipelined) needs control periods of at least one 32-sample block; the general
-	// v0 kernel takes everything else (and all streaming / resumed work).  GTTS_KERNEL=v0 forces v0.
+	// kernel choice: v1 (pipelined) needs control periods of at least one 32-sample block, or of exactly one
+	// sample (the plugin shim's mode: every internal sample has its own frame); the general v0 kernel takes
+	// everything else (and all streaming / resumed work).  GTTS_KERNEL=v0 forces v0.
 	b->use_v1 = true;
-	for (const UttDesc& d : p.utts) if (d.steps < kBlock) b->use_v1 = false;
+	for (const UttDesc& d : p.utts) if (d.steps < kBlock && d.steps != 1) b->use_v1 = false;
 	if (const char* env = std::getenv("GTTS_KERNEL")) { if (std::strcmp(env, "v0") == 0) b->use_v1 = false; }
 	if (b->use_v1) {
 		std::vector<double> tables(p.voices.size() * kTableLen);

@@ -151,6 +151,18 @@ GTTS_DEV int block_len(const SlotSm::Ctl& k, int b)
 	return b == k.nblocks - 1 ? k.last_len : kBlock;
 }
 
+// one parameter of nb consecutive frames -> the lane's row (zero-filled to the block), 16 bytes per store
+GTTS_DEV_NOINLINE void copy_frames(const float* src, int nb, float* out)
+{
+#pragma unroll 2
+	for (int j = 0; j < kBlock; j += 4) {
+		float v[4];
+#pragma unroll
+		for (int q = 0; q < 4; ++q) v[q] = (j + q < nb) ? src[(long long) (j + q) * kNumParams] : 0.f;
+		reinterpret_cast<float4*>(out)[j >> 2] = make_float4(v[0], v[1], v[2], v[3]);
+	}
+}
+
 // ---- float32 walk of a group of parameters over one block (Controller.cpp:297-311) -----------------
 // lane k walks parameter base + k: cur/delta/off/frame are the lane's cursor (registers or shared),
 // out[j] (the lane's own row of kParamRow floats, 16-byte aligned) receives the value used for sample j.  Control periods are >= one block, so at most one
@@ -165,6 +177,16 @@ GTTS_DEV void walk_block(const float* frames, long long nFrames, int steps, floa
 	// (or exactly at the end of) this block iff off + first == steps.  At step `first` the walk restarts
 	// from the next frame value (the reference restarts from the frame value, not from the accumulated
 	// one: Controller.cpp:297-300).
+	if (steps == 1) {
+		// one frame per internal sample (the plugin shim records the reference's per-sample parameters:
+		// Controller.cpp:303-311 runs one step on cur = frame[i]): the values ARE the frames, no walk.
+		// `frame` counts the samples consumed so far.  Out of line: it must not sit in the hot instruction stream.
+		if (active) {
+			copy_frames(frames + (long long) frame * kNumParams + param, nb, out);
+			frame += nb;
+		}
+		return;
+	}
 	const int first = (steps - off) < nb ? (steps - off) : nb;
 	const bool reaches = active && (off + first == steps);
 	const int restart = reaches ? first : -1;

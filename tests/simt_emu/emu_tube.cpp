@@ -96,7 +96,7 @@ extern "C" int emu_batch_v1(const gtts_voice_config* voices, int n_voices, const
 	for (long long u = 0; u < n_utt; ++u) out_lengths[u] = plan.utts[u].n_out;
 	if (!out) return 0;
 	for (const UttDesc& d : plan.utts) {
-		if (d.steps < kBlock) { g_err = "v1 needs control periods of at least one block"; return GTTS_ERR_UNSUPPORTED; }
+		if (d.steps < kBlock && d.steps != 1) { g_err = "v1 needs control periods of at least one block (or of one sample)"; return GTTS_ERR_UNSUPPORTED; }
 	}
 	std::vector<double> taps = designGlottalFir();
 	std::memset(c_fir, 0, sizeof c_fir);

@@ -74,13 +74,15 @@ def emu_v1():
     L.emu_batch_v1.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
                                C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
 
-    def run(voices, vidx, tracks, ctas=1, rate=250.0):
+    def run(voices, vidx, tracks, ctas=1, rate=250.0, steps=None):
         va = voice_array(voices)
         frames, fo = pack_tracks(tracks)
         vi = np.ascontiguousarray(vidx, np.int32)
+        so = None if steps is None else np.ascontiguousarray(steps, np.int32)
         oo = np.zeros(len(tracks) + 1, np.int64)
         ol = np.zeros(len(tracks) + 1, np.int64)
-        args = [va, len(voices), vi.ctypes.data, rate, None, frames.ctypes.data, fo.ctypes.data, len(tracks)]
+        args = [va, len(voices), vi.ctypes.data, rate, None if so is None else so.ctypes.data, frames.ctypes.data,
+                fo.ctypes.data, len(tracks)]
         assert L.emu_batch_v1(*args, None, oo.ctypes.data, ol.ctypes.data, ctas) == 0, L.emu_last_error()
         out = np.full(int(oo[-1]), np.nan, np.float32)
         assert L.emu_batch_v1(*args, out.ctypes.data, oo.ctypes.data, ol.ctypes.data, ctas) == 0, L.emu_last_error()
@@ -132,3 +134,15 @@ def test_emulated_pipelined_kernel_unaligned_output(emu_v1, oracle, monkeypatch)
         monkeypatch.setenv("EMU_OUT_SHIFT", shift)
         for out, ref in zip(emu_v1([v], [0] * len(tracks), tracks), refs):
             assert np.array_equal(out, ref)
+
+
+def test_emulated_pipelined_kernel_per_sample_mode(emu_v1, oracle, real_tracks):
+    # steps = 1 (what the plugin shim records: the reference's parameters of every internal sample) runs on the
+    # pipelined kernel too: the "walk" is a copy of the frames.  Lengths that are not multiples of the block.
+    v = default_voice("male")
+    hello = real_tracks[0]
+    params = [np.repeat(hello[40:44], 80, axis=0)[:300], np.repeat(hello[100:102], 80, axis=0)[:95],
+              T.synthetic_track(5, 33), hello[:1]]
+    outs = emu_v1([v], [0] * len(params), params, steps=[1] * len(params))
+    for p, out in zip(params, outs):
+        assert np.array_equal(out, oracle.synthesize_samples(v, p))
