@@ -30,6 +30,8 @@
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <map>
+#include <mutex>
 #include <vector>
 
 #include "ConfigurationData.h"
@@ -54,8 +56,10 @@ public:
 	std::vector<float>& outputBuffer() noexcept override { return outputBuffer_; }
 
 private:
+	static gtts_handle* sharedHandle(int device);
+
 	gtts_voice_config voice_;
-	gtts_handle* handle_ = nullptr;
+	gtts_handle* handle_ = nullptr;       // process-wide, not owned
 	int32_t internalRate_ = 0;
 	float current_[GTTS_NUM_PARAMS];
 	std::vector<float> recorded_;          // one row of 16 per execSynthesisStep()
@@ -92,14 +96,27 @@ B200VocalTractModel::B200VocalTractModel(const GS::ConfigurationData& data, int 
 	if (gtts_voice_internal_rate(&voice_, &internalRate_) != GTTS_OK) throw std::runtime_error(gtts_last_error());
 	int64_t nInternal = 0, nOut = 0;
 	if (gtts_output_length(&voice_, 1, 0, &nInternal, &nOut) != GTTS_OK) throw std::runtime_error(gtts_last_error());
-	if (gtts_create(device, &handle_) != GTTS_OK) throw std::runtime_error(gtts_last_error());
+	handle_ = sharedHandle(device);
 	outputBuffer_.reserve(OUTPUT_BUFFER_RESERVE);
 }
 
-B200VocalTractModel::~B200VocalTractModel() noexcept
+// The host constructs one model per synthesis and dlcloses the plugin after it (VocalTractModelPlugin.cpp:95-98).
+// The device handle (CUDA context, tables, loaded kernels: ~0.4 s to set up) is therefore kept for the life of
+// the process -- one per device -- and the libraries are linked -z nodelete so that it survives the dlclose.
+gtts_handle* B200VocalTractModel::sharedHandle(int device)
 {
-	gtts_destroy(handle_);
+	static std::mutex lock;
+	static std::map<int, gtts_handle*> handles;
+	std::lock_guard<std::mutex> g(lock);
+	auto it = handles.find(device);
+	if (it != handles.end()) return it->second;
+	gtts_handle* h = nullptr;
+	if (gtts_create(device, &h) != GTTS_OK) throw std::runtime_error(gtts_last_error());
+	handles[device] = h;
+	return h;
 }
+
+B200VocalTractModel::~B200VocalTractModel() noexcept = default;
 
 // VocalTractModel0::reset (VocalTractModel0.h:309-326): all dynamic state back to zero, output cleared;
 // like the reference, the current parameters are kept.
