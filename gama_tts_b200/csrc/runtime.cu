@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <limits>
 #include <new>
 #include <string>
@@ -416,11 +417,20 @@ int gtts_batch_prepare(gtts_handle* h, const gtts_voice_config* voices, int32_t 
 	gtts_batch* b = new (std::nothrow) gtts_batch;
 	if (!b) return fail(GTTS_ERR_NOMEM, "out of memory");
 	b->h = h;
-	int err = GTTS_OK;
-	const std::string msg = planBatch(voices, n_voices, voice_index, control_rate, steps_override, frame_offsets, n_utt, b->plan, &err);
-	if (err != GTTS_OK) { delete b; return fail(err, msg); }
-	const int rc = uploadPlan(b);
-	if (rc != GTTS_OK) { gtts_batch_free(b); return rc; }
+	// no exception may cross the C ABI: host-side allocation failures become GTTS_ERR_NOMEM
+	try {
+		int err = GTTS_OK;
+		const std::string msg = planBatch(voices, n_voices, voice_index, control_rate, steps_override, frame_offsets, n_utt, b->plan, &err);
+		if (err != GTTS_OK) { delete b; return fail(err, msg); }
+		const int rc = uploadPlan(b);
+		if (rc != GTTS_OK) { gtts_batch_free(b); return rc; }
+	} catch (const std::bad_alloc&) {
+		gtts_batch_free(b);
+		return fail(GTTS_ERR_NOMEM, "out of host memory while planning the batch");
+	} catch (const std::exception& e) {
+		gtts_batch_free(b);
+		return fail(GTTS_ERR_INVALID, e.what());
+	}
 	*batch_out = b;
 	return GTTS_OK;
 }
