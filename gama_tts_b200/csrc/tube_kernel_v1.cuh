@@ -1144,14 +1144,27 @@ GTTS_DEV void tube_v1_cta_body(const KernelParamsV1& P, unsigned char* smem, int
 {
 	CtaSm* C = reinterpret_cast<CtaSm*>(smem);
 	const int lane = tid & 31;
-#ifndef GTTS_CHAIN_A_HW
-#define GTTS_CHAIN_A_HW 23
+	// Hardware warp w runs on SM sub-partition w % 4 and the roles slow each other down through its issue slots
+	// and FP64 pipe, so which role runs where matters by a few percent (measured with tools/ab_build.sh
+	// -DGTTS_ROLE_PRESET=n): chain A (role 4) trades places with the lightest worker (role 23, the third SRC row).
+#ifndef GTTS_ROLE_PRESET
+#define GTTS_ROLE_PRESET 0
 #endif
-	// Hardware warp w runs on SM sub-partition w % 4 and the roles slow each other down through its issue
-	// slots and FP64 pipe: chain A trades places with another role so that the sub-partitions are evenly loaded
-	// (measured: chain A on the sub-partition of the idle worker +2.4 %).
+#if GTTS_ROLE_PRESET == 0
+#define GTTS_ROLE_TABLE 0, 1, 2, 3, 23, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 4
+#elif GTTS_ROLE_PRESET == 1      // chain B next to tube 0, the light worker next to tube 1
+#define GTTS_ROLE_TABLE 0, 1, 2, 3, 5, 23, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 4
+#elif GTTS_ROLE_PRESET == 2      // a helper of sub-partition 1 trades places with a coefficient worker of sub-partition 2
+#define GTTS_ROLE_TABLE 0, 1, 2, 3, 23, 5, 6, 7, 8, 9, 10, 11, 12, 18, 14, 15, 16, 17, 13, 19, 20, 21, 22, 4
+#else                            // both
+#define GTTS_ROLE_TABLE 0, 1, 2, 3, 5, 23, 6, 7, 8, 9, 10, 11, 12, 18, 14, 15, 16, 17, 13, 19, 20, 21, 22, 4
+#endif
 	const int hw = tid >> 5;
-	const int warp = hw == kChainAWarp ? GTTS_CHAIN_A_HW : (hw == GTTS_CHAIN_A_HW ? kChainAWarp : hw);
+	int warp;
+	{
+		constexpr int roleOfHw[kWarps] = {GTTS_ROLE_TABLE};
+		warp = roleOfHw[hw];
+	}
 	for (int i = tid; i < kSrcFilterLen; i += kThreads) C->tab[i] = P.src_tab[i];
 	if (tid < kSlots) {
 		for (int b = 0; b < 2; ++b) { C->slot[tid].ctl[b].it = -1; C->slot[tid].ctl[b].voice = 0; C->slot[tid].ctl[b].nblocks = 0; }
