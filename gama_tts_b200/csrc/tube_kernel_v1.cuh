@@ -1148,7 +1148,7 @@ GTTS_DEV void tube_v1_cta_body(const KernelParamsV1& P, unsigned char* smem, int
 	// and FP64 pipe, so which role runs where matters by a few percent (measured with tools/ab_build.sh
 	// -DGTTS_ROLE_PRESET=n): chain A (role 4) trades places with the lightest worker (role 23, the third SRC row).
 #ifndef GTTS_ROLE_PRESET
-#define GTTS_ROLE_PRESET 0
+#define GTTS_ROLE_PRESET 1      // measured: 0: 2.132 ms, 1: 2.111 ms, 2: 2.128 ms, 3: 2.119 ms (profile_run 1036 x 200)
 #endif
 #if GTTS_ROLE_PRESET == 0
 #define GTTS_ROLE_TABLE 0, 1, 2, 3, 23, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 4
