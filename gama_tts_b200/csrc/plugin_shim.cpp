@@ -28,6 +28,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <stdexcept>
 #include <string>
 #include <map>
@@ -64,7 +65,12 @@ private:
 	float current_[GTTS_NUM_PARAMS];
 	std::vector<float> recorded_;          // one row of 16 per execSynthesisStep()
 	std::vector<float> outputBuffer_;
+	bool failed_ = false;                  // recording abandoned: nothing more is recorded until finishSynthesis() / reset()
+
+	void fail(const char* what) noexcept;
 };
+
+int g_lastStatus = GTTS_OK;                // status of the last finishSynthesis() in this process (GTTS_plugin_last_status)
 
 // Same keys, same order as VocalTractModel0::loadConfiguration (VocalTractModel0.h:266-305).
 B200VocalTractModel::B200VocalTractModel(const GS::ConfigurationData& data, int device)
@@ -124,6 +130,24 @@ void B200VocalTractModel::reset() noexcept
 {
 	recorded_.clear();
 	outputBuffer_.clear();
+	failed_ = false;
+}
+
+// The VocalTractModel interface has no error channel (all eight virtuals are noexcept void, VocalTractModel.h:43-71)
+// and the host would write a silent, empty WAV with exit code 0 from an empty outputBuffer() (Controller.cpp:315-328).
+// A failed synthesis therefore ends the process the way an exception escaping a noexcept function of the reference
+// would: message on stderr, std::terminate().  Hosts that must survive (a speech server) set
+// GTTS_PLUGIN_ON_ERROR=continue: the output stays empty, the recording is dropped, further steps are ignored until
+// reset(), and GTTS_plugin_last_status() reports the error code.
+void B200VocalTractModel::fail(const char* what) noexcept
+{
+	std::fprintf(stderr, "[gtts_plugin] synthesis failed: %s\n", what);
+	recorded_.clear();
+	outputBuffer_.clear();
+	failed_ = true;
+	if (g_lastStatus == GTTS_OK) g_lastStatus = GTTS_ERR_CUDA;
+	const char* mode = std::getenv("GTTS_PLUGIN_ON_ERROR");
+	if (!(mode && std::strcmp(mode, "continue") == 0)) std::terminate();
 }
 
 // VocalTractModel0.h:665-694: an invalid index is ignored silently.  The radius scaling
@@ -143,40 +167,49 @@ void B200VocalTractModel::setAllParameters(const std::vector<float>& parameters)
 
 void B200VocalTractModel::execSynthesisStep() noexcept
 {
+	if (failed_) return;
 	try {
 		recorded_.insert(recorded_.end(), current_, current_ + GTTS_NUM_PARAMS);
 	} catch (...) {
-		std::fprintf(stderr, "[gtts_plugin] out of memory while recording parameters\n");
+		g_lastStatus = GTTS_ERR_NOMEM;
+		fail("out of memory while recording parameters");
 	}
 }
 
 // VocalTractModel0.h:720-723 (SRC flush) -- here: the deferred synthesis of everything recorded.
 void B200VocalTractModel::finishSynthesis() noexcept
 {
+	if (failed_) {
+		// the recording of this utterance was abandoned (GTTS_PLUGIN_ON_ERROR=continue): nothing to synthesise; the
+		// host does not call reset() on an empty output (Controller.cpp:231), so the next utterance starts here
+		failed_ = false;
+		return;
+	}
+	g_lastStatus = GTTS_OK;
+	gtts_batch* batch = nullptr;
 	try {
 		const int64_t nSamples = static_cast<int64_t>(recorded_.size() / GTTS_NUM_PARAMS);
 		const int64_t frameOffsets[2] = {0, nSamples};
 		const int32_t steps[1] = {1};
-		gtts_batch* batch = nullptr;
-		if (gtts_batch_prepare(handle_, &voice_, 1, nullptr, 250.0, steps, frameOffsets, 1, &batch) != GTTS_OK) {
-			std::fprintf(stderr, "[gtts_plugin] %s\n", gtts_last_error());
-			return;
-		}
+		int rc = gtts_batch_prepare(handle_, &voice_, 1, nullptr, 250.0, steps, frameOffsets, 1, &batch);
+		if (rc != GTTS_OK) { g_lastStatus = rc; fail(gtts_last_error()); failed_ = false; return; }
 		int64_t outOffsets[2] = {0, 0};
 		int64_t nOut = 0;
 		gtts_batch_layout(batch, outOffsets, nullptr);
 		gtts_batch_lengths(batch, &nOut);
 		const size_t base = outputBuffer_.size();
 		outputBuffer_.resize(base + static_cast<size_t>(outOffsets[1]));     // the layout is padded to whole rows
-		if (gtts_batch_run_host(batch, recorded_.data(), outputBuffer_.data() + base) != GTTS_OK) {
-			std::fprintf(stderr, "[gtts_plugin] %s\n", gtts_last_error());
-			nOut = 0;
-		}
-		outputBuffer_.resize(base + static_cast<size_t>(nOut));
+		rc = gtts_batch_run_host(batch, recorded_.data(), outputBuffer_.data() + base);
 		gtts_batch_free(batch);
+		batch = nullptr;
+		if (rc != GTTS_OK) { g_lastStatus = rc; fail(gtts_last_error()); failed_ = false; return; }
+		outputBuffer_.resize(base + static_cast<size_t>(nOut));
 		recorded_.clear();
 	} catch (...) {
-		std::fprintf(stderr, "[gtts_plugin] finishSynthesis failed\n");
+		if (batch) gtts_batch_free(batch);
+		g_lastStatus = GTTS_ERR_NOMEM;
+		fail("out of memory in finishSynthesis");
+		failed_ = false;
 	}
 }
 
@@ -209,5 +242,9 @@ void GAMA_TTS_destruct_vocal_tract_model(void* vtm)
 {
 	delete static_cast<GS::VTM::VocalTractModel*>(vtm);
 }
+
+// Not looked up by the reference: GTTS_OK or the GTTS_ERR_* code of the last finishSynthesis() in this process, for
+// hosts that run with GTTS_PLUGIN_ON_ERROR=continue.
+int GTTS_plugin_last_status(void) { return g_lastStatus; }
 
 } // extern "C"

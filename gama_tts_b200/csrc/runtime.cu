@@ -83,7 +83,8 @@ struct gtts_batch {
 	cudaStream_t stream = nullptr;      // used by run_host
 	int32_t last_launches = 0;
 	double* d_tables = nullptr;         // per-voice glottal wavetables (v1 kernel)
-	bool use_v1 = false;
+	bool streaming = false;             // one-utterance batch of a gtts_stream (set before the plan is uploaded)
+	int32_t n_fast = 0;                 // the first n_fast entries of the order list run on the pipelined kernel
 	const char* last_kernel = "none";
 };
 
@@ -106,18 +107,12 @@ int launchBatch(gtts_batch* b, const float* dFrames, float* dOut, cudaStream_t s
 	b->last_launches = 0;
 	if (nUtt == 0) return GTTS_OK;
 	GTTS_CUDA(cudaSetDevice(b->h->device));
-	GTTS_CUDA(cudaMemsetAsync(b->d_queue, 0, sizeof(int32_t), stream));
-	KernelParams P;
-	P.voices = b->d_voices;
-	P.utts = b->d_utts;
-	P.order = b->d_order;
-	P.frames = dFrames;
-	P.out = dOut;
-	P.states = b->d_states;
-	P.src_tab = b->h->d_src_tab;
-	P.queue = b->d_queue;
-	P.n_utt = static_cast<int32_t>(nUtt);
-	if (b->use_v1 && b->d_states == nullptr) {
+	GTTS_CUDA(cudaMemsetAsync(b->d_queue, 0, 2 * sizeof(int32_t), stream));
+	// The processing order is [pipelined-kernel utterances | general-kernel utterances], each part longest first:
+	// one launch per non-empty part, each with its own work counter (uploadPlan).
+	const int32_t nFast = b->n_fast, nGeneral = static_cast<int32_t>(nUtt) - b->n_fast;
+	b->last_kernel = "none";
+	if (nFast > 0) {
 		// pipelined warp-specialised kernel: one persistent CTA per SM, 7 utterance slots each
 		v1::KernelParamsV1 Q;
 		Q.voices = b->d_voices;
@@ -128,28 +123,39 @@ int launchBatch(gtts_batch* b, const float* dFrames, float* dOut, cudaStream_t s
 		Q.out = dOut;
 		Q.src_tab = b->h->d_src_tab;
 		Q.queue = b->d_queue;
-		Q.n_utt = static_cast<int32_t>(nUtt);
+		Q.n_utt = nFast;
 		Q.prof = nullptr;
 		Q.debug_skip = 0;
-		if (const char* dbg = std::getenv("GTTS_DEBUG_SKIP")) Q.debug_skip = std::atoi(dbg);   // experiments only: wrong output
-		const int64_t ctasWanted = (nUtt + v1::kSlots - 1) / v1::kSlots;
+		const int64_t ctasWanted = (static_cast<int64_t>(nFast) + v1::kSlots - 1) / v1::kSlots;
 		const int grid = static_cast<int>(std::min<int64_t>(ctasWanted, b->h->sms));
+#ifdef GTTS_EXPERIMENTS
+		// development builds only (tools/ab_build.sh NAME -DGTTS_EXPERIMENTS): GTTS_DEBUG_SKIP=<bits> leaves pipeline
+		// roles out (wrong audio, for isolating a role under ncu); the shipped library has no such switch
+		if (const char* dbg = std::getenv("GTTS_DEBUG_SKIP")) Q.debug_skip = std::atoi(dbg);
+#endif
+#ifdef GTTS_ROLE_PROFILE
+		// development builds only: per-role busy cycles (GTTS_PROFILE=1)
 		const bool profile = std::getenv("GTTS_PROFILE") != nullptr;
 		long long* dProf = nullptr;
 		if (profile) {
 			GTTS_CUDA(cudaMalloc(&dProf, sizeof(long long) * grid * (2 * v1::kWarps + 1)));
-			GTTS_CUDA(cudaMemsetAsync(dProf, 0, sizeof(long long) * grid * (2 * v1::kWarps + 1), stream));
+			if (cudaMemsetAsync(dProf, 0, sizeof(long long) * grid * (2 * v1::kWarps + 1), stream) != cudaSuccess) {
+				cudaFree(dProf);
+				return failCuda(cudaGetLastError(), "profile buffer");
+			}
 			Q.prof = dProf;
 		}
+#endif
 		v1::tube_kernel_v1<<<grid, v1::kThreads, v1::smem_bytes(), stream>>>(Q);
 		GTTS_CUDA(cudaGetLastError());
+#ifdef GTTS_ROLE_PROFILE
 		if (profile) {
-			// debugging aid: busy cycles per warp role and iteration, averaged over the CTAs
 			const size_t rowLen = 2 * v1::kWarps + 1;
 			std::vector<long long> hp(static_cast<size_t>(grid) * rowLen);
-			GTTS_CUDA(cudaStreamSynchronize(stream));
-			GTTS_CUDA(cudaMemcpy(hp.data(), dProf, sizeof(long long) * hp.size(), cudaMemcpyDeviceToHost));
+			cudaError_t pe = cudaStreamSynchronize(stream);
+			if (pe == cudaSuccess) pe = cudaMemcpy(hp.data(), dProf, sizeof(long long) * hp.size(), cudaMemcpyDeviceToHost);
 			cudaFree(dProf);
+			if (pe != cudaSuccess) return failCuda(pe, "profile readback");
 			double sum[v1::kWarps] = {0}, last[v1::kWarps] = {0};
 			double iters = 0;
 			for (int c = 0; c < grid; ++c) {
@@ -159,53 +165,73 @@ int launchBatch(gtts_batch* b, const float* dFrames, float* dOut, cudaStream_t s
 				}
 				iters += static_cast<double>(hp[static_cast<size_t>(c) * rowLen + v1::kWarps]);
 			}
-#ifndef GTTS_ROLE_PROFILE
-			std::fprintf(stderr, "[gtts profile] this build has no per-role counters: rebuild with -DGTTS_ROLE_PROFILE (tools/ab_build.sh)\n");
-#endif
 			std::fprintf(stderr, "[gtts profile] grid %d, iterations per CTA %.0f; busy cycles per iteration by warp:", grid, iters / grid);
 			for (int w = 0; w < v1::kWarps; ++w) std::fprintf(stderr, " %d:%.0f", w, sum[w] / (iters > 0 ? iters : 1));
 			std::fprintf(stderr, "\n[gtts profile] share of iterations in which the role reached the barrier last (%%):");
 			for (int w = 0; w < v1::kWarps; ++w) std::fprintf(stderr, " %d:%.0f", w, 100.0 * last[w] / (iters > 0 ? iters : 1));
 			std::fprintf(stderr, "\n");
 		}
+#endif
 		b->last_kernel = "tube_kernel_v1";
-	} else {
-		const int64_t ctasWanted = (nUtt + kWarpsPerCta - 1) / kWarpsPerCta;
+		b->last_launches += 1;
+	}
+	if (nGeneral > 0) {
+		KernelParams P;
+		P.voices = b->d_voices;
+		P.utts = b->d_utts;
+		P.order = b->d_order + nFast;
+		P.frames = dFrames;
+		P.out = dOut;
+		P.states = b->d_states;
+		P.src_tab = b->h->d_src_tab;
+		P.queue = b->d_queue + 1;
+		P.n_utt = nGeneral;
+		const int64_t ctasWanted = (static_cast<int64_t>(nGeneral) + kWarpsPerCta - 1) / kWarpsPerCta;
 		const int grid = static_cast<int>(std::min<int64_t>(ctasWanted, b->h->sms));
 		const size_t smem = tube_smem_bytes(kWarpsPerCta);
 		tube_kernel_v0<kWarpsPerCta><<<grid, kWarpsPerCta * 32, smem, stream>>>(P);
 		GTTS_CUDA(cudaGetLastError());
-		b->last_kernel = "tube_kernel_v0";
+		b->last_kernel = nFast > 0 ? "tube_kernel_v1+tube_kernel_v0" : "tube_kernel_v0";
+		b->last_launches += 1;
 	}
-	b->last_launches = 1;
 	return GTTS_OK;
 }
 
 int uploadPlan(gtts_batch* b)
 {
-	const BatchPlan& p = b->plan;
+	BatchPlan& p = b->plan;
 	GTTS_CUDA(cudaSetDevice(b->h->device));
+	// Every upload of the plan goes through the batch's own stream and is synchronised before the call returns:
+	// the kernels run on that stream or on the caller's, neither of which is ordered against the legacy default
+	// stream a plain cudaMemcpy / cudaMemset would use.
+	if (!b->stream) GTTS_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
 	GTTS_CUDA(cudaMalloc(&b->d_voices, sizeof(VoiceDev) * std::max<size_t>(p.voices.size(), 1)));
 	GTTS_CUDA(cudaMalloc(&b->d_utts, sizeof(UttDesc) * std::max<size_t>(p.utts.size(), 1)));
 	GTTS_CUDA(cudaMalloc(&b->d_order, sizeof(int32_t) * std::max<size_t>(p.order.size(), 1)));
-	GTTS_CUDA(cudaMalloc(&b->d_queue, sizeof(int32_t)));
-	// kernel choice: v1 (pipelined) needs control periods of at least one 32-sample block, or of exactly one
-	// sample (the plugin shim's mode: every internal sample has its own frame); the general v0 kernel takes
-	// everything else (and all streaming / resumed work).  GTTS_KERNEL=v0 forces v0.
-	b->use_v1 = true;
-	for (const UttDesc& d : p.utts) if (d.steps < kBlock && d.steps != 1) b->use_v1 = false;
-	if (const char* env = std::getenv("GTTS_KERNEL")) { if (std::strcmp(env, "v0") == 0) b->use_v1 = false; }
-	if (b->use_v1) {
+	GTTS_CUDA(cudaMalloc(&b->d_queue, 2 * sizeof(int32_t)));
+	// Kernel choice per utterance: v1 (pipelined) needs control periods of at least one 32-sample block, or of
+	// exactly one sample (the plugin shim's mode: every internal sample has its own frame); the general v0 kernel
+	// takes everything else (and all streaming / resumed work).  The order list is partitioned accordingly, each
+	// part longest first (stable partition of the planner's order), so one odd utterance no longer moves the whole
+	// batch to the slow kernel.  GTTS_KERNEL=v0 forces v0 for all.
+	bool forceGeneral = b->streaming;     // resumed utterances (UttState) exist in the general kernel only
+	if (const char* env = std::getenv("GTTS_KERNEL")) forceGeneral = std::strcmp(env, "v0") == 0;
+	auto fast = [&](int32_t u) { const UttDesc& d = p.utts[u]; return !forceGeneral && (d.steps >= kBlock || d.steps == 1); };
+	const auto mid = std::stable_partition(p.order.begin(), p.order.end(), fast);
+	b->n_fast = static_cast<int32_t>(mid - p.order.begin());
+	if (b->n_fast > 0) {
 		std::vector<double> tables(p.voices.size() * kTableLen);
 		for (size_t v = 0; v < p.voices.size(); ++v) buildWavetable(p.voices[v], tables.data() + v * kTableLen);
 		GTTS_CUDA(cudaMalloc(&b->d_tables, sizeof(double) * std::max<size_t>(tables.size(), 1)));
-		GTTS_CUDA(cudaMemcpy(b->d_tables, tables.data(), sizeof(double) * tables.size(), cudaMemcpyHostToDevice));
+		GTTS_CUDA(cudaMemcpyAsync(b->d_tables, tables.data(), sizeof(double) * tables.size(), cudaMemcpyHostToDevice, b->stream));
+		GTTS_CUDA(cudaStreamSynchronize(b->stream));      // `tables` goes out of scope
 	}
-	GTTS_CUDA(cudaMemcpy(b->d_voices, p.voices.data(), sizeof(VoiceDev) * p.voices.size(), cudaMemcpyHostToDevice));
+	GTTS_CUDA(cudaMemcpyAsync(b->d_voices, p.voices.data(), sizeof(VoiceDev) * p.voices.size(), cudaMemcpyHostToDevice, b->stream));
 	if (!p.utts.empty()) {
-		GTTS_CUDA(cudaMemcpy(b->d_utts, p.utts.data(), sizeof(UttDesc) * p.utts.size(), cudaMemcpyHostToDevice));
-		GTTS_CUDA(cudaMemcpy(b->d_order, p.order.data(), sizeof(int32_t) * p.order.size(), cudaMemcpyHostToDevice));
+		GTTS_CUDA(cudaMemcpyAsync(b->d_utts, p.utts.data(), sizeof(UttDesc) * p.utts.size(), cudaMemcpyHostToDevice, b->stream));
+		GTTS_CUDA(cudaMemcpyAsync(b->d_order, p.order.data(), sizeof(int32_t) * p.order.size(), cudaMemcpyHostToDevice, b->stream));
 	}
+	GTTS_CUDA(cudaStreamSynchronize(b->stream));
 	return GTTS_OK;
 }
 
@@ -283,7 +309,22 @@ int gtts_probe_voice_constants(const gtts_voice_config* voice, double* out, int3
 	return GTTS_OK;
 }
 
+namespace { int createHandle(int32_t device, gtts_handle** handle_out); }
+
 int gtts_create(int32_t device, gtts_handle** handle_out)
+{
+	// no exception may cross the C ABI (std::vector / std::string allocations inside)
+	try {
+		return createHandle(device, handle_out);
+	} catch (const std::bad_alloc&) {
+		return fail(GTTS_ERR_NOMEM, "out of host memory in gtts_create");
+	} catch (const std::exception& e) {
+		return fail(GTTS_ERR_INVALID, e.what());
+	}
+}
+
+namespace {
+int createHandle(int32_t device, gtts_handle** handle_out)
 {
 	if (!handle_out) return fail(GTTS_ERR_INVALID, "null handle_out");
 	*handle_out = nullptr;
@@ -330,6 +371,9 @@ int gtts_create(int32_t device, gtts_handle** handle_out)
 		delete h;
 		return failCuda(ce, "gtts_create: device setup");
 	}
+	// the uploads above went through the legacy default stream from pageable memory: wait for them, the kernels
+	// run on non-blocking streams that are not ordered against it
+	if ((ce = cudaDeviceSynchronize()) != cudaSuccess) { cudaFree(h->d_src_tab); delete h; return failCuda(ce, "gtts_create: device setup"); }
 	char buf[1024];
 	std::snprintf(buf, sizeof buf,
 			"{\"device\": %d, \"name\": \"%s\", \"sm\": \"%d.%d\", \"sms\": %d, "
@@ -341,6 +385,7 @@ int gtts_create(int32_t device, gtts_handle** handle_out)
 	*handle_out = h;
 	return GTTS_OK;
 }
+} // namespace
 
 void gtts_destroy(gtts_handle* h)
 {
@@ -407,9 +452,10 @@ int gtts_probe_fp64_peak(gtts_handle* h, double* tflops_out)
 	return GTTS_OK;
 }
 
-int gtts_batch_prepare(gtts_handle* h, const gtts_voice_config* voices, int32_t n_voices,
+namespace {
+int prepareBatch(gtts_handle* h, const gtts_voice_config* voices, int32_t n_voices,
 			const int32_t* voice_index, double control_rate, const int32_t* steps_override,
-			const int64_t* frame_offsets, int64_t n_utt, gtts_batch** batch_out)
+			const int64_t* frame_offsets, int64_t n_utt, bool streaming, gtts_batch** batch_out)
 {
 	if (!h || !batch_out) return fail(GTTS_ERR_INVALID, "null argument");
 	*batch_out = nullptr;
@@ -417,6 +463,7 @@ int gtts_batch_prepare(gtts_handle* h, const gtts_voice_config* voices, int32_t 
 	gtts_batch* b = new (std::nothrow) gtts_batch;
 	if (!b) return fail(GTTS_ERR_NOMEM, "out of memory");
 	b->h = h;
+	b->streaming = streaming;
 	// no exception may cross the C ABI: host-side allocation failures become GTTS_ERR_NOMEM
 	try {
 		int err = GTTS_OK;
@@ -433,6 +480,14 @@ int gtts_batch_prepare(gtts_handle* h, const gtts_voice_config* voices, int32_t 
 	}
 	*batch_out = b;
 	return GTTS_OK;
+}
+} // namespace
+
+int gtts_batch_prepare(gtts_handle* h, const gtts_voice_config* voices, int32_t n_voices,
+			const int32_t* voice_index, double control_rate, const int32_t* steps_override,
+			const int64_t* frame_offsets, int64_t n_utt, gtts_batch** batch_out)
+{
+	return prepareBatch(h, voices, n_voices, voice_index, control_rate, steps_override, frame_offsets, n_utt, false, batch_out);
 }
 
 int gtts_batch_layout(const gtts_batch* b, int64_t* out_offsets, int64_t* n_internal)
@@ -568,12 +623,13 @@ int gtts_stream_open(gtts_handle* h, const gtts_voice_config* voice, double cont
 	// a one-utterance batch whose descriptor is rewritten for every chunk
 	const int64_t fo[2] = {0, 0};
 	const int32_t so[1] = {steps_override};
-	int rc = gtts_batch_prepare(h, voice, 1, nullptr, control_rate, steps_override > 0 ? so : nullptr, fo, 1, &s->batch);
+	int rc = prepareBatch(h, voice, 1, nullptr, control_rate, steps_override > 0 ? so : nullptr, fo, 1, true, &s->batch);
 	if (rc != GTTS_OK) { delete s; return rc; }
 	s->vdev = s->batch->plan.voices[0];
 	s->steps = s->batch->plan.utts[0].steps;
+	// the state is cleared on the stream every chunk of this utterance runs on (stream-ordered before the first kernel)
 	cudaError_t e = cudaMalloc(&s->batch->d_states, sizeof(UttState));
-	if (e == cudaSuccess) e = cudaMemset(s->batch->d_states, 0, sizeof(UttState));
+	if (e == cudaSuccess) e = cudaMemsetAsync(s->batch->d_states, 0, sizeof(UttState), s->batch->stream);
 	if (e != cudaSuccess) { gtts_batch_free(s->batch); delete s; return failCuda(e, "gtts_stream_open"); }
 	*stream_out = s;
 	return GTTS_OK;
@@ -642,11 +698,19 @@ int gtts_stream_push_frames(gtts_stream* s, const float* frames, int64_t n_frame
 	if (s->finished) return fail(GTTS_ERR_INVALID, "stream already finished; call gtts_stream_reset");
 	if (n_written) *n_written = 0;
 	if (n_frames <= 0) return GTTS_OK;
-	s->pending.insert(s->pending.end(), frames, frames + n_frames * kNumParams);
+	// A failed push leaves the stream as it was (the frames are not queued), so the caller may retry, e.g. with a
+	// larger output buffer.
+	const size_t before = s->pending.size();
+	try {
+		s->pending.insert(s->pending.end(), frames, frames + n_frames * kNumParams);
+	} catch (const std::bad_alloc&) {
+		s->pending.resize(before);
+		return fail(GTTS_ERR_NOMEM, "out of host memory while queueing frames");
+	}
 	const int64_t have = static_cast<int64_t>(s->pending.size()) / kNumParams;
 	if (have < 2) return GTTS_OK;
 	const int rc = streamChunk(s, have - 1, true, false, out, out_capacity, n_written);
-	if (rc != GTTS_OK) return rc;
+	if (rc != GTTS_OK) { s->pending.resize(before); return rc; }
 	s->pending.erase(s->pending.begin(), s->pending.begin() + (have - 1) * kNumParams);
 	return GTTS_OK;
 }
@@ -668,7 +732,7 @@ int gtts_stream_reset(gtts_stream* s)
 {
 	if (!s) return fail(GTTS_ERR_INVALID, "null argument");
 	GTTS_CUDA(cudaSetDevice(s->h->device));
-	GTTS_CUDA(cudaMemset(s->batch->d_states, 0, sizeof(UttState)));
+	GTTS_CUDA(cudaMemsetAsync(s->batch->d_states, 0, sizeof(UttState), s->batch->stream));
 	s->pending.clear();
 	s->n_in_done = 0;
 	s->n_out_done = 0;

@@ -89,6 +89,7 @@ enum {
 	kSrcRing = 128,             // tube-output ring (doubles), power of two
 	kVRing = 64,                // 2x-oversampled oscillator stream rings (even / odd), power of two
 	kCurStride = 17,            // padded float row (16 parameters)
+	kNoLowMark = 1 << 30,       // wavetable rise segment intact (see stage_lookup)
 };
 
 // Rows of WarpSm::row -- one double per sample of the block.
@@ -330,36 +331,47 @@ GTTS_DEV void stage_phase(WarpSm* S, int lane, int nb, double& pos)
 // fall time does not depend on the amplitude) the fall segment; with tn_min != tn_max the fall
 // segment is a function of the current amplitude (WavetableGlottalSource.h:162-184) and is evaluated
 // analytically: 1 - ((i - div1) / (newDiv2 - div1))^2 below newDiv2, 0 up to div2.
-GTTS_DEV double table_at(const WarpSm* S, const VoiceDev& V, unsigned i, bool dynamic, double nd2, double inv)
+GTTS_DEV double table_at(const WarpSm* S, const VoiceDev& V, unsigned i, bool dynamic, double nd2, double inv, int low)
 {
 	if (dynamic && i >= (unsigned) V.div1 && i < (unsigned) V.div2) {
 		if (i >= (unsigned) nd2) return 0.0;
 		const double x = (double) (int) (i - V.div1) * inv;
 		return 1.0 - (x * x);
 	}
+	if ((int) i >= low && i < (unsigned) V.div1) return 0.0;      // rise segment zeroed by an earlier closure point below div1
 	return S->table[i];
 }
 
 // ---- stage: wavetable lookup of both half samples, lane = sample (:212-228) --------------------------
-GTTS_DEV void stage_lookup(WarpSm* S, const VoiceDev& V, int lane, int nb, long long n0)
+// `low`: the lowest closure point seen so far if one fell below div1 (glottal volume above 60 dB with
+// tn_min != tn_max: setup() then zeroes [newDiv2, div2), part of the rise segment, for good; :176-183).
+GTTS_DEV void stage_lookup(WarpSm* S, const VoiceDev& V, int lane, int nb, long long n0, int& low)
 {
-	if (lane < nb) {
-		const bool dynamic = (V.waveform == 0) && (V.tn_delta != 0.0);
-		double nd2 = 0.0, inv = 0.0;
-		if (dynamic) {
-			const double ax = S->row[R_AX][lane];
-			nd2 = (double) V.div2 - rint(ax * V.tn_delta);
-			nd2 = nd2 > 0.0 ? nd2 : 0.0;
-			inv = 1.0 / (nd2 - (double) V.div1);
+	const bool dynamic = (V.waveform == 0) && (V.tn_delta != 0.0);
+	double nd2 = 0.0, inv = 0.0;
+	int lowHere = low;
+	if (dynamic) {
+		const double ax = S->row[R_AX][lane < nb ? lane : 0];
+		nd2 = (double) V.div2 - rint(ax * V.tn_delta);
+		nd2 = nd2 > 0.0 ? nd2 : 0.0;
+		inv = 1.0 / (nd2 - (double) V.div1);
+		int mine = (lane < nb && nd2 < (double) V.div1) ? (int) nd2 : kNoLowMark;
+		for (int dlt = 1; dlt < 32; dlt <<= 1) {
+			const int o = __shfl_up_sync(0xffffffffu, mine, dlt, 32);
+			if (lane >= dlt) mine = mine < o ? mine : o;
 		}
+		lowHere = mine < low ? mine : low;
+		low = __shfl_sync(0xffffffffu, lowHere, 31, 32);
+	}
+	if (lane < nb) {
 		double v[2];
 #pragma unroll
 		for (int s = 0; s < 2; ++s) {
 			const double pos = S->row[s ? R_P1 : R_P0][lane];
 			const unsigned lo = __double2uint_rz(pos);
 			const unsigned up = (lo + 1 > 511u) ? lo + 1 - 512u : lo + 1;
-			const double tl = table_at(S, V, lo, dynamic, nd2, inv);
-			const double tu = table_at(S, V, up, dynamic, nd2, inv);
+			const double tl = table_at(S, V, lo, dynamic, nd2, inv, lowHere);
+			const double tu = table_at(S, V, up, dynamic, nd2, inv, lowHere);
 			v[s] = tl + ((pos - (double) lo) * (tu - tl));
 		}
 		const int slot = (int) ((n0 + lane) & (kVRing - 1));
@@ -639,6 +651,7 @@ GTTS_DEV void run_utterance(WarpSm* S, const double2* tab, const KernelParams& P
 	TubeLane tl = {0.0, 0.0, 0.0, 0.0, 0.0};
 	PostState ps = {0.0, 0.0};
 	long long nDone = 0, kDone = 0;
+	int tableLow = kNoLowMark;
 	const TubeRole role = tube_role(V, lane);
 	const int g = lane & 7;
 
@@ -651,6 +664,7 @@ GTTS_DEV void run_utterance(WarpSm* S, const double2* tab, const KernelParams& P
 		seed = st->seed; noiseX1 = st->noise_x1; pos = st->pos;
 		bp.x1 = st->bp_x1; bp.x2 = st->bp_x2; bp.y1 = st->bp_y1; bp.y2 = st->bp_y2;
 		nDone = st->n_in_done; kDone = st->n_out_done;
+		tableLow = st->table_low;
 		// waves: cell inputs from the section arrays
 		const double* ot = st->oral_t; const double* ob = st->oral_b;
 		const double* nt = st->nasal_t; const double* nbw = st->nasal_b;
@@ -696,7 +710,7 @@ GTTS_DEV void run_utterance(WarpSm* S, const double2* tab, const KernelParams& P
 			stage_convert(S, V, lane, nb);
 			const double lp = stage_noise(lane, nb, seed, noiseX1);
 			stage_phase(S, lane, nb, pos);
-			stage_lookup(S, V, lane, nb, nDone);
+			stage_lookup(S, V, lane, nb, nDone, tableLow);
 			stage_fir_mix(S, V, lane, nb, nDone, lp);
 			stage_bandpass(S, lane, nb, bp);
 			stage_tube(S, V, role, lane, nb, tl);
@@ -739,6 +753,7 @@ GTTS_DEV void run_utterance(WarpSm* S, const double2* tab, const KernelParams& P
 			st->seed = seed; st->noise_x1 = noiseX1; st->pos = pos;
 			st->bp_x1 = bp.x1; st->bp_x2 = bp.x2; st->bp_y1 = bp.y1; st->bp_y2 = bp.y2;
 			st->n_in_done = nDone; st->n_out_done = kDone; st->started = 1;
+			st->table_low = tableLow;
 		} else if (lane == 1) {
 			st->rad_x1_n = ps.x1; st->rad_y1_n = ps.y1;
 		} else if (lane == 2) {

@@ -75,7 +75,7 @@ struct UttState {
 	int64_t n_in_done;              // internal samples consumed so far
 	int64_t n_out_done;             // output samples produced so far
 	int32_t started;
-	int32_t pad_;
+	int32_t table_low;              // lowest wavetable closure point below div1 seen so far (1 << 30: none)
 };
 
 } // namespace gtts

@@ -148,8 +148,11 @@ int gtts_batch_last_launches(const gtts_batch* batch, int32_t* n_out);
 void gtts_batch_free(gtts_batch* batch);
 
 /* One-call convenience over prepare + run_host + free (what a C caller of the reference's
- * Controller::synthesize + outputBuffer() would use).  out must hold out_offsets[n_utt] samples as
- * given by gtts_output_length per utterance; out_offsets is filled if not NULL. */
+ * Controller::synthesize + outputBuffer() would use).  Utterance u is written at out[out_offsets[u]] with
+ * gtts_output_length() samples; every utterance starts on a multiple of 32 samples (see gtts_batch_layout), so
+ * out_capacity must be at least the sum over the utterances of their length rounded up to a multiple of 32 (the call
+ * fails with "output buffer too small" otherwise and still fills out_offsets, whose last entry is the size needed).
+ * out_offsets[n_utt + 1] is filled if not NULL. */
 int gtts_batch_synthesize(gtts_handle* handle, const gtts_voice_config* voices, int32_t n_voices,
 			const int32_t* voice_index, double control_rate, const float* frames,
 			const int64_t* frame_offsets, int64_t n_utt, float* out, int64_t out_capacity,

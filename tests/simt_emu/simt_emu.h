@@ -175,6 +175,12 @@ template<class T> inline T __shfl_sync(unsigned mask, T v, int src, int width = 
 	const int s = (lane & ~(width - 1)) | (src & (width - 1));
 	return simt::shfl<T>(mask, v, s);
 }
+template<class T> inline T __shfl_up_sync(unsigned mask, T v, unsigned delta, int width = 32)
+{
+	const int lane = simt::g_cta->cur & 31;
+	const int src = ((lane & (width - 1)) >= (int) delta) ? lane - (int) delta : lane;
+	return simt::shfl<T>(mask, v, src);
+}
 inline int atomicAdd(int* p, int v) { const int old = *p; *p += v; return old; }
 inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
 inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }

@@ -146,3 +146,25 @@ def test_emulated_pipelined_kernel_per_sample_mode(emu_v1, oracle, real_tracks):
     outs = emu_v1([v], [0] * len(params), params, steps=[1] * len(params))
     for p, out in zip(params, outs):
         assert np.array_equal(out, oracle.synthesize_samples(v, p))
+
+
+def _loud_track(n=40, seed=11):
+    # glottal volume ramps through 60 dB up to 78 dB and back: with tn_min != tn_max the closure point falls below
+    # the end of the rise segment and the reference zeroes part of it for good (WavetableGlottalSource.h:162-184)
+    tr = T.synthetic_track(seed, n).copy()
+    tr[:, 1] = np.concatenate([np.linspace(50, 78, n // 2), np.linspace(78, 40, n - n // 2)]).astype(np.float32)
+    return tr
+
+
+def test_emulated_kernels_reproduce_rise_segment_corruption(emu, emu_v1, oracle):
+    v = dict(default_voice("male"))
+    v["glottal_pulse_tn_min"], v["glottal_pulse_tn_max"] = 16.0, 32.0
+    tr = _loud_track()
+    ref = oracle.synthesize(v, tr)
+    quiet = tr.copy()
+    quiet[:, 1] = np.minimum(quiet[:, 1], 60.0)
+    assert full_scale_error(oracle.synthesize(v, quiet)[-2000:], ref[-2000:]) > 1e-3     # the corruption is audible and lasting
+    for run in (lambda: emu([v], [0], [tr], warps=1)[0], lambda: emu_v1([v], [0], [tr])[0]):
+        out = run()
+        assert len(out) == len(ref)
+        assert full_scale_error(out, ref) <= 1e-9
