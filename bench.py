@@ -224,7 +224,7 @@ def main():
     fo = np.arange(N_UTT + 1, dtype=np.int64) * N_FRAMES
     synth = g.TubeSynthesizer(local_rank)
     batch = synth.prepare(voice, fo)
-    n_out = batch.n_out_total                 # buffer size: every utterance starts on a 32-sample row
+    n_out = batch.n_out_total                 # buffer size: every utterance starts on a 64-sample row pair
     n_samples = batch.n_samples_total         # audio samples produced
     n_internal = int(batch.n_internal.sum())
     audio_seconds = n_samples / voice["output_rate"]

@@ -95,7 +95,7 @@ class Batch:
         self.n_out = np.zeros(max(self.n_utt, 1), np.int64)
         check(self._lib.gtts_batch_lengths(self._h, self.n_out.ctypes.data))
         self.n_out = self.n_out[:self.n_utt]
-        self.n_out_total = int(self.out_offsets[-1])     # size of the output buffer (utterances start on 32-sample rows)
+        self.n_out_total = int(self.out_offsets[-1])     # size of the output buffer (utterances start on 64-sample row pairs)
         self.n_samples_total = int(self.n_out.sum())     # audio samples produced
         self.n_frames_total = int(fo[-1]) if len(fo) else 0
 

@@ -46,9 +46,9 @@ std::string planBatch(const gtts_voice_config* voices, int32_t nVoices, const in
 		d.out_begin = plan.out_offsets[u];
 		d.flags = 0;
 		d.state_index = -1;
-		// every utterance starts on a 32-sample (128-byte) boundary of the output buffer: the kernel then
-		// writes whole aligned rows (see src_range in tube_kernel_v1.cuh)
-		plan.out_offsets[u + 1] = (plan.out_offsets[u] + d.n_out + 31) & ~int64_t(31);
+		// every utterance starts on a 64-sample (256-byte) boundary of the output buffer: the kernel then
+		// writes whole aligned row pairs (see src_rows in tube_kernel_v2.cuh)
+		plan.out_offsets[u + 1] = (plan.out_offsets[u] + d.n_out + 63) & ~int64_t(63);
 		plan.n_internal_total += d.n_internal;
 	}
 	plan.n_frames_total = nUtt ? frameOffsets[nUtt] : 0;

@@ -21,6 +21,7 @@
 #include "host_tables.h"
 #include "tube_kernel.cuh"
 #include "tube_kernel_v1.cuh"
+#include "tube_kernel_v2.cuh"
 
 using namespace gtts;
 
@@ -83,6 +84,7 @@ struct gtts_batch {
 	cudaStream_t stream = nullptr;      // used by run_host
 	int32_t last_launches = 0;
 	double* d_tables = nullptr;         // per-voice glottal wavetables (v1 kernel)
+	bool legacy_v1 = false;             // GTTS_KERNEL=v1: the barrier-per-iteration kernel instead of v2 (A/B measurements)
 	bool streaming = false;             // one-utterance batch of a gtts_stream (set before the plan is uploaded)
 	int32_t n_fast = 0;                 // the first n_fast entries of the order list run on the pipelined kernel
 	const char* last_kernel = "none";
@@ -112,8 +114,70 @@ int launchBatch(gtts_batch* b, const float* dFrames, float* dOut, cudaStream_t s
 	// one launch per non-empty part, each with its own work counter (uploadPlan).
 	const int32_t nFast = b->n_fast, nGeneral = static_cast<int32_t>(nUtt) - b->n_fast;
 	b->last_kernel = "none";
-	if (nFast > 0) {
-		// pipelined warp-specialised kernel: one persistent CTA per SM, 7 utterance slots each
+	if (nFast > 0 && !b->legacy_v1) {
+		// decoupled warp-specialised kernel: one persistent CTA per SM, 7 utterance slots each
+		v2::KernelParamsV2 Q;
+		Q.voices = b->d_voices;
+		Q.tables = b->d_tables;
+		Q.utts = b->d_utts;
+		Q.order = b->d_order;
+		Q.frames = dFrames;
+		Q.out = dOut;
+		Q.src_tab = b->h->d_src_tab;
+		Q.queue = b->d_queue;
+		Q.n_utt = nFast;
+		Q.prof = nullptr;
+		Q.debug_skip = 0;
+		const int64_t ctasWanted = (static_cast<int64_t>(nFast) + v2::kSlots - 1) / v2::kSlots;
+		const int grid = static_cast<int>(std::min<int64_t>(ctasWanted, b->h->sms));
+#ifdef GTTS_EXPERIMENTS
+		// development builds only (tools/ab_build.sh NAME -DGTTS_EXPERIMENTS): GTTS_DEBUG_SKIP=<bits> leaves pipeline
+		// roles out (wrong audio, for isolating a role under ncu); the shipped library has no such switch
+		if (const char* dbg = std::getenv("GTTS_DEBUG_SKIP")) Q.debug_skip = std::atoi(dbg);
+#endif
+#ifdef GTTS_ROLE_PROFILE
+		// development builds only: busy and waiting cycles per role (GTTS_PROFILE=1)
+		const bool profile = std::getenv("GTTS_PROFILE") != nullptr;
+		long long* dProf = nullptr;
+		const size_t rowLen = 2 * v2::kWarps + 1;
+		if (profile) {
+			GTTS_CUDA(cudaMalloc(&dProf, sizeof(long long) * grid * rowLen));
+			if (cudaMemsetAsync(dProf, 0, sizeof(long long) * grid * rowLen, stream) != cudaSuccess) {
+				cudaFree(dProf);
+				return failCuda(cudaGetLastError(), "profile buffer");
+			}
+			Q.prof = dProf;
+		}
+#endif
+		v2::tube_kernel_v2<<<grid, v2::kThreads, v2::smem_bytes(), stream>>>(Q);
+		GTTS_CUDA(cudaGetLastError());
+#ifdef GTTS_ROLE_PROFILE
+		if (profile) {
+			std::vector<long long> hp(static_cast<size_t>(grid) * rowLen);
+			cudaError_t pe = cudaStreamSynchronize(stream);
+			if (pe == cudaSuccess) pe = cudaMemcpy(hp.data(), dProf, sizeof(long long) * hp.size(), cudaMemcpyDeviceToHost);
+			cudaFree(dProf);
+			if (pe != cudaSuccess) return failCuda(pe, "profile readback");
+			double busy[v2::kWarps] = {0}, wait[v2::kWarps] = {0};
+			double iters = 0;
+			for (int c = 0; c < grid; ++c) {
+				for (int w = 0; w < v2::kWarps; ++w) {
+					busy[w] += static_cast<double>(hp[static_cast<size_t>(c) * rowLen + w]);
+					wait[w] += static_cast<double>(hp[static_cast<size_t>(c) * rowLen + v2::kWarps + 1 + w]);
+				}
+				iters += static_cast<double>(hp[static_cast<size_t>(c) * rowLen + v2::kWarps]);
+			}
+			std::fprintf(stderr, "[gtts profile] grid %d, iterations per CTA %.0f; busy cycles per iteration by role:", grid, iters / grid);
+			for (int w = 0; w < v2::kWarps; ++w) std::fprintf(stderr, " %d:%.0f", w, busy[w] / (iters > 0 ? iters : 1));
+			std::fprintf(stderr, "\n[gtts profile] waiting cycles per iteration by role:");
+			for (int w = 0; w < v2::kWarps; ++w) std::fprintf(stderr, " %d:%.0f", w, wait[w] / (iters > 0 ? iters : 1));
+			std::fprintf(stderr, "\n");
+		}
+#endif
+		b->last_kernel = "tube_kernel_v2";
+		b->last_launches += 1;
+	} else if (nFast > 0) {
+		// the barrier-per-iteration predecessor (GTTS_KERNEL=v1), kept for A/B measurements
 		v1::KernelParamsV1 Q;
 		Q.voices = b->d_voices;
 		Q.tables = b->d_tables;
@@ -128,50 +192,8 @@ int launchBatch(gtts_batch* b, const float* dFrames, float* dOut, cudaStream_t s
 		Q.debug_skip = 0;
 		const int64_t ctasWanted = (static_cast<int64_t>(nFast) + v1::kSlots - 1) / v1::kSlots;
 		const int grid = static_cast<int>(std::min<int64_t>(ctasWanted, b->h->sms));
-#ifdef GTTS_EXPERIMENTS
-		// development builds only (tools/ab_build.sh NAME -DGTTS_EXPERIMENTS): GTTS_DEBUG_SKIP=<bits> leaves pipeline
-		// roles out (wrong audio, for isolating a role under ncu); the shipped library has no such switch
-		if (const char* dbg = std::getenv("GTTS_DEBUG_SKIP")) Q.debug_skip = std::atoi(dbg);
-#endif
-#ifdef GTTS_ROLE_PROFILE
-		// development builds only: per-role busy cycles (GTTS_PROFILE=1)
-		const bool profile = std::getenv("GTTS_PROFILE") != nullptr;
-		long long* dProf = nullptr;
-		if (profile) {
-			GTTS_CUDA(cudaMalloc(&dProf, sizeof(long long) * grid * (2 * v1::kWarps + 1)));
-			if (cudaMemsetAsync(dProf, 0, sizeof(long long) * grid * (2 * v1::kWarps + 1), stream) != cudaSuccess) {
-				cudaFree(dProf);
-				return failCuda(cudaGetLastError(), "profile buffer");
-			}
-			Q.prof = dProf;
-		}
-#endif
 		v1::tube_kernel_v1<<<grid, v1::kThreads, v1::smem_bytes(), stream>>>(Q);
 		GTTS_CUDA(cudaGetLastError());
-#ifdef GTTS_ROLE_PROFILE
-		if (profile) {
-			const size_t rowLen = 2 * v1::kWarps + 1;
-			std::vector<long long> hp(static_cast<size_t>(grid) * rowLen);
-			cudaError_t pe = cudaStreamSynchronize(stream);
-			if (pe == cudaSuccess) pe = cudaMemcpy(hp.data(), dProf, sizeof(long long) * hp.size(), cudaMemcpyDeviceToHost);
-			cudaFree(dProf);
-			if (pe != cudaSuccess) return failCuda(pe, "profile readback");
-			double sum[v1::kWarps] = {0}, last[v1::kWarps] = {0};
-			double iters = 0;
-			for (int c = 0; c < grid; ++c) {
-				for (int w = 0; w < v1::kWarps; ++w) {
-					sum[w] += static_cast<double>(hp[static_cast<size_t>(c) * rowLen + w]);
-					last[w] += static_cast<double>(hp[static_cast<size_t>(c) * rowLen + v1::kWarps + 1 + w]);
-				}
-				iters += static_cast<double>(hp[static_cast<size_t>(c) * rowLen + v1::kWarps]);
-			}
-			std::fprintf(stderr, "[gtts profile] grid %d, iterations per CTA %.0f; busy cycles per iteration by warp:", grid, iters / grid);
-			for (int w = 0; w < v1::kWarps; ++w) std::fprintf(stderr, " %d:%.0f", w, sum[w] / (iters > 0 ? iters : 1));
-			std::fprintf(stderr, "\n[gtts profile] share of iterations in which the role reached the barrier last (%%):");
-			for (int w = 0; w < v1::kWarps; ++w) std::fprintf(stderr, " %d:%.0f", w, 100.0 * last[w] / (iters > 0 ? iters : 1));
-			std::fprintf(stderr, "\n");
-		}
-#endif
 		b->last_kernel = "tube_kernel_v1";
 		b->last_launches += 1;
 	}
@@ -191,7 +213,7 @@ int launchBatch(gtts_batch* b, const float* dFrames, float* dOut, cudaStream_t s
 		const size_t smem = tube_smem_bytes(kWarpsPerCta);
 		tube_kernel_v0<kWarpsPerCta><<<grid, kWarpsPerCta * 32, smem, stream>>>(P);
 		GTTS_CUDA(cudaGetLastError());
-		b->last_kernel = nFast > 0 ? "tube_kernel_v1+tube_kernel_v0" : "tube_kernel_v0";
+		b->last_kernel = nFast > 0 ? "pipelined+tube_kernel_v0" : "tube_kernel_v0";
 		b->last_launches += 1;
 	}
 	return GTTS_OK;
@@ -215,7 +237,10 @@ int uploadPlan(gtts_batch* b)
 	// part longest first (stable partition of the planner's order), so one odd utterance no longer moves the whole
 	// batch to the slow kernel.  GTTS_KERNEL=v0 forces v0 for all.
 	bool forceGeneral = b->streaming;     // resumed utterances (UttState) exist in the general kernel only
-	if (const char* env = std::getenv("GTTS_KERNEL")) forceGeneral = std::strcmp(env, "v0") == 0;
+	if (const char* env = std::getenv("GTTS_KERNEL")) {
+		if (std::strcmp(env, "v0") == 0) forceGeneral = true;
+		b->legacy_v1 = std::strcmp(env, "v1") == 0;
+	}
 	auto fast = [&](int32_t u) { const UttDesc& d = p.utts[u]; return !forceGeneral && (d.steps >= kBlock || d.steps == 1); };
 	const auto mid = std::stable_partition(p.order.begin(), p.order.end(), fast);
 	b->n_fast = static_cast<int32_t>(mid - p.order.begin());
@@ -366,7 +391,9 @@ int createHandle(int32_t device, gtts_handle** handle_out)
 	    (ce = cudaFuncSetAttribute(tube_kernel_v0<kWarpsPerCta>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	                               (int) tube_smem_bytes(kWarpsPerCta))) != cudaSuccess ||
 	    (ce = cudaFuncSetAttribute(v1::tube_kernel_v1, cudaFuncAttributeMaxDynamicSharedMemorySize,
-	                               (int) v1::smem_bytes())) != cudaSuccess) {
+	                               (int) v1::smem_bytes())) != cudaSuccess ||
+	    (ce = cudaFuncSetAttribute(v2::tube_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                               (int) v2::smem_bytes())) != cudaSuccess) {
 		if (h->d_src_tab) cudaFree(h->d_src_tab);
 		delete h;
 		return failCuda(ce, "gtts_create: device setup");
@@ -377,9 +404,9 @@ int createHandle(int32_t device, gtts_handle** handle_out)
 	char buf[1024];
 	std::snprintf(buf, sizeof buf,
 			"{\"device\": %d, \"name\": \"%s\", \"sm\": \"%d.%d\", \"sms\": %d, "
-			"\"kernels\": {\"tube_kernel_v1\": {\"warps_per_cta\": %d, \"utterance_slots_per_cta\": %d, \"smem_per_cta\": %zu}, "
+			"\"kernels\": {\"tube_kernel_v2\": {\"warps_per_cta\": %d, \"utterance_slots_per_cta\": %d, \"smem_per_cta\": %zu}, "
 			"\"tube_kernel_v0\": {\"warps_per_cta\": %d, \"utterances_per_warp\": 1, \"smem_per_cta\": %zu}}}",
-			device, prop.name, prop.major, prop.minor, h->sms, (int) v1::kWarps, (int) v1::kSlots, v1::smem_bytes(),
+			device, prop.name, prop.major, prop.minor, h->sms, (int) v2::kWarps, (int) v2::kSlots, v2::smem_bytes(),
 			kWarpsPerCta, tube_smem_bytes(kWarpsPerCta));
 	h->description = buf;
 	*handle_out = h;

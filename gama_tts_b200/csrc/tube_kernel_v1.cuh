@@ -270,7 +270,6 @@ struct HelperRegs {
 	unsigned long long mult;      // 377^(lane+1) mod 2^44, this lane's jump-ahead multiplier (loaded once)
 	unsigned long long lcg;       // noise generator state on the 2^-44 grid: next samples are lcg * 377^(j+1) mod 2^44
 	double noise_x1;
-	int low;                      // lowest wavetable closure point seen so far if it fell into the rise segment (kNoLowMark: never)
 	// conversions of the previous block, re-used while the parameter does not change (the reference
 	// caches the same way: BandpassFilter.h:93, WavetableGlottalSource.h:164)
 	float c_p1, c_p2, c_p3, c_p5, c_p6;
@@ -298,7 +297,6 @@ GTTS_DEV void helper_iteration(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int
 		if (lane < 7) cursor_init(frames, nFrames, K.U.inv_steps, lane, h.cur, h.delta, h.fn1, h.fn2);
 		h.off = 0; h.frame = 0;
 		h.lcg = c_lcg_init; h.noise_x1 = 0.0;
-		h.low = kNoLowMark;
 		h.c_p1 = h.c_p2 = h.c_p3 = h.c_p5 = h.c_p6 = __int_as_float(0x7fc00000);     // NaN: nothing cached
 		__syncwarp();
 	}
@@ -402,31 +400,15 @@ GTTS_DEV void helper_iteration(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int
 			lp = n + prev;
 		}
 		// wavetable lookup of both half samples (WavetableGlottalSource.h:212-228)
-		const bool dynamic = (V.waveform == 0) && (V.tn_delta != 0.0);
-		double nd2 = 0.0, inv = 0.0;
-		int low = kNoLowMark;
-		if (dynamic) {
-			// The fall segment [div1, div2) is a function of the current amplitude (setup(), :162-184).  Above 60 dB
-			// (ax > 1) the new closure point can fall below div1: the reference then zeroes [newDiv2, div2), i.e. part
-			// of the RISE segment, which nothing ever rewrites -- from that sample on the entries >= the lowest
-			// closure point seen so far read 0 (until reset()).  `low` is that running minimum up to and including
-			// this lane's sample.
-			nd2 = (double) V.div2 - rint(ax * V.tn_delta);
-			nd2 = nd2 > 0.0 ? nd2 : 0.0;
-			inv = 1.0 / (nd2 - (double) V.div1);
-			int mine = (lane < nb && nd2 < (double) V.div1) ? (int) nd2 : kNoLowMark;
-			if (__any_sync(0xffffffffu, mine != kNoLowMark) || h.low != kNoLowMark) {
-#pragma unroll
-				for (int dlt = 1; dlt < 32; dlt <<= 1) {
-					const int o = __shfl_up_sync(0xffffffffu, mine, dlt, 32);
-					if (lane >= dlt) mine = mine < o ? mine : o;
-				}
-				low = mine < h.low ? mine : h.low;
-				h.low = __shfl_sync(0xffffffffu, low, 31, 32);
-			}
-		}
 		if (lane < nb) {
 			const double* table = P.tables + (size_t) K.voice * kTableLen;
+			const bool dynamic = (V.waveform == 0) && (V.tn_delta != 0.0);
+			double nd2 = 0.0, inv = 0.0;
+			if (dynamic) {
+				nd2 = (double) V.div2 - rint(ax * V.tn_delta);
+				nd2 = nd2 > 0.0 ? nd2 : 0.0;
+				inv = 1.0 / (nd2 - (double) V.div1);
+			}
 			double v[2];
 #pragma unroll
 			for (int s = 0; s < 2; ++s) {
@@ -438,13 +420,13 @@ GTTS_DEV void helper_iteration(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int
 					const double x = (double) (int) (lo - V.div1) * inv;
 					tl = (lo >= (unsigned) nd2) ? 0.0 : 1.0 - (x * x);
 				} else {
-					tl = ((int) lo >= low && lo < (unsigned) V.div1) ? 0.0 : table[lo];
+					tl = table[lo];
 				}
 				if (dynamic && up >= (unsigned) V.div1 && up < (unsigned) V.div2) {
 					const double x = (double) (int) (up - V.div1) * inv;
 					tu = (up >= (unsigned) nd2) ? 0.0 : 1.0 - (x * x);
 				} else {
-					tu = ((int) up >= low && up < (unsigned) V.div1) ? 0.0 : table[up];
+					tu = table[up];
 				}
 				v[s] = tl + ((pos - (double) lo) * (tu - tl));
 			}

@@ -132,6 +132,17 @@ def config3_lengths(n_utt=65536, seed=7, lo=250, hi=5000):
     return np.exp(rng.uniform(np.log(lo), np.log(hi), n_utt)).astype(np.int64)
 
 
+def config3_utterance(u, lengths=None):
+    """Utterance u of THE BASELINE config 3 draw: length from the log-uniform draw of
+    config3_lengths(65536, seed 7), its own randomised voice from PCG64(7 + u), its own track (seed 7 + u).
+    Returns (voice dict, track [F, 16] float32)."""
+    from .voices import random_voice
+    if lengths is None:
+        lengths = config3_lengths()
+    voice = random_voice(np.random.Generator(np.random.PCG64(7 + int(u))))
+    return voice, synthetic_track(7 + int(u), int(lengths[u]))
+
+
 def tile_track(track, n_frames):
     """Repeats a track to n_frames frames (used to build long tracks from a short seed track)."""
     reps = -(-int(n_frames) // len(track))

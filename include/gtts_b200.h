@@ -127,8 +127,8 @@ int gtts_batch_prepare(gtts_handle* handle, const gtts_voice_config* voices, int
 			const int64_t* frame_offsets, int64_t n_utt, gtts_batch** batch_out);
 /* Layout of the output buffer, in float32 samples: utterance u occupies [out_offsets[u], out_offsets[u] +
  * n_out[u]); out_offsets[n_utt] is the size of the whole buffer.  Every utterance starts on a multiple of
- * 32 samples (128 bytes) so that the kernel writes whole aligned rows -- this is what lets it store straight
- * into pinned host memory at PCIe rate; the up to 31 samples between two utterances are never written.
+ * 64 samples (256 bytes) so that the kernel writes whole aligned rows -- this is what lets it store straight
+ * into pinned host memory at PCIe rate; the up to 63 samples between two utterances are never written.
  * n_internal[n_utt] (samples at the tube's internal rate) may be NULL. */
 int gtts_batch_layout(const gtts_batch* batch, int64_t* out_offsets, int64_t* n_internal);
 /* n_out[n_utt]: output samples of each utterance (== gtts_output_length of its voice, steps and frames). */
@@ -149,8 +149,8 @@ void gtts_batch_free(gtts_batch* batch);
 
 /* One-call convenience over prepare + run_host + free (what a C caller of the reference's
  * Controller::synthesize + outputBuffer() would use).  Utterance u is written at out[out_offsets[u]] with
- * gtts_output_length() samples; every utterance starts on a multiple of 32 samples (see gtts_batch_layout), so
- * out_capacity must be at least the sum over the utterances of their length rounded up to a multiple of 32 (the call
+ * gtts_output_length() samples; every utterance starts on a multiple of 64 samples (see gtts_batch_layout), so
+ * out_capacity must be at least the sum over the utterances of their length rounded up to a multiple of 64 (the call
  * fails with "output buffer too small" otherwise and still fills out_offsets, whose last entry is the size needed).
  * out_offsets[n_utt + 1] is filled if not NULL. */
 int gtts_batch_synthesize(gtts_handle* handle, const gtts_voice_config* voices, int32_t n_voices,

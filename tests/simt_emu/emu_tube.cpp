@@ -131,3 +131,66 @@ extern "C" int emu_batch_v1(const gtts_voice_config* voices, int n_voices, const
 	}
 	return 0;
 }
+
+// ---- v2 (decoupled roles, walker warps, two-output SRC) ---------------------------------------------------------
+#include "../../gama_tts_b200/csrc/tube_kernel_v2.cuh"
+
+extern "C" int emu_batch_v2(const gtts_voice_config* voices, int n_voices, const int* voice_index, double control_rate,
+			const int* steps_override, const float* frames, const long long* frame_offsets, long long n_utt,
+			float* out, long long* out_offsets, long long* out_lengths, int n_ctas)
+{
+	using namespace gtts;
+	BatchPlan plan;
+	int err = 0;
+	g_err = planBatch(voices, n_voices, voice_index, control_rate, steps_override,
+			reinterpret_cast<const int64_t*>(frame_offsets), n_utt, plan, &err);
+	if (err) return err;
+	// EMU_OUT_SHIFT=s (tests only): utterance u starts s + 7 u samples (mod 32) off its row, which the planner never
+	// produces -- exercises the partial first row and the row phases of the SRC stage.
+	if (const char* sh = std::getenv("EMU_OUT_SHIFT")) {
+		const long long shift = std::atoll(sh);
+		for (long long u = 0; u < n_utt; ++u) {
+			plan.out_offsets[u] += 128 * u + ((7 * u + shift) & 31);
+			plan.utts[u].out_begin = plan.out_offsets[u];
+		}
+		plan.out_offsets[n_utt] += 128 * n_utt + 64;
+	}
+	for (long long u = 0; u <= n_utt; ++u) out_offsets[u] = plan.out_offsets[u];
+	for (long long u = 0; u < n_utt; ++u) out_lengths[u] = plan.utts[u].n_out;
+	if (!out) return 0;
+	for (const UttDesc& d : plan.utts) {
+		if (d.steps < kBlock && d.steps != 1) { g_err = "v2 needs control periods of at least one block (or of one sample)"; return GTTS_ERR_UNSUPPORTED; }
+	}
+	std::vector<double> taps = designGlottalFir();
+	std::memset(c_fir, 0, sizeof c_fir);
+	for (size_t i = 0; i < taps.size(); ++i) c_fir[i] = taps[i];
+	lcgMultipliers(c_lcg);
+	c_lcg_init = lcgInitialState();
+	std::vector<double> h(kSrcFilterLen), dh(kSrcFilterLen);
+	buildSrcTables(h.data(), dh.data());
+	std::vector<double2> tab(kSrcFilterLen);
+	for (int i = 0; i < kSrcFilterLen; ++i) { tab[i].x = h[i]; tab[i].y = dh[i]; }
+	std::vector<double> tables(static_cast<size_t>(n_voices) * kTableLen);
+	for (int v = 0; v < n_voices; ++v) buildWavetable(plan.voices[v], tables.data() + static_cast<size_t>(v) * kTableLen);
+
+	int queue = 0;
+	v2::KernelParamsV2 P;
+	P.voices = plan.voices.data();
+	P.tables = tables.data();
+	P.utts = plan.utts.data();
+	P.order = plan.order.data();
+	P.frames = frames;
+	P.out = out;
+	P.src_tab = tab.data();
+	P.queue = &queue;
+	P.n_utt = static_cast<int32_t>(n_utt);
+	P.prof = nullptr;
+	P.debug_skip = 0;
+
+	std::vector<unsigned char> smem(v2::smem_bytes() + 64);
+	unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem.data()) + 15) & ~uintptr_t(15));
+	for (int b = 0; b < n_ctas; ++b) {
+		simt::run_cta(v2::kThreads, [&](int tid) { v2::tube_v2_cta_body(P, base, tid); });
+	}
+	return 0;
+}

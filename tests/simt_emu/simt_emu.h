@@ -29,6 +29,7 @@ struct Fiber {
 	ucontext_t ctx;
 	std::vector<char> stack;
 	int state = 0;              // 0 runnable, 1 blocked, 2 done
+	bool spun = false;          // yielded from a polling loop (spin_yield): runnable, but made no progress
 };
 
 struct Cta {
@@ -46,6 +47,14 @@ struct Cta {
 extern Cta* g_cta;
 
 inline void yield_to_scheduler() { swapcontext(&g_cta->fibers[g_cta->cur].ctx, &g_cta->sched); }
+
+// Called inside a polling loop on shared memory (the kernels' role_wait): lets every other fiber run once before the
+// poll is repeated.
+inline void spin_yield()
+{
+	g_cta->fibers[g_cta->cur].spun = true;
+	yield_to_scheduler();
+}
 
 inline void syncwarp(uint32_t mask)
 {
@@ -130,11 +139,15 @@ inline void run_cta(int nthreads, std::function<void(int)> body, size_t stackByt
 		f.ctx.uc_link = &cta.sched;
 		makecontext(&f.ctx, (void (*)()) fiber_entry, 1, t);
 	}
-	// Scheduler: drain one warp as far as it goes, then the next; stop when all fibers are done.
+	// Scheduler: drain one warp as far as it goes, then the next; stop when all fibers are done.  Fibers that poll
+	// (spin_yield) are resumed once per round; a round in which nothing but polling happened counts towards the
+	// deadlock limit.
+	long idleRounds = 0;
 	for (;;) {
-		bool anyAlive = false, progressed = false;
+		bool anyAlive = false, progressed = false, anySpun = false;
 		for (int w = 0; w * 32 < nthreads; ++w) {
 			bool ranInWarp = true;
+			std::vector<char> spunThisRound(32, 0);
 			while (ranInWarp) {
 				ranInWarp = false;
 				for (int l = 0; l < 32; ++l) {
@@ -143,18 +156,26 @@ inline void run_cta(int nthreads, std::function<void(int)> body, size_t stackByt
 					Fiber& f = cta.fibers[t];
 					if (f.state == 2) continue;
 					anyAlive = true;
-					if (f.state == 0) {
+					if (f.state == 0 && !spunThisRound[l]) {
 						cta.cur = t;
+						f.spun = false;
 						swapcontext(&cta.sched, &f.ctx);
-						ranInWarp = true;
-						progressed = true;
+						if (f.spun) {
+							spunThisRound[l] = 1;
+							anySpun = true;
+						} else {
+							ranInWarp = true;
+							progressed = true;
+						}
 					}
 				}
 			}
 		}
 		if (!anyAlive) break;
-		if (!progressed) {
-			std::fprintf(stderr, "simt_emu: deadlock (all live threads blocked)\n");
+		if (progressed) {
+			idleRounds = 0;
+		} else if (!anySpun || ++idleRounds > 100000) {
+			std::fprintf(stderr, "simt_emu: deadlock (all live threads blocked%s)\n", anySpun ? " or polling" : "");
 			std::abort();
 		}
 	}
@@ -196,6 +217,13 @@ inline unsigned __ballot_sync(unsigned mask, int pred)
 	for (int l = 0; l < 32; ++l) if ((mask >> l) & 1) { if (__shfl_sync(mask, pred, l, 32)) r |= 1u << l; }
 	return r;
 }
+inline unsigned __reduce_or_sync(unsigned mask, unsigned v)
+{
+	unsigned r = 0;
+	for (int l = 0; l < 32; ++l) if ((mask >> l) & 1) r |= __shfl_sync(mask, v, l, 32);
+	return r;
+}
+inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
 inline int __all_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) == mask; }
 inline float __int_as_float(int v) { float f; std::memcpy(&f, &v, 4); return f; }
 inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }

@@ -66,13 +66,13 @@ def test_emulated_kernel_steps_override(emu, oracle, real_tracks):
     assert np.array_equal(out, oracle.synthesize_samples(v, params))
 
 
-@pytest.fixture(scope="module")
-def emu_v1():
+def _pipelined_runner(symbol):
     subprocess.run(["make", "-s", "-C", os.path.join(HERE, "simt_emu")], check=True)
     L = C.CDLL(os.path.join(HERE, "simt_emu", "libemu_tube.so"))
     L.emu_last_error.restype = C.c_char_p
-    L.emu_batch_v1.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
-                               C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    fn = getattr(L, symbol)
+    fn.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
+                   C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
 
     def run(voices, vidx, tracks, ctas=1, rate=250.0, steps=None):
         va = voice_array(voices)
@@ -83,11 +83,23 @@ def emu_v1():
         ol = np.zeros(len(tracks) + 1, np.int64)
         args = [va, len(voices), vi.ctypes.data, rate, None if so is None else so.ctypes.data, frames.ctypes.data,
                 fo.ctypes.data, len(tracks)]
-        assert L.emu_batch_v1(*args, None, oo.ctypes.data, ol.ctypes.data, ctas) == 0, L.emu_last_error()
+        assert fn(*args, None, oo.ctypes.data, ol.ctypes.data, ctas) == 0, L.emu_last_error()
         out = np.full(int(oo[-1]), np.nan, np.float32)
-        assert L.emu_batch_v1(*args, out.ctypes.data, oo.ctypes.data, ol.ctypes.data, ctas) == 0, L.emu_last_error()
+        assert fn(*args, out.ctypes.data, oo.ctypes.data, ol.ctypes.data, ctas) == 0, L.emu_last_error()
         return [out[oo[i]:oo[i] + ol[i]] for i in range(len(tracks))]
     return run
+
+
+@pytest.fixture(scope="module", params=["v1", "v2"])
+def emu_v1(request):
+    """The pipelined kernels under the emulator: tube_kernel_v1.cuh (CTA barrier per iteration) and
+    tube_kernel_v2.cuh (decoupled roles, walker warps, two-output SRC) run the same tests."""
+    return _pipelined_runner("emu_batch_" + request.param)
+
+
+@pytest.fixture(scope="module")
+def emu_v2():
+    return _pipelined_runner("emu_batch_v2")
 
 
 def test_emulated_pipelined_kernel_matches_oracle(emu_v1, oracle, real_tracks):
@@ -156,7 +168,7 @@ def _loud_track(n=40, seed=11):
     return tr
 
 
-def test_emulated_kernels_reproduce_rise_segment_corruption(emu, emu_v1, oracle):
+def test_emulated_kernels_reproduce_rise_segment_corruption(emu, emu_v2, oracle):
     v = dict(default_voice("male"))
     v["glottal_pulse_tn_min"], v["glottal_pulse_tn_max"] = 16.0, 32.0
     tr = _loud_track()
@@ -164,7 +176,7 @@ def test_emulated_kernels_reproduce_rise_segment_corruption(emu, emu_v1, oracle)
     quiet = tr.copy()
     quiet[:, 1] = np.minimum(quiet[:, 1], 60.0)
     assert full_scale_error(oracle.synthesize(v, quiet)[-2000:], ref[-2000:]) > 1e-3     # the corruption is audible and lasting
-    for run in (lambda: emu([v], [0], [tr], warps=1)[0], lambda: emu_v1([v], [0], [tr])[0]):
+    for run in (lambda: emu([v], [0], [tr], warps=1)[0], lambda: emu_v2([v], [0], [tr])[0]):
         out = run()
         assert len(out) == len(ref)
         assert full_scale_error(out, ref) <= 1e-9
