@@ -110,6 +110,25 @@ class Batch:
         check(self._lib.gtts_batch_run_host(self._h, frames.ctypes.data, out.ctypes.data))
         return out
 
+    def run_host_pcm16(self, frames, want_scale=True):
+        """The reference's output stage on the device: (int16 payload in the batch layout, scale per utterance)."""
+        frames = np.ascontiguousarray(frames, np.float32)
+        pcm = np.zeros(self.n_out_total, np.int16)
+        scale = np.zeros(max(self.n_utt, 1), np.float32) if want_scale else None
+        check(self._lib.gtts_batch_run_host_pcm16(self._h, frames.ctypes.data, pcm.ctypes.data,
+                                                  None if scale is None else scale.ctypes.data))
+        return pcm, (None if scale is None else scale[:self.n_utt])
+
+    def run_host_pcm16_ptr(self, frames_ptr, pcm_ptr, scale_ptr=0):
+        check(self._lib.gtts_batch_run_host_pcm16(self._h, C.c_void_p(frames_ptr), C.c_void_p(pcm_ptr), C.c_void_p(scale_ptr)))
+
+    def submit_host_pcm16_ptr(self, frames_ptr, pcm_ptr, scale_ptr=0):
+        """Queues the whole pipeline on the batch's stream and returns; wait() blocks until it is done."""
+        check(self._lib.gtts_batch_submit_host_pcm16(self._h, C.c_void_p(frames_ptr), C.c_void_p(pcm_ptr), C.c_void_p(scale_ptr)))
+
+    def wait(self):
+        check(self._lib.gtts_batch_wait(self._h))
+
     def run_host_ptr(self, frames_ptr, out_ptr):
         check(self._lib.gtts_batch_run_host(self._h, C.c_void_p(frames_ptr), C.c_void_p(out_ptr)))
 
@@ -214,6 +233,16 @@ class TubeSynthesizer:
         b = self.prepare(voice_or_voices, fo, voice_index, control_rate, steps_override)
         try:
             return [a.copy() for a in b.split(b.run_host(frames))]
+        finally:
+            b.close()
+
+    def synthesize_pcm16(self, voice_or_voices, tracks, voice_index=None, control_rate=voices.DEFAULT_CONTROL_RATE):
+        """tracks -> (list of int16 arrays: the WAVE payload the reference would write, float32 scales)."""
+        frames, fo = pack_tracks(tracks)
+        b = self.prepare(voice_or_voices, fo, voice_index, control_rate)
+        try:
+            pcm, scale = b.run_host_pcm16(frames)
+            return [a.copy() for a in b.split(pcm)], scale
         finally:
             b.close()
 

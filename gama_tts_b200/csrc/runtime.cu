@@ -61,6 +61,67 @@ __global__ void fp64_peak_kernel(double* out, int iters, double a, double b)
 	out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// ---- output stage on the device: peak normalisation + 16-bit PCM ------------------------------------------------
+// The reference's Controller::writeOutputToFile (vtm_control_model/Controller.cpp:315-328): scale =
+// VTM::Util::calculateOutputScale(buffer) = 0.95f / max|x| (0 below 1e-30f; vtm/VTMUtil.cpp:20-21, 48-57), then
+// WAVEFileWriter::writeSample(x * scale) = (int) round((x * scale) * 32767.0f), low 16 bits (WAVEFileWriter.cpp:36-37,
+// 122-126).  All in float32, every product rounded on its own (no contraction), round half away from zero: the PCM
+// payload is bit-identical to the reference's for the same float32 input.  One CTA per utterance, HBM-bound.
+__global__ void utterance_peak_kernel(const float* audio, const UttDesc* utts, unsigned* peakBits)
+{
+	const UttDesc U = utts[blockIdx.x];
+	const float* x = audio + U.out_begin;
+	float m = 0.0f;
+	const long long n4 = U.n_out >> 2;
+	const float4* x4 = reinterpret_cast<const float4*>(x);          // utterances start on 256-byte boundaries
+	for (long long i = threadIdx.x; i < n4; i += blockDim.x) {
+		const float4 v = x4[i];
+		m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+	}
+	for (long long i = (n4 << 2) + threadIdx.x; i < U.n_out; i += blockDim.x) m = fmaxf(m, fabsf(x[i]));
+	for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+	__shared__ float warpMax[32];
+	if ((threadIdx.x & 31) == 0) warpMax[threadIdx.x >> 5] = m;
+	__syncthreads();
+	if (threadIdx.x < 32) {
+		m = threadIdx.x < (blockDim.x >> 5) ? warpMax[threadIdx.x] : 0.0f;
+		for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+		if (threadIdx.x == 0) peakBits[blockIdx.x] = __float_as_uint(m);     // NaN-free maxima of non-negative floats
+	}
+}
+
+__device__ __forceinline__ short pcm16_of(float x, float scale)
+{
+	const float sample = __fmul_rn(x, scale);
+	const int v = (int) roundf(__fmul_rn(sample, 32767.0f));
+	return (short) (v & 0xffff);
+}
+
+__global__ void utterance_pcm16_kernel(const float* audio, const UttDesc* utts, const unsigned* peakBits, short* pcm, float* scaleOut)
+{
+	const UttDesc U = utts[blockIdx.x];
+	const float peak = __uint_as_float(peakBits[blockIdx.x]);
+	const float scale = (peak < 1.0e-30f) ? 0.0f : __fdiv_rn(0.95f, peak);
+	if (scaleOut != nullptr && threadIdx.x == 0) scaleOut[blockIdx.x] = scale;
+	const float* x = audio + U.out_begin;
+	short* o = pcm + U.out_begin;
+	const long long n8 = U.n_out >> 3;
+	const float4* x4 = reinterpret_cast<const float4*>(x);
+	for (long long i = threadIdx.x; i < n8; i += blockDim.x) {
+		const float4 a = x4[2 * i], b = x4[2 * i + 1];
+		short4 lo, hi;
+		lo.x = pcm16_of(a.x, scale); lo.y = pcm16_of(a.y, scale); lo.z = pcm16_of(a.z, scale); lo.w = pcm16_of(a.w, scale);
+		hi.x = pcm16_of(b.x, scale); hi.y = pcm16_of(b.y, scale); hi.z = pcm16_of(b.z, scale); hi.w = pcm16_of(b.w, scale);
+		int4 packed;
+		packed.x = (unsigned short) lo.x | ((unsigned) (unsigned short) lo.y << 16);
+		packed.y = (unsigned short) lo.z | ((unsigned) (unsigned short) lo.w << 16);
+		packed.z = (unsigned short) hi.x | ((unsigned) (unsigned short) hi.y << 16);
+		packed.w = (unsigned short) hi.z | ((unsigned) (unsigned short) hi.w << 16);
+		reinterpret_cast<int4*>(o)[i] = packed;                         // 16 bytes per thread, utterances start on 128-byte boundaries
+	}
+	for (long long i = (n8 << 3) + threadIdx.x; i < U.n_out; i += blockDim.x) o[i] = pcm16_of(x[i], scale);
+}
+
 } // namespace
 
 struct gtts_handle {
@@ -80,7 +141,10 @@ struct gtts_batch {
 	UttState* d_states = nullptr;       // streaming only
 	float* d_frames = nullptr;          // staging for run_host
 	float* d_out = nullptr;
-	int64_t cap_frames = 0, cap_out = 0;
+	short* d_pcm = nullptr;             // run_host_pcm16 staging
+	unsigned* d_peak = nullptr;         // per-utterance max |sample| (float bits)
+	float* d_scale = nullptr;           // per-utterance normalisation scale
+	int64_t cap_frames = 0, cap_out = 0, cap_pcm = 0;
 	cudaStream_t stream = nullptr;      // used by run_host
 	int32_t last_launches = 0;
 	double* d_tables = nullptr;         // per-voice glottal wavetables (v1 kernel)
@@ -601,6 +665,99 @@ int gtts_batch_run_host(gtts_batch* b, const float* h_frames, float* h_out)
 	return GTTS_OK;
 }
 
+namespace {
+// the output stage after the synthesis kernels, same stream
+int launchPcm16(gtts_batch* b, const float* dAudio, short* dPcm, float* dScale, cudaStream_t stream)
+{
+	const int nUtt = static_cast<int>(b->plan.utts.size());
+	if (nUtt == 0) return GTTS_OK;
+	if (!b->d_peak) GTTS_CUDA(cudaMalloc(&b->d_peak, sizeof(unsigned) * nUtt));
+	utterance_peak_kernel<<<nUtt, 256, 0, stream>>>(dAudio, b->d_utts, b->d_peak);
+	GTTS_CUDA(cudaGetLastError());
+	utterance_pcm16_kernel<<<nUtt, 256, 0, stream>>>(dAudio, b->d_utts, b->d_peak, dPcm, dScale);
+	GTTS_CUDA(cudaGetLastError());
+	b->last_launches += 2;
+	return GTTS_OK;
+}
+} // namespace
+
+int gtts_batch_run_device_pcm16(gtts_batch* b, const float* d_frames, float* d_audio, int16_t* d_pcm, float* d_scale, void* cuda_stream)
+{
+	if (!b) return fail(GTTS_ERR_INVALID, "null batch");
+	if (!b->plan.utts.empty() && (!d_audio || !d_pcm || (b->plan.n_frames_total > 0 && !d_frames))) return fail(GTTS_ERR_INVALID, "null device buffer");
+	cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+	const int rc = launchBatch(b, d_frames, d_audio, stream);
+	if (rc != GTTS_OK) return rc;
+	return launchPcm16(b, d_audio, reinterpret_cast<short*>(d_pcm), d_scale, stream);
+}
+
+int gtts_batch_wait(gtts_batch* b)
+{
+	if (!b) return fail(GTTS_ERR_INVALID, "null batch");
+	if (!b->stream) return GTTS_OK;
+	GTTS_CUDA(cudaSetDevice(b->h->device));
+	GTTS_CUDA(cudaStreamSynchronize(b->stream));
+	return GTTS_OK;
+}
+
+int gtts_batch_run_host_pcm16(gtts_batch* b, const float* h_frames, int16_t* h_pcm, float* h_scale)
+{
+	const int rc = gtts_batch_submit_host_pcm16(b, h_frames, h_pcm, h_scale);
+	if (rc != GTTS_OK) return rc;
+	return gtts_batch_wait(b);
+}
+
+int gtts_batch_submit_host_pcm16(gtts_batch* b, const float* h_frames, int16_t* h_pcm, float* h_scale)
+{
+	if (!b) return fail(GTTS_ERR_INVALID, "null batch");
+	const int64_t nFrames = b->plan.n_frames_total;
+	const int64_t nOut = b->plan.out_offsets.empty() ? 0 : b->plan.out_offsets.back();
+	const int64_t nUtt = static_cast<int64_t>(b->plan.utts.size());
+	if ((nFrames > 0 && !h_frames) || (nOut > 0 && !h_pcm)) return fail(GTTS_ERR_INVALID, "null host buffer");
+	if (nUtt == 0) return GTTS_OK;
+	GTTS_CUDA(cudaSetDevice(b->h->device));
+	// frames: pinned host memory is read in place by the kernel, pageable memory is copied first (see run_host)
+	const float* dFrames = nullptr;
+	if (nFrames > 0) {
+		cudaPointerAttributes attr;
+		if (cudaPointerGetAttributes(&attr, h_frames) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer) {
+			dFrames = static_cast<const float*>(attr.devicePointer);
+		} else {
+			cudaGetLastError();
+			if (nFrames > b->cap_frames) {
+				if (b->d_frames) cudaFree(b->d_frames);
+				b->d_frames = nullptr; b->cap_frames = 0;
+				GTTS_CUDA(cudaMalloc(&b->d_frames, sizeof(float) * kNumParams * nFrames));
+				b->cap_frames = nFrames;
+			}
+			GTTS_CUDA(cudaMemcpyAsync(b->d_frames, h_frames, sizeof(float) * kNumParams * nFrames, cudaMemcpyHostToDevice, b->stream));
+			dFrames = b->d_frames;
+		}
+	}
+	// The float32 audio stays in device memory: the scale of an utterance needs all of it.  Only the 16-bit payload
+	// (half the bytes of the float32 path) and, if asked for, the scales travel to the host.
+	if (nOut > b->cap_out) {
+		if (b->d_out) cudaFree(b->d_out);
+		b->d_out = nullptr; b->cap_out = 0;
+		GTTS_CUDA(cudaMalloc(&b->d_out, sizeof(float) * nOut));
+		b->cap_out = nOut;
+	}
+	if (nOut > b->cap_pcm) {
+		if (b->d_pcm) cudaFree(b->d_pcm);
+		b->d_pcm = nullptr; b->cap_pcm = 0;
+		GTTS_CUDA(cudaMalloc(&b->d_pcm, sizeof(short) * nOut));
+		b->cap_pcm = nOut;
+	}
+	if (h_scale && !b->d_scale) GTTS_CUDA(cudaMalloc(&b->d_scale, sizeof(float) * nUtt));
+	int rc = launchBatch(b, dFrames, b->d_out, b->stream);
+	if (rc != GTTS_OK) return rc;
+	rc = launchPcm16(b, b->d_out, b->d_pcm, h_scale ? b->d_scale : nullptr, b->stream);
+	if (rc != GTTS_OK) return rc;
+	GTTS_CUDA(cudaMemcpyAsync(h_pcm, b->d_pcm, sizeof(short) * nOut, cudaMemcpyDeviceToHost, b->stream));
+	if (h_scale) GTTS_CUDA(cudaMemcpyAsync(h_scale, b->d_scale, sizeof(float) * nUtt, cudaMemcpyDeviceToHost, b->stream));
+	return GTTS_OK;
+}
+
 int gtts_batch_last_launches(const gtts_batch* b, int32_t* n_out)
 {
 	if (!b || !n_out) return fail(GTTS_ERR_INVALID, "null argument");
@@ -615,6 +772,7 @@ void gtts_batch_free(gtts_batch* b)
 	if (b->stream) { cudaStreamSynchronize(b->stream); cudaStreamDestroy(b->stream); }
 	cudaFree(b->d_voices); cudaFree(b->d_utts); cudaFree(b->d_order); cudaFree(b->d_queue);
 	cudaFree(b->d_states); cudaFree(b->d_frames); cudaFree(b->d_out); cudaFree(b->d_tables);
+	cudaFree(b->d_pcm); cudaFree(b->d_peak); cudaFree(b->d_scale);
 	delete b;
 }
 

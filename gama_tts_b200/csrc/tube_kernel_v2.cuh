@@ -19,11 +19,11 @@
 //                           register-held window, whole 256-byte row pairs                    lane = output pair
 //
 // What changed against v1 (measurements in DESIGN.md section 4):
-//  * No CTA-wide barrier.  Every role publishes the number of iterations it has completed in a shared-memory counter
-//    (st.release) and, before iteration i, waits (ld.acquire, one 32-lane load + vote per poll) until each role it
-//    shares a buffer with -- its producers AND its consumers -- has completed iteration i - 1.  That is the guarantee
-//    the barrier gave, restricted to the pairs that need it; roles that are not neighbours drift apart by up to
-//    three iterations (bounded by the four-deep ring of slot control blocks).
+//  * No CTA-wide barrier.  Before iteration i a role waits only for the roles it shares a buffer with -- its
+//    producers AND its consumers -- to have completed iteration i - 1: one named hardware barrier per role type and
+//    iteration parity, neighbours arrive without blocking, the type's warps wait without issuing.  That is the
+//    guarantee the CTA barrier gave, restricted to the pairs that need it; roles that are not neighbours drift apart
+//    by up to three iterations (bounded by the four-deep ring of slot control blocks).
 //  * The float32 parameter walks (Controller.cpp:297-311) run on two dedicated walker warps, 32 (slot, parameter)
 //    lanes per call instead of 7 or 9: a quarter of the instructions, and the serial walk is off the helpers.
 //  * SRC: every lane forms two consecutive outputs from ONE 27-sample window held in registers (half the window
@@ -44,7 +44,7 @@ namespace v2 {
 
 enum {
 	kSlots = 7,
-	kWarps = 24,
+	kWarps = 23,
 	kThreads = kWarps * 32,
 	kTubeWarps = 4,
 	kParamRow = 36,               // floats per walked-parameter row: 16-byte aligned, rows 4 banks apart
@@ -60,10 +60,9 @@ enum {
 	kRoleChainB = 5,
 	kRoleChainA2 = 6,
 	kRoleHelper0 = 7,             // + slot
-	kRoleCoef0 = 14,              // + slot
-	kRoleWalk0 = 21,              // slots 0..3
-	kRoleWalk1 = 22,              // slots 4..6
-	kRoleSrc = 23,                // shared SRC tasks (slots in lockstep); per-slot SRC runs on the slot's coefficient worker
+	kRoleCoef0 = 14,              // + slot: the slot's float32 walks, junction coefficients, per-slot SRC
+	kRoleSrcB = 21,               // shared SRC tasks (slots in lockstep), slots 4..6; per-slot SRC runs on the slot's coefficient worker
+	kRoleSrcA = 22,               // shared SRC tasks, slots 0..3
 	kCtrSched = 24,               // counter: control blocks published by the scheduler
 	kCounters = 32,
 	kCtlRing = 4,
@@ -105,8 +104,9 @@ struct SlotSm {
 		long long eq;
 		unsigned erem, eQ, eR, inc;
 	} ctl[kCtlRing];
-	int     pad_[2];              // slot stride = 16 mod 128 bytes: the 7 slots start in different banks
+	int     pad_[22];             // slot stride = 16 mod 128 bytes: the 7 slots start in different banks
 };
+static_assert(sizeof(SlotSm) % 128 == 16, "slot stride should be 16 mod 128 bytes (the chains read one 16-byte word per slot and lane); adjust pad_");
 
 struct CtaSm {
 	double2 tab[kSrcFilterLen + kSrcPad];
@@ -154,66 +154,140 @@ GTTS_DEV void st_release_shared(int* p, int v)
 {
 	asm volatile("st.release.cta.shared.b32 [%0], %1;" :: "r"((unsigned) __cvta_generic_to_shared(p)), "r"(v) : "memory");
 }
-GTTS_DEV void backoff() { __nanosleep(32); }
+GTTS_DEV void backoff(unsigned ns) { __nanosleep(ns); }
+// Named hardware barriers (ids 1..15; 0 is __syncthreads): `count` threads take part, some arriving (not blocking),
+// some waiting; prior shared-memory writes of the arriving threads are visible to the waiting ones when it completes.
+GTTS_DEV void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(count) : "memory"); }
+GTTS_DEV void bar_wait(int id, int count) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory"); }
 #define GTTS_OPAQUE_INT(x) asm volatile("" : "+r"(x))
 #else
 GTTS_DEV int ld_acquire_shared(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
 GTTS_DEV void st_release_shared(int* p, int v) { *reinterpret_cast<volatile int*>(p) = v; }
-GTTS_DEV void backoff() { simt::spin_yield(); }
+GTTS_DEV void backoff(unsigned) { simt::spin_yield(); }
+GTTS_DEV void bar_arrive(int id, int count) { simt::cta_barrier_arrive(id, count); }
+GTTS_DEV void bar_wait(int id, int count) { simt::cta_barrier(id, count); }
 #define GTTS_OPAQUE_INT(x) ((void) 0)
 #endif
 
-// Waits until done[q] >= need for every counter q (lane q polls counter q; `need` is the lane's own threshold,
-// -kNever for counters the role does not depend on).
-GTTS_DEV void role_wait(const CtaSm* C, int lane, int need)
+// ---- who waits for whom ----------------------------------------------------------------------------------------
+// Two roles are neighbours when they share a buffer, in either direction (producer -> consumer: the data must be
+// there; consumer -> producer: the buffer must be free again; every buffer is as deep as its stage distance + 1).
+// A role starts iteration i when every neighbour has completed iteration i - 1: the guarantee the CTA barrier of v1
+// gave, restricted to the pairs that need it.  Neighbourhood is kept per role TYPE:
+//
+//   type      warps  neighbours (shared buffers)
+//   tube        4    helper (in, ip), coef (kab), chain A2 (pab, fric), chain B (endm, endn)
+//   chain A     1    helper (osc, pos)
+//   chain A2    1    helper (sig, bp, taps), tube
+//   chain B     1    tube, helper (thr), coef (onepk7; xring for the per-slot SRC), SRC (xring)
+//   helper      7    chain A, chain A2, tube, chain B, walker (cur)
+//   coef        7    walker (pscr), tube, chain B
+//   SRC         2    chain B
+//   walker      1    helper, coef
+//
+// and implemented with one named hardware barrier per type and iteration parity (14 of the 15 ids): before
+// iteration i the warps of a type wait on barrier (type, i & 1); every neighbour warp arrives on it -- without
+// blocking -- when it has completed its iteration i - 1.  A waiting warp issues nothing.  (A neighbour cannot arrive
+// for iteration i + 2 before the type has passed iteration i: it would have to complete i + 1 first, which needs the
+// type's iteration i.)  The walker, the only type nobody produces for, polls its neighbours' completion counters
+// instead; so does the scheduler for its loose bound (the ring of control blocks), and every role checks that its
+// control block is published -- it is, up to kFar iterations ahead.
+enum { kTypeTube = 0, kTypeA, kTypeA2, kTypeB, kTypeHelper, kTypeCoef, kTypeSrc, kTypes };
+
+GTTS_DEV constexpr int type_of_role(int role)
 {
+	if (role < kTubeWarps) return kTypeTube;
+	if (role == kRoleChainA) return kTypeA;
+	if (role == kRoleChainB) return kTypeB;
+	if (role == kRoleChainA2) return kTypeA2;
+	if (role < kRoleCoef0) return kTypeHelper;
+	if (role < kRoleSrcB) return kTypeCoef;
+	return kTypeSrc;
+}
+
+// bit t set: type t is a neighbour
+GTTS_DEV constexpr unsigned neighbour_types(int type)
+{
+	switch (type) {
+	case kTypeTube:   return (1u << kTypeHelper) | (1u << kTypeCoef) | (1u << kTypeA2) | (1u << kTypeB);
+	case kTypeA:      return (1u << kTypeHelper);
+	case kTypeA2:     return (1u << kTypeHelper) | (1u << kTypeTube);
+	case kTypeB:      return (1u << kTypeTube) | (1u << kTypeHelper) | (1u << kTypeCoef) | (1u << kTypeSrc);
+	case kTypeHelper: return (1u << kTypeA) | (1u << kTypeA2) | (1u << kTypeTube) | (1u << kTypeB) | (1u << kTypeCoef);
+	case kTypeCoef:   return (1u << kTypeHelper) | (1u << kTypeTube) | (1u << kTypeB);
+	default:          return (1u << kTypeB);
+	}
+}
+
+GTTS_DEV constexpr int warps_of_type(int type)
+{
+	return type == kTypeTube ? kTubeWarps : ((type == kTypeHelper || type == kTypeCoef) ? kSlots : (type == kTypeSrc ? 2 : 1));
+}
+
+// threads taking part in the barrier of `type`: its own warps (waiting) and its neighbours' (arriving)
+GTTS_DEV constexpr int barrier_threads(int type)
+{
+	int warps = warps_of_type(type);
+	const unsigned nb = neighbour_types(type);
+	for (int t = 0; t < kTypes; ++t) if ((nb >> t) & 1u) warps += warps_of_type(t);
+	return 32 * warps;
+}
+
+GTTS_DEV constexpr int barrier_id(int type, int it) { return 1 + 2 * type + (it & 1); }
+
+// Polls until done[q] >= need for every counter q (lane q reads counter q; lanes with takesPart == false are left
+// out).  Between polls the warp sleeps, 100 ns at first and twice as long every time up to 0.8 us.  Used where a
+// wait is rare or the waiting warp is a single light one (see above).
+GTTS_DEV void poll_counters(CtaSm* C, int lane, int need, bool takesPart)
+{
+	unsigned ns = 100;
 	for (;;) {
 		const int v = ld_acquire_shared(&C->done[lane]);
-		if (__all_sync(0xffffffffu, v >= need)) break;
-		backoff();
+		const bool ok = !takesPart || v >= need;
+		if (__all_sync(0xffffffffu, ok)) break;
+		backoff(ns);
+		ns = ns < 800u ? 2u * ns : ns;
 	}
 }
 
-GTTS_DEV void role_signal(CtaSm* C, int counter, int lane, int value)
+// Before iteration `it`: the neighbours have completed it - 1, control block `it` is published.
+template<int TYPE>
+GTTS_DEV void role_wait(CtaSm* C, int lane, int it)
+{
+	if (it > 0) {
+		constexpr int threads = barrier_threads(TYPE);
+		bar_wait(barrier_id(TYPE, it), threads);
+	}
+	poll_counters(C, lane, it + 1, lane == kCtrSched);
+}
+
+// iteration `it` of `role` is complete: publish the counter, arrive on the neighbour types' barriers of iteration it + 1
+template<int TYPE, int T>
+GTTS_DEV void arrive_on_neighbours(int it)
+{
+	if (T < kTypes) {
+		constexpr unsigned nb = neighbour_types(TYPE);
+		if ((nb >> T) & 1u) {
+			constexpr int threads = barrier_threads(T);
+			bar_arrive(barrier_id(T, it + 1), threads);
+		}
+		arrive_on_neighbours<TYPE, (T < kTypes ? T + 1 : T)>(it);
+	}
+}
+
+template<int TYPE>
+GTTS_DEV void role_signal(CtaSm* C, int role, int lane, int it)
 {
 	__syncwarp();
-	if (lane == 0) st_release_shared(&C->done[counter], value);
+	if (lane == 0) st_release_shared(&C->done[role], it + 1);
+	arrive_on_neighbours<TYPE, 0>(it);
 }
 
-// slot -> tube role / helper role / coefficient worker / walker
-GTTS_DEV int tube_role_of_slot(int s) { return kRoleTube0 + (s & 3); }      // tube warp w steps slots w and w + 4
-GTTS_DEV int walk_role_of_slot(int s) { return s < 4 ? kRoleWalk0 : kRoleWalk1; }
-
-// Do roles a and b share a buffer (in either direction)?  See the buffer list in DESIGN.md section 4.1.
-GTTS_DEV bool roles_adjacent(int a, int b)
+// control blocks 0 .. n - 1 are published
+GTTS_DEV void sched_signal(CtaSm* C, int lane, int n)
 {
-	if (a > b) { const int t = a; a = b; b = t; }
-	const bool aTube = a < kTubeWarps;
-	const bool bHelper = b >= kRoleHelper0 && b < kRoleHelper0 + kSlots, aHelper = a >= kRoleHelper0 && a < kRoleHelper0 + kSlots;
-	const bool bCoef = b >= kRoleCoef0 && b < kRoleCoef0 + kSlots, aCoef = a >= kRoleCoef0 && a < kRoleCoef0 + kSlots;
-	const bool bWalk = b == kRoleWalk0 || b == kRoleWalk1;
-	if (aTube) {
-		if (b == kRoleChainB || b == kRoleChainA2) return true;                               // endm / endn; pab, fric
-		if (bHelper) return tube_role_of_slot(b - kRoleHelper0) == a;                          // in, ip
-		if (bCoef) return tube_role_of_slot(b - kRoleCoef0) == a;                              // kab
-		return false;
-	}
-	if (a == kRoleChainA) return bHelper;                                                     // osc, pos
-	if (a == kRoleChainB) return bHelper || bCoef || b == kRoleSrc;                           // thr; onepk7, xring (per-slot SRC); xring
-	if (a == kRoleChainA2) return bHelper;                                                    // sig, bp, taps
-	if (aHelper) return bWalk && walk_role_of_slot(a - kRoleHelper0) == b;                    // cur
-	if (aCoef) return bWalk && walk_role_of_slot(a - kRoleCoef0) == b;                        // pscr
-	return false;
-}
-
-// The lane's slack for counter `lane` as seen from `role`: iteration i of the role may start when
-// done[lane] >= i - slack.
-GTTS_DEV int role_slack(int role, int lane)
-{
-	if (lane == kCtrSched) return -1;                        // control block i exists once i + 1 blocks are published
-	if (lane >= kWarps || lane == role) return kNever;
-	if (roles_adjacent(role, lane)) return 0;
-	return role == kRoleChainA ? kFar : kNever;              // the scheduler recycles control blocks: nobody falls behind by more than kFar
+	__syncwarp();
+	if (lane == 0) st_release_shared(&C->done[kCtrSched], n);
 }
 
 GTTS_DEV int block_len(const SlotSm::Ctl& k, int b)
@@ -253,8 +327,9 @@ GTTS_DEV void cursor_init(const float* frames, long long nFrames, float invSteps
 // least one block long, so at most one frame boundary falls inside the block; at it the walk restarts from the next
 // frame value, not from the accumulated one (Controller.cpp:297-300).  The cursor carries the next two frame values
 // (fn1 = frame[f+1], fn2 = frame[f+2], clamped to the last frame): they are fetched from global memory one control
-// period ahead and fn2 is not touched on any other path, so that a fetch still in flight (pinned host memory:
-// microseconds over PCIe) never stalls the walk.
+// period ahead, and fn2 is read only in a block that contains a boundary, so that a fetch still in flight (pinned
+// host memory: microseconds over PCIe) never stalls the walk.  One compact loop (restart by select): the code is
+// shared by the seven coefficient workers, which matters more than its instruction count (instruction cache).
 GTTS_DEV void walk_block(const float* frames, long long nFrames, int steps, float invSteps, int param,
 			int nb, WalkRegs& w, float* out, bool active)
 {
@@ -262,9 +337,11 @@ GTTS_DEV void walk_block(const float* frames, long long nFrames, int steps, floa
 	const int first = (steps - w.off) < nb ? (steps - w.off) : nb;
 	const bool reaches = active && !perSample && (w.off + first == steps);
 	const int restart = reaches ? first : -1;
-	// chunks of four samples that contain some lane's restart point test every sample (warp-uniform branch), the
-	// others are four adds and one 16-byte store
-	const unsigned chunkMask = __reduce_or_sync(0xffffffffu, (reaches && first < kBlock) ? (1u << (first >> 2)) : 0u);
+	float c = w.cur, d = w.delta, c1 = 0.f, d1 = 0.f;
+	if (__any_sync(0xffffffffu, reaches)) {
+		c1 = w.fn1;
+		d1 = __fmul_rn(__fsub_rn(w.fn2, w.fn1), invSteps);
+	}
 	if (perSample) {
 		// one frame per internal sample (the plugin shim records the reference's per-sample parameters): the values
 		// ARE the frames, no walk; `frame` counts the samples consumed so far
@@ -274,35 +351,21 @@ GTTS_DEV void walk_block(const float* frames, long long nFrames, int steps, floa
 		}
 		return;
 	}
-	float c = w.cur, d = w.delta;
 	float4* o = reinterpret_cast<float4*>(out);
 #pragma unroll 1
 	for (int j0 = 0; j0 < kBlock; j0 += 4) {
 		float v[4];
-		if (!((chunkMask >> (j0 >> 2)) & 1u)) {
 #pragma unroll
-			for (int q = 0; q < 4; ++q) {
-				v[q] = c;
-				c = __fadd_rn(c, d);
-			}
-		} else {
-#pragma unroll
-			for (int q = 0; q < 4; ++q) {
-				if (j0 + q == restart) {
-					c = w.fn1;
-					d = __fmul_rn(__fsub_rn(w.fn2, w.fn1), invSteps);
-				}
-				v[q] = c;
-				c = __fadd_rn(c, d);
-			}
+		for (int q = 0; q < 4; ++q) {
+			const bool r = (j0 + q) == restart;
+			c = r ? c1 : c;
+			d = r ? d1 : d;
+			v[q] = c;
+			c = __fadd_rn(c, d);
 		}
-		if (active) *o = make_float4(v[0], v[1], v[2], v[3]);
-		o += 1;
+		if (active) o[j0 >> 2] = make_float4(v[0], v[1], v[2], v[3]);
 	}
-	if (restart == kBlock) {
-		c = w.fn1;
-		d = __fmul_rn(__fsub_rn(w.fn2, w.fn1), invSteps);
-	}
+	if (restart == kBlock) { c = c1; d = d1; }
 	if (active) {
 		w.cur = c;
 		w.delta = d;
@@ -316,25 +379,19 @@ GTTS_DEV void walk_block(const float* frames, long long nFrames, int steps, floa
 	}
 }
 
-// walker g (0: slots 0..3, 1: slots 4..6): two calls of 32 lanes = (2 slots) x (16 parameters)
-GTTS_DEV void walker_iteration(CtaSm* C, const KernelParamsV2& P, int lane, int g, int p, WalkRegs (&w)[2])
+// The slot's sixteen walks (lanes 0..15 = parameters): parameter 0 of block it, 1..6 of block it - 2, 7..15 of block it - 3.
+GTTS_DEV void walk_slot(SlotSm* S, const KernelParamsV2& P, int lane, int p, WalkRegs& w)
 {
 	const int param = lane & 15;
 	const int stage = param == 0 ? kStWalk0 : (param < 7 ? kStWalk1 : kStWalk7);
-#pragma unroll
-	for (int h = 0; h < 2; ++h) {
-		const int slot = 4 * g + 2 * h + (lane >> 4);
-		const bool valid = slot < kSlots;
-		SlotSm* S = &C->slot[valid ? slot : 0];
-		const SlotSm::Ctl& K = S->ctl[p];
-		const int b = K.it - stage;
-		const bool active = valid && K.it >= 0 && b >= 0 && b < K.nblocks;
-		const float* frames = P.frames + K.U.frame_begin * kNumParams;
-		if (active && b == 0) cursor_init(frames, K.U.n_frames, K.U.inv_steps, param, w[h]);
-		const int nb = active ? block_len(K, b) : kBlock;
-		float* row = param < 7 ? S->cur[b & 1][param] : S->pscr[b & 1][param - 7];
-		walk_block(frames, K.U.n_frames, active ? K.U.steps : kBlock, K.U.inv_steps, param, nb, w[h], row, active);
-	}
+	const SlotSm::Ctl& K = S->ctl[p];
+	const int b = K.it - stage;
+	const bool active = lane < 16 && K.it >= 0 && b >= 0 && b < K.nblocks;
+	const float* frames = P.frames + K.U.frame_begin * kNumParams;
+	if (active && b == 0) cursor_init(frames, K.U.n_frames, K.U.inv_steps, param, w);
+	const int nb = active ? block_len(K, b) : kBlock;
+	float* row = param < 7 ? S->cur[b & 1][param] : S->pscr[b & 1][param - 7];
+	walk_block(frames, K.U.n_frames, active ? K.U.steps : kBlock, K.U.inv_steps, param, nb, w, row, active);
 }
 
 // ---- slot helper: stage 1 (f0) and stage 3 (source) ------------------------------------------------------------
@@ -751,6 +808,22 @@ GTTS_DEV void src_task(CtaSm* C, const KernelParamsV2& P, int lane, int slot0, i
 	}
 }
 
+// Shared SRC tasks (all slots in the SRC stage in lockstep): the slots are split into two groups, one per SRC warp,
+// each of which forms the coefficients for its NS windows (`keep`: the slots of the group this warp stores).
+template<int NS>
+GTTS_DEV void src_shared_group(CtaSm* C, const KernelParamsV2& P, int lane, int slot0, int keep, int p)
+{
+	const CtaSm::Sched& D = C->sched[p];
+	if (!D.src_shared) return;
+	const int mask = (D.src_mask >> slot0) & keep;
+	if (mask == 0) return;
+	int ref = 0;
+	while (!((D.src_mask >> ref) & 1)) ++ref;
+	const unsigned inc = C->slot[ref].ctl[p].inc;
+#pragma unroll 1
+	for (int task = 0; task < D.src_tasks; ++task) src_task<NS>(C, P, lane, slot0, mask, inc, D.src_k0 + 64ll * task, D.src_k0w, D.src_k1, p);
+}
+
 // per-slot SRC (slots not in lockstep): the slot's own outputs, 64 per pass
 GTTS_DEV void src_slot_task(CtaSm* C, const KernelParamsV2& P, int lane, int slot, int p)
 {
@@ -914,19 +987,23 @@ GTTS_DEV void chain_b_iteration(CtaSm* C, int lane, ChainBRegs& r, int p)
 // ---- tube warps: block it - 5, one cell per lane, 16 lanes per utterance, two utterances per warp --------------
 // Cells: u = 0..9 oral S1..S10 (u = 3: the 3-way junction after S4, u = 9: mouth end), u = 10..15 nasal N1..N6
 // (u = 15: nose end).  The forward wave goes u -> u + 1, the backward wave u + 1 -> u, the velum branch links
-// u = 3 <-> u = 10: three 64-bit shuffles per sample.  The three kinds of cell are ONE formula with per-lane
-// constants (a 64-bit select costs two issue slots on top of the arithmetic it chooses between):
-//        dl = e3 nb + k (T + sigma Bn)      Tout = (T + dl) d + tap      Bout = (cA last + cW Bn + dl) d
-//      2-port junction  sigma = -1, cW = 1, cA = 0, e3 = 0: dl = k (T - Bn)                (VocalTractModel0.h:575-600)
-//      3-way junction   sigma = +1, cW = 1, e3 = alpha_u, k = alpha - 1: dl = jp - T - Bn with
-//                       jp = alpha (T + Bn) + alpha_u nb; Tout = (jp - Bn) d, Bout = (jp - T) d, and the wave into
-//                       the nose (jp - nb) d = (T + dl + Bn - nb) d; alpha_u = 2 - 2 alpha = -2 k              (:602-617)
-//      open end         sigma = 0, cW = 0, cA = -a1 / d, k = b0 k_end: Bout / d = b0 (k T) - a1 y1 is the reflection
-//                       low-pass, whose state y1 is last / d (last = the lane's own Bout of the previous sample)  (:619-630)
-// Damping is folded into the coefficients (the coefficient worker stores k d), so that every output is two dependent
-// FMAs behind T.  Cells whose coefficient is a per-voice constant (S6|S7: 0, the nasal junctions N1|N2 .. N5|N6 and
-// the nose end) keep it in a register; the other ten read it per sample (kab row v >> 1, component v & 1, v = kVarCell).
-// Lanes of slots without a block at this stage run on dummy data: their state is reset when their block 0 arrives.
+// u = 3 <-> u = 10: three 64-bit shuffles per sample.  A single warp issues in order and every FP64 instruction costs
+// it two cycles whether the result is needed soon or not (tools/microbench/tube_chain.cu), so the step is written for
+// the fewest FP64 operations (12) and the shortest chain behind the incoming wave T (two operations).  The three
+// kinds of cell are ONE formula with per-lane constants; kd = k d is what the coefficient worker stores:
+//        ts = T + sigma Bn + tau nb       Tout = kd ts + (d T + tap)       Bout = kd ts + cB B*       Lout = kd ts + (m3 d T + E)
+//      2-port junction  sigma = -1, tau = 0, cB = d, B* = Bn: dl = k (T - Bn), Tout = (T + dl) d + tap,
+//                       Bout = (Bn + dl) d; Lout == Bout (m3 = 0, E = cB B*)                   (VocalTractModel0.h:575-600)
+//      3-way junction   k = alpha - 1 (alpha = alpha_left = alpha_right), alpha_u = 2 - 2 alpha = -2 k, hence
+//                       sigma = +1, tau = -2: kd ts = d (jp - T - Bn) with jp = alpha (T + Bn) + alpha_u nb;
+//                       Tout = (jp - Bn) d + tap, Bout = (jp - T) d, and the wave into the nose
+//                       Lout = (jp - nb) d = kd ts + d T + d (Bn - nb)  (m3 = 1, E = d (Bn - nb))              (:602-617)
+//      open end         sigma = tau = 0, kd = b0 k_end d, cB = -a1, B* = the lane's own Bout of the previous sample
+//                       (it shuffles from itself): Bout / d = b0 (k T) - a1 y1 is the reflection low-pass, y1 = B* / d (:619-630)
+// The incoming wave of the next sample: T = from the previous cell | the link (N1) | d B[S1] + glottal input (S1).  Cells whose coefficient is a per-voice constant (S6|S7: 0, the nasal
+// junctions N1|N2 .. N5|N6 and the nose end) keep it in a register; the other ten read it per sample (kab row v >> 1,
+// component v & 1).  Lanes of slots without a block at this stage run on dummy data: their state is reset when
+// their block 0 arrives.
 struct TubeCell { double T, Bn, nb, last; };
 
 GTTS_DEV void tube_iteration(CtaSm* C, int warp, int lane, TubeCell& t, int p)
@@ -943,13 +1020,15 @@ GTTS_DEV void tube_iteration(CtaSm* C, int warp, int lane, TubeCell& t, int p)
 	const VoiceDev& V = S->V[K.vbuf];
 	if (b == 0) { t.T = t.Bn = t.nb = t.last = 0.0; }
 	const double d = V.damping;
-	const bool is3 = u == 3, isEnd = (u == 9) || (u == 15);
+	const bool is3 = u == 3, isEnd = (u == 9) || (u == 15), isGlot = u == 0, isN1 = u == 10;
 	const bool storesEnd = isEnd && slot < kSlots;     // the second group of the last warp is a dummy: it must not store
+	// per-lane constants of the one formula (see above)
 	const double sigma = is3 ? 1.0 : (isEnd ? 0.0 : -1.0);
-	const double cWd = isEnd ? 0.0 : d;
-	const double cAd = isEnd ? -(u == 9 ? V.refl_a1_m : V.refl_a1_n) : 0.0;
-	const double mP = (u == 0 || u == 10) ? 0.0 : 1.0, mL = (u == 10) ? 1.0 : 0.0, mG = (u == 0) ? d : 0.0;
-	const double e3c = is3 ? -2.0 : 0.0;               // alpha_u d = -2 (alpha - 1) d
+	const double tau = is3 ? -2.0 : 0.0;               // alpha_u d = (2 - 2 alpha) d = -2 k: folded into ts
+	const double cB = isEnd ? -(u == 9 ? V.refl_a1_m : V.refl_a1_n) : d;
+	const double m3d = is3 ? d : 0.0;
+	const double mG = isGlot ? d : 0.0;
+	const double mP = (isGlot || isN1) ? 0.0 : 1.0;
 	const int tap = (u >= 1 && u <= 8) ? u - 1 : -100;
 	// index among the cells with a per-sample coefficient: u = 0..4 -> 0..4, 6..10 -> 5..9; -1: constant
 	const int var = u <= 4 ? u : (u >= 6 && u <= 10 ? u - 1 : -1);
@@ -957,13 +1036,13 @@ GTTS_DEV void tube_iteration(CtaSm* C, int warp, int lane, TubeCell& t, int p)
 	const double kConst = (u == 5) ? 0.0 : ((u == 15 ? V.nasal_k[5] * V.refl_b0_n : V.nasal_k[u >= 11 ? u - 10 : 1]) * d);
 	const double* kRowp = &S->kab[buf][isVar ? var >> 1 : 0][0].x + (var & 1);     // stride 2 doubles per sample
 	const double2* pabRow = S->pab[buf];
-	const bool isGlot = u == 0;
 	const double* inRow = S->in[b3];                   // read by lane u = 0 only
 	const signed char* ipRow = S->ip[b3];
 	double* endRow = (u == 15) ? S->endn[buf] : S->endm[buf];
-	const int srcPrev = 2 * ((u + 15) & 15) + sbit, srcNext = 2 * ((u + 1) & 15) + sbit, srcLink = 2 * (is3 ? 10 : 3) + sbit;
-	// T = forward wave into the cell, Bn = backward wave from the next cell, nb = wave on the velum link,
-	// last = the cell's own backward output of the previous sample (glottis reflection, end-filter state)
+	// an end cell has no next cell: it takes its own backward output instead, so that Bn is its filter state y1 d
+	const int srcPrev = 2 * ((u + 15) & 15) + sbit, srcNext = isEnd ? lane : 2 * ((u + 1) & 15) + sbit, srcLink = 2 * (is3 ? 10 : 3) + sbit;
+	// T = forward wave into the cell, Bn = backward wave from the next cell (end cells: own previous backward output),
+	// nb = wave on the velum link, last = the cell's own backward output of the previous sample (glottis reflection)
 	double T = t.T, Bn = t.Bn, nb = t.nb, last = t.last;
 	double inv[4] = {0.0, 0.0, 0.0, 0.0};              // glottal input (lane u = 0): zero on every other lane
 #pragma unroll 1
@@ -976,10 +1055,7 @@ GTTS_DEV void tube_iteration(CtaSm* C, int warp, int lane, TubeCell& t, int p)
 			if (isGlot) inv[q] = inRow[j0 + q];
 			tf[q] = 0.0;
 		}
-		// the flag is opaque inside the loop: unswitched into two copies, the loop costs 10 % through the instruction cache
-		int fricNow = fricBlock;
-		GTTS_OPAQUE_INT(fricNow);
-		if (fricNow) {
+		if (fricBlock) {
 			// frication injected at taps ip, ip + 1 (the reference adds tap * 0 = 0 everywhere else)
 #pragma unroll
 			for (int q = 0; q < 4; ++q) {
@@ -990,25 +1066,24 @@ GTTS_DEV void tube_iteration(CtaSm* C, int warp, int lane, TubeCell& t, int p)
 		}
 #pragma unroll
 		for (int q = 0; q < 4; ++q) {
-			// known before T: everything that depends only on the neighbours' waves and the lane's own state
-			const double e = (e3c * kv[q]) * nb;                     // alpha_u d NB[N1] (3-way junction only)
-			const double pre = (mG * last) + inv[q];                 // glottis: T[S1] = B[S1] d + input, B[S1] of the previous sample
-			const double eB = (cAd * last) + ((cWd * Bn) + e);
-			const double eT = e + tf[q];
-			const double eX = e + (d * (Bn - nb));
-			// behind T: two dependent FMAs per output
-			const double ts = (sigma * Bn) + T;
-			const double dT = d * T;
+			// before T is known: everything that depends only on the neighbours' waves and the lane's own state
+			const double w = (tau * nb) + (sigma * Bn);
+			const double cBB = cB * Bn;                                  // d Bn | -a1 (y1 d) of the end filter
+			const double el0 = cBB - (m3d * nb);                         // 3-way junction: d (Bn - nb)
+			const double pre = (mG * last) + inv[q];                     // glottis: T[S1] = B[S1] d + input, B[S1] of the previous sample
+			// behind T: two dependent operations per output
+			const double ts = T + w;
+			const double dTf = (d * T) + tf[q];
+			const double el = (m3d * T) + el0;
 			if (storesEnd) endRow[j0 + q] = T;
-			const double Tout = (kv[q] * ts) + (dT + eT);
-			const double Bout = (kv[q] * ts) + eB;
-			const double Xd = (kv[q] * ts) + (dT + eX);
-			const double linkOut = is3 ? Xd : Bout;
+			const double Tout = (kv[q] * ts) + dTf;
+			const double Bout = (kv[q] * ts) + cBB;
+			const double Lout = (kv[q] * ts) + el;                       // 3-way junction: the wave into the nose; else == Bout
 			const double fromPrev = shfl_d(Tout, srcPrev, 32);
 			const double fromNext = shfl_d(Bout, srcNext, 32);
-			const double link = shfl_d(linkOut, srcLink, 32);
+			const double link = shfl_d(Lout, srcLink, 32);
 			last = Bout;
-			T = (mP * fromPrev) + ((mL * link) + pre);
+			T = (mP * fromPrev) + (isN1 ? link : pre);
 			Bn = fromNext;
 			nb = link;
 		}
@@ -1145,18 +1220,17 @@ GTTS_DEV void schedule_slots(CtaSm* C, const KernelParamsV2& P, int lane, int i,
 
 // A role's loop: before iteration i wait for the neighbours' iteration i - 1 (and for control block i), run the body
 // on control block p = i % 4, publish i + 1.
-#define GTTS_ROLE_LOOP2(BODY)                                                    \
+#define GTTS_ROLE_LOOP2(TYPE, BODY)                                              \
 	{                                                                            \
 		GTTS_PROF_DECL;                                                          \
-		const int slack = role_slack(role, lane);                                \
 		for (int it = 0;; ++it) {                                                \
 			GTTS_PROF_T0();                                                      \
-			role_wait(C, lane, it - slack);                                      \
+			role_wait<TYPE>(C, lane, it);                                        \
 			GTTS_PROF_T1();                                                      \
 			const int p = it & (kCtlRing - 1);                                   \
 			if (!C->sched[p].live) break;                                        \
 			BODY                                                                 \
-			role_signal(C, role, lane, it + 1);                                  \
+			role_signal<TYPE>(C, role, lane, it);                                \
 			GTTS_PROF_T2();                                                      \
 		}                                                                        \
 		GTTS_PROF_STORE(P, role, lane);                                          \
@@ -1169,13 +1243,15 @@ GTTS_DEV void tube_v2_cta_body(const KernelParamsV2& P, unsigned char* smem, int
 	// Hardware warp w runs on SM sub-partition w % 4; which role runs where matters by a few percent (v1 measurements):
 	// tube warps one per sub-partition, the chains and the light workers spread next to them.
 #ifndef GTTS_ROLE_TABLE2
-#define GTTS_ROLE_TABLE2 0, 1, 2, 3, 5, 23, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 4
+#define GTTS_ROLE_TABLE2 0, 1, 2, 3, 5, 22, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 4, 21
 #endif
 	const int hw = tid >> 5;
 	int role;
 	{
 		constexpr int roleOfHw[kWarps] = {GTTS_ROLE_TABLE2};
-		role = roleOfHw[hw];
+		// through a shuffle: the compiler then knows that the role is the same for the whole warp -- without it every
+		// warp-collective instruction of the kernel is guarded against divergence (750 instructions of code)
+		role = __shfl_sync(0xffffffffu, roleOfHw[hw], 0, 32);
 	}
 	for (int i = tid; i < kSrcFilterLen + kSrcPad; i += kThreads) C->tab[i] = i < kSrcFilterLen ? P.src_tab[i] : make_double2(0.0, 0.0);
 	if (tid < kCounters) C->done[tid] = 0;
@@ -1185,50 +1261,57 @@ GTTS_DEV void tube_v2_cta_body(const KernelParamsV2& P, unsigned char* smem, int
 	__syncthreads();
 	if (role == kRoleChainA) {
 		schedule_slots(C, P, lane, -1, true);      // fills ctl[0] / sched[0]
-		role_signal(C, kCtrSched, lane, 1);
+		sched_signal(C, lane, 1);
 	}
 	__syncthreads();
 
 	GTTS_SKIP_BITS2(P);
 	if (role < kTubeWarps) {
 		TubeCell tl = {0.0, 0.0, 0.0, 0.0};
-		GTTS_ROLE_LOOP2(if (!(skip & 32)) tube_iteration(C, role, lane, tl, p);)
+		GTTS_ROLE_LOOP2(kTypeTube, if (!(skip & 32)) tube_iteration(C, role, lane, tl, p);)
 	} else if (role == kRoleChainA) {
+		// The scheduler publishes control block it + 1 BEFORE it waits for the helpers of its own chain: the control
+		// blocks then run up to kFar iterations ahead of the slowest role, and no role ever waits for one.
 		double pos = 0.0;
-		GTTS_ROLE_LOOP2(
+		GTTS_PROF_DECL;
+		for (int it = 0;; ++it) {
+			GTTS_PROF_T0();
+			poll_counters(C, lane, it - kFar, lane < kWarps && lane != role);      // ring of control blocks: nobody more than kFar behind
+			const int p = it & (kCtlRing - 1);
+			if (!C->sched[p].live) break;
 			schedule_slots(C, P, lane, it, false);
-			role_signal(C, kCtrSched, lane, it + 2);
-			if (!(skip & 8)) chain_a_iteration(C, lane, pos, p);)
+			sched_signal(C, lane, it + 2);
+			if (it > 0) bar_wait(barrier_id(kTypeA, it), barrier_threads(kTypeA));   // the helpers' oscillator increments of iteration it - 1
+			GTTS_PROF_T1();
+			if (!(skip & 8)) chain_a_iteration(C, lane, pos, p);
+			role_signal<kTypeA>(C, role, lane, it);
+			GTTS_PROF_T2();
+		}
+		GTTS_PROF_STORE(P, role, lane);
 	} else if (role == kRoleChainA2) {
 		BandpassState bp = {0.0, 0.0, 0.0, 0.0};
-		GTTS_ROLE_LOOP2(if (!(skip & 8)) chain_a2_iteration(C, lane, bp, p);)
+		GTTS_ROLE_LOOP2(kTypeA2, if (!(skip & 8)) chain_a2_iteration(C, lane, bp, p);)
 	} else if (role == kRoleChainB) {
 		ChainBRegs cb = {0.0, 0.0};
-		GTTS_ROLE_LOOP2(if (!(skip & 16)) chain_b_iteration(C, lane, cb, p);)
+		GTTS_ROLE_LOOP2(kTypeB, if (!(skip & 16)) chain_b_iteration(C, lane, cb, p);)
 	} else if (role < kRoleCoef0) {
 		HelperRegs hr = {};
 		hr.mult = c_lcg[lane];
 		hr.low = kNoLowMark;
 		SlotSm* S = &C->slot[role - kRoleHelper0];
-		GTTS_ROLE_LOOP2(if (!(skip & 4)) helper_iteration(S, P, lane, hr, p);)
-	} else if (role < kRoleWalk0) {
+		GTTS_ROLE_LOOP2(kTypeHelper, if (!(skip & 4)) helper_iteration(S, P, lane, hr, p);)
+	} else if (role < kRoleSrcB) {
 		const int slot = role - kRoleCoef0;
-		GTTS_ROLE_LOOP2(
+		WalkRegs wr = {0.f, 0.f, 0.f, 0.f, 0, 0};
+		GTTS_ROLE_LOOP2(kTypeCoef,
+			if (!(skip & 64)) walk_slot(&C->slot[slot], P, lane, p, wr);
 			if (!(skip & 2)) coef_task(&C->slot[slot], lane, p);
 			if (!(skip & 1) && !C->sched[p].src_shared && ((C->sched[p].src_mask >> slot) & 1)) src_slot_task(C, P, lane, slot, p);)
-	} else if (role < kRoleSrc) {
-		WalkRegs wr[2] = {{0.f, 0.f, 0.f, 0.f, 0, 0}, {0.f, 0.f, 0.f, 0.f, 0, 0}};
-		const int g = role - kRoleWalk0;
-		GTTS_ROLE_LOOP2(if (!(skip & 64)) walker_iteration(C, P, lane, g, p, wr);)
 	} else {
-		GTTS_ROLE_LOOP2(
-			if (!(skip & 1) && C->sched[p].src_shared) {
-				const CtaSm::Sched& D = C->sched[p];
-				int ref = 0;
-				while (!((D.src_mask >> ref) & 1)) ++ref;
-				const unsigned inc = C->slot[ref].ctl[p].inc;
-				for (int task = 0; task < D.src_tasks; ++task) src_task<kSlots>(C, P, lane, 0, D.src_mask, inc, D.src_k0 + 64ll * task, D.src_k0w, D.src_k1, p);
-			})
+		// the shared SRC tasks on two warps: windows of slots 0..3 | slots 3..6 with slot 3 left out (one instantiation)
+		const int slot0 = role == kRoleSrcA ? 0 : 3;
+		const int keep = role == kRoleSrcA ? 0xf : 0xe;
+		GTTS_ROLE_LOOP2(kTypeSrc, if (!(skip & 1)) src_shared_group<4>(C, P, lane, slot0, keep, p);)
 	}
 }
 

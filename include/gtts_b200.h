@@ -143,6 +143,23 @@ int gtts_batch_run_device(gtts_batch* batch, const float* d_frames, float* d_out
  * aligned, which pinned allocations are).  The samples between two utterances (see gtts_batch_layout) are not
  * written. */
 int gtts_batch_run_host(gtts_batch* batch, const float* h_frames, float* h_out);
+/* The reference's output stage on the device (BASELINE next row 2): per utterance the peak-normalisation scale
+ * 0.95f / max|x| (0 below 1e-30f: VTM::Util::calculateOutputScale, gama_tts/src/vtm/VTMUtil.cpp:20-21, 48-57) and the
+ * 16-bit PCM payload Controller::writeOutputToFile + WAVEFileWriter::writeSample would put into the WAVE file
+ * (gama_tts/src/vtm_control_model/Controller.cpp:315-328, gama_tts/src/WAVEFileWriter.cpp:36-37, 122-126): bit-identical
+ * to the reference's for the same float32 audio.  pcm has the layout of the float32 output (gtts_batch_layout, in
+ * samples); scale[n_utt] may be NULL.  The float32 audio is kept in device memory (d_audio: a scratch buffer of
+ * out_offsets[n_utt] floats for the device call), only the 16-bit payload -- half the bytes -- goes to the host. */
+int gtts_batch_run_device_pcm16(gtts_batch* batch, const float* d_frames, float* d_audio, int16_t* d_pcm,
+			float* d_scale, void* cuda_stream);
+int gtts_batch_run_host_pcm16(gtts_batch* batch, const float* h_frames, int16_t* h_pcm, float* h_scale);
+/* The same without waiting: everything (frame copy if the frames are pageable, synthesis, output stage, device->host
+ * copy of the payload) is queued on the batch's own stream and the call returns; gtts_batch_wait() blocks until it
+ * is done.  With two prepared batches a host keeps the GPU busy: while batch A's payload travels to the host (copy
+ * engine), batch B is being synthesised -- a serving loop's steady state is then max(synthesis, transfer) per batch
+ * instead of their sum.  The host buffers must stay valid (and, to overlap, be pinned) until the wait returns. */
+int gtts_batch_submit_host_pcm16(gtts_batch* batch, const float* h_frames, int16_t* h_pcm, float* h_scale);
+int gtts_batch_wait(gtts_batch* batch);
 /* Number of kernel launches the last run issued (for bench.py's gpu_launches claim). */
 int gtts_batch_last_launches(const gtts_batch* batch, int32_t* n_out);
 void gtts_batch_free(gtts_batch* batch);

@@ -95,6 +95,10 @@ class Oracle:
         L.oracle_src_run.argtypes = [C.c_double, C.c_double, C.c_void_p, C.c_long, C.c_void_p, C.c_long]
         L.oracle_wavetable.argtypes = [C.POINTER(OracleVoice), C.c_double, C.c_void_p, C.c_void_p]
         L.oracle_constants.argtypes = [C.POINTER(OracleVoice), C.c_void_p]
+        L.oracle_pcm16.restype = C.c_float
+        L.oracle_pcm16.argtypes = [C.c_void_p, C.c_long, C.c_void_p]
+        L.oracle_output_scale.restype = C.c_float
+        L.oracle_output_scale.argtypes = [C.c_void_p, C.c_long]
 
     def synthesize(self, voice, frames, control_rate=250.0, return_internal=False):
         frames = _f32(frames).reshape(-1, 16)
@@ -111,6 +115,13 @@ class Oracle:
             return out
         finally:
             self.lib.oracle_destroy(m)
+
+    def pcm16(self, audio):
+        """The reference's output stage on a raw output buffer: (int16 payload, normalisation scale)."""
+        x = _f32(audio)
+        out = np.empty(len(x), np.int16)
+        scale = self.lib.oracle_pcm16(x.ctypes.data, len(x), out.ctypes.data)
+        return out, float(scale)
 
     def synthesize_samples(self, voice, params):
         """Per-sample entry (setAllParameters + execSynthesisStep for every row of params)."""
@@ -203,6 +214,7 @@ class Reference:
         L.ref_wavetable.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
                                     C.c_void_p, C.c_void_p]
         L.ref_model0_constants.argtypes = [C.c_char_p, C.c_void_p]
+        L.ref_pcm16.argtypes = [C.c_void_p, C.c_long, C.c_float, C.c_void_p, C.POINTER(C.c_float)]
 
     def _take(self, p, n):
         out = np.ctypeslib.as_array(p, shape=(max(n.value, 1),))[:n.value].copy()
@@ -218,6 +230,15 @@ class Reference:
         if rc:
             raise RuntimeError(self.lib.ref_last_error().decode())
         return self._take(p, n)
+
+    def pcm16(self, audio, rate=48000.0):
+        """The reference's own writer (Controller::writeOutputToFile + WAVEFileWriter) on a raw output buffer."""
+        x = _f32(audio)
+        out = np.empty(len(x), np.int16)
+        scale = C.c_float()
+        if self.lib.ref_pcm16(x.ctypes.data, len(x), rate, out.ctypes.data, C.byref(scale)):
+            raise RuntimeError(self.lib.ref_last_error().decode())
+        return out, float(scale.value)
 
     def synthesize_samples(self, voice, params, model=0):
         params = _f32(params).reshape(-1, 16)

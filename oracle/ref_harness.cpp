@@ -43,6 +43,8 @@
 #include "SampleRateConverter.h"
 #include "WavetableGlottalSource.h"
 #include "WavetableGlottalSourceFIRFilter.h"
+#include "VTMUtil.h"
+#include "WAVEFileWriter.h"
 #undef private
 #undef protected
 
@@ -208,6 +210,38 @@ int ref_batch(const char* const* config_texts, int n_configs, double control_rat
 		auto w1 = std::chrono::steady_clock::now();
 		if (seconds) *seconds = std::chrono::duration<double>(w1 - w0).count();
 		return failed ? 1 : 0;
+	} catch (const std::exception& e) {
+		g_err = e.what();
+		return 1;
+	}
+}
+
+// The reference's own output stage on a raw output buffer: Controller::writeOutputToFile (Controller.cpp:315-328)
+// -- VTM::Util::calculateOutputScale + WAVEFileWriter::writeSample(sample * scale) -- into a temporary WAVE file,
+// whose 16-bit payload (after the 44-byte header, WAVEFileWriter.cpp:62-105) is read back.  Returns the scale.
+int ref_pcm16(const float* x, long n, float rate, short* out, float* scale_out)
+{
+	try {
+		char path[] = "/tmp/gtts_ref_wav_XXXXXX";
+		int fd = mkstemp(path);
+		if (fd < 0) throw std::runtime_error("mkstemp failed");
+		close(fd);
+		const std::vector<float> audioData(x, x + n);
+		float scale;
+		{
+			GS::WAVEFileWriter fileWriter(path, 1, audioData.size(), rate);
+			scale = GS::VTM::Util::calculateOutputScale(audioData);
+			for (std::size_t i = 0, end = audioData.size(); i < end; ++i) fileWriter.writeSample(audioData[i] * scale);
+		}
+		if (scale_out) *scale_out = scale;
+		FILE* f = std::fopen(path, "rb");
+		if (!f) { unlink(path); throw std::runtime_error("cannot reopen the WAVE file"); }
+		std::fseek(f, 44, SEEK_SET);
+		const size_t got = std::fread(out, sizeof(short), static_cast<size_t>(n), f);
+		std::fclose(f);
+		unlink(path);
+		if (got != static_cast<size_t>(n)) throw std::runtime_error("short WAVE payload");
+		return 0;
 	} catch (const std::exception& e) {
 		g_err = e.what();
 		return 1;

@@ -672,3 +672,30 @@ int oracle_constants(const oracle_voice* voice, double* out)
 	oracle_destroy(m);
 	return k;
 }
+
+/* ---- output stage: peak normalisation + 16-bit PCM ------------------------------------------------------------
+ * VTM::Util::maximumAbsoluteValue / calculateOutputScale (vtm/VTMUtil.h:115-127, vtm/VTMUtil.cpp:20-21, 48-57),
+ * Controller::writeOutputToFile (vtm_control_model/Controller.cpp:315-328: sample * scale in float),
+ * WAVEFileWriter::writeSample (WAVEFileWriter.cpp:36-37, 122-126: round(sample * 32767.0f) as int, low 16 bits). */
+float oracle_output_scale(const float* x, long n)
+{
+	float max_value = 0.0f;
+	for (long i = 0; i < n; i++) {
+		const float a = fabsf(x[i]);
+		if (a > max_value) max_value = a;
+	}
+	if (max_value < 1.0e-30f) return 0.0f;
+	return 0.95f / max_value;
+}
+
+float oracle_pcm16(const float* x, long n, short* out)
+{
+	const float scale = oracle_output_scale(x, n);
+	const float sample_scale = 32767.0f;           /* sampleScale_(INT16_MAX) */
+	for (long i = 0; i < n; i++) {
+		const float sample = x[i] * scale;
+		const int v = (int) roundf(sample * sample_scale);
+		out[i] = (short) (v & 0xffff);
+	}
+	return scale;
+}

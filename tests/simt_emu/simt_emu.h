@@ -101,6 +101,20 @@ inline void cta_barrier(int id, int count)
 	}
 }
 
+// bar.arrive: counts towards the barrier without waiting for it
+inline void cta_barrier_arrive(int id, int count)
+{
+	Cta& c = *g_cta;
+	auto& b = c.ctaBarriers[id];
+	b.first++;
+	if (b.first >= count) {
+		b.first = 0;
+		b.second++;
+		for (int t : c.ctaWaiters[id]) c.fibers[t].state = 0;
+		c.ctaWaiters[id].clear();
+	}
+}
+
 template<class T>
 inline T shfl(uint32_t mask, T v, int src)
 {

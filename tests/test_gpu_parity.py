@@ -182,6 +182,31 @@ def test_config2_full_batch_parity(synth, oracle):
     assert np.array_equal(outs[7], synth.synthesize(v, [tracks[7]])[0])
 
 
+def test_pcm16_output_stage_is_bit_exact(synth, oracle, golden, real_tracks):
+    # gtts_batch_run_host_pcm16: per-utterance peak normalisation + 16-bit PCM on the device.  For the float32 audio the
+    # GPU produced, the payload and the scale are the reference's own (oracle.pcm16 is pinned bit for bit against the
+    # reference's WAVEFileWriter in tests/test_oracle.py); against the reference's audio the payload differs by at
+    # most one LSB (the float32 audio itself agrees to 2e-7 of full scale).
+    v = default_voice("male")
+    tracks = [real_tracks[0], real_tracks[1][:1], real_tracks[1][100:163], real_tracks[0][:0], T.synthetic_track(5, 77),
+              np.zeros((3, 16), np.float32)]
+    audio = synth.synthesize(v, tracks)
+    pcm, scale = synth.synthesize_pcm16(v, tracks)
+    for a, p, s, tr in zip(audio, pcm, scale, tracks):
+        want, want_scale = oracle.pcm16(a)
+        assert len(p) == len(a)
+        assert np.array_equal(p, want)
+        assert s == np.float32(want_scale)
+        ref_pcm, _ = oracle.pcm16(oracle.synthesize(v, tr))
+        assert np.abs(p.astype(np.int32) - ref_pcm.astype(np.int32)).max(initial=0) <= 1
+    assert scale[3] == 0.0 and not pcm[3].any()                 # empty track: 63 zeros, scale 0
+    name = golden.names[1]
+    voice, track, ref, _ = golden.case(name)
+    p, s = synth.synthesize_pcm16(voice, [track])
+    ref_pcm, _ = oracle.pcm16(ref)
+    assert np.abs(p[0].astype(np.int32) - ref_pcm.astype(np.int32)).max() <= 1
+
+
 def test_general_kernel_golden_vectors(synth, golden, monkeypatch):
     # GTTS_KERNEL=v0 forces the general warp-per-utterance kernel (the one streaming uses) on batches
     monkeypatch.setenv("GTTS_KERNEL", "v0")

@@ -29,7 +29,7 @@ def main():
     txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(txt.splitlines()))
-    ranges = {f: func_ranges(os.path.join(ROOT, "gama_tts_b200", "csrc", f)) for f in ("tube_kernel_v1.cuh", "tube_kernel.cuh")}
+    ranges = {f: func_ranges(os.path.join(ROOT, "gama_tts_b200", "csrc", f)) for f in ("tube_kernel_v2.cuh", "tube_kernel_v1.cuh", "tube_kernel.cuh")}
     agg = collections.defaultdict(lambda: [0, 0])
     cur, hdr = None, None
 

@@ -15,7 +15,7 @@ def main():
     rep = sys.argv[1]
     txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"],
                          capture_output=True, text=True).stdout
-    ranges = {f: func_ranges(os.path.join(ROOT, "gama_tts_b200", "csrc", f)) for f in ("tube_kernel_v1.cuh", "tube_kernel.cuh")}
+    ranges = {f: func_ranges(os.path.join(ROOT, "gama_tts_b200", "csrc", f)) for f in ("tube_kernel_v2.cuh", "tube_kernel_v1.cuh", "tube_kernel.cuh")}
     by_fn, by_line, ideal_fn = collections.Counter(), collections.Counter(), collections.Counter()
     shfl = collections.Counter()
     cur = curline = hdr = None

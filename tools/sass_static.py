@@ -10,6 +10,7 @@ import sys
 import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+KERNEL = os.environ.get("KERNEL", "tube_kernel_v2")
 
 
 def func_ranges(path):
@@ -31,7 +32,7 @@ def main():
     subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, capture_output=True)
     cubin = max(glob.glob(os.path.join(tmp, "*.cubin")), key=os.path.getsize)
     dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout
-    ranges = {f: func_ranges(os.path.join(ROOT, "gama_tts_b200", "csrc", f)) for f in ("tube_kernel_v1.cuh", "tube_kernel.cuh")}
+    ranges = {f: func_ranges(os.path.join(ROOT, "gama_tts_b200", "csrc", f)) for f in ("tube_kernel_v2.cuh", "tube_kernel_v1.cuh", "tube_kernel.cuh")}
     counts = collections.Counter()
     lines = collections.Counter()
     lkey = None
@@ -50,11 +51,11 @@ def main():
                 if a <= l <= b:
                     key = f.replace("tube_kernel", "k").replace(".cuh", "") + ":" + name
             continue
-        if section and "tube_kernel_v1" in section and re.match(r"\s+/\*[0-9a-f]{4,5}\*/", line):
+        if section and KERNEL in section and re.match(r"\s+/\*[0-9a-f]{4,5}\*/", line):
             counts[key] += 1
             lines[lkey] += 1
     total = sum(counts.values())
-    print("tube_kernel_v1: %d SASS instructions, %.1f KB" % (total, total * 16 / 1024.0))
+    print("%s: %d SASS instructions, %.1f KB" % (KERNEL, total, total * 16 / 1024.0))
     for k, v in counts.most_common(24):
         print("  %-36s %5d" % (k, v))
     if "--lines" in sys.argv:
