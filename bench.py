@@ -13,8 +13,14 @@ is used only for the barrier and the max-over-ranks of the timings).
 
 value  = audio-seconds / wall-second with the control tracks already resident in HBM (CUDA events on
          the launching stream around K launches, max over ranks).
-e2e    = the same through gtts_batch_run_host: pinned HOST buffers in, H2D copy + kernel + D2H copy of
-         the float32 audio inside the timed region.
+e2e    = the same through the C ABI with pinned HOST buffers, every step's input transfer (the kernel
+         reads the frames in place over PCIe) and output transfer inside the timed region.  The output
+         is what the reference's pipeline ends in: the peak-normalised 16-bit PCM payload
+         (gtts_batch_submit_host_pcm16 / gtts_batch_wait on two alternating batches, so that one
+         step's payload travels while the next step is synthesised).  e2e.variants also gives the
+         float32 output (gtts_batch_run_host, the round-1 definition) and the unpipelined PCM call;
+         e2e.ceiling is the plain device->host copy rate measured on the same box (all ranks at once)
+         and what it allows for this payload.
 roofline: FP64 FMA pipe. achieved = algorithmic flops per launch (384 per internal sample + 106 per
          output sample) / launch duration; peak = the DFMA peak measured on this
          GPU by gtts_probe_fp64_peak just before the timed region.
@@ -66,7 +72,9 @@ def make_tracks(rank, n_utt, n_frames):
 
 def measured_traffic():
     """DRAM bytes per launch of the dominant kernel on this workload, from the committed ncu capture (or None)."""
-    path = os.path.join(ROOT, "profiles", "ncu_r01_traffic_bench.json")
+    path = os.path.join(ROOT, "profiles", "ncu_r02_traffic_bench.json")
+    if not os.path.exists(path):
+        path = os.path.join(ROOT, "profiles", "ncu_r01_traffic_bench.json")
     try:
         with open(path) as f:
             d = json.load(f)
@@ -190,6 +198,85 @@ def workload_config():
             "cache": "inputs (164 MB) + outputs (1.96 GB) per step exceed the 126 MB L2; no explicit flush"}
 
 
+def config34_leg(synth, rank, world, dist, barrier, max_over_ranks, peak, args):
+    """BASELINE config 3 (N = 1) / config 4 (N > 1): a FIXED batch -- the first --config3-utts utterances of the
+    65,536-utterance draw (log-uniform 250..5,000 frames, every utterance its own randomised voice) -- sharded by
+    utterance over the ranks with gtts_shard_plan (strong scaling: the batch does not grow with N).  Device-resident
+    timing, 3 warm-ups.  With N > 1, rank 0 also runs the whole batch on its one GPU and the per-utterance checksums
+    of the shards are compared with it (config 4: bitwise equal, no collective on the data path)."""
+    import torch
+    import gama_tts_b200 as g
+    from gama_tts_b200 import tracks as T
+    from gama_tts_b200.sharding import shard_utterances, utterance_cost
+    from gama_tts_b200.voices import random_voice
+    U = args.config3_utts
+    lengths = T.config3_lengths()[:U]
+    voices = [random_voice(np.random.Generator(np.random.PCG64(7 + u))) for u in range(U)]
+    uniq = [T.synthetic_track(7 + i, 5000) for i in range(128)]      # tracks cycle over 128 unique ones (host time)
+
+    def build(ids):
+        fo = np.zeros(len(ids) + 1, np.int64)
+        fo[1:] = np.cumsum(lengths[ids])
+        frames = np.empty((int(fo[-1]), 16), np.float32)
+        for k, u in enumerate(ids):
+            frames[fo[k]:fo[k + 1]] = uniq[u % 128][:lengths[u]]
+        b = synth.prepare([voices[u] for u in ids], fo, voice_index=np.arange(len(ids), dtype=np.int32))
+        return b, torch.from_numpy(frames).cuda()
+
+    def checksums(b, d_out):
+        sums = torch.zeros(max(b.n_utt, 1), dtype=torch.int64, device="cuda")
+        g.check(g.load().gtts_batch_checksum_device(b._h, d_out.data_ptr(), sums.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        return sums[:b.n_utt]
+
+    cost = utterance_cost(voices, np.arange(U), lengths)
+    shards = shard_utterances(cost, world)
+    mine = shards[rank]
+    b, d_frames = build(mine)
+    d_out = torch.empty(b.n_out_total, dtype=torch.float32, device="cuda")
+    s = torch.cuda.current_stream()
+    for _ in range(3):
+        b.run_device(d_frames.data_ptr(), d_out.data_ptr(), s.cuda_stream)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 3
+    e0.record(s)
+    for _ in range(reps):
+        b.run_device(d_frames.data_ptr(), d_out.data_ptr(), s.cuda_stream)
+    e1.record(s)
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1) / reps)
+    finite = bool(torch.isfinite(d_out[::1009]).all().item())
+    mine_sums = checksums(b, d_out)
+    n_internal = int(b.n_internal.sum())
+    n_samples = int(b.n_samples_total)
+    tot = torch.tensor([n_internal, n_samples], dtype=torch.int64, device="cuda")
+    bitwise = None
+    if dist is not None:
+        dist.all_reduce(tot)
+        allsums = torch.zeros(U, dtype=torch.int64, device="cuda")
+        allsums[torch.from_numpy(mine).cuda()] = mine_sums
+        dist.all_reduce(allsums)                   # every entry is contributed by exactly one rank
+        del d_out, d_frames
+        b.close()
+        if rank == 0:
+            bw, dfw = build(np.arange(U))
+            d_all = torch.empty(bw.n_out_total, dtype=torch.float32, device="cuda")
+            bw.run_device(dfw.data_ptr(), d_all.data_ptr(), s.cuda_stream)
+            bitwise = bool(torch.equal(checksums(bw, d_all), allsums))
+            bw.close()
+    n_internal, n_samples = int(tot[0]), int(tot[1])
+    audio = n_samples / 48000.0
+    flops = FLOP_PER_INTERNAL * n_internal + FLOP_PER_OUTPUT * n_samples
+    ach = flops / (ms * 1e-3) * 1e-12
+    return {"workload": "first %d utterances of the BASELINE config 3 draw (log-uniform 250..5000 frames, one randomised voice "
+                        "each), sharded by utterance over %d GPU(s) with gtts_shard_plan" % (U, world),
+            "utterances": U, "n_gpus": world, "scaling": "strong", "audio_seconds": audio, "ms": ms,
+            "value": audio / (ms * 1e-3), "unit": UNIT, "warmup": 3, "reps": reps, "finite": finite,
+            "roofline_frac": ach / (peak * world), "achieved_tflops": ach,
+            "config4_bitwise_equal": bitwise}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -197,6 +284,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-config3", action="store_true", help="skip the config 3 / 4 leg")
+    ap.add_argument("--config3-utts", type=int, default=16384)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -269,19 +358,60 @@ def main():
     barrier()
     ms_dev = max_over_ranks(e0.elapsed_time(e1) / args.steps)
 
-    # ---- end to end: pinned host buffers through the C ABI ------------------------------------------
-    for _ in range(min(args.warmup, 2)):
-        batch.run_host_ptr(h_frames.data_ptr(), h_out.data_ptr())
+    # ---- end to end: pinned host buffers through the C ABI ----------------------------------------------
+    def timed_host_loop(step_fn, drain_fn=None):
+        for i in range(min(args.warmup, 2)):
+            step_fn(i)
+        if drain_fn:
+            drain_fn()
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            step_fn(i)
+        if drain_fn:
+            drain_fn()
+        torch.cuda.synchronize()
+        ms_local = (time.perf_counter() - t0) * 1e3 / args.steps
+        barrier()
+        return max_over_ranks(ms_local)
+
+    # (a) float32 audio, synchronous call (round-1 definition)
+    ms_f32 = timed_host_loop(lambda i: batch.run_host_ptr(h_frames.data_ptr(), h_out.data_ptr()))
+    checksum = float(h_out[::4097].double().abs().sum())
+    del h_out
+    # (b) 16-bit PCM payload, synchronous call
+    h_pcm = [torch.empty(n_out, dtype=torch.int16).pin_memory() for _ in range(2)]
+    ms_pcm_sync = timed_host_loop(lambda i: batch.run_host_pcm16_ptr(h_frames.data_ptr(), h_pcm[0].data_ptr()))
+    # (c) 16-bit PCM payload, two batches in flight
+    batch2 = synth.prepare(voice, fo)
+    pair = [batch, batch2]
+
+    def pipelined_step(i):
+        b = pair[i & 1]
+        b.wait()                                   # its previous step (and the host buffer it wrote) is done
+        b.submit_host_pcm16_ptr(h_frames.data_ptr(), h_pcm[i & 1].data_ptr())
+
+    ms_pcm_pipe = timed_host_loop(pipelined_step, lambda: (pair[0].wait(), pair[1].wait()))
+    pcm_checksum = int(h_pcm[0][::4097].to(torch.int64).abs().sum())
+    ms_e2e = ms_pcm_pipe
+    # (d) the ceiling: plain device->host copies of the same payload size, all ranks at once
+    d_pcm_probe = torch.empty(n_out, dtype=torch.int16, device="cuda")
+    for _ in range(2):
+        h_pcm[1].copy_(d_pcm_probe, non_blocking=True)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        batch.run_host_ptr(h_frames.data_ptr(), h_out.data_ptr())
+    for _ in range(3):
+        h_pcm[1].copy_(d_pcm_probe, non_blocking=True)
     torch.cuda.synchronize()
-    ms_e2e_local = (time.perf_counter() - t0) * 1e3 / args.steps
+    ms_copy_local = (time.perf_counter() - t0) * 1e3 / 3
     barrier()
-    ms_e2e = max_over_ranks(ms_e2e_local)
+    ms_copy = max_over_ranks(ms_copy_local)
+    d2h_gbs = n_out * 2 / (ms_copy * 1e-3) * 1e-9
+    del d_pcm_probe
     clocks = sampler.stop() if sampler is not None else None
-    checksum = float(h_out[::4097].double().abs().sum())
+
+    # ---- BASELINE configs 3 / 4: a fixed slice of the 65,536-utterance draw, sharded over the ranks ---------
+    cfg34 = None if args.no_config3 else config34_leg(synth, rank, world, dist, barrier, max_over_ranks, peak, args)
 
     value = audio_seconds * world / (ms_dev * 1e-3)
     e2e_value = audio_seconds * world / (ms_e2e * 1e-3)
@@ -293,7 +423,20 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(),
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": int(frames_np.nbytes), "d2h_bytes_per_step": int(n_samples * 4)},
+                    "h2d_bytes_per_step": int(frames_np.nbytes), "d2h_bytes_per_step": int(n_samples * 2),
+                    "output": "peak-normalised 16-bit PCM payload (the reference's WAVE data), two batches in flight",
+                    "variants": {
+                        "float32_sync": {"value": audio_seconds * world / (ms_f32 * 1e-3), "ms_per_step": ms_f32,
+                                         "d2h_bytes_per_step": int(n_samples * 4)},
+                        "pcm16_sync": {"value": audio_seconds * world / (ms_pcm_sync * 1e-3), "ms_per_step": ms_pcm_sync,
+                                       "d2h_bytes_per_step": int(n_samples * 2)},
+                        "pcm16_pipelined": {"value": e2e_value, "ms_per_step": ms_e2e,
+                                            "d2h_bytes_per_step": int(n_samples * 2)}},
+                    "ceiling": {"d2h_gbs_per_gpu": d2h_gbs, "d2h_gbs_aggregate": d2h_gbs * world,
+                                "how": "torch copy_ of the payload size, device -> pinned host, all ranks at once, max over ranks",
+                                "value_at_ceiling": audio_seconds * world / (ms_copy * 1e-3),
+                                "frac_of_ceiling": ms_copy / ms_e2e},
+                    "pcm_checksum": pcm_checksum},
             "gpu_launches": launches,
             "roofline": {"bound": "fp64_fma", "achieved": achieved_tflops, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved_tflops / peak, "traffic": measured_traffic(), "peak_source": peak_src,
@@ -303,6 +446,8 @@ def main():
             "kernel": json.loads(synth.describe()),
             "checksum": checksum,
         }
+        if cfg34 is not None:
+            line["config3"] = cfg34
         if world == 1 and not args.no_cpu_baseline:
             threads = host_threads()
             n_sample = min(N_UTT, threads * 16)

@@ -14,6 +14,7 @@
 #include <limits>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/gtts_b200.h"
@@ -90,6 +91,25 @@ __global__ void utterance_peak_kernel(const float* audio, const UttDesc* utts, u
 	}
 }
 
+// Order-independent 64-bit checksum of one utterance's float32 audio (sum of bits_i * (2 i + 1) mod 2^64): what the
+// multi-GPU determinism checks compare instead of the audio itself (BASELINE config 4).
+__global__ void utterance_checksum_kernel(const float* audio, const UttDesc* utts, unsigned long long* sums)
+{
+	const UttDesc U = utts[blockIdx.x];
+	const unsigned* x = reinterpret_cast<const unsigned*>(audio + U.out_begin);
+	unsigned long long h = 0;
+	for (long long i = threadIdx.x; i < U.n_out; i += blockDim.x) h += (unsigned long long) x[i] * (unsigned long long) (2 * i + 1);
+	for (int d = 16; d > 0; d >>= 1) h += __shfl_xor_sync(0xffffffffu, h, d);
+	__shared__ unsigned long long warpSum[32];
+	if ((threadIdx.x & 31) == 0) warpSum[threadIdx.x >> 5] = h;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		unsigned long long t = 0;
+		for (unsigned w = 0; w < (blockDim.x >> 5); ++w) t += warpSum[w];
+		sums[blockIdx.x] = t + (unsigned long long) U.n_out;
+	}
+}
+
 __device__ __forceinline__ short pcm16_of(float x, float scale)
 {
 	const float sample = __fmul_rn(x, scale);
@@ -97,14 +117,17 @@ __device__ __forceinline__ short pcm16_of(float x, float scale)
 	return (short) (v & 0xffff);
 }
 
-__global__ void utterance_pcm16_kernel(const float* audio, const UttDesc* utts, const unsigned* peakBits, short* pcm, float* scaleOut)
+// `utts` gives where the float32 audio of an utterance lies, `dst` where its payload goes (the same layout for a
+// batch on one GPU; a shard of a multi-GPU batch keeps its audio compact on the device and writes the payload at the
+// utterance's place in the caller's buffer).
+__global__ void utterance_pcm16_kernel(const float* audio, const UttDesc* utts, const UttDesc* dst, const unsigned* peakBits, short* pcm, float* scaleOut)
 {
 	const UttDesc U = utts[blockIdx.x];
 	const float peak = __uint_as_float(peakBits[blockIdx.x]);
 	const float scale = (peak < 1.0e-30f) ? 0.0f : __fdiv_rn(0.95f, peak);
 	if (scaleOut != nullptr && threadIdx.x == 0) scaleOut[blockIdx.x] = scale;
 	const float* x = audio + U.out_begin;
-	short* o = pcm + U.out_begin;
+	short* o = pcm + dst[blockIdx.x].out_begin;
 	const long long n8 = U.n_out >> 3;
 	const float4* x4 = reinterpret_cast<const float4*>(x);
 	for (long long i = threadIdx.x; i < n8; i += blockDim.x) {
@@ -142,6 +165,8 @@ struct gtts_batch {
 	float* d_frames = nullptr;          // staging for run_host
 	float* d_out = nullptr;
 	short* d_pcm = nullptr;             // run_host_pcm16 staging
+	UttDesc* d_utts_local = nullptr;    // shard of a multi-GPU batch: the same utterances laid out compactly (device-side audio of the PCM path)
+	int64_t local_out_total = 0;
 	unsigned* d_peak = nullptr;         // per-utterance max |sample| (float bits)
 	float* d_scale = nullptr;           // per-utterance normalisation scale
 	int64_t cap_frames = 0, cap_out = 0, cap_pcm = 0;
@@ -167,8 +192,9 @@ struct gtts_stream {
 
 namespace {
 
-int launchBatch(gtts_batch* b, const float* dFrames, float* dOut, cudaStream_t stream)
+int launchBatch(gtts_batch* b, const float* dFrames, float* dOut, cudaStream_t stream, const UttDesc* dUtts = nullptr)
 {
+	if (!dUtts) dUtts = b->d_utts;
 	const int64_t nUtt = static_cast<int64_t>(b->plan.utts.size());
 	b->last_launches = 0;
 	if (nUtt == 0) return GTTS_OK;
@@ -183,7 +209,7 @@ int launchBatch(gtts_batch* b, const float* dFrames, float* dOut, cudaStream_t s
 		v2::KernelParamsV2 Q;
 		Q.voices = b->d_voices;
 		Q.tables = b->d_tables;
-		Q.utts = b->d_utts;
+		Q.utts = dUtts;
 		Q.order = b->d_order;
 		Q.frames = dFrames;
 		Q.out = dOut;
@@ -245,7 +271,7 @@ int launchBatch(gtts_batch* b, const float* dFrames, float* dOut, cudaStream_t s
 		v1::KernelParamsV1 Q;
 		Q.voices = b->d_voices;
 		Q.tables = b->d_tables;
-		Q.utts = b->d_utts;
+		Q.utts = dUtts;
 		Q.order = b->d_order;
 		Q.frames = dFrames;
 		Q.out = dOut;
@@ -264,7 +290,7 @@ int launchBatch(gtts_batch* b, const float* dFrames, float* dOut, cudaStream_t s
 	if (nGeneral > 0) {
 		KernelParams P;
 		P.voices = b->d_voices;
-		P.utts = b->d_utts;
+		P.utts = dUtts;
 		P.order = b->d_order + nFast;
 		P.frames = dFrames;
 		P.out = dOut;
@@ -667,14 +693,15 @@ int gtts_batch_run_host(gtts_batch* b, const float* h_frames, float* h_out)
 
 namespace {
 // the output stage after the synthesis kernels, same stream
-int launchPcm16(gtts_batch* b, const float* dAudio, short* dPcm, float* dScale, cudaStream_t stream)
+int launchPcm16(gtts_batch* b, const float* dAudio, short* dPcm, float* dScale, cudaStream_t stream, const UttDesc* dUttsAudio = nullptr)
 {
 	const int nUtt = static_cast<int>(b->plan.utts.size());
 	if (nUtt == 0) return GTTS_OK;
+	if (!dUttsAudio) dUttsAudio = b->d_utts;
 	if (!b->d_peak) GTTS_CUDA(cudaMalloc(&b->d_peak, sizeof(unsigned) * nUtt));
-	utterance_peak_kernel<<<nUtt, 256, 0, stream>>>(dAudio, b->d_utts, b->d_peak);
+	utterance_peak_kernel<<<nUtt, 256, 0, stream>>>(dAudio, dUttsAudio, b->d_peak);
 	GTTS_CUDA(cudaGetLastError());
-	utterance_pcm16_kernel<<<nUtt, 256, 0, stream>>>(dAudio, b->d_utts, b->d_peak, dPcm, dScale);
+	utterance_pcm16_kernel<<<nUtt, 256, 0, stream>>>(dAudio, dUttsAudio, b->d_utts, b->d_peak, dPcm, dScale);
 	GTTS_CUDA(cudaGetLastError());
 	b->last_launches += 2;
 	return GTTS_OK;
@@ -689,6 +716,17 @@ int gtts_batch_run_device_pcm16(gtts_batch* b, const float* d_frames, float* d_a
 	const int rc = launchBatch(b, d_frames, d_audio, stream);
 	if (rc != GTTS_OK) return rc;
 	return launchPcm16(b, d_audio, reinterpret_cast<short*>(d_pcm), d_scale, stream);
+}
+
+int gtts_batch_checksum_device(gtts_batch* b, const float* d_audio, uint64_t* d_sums, void* cuda_stream)
+{
+	if (!b || (!b->plan.utts.empty() && (!d_audio || !d_sums))) return fail(GTTS_ERR_INVALID, "null argument");
+	if (b->plan.utts.empty()) return GTTS_OK;
+	GTTS_CUDA(cudaSetDevice(b->h->device));
+	utterance_checksum_kernel<<<static_cast<int>(b->plan.utts.size()), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+			d_audio, b->d_utts, reinterpret_cast<unsigned long long*>(d_sums));
+	GTTS_CUDA(cudaGetLastError());
+	return GTTS_OK;
 }
 
 int gtts_batch_wait(gtts_batch* b)
@@ -716,23 +754,19 @@ int gtts_batch_submit_host_pcm16(gtts_batch* b, const float* h_frames, int16_t* 
 	if ((nFrames > 0 && !h_frames) || (nOut > 0 && !h_pcm)) return fail(GTTS_ERR_INVALID, "null host buffer");
 	if (nUtt == 0) return GTTS_OK;
 	GTTS_CUDA(cudaSetDevice(b->h->device));
-	// frames: pinned host memory is read in place by the kernel, pageable memory is copied first (see run_host)
+	// frames: always copied to the device first (copy engine, 3 ms for BASELINE config 2).  Reading pinned frames in
+	// place, as gtts_batch_run_host does, would compete with the payload of another batch travelling the other way
+	// at the same time: the kernel's reads then starve behind the DMA stream (measured: kernel 26 -> 50 ms).
 	const float* dFrames = nullptr;
 	if (nFrames > 0) {
-		cudaPointerAttributes attr;
-		if (cudaPointerGetAttributes(&attr, h_frames) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer) {
-			dFrames = static_cast<const float*>(attr.devicePointer);
-		} else {
-			cudaGetLastError();
-			if (nFrames > b->cap_frames) {
-				if (b->d_frames) cudaFree(b->d_frames);
-				b->d_frames = nullptr; b->cap_frames = 0;
-				GTTS_CUDA(cudaMalloc(&b->d_frames, sizeof(float) * kNumParams * nFrames));
-				b->cap_frames = nFrames;
-			}
-			GTTS_CUDA(cudaMemcpyAsync(b->d_frames, h_frames, sizeof(float) * kNumParams * nFrames, cudaMemcpyHostToDevice, b->stream));
-			dFrames = b->d_frames;
+		if (nFrames > b->cap_frames) {
+			if (b->d_frames) cudaFree(b->d_frames);
+			b->d_frames = nullptr; b->cap_frames = 0;
+			GTTS_CUDA(cudaMalloc(&b->d_frames, sizeof(float) * kNumParams * nFrames));
+			b->cap_frames = nFrames;
 		}
+		GTTS_CUDA(cudaMemcpyAsync(b->d_frames, h_frames, sizeof(float) * kNumParams * nFrames, cudaMemcpyHostToDevice, b->stream));
+		dFrames = b->d_frames;
 	}
 	// The float32 audio stays in device memory: the scale of an utterance needs all of it.  Only the 16-bit payload
 	// (half the bytes of the float32 path) and, if asked for, the scales travel to the host.
@@ -772,7 +806,7 @@ void gtts_batch_free(gtts_batch* b)
 	if (b->stream) { cudaStreamSynchronize(b->stream); cudaStreamDestroy(b->stream); }
 	cudaFree(b->d_voices); cudaFree(b->d_utts); cudaFree(b->d_order); cudaFree(b->d_queue);
 	cudaFree(b->d_states); cudaFree(b->d_frames); cudaFree(b->d_out); cudaFree(b->d_tables);
-	cudaFree(b->d_pcm); cudaFree(b->d_peak); cudaFree(b->d_scale);
+	cudaFree(b->d_pcm); cudaFree(b->d_peak); cudaFree(b->d_scale); cudaFree(b->d_utts_local);
 	delete b;
 }
 
@@ -930,6 +964,240 @@ void gtts_stream_close(gtts_stream* s)
 	if (!s) return;
 	gtts_batch_free(s->batch);
 	delete s;
+}
+
+// ---- one batch over several GPUs (BASELINE config 4) ------------------------------------------
+// Utterances are independent, so the batch is partitioned by utterance (gtts_shard_plan on internal + output samples),
+// every GPU gets its own gtts_batch over ITS utterances -- whose frames and audio stay where they are in the caller's
+// packed arrays -- and gtts_multi_batch_run_host drives the GPUs from one host thread each.  No collective, no
+// inter-GPU traffic: the result is, utterance by utterance, what one GPU produces.
+
+struct gtts_multi {
+	std::vector<gtts_handle*> handles;
+};
+
+struct gtts_multi_batch {
+	gtts_multi* m = nullptr;
+	BatchPlan plan;                       // the whole batch: layout, lengths
+	std::vector<gtts_batch*> shards;      // one per GPU (nullptr: no utterance)
+	std::vector<int32_t> shard_of;
+	std::string error;
+};
+
+int gtts_multi_create(const int32_t* devices, int32_t n_devices, gtts_multi** multi_out)
+{
+	if (!devices || n_devices <= 0 || !multi_out) return fail(GTTS_ERR_INVALID, "bad device list");
+	*multi_out = nullptr;
+	try {
+		gtts_multi* m = new gtts_multi;
+		for (int32_t i = 0; i < n_devices; ++i) {
+			gtts_handle* h = nullptr;
+			const int rc = gtts_create(devices[i], &h);
+			if (rc != GTTS_OK) {
+				for (gtts_handle* g : m->handles) gtts_destroy(g);
+				delete m;
+				return rc;
+			}
+			m->handles.push_back(h);
+		}
+		*multi_out = m;
+		return GTTS_OK;
+	} catch (const std::bad_alloc&) {
+		return fail(GTTS_ERR_NOMEM, "out of host memory in gtts_multi_create");
+	}
+}
+
+void gtts_multi_destroy(gtts_multi* m)
+{
+	if (!m) return;
+	for (gtts_handle* h : m->handles) gtts_destroy(h);
+	delete m;
+}
+
+int32_t gtts_multi_device_count(const gtts_multi* m) { return m ? static_cast<int32_t>(m->handles.size()) : 0; }
+
+void gtts_multi_batch_free(gtts_multi_batch* b)
+{
+	if (!b) return;
+	for (gtts_batch* s : b->shards) gtts_batch_free(s);
+	delete b;
+}
+
+int gtts_multi_batch_prepare(gtts_multi* m, const gtts_voice_config* voices, int32_t n_voices,
+			const int32_t* voice_index, double control_rate, const int32_t* steps_override,
+			const int64_t* frame_offsets, int64_t n_utt, gtts_multi_batch** batch_out)
+{
+	if (!m || !batch_out) return fail(GTTS_ERR_INVALID, "null argument");
+	*batch_out = nullptr;
+	if (n_utt > std::numeric_limits<int32_t>::max()) return fail(GTTS_ERR_INVALID, "too many utterances");
+	gtts_multi_batch* b = nullptr;
+	try {
+		b = new gtts_multi_batch;
+		b->m = m;
+		int err = GTTS_OK;
+		const std::string msg = planBatch(voices, n_voices, voice_index, control_rate, steps_override, frame_offsets, n_utt, b->plan, &err);
+		if (err != GTTS_OK) { delete b; return fail(err, msg); }
+		const int nDev = static_cast<int>(m->handles.size());
+		std::vector<int64_t> cost(static_cast<size_t>(n_utt));
+		for (int64_t u = 0; u < n_utt; ++u) cost[u] = b->plan.utts[u].n_internal + b->plan.utts[u].n_out + 1;
+		b->shard_of.assign(static_cast<size_t>(n_utt), 0);
+		if (n_utt > 0) shardPlan(cost.data(), n_utt, nDev, b->shard_of.data());
+		b->shards.assign(nDev, nullptr);
+		for (int g = 0; g < nDev; ++g) {
+			gtts_batch* sb = new gtts_batch;
+			sb->h = m->handles[g];
+			sb->plan.voices = b->plan.voices;
+			for (int64_t u = 0; u < n_utt; ++u) if (b->shard_of[u] == g) sb->plan.utts.push_back(b->plan.utts[u]);   // global frame_begin / out_begin kept
+			sb->plan.out_offsets = b->plan.out_offsets;              // sizes of the caller's buffers
+			sb->plan.n_frames_total = b->plan.n_frames_total;
+			sb->plan.order.resize(sb->plan.utts.size());
+			for (size_t i = 0; i < sb->plan.order.size(); ++i) sb->plan.order[i] = static_cast<int32_t>(i);
+			std::stable_sort(sb->plan.order.begin(), sb->plan.order.end(), [&](int32_t x, int32_t y) {
+				return sb->plan.utts[x].n_internal > sb->plan.utts[y].n_internal;
+			});
+			b->shards[g] = sb;
+			int rc = uploadPlan(sb);
+			if (rc != GTTS_OK) { gtts_multi_batch_free(b); return rc; }
+			// the same utterances laid out compactly: where the shard keeps its float32 audio on the device (PCM path)
+			std::vector<UttDesc> local = sb->plan.utts;
+			int64_t off = 0;
+			for (UttDesc& d : local) { d.out_begin = off; off = (off + d.n_out + 63) & ~int64_t(63); }
+			sb->local_out_total = off;
+			if (!local.empty()) {
+				cudaError_t ce = cudaMalloc(&sb->d_utts_local, sizeof(UttDesc) * local.size());
+				if (ce == cudaSuccess) ce = cudaMemcpyAsync(sb->d_utts_local, local.data(), sizeof(UttDesc) * local.size(), cudaMemcpyHostToDevice, sb->stream);
+				if (ce == cudaSuccess) ce = cudaStreamSynchronize(sb->stream);
+				if (ce != cudaSuccess) { gtts_multi_batch_free(b); return failCuda(ce, "shard layout"); }
+			}
+		}
+	} catch (const std::bad_alloc&) {
+		gtts_multi_batch_free(b);
+		return fail(GTTS_ERR_NOMEM, "out of host memory while planning the batch");
+	} catch (const std::exception& e) {
+		gtts_multi_batch_free(b);
+		return fail(GTTS_ERR_INVALID, e.what());
+	}
+	*batch_out = b;
+	return GTTS_OK;
+}
+
+int gtts_multi_batch_layout(const gtts_multi_batch* b, int64_t* out_offsets, int64_t* n_out, int32_t* shard_of)
+{
+	if (!b) return fail(GTTS_ERR_INVALID, "null batch");
+	if (out_offsets) std::copy(b->plan.out_offsets.begin(), b->plan.out_offsets.end(), out_offsets);
+	if (n_out) for (size_t u = 0; u < b->plan.utts.size(); ++u) n_out[u] = b->plan.utts[u].n_out;
+	if (shard_of) std::copy(b->shard_of.begin(), b->shard_of.end(), shard_of);
+	return GTTS_OK;
+}
+
+namespace {
+// pins a pageable host range for the duration of a call (the shards read frames / write audio in place)
+struct ScopedPin {
+	void* p = nullptr;
+	bool mine = false;
+	int pin(const void* ptr, size_t bytes)
+	{
+		if (!ptr || bytes == 0) return GTTS_OK;
+		cudaPointerAttributes attr;
+		if (cudaPointerGetAttributes(&attr, ptr) == cudaSuccess && attr.type == cudaMemoryTypeHost) return GTTS_OK;
+		cudaGetLastError();
+		const cudaError_t e = cudaHostRegister(const_cast<void*>(ptr), bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
+		if (e != cudaSuccess) return failCuda(e, "cudaHostRegister");
+		p = const_cast<void*>(ptr);
+		mine = true;
+		return GTTS_OK;
+	}
+	~ScopedPin() { if (mine) cudaHostUnregister(p); }
+};
+} // namespace
+
+// One shard's PCM path: synthesis into a compact device buffer, then the output stage stores the payload straight
+// into the caller's (pinned, mapped) buffer at the utterances' own places.
+static int shardRunPcm16(gtts_batch* sb, const float* h_frames, int16_t* h_pcm, float* h_scale)
+{
+	GTTS_CUDA(cudaSetDevice(sb->h->device));
+	cudaPointerAttributes fa, pa;
+	if (cudaPointerGetAttributes(&fa, h_frames) != cudaSuccess || fa.type != cudaMemoryTypeHost || !fa.devicePointer ||
+	    cudaPointerGetAttributes(&pa, h_pcm) != cudaSuccess || pa.type != cudaMemoryTypeHost || !pa.devicePointer) {
+		cudaGetLastError();
+		return fail(GTTS_ERR_CUDA, "host buffers are not mapped into the device address space");
+	}
+	const int64_t nUtt = static_cast<int64_t>(sb->plan.utts.size());
+	if (sb->local_out_total > sb->cap_out) {
+		if (sb->d_out) cudaFree(sb->d_out);
+		sb->d_out = nullptr; sb->cap_out = 0;
+		GTTS_CUDA(cudaMalloc(&sb->d_out, sizeof(float) * sb->local_out_total));
+		sb->cap_out = sb->local_out_total;
+	}
+	if (h_scale && !sb->d_scale) GTTS_CUDA(cudaMalloc(&sb->d_scale, sizeof(float) * nUtt));
+	int rc = launchBatch(sb, static_cast<const float*>(fa.devicePointer), sb->d_out, sb->stream, sb->d_utts_local);
+	if (rc != GTTS_OK) return rc;
+	rc = launchPcm16(sb, sb->d_out, static_cast<short*>(pa.devicePointer), h_scale ? sb->d_scale : nullptr, sb->stream, sb->d_utts_local);
+	if (rc != GTTS_OK) return rc;
+	if (h_scale) GTTS_CUDA(cudaMemcpyAsync(h_scale, sb->d_scale, sizeof(float) * nUtt, cudaMemcpyDeviceToHost, sb->stream));
+	GTTS_CUDA(cudaStreamSynchronize(sb->stream));
+	return GTTS_OK;
+}
+
+// pcm == nullptr: float32 audio into h_out; else the 16-bit payload into pcm (and the scales into h_scale if not null)
+static int multiRun(gtts_multi_batch* b, const float* h_frames, float* h_out, int16_t* h_pcm, float* h_scale)
+{
+	if (!b) return fail(GTTS_ERR_INVALID, "null batch");
+	const int64_t nFrames = b->plan.n_frames_total;
+	const int64_t nOut = b->plan.out_offsets.empty() ? 0 : b->plan.out_offsets.back();
+	if ((nFrames > 0 && !h_frames) || (nOut > 0 && !h_out && !h_pcm)) return fail(GTTS_ERR_INVALID, "null host buffer");
+	ScopedPin pinFrames, pinOut;
+	int rc = pinFrames.pin(h_frames, sizeof(float) * kNumParams * static_cast<size_t>(nFrames));
+	if (rc != GTTS_OK) return rc;
+	if (h_pcm) rc = pinOut.pin(h_pcm, sizeof(int16_t) * static_cast<size_t>(nOut));
+	else rc = pinOut.pin(h_out, sizeof(float) * static_cast<size_t>(nOut));
+	if (rc != GTTS_OK) return rc;
+	const size_t nDev = b->shards.size();
+	std::vector<int> codes(nDev, GTTS_OK);
+	std::vector<std::string> texts(nDev);
+	std::vector<std::thread> pool;
+	// per-utterance scales come back in shard order: gather them into the caller's order afterwards
+	std::vector<std::vector<float>> shardScale(nDev);
+	for (size_t g = 0; g < nDev; ++g) {
+		gtts_batch* sb = b->shards[g];
+		if (!sb || sb->plan.utts.empty()) continue;
+		if (h_pcm && h_scale) shardScale[g].resize(sb->plan.utts.size());
+		pool.emplace_back([=, &codes, &texts, &shardScale]() {
+			int r;
+			if (h_pcm) r = shardRunPcm16(sb, h_frames, h_pcm, shardScale[g].empty() ? nullptr : shardScale[g].data());
+			else r = gtts_batch_run_host(sb, h_frames, h_out);
+			codes[g] = r;
+			if (r != GTTS_OK) texts[g] = gtts_last_error();
+		});
+	}
+	for (std::thread& t : pool) t.join();
+	for (size_t g = 0; g < nDev; ++g) if (codes[g] != GTTS_OK) return fail(codes[g], "GPU " + std::to_string(g) + ": " + texts[g]);
+	if (h_pcm && h_scale) {
+		std::vector<size_t> next(nDev, 0);
+		for (size_t u = 0; u < b->shard_of.size(); ++u) {
+			const size_t g = static_cast<size_t>(b->shard_of[u]);
+			h_scale[u] = shardScale[g][next[g]++];
+		}
+	}
+	return GTTS_OK;
+}
+
+int gtts_multi_batch_run_host(gtts_multi_batch* b, const float* h_frames, float* h_out)
+{
+	try {
+		return multiRun(b, h_frames, h_out, nullptr, nullptr);
+	} catch (const std::exception& e) {
+		return fail(GTTS_ERR_NOMEM, e.what());
+	}
+}
+
+int gtts_multi_batch_run_host_pcm16(gtts_multi_batch* b, const float* h_frames, int16_t* h_pcm, float* h_scale)
+{
+	try {
+		return multiRun(b, h_frames, nullptr, h_pcm, h_scale);
+	} catch (const std::exception& e) {
+		return fail(GTTS_ERR_NOMEM, e.what());
+	}
 }
 
 } // extern "C"

@@ -160,6 +160,9 @@ int gtts_batch_run_host_pcm16(gtts_batch* batch, const float* h_frames, int16_t*
  * instead of their sum.  The host buffers must stay valid (and, to overlap, be pinned) until the wait returns. */
 int gtts_batch_submit_host_pcm16(gtts_batch* batch, const float* h_frames, int16_t* h_pcm, float* h_scale);
 int gtts_batch_wait(gtts_batch* batch);
+/* Order-independent 64-bit checksum per utterance of float32 audio in device memory (batch layout): what the
+ * multi-GPU determinism checks of BASELINE config 4 compare instead of the audio. d_sums[n_utt] is device memory. */
+int gtts_batch_checksum_device(gtts_batch* batch, const float* d_audio, uint64_t* d_sums, void* cuda_stream);
 /* Number of kernel launches the last run issued (for bench.py's gpu_launches claim). */
 int gtts_batch_last_launches(const gtts_batch* batch, int32_t* n_out);
 void gtts_batch_free(gtts_batch* batch);
@@ -174,6 +177,26 @@ int gtts_batch_synthesize(gtts_handle* handle, const gtts_voice_config* voices, 
 			const int32_t* voice_index, double control_rate, const float* frames,
 			const int64_t* frame_offsets, int64_t n_utt, float* out, int64_t out_capacity,
 			int64_t* out_offsets);
+
+/* ---- one batch over the GPUs of a box (BASELINE config 4) ------------------------------------------------
+ * The batch is partitioned by utterance (gtts_shard_plan on internal + output samples); every GPU synthesises its
+ * utterances from / into the caller's ONE packed frame array and ONE output buffer (utterance u at out_offsets[u],
+ * as in gtts_batch_layout), driven by one host thread per GPU.  No collective and no inter-GPU traffic: utterances are
+ * independent, and the result is bit for bit what a single GPU produces.  Host buffers
+ * should be pinned (they are read / written in place by all GPUs); pageable buffers are pinned for the call. */
+typedef struct gtts_multi gtts_multi;
+typedef struct gtts_multi_batch gtts_multi_batch;
+int gtts_multi_create(const int32_t* devices, int32_t n_devices, gtts_multi** multi_out);
+void gtts_multi_destroy(gtts_multi* multi);
+int32_t gtts_multi_device_count(const gtts_multi* multi);
+int gtts_multi_batch_prepare(gtts_multi* multi, const gtts_voice_config* voices, int32_t n_voices,
+			const int32_t* voice_index, double control_rate, const int32_t* steps_override,
+			const int64_t* frame_offsets, int64_t n_utt, gtts_multi_batch** batch_out);
+/* out_offsets[n_utt + 1], n_out[n_utt], shard_of[n_utt] (which GPU of the list got the utterance); any may be NULL */
+int gtts_multi_batch_layout(const gtts_multi_batch* batch, int64_t* out_offsets, int64_t* n_out, int32_t* shard_of);
+int gtts_multi_batch_run_host(gtts_multi_batch* batch, const float* h_frames, float* h_out);
+int gtts_multi_batch_run_host_pcm16(gtts_multi_batch* batch, const float* h_frames, int16_t* h_pcm, float* h_scale);
+void gtts_multi_batch_free(gtts_multi_batch* batch);
 
 /* ---- streaming (one utterance, control frame by control frame; BASELINE config 5) ------------------ */
 

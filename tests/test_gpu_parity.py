@@ -386,6 +386,32 @@ def test_loud_glottis_rise_segment_corruption(synth, oracle, monkeypatch):
     assert full_scale_error(synth.synthesize(v, [tr])[0], ref) <= TIGHT
 
 
+def test_multi_gpu_dispatch_through_the_c_abi(synth):
+    # gtts_multi_*: ONE call partitions the batch by utterance over the GPUs of the box (one host thread per GPU, no
+    # collective), every utterance's audio lands at its place in ONE caller buffer, bit for bit what one GPU gives
+    # (BASELINE config 4).  With one GPU the dispatcher is exercised with that GPU listed twice (two shards).
+    import torch
+    n_gpu = torch.cuda.device_count()
+    devices = list(range(n_gpu)) if n_gpu >= 2 else [0, 0]
+    rng = np.random.Generator(np.random.PCG64(45))
+    n = 300
+    voices = [default_voice("male"), default_voice("female"), random_voice(rng)]
+    vidx = rng.integers(0, 3, n)
+    tracks = [T.synthetic_track(4500 + i, int(rng.integers(0, 150))) for i in range(n)]
+    whole = synth.synthesize(voices, tracks, voice_index=vidx)
+    multi = g.MultiSynthesizer(devices)
+    outs, shard_of = multi.synthesize(voices, tracks, voice_index=vidx, return_shards=True)
+    assert set(shard_of.tolist()) == set(range(len(devices)))
+    for a, b in zip(whole, outs):
+        assert np.array_equal(a, b)
+    (pcm, scale), _ = multi.synthesize(voices, tracks, voice_index=vidx, pcm16=True, return_shards=True)
+    want_pcm, want_scale = synth.synthesize_pcm16(voices, tracks, voice_index=vidx)
+    for a, b in zip(want_pcm, pcm):
+        assert np.array_equal(a, b)
+    assert np.array_equal(scale, want_scale)
+    multi.close()
+
+
 def test_sharded_over_gpus_equals_one_gpu(synth):
     # BASELINE config 4: the batch partitioned by utterance over the GPUs of the box (no collective on the data
     # path) gives, utterance by utterance, the bits of the one-GPU run.  Needs >= 2 GPUs.
