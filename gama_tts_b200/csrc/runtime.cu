@@ -13,6 +13,7 @@
 #include <exception>
 #include <limits>
 #include <new>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -150,6 +151,8 @@ __global__ void utterance_pcm16_kernel(const float* audio, const UttDesc* utts, 
 struct gtts_handle {
 	int device = 0;
 	int sms = 0;
+	std::mutex order_lock;
+	cudaEvent_t last_output_stage = nullptr;   // end of the output stage of the batch submitted last (PCM path)
 	double2* d_src_tab = nullptr;
 	std::string description;
 };
@@ -171,6 +174,8 @@ struct gtts_batch {
 	float* d_scale = nullptr;           // per-utterance normalisation scale
 	int64_t cap_frames = 0, cap_out = 0, cap_pcm = 0;
 	cudaStream_t stream = nullptr;      // used by run_host
+	cudaStream_t stream_out = nullptr;  // highest priority: output stage + payload copy of the PCM path (see submit_host_pcm16)
+	cudaEvent_t ev_synth = nullptr;
 	int32_t last_launches = 0;
 	double* d_tables = nullptr;         // per-voice glottal wavetables (v1 kernel)
 	bool legacy_v1 = false;             // GTTS_KERNEL=v1: the barrier-per-iteration kernel instead of v2 (A/B measurements)
@@ -509,6 +514,7 @@ void gtts_destroy(gtts_handle* h)
 	if (!h) return;
 	cudaSetDevice(h->device);
 	if (h->d_src_tab) cudaFree(h->d_src_tab);
+	if (h->last_output_stage) cudaEventDestroy(h->last_output_stage);
 	delete h;
 }
 
@@ -735,6 +741,7 @@ int gtts_batch_wait(gtts_batch* b)
 	if (!b->stream) return GTTS_OK;
 	GTTS_CUDA(cudaSetDevice(b->h->device));
 	GTTS_CUDA(cudaStreamSynchronize(b->stream));
+	if (b->stream_out) GTTS_CUDA(cudaStreamSynchronize(b->stream_out));
 	return GTTS_OK;
 }
 
@@ -783,12 +790,31 @@ int gtts_batch_submit_host_pcm16(gtts_batch* b, const float* h_frames, int16_t* 
 		b->cap_pcm = nOut;
 	}
 	if (h_scale && !b->d_scale) GTTS_CUDA(cudaMalloc(&b->d_scale, sizeof(float) * nUtt));
+	// The output stage and the payload copy run on a stream of the highest priority: when the synthesis kernel of
+	// this batch ends, they get the SMs before the (already queued) synthesis kernel of another batch does -- its
+	// persistent CTAs fill the register file and would otherwise keep the output stage, and with it the copy, waiting
+	// until they have finished.
+	if (!b->stream_out) {
+		int lo = 0, hi = 0;
+		GTTS_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+		GTTS_CUDA(cudaStreamCreateWithPriority(&b->stream_out, cudaStreamNonBlocking, hi));
+		GTTS_CUDA(cudaEventCreateWithFlags(&b->ev_synth, cudaEventDisableTiming));
+	}
+	// ... and a synthesis kernel is ordered behind the output stage (not the copy) of the batch submitted before it:
+	// its CTAs become resident the moment the previous synthesis kernel's CTAs exit, i.e. before that batch's output
+	// stage is even runnable, and priorities do not preempt resident CTAs.
+	std::lock_guard<std::mutex> order(b->h->order_lock);
+	if (b->h->last_output_stage) GTTS_CUDA(cudaStreamWaitEvent(b->stream, b->h->last_output_stage, 0));
+	else GTTS_CUDA(cudaEventCreateWithFlags(&b->h->last_output_stage, cudaEventDisableTiming));
 	int rc = launchBatch(b, dFrames, b->d_out, b->stream);
 	if (rc != GTTS_OK) return rc;
-	rc = launchPcm16(b, b->d_out, b->d_pcm, h_scale ? b->d_scale : nullptr, b->stream);
+	GTTS_CUDA(cudaEventRecord(b->ev_synth, b->stream));
+	GTTS_CUDA(cudaStreamWaitEvent(b->stream_out, b->ev_synth, 0));
+	rc = launchPcm16(b, b->d_out, b->d_pcm, h_scale ? b->d_scale : nullptr, b->stream_out);
 	if (rc != GTTS_OK) return rc;
-	GTTS_CUDA(cudaMemcpyAsync(h_pcm, b->d_pcm, sizeof(short) * nOut, cudaMemcpyDeviceToHost, b->stream));
-	if (h_scale) GTTS_CUDA(cudaMemcpyAsync(h_scale, b->d_scale, sizeof(float) * nUtt, cudaMemcpyDeviceToHost, b->stream));
+	GTTS_CUDA(cudaEventRecord(b->h->last_output_stage, b->stream_out));
+	GTTS_CUDA(cudaMemcpyAsync(h_pcm, b->d_pcm, sizeof(short) * nOut, cudaMemcpyDeviceToHost, b->stream_out));
+	if (h_scale) GTTS_CUDA(cudaMemcpyAsync(h_scale, b->d_scale, sizeof(float) * nUtt, cudaMemcpyDeviceToHost, b->stream_out));
 	return GTTS_OK;
 }
 
@@ -803,6 +829,8 @@ void gtts_batch_free(gtts_batch* b)
 {
 	if (!b) return;
 	cudaSetDevice(b->h->device);
+	if (b->stream_out) { cudaStreamSynchronize(b->stream_out); cudaStreamDestroy(b->stream_out); }
+	if (b->ev_synth) cudaEventDestroy(b->ev_synth);
 	if (b->stream) { cudaStreamSynchronize(b->stream); cudaStreamDestroy(b->stream); }
 	cudaFree(b->d_voices); cudaFree(b->d_utts); cudaFree(b->d_order); cudaFree(b->d_queue);
 	cudaFree(b->d_states); cudaFree(b->d_frames); cudaFree(b->d_out); cudaFree(b->d_tables);

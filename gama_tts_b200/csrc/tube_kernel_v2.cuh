@@ -1306,12 +1306,22 @@ GTTS_DEV void tube_v2_cta_body(const KernelParamsV2& P, unsigned char* smem, int
 		GTTS_ROLE_LOOP2(kTypeCoef,
 			if (!(skip & 64)) walk_slot(&C->slot[slot], P, lane, p, wr);
 			if (!(skip & 2)) coef_task(&C->slot[slot], lane, p);
-			if (!(skip & 1) && !C->sched[p].src_shared && ((C->sched[p].src_mask >> slot) & 1)) src_slot_task(C, P, lane, slot, p);)
+			if (!(skip & 1) && slot == kSlots - 1 && !C->sched[p].src_shared && ((C->sched[p].src_mask >> slot) & 1)) src_slot_task(C, P, lane, slot, p);)
 	} else {
-		// the shared SRC tasks on two warps: windows of slots 0..3 | slots 3..6 with slot 3 left out (one instantiation)
+		// The SRC warps.  Slots in lockstep (one voice, equal lengths: the batch case): the shared SRC tasks, windows
+		// of slots 0..3 | slots 3..6 with slot 3 left out (one instantiation).  Otherwise every slot converts its own
+		// outputs: slots 0..2 | 3..5 here, slot 6 on its coefficient worker.
 		const int slot0 = role == kRoleSrcA ? 0 : 3;
 		const int keep = role == kRoleSrcA ? 0xf : 0xe;
-		GTTS_ROLE_LOOP2(kTypeSrc, if (!(skip & 1)) src_shared_group<4>(C, P, lane, slot0, keep, p);)
+		GTTS_ROLE_LOOP2(kTypeSrc,
+			if (!(skip & 1)) {
+				if (C->sched[p].src_shared) {
+					src_shared_group<4>(C, P, lane, slot0, keep, p);
+				} else {
+#pragma unroll 1
+					for (int q = slot0; q < slot0 + 3; ++q) if ((C->sched[p].src_mask >> q) & 1) src_slot_task(C, P, lane, q, p);
+				}
+			})
 	}
 }
 
