@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libgtts_b200.so")
+LIB_PATH = os.environ.get("GTTS_LIB_PATH") or os.path.join(HERE, "csrc", "libgtts_b200.so")   # GTTS_LIB_PATH: another build (tools/ab_build.sh)
 
 GTTS_OK, GTTS_ERR_INVALID, GTTS_ERR_CUDA, GTTS_ERR_NO_DEVICE, GTTS_ERR_NOMEM, GTTS_ERR_UNSUPPORTED = range(6)
 

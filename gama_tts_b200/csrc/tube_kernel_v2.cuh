@@ -136,6 +136,15 @@ struct KernelParamsV2 {
 	long long* prof;              // development builds only (-DGTTS_ROLE_PROFILE): [grid][2 * kWarps + 1]
 };
 
+// slots whose per-slot SRC (slots not in lockstep) runs on the two SRC warps; the rest on their coefficient workers
+#ifndef GTTS_SRC_OWN0
+#define GTTS_SRC_OWN0 4
+#endif
+
+#ifndef GTTS_SRC1_UNROLL
+#define GTTS_SRC1_UNROLL 1
+#endif
+
 #ifdef GTTS_EXPERIMENTS
 #define GTTS_SKIP_BITS2(P) const int skip = (P).debug_skip
 #else
@@ -755,8 +764,11 @@ GTTS_DEV void src_task(CtaSm* C, const KernelParamsV2& P, int lane, int slot0, i
 	double accA[NS], accB[NS];
 #pragma unroll
 	for (int q = 0; q < NS; ++q) { accA[q] = 0.0; accB[q] = 0.0; }
+	// one slot: the loop is a chain of load -> coefficient -> accumulate; unrolled, the loads of several positions are
+	// in flight together (with several slots the accumulators of one position are independent work enough)
+	constexpr int kUnroll = NS == 1 ? GTTS_SRC1_UNROLL : 1;
 	// left wings: window positions 12 .. 0
-#pragma unroll 1
+#pragma unroll kUnroll
 	for (int t = 0; t < kSrcZeroCrossings; ++t) {
 		const double2 ca = pLa[256 * t], cb = pLb[256 * t];
 		const double cca = ca.x + (ca.y * iLa), ccb = cb.x + (cb.y * iLb);
@@ -780,7 +792,7 @@ GTTS_DEV void src_task(CtaSm* C, const KernelParamsV2& P, int lane, int slot0, i
 	}
 	// right wings: window positions 14 .. 26
 	pRb -= 256 * dl;
-#pragma unroll 1
+#pragma unroll kUnroll
 	for (int t = 1; t <= kSrcZeroCrossings; ++t) {
 		const double2 ca = pRa[256 * t], cb = pRb[256 * t];
 		const double cca = ca.x + (ca.y * iRa), ccb = cb.x + (cb.y * iRb);
@@ -1306,20 +1318,21 @@ GTTS_DEV void tube_v2_cta_body(const KernelParamsV2& P, unsigned char* smem, int
 		GTTS_ROLE_LOOP2(kTypeCoef,
 			if (!(skip & 64)) walk_slot(&C->slot[slot], P, lane, p, wr);
 			if (!(skip & 2)) coef_task(&C->slot[slot], lane, p);
-			if (!(skip & 1) && slot == kSlots - 1 && !C->sched[p].src_shared && ((C->sched[p].src_mask >> slot) & 1)) src_slot_task(C, P, lane, slot, p);)
+			if (!(skip & 1) && slot >= GTTS_SRC_OWN0 && !C->sched[p].src_shared && ((C->sched[p].src_mask >> slot) & 1)) src_slot_task(C, P, lane, slot, p);)
 	} else {
 		// The SRC warps.  Slots in lockstep (one voice, equal lengths: the batch case): the shared SRC tasks, windows
 		// of slots 0..3 | slots 3..6 with slot 3 left out (one instantiation).  Otherwise every slot converts its own
-		// outputs: slots 0..2 | 3..5 here, slot 6 on its coefficient worker.
+		// outputs: the first GTTS_SRC_OWN0 slots here (half each), the others on their coefficient workers.
 		const int slot0 = role == kRoleSrcA ? 0 : 3;
 		const int keep = role == kRoleSrcA ? 0xf : 0xe;
+		const int own0 = role == kRoleSrcA ? 0 : GTTS_SRC_OWN0 / 2, own1 = role == kRoleSrcA ? GTTS_SRC_OWN0 / 2 : GTTS_SRC_OWN0;
 		GTTS_ROLE_LOOP2(kTypeSrc,
 			if (!(skip & 1)) {
 				if (C->sched[p].src_shared) {
 					src_shared_group<4>(C, P, lane, slot0, keep, p);
 				} else {
 #pragma unroll 1
-					for (int q = slot0; q < slot0 + 3; ++q) if ((C->sched[p].src_mask >> q) & 1) src_slot_task(C, P, lane, q, p);
+					for (int q = own0; q < own1; ++q) if ((C->sched[p].src_mask >> q) & 1) src_slot_task(C, P, lane, q, p);
 				}
 			})
 	}
