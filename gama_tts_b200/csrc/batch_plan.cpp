@@ -46,6 +46,7 @@ std::string planBatch(const gtts_voice_config* voices, int32_t nVoices, const in
 		d.out_begin = plan.out_offsets[u];
 		d.flags = 0;
 		d.state_index = -1;
+		d.n_in_base = 0;
 		// every utterance starts on a 64-sample (256-byte) boundary of the output buffer: the kernel then
 		// writes whole aligned row pairs (see src_rows in tube_kernel_v2.cuh)
 		plan.out_offsets[u + 1] = (plan.out_offsets[u] + d.n_out + 63) & ~int64_t(63);
@@ -59,6 +60,35 @@ std::string planBatch(const gtts_voice_config* voices, int32_t nVoices, const in
 	});
 	*err = GTTS_OK;
 	return std::string();
+}
+
+int64_t streamSamplesReady(int64_t period0, int64_t have, int32_t steps, int64_t nInDone, int32_t block)
+{
+	if (have < 2) return 0;
+	const int64_t avail = (period0 + have - 1) * steps - nInDone;
+	return avail > 0 ? ((avail - 1) / block) * block : 0;
+}
+
+int64_t streamOutputsAfter(const VoiceDev& v, int64_t nIn, bool flush)
+{
+	if (flush) return outputLength(v, nIn);
+	if (nIn == 0) return 0;
+	return static_cast<int64_t>(((static_cast<unsigned __int128>(nIn) << 16) + v.src_inc - 1) / v.src_inc);
+}
+
+UttDesc streamChunkDesc(const UttDesc& base, int64_t nAvail, int64_t nSamples, int64_t nInDone, int64_t nOutDone,
+			int64_t outputsAfter, bool flush)
+{
+	UttDesc d = base;
+	d.frame_begin = 0;
+	d.n_frames = nAvail;
+	d.n_internal = nSamples;
+	d.n_in_base = nInDone;
+	d.out_begin = -nOutDone;              // the kernel indexes outputs absolutely; staging index = k - nOutDone
+	d.n_out = outputsAfter;
+	d.flags = 1 | (flush ? 0 : 2);
+	d.state_index = 0;
+	return d;
 }
 
 void lcgMultipliers(unsigned long long* out32)

@@ -25,6 +25,18 @@ std::string planBatch(const gtts_voice_config* voices, int32_t nVoices, const in
 			double controlRate, const int32_t* stepsOverride, const int64_t* frameOffsets,
 			int64_t nUtt, BatchPlan& plan, int* err);
 
+// ---- streaming on the pipelined kernel: chunk planning (pure host logic, shared with the emulated tests) ----------
+// A stream is synthesised in chunks of whole 32-sample blocks; the frame window handed to the kernel starts at the
+// control period `period0` that contains the first sample of the chunk.
+// Samples that can be synthesised now: the control periods whose end frame is known (`have` frames in the window),
+// in whole blocks, leaving at least one sample for the final chunk.
+int64_t streamSamplesReady(int64_t period0, int64_t have, int32_t steps, int64_t nInDone, int32_t block);
+// Outputs complete after nIn internal samples (flush: the whole utterance, SampleRateConverter.h:462-471).
+int64_t streamOutputsAfter(const VoiceDev& v, int64_t nIn, bool flush);
+// The descriptor of a chunk of nSamples internal samples over a window of nAvail frames.
+UttDesc streamChunkDesc(const UttDesc& base, int64_t nAvail, int64_t nSamples, int64_t nInDone, int64_t nOutDone,
+			int64_t outputsAfter, bool flush);
+
 // 377^(j+1) mod 2^44, j = 0..31: jump-ahead multipliers of the noise generator
 // (reference NoiseSource.h:40-44 is exactly this LCG on the 2^-44 grid).
 void lcgMultipliers(unsigned long long* out32);

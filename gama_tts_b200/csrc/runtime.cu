@@ -193,6 +193,18 @@ struct gtts_stream {
 	std::vector<float> pending;         // frames not yet consumed as a period start (<= 1 after a push)
 	int64_t n_in_done = 0, n_out_done = 0;
 	bool finished = false;
+	// fast path (pipelined kernel, control periods of at least one block): whole 32-sample blocks per chunk, every
+	// role's state in d_state between chunks, frames / descriptor / audio through mapped pinned staging buffers,
+	// one graph launch (counter reset + kernel) per chunk
+	bool fast = false;
+	int64_t period0 = 0;                // control period of pending[0]
+	UttStateV2* d_state = nullptr;
+	float* m_frames = nullptr;          // mapped pinned: the frame window the kernel reads
+	UttDesc* m_utt = nullptr;           // mapped pinned: the chunk's descriptor
+	float* m_out = nullptr;             // mapped pinned: the chunk's audio
+	int64_t cap_frames = 0, cap_out = 0;
+	cudaGraph_t graph = nullptr;
+	cudaGraphExec_t graph_exec = nullptr;
 };
 
 namespace {
@@ -223,6 +235,7 @@ int launchBatch(gtts_batch* b, const float* dFrames, float* dOut, cudaStream_t s
 		Q.n_utt = nFast;
 		Q.prof = nullptr;
 		Q.debug_skip = 0;
+		Q.states = nullptr;
 		const int64_t ctasWanted = (static_cast<int64_t>(nFast) + v2::kSlots - 1) / v2::kSlots;
 		const int grid = static_cast<int>(std::min<int64_t>(ctasWanted, b->h->sms));
 #ifdef GTTS_EXPERIMENTS
@@ -488,6 +501,8 @@ int createHandle(int32_t device, gtts_handle** handle_out)
 	    (ce = cudaFuncSetAttribute(v1::tube_kernel_v1, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	                               (int) v1::smem_bytes())) != cudaSuccess ||
 	    (ce = cudaFuncSetAttribute(v2::tube_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                               (int) v2::smem_bytes())) != cudaSuccess ||
+	    (ce = cudaFuncSetAttribute(v2::tube_kernel_v2_stream, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	                               (int) v2::smem_bytes())) != cudaSuccess) {
 		if (h->d_src_tab) cudaFree(h->d_src_tab);
 		delete h;
@@ -858,6 +873,8 @@ int gtts_batch_synthesize(gtts_handle* h, const gtts_voice_config* voices, int32
 
 // ---- streaming ----------------------------------------------------------------------------------------
 
+namespace { void streamFreeFast(gtts_stream* s); }
+
 int gtts_stream_open(gtts_handle* h, const gtts_voice_config* voice, double control_rate,
 			int32_t steps_override, gtts_stream** stream_out)
 {
@@ -874,10 +891,25 @@ int gtts_stream_open(gtts_handle* h, const gtts_voice_config* voice, double cont
 	if (rc != GTTS_OK) { delete s; return rc; }
 	s->vdev = s->batch->plan.voices[0];
 	s->steps = s->batch->plan.utts[0].steps;
+	// control periods of at least one block run on the pipelined kernel (whole blocks per chunk), shorter ones on the
+	// general kernel (whole control periods per chunk); GTTS_KERNEL=v0 forces the latter
+	s->fast = s->steps >= kBlock;
+	if (const char* env = std::getenv("GTTS_KERNEL")) { if (std::strcmp(env, "v0") == 0 || std::strcmp(env, "v1") == 0) s->fast = false; }
 	// the state is cleared on the stream every chunk of this utterance runs on (stream-ordered before the first kernel)
-	cudaError_t e = cudaMalloc(&s->batch->d_states, sizeof(UttState));
-	if (e == cudaSuccess) e = cudaMemsetAsync(s->batch->d_states, 0, sizeof(UttState), s->batch->stream);
-	if (e != cudaSuccess) { gtts_batch_free(s->batch); delete s; return failCuda(e, "gtts_stream_open"); }
+	cudaError_t e;
+	if (s->fast) {
+		std::vector<double> table(kTableLen);
+		buildWavetable(s->vdev, table.data());
+		e = cudaMalloc(&s->d_state, sizeof(UttStateV2));
+		if (e == cudaSuccess) e = cudaMemsetAsync(s->d_state, 0, sizeof(UttStateV2), s->batch->stream);
+		if (e == cudaSuccess && !s->batch->d_tables) e = cudaMalloc(&s->batch->d_tables, sizeof(double) * kTableLen);
+		if (e == cudaSuccess) e = cudaMemcpyAsync(s->batch->d_tables, table.data(), sizeof(double) * kTableLen, cudaMemcpyHostToDevice, s->batch->stream);
+		if (e == cudaSuccess) e = cudaStreamSynchronize(s->batch->stream);
+	} else {
+		e = cudaMalloc(&s->batch->d_states, sizeof(UttState));
+		if (e == cudaSuccess) e = cudaMemsetAsync(s->batch->d_states, 0, sizeof(UttState), s->batch->stream);
+	}
+	if (e != cudaSuccess) { streamFreeFast(s); gtts_batch_free(s->batch); delete s; return failCuda(e, "gtts_stream_open"); }
 	*stream_out = s;
 	return GTTS_OK;
 }
@@ -885,6 +917,89 @@ int gtts_stream_open(gtts_handle* h, const gtts_voice_config* voice, double cont
 namespace {
 
 // Runs `periods` control periods over the first `periods` (+1 if lookahead) pending frames.
+void streamFreeFast(gtts_stream* s)
+{
+	if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
+	if (s->graph) cudaGraphDestroy(s->graph);
+	s->graph_exec = nullptr; s->graph = nullptr;
+	cudaFree(s->d_state); s->d_state = nullptr;
+	cudaFreeHost(s->m_frames); cudaFreeHost(s->m_utt); cudaFreeHost(s->m_out);
+	s->m_frames = nullptr; s->m_utt = nullptr; s->m_out = nullptr;
+	s->cap_frames = s->cap_out = 0;
+}
+
+// (Re)captures the per-chunk work -- work-counter reset + kernel on the staging buffers -- into a graph.
+int streamBuildGraph(gtts_stream* s)
+{
+	gtts_batch* b = s->batch;
+	if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
+	if (s->graph) { cudaGraphDestroy(s->graph); s->graph = nullptr; }
+	v2::KernelParamsV2 Q;
+	Q.voices = b->d_voices;
+	Q.tables = b->d_tables;
+	GTTS_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(const_cast<UttDesc**>(&Q.utts)), s->m_utt, 0));
+	Q.order = b->d_order;
+	GTTS_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(const_cast<float**>(&Q.frames)), s->m_frames, 0));
+	GTTS_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&Q.out), s->m_out, 0));
+	Q.src_tab = s->h->d_src_tab;
+	Q.queue = b->d_queue;
+	Q.n_utt = 1;
+	Q.states = s->d_state;
+	Q.prof = nullptr;
+	Q.debug_skip = 0;
+	GTTS_CUDA(cudaStreamBeginCapture(b->stream, cudaStreamCaptureModeThreadLocal));
+	cudaError_t e = cudaMemsetAsync(b->d_queue, 0, 2 * sizeof(int32_t), b->stream);
+	if (e == cudaSuccess) {
+		v2::tube_kernel_v2_stream<<<1, v2::kThreads, v2::smem_bytes(), b->stream>>>(Q);
+		e = cudaGetLastError();
+	}
+	cudaError_t e2 = cudaStreamEndCapture(b->stream, &s->graph);
+	if (e != cudaSuccess) return failCuda(e, "stream graph capture");
+	GTTS_CUDA(e2);
+	GTTS_CUDA(cudaGraphInstantiate(&s->graph_exec, s->graph, 0));
+	return GTTS_OK;
+}
+
+// Fast path: synthesises `nSamples` internal samples (whole blocks unless `flush`) from the frame window in
+// s->pending, which starts at control period s->period0.
+int streamChunkFast(gtts_stream* s, int64_t nSamples, bool flush, float* out, int64_t cap, int64_t* written)
+{
+	gtts_batch* b = s->batch;
+	const int64_t nAvail = static_cast<int64_t>(s->pending.size()) / kNumParams;
+	const int64_t nInAfter = s->n_in_done + nSamples;
+	const int64_t kAfter = streamOutputsAfter(s->vdev, nInAfter, flush);
+	const int64_t produced = kAfter - s->n_out_done;
+	if (produced > cap) return fail(GTTS_ERR_INVALID, "stream output buffer too small");
+	GTTS_CUDA(cudaSetDevice(s->h->device));
+	bool rebuild = s->graph_exec == nullptr;
+	if (nAvail > s->cap_frames) {
+		cudaFreeHost(s->m_frames); s->m_frames = nullptr; s->cap_frames = 0;
+		const int64_t want = std::max<int64_t>(2 * nAvail, 256);
+		GTTS_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&s->m_frames), sizeof(float) * kNumParams * want, cudaHostAllocMapped));
+		s->cap_frames = want;
+		rebuild = true;
+	}
+	if (produced + 64 > s->cap_out) {
+		cudaFreeHost(s->m_out); s->m_out = nullptr; s->cap_out = 0;
+		const int64_t want = std::max<int64_t>(2 * (produced + 64), 16384);
+		GTTS_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&s->m_out), sizeof(float) * want, cudaHostAllocMapped));
+		s->cap_out = want;
+		rebuild = true;
+	}
+	if (!s->m_utt) GTTS_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&s->m_utt), sizeof(UttDesc), cudaHostAllocMapped));
+	if (rebuild) { const int rc = streamBuildGraph(s); if (rc != GTTS_OK) return rc; }
+	if (nSamples == 0 && !flush) { if (written) *written = 0; return GTTS_OK; }
+	std::memcpy(s->m_frames, s->pending.data(), sizeof(float) * kNumParams * nAvail);
+	*s->m_utt = streamChunkDesc(b->plan.utts[0], nAvail, nSamples, s->n_in_done, s->n_out_done, kAfter, flush);
+	GTTS_CUDA(cudaGraphLaunch(s->graph_exec, b->stream));
+	GTTS_CUDA(cudaStreamSynchronize(b->stream));
+	if (produced > 0) std::memcpy(out, s->m_out, sizeof(float) * produced);
+	s->n_in_done = nInAfter;
+	s->n_out_done = kAfter;
+	if (written) *written = produced;
+	return GTTS_OK;
+}
+
 int streamChunk(gtts_stream* s, int64_t periods, bool lookahead, bool flush, float* out, int64_t cap, int64_t* written)
 {
 	gtts_batch* b = s->batch;
@@ -956,6 +1071,17 @@ int gtts_stream_push_frames(gtts_stream* s, const float* frames, int64_t n_frame
 	}
 	const int64_t have = static_cast<int64_t>(s->pending.size()) / kNumParams;
 	if (have < 2) return GTTS_OK;
+	if (s->fast) {
+		// the control periods whose end frame is known, in whole blocks; at least one sample is always left for finish()
+		const int64_t nSamples = streamSamplesReady(s->period0, have, s->steps, s->n_in_done, kBlock);
+		if (nSamples == 0) return GTTS_OK;
+		const int rc = streamChunkFast(s, nSamples, false, out, out_capacity, n_written);
+		if (rc != GTTS_OK) { s->pending.resize(before); return rc; }
+		const int64_t p0 = s->n_in_done / s->steps;                // the period the next chunk starts in
+		s->pending.erase(s->pending.begin(), s->pending.begin() + (p0 - s->period0) * kNumParams);
+		s->period0 = p0;
+		return GTTS_OK;
+	}
 	const int rc = streamChunk(s, have - 1, true, false, out, out_capacity, n_written);
 	if (rc != GTTS_OK) { s->pending.resize(before); return rc; }
 	s->pending.erase(s->pending.begin(), s->pending.begin() + (have - 1) * kNumParams);
@@ -968,7 +1094,14 @@ int gtts_stream_finish(gtts_stream* s, float* out, int64_t out_capacity, int64_t
 	if (s->finished) return fail(GTTS_ERR_INVALID, "stream already finished; call gtts_stream_reset");
 	if (n_written) *n_written = 0;
 	const int64_t have = static_cast<int64_t>(s->pending.size()) / kNumParams;
-	const int rc = streamChunk(s, have, false, true, out, out_capacity, n_written);
+	int rc;
+	if (s->fast) {
+		// everything that is left, the last control period (the duplicated last frame, Controller.cpp:283) included
+		const int64_t total = (s->period0 + have) * s->steps;
+		rc = streamChunkFast(s, have > 0 ? total - s->n_in_done : 0, true, out, out_capacity, n_written);
+	} else {
+		rc = streamChunk(s, have, false, true, out, out_capacity, n_written);
+	}
 	if (rc != GTTS_OK) return rc;
 	s->pending.clear();
 	s->finished = true;
@@ -979,8 +1112,10 @@ int gtts_stream_reset(gtts_stream* s)
 {
 	if (!s) return fail(GTTS_ERR_INVALID, "null argument");
 	GTTS_CUDA(cudaSetDevice(s->h->device));
-	GTTS_CUDA(cudaMemsetAsync(s->batch->d_states, 0, sizeof(UttState), s->batch->stream));
+	if (s->fast) GTTS_CUDA(cudaMemsetAsync(s->d_state, 0, sizeof(UttStateV2), s->batch->stream));
+	else GTTS_CUDA(cudaMemsetAsync(s->batch->d_states, 0, sizeof(UttState), s->batch->stream));
 	s->pending.clear();
+	s->period0 = 0;
 	s->n_in_done = 0;
 	s->n_out_done = 0;
 	s->finished = false;
@@ -990,6 +1125,9 @@ int gtts_stream_reset(gtts_stream* s)
 void gtts_stream_close(gtts_stream* s)
 {
 	if (!s) return;
+	cudaSetDevice(s->h->device);
+	if (s->batch && s->batch->stream) cudaStreamSynchronize(s->batch->stream);
+	streamFreeFast(s);
 	gtts_batch_free(s->batch);
 	delete s;
 }

@@ -105,7 +105,7 @@ struct SlotSm {
 		long long eq;
 		unsigned erem, eQ, eR, inc;
 	} ctl[2];
-	int     pad_[5];              // slot stride = 16 mod 128 bytes: the 7 slots start in different banks
+	int     pad_[1];              // slot stride = 16 mod 128 bytes: the 7 slots start in different banks
 };
 static_assert(sizeof(SlotSm) % 128 == 16, "slot stride should be 16 mod 128 bytes (bank spreading); adjust pad_");
 

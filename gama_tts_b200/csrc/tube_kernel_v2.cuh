@@ -104,7 +104,7 @@ struct SlotSm {
 		long long eq;
 		unsigned erem, eQ, eR, inc;
 	} ctl[kCtlRing];
-	int     pad_[22];             // slot stride = 16 mod 128 bytes: the 7 slots start in different banks
+	int     pad_[14];             // slot stride = 16 mod 128 bytes: the 7 slots start in different banks
 };
 static_assert(sizeof(SlotSm) % 128 == 16, "slot stride should be 16 mod 128 bytes (the chains read one 16-byte word per slot and lane); adjust pad_");
 
@@ -132,6 +132,7 @@ struct KernelParamsV2 {
 	const double2* src_tab;
 	int32_t* queue;
 	int32_t n_utt;
+	UttStateV2* states;           // streaming: per-utterance state between chunks (UttDesc::state_index), else nullptr
 	int32_t debug_skip;           // development builds only (-DGTTS_EXPERIMENTS)
 	long long* prof;              // development builds only (-DGTTS_ROLE_PROFILE): [grid][2 * kWarps + 1]
 };
@@ -299,6 +300,20 @@ GTTS_DEV void sched_signal(CtaSm* C, int lane, int n)
 	if (lane == 0) st_release_shared(&C->done[kCtrSched], n);
 }
 
+// Streaming (gtts_stream_*): an utterance arrives in chunks of whole control periods.  A chunk runs like a short
+// utterance -- every pipeline stage sees every block of it, so all roles end at the same sample -- except that each
+// role starts from the state it saved at the end of the previous chunk (UttDesc::flags bit 0) and, unless it is the
+// last one (bit 1), the SRC is not flushed.  Sample and output indices are absolute (UttDesc::n_in_base, out_begin =
+// destination - outputs produced so far).
+// ST: the kernel is instantiated twice; the batch kernel (ST = false) carries none of the state handling.
+template<bool ST>
+GTTS_DEV UttStateV2* chunk_state(const KernelParamsV2& P, const UttDesc& U)
+{
+	if (!ST) return nullptr;
+	return (P.states != nullptr && U.state_index >= 0) ? &P.states[U.state_index] : nullptr;
+}
+GTTS_DEV bool chunk_resumes(const UttStateV2* st, const UttDesc& U) { return st != nullptr && (U.flags & 1) != 0 && st->started != 0; }
+
 GTTS_DEV int block_len(const SlotSm::Ctl& k, int b)
 {
 	return b == k.nblocks - 1 ? k.last_len : kBlock;
@@ -389,6 +404,7 @@ GTTS_DEV void walk_block(const float* frames, long long nFrames, int steps, floa
 }
 
 // The slot's sixteen walks (lanes 0..15 = parameters): parameter 0 of block it, 1..6 of block it - 2, 7..15 of block it - 3.
+template<bool ST>
 GTTS_DEV void walk_slot(SlotSm* S, const KernelParamsV2& P, int lane, int p, WalkRegs& w)
 {
 	const int param = lane & 15;
@@ -397,10 +413,20 @@ GTTS_DEV void walk_slot(SlotSm* S, const KernelParamsV2& P, int lane, int p, Wal
 	const int b = K.it - stage;
 	const bool active = lane < 16 && K.it >= 0 && b >= 0 && b < K.nblocks;
 	const float* frames = P.frames + K.U.frame_begin * kNumParams;
-	if (active && b == 0) cursor_init(frames, K.U.n_frames, K.U.inv_steps, param, w);
+	UttStateV2* st = chunk_state<ST>(P, K.U);
+	if (active && b == 0) {
+		cursor_init(frames, K.U.n_frames, K.U.inv_steps, param, w);
+		if (chunk_resumes(st, K.U)) {
+			// a chunk of a stream starts inside the control period of its first frame: the accumulated value comes
+			// from the previous chunk, the position in the period from the sample count
+			w.cur = st->walk_cur[param];
+			w.off = (int) (K.U.n_in_base % K.U.steps);
+		}
+	}
 	const int nb = active ? block_len(K, b) : kBlock;
 	float* row = param < 7 ? S->cur[b & 1][param] : S->pscr[b & 1][param - 7];
 	walk_block(frames, K.U.n_frames, active ? K.U.steps : kBlock, K.U.inv_steps, param, nb, w, row, active);
+	if (active && st != nullptr && b == K.nblocks - 1) st->walk_cur[param] = w.cur;
 }
 
 // ---- slot helper: stage 1 (f0) and stage 3 (source) ------------------------------------------------------------
@@ -431,6 +457,7 @@ GTTS_DEV_NOINLINE int rise_segment_scan(int mine, int lane, int carried)
 	return mine < carried ? mine : carried;
 }
 
+template<bool ST>
 GTTS_DEV void helper_iteration(SlotSm* S, const KernelParamsV2& P, int lane, HelperRegs& h, int p)
 {
 	const SlotSm::Ctl& K = S->ctl[p];
@@ -447,11 +474,19 @@ GTTS_DEV void helper_iteration(SlotSm* S, const KernelParamsV2& P, int lane, Hel
 		}
 	}
 	if (b3 < 0 || b3 >= K.nblocks) return;
+	UttStateV2* st = chunk_state<ST>(P, K.U);
 	if (b3 == 0) {
-		// new utterance: clear the oscillator history, reset the noise generator and the caches
-		if (lane < 24) S->vw[lane] = make_double2(0.0, 0.0);
-		h.lcg = c_lcg_init; h.noise_x1 = 0.0;
-		h.low = kNoLowMark;
+		// new utterance: clear the oscillator history, reset the noise generator and the caches (a chunk of a
+		// stream: take them over from the previous chunk)
+		if (chunk_resumes(st, K.U)) {
+			if (lane < 24) S->vw[lane] = make_double2(st->vw[lane][0], st->vw[lane][1]);
+			h.lcg = st->lcg; h.noise_x1 = st->noise_x1;
+			h.low = st->table_low;
+		} else {
+			if (lane < 24) S->vw[lane] = make_double2(0.0, 0.0);
+			h.lcg = c_lcg_init; h.noise_x1 = 0.0;
+			h.low = kNoLowMark;
+		}
 		h.c_p1 = h.c_p2 = h.c_p3 = h.c_p5 = h.c_p6 = __int_as_float(0x7fc00000);     // NaN: nothing cached
 		__syncwarp();
 	}
@@ -627,6 +662,12 @@ GTTS_DEV void helper_iteration(SlotSm* S, const KernelParamsV2& P, int lane, Hel
 		S->in[b3 % 3][lane] = (pulse + (ah1 * sig)) * 0.125;
 		S->thr[b3 & 3][lane] = pulse * 0.125;
 	}
+	if (st != nullptr && b3 == K.nblocks - 1) {
+		// end of a chunk (whole blocks): what the next chunk starts from
+		__syncwarp();
+		if (lane < 24) { st->vw[lane][0] = S->vw[lane].x; st->vw[lane][1] = S->vw[lane].y; }
+		if (lane == 0) { st->lcg = h.lcg; st->noise_x1 = h.noise_x1; st->table_low = h.low; st->started = 1; }
+	}
 }
 
 // ---- coefficient worker: junction coefficients of block it - 4 (VocalTractModel0.h:484-512, 698-716) ----------
@@ -716,7 +757,7 @@ GTTS_DEV void src_rows(SlotSm::Ctl& N, int b, long long e0, long long e1)
 {
 	const long long m = N.gran - 1;
 	const long long a = N.U.out_begin & m;
-	long long k0 = (b == 0) ? 0 : (b == N.nblocks - 2 ? e0 : ((e0 + a) & ~m) - a);
+	long long k0 = (b == 0 || b == N.nblocks - 2) ? e0 : ((e0 + a) & ~m) - a;     // e0 = 0 for a whole utterance, the outputs of the earlier chunks for a stream
 	long long k1;
 	if (b == N.nblocks - 1) {
 		k1 = N.U.n_out;                             // flush: chain B appended the 26 zeros
@@ -852,12 +893,16 @@ GTTS_DEV void src_slot_task(CtaSm* C, const KernelParamsV2& P, int lane, int slo
 // ---- chain A: oscillator phase of block it - 2, lane = slot (WavetableGlottalSource.h:196-199, 265-272) --------
 // Two half-sample increments per sample, wrap above 511; 42 dependent cycles per sample.  Lanes whose slot has no
 // such block run on dummy data (their results are never read), which keeps the loop free of divergent branches.
-GTTS_DEV void chain_a_iteration(CtaSm* C, int lane, double& posReg, int p)
+template<bool ST>
+GTTS_DEV void chain_a_iteration(CtaSm* C, const KernelParamsV2& P, int lane, double& posReg, int p)
 {
+	SlotSm* S = &C->slot[lane < kSlots ? lane : 0];
+	const SlotSm::Ctl& K = S->ctl[p];
+	const int b = K.it - kStPhase;
+	if (!__any_sync(0xffffffffu, lane < kSlots && K.it >= 0 && b >= 0 && b < K.nblocks)) return;
 	if (lane >= kSlots) return;
-	SlotSm* S = &C->slot[lane];
-	const int b = S->ctl[p].it - kStPhase;
-	if (b == 0) posReg = 0.0;
+	UttStateV2* st = chunk_state<ST>(P, K.U);
+	if (b == 0) posReg = chunk_resumes(st, K.U) ? st->pos : 0.0;
 	const int buf = b & 1;
 	const double2* osc = reinterpret_cast<const double2*>(S->osc[buf]);
 	double2* p0 = reinterpret_cast<double2*>(S->pos[buf][0]);
@@ -881,15 +926,23 @@ GTTS_DEV void chain_a_iteration(CtaSm* C, int lane, double& posReg, int p)
 		p1[j0] = make_double2(o1[0], o1[1]); p1[j0 + 1] = make_double2(o1[2], o1[3]);
 	}
 	posReg = pos;
+	if (st != nullptr && K.it >= 0 && b == K.nblocks - 1) st->pos = pos;
 }
 
 // ---- chain A2: frication bandpass of block it - 4 and the two tap signals, lane = slot (BandpassFilter.h:114-122)
-GTTS_DEV void chain_a2_iteration(CtaSm* C, int lane, BandpassState& st, int p)
+template<bool ST>
+GTTS_DEV void chain_a2_iteration(CtaSm* C, const KernelParamsV2& P, int lane, BandpassState& st, int p)
 {
+	SlotSm* S = &C->slot[lane < kSlots ? lane : 0];
+	const SlotSm::Ctl& K = S->ctl[p];
+	const int b = K.it - kStCoef;
+	if (!__any_sync(0xffffffffu, lane < kSlots && K.it >= 0 && b >= 0 && b < K.nblocks)) return;
 	if (lane >= kSlots) return;
-	SlotSm* S = &C->slot[lane];
-	const int b = S->ctl[p].it - kStCoef;
-	if (b == 0) { st.x1 = st.x2 = st.y1 = st.y2 = 0.0; }
+	UttStateV2* cs = chunk_state<ST>(P, K.U);
+	if (b == 0) {
+		if (chunk_resumes(cs, K.U)) { st.x1 = cs->bp[0]; st.x2 = cs->bp[1]; st.y1 = cs->bp[2]; st.y2 = cs->bp[3]; }
+		else { st.x1 = st.x2 = st.y1 = st.y2 = 0.0; }
+	}
 	const int buf = b & 1;
 	const double2* sig = reinterpret_cast<const double2*>(S->sig[buf]);
 	const double2* c0 = reinterpret_cast<const double2*>(S->bp[buf][0]);
@@ -919,6 +972,7 @@ GTTS_DEV void chain_a2_iteration(CtaSm* C, int lane, BandpassState& st, int p)
 	}
 	S->fric[buf] = anyFric ? 1 : 0;
 	st.x1 = x1; st.x2 = x2; st.y1 = y1; st.y2 = y2;
+	if (cs != nullptr && K.it >= 0 && b == K.nblocks - 1) { cs->bp[0] = x1; cs->bp[1] = x2; cs->bp[2] = y1; cs->bp[3] = y2; }
 }
 
 // ---- chain B: radiation filters + throat low-pass of block it - 6, lane = slot * 4 + filter ----------------------
@@ -929,15 +983,25 @@ GTTS_DEV void chain_a2_iteration(CtaSm* C, int lane, BandpassState& st, int p)
 // then the output sum (lane = sample) into the SRC ring, which this role also clears for a new utterance.
 struct ChainBRegs { double x1, y1; };
 
-GTTS_DEV void chain_b_iteration(CtaSm* C, int lane, ChainBRegs& r, int p)
+template<bool ST>
+GTTS_DEV void chain_b_iteration(CtaSm* C, const KernelParamsV2& P, int lane, ChainBRegs& r, int p)
 {
 	const int s = lane >> 2, f = lane & 3;
+	{
+		const SlotSm::Ctl& K0 = C->slot[s < kSlots ? s : 0].ctl[p];
+		const int b0 = K0.it - kStRad;
+		if (!__any_sync(0xffffffffu, s < kSlots && K0.it >= 0 && b0 >= 0 && b0 < K0.nblocks)) return;
+	}
 	if (s < kSlots && f < 3) {
 		SlotSm* S = &C->slot[s];
 		const SlotSm::Ctl& K = S->ctl[p];
 		const int b = K.it - kStRad;
 		const VoiceDev& V = S->V[K.vbuf];
-		if (b == 0) { r.x1 = 0.0; r.y1 = 0.0; }
+		UttStateV2* st = chunk_state<ST>(P, K.U);
+		if (b == 0) {
+			if (chunk_resumes(st, K.U)) { r.x1 = st->rad[f][0]; r.y1 = st->rad[f][1]; }
+			else { r.x1 = 0.0; r.y1 = 0.0; }
+		}
 		const double b0 = f == 0 ? V.rad_m : (f == 1 ? V.rad_n : V.throat_b0);
 		const double b1 = f == 0 ? -V.rad_m : (f == 1 ? -V.rad_n : 0.0);
 		const double a1 = f == 0 ? -V.rad_m : (f == 1 ? -V.rad_n : V.throat_a1);
@@ -965,6 +1029,7 @@ GTTS_DEV void chain_b_iteration(CtaSm* C, int lane, ChainBRegs& r, int p)
 			out[j0 + 1] = make_double2(o[2], o[3]);
 		}
 		r.x1 = x1; r.y1 = y1;
+		if (st != nullptr && K.it >= 0 && b == K.nblocks - 1) { st->rad[f][0] = x1; st->rad[f][1] = y1; }
 	}
 	__syncwarp();
 	// output sum, lane = sample: (mouth + nose) + throat (VocalTractModel0.h:657-660, 441)
@@ -974,24 +1039,31 @@ GTTS_DEV void chain_b_iteration(CtaSm* C, int lane, ChainBRegs& r, int p)
 		const SlotSm::Ctl& QK = Q->ctl[p];
 		const int qb = QK.it - kStRad;
 		if (QK.it < 0 || qb < 0 || qb >= QK.nblocks) continue;
+		UttStateV2* qs = chunk_state<ST>(P, QK.U);
 		if (qb == 0) {
-			// new utterance: inputs before the first one are zero (SampleRateConverter.h:98-115)
-			for (int i = lane; i < kXr; i += 32) Q->xring[i] = 0.0;
+			// new utterance: inputs before the first one are zero (SampleRateConverter.h:98-115); a chunk of a stream:
+			// the ring as the previous chunk left it
+			const bool resumes = chunk_resumes(qs, QK.U);
+			for (int i = lane; i < kXr; i += 32) Q->xring[i] = resumes ? qs->xring[i & (kSrcRing - 1)] : 0.0;
 			__syncwarp();
 		}
 		const int qn = block_len(QK, qb);
-		const long long n0 = (long long) qb * kBlock;
+		const long long n0 = QK.U.n_in_base + (long long) qb * kBlock;
 		if (lane < qn) {
 			const int idx = (int) ((n0 + lane) & (kSrcRing - 1));
 			const double v = (Q->rad[0][lane] + Q->rad[1][lane]) + Q->rad[2][lane];
 			Q->xring[idx] = v;
 			if (idx < kXr - kSrcRing) Q->xring[idx + kSrcRing] = v;
 		}
-		if (qb == QK.nblocks - 1 && lane < 2 * kSrcZeroCrossings) {
-			// flushBuffer(): 26 zeros after the last input (SampleRateConverter.h:462-471)
-			const int idx = (int) ((QK.U.n_internal + lane) & (kSrcRing - 1));
+		if (qb == QK.nblocks - 1 && (QK.U.flags & 2) == 0 && lane < 2 * kSrcZeroCrossings) {
+			// flushBuffer(): 26 zeros after the last input (SampleRateConverter.h:462-471); not between the chunks of a stream
+			const int idx = (int) ((QK.U.n_in_base + QK.U.n_internal + lane) & (kSrcRing - 1));
 			Q->xring[idx] = 0.0;
 			if (idx < kXr - kSrcRing) Q->xring[idx + kSrcRing] = 0.0;
+		}
+		if (qs != nullptr && qb == QK.nblocks - 1) {
+			__syncwarp();
+			for (int i = lane; i < kSrcRing; i += 32) qs->xring[i] = Q->xring[i];
 		}
 	}
 }
@@ -1018,7 +1090,8 @@ GTTS_DEV void chain_b_iteration(CtaSm* C, int lane, ChainBRegs& r, int p)
 // their block 0 arrives.
 struct TubeCell { double T, Bn, nb, last; };
 
-GTTS_DEV void tube_iteration(CtaSm* C, int warp, int lane, TubeCell& t, int p)
+template<bool ST>
+GTTS_DEV void tube_iteration(CtaSm* C, const KernelParamsV2& P, int warp, int lane, TubeCell& t, int p)
 {
 	const int u = lane >> 1;
 	const int sbit = lane & 1;
@@ -1028,9 +1101,14 @@ GTTS_DEV void tube_iteration(CtaSm* C, int warp, int lane, TubeCell& t, int p)
 	const int b = (slot < kSlots) ? K.it - kStTube : -1;
 	const bool hasBlock = slot < kSlots && K.it >= 0 && b >= 0 && b < K.nblocks;
 	const int buf = b & 1, b3 = (b % 3 + 3) % 3;
+	if (!__any_sync(0xffffffffu, hasBlock)) return;    // pipeline filling or draining (every iteration of a short stream chunk but a few)
 	const bool fricBlock = __any_sync(0xffffffffu, hasBlock && S->fric[buf] != 0);
 	const VoiceDev& V = S->V[K.vbuf];
-	if (b == 0) { t.T = t.Bn = t.nb = t.last = 0.0; }
+	UttStateV2* st = hasBlock ? chunk_state<ST>(P, K.U) : nullptr;
+	if (b == 0) {
+		if (hasBlock && chunk_resumes(st, K.U)) { t.T = st->tube[u][0]; t.Bn = st->tube[u][1]; t.nb = st->tube[u][2]; t.last = st->tube[u][3]; }
+		else { t.T = t.Bn = t.nb = t.last = 0.0; }
+	}
 	const double d = V.damping;
 	const bool is3 = u == 3, isEnd = (u == 9) || (u == 15), isGlot = u == 0, isN1 = u == 10;
 	const bool storesEnd = isEnd && slot < kSlots;     // the second group of the last warp is a dummy: it must not store
@@ -1101,6 +1179,7 @@ GTTS_DEV void tube_iteration(CtaSm* C, int warp, int lane, TubeCell& t, int p)
 		}
 	}
 	t.T = T; t.Bn = Bn; t.nb = nb; t.last = last;
+	if (st != nullptr && b == K.nblocks - 1) { st->tube[u][0] = T; st->tube[u][1] = Bn; st->tube[u][2] = nb; st->tube[u][3] = last; }
 }
 
 // ---- slot bookkeeping for iteration i + 1 (chain A warp, lane = slot) -------------------------------------------
@@ -1150,8 +1229,11 @@ GTTS_DEV void schedule_slots(CtaSm* C, const KernelParamsV2& P, int lane, int i,
 				N.gran = uinc <= 32768u ? 64 : 32;
 				N.eQ = (unsigned) (kBlock << 16) / uinc;
 				N.eR = (unsigned) (kBlock << 16) % uinc;
-				N.eq = 0;
-				N.erem = uinc - 1;
+				// e(0) = ceil(n_in_base 65536 / inc) as quotient / remainder of (n_in_base 65536 + inc - 1) / inc
+				// (0 and inc - 1 for a whole utterance)
+				const unsigned long long num = ((unsigned long long) U.n_in_base << 16) + uinc - 1;
+				N.eq = (long long) (num / uinc);
+				N.erem = (unsigned) (num % uinc);
 				it = 0;
 				fresh = 1; voice = U.voice; vbuf = N.vbuf;
 				break;
@@ -1248,6 +1330,7 @@ GTTS_DEV void schedule_slots(CtaSm* C, const KernelParamsV2& P, int lane, int i,
 		GTTS_PROF_STORE(P, role, lane);                                          \
 	}
 
+template<bool ST>
 GTTS_DEV void tube_v2_cta_body(const KernelParamsV2& P, unsigned char* smem, int tid)
 {
 	CtaSm* C = reinterpret_cast<CtaSm*>(smem);
@@ -1280,7 +1363,7 @@ GTTS_DEV void tube_v2_cta_body(const KernelParamsV2& P, unsigned char* smem, int
 	GTTS_SKIP_BITS2(P);
 	if (role < kTubeWarps) {
 		TubeCell tl = {0.0, 0.0, 0.0, 0.0};
-		GTTS_ROLE_LOOP2(kTypeTube, if (!(skip & 32)) tube_iteration(C, role, lane, tl, p);)
+		GTTS_ROLE_LOOP2(kTypeTube, if (!(skip & 32)) tube_iteration<ST>(C, P, role, lane, tl, p);)
 	} else if (role == kRoleChainA) {
 		// The scheduler publishes control block it + 1 BEFORE it waits for the helpers of its own chain: the control
 		// blocks then run up to kFar iterations ahead of the slowest role, and no role ever waits for one.
@@ -1295,28 +1378,28 @@ GTTS_DEV void tube_v2_cta_body(const KernelParamsV2& P, unsigned char* smem, int
 			sched_signal(C, lane, it + 2);
 			if (it > 0) bar_wait(barrier_id(kTypeA, it), barrier_threads(kTypeA));   // the helpers' oscillator increments of iteration it - 1
 			GTTS_PROF_T1();
-			if (!(skip & 8)) chain_a_iteration(C, lane, pos, p);
+			if (!(skip & 8)) chain_a_iteration<ST>(C, P, lane, pos, p);
 			role_signal<kTypeA>(C, role, lane, it);
 			GTTS_PROF_T2();
 		}
 		GTTS_PROF_STORE(P, role, lane);
 	} else if (role == kRoleChainA2) {
 		BandpassState bp = {0.0, 0.0, 0.0, 0.0};
-		GTTS_ROLE_LOOP2(kTypeA2, if (!(skip & 8)) chain_a2_iteration(C, lane, bp, p);)
+		GTTS_ROLE_LOOP2(kTypeA2, if (!(skip & 8)) chain_a2_iteration<ST>(C, P, lane, bp, p);)
 	} else if (role == kRoleChainB) {
 		ChainBRegs cb = {0.0, 0.0};
-		GTTS_ROLE_LOOP2(kTypeB, if (!(skip & 16)) chain_b_iteration(C, lane, cb, p);)
+		GTTS_ROLE_LOOP2(kTypeB, if (!(skip & 16)) chain_b_iteration<ST>(C, P, lane, cb, p);)
 	} else if (role < kRoleCoef0) {
 		HelperRegs hr = {};
 		hr.mult = c_lcg[lane];
 		hr.low = kNoLowMark;
 		SlotSm* S = &C->slot[role - kRoleHelper0];
-		GTTS_ROLE_LOOP2(kTypeHelper, if (!(skip & 4)) helper_iteration(S, P, lane, hr, p);)
+		GTTS_ROLE_LOOP2(kTypeHelper, if (!(skip & 4)) helper_iteration<ST>(S, P, lane, hr, p);)
 	} else if (role < kRoleSrcB) {
 		const int slot = role - kRoleCoef0;
 		WalkRegs wr = {0.f, 0.f, 0.f, 0.f, 0, 0};
 		GTTS_ROLE_LOOP2(kTypeCoef,
-			if (!(skip & 64)) walk_slot(&C->slot[slot], P, lane, p, wr);
+			if (!(skip & 64)) walk_slot<ST>(&C->slot[slot], P, lane, p, wr);
 			if (!(skip & 2)) coef_task(&C->slot[slot], lane, p);
 			if (!(skip & 1) && slot >= GTTS_SRC_OWN0 && !C->sched[p].src_shared && ((C->sched[p].src_mask >> slot) & 1)) src_slot_task(C, P, lane, slot, p);)
 	} else {
@@ -1342,7 +1425,14 @@ GTTS_DEV void tube_v2_cta_body(const KernelParamsV2& P, unsigned char* smem, int
 __global__ void __launch_bounds__(kThreads, 1) tube_kernel_v2(const KernelParamsV2 P)
 {
 	extern __shared__ __align__(16) unsigned char gtts_smem_v2[];
-	tube_v2_cta_body(P, gtts_smem_v2, threadIdx.x);
+	tube_v2_cta_body<false>(P, gtts_smem_v2, threadIdx.x);
+}
+
+// the same pipeline for the chunks of a stream (gtts_stream_*): roles start from / save to UttStateV2
+__global__ void __launch_bounds__(kThreads, 1) tube_kernel_v2_stream(const KernelParamsV2 P)
+{
+	extern __shared__ __align__(16) unsigned char gtts_smem_v2s[];
+	tube_v2_cta_body<true>(P, gtts_smem_v2s, threadIdx.x);
 }
 #endif
 

@@ -57,6 +57,7 @@ struct UttDesc {
 	float   inv_steps;           // 1.0f / steps (Controller.cpp:287)
 	int32_t flags;               // bit0: resume from state[], bit1: do not flush (streaming chunk)
 	int64_t state_index;         // index into the UttState array (-1: none)
+	int64_t n_in_base;           // internal samples synthesised before this chunk (streaming; 0 for a whole utterance)
 };
 
 // Everything one utterance carries from one internal sample to the next (SURVEY.md section 8a,
@@ -76,6 +77,22 @@ struct UttState {
 	int64_t n_out_done;             // output samples produced so far
 	int32_t started;
 	int32_t table_low;              // lowest wavetable closure point below div1 seen so far (1 << 30: none)
+};
+
+// The same for the pipelined kernel (tube_kernel_v2.cuh): a chunk is drained through every pipeline stage, so all
+// roles stop at the same sample and each saves / restores its own part.
+struct UttStateV2 {
+	double tube[16][4];             // per cell: T, Bn, nb, last (tube_iteration)
+	double pos;                     // oscillator phase
+	double bp[4];                   // bandpass x1, x2, y1, y2
+	double rad[3][2];               // mouth radiation, nose radiation, throat: x1, y1
+	double noise_x1;
+	unsigned long long lcg;         // noise generator state on the 2^-44 grid
+	double vw[24][2];               // last 24 samples of the 2x oscillator stream {even, odd}
+	double xring[128];              // tube-output ring (SRC input), by absolute sample index & 127
+	float  walk_cur[16];            // the float32 interpolation accumulators (Controller.cpp:307-310) at the end of the chunk
+	int32_t table_low;              // lowest wavetable closure point below div1 seen so far (1 << 30: none)
+	int32_t started;
 };
 
 } // namespace gtts

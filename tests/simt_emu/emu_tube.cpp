@@ -186,11 +186,90 @@ extern "C" int emu_batch_v2(const gtts_voice_config* voices, int n_voices, const
 	P.n_utt = static_cast<int32_t>(n_utt);
 	P.prof = nullptr;
 	P.debug_skip = 0;
+	P.states = nullptr;
 
 	std::vector<unsigned char> smem(v2::smem_bytes() + 64);
 	unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem.data()) + 15) & ~uintptr_t(15));
 	for (int b = 0; b < n_ctas; ++b) {
-		simt::run_cta(v2::kThreads, [&](int tid) { v2::tube_v2_cta_body(P, base, tid); });
+		simt::run_cta(v2::kThreads, [&](int tid) { v2::tube_v2_cta_body<false>(P, base, tid); });
 	}
 	return 0;
+}
+
+// A stream on the pipelined kernel: frames are pushed in pieces of push_sizes[i] frames, every chunk is one emulated
+// launch of the streaming instantiation with the roles' state carried in UttStateV2 (host logic of runtime.cu:
+// gtts_stream_push_frames / gtts_stream_finish, through the same planning functions).
+extern "C" long long emu_stream_v2(const gtts_voice_config* voice, double control_rate, const float* frames, long long n_frames,
+			const int* push_sizes, int n_pushes, float* out, long long cap)
+{
+	using namespace gtts;
+	BatchPlan plan;
+	int err = 0;
+	const int64_t fo[2] = {0, 0};
+	g_err = planBatch(voice, 1, nullptr, control_rate, nullptr, fo, 1, plan, &err);
+	if (err) return -err;
+	const UttDesc base = plan.utts[0];
+	const int32_t steps = base.steps;
+	if (steps < kBlock) { g_err = "control period shorter than one block"; return -GTTS_ERR_UNSUPPORTED; }
+	std::vector<double> taps = designGlottalFir();
+	std::memset(c_fir, 0, sizeof c_fir);
+	for (size_t i = 0; i < taps.size(); ++i) c_fir[i] = taps[i];
+	lcgMultipliers(c_lcg);
+	c_lcg_init = lcgInitialState();
+	std::vector<double> h(kSrcFilterLen), dh(kSrcFilterLen);
+	buildSrcTables(h.data(), dh.data());
+	std::vector<double2> tab(kSrcFilterLen);
+	for (int i = 0; i < kSrcFilterLen; ++i) { tab[i].x = h[i]; tab[i].y = dh[i]; }
+	std::vector<double> table(kTableLen);
+	buildWavetable(plan.voices[0], table.data());
+	UttStateV2 state;
+	std::memset(&state, 0, sizeof state);
+	std::vector<float> pending;
+	int64_t period0 = 0, nInDone = 0, nOutDone = 0, fed = 0;
+	const int32_t order0 = 0;
+	std::vector<unsigned char> smem(v2::smem_bytes() + 64);
+	unsigned char* sbase = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem.data()) + 15) & ~uintptr_t(15));
+	auto run = [&](int64_t nSamples, bool flush) -> int {
+		const int64_t nAvail = static_cast<int64_t>(pending.size()) / kNumParams;
+		const int64_t kAfter = streamOutputsAfter(plan.voices[0], nInDone + nSamples, flush);
+		if (kAfter > cap) { g_err = "output buffer too small"; return 1; }
+		UttDesc d = streamChunkDesc(base, nAvail, nSamples, nInDone, nOutDone, kAfter, flush);
+		int queue = 0;
+		v2::KernelParamsV2 P;
+		P.voices = plan.voices.data();
+		P.tables = table.data();
+		P.utts = &d;
+		P.order = &order0;
+		P.frames = pending.data();
+		P.out = out + nOutDone;               // out_begin = -nOutDone: absolute output k lands at out[k]
+		P.src_tab = tab.data();
+		P.queue = &queue;
+		P.n_utt = 1;
+		P.states = &state;
+		P.prof = nullptr;
+		P.debug_skip = 0;
+		simt::run_cta(v2::kThreads, [&](int tid) { v2::tube_v2_cta_body<true>(P, sbase, tid); });
+		nInDone += nSamples;
+		nOutDone = kAfter;
+		return 0;
+	};
+	for (int i = 0; i < n_pushes && fed < n_frames; ++i) {
+		const int64_t n = std::min<int64_t>(push_sizes[i], n_frames - fed);
+		pending.insert(pending.end(), frames + fed * kNumParams, frames + (fed + n) * kNumParams);
+		fed += n;
+		const int64_t have = static_cast<int64_t>(pending.size()) / kNumParams;
+		const int64_t nSamples = streamSamplesReady(period0, have, steps, nInDone, kBlock);
+		if (nSamples == 0) continue;
+		if (run(nSamples, false)) return -1;
+		const int64_t p0 = nInDone / steps;
+		pending.erase(pending.begin(), pending.begin() + (p0 - period0) * kNumParams);
+		period0 = p0;
+	}
+	if (fed < n_frames) {
+		pending.insert(pending.end(), frames + fed * kNumParams, frames + n_frames * kNumParams);
+		fed = n_frames;
+	}
+	const int64_t have = static_cast<int64_t>(pending.size()) / kNumParams;
+	if (run(have > 0 ? (period0 + have) * steps - nInDone : 0, true)) return -1;
+	return nOutDone;
 }

@@ -180,3 +180,28 @@ def test_emulated_kernels_reproduce_rise_segment_corruption(emu, emu_v2, oracle)
         out = run()
         assert len(out) == len(ref)
         assert full_scale_error(out, ref) <= 1e-9
+
+
+def test_emulated_stream_on_pipelined_kernel(oracle, real_tracks):
+    # gtts_stream_* on the pipelined kernel: the utterance arrives in pushes of 1..7 frames, every chunk (whole
+    # 32-sample blocks) is a launch whose roles resume from the state the previous chunk saved; the result is the
+    # batch result, i.e. the oracle's, bit for bit
+    subprocess.run(["make", "-s", "-C", os.path.join(HERE, "simt_emu")], check=True)
+    L = C.CDLL(os.path.join(HERE, "simt_emu", "libemu_tube.so"))
+    L.emu_last_error.restype = C.c_char_p
+    L.emu_stream_v2.restype = C.c_longlong
+    L.emu_stream_v2.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_void_p, C.c_longlong]
+    rng = np.random.Generator(np.random.PCG64(12))
+    for voice, track in ((default_voice("male"), real_tracks[0][:24]), (default_voice("baby"), real_tracks[2][640:652]),
+                         (random_voice(rng), T.synthetic_track(3, 9))):
+        ref = oracle.synthesize(voice, track)
+        for sizes in ([1] * len(track), rng.integers(1, 8, len(track)).tolist(), [len(track)]):
+            va = voice_array([voice])
+            fr = np.ascontiguousarray(track, np.float32)
+            ps = np.ascontiguousarray(sizes, np.int32)
+            out = np.full(len(ref) + 64, np.nan, np.float32)
+            n = L.emu_stream_v2(va, 250.0, fr.ctypes.data, len(fr), ps.ctypes.data, len(ps), out.ctypes.data, len(out))
+            assert n == len(ref), (n, len(ref), L.emu_last_error())
+            assert full_scale_error(out[:n], ref) <= 1e-9
+            if voice["glottal_pulse_tn_min"] == voice["glottal_pulse_tn_max"]:
+                assert np.array_equal(out[:n], ref)
