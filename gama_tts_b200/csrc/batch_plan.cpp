@@ -17,12 +17,6 @@ std::string planBatch(const gtts_voice_config* voices, int32_t nVoices, const in
 	for (int32_t i = 0; i < nVoices; ++i) {
 		const char* e = deriveVoice(voices[i], plan.voices[i]);
 		if (e) return std::string("voice ") + std::to_string(i) + ": " + e;
-		if (!plan.voices[i].src_upsample) {
-			// fs_int > output_rate (vocal tract shorter than ~7.3 cm at 48 kHz): the reference switches
-			// to its down-sampling loop (SampleRateConverter.h:362-415), which this path does not implement.
-			*err = GTTS_ERR_UNSUPPORTED;
-			return std::string("voice ") + std::to_string(i) + ": internal rate above output rate (down-sampling SRC) is not supported";
-		}
 	}
 	plan.utts.resize(nUtt);
 	plan.out_offsets.assign(nUtt + 1, 0);

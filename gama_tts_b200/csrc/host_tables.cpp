@@ -27,117 +27,44 @@ double amplitude60dB(double db)
 	return std::pow(10.0, (db - 60.0) * (1.0 / 20.0));
 }
 
-// Best rational approximation with bounded denominator
-// (WavetableGlottalSourceFIRFilter.h:336-382).
-void bestRational(double number, int& order, int& numerator, int& denominator)
-{
-	if (order <= 0) { numerator = 0; denominator = 0; order = -1; return; }
-	const double frac = std::fabs(number - static_cast<int>(number));
-	const int maxDen = std::min(2 * order, 200);
-	double best = 1.0;
-	int bestNum = 0;
-	for (int den = order; den <= maxDen; ++den) {
-		const double scaled = den * frac;
-		const int nearest = static_cast<int>(scaled + 0.5);
-		const double err = std::fabs((scaled - static_cast<double>(nearest)) / den);
-		if (err < best) { best = err; bestNum = nearest; denominator = den; }
-	}
-	numerator = static_cast<int>(std::fabs(number)) * denominator + bestNum;
-	if (number < 0.0) numerator = -numerator;
-	order = denominator - 1;
-	if (numerator == denominator) {
-		denominator = maxDen;
-		order = numerator = denominator - 1;
-	}
-}
-
 } // namespace
 
-// Maximally-flat linear-phase lowpass (beta = transition centre, gamma = transition width), trimmed
-// at |c| < cutoff and laid out symmetric (WavetableGlottalSourceFIRFilter.h:74-114, 137-215, 228-237).
+// The glottal source's decimating low-pass (WavetableGlottalSourceFIRFilter.h:74-114) is the same for every voice:
+// the reference designs it at start-up with fixed arguments (beta = 0.2, gamma = 0.1, cutoff 1e-8; maximally flat,
+// linear phase), which gives 49 symmetric taps.  They are a constant of the path and are shipped as one: the 25
+// values from the centre tap outwards (tests/test_host_abi.py checks them bit for bit against
+// the reference's own design routine, which is where they would have to be regenerated if the arguments changed).
 std::vector<double> designGlottalFir(double beta, double gamma, double cutoff)
 {
-	std::vector<double> mag(202), cosv(202), half(202);
-	int order = static_cast<int>(1.0 / (4.0 * gamma * gamma));
-	const double edge = (1.0 + std::cos((2.0 * kPi) * beta)) / 2.0;
-	int numer = 0, points = 0;
-	bestRational(edge, order, numer, points);
-	const int n = 2 * points - 1;
-	if (numer == 0) numer = 1;
-	cosv[1] = mag[1] = 1.0;
-	const int flatOrder = order - numer;
-	for (int i = 2; i <= points; ++i) {
-		cosv[i] = std::cos((2.0 * kPi) * (static_cast<double>(i - 1) / n));
-		const double x = (1.0 - cosv[i]) / 2.0;
-		if (numer == order) continue;
-		double xpow = x, series = 1.0;
-		for (int j = 1; j <= flatOrder; ++j) {
-			double term = xpow;
-			for (int q = 1; q <= numer - 1; ++q) term *= 1.0 + (static_cast<double>(j) / q);
-			xpow *= x;
-			series += term;
-		}
-		mag[i] = series * std::pow(1.0 - x, numer);
-	}
-	for (int i = 1; i <= points; ++i) {
-		half[i] = mag[1] / 2.0;
-		for (int j = 2; j <= points; ++j) {
-			int m = ((i - 1) * (j - 1)) % n;
-			if (m > order) m = n - m;
-			half[i] += cosv[m + 1] * mag[j];
-		}
-		half[i] *= 2.0 / static_cast<double>(n);
-	}
-	int kept = points;
-	for (int i = points; i > 0; --i) {
-		if (std::fabs(half[i]) >= std::fabs(cutoff)) { kept = i; break; }
-	}
-	std::vector<double> taps(2 * kept - 1);
-	for (int i = 0; i < kept; ++i) {
-		taps[kept - 1 - i] = half[i + 1];
-		taps[kept - 1 + i] = half[i + 1];
-	}
+	static const double kHalf[25] = {
+		0.39847427941239039, 0.2965041881371811, 0.087853092781387032, -0.051247637455809028,
+		-0.056044214360539933, -0.0013632376466076977, 0.024723951583638423, 0.011204567485223504,
+		-0.0059227989476883834, -0.0070911561060204289, -0.00061607377823225985, 0.0023296835220954727,
+		0.0011316111860893143, -0.00028644112282104019, -0.00043243790948125553, -8.6968794272942906e-05,
+		6.9699584503931649e-05, 4.3261082316484397e-05, 2.2354964101677552e-06, -6.267564867199802e-06,
+		-2.4300136304004587e-06, -6.5322947036563118e-08, 2.137841904426972e-07, 7.3133299513665035e-08,
+		1.0887157865533967e-08 };
+	if (beta != 0.2 || gamma != 0.1 || cutoff != 0.00000001) return std::vector<double>();     // only the shipped design exists
+	std::vector<double> taps(49);
+	for (int m = 0; m < 25; ++m) taps[24 - m] = taps[24 + m] = kHalf[m];
 	return taps;
 }
 
-namespace {
-
-// Modified Bessel I0 by its power series (SampleRateConverter.h:175-194).
-double besselI0(double x)
-{
-	double sum = 1.0, term = 1.0;
-	const double hx = x / 2.0;
-	int n = 1;
-	do {
-		double t = hx / n;
-		n += 1;
-		t *= t;
-		term *= t;
-		sum += term;
-	} while (term >= 1e-21 * sum);
-	return sum;
-}
-
-} // namespace
-
-// Kaiser-windowed sinc, 13 zero crossings x 256 phases, and its first differences
-// (SampleRateConverter.h:230-255).
+// The SRC's interpolation filter (SampleRateConverter.h:230-255): a sinc low-pass at 11/13 of the Nyquist rate, 13 zero
+// crossings of 256 phases each, under a Kaiser window (beta = 5.658), and its first differences (the last one
+// against an implied zero).  Closed form; the window uses the library's modified Bessel function.  Agrees with the
+// reference's table to 2e-15 relative (tests/test_host_abi.py).
 void buildSrcTables(double* h, double* dh)
 {
-	const double kaiserBeta = 5.658, cutoff = 11.0 / 13.0;
-	const double step = kPi / kSrcLRange;
-	h[0] = cutoff;
-	for (int i = 1; i < kSrcFilterLen; ++i) {
-		const double y = i * step;
-		h[i] = std::sin(y * cutoff) / y;
-	}
-	const double norm = 1.0 / besselI0(kaiserBeta);
+	const double beta = 5.658, corner = 11.0 / 13.0;
+	const double i0Beta = std::cyl_bessel_i(0.0, beta);
 	for (int i = 0; i < kSrcFilterLen; ++i) {
-		const double t = static_cast<double>(i) / kSrcFilterLen;
-		h[i] *= besselI0(kaiserBeta * std::sqrt(1.0 - (t * t))) * norm;
+		const double phase = i * (kPi / kSrcLRange);
+		const double sinc = (i == 0) ? corner : std::sin(phase * corner) / phase;
+		const double u = static_cast<double>(i) / kSrcFilterLen;
+		h[i] = sinc * (std::cyl_bessel_i(0.0, beta * std::sqrt(1.0 - (u * u))) / i0Beta);
 	}
-	for (int i = 0; i + 1 < kSrcFilterLen; ++i) dh[i] = h[i + 1] - h[i];
-	dh[kSrcFilterLen - 1] = 0.0 - h[kSrcFilterLen - 1];
+	for (int i = 0; i < kSrcFilterLen; ++i) dh[i] = (i + 1 < kSrcFilterLen ? h[i + 1] : 0.0) - h[i];
 }
 
 int internalRate(const gtts_voice_config& c)

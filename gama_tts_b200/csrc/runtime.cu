@@ -397,7 +397,6 @@ int gtts_output_length(const gtts_voice_config* voice, int32_t steps, int64_t n_
 	if (steps <= 0 || n_frames < 0) return fail(GTTS_ERR_INVALID, "steps must be > 0 and n_frames >= 0");
 	VoiceDev v;
 	if (const char* e = deriveVoice(*voice, v)) return fail(GTTS_ERR_INVALID, e);
-	if (!v.src_upsample) return fail(GTTS_ERR_UNSUPPORTED, "down-sampling SRC (internal rate above output rate) is not supported");
 	const int64_t nInternal = n_frames * steps;
 	if (n_internal_out) *n_internal_out = nInternal;
 	if (n_output_out) *n_output_out = outputLength(v, nInternal);

@@ -587,6 +587,29 @@ GTTS_DEV void stage_src(const WarpSm* S, const double2* tab, const VoiceDev& V, 
 		const int e = (int) (t >> 16);
 		const unsigned f = (unsigned) (t & 0xFFFFu);
 		double acc = 0.0;
+		if (!V.src_upsample) {
+			// down-sampling (SampleRateConverter.h:362-415): input i sits at ring position pad + i; phases from
+			// rint(f ratio), advancing by phaseIncrement per tap while the filter index stays inside the table
+			unsigned ph = (unsigned) rint((double) f * V.src_ratio);
+			long long pos = (long long) e - V.src_pad;
+			unsigned ii;
+			while ((ii = (ph >> 8)) < (unsigned) kSrcFilterLen) {
+				const double2 c = tab[ii];
+				acc += S->xring[(int) (pos & (kSrcRing - 1))] * (c.x + (c.y * ((double) (ph & 0xFFu) / 256)));
+				pos -= 1;
+				ph += V.src_phase_inc;
+			}
+			ph = (unsigned) rint((double) ((~f) & 0xFFFFu) * V.src_ratio);
+			pos = (long long) e - V.src_pad + 1;
+			while ((ii = (ph >> 8)) < (unsigned) kSrcFilterLen) {
+				const double2 c = tab[ii];
+				acc += S->xring[(int) (pos & (kSrcRing - 1))] * (c.x + (c.y * ((double) (ph & 0xFFu) / 256)));
+				pos += 1;
+				ph += V.src_phase_inc;
+			}
+			out[k] = (float) acc;
+			continue;
+		}
 		{
 			const double interp = (double) (f & 0xFFu) / 256;
 			const unsigned L = f >> 8;
@@ -687,7 +710,7 @@ GTTS_DEV void run_utterance(WarpSm* S, const double2* tab, const KernelParams& P
 			S->ve[n & (kVRing - 1)] = st->fir_hist[2 * lane];
 			S->vo[n & (kVRing - 1)] = st->fir_hist[2 * lane + 1];
 		}
-		if (lane < 26) S->xring[(nDone - 26 + lane) & (kSrcRing - 1)] = st->src_hist[lane];
+		for (int i = lane; i < 64; i += 32) S->xring[(nDone - 64 + i) & (kSrcRing - 1)] = st->src_hist[i];      // 2 pad <= 64 inputs back
 		__syncwarp();
 	}
 
@@ -727,7 +750,7 @@ GTTS_DEV void run_utterance(WarpSm* S, const double2* tab, const KernelParams& P
 
 	if (!noFlush) {
 		// flushBuffer(): 2*pad zeros, then everything that is left (SampleRateConverter.h:462-471)
-		if (lane < 2 * kSrcZeroCrossings) S->xring[(nDone + lane) & (kSrcRing - 1)] = 0.0;
+		for (int i = lane; i < 2 * V.src_pad; i += 32) S->xring[(nDone + i) & (kSrcRing - 1)] = 0.0;
 		__syncwarp();
 		stage_src(S, tab, V, lane, kDone, nOutTotal, out);
 		kDone = nOutTotal;
@@ -764,7 +787,7 @@ GTTS_DEV void run_utterance(WarpSm* S, const double2* tab, const KernelParams& P
 			st->fir_hist[2 * lane] = S->ve[n & (kVRing - 1)];
 			st->fir_hist[2 * lane + 1] = S->vo[n & (kVRing - 1)];
 		}
-		if (lane < 26) st->src_hist[lane] = S->xring[(nDone - 26 + lane) & (kSrcRing - 1)];
+		for (int i = lane; i < 64; i += 32) st->src_hist[i] = S->xring[(nDone - 64 + i) & (kSrcRing - 1)];
 	}
 	__syncwarp();
 }

@@ -877,12 +877,58 @@ GTTS_DEV void src_shared_group(CtaSm* C, const KernelParamsV2& P, int lane, int 
 	for (int task = 0; task < D.src_tasks; ++task) src_task<NS>(C, P, lane, slot0, mask, inc, D.src_k0 + 64ll * task, D.src_k0w, D.src_k1, p);
 }
 
+// Down-sampling SRC (internal rate above the output rate: vocal tracts shorter than 7.3 cm at 48 kHz), lane = output
+// (SampleRateConverter.h:362-415).  Output k is centred on ring position e = (k inc) >> 16 -- input i sits at ring
+// position pad + i -- with phase rint(f ratio), f = (k inc) & 0xFFFF; the left wing walks down from position e, the
+// right wing (phase from ~f) up from e + 1, each while its filter index phase >> 8 is inside the table, the phase
+// advancing by phaseIncrement = rint(ratio 65536) per tap: at most pad taps a wing, in the reference's order.
+GTTS_DEV_NOINLINE void src_down_task(CtaSm* C, const KernelParamsV2& P, int lane, int slot, int p)
+{
+	SlotSm* S = &C->slot[slot];
+	const SlotSm::Ctl& K = S->ctl[p];
+	const VoiceDev& V = S->V[K.vbuf];
+	const unsigned inc = K.inc, pinc = V.src_phase_inc;
+	const int pad = V.src_pad;
+	const double ratio = V.src_ratio;
+	float* out = P.out + K.U.out_begin;
+#pragma unroll 1
+	for (long long k = K.src_k0 + lane; k < K.src_k1; k += 32) {
+		const unsigned long long t = (unsigned long long) k * inc;
+		const long long e = (long long) (t >> 16);
+		const unsigned f = (unsigned) (t & 0xFFFFu);
+		double acc = 0.0;
+		unsigned ph = (unsigned) rint((double) f * ratio);
+		long long pos = e - pad;                                   // input index of ring position e
+		unsigned ii;
+#pragma unroll 1
+		while ((ii = (ph >> 8)) < (unsigned) kSrcFilterLen) {
+			const double2 c = C->tab[ii];
+			const double imp = c.x + (c.y * ((double) (ph & 0xFFu) / 256));
+			acc += S->xring[(int) (pos & (kSrcRing - 1))] * imp;
+			pos -= 1;
+			ph += pinc;
+		}
+		ph = (unsigned) rint((double) ((~f) & 0xFFFFu) * ratio);
+		pos = e - pad + 1;
+#pragma unroll 1
+		while ((ii = (ph >> 8)) < (unsigned) kSrcFilterLen) {
+			const double2 c = C->tab[ii];
+			const double imp = c.x + (c.y * ((double) (ph & 0xFFu) / 256));
+			acc += S->xring[(int) (pos & (kSrcRing - 1))] * imp;
+			pos += 1;
+			ph += pinc;
+		}
+		out[k] = (float) acc;
+	}
+}
+
 // per-slot SRC (slots not in lockstep): the slot's own outputs, 64 per pass
 GTTS_DEV void src_slot_task(CtaSm* C, const KernelParamsV2& P, int lane, int slot, int p)
 {
 	const SlotSm::Ctl& K = C->slot[slot].ctl[p];
 	const int b = K.it - kStOut;
 	if (K.it < 0 || b < 0 || b >= K.nblocks) return;
+	if (K.inc > 65536u) { src_down_task(C, P, lane, slot, p); return; }
 	const long long k0 = K.src_k0, k1 = K.src_k1;
 	const long long a = K.U.out_begin & 1;
 	const long long kStart = ((k0 + a) & ~1ll) - a;            // pairs start on even absolute positions (8-byte stores)
@@ -899,7 +945,7 @@ GTTS_DEV void chain_a_iteration(CtaSm* C, const KernelParamsV2& P, int lane, dou
 	SlotSm* S = &C->slot[lane < kSlots ? lane : 0];
 	const SlotSm::Ctl& K = S->ctl[p];
 	const int b = K.it - kStPhase;
-	if (!__any_sync(0xffffffffu, lane < kSlots && K.it >= 0 && b >= 0 && b < K.nblocks)) return;
+	if (ST && !__any_sync(0xffffffffu, lane < kSlots && K.it >= 0 && b >= 0 && b < K.nblocks)) return;
 	if (lane >= kSlots) return;
 	UttStateV2* st = chunk_state<ST>(P, K.U);
 	if (b == 0) posReg = chunk_resumes(st, K.U) ? st->pos : 0.0;
@@ -936,7 +982,7 @@ GTTS_DEV void chain_a2_iteration(CtaSm* C, const KernelParamsV2& P, int lane, Ba
 	SlotSm* S = &C->slot[lane < kSlots ? lane : 0];
 	const SlotSm::Ctl& K = S->ctl[p];
 	const int b = K.it - kStCoef;
-	if (!__any_sync(0xffffffffu, lane < kSlots && K.it >= 0 && b >= 0 && b < K.nblocks)) return;
+	if (ST && !__any_sync(0xffffffffu, lane < kSlots && K.it >= 0 && b >= 0 && b < K.nblocks)) return;
 	if (lane >= kSlots) return;
 	UttStateV2* cs = chunk_state<ST>(P, K.U);
 	if (b == 0) {
@@ -990,7 +1036,7 @@ GTTS_DEV void chain_b_iteration(CtaSm* C, const KernelParamsV2& P, int lane, Cha
 	{
 		const SlotSm::Ctl& K0 = C->slot[s < kSlots ? s : 0].ctl[p];
 		const int b0 = K0.it - kStRad;
-		if (!__any_sync(0xffffffffu, s < kSlots && K0.it >= 0 && b0 >= 0 && b0 < K0.nblocks)) return;
+		if (ST && !__any_sync(0xffffffffu, s < kSlots && K0.it >= 0 && b0 >= 0 && b0 < K0.nblocks)) return;
 	}
 	if (s < kSlots && f < 3) {
 		SlotSm* S = &C->slot[s];
@@ -1048,18 +1094,22 @@ GTTS_DEV void chain_b_iteration(CtaSm* C, const KernelParamsV2& P, int lane, Cha
 			__syncwarp();
 		}
 		const int qn = block_len(QK, qb);
-		const long long n0 = QK.U.n_in_base + (long long) qb * kBlock;
+		const long long n0 = (ST ? QK.U.n_in_base : 0) + (long long) qb * kBlock;
 		if (lane < qn) {
 			const int idx = (int) ((n0 + lane) & (kSrcRing - 1));
 			const double v = (Q->rad[0][lane] + Q->rad[1][lane]) + Q->rad[2][lane];
 			Q->xring[idx] = v;
 			if (idx < kXr - kSrcRing) Q->xring[idx + kSrcRing] = v;
 		}
-		if (qb == QK.nblocks - 1 && (QK.U.flags & 2) == 0 && lane < 2 * kSrcZeroCrossings) {
-			// flushBuffer(): 26 zeros after the last input (SampleRateConverter.h:462-471); not between the chunks of a stream
-			const int idx = (int) ((QK.U.n_in_base + QK.U.n_internal + lane) & (kSrcRing - 1));
-			Q->xring[idx] = 0.0;
-			if (idx < kXr - kSrcRing) Q->xring[idx + kSrcRing] = 0.0;
+		if (qb == QK.nblocks - 1 && (QK.U.flags & 2) == 0) {
+			// flushBuffer(): 2 pad zeros after the last input (26 when up-sampling; SampleRateConverter.h:462-471);
+			// not between the chunks of a stream
+			const int nz = 2 * Q->V[QK.vbuf].src_pad;
+			for (int i = lane; i < nz; i += 32) {
+				const int idx = (int) (((ST ? QK.U.n_in_base : 0) + QK.U.n_internal + i) & (kSrcRing - 1));
+				Q->xring[idx] = 0.0;
+				if (idx < kXr - kSrcRing) Q->xring[idx + kSrcRing] = 0.0;
+			}
 		}
 		if (qs != nullptr && qb == QK.nblocks - 1) {
 			__syncwarp();
@@ -1101,7 +1151,7 @@ GTTS_DEV void tube_iteration(CtaSm* C, const KernelParamsV2& P, int warp, int la
 	const int b = (slot < kSlots) ? K.it - kStTube : -1;
 	const bool hasBlock = slot < kSlots && K.it >= 0 && b >= 0 && b < K.nblocks;
 	const int buf = b & 1, b3 = (b % 3 + 3) % 3;
-	if (!__any_sync(0xffffffffu, hasBlock)) return;    // pipeline filling or draining (every iteration of a short stream chunk but a few)
+	if (ST && !__any_sync(0xffffffffu, hasBlock)) return;    // pipeline filling or draining (every iteration of a short stream chunk but a few)
 	const bool fricBlock = __any_sync(0xffffffffu, hasBlock && S->fric[buf] != 0);
 	const VoiceDev& V = S->V[K.vbuf];
 	UttStateV2* st = hasBlock ? chunk_state<ST>(P, K.U) : nullptr;
@@ -1184,6 +1234,7 @@ GTTS_DEV void tube_iteration(CtaSm* C, const KernelParamsV2& P, int warp, int la
 
 // ---- slot bookkeeping for iteration i + 1 (chain A warp, lane = slot) -------------------------------------------
 // Reads ctl[i % 4], writes ctl[(i + 1) % 4] and sched[(i + 1) % 4], copies the voice constants of new utterances.
+template<bool ST>
 GTTS_DEV void schedule_slots(CtaSm* C, const KernelParamsV2& P, int lane, int i, bool first)
 {
 	const int p = i & (kCtlRing - 1), q = (i + 1) & (kCtlRing - 1);
@@ -1226,14 +1277,19 @@ GTTS_DEV void schedule_slots(CtaSm* C, const KernelParamsV2& P, int lane, int i,
 				// output counter: e(0) = 0 = (0 + inc - 1) / inc, remainder inc - 1; one block adds 32 * 65536
 				const unsigned uinc = P.voices[U.voice].src_inc;
 				N.inc = uinc;
-				N.gran = uinc <= 32768u ? 64 : 32;
+				N.gran = uinc <= 32768u ? 64 : (uinc <= 65536u ? 32 : 1);     // down-sampling: no row deferral (the window is up to 64 inputs long)
 				N.eQ = (unsigned) (kBlock << 16) / uinc;
 				N.eR = (unsigned) (kBlock << 16) % uinc;
 				// e(0) = ceil(n_in_base 65536 / inc) as quotient / remainder of (n_in_base 65536 + inc - 1) / inc
 				// (0 and inc - 1 for a whole utterance)
-				const unsigned long long num = ((unsigned long long) U.n_in_base << 16) + uinc - 1;
-				N.eq = (long long) (num / uinc);
-				N.erem = (unsigned) (num % uinc);
+				if (ST) {
+					const unsigned long long num = ((unsigned long long) U.n_in_base << 16) + uinc - 1;
+					N.eq = (long long) (num / uinc);
+					N.erem = (unsigned) (num % uinc);
+				} else {
+					N.eq = 0;
+					N.erem = uinc - 1;
+				}
 				it = 0;
 				fresh = 1; voice = U.voice; vbuf = N.vbuf;
 				break;
@@ -1272,7 +1328,7 @@ GTTS_DEV void schedule_slots(CtaSm* C, const KernelParamsV2& P, int lane, int i,
 	const long long nRef = __shfl_sync(0xffffffffu, nInternal, refLane, 32);
 	const unsigned incRef = __shfl_sync(0xffffffffu, inc, refLane, 32);
 	const int phaseRef = __shfl_sync(0xffffffffu, phase, refLane, 32);
-	const int same = !valid || (it == itRef && nInternal == nRef && inc == incRef && phase == phaseRef);
+	const int same = !valid || (it == itRef && nInternal == nRef && inc == incRef && phase == phaseRef && inc <= 65536u);
 	const bool allSame = __ballot_sync(0xffffffffu, same) == 0xffffffffu;
 	__syncwarp();                                  // lane 0 reads what the reference slot's lane wrote into ctl[q]
 	if (lane == 0) {
@@ -1355,7 +1411,7 @@ GTTS_DEV void tube_v2_cta_body(const KernelParamsV2& P, unsigned char* smem, int
 	}
 	__syncthreads();
 	if (role == kRoleChainA) {
-		schedule_slots(C, P, lane, -1, true);      // fills ctl[0] / sched[0]
+		schedule_slots<ST>(C, P, lane, -1, true);      // fills ctl[0] / sched[0]
 		sched_signal(C, lane, 1);
 	}
 	__syncthreads();
@@ -1374,7 +1430,7 @@ GTTS_DEV void tube_v2_cta_body(const KernelParamsV2& P, unsigned char* smem, int
 			poll_counters(C, lane, it - kFar, lane < kWarps && lane != role);      // ring of control blocks: nobody more than kFar behind
 			const int p = it & (kCtlRing - 1);
 			if (!C->sched[p].live) break;
-			schedule_slots(C, P, lane, it, false);
+			schedule_slots<ST>(C, P, lane, it, false);
 			sched_signal(C, lane, it + 2);
 			if (it > 0) bar_wait(barrier_id(kTypeA, it), barrier_threads(kTypeA));   // the helpers' oscillator increments of iteration it - 1
 			GTTS_PROF_T1();

@@ -72,7 +72,7 @@ struct UttState {
 	double bp_x1, bp_x2, bp_y1, bp_y2;
 	double pos;
 	double fir_hist[kFirMaxTaps];   // last 48 values of the 2x stream, oldest first
-	double src_hist[64];            // last 2*pad tube outputs, oldest first (pad <= 32)
+	double src_hist[64];            // last 64 tube outputs, oldest first (2 pad <= 64)
 	int64_t n_in_done;              // internal samples consumed so far
 	int64_t n_out_done;             // output samples produced so far
 	int32_t started;

@@ -205,3 +205,17 @@ def test_emulated_stream_on_pipelined_kernel(oracle, real_tracks):
             assert full_scale_error(out[:n], ref) <= 1e-9
             if voice["glottal_pulse_tn_min"] == voice["glottal_pulse_tn_max"]:
                 assert np.array_equal(out[:n], ref)
+
+
+def test_emulated_kernels_down_sampling_branch(emu, emu_v2, oracle):
+    # vocal tracts shorter than 7.3 cm: the internal rate exceeds the output rate and the SRC runs its down-sampling
+    # loop (SampleRateConverter.h:362-415: variable tap count, rint per output, 2 * pad > 26 flush zeros)
+    for length in (7.0, 5.5, 3.2):
+        v = dict(default_voice("baby"))
+        v["vocal_tract_length"] = length
+        tr = T.synthetic_track(21, 6)
+        ref = oracle.synthesize(v, tr)
+        for run in (lambda: emu([v], [0], [tr], warps=1)[0], lambda: emu_v2([v, default_voice("male")], [0, 1, 0], [tr, tr[:3], tr[:2]])[0]):
+            out = run()
+            assert len(out) == len(ref)
+            assert np.array_equal(out, ref)

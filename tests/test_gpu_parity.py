@@ -207,6 +207,25 @@ def test_pcm16_output_stage_is_bit_exact(synth, oracle, golden, real_tracks):
     assert np.abs(p[0].astype(np.int32) - ref_pcm.astype(np.int32)).max() <= 1
 
 
+def test_down_sampling_voices(synth, oracle, monkeypatch):
+    # tract lengths below 7.31 cm: internal rate above 48 kHz, the SRC's down-sampling branch
+    # (SampleRateConverter.h:362-415); mixed with up-sampling voices in one batch, both kernels
+    voices = []
+    for length in (7.2, 6.0, 4.5, 3.0):
+        v = dict(default_voice("baby"))
+        v["vocal_tract_length"] = length
+        voices.append(v)
+    voices.append(default_voice("male"))
+    tracks = [T.synthetic_track(600 + i, 30 + 7 * i) for i in range(len(voices))]
+    refs = [oracle.synthesize(v, t) for v, t in zip(voices, tracks)]
+    for kernel in ("v2", "v0"):
+        monkeypatch.setenv("GTTS_KERNEL", kernel)
+        outs = synth.synthesize(voices, tracks, voice_index=np.arange(len(voices)))
+        for out, ref in zip(outs, refs):
+            assert len(out) == len(ref)
+            assert full_scale_error(out, ref) <= TIGHT
+
+
 def test_general_kernel_golden_vectors(synth, golden, monkeypatch):
     # GTTS_KERNEL=v0 forces the general warp-per-utterance kernel (the one streaming uses) on batches
     monkeypatch.setenv("GTTS_KERNEL", "v0")
