@@ -48,3 +48,55 @@ def test_reference_drives_plugin_through_its_own_seam(reference, oracle, real_tr
         assert len(out) == len(builtin)
         assert full_scale_error(out, builtin) <= 2e-7
         assert full_scale_error(out, oracle.synthesize(v, track)) <= 2e-7
+
+
+STOCK = os.path.join(ROOT, "oracle", "_ref", "gama_tts")
+STOCK_VOICE = os.path.join(ROOT, "oracle", "_ref", "voice_0_male")
+
+
+def _stock_run(tmp_path, name, params_txt, model, extra=""):
+    """Runs the UNMODIFIED reference program `gama_tts vtm <voice dir> <parameter file> <out.wav>` (main.cpp:286-337)
+    on a copy of the shipped voice whose vtm.txt selects `model`; returns (exit code, stderr, int16 payload)."""
+    import shutil
+    import subprocess
+    voice = tmp_path / ("voice_" + name)
+    shutil.copytree(STOCK_VOICE, voice)
+    vtm = (voice / "vtm.txt").read_text().replace("model = 0", "model = %d" % model) + extra
+    (voice / "vtm.txt").write_text(vtm)
+    wav = tmp_path / (name + ".wav")
+    r = subprocess.run([STOCK, "vtm", str(voice), str(params_txt), str(wav)], capture_output=True, text=True)
+    data = np.fromfile(wav, np.int16)[22:] if wav.exists() else np.zeros(0, np.int16)     # 44-byte header
+    return r.returncode, r.stderr, data
+
+
+@pytest.mark.gpu
+def test_stock_gama_tts_binary_drives_the_plugin(tmp_path, real_tracks, product_lib):
+    # SURVEY.md section 4(v) / 7-6: the stock command-line program (every source of the reference, compiled unmodified
+    # with its plugin option, oracle/Makefile) loads libgtts_plugin.so through `model = 2000` / `dll_path` and writes a
+    # WAVE file; the same program with its built-in model 0 is the comparison.  Both read the same parameter file, so
+    # the 16-bit payloads agree to one LSB (the float32 audio agrees to 2e-7 of full scale).
+    _need_plugin()
+    if not (os.path.exists(STOCK) and os.path.isdir(STOCK_VOICE)):
+        pytest.skip("oracle/_ref/gama_tts not built (needs the reference sources at build time)")
+    params = tmp_path / "params.txt"
+    np.savetxt(params, real_tracks[0], fmt="%.9g")
+    rc0, err0, builtin = _stock_run(tmp_path, "builtin", params, 0)
+    assert rc0 == 0, err0
+    rc1, err1, plugin = _stock_run(tmp_path, "plugin", params, 2000, "\ndll_path = %s\n" % PLUGIN)
+    assert rc1 == 0, err1
+    assert len(plugin) == len(builtin) > 1000
+    assert np.abs(plugin.astype(np.int32) - builtin.astype(np.int32)).max() <= 1
+    assert (plugin == builtin).mean() > 0.99
+
+
+def test_stock_gama_tts_binary_reports_a_missing_gpu(tmp_path, real_tracks, product_lib):
+    import torch
+    _need_plugin()
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    if not (os.path.exists(STOCK) and os.path.isdir(STOCK_VOICE)):
+        pytest.skip("oracle/_ref/gama_tts not built")
+    params = tmp_path / "params.txt"
+    np.savetxt(params, real_tracks[0][:20], fmt="%.9g")
+    rc, err, data = _stock_run(tmp_path, "nogpu", params, 2000, "\ndll_path = %s\n" % PLUGIN)
+    assert rc != 0 and "Could not construct" in err and len(data) == 0
