@@ -891,6 +891,10 @@ GTTS_DEV_NOINLINE void src_down_task(CtaSm* C, const KernelParamsV2& P, int lane
 	const int pad = V.src_pad;
 	const double ratio = V.src_ratio;
 	float* out = P.out + K.U.out_begin;
+	// Inputs at and after nEnd are the flush zeros (SampleRateConverter.h:462-471).  They are not written into the
+	// ring here: 2 pad of them (up to 64) behind the last block would wrap onto inputs the SRC warp may still be
+	// reading for the block before (window 2 pad + 32, chain B one block ahead: 128 entries hold that and no more).
+	const long long nEnd = K.U.n_in_base + K.U.n_internal;
 #pragma unroll 1
 	for (long long k = K.src_k0 + lane; k < K.src_k1; k += 32) {
 		const unsigned long long t = (unsigned long long) k * inc;
@@ -904,7 +908,7 @@ GTTS_DEV_NOINLINE void src_down_task(CtaSm* C, const KernelParamsV2& P, int lane
 		while ((ii = (ph >> 8)) < (unsigned) kSrcFilterLen) {
 			const double2 c = C->tab[ii];
 			const double imp = c.x + (c.y * ((double) (ph & 0xFFu) / 256));
-			acc += S->xring[(int) (pos & (kSrcRing - 1))] * imp;
+			acc += (pos < nEnd ? S->xring[(int) (pos & (kSrcRing - 1))] : 0.0) * imp;
 			pos -= 1;
 			ph += pinc;
 		}
@@ -914,7 +918,7 @@ GTTS_DEV_NOINLINE void src_down_task(CtaSm* C, const KernelParamsV2& P, int lane
 		while ((ii = (ph >> 8)) < (unsigned) kSrcFilterLen) {
 			const double2 c = C->tab[ii];
 			const double imp = c.x + (c.y * ((double) (ph & 0xFFu) / 256));
-			acc += S->xring[(int) (pos & (kSrcRing - 1))] * imp;
+			acc += (pos < nEnd ? S->xring[(int) (pos & (kSrcRing - 1))] : 0.0) * imp;
 			pos += 1;
 			ph += pinc;
 		}
@@ -1104,7 +1108,8 @@ GTTS_DEV void chain_b_iteration(CtaSm* C, const KernelParamsV2& P, int lane, Cha
 		if (qb == QK.nblocks - 1 && (QK.U.flags & 2) == 0) {
 			// flushBuffer(): 2 pad zeros after the last input (26 when up-sampling; SampleRateConverter.h:462-471);
 			// not between the chunks of a stream
-			const int nz = 2 * Q->V[QK.vbuf].src_pad;
+			// (up-sampling only: the down-sampling SRC takes inputs past the end as zero, see src_down_task)
+			const int nz = Q->V[QK.vbuf].src_upsample ? 2 * Q->V[QK.vbuf].src_pad : 0;
 			for (int i = lane; i < nz; i += 32) {
 				const int idx = (int) (((ST ? QK.U.n_in_base : 0) + QK.U.n_internal + i) & (kSrcRing - 1));
 				Q->xring[idx] = 0.0;
