@@ -56,6 +56,41 @@ std::string planBatch(const gtts_voice_config* voices, int32_t nVoices, const in
 	return std::string();
 }
 
+std::vector<int32_t> wideGroups(const BatchPlan& plan, std::vector<int32_t> utts)
+{
+	std::vector<int32_t> out;
+	if (utts.empty()) return out;
+	int32_t lo = plan.utts[utts[0]].steps, hi = lo;
+	for (int32_t u : utts) { lo = std::min(lo, plan.utts[u].steps); hi = std::max(hi, plan.utts[u].steps); }
+	const int kClasses = 8;
+	auto cls = [&](int32_t u) { return hi == lo ? 0 : static_cast<int>((static_cast<int64_t>(plan.utts[u].steps - lo) * kClasses) / (hi - lo + 1)); };
+	std::stable_sort(utts.begin(), utts.end(), [&](int32_t a, int32_t b) {
+		const int ca = cls(a), cb = cls(b);
+		if (ca != cb) return ca < cb;
+		return plan.utts[a].n_internal > plan.utts[b].n_internal;
+	});
+	// whole groups inside a class; what is left of every class (fewer than 32 each) is grouped across classes
+	std::vector<std::vector<int32_t>> groups;
+	std::vector<int32_t> rest;
+	size_t i = 0;
+	while (i < utts.size()) {
+		size_t j = i;
+		while (j < utts.size() && cls(utts[j]) == cls(utts[i])) ++j;
+		size_t k = i;
+		for (; k + 32 <= j; k += 32) groups.emplace_back(utts.begin() + k, utts.begin() + k + 32);
+		rest.insert(rest.end(), utts.begin() + k, utts.begin() + j);
+		i = j;
+	}
+	std::stable_sort(rest.begin(), rest.end(), [&](int32_t a, int32_t b) { return plan.utts[a].n_internal > plan.utts[b].n_internal; });
+	for (size_t k = 0; k < rest.size(); k += 32) groups.emplace_back(rest.begin() + k, rest.begin() + std::min(rest.size(), k + 32));
+	std::stable_sort(groups.begin(), groups.end(), [&](const std::vector<int32_t>& a, const std::vector<int32_t>& b) {
+		return plan.utts[a[0]].n_internal > plan.utts[b[0]].n_internal;
+	});
+	out.assign(groups.size() * 32, -1);
+	for (size_t g = 0; g < groups.size(); ++g) std::copy(groups[g].begin(), groups[g].end(), out.begin() + g * 32);
+	return out;
+}
+
 int64_t streamSamplesReady(int64_t period0, int64_t have, int32_t steps, int64_t nInDone, int32_t block)
 {
 	if (have < 2) return 0;

@@ -25,6 +25,13 @@ std::string planBatch(const gtts_voice_config* voices, int32_t nVoices, const in
 			double controlRate, const int32_t* stepsOverride, const int64_t* frameOffsets,
 			int64_t nUtt, BatchPlan& plan, int* err);
 
+// ---- wide-batch kernel (tube_kernel_v3.cuh: one thread per utterance, 32 utterances of a warp in lockstep) ----------
+// Groups the utterances `utts` (indices into plan.utts) into warps: utterances of similar internal rate together
+// (the SRC loop of a warp runs as often as its fastest-converting lane needs), longest first inside a rate class
+// (a warp runs until its longest utterance ends), the groups themselves longest first (the persistent warps pop
+// them in this order).  Returns n_groups x 32 indices, -1 for the empty lanes of the last group of a class.
+std::vector<int32_t> wideGroups(const BatchPlan& plan, std::vector<int32_t> utts);
+
 // ---- streaming on the pipelined kernel: chunk planning (pure host logic, shared with the emulated tests) ----------
 // A stream is synthesised in chunks of whole 32-sample blocks; the frame window handed to the kernel starts at the
 // control period `period0` that contains the first sample of the chunk.

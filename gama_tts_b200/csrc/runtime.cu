@@ -24,6 +24,7 @@
 #include "tube_kernel.cuh"
 #include "tube_kernel_v1.cuh"
 #include "tube_kernel_v2.cuh"
+#include "tube_kernel_v3.cuh"
 
 using namespace gtts;
 
@@ -181,6 +182,9 @@ struct gtts_batch {
 	bool legacy_v1 = false;             // GTTS_KERNEL=v1: the barrier-per-iteration kernel instead of v2 (A/B measurements)
 	bool streaming = false;             // one-utterance batch of a gtts_stream (set before the plan is uploaded)
 	int32_t n_fast = 0;                 // the first n_fast entries of the order list run on the pipelined kernel
+	int32_t* d_order_wide = nullptr;    // wide-batch kernel (one thread per utterance): n_wide_groups x 32 indices, -1 = empty lane
+	int32_t n_wide_groups = 0;
+	int32_t n_wide = 0;                 // utterances in those groups (they are NOT in the order list)
 	const char* last_kernel = "none";
 };
 
@@ -216,11 +220,33 @@ int launchBatch(gtts_batch* b, const float* dFrames, float* dOut, cudaStream_t s
 	b->last_launches = 0;
 	if (nUtt == 0) return GTTS_OK;
 	GTTS_CUDA(cudaSetDevice(b->h->device));
-	GTTS_CUDA(cudaMemsetAsync(b->d_queue, 0, 2 * sizeof(int32_t), stream));
+	GTTS_CUDA(cudaMemsetAsync(b->d_queue, 0, 4 * sizeof(int32_t), stream));
 	// The processing order is [pipelined-kernel utterances | general-kernel utterances], each part longest first:
 	// one launch per non-empty part, each with its own work counter (uploadPlan).
-	const int32_t nFast = b->n_fast, nGeneral = static_cast<int32_t>(nUtt) - b->n_fast;
+	const int32_t nFast = b->n_fast;
 	b->last_kernel = "none";
+	int32_t nWide = 0;
+	if (b->n_wide_groups > 0) {
+		// wide-batch kernel: one thread per utterance, one CTA of 128 per SM, warps pop groups of 32 (uploadPlan)
+		v3::KernelParamsV3 W;
+		W.voices = b->d_voices;
+		W.tables = b->d_tables;
+		W.utts = dUtts;
+		W.order = b->d_order_wide;
+		W.frames = dFrames;
+		W.out = dOut;
+		W.src_tab = b->h->d_src_tab;
+		W.queue = b->d_queue + 2;
+		W.n_groups = b->n_wide_groups;
+		const int64_t ctasWanted = (static_cast<int64_t>(b->n_wide_groups) + v3::kWarps - 1) / v3::kWarps;
+		const int grid = static_cast<int>(std::min<int64_t>(ctasWanted, b->h->sms));
+		v3::tube_kernel_v3<<<grid, v3::kThreads, v3::smem_bytes(), stream>>>(W);
+		GTTS_CUDA(cudaGetLastError());
+		b->last_kernel = "tube_kernel_v3";
+		b->last_launches += 1;
+		nWide = b->n_wide;
+	}
+	const int32_t nGeneral = static_cast<int32_t>(nUtt) - nFast - nWide;
 	if (nFast > 0 && !b->legacy_v1) {
 		// decoupled warp-specialised kernel: one persistent CTA per SM, 7 utterance slots each
 		v2::KernelParamsV2 Q;
@@ -282,7 +308,7 @@ int launchBatch(gtts_batch* b, const float* dFrames, float* dOut, cudaStream_t s
 			std::fprintf(stderr, "\n");
 		}
 #endif
-		b->last_kernel = "tube_kernel_v2";
+		b->last_kernel = nWide > 0 ? "tube_kernel_v3+tube_kernel_v2" : "tube_kernel_v2";
 		b->last_launches += 1;
 	} else if (nFast > 0) {
 		// the barrier-per-iteration predecessor (GTTS_KERNEL=v1), kept for A/B measurements
@@ -321,7 +347,7 @@ int launchBatch(gtts_batch* b, const float* dFrames, float* dOut, cudaStream_t s
 		const size_t smem = tube_smem_bytes(kWarpsPerCta);
 		tube_kernel_v0<kWarpsPerCta><<<grid, kWarpsPerCta * 32, smem, stream>>>(P);
 		GTTS_CUDA(cudaGetLastError());
-		b->last_kernel = nFast > 0 ? "pipelined+tube_kernel_v0" : "tube_kernel_v0";
+		b->last_kernel = (nFast > 0 || nWide > 0) ? "pipelined+tube_kernel_v0" : "tube_kernel_v0";
 		b->last_launches += 1;
 	}
 	return GTTS_OK;
@@ -338,7 +364,7 @@ int uploadPlan(gtts_batch* b)
 	GTTS_CUDA(cudaMalloc(&b->d_voices, sizeof(VoiceDev) * std::max<size_t>(p.voices.size(), 1)));
 	GTTS_CUDA(cudaMalloc(&b->d_utts, sizeof(UttDesc) * std::max<size_t>(p.utts.size(), 1)));
 	GTTS_CUDA(cudaMalloc(&b->d_order, sizeof(int32_t) * std::max<size_t>(p.order.size(), 1)));
-	GTTS_CUDA(cudaMalloc(&b->d_queue, 2 * sizeof(int32_t)));
+	GTTS_CUDA(cudaMalloc(&b->d_queue, 4 * sizeof(int32_t)));
 	// Kernel choice per utterance: v1 (pipelined) needs control periods of at least one 32-sample block, or of
 	// exactly one sample (the plugin shim's mode: every internal sample has its own frame); the general v0 kernel
 	// takes everything else (and all streaming / resumed work).  The order list is partitioned accordingly, each
@@ -349,10 +375,52 @@ int uploadPlan(gtts_batch* b)
 		if (std::strcmp(env, "v0") == 0) forceGeneral = true;
 		b->legacy_v1 = std::strcmp(env, "v1") == 0;
 	}
+	// The wide-batch kernel (one thread per utterance, tube_kernel_v3.cuh) is a throughput design: 128 utterances
+	// per SM, about 2.5 us per internal sample for each of them (measured), against 0.25 us on the pipelined kernel,
+	// which finds its parallelism inside the utterance.  Its run time is therefore bounded below by the longest
+	// utterance (a 20 s utterance alone takes 2.3 s), and it pays only for batches of many SHORT utterances: it
+	// takes the up-sampling utterances of a batch when the estimate below says so.  Measured on B200: BASELINE
+	// config 3 (lengths up to 20 s) is 4.5x slower on it than on the pipelined kernel, so configs 2-4 never take
+	// this path.  GTTS_KERNEL=v3 forces it (tests), any other GTTS_KERNEL value forbids it.
+	{
+		bool wideForced = false, wideAllowed = !forceGeneral;
+		if (const char* env = std::getenv("GTTS_KERNEL")) {
+			if (std::strcmp(env, "v3") == 0) wideForced = true;
+			else wideAllowed = false;
+		}
+		auto wide = [&](int32_t u) { return p.voices[p.utts[u].voice].src_upsample != 0 && (p.utts[u].flags & 3) == 0; };
+		std::vector<int32_t> cand;
+		if (wideAllowed && !b->streaming) for (int32_t u : p.order) if (wide(u)) cand.push_back(u);
+		std::vector<int32_t> groups;
+		bool take = wideForced && !cand.empty();
+		if (!take && static_cast<int64_t>(cand.size()) >= 64ll * b->h->sms) {
+			groups = wideGroups(p, cand);
+			double iters = 0.0, longest = 0.0, samples = 0.0;
+			for (size_t g = 0; g < groups.size(); g += 32) {
+				const double n = static_cast<double>(p.utts[groups[g]].n_internal) + 26.0;     // lane 0 holds the group's longest
+				iters += n;
+				longest = std::max(longest, n);
+			}
+			for (int32_t u : cand) samples += static_cast<double>(p.utts[u].n_internal);
+			const double sms = static_cast<double>(b->h->sms);
+			const double estWide = std::max(longest, iters / (v3::kWarps * sms)) * 4900.0;   // cycles per iteration of a warp
+			const double estPipelined = samples * 70.0 / sms;                                // cycles per sample and SM, mixed voices
+			take = estWide * 1.25 < estPipelined;
+		}
+		if (take) {
+			if (groups.empty()) groups = wideGroups(p, cand);
+			p.order.erase(std::remove_if(p.order.begin(), p.order.end(), wide), p.order.end());
+			b->n_wide = static_cast<int32_t>(cand.size());
+			b->n_wide_groups = static_cast<int32_t>(groups.size() / 32);
+			GTTS_CUDA(cudaMalloc(&b->d_order_wide, sizeof(int32_t) * groups.size()));
+			GTTS_CUDA(cudaMemcpyAsync(b->d_order_wide, groups.data(), sizeof(int32_t) * groups.size(), cudaMemcpyHostToDevice, b->stream));
+			GTTS_CUDA(cudaStreamSynchronize(b->stream));      // `groups` goes out of scope
+		}
+	}
 	auto fast = [&](int32_t u) { const UttDesc& d = p.utts[u]; return !forceGeneral && (d.steps >= kBlock || d.steps == 1); };
 	const auto mid = std::stable_partition(p.order.begin(), p.order.end(), fast);
 	b->n_fast = static_cast<int32_t>(mid - p.order.begin());
-	if (b->n_fast > 0) {
+	if (b->n_fast > 0 || b->n_wide > 0) {
 		std::vector<double> tables(p.voices.size() * kTableLen);
 		for (size_t v = 0; v < p.voices.size(); ++v) buildWavetable(p.voices[v], tables.data() + v * kTableLen);
 		GTTS_CUDA(cudaMalloc(&b->d_tables, sizeof(double) * std::max<size_t>(tables.size(), 1)));
@@ -502,7 +570,9 @@ int createHandle(int32_t device, gtts_handle** handle_out)
 	    (ce = cudaFuncSetAttribute(v2::tube_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	                               (int) v2::smem_bytes())) != cudaSuccess ||
 	    (ce = cudaFuncSetAttribute(v2::tube_kernel_v2_stream, cudaFuncAttributeMaxDynamicSharedMemorySize,
-	                               (int) v2::smem_bytes())) != cudaSuccess) {
+	                               (int) v2::smem_bytes())) != cudaSuccess ||
+	    (ce = cudaFuncSetAttribute(v3::tube_kernel_v3, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                               (int) v3::smem_bytes())) != cudaSuccess) {
 		if (h->d_src_tab) cudaFree(h->d_src_tab);
 		delete h;
 		return failCuda(ce, "gtts_create: device setup");
@@ -846,7 +916,7 @@ void gtts_batch_free(gtts_batch* b)
 	if (b->stream_out) { cudaStreamSynchronize(b->stream_out); cudaStreamDestroy(b->stream_out); }
 	if (b->ev_synth) cudaEventDestroy(b->ev_synth);
 	if (b->stream) { cudaStreamSynchronize(b->stream); cudaStreamDestroy(b->stream); }
-	cudaFree(b->d_voices); cudaFree(b->d_utts); cudaFree(b->d_order); cudaFree(b->d_queue);
+	cudaFree(b->d_voices); cudaFree(b->d_utts); cudaFree(b->d_order); cudaFree(b->d_order_wide); cudaFree(b->d_queue);
 	cudaFree(b->d_states); cudaFree(b->d_frames); cudaFree(b->d_out); cudaFree(b->d_tables);
 	cudaFree(b->d_pcm); cudaFree(b->d_peak); cudaFree(b->d_scale); cudaFree(b->d_utts_local);
 	delete b;
@@ -947,7 +1017,7 @@ int streamBuildGraph(gtts_stream* s)
 	Q.prof = nullptr;
 	Q.debug_skip = 0;
 	GTTS_CUDA(cudaStreamBeginCapture(b->stream, cudaStreamCaptureModeThreadLocal));
-	cudaError_t e = cudaMemsetAsync(b->d_queue, 0, 2 * sizeof(int32_t), b->stream);
+	cudaError_t e = cudaMemsetAsync(b->d_queue, 0, 4 * sizeof(int32_t), b->stream);
 	if (e == cudaSuccess) {
 		v2::tube_kernel_v2_stream<<<1, v2::kThreads, v2::smem_bytes(), b->stream>>>(Q);
 		e = cudaGetLastError();

@@ -273,3 +273,54 @@ extern "C" long long emu_stream_v2(const gtts_voice_config* voice, double contro
 	if (run(have > 0 ? (period0 + have) * steps - nInDone : 0, true)) return -1;
 	return nOutDone;
 }
+
+// ---- v3 (wide batch: one thread per utterance) --------------------------------------------------------------------
+#include "../../gama_tts_b200/csrc/tube_kernel_v3.cuh"
+
+extern "C" int emu_batch_v3(const gtts_voice_config* voices, int n_voices, const int* voice_index, double control_rate,
+			const int* steps_override, const float* frames, const long long* frame_offsets, long long n_utt,
+			float* out, long long* out_offsets, long long* out_lengths, int n_ctas)
+{
+	using namespace gtts;
+	BatchPlan plan;
+	int err = 0;
+	g_err = planBatch(voices, n_voices, voice_index, control_rate, steps_override,
+			reinterpret_cast<const int64_t*>(frame_offsets), n_utt, plan, &err);
+	if (err) return err;
+	for (long long u = 0; u <= n_utt; ++u) out_offsets[u] = plan.out_offsets[u];
+	for (long long u = 0; u < n_utt; ++u) out_lengths[u] = plan.utts[u].n_out;
+	if (!out) return 0;
+	for (const UttDesc& d : plan.utts) {
+		if (!plan.voices[d.voice].src_upsample) { g_err = "v3 takes up-sampling voices only"; return GTTS_ERR_UNSUPPORTED; }
+	}
+	std::vector<double> taps = designGlottalFir();
+	std::memset(c_fir, 0, sizeof c_fir);
+	for (size_t i = 0; i < taps.size(); ++i) c_fir[i] = taps[i];
+	c_lcg_init = lcgInitialState();
+	std::vector<double> h(kSrcFilterLen), dh(kSrcFilterLen);
+	buildSrcTables(h.data(), dh.data());
+	std::vector<double2> tab(kSrcFilterLen);
+	for (int i = 0; i < kSrcFilterLen; ++i) { tab[i].x = h[i]; tab[i].y = dh[i]; }
+	std::vector<double> tables(static_cast<size_t>(n_voices) * kTableLen);
+	for (int v = 0; v < n_voices; ++v) buildWavetable(plan.voices[v], tables.data() + static_cast<size_t>(v) * kTableLen);
+	const std::vector<int32_t> groups = wideGroups(plan, plan.order);
+
+	int queue = 0;
+	v3::KernelParamsV3 P;
+	P.voices = plan.voices.data();
+	P.tables = tables.data();
+	P.utts = plan.utts.data();
+	P.order = groups.data();
+	P.frames = frames;
+	P.out = out;
+	P.src_tab = tab.data();
+	P.queue = &queue;
+	P.n_groups = static_cast<int32_t>(groups.size() / 32);
+
+	std::vector<unsigned char> smem(v3::smem_bytes() + 64);
+	unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem.data()) + 15) & ~uintptr_t(15));
+	for (int b = 0; b < n_ctas; ++b) {
+		simt::run_cta(v3::kThreads, [&](int tid) { v3::tube_v3_cta_body(P, base, tid); });
+	}
+	return 0;
+}

@@ -219,3 +219,29 @@ def test_emulated_kernels_down_sampling_branch(emu, emu_v2, oracle):
             out = run()
             assert len(out) == len(ref)
             assert np.array_equal(out, ref)
+
+
+def test_emulated_wide_batch_kernel_matches_oracle(oracle, real_tracks):
+    # tube_kernel_v3.cuh (one thread per utterance, 32 utterances of a warp in lockstep): 70 ragged utterances, each
+    # its own voice (dynamic wavetable), a sine voice, one without noise modulation, an empty and a one-frame track,
+    # control periods of 1 sample and of a non-default rate; three groups, so a warp takes more than one
+    # (the FIR and SRC sums run on four / two accumulators: a float32 output sample may round the other way)
+    WIDE_TOL = 5e-8
+    emu = _pipelined_runner("emu_batch_v3")
+    rng = np.random.Generator(np.random.PCG64(11))
+    voices = [random_voice(rng) for _ in range(66)] + [default_voice("male"), default_voice("female"), default_voice("baby"),
+                                                        default_voice("small_child")]
+    voices[5]["waveform"] = 1
+    voices[7]["noise_modulation"] = 0
+    hello = real_tracks[0]
+    tracks = [T.synthetic_track(100 + i, int(rng.integers(20, 90))) for i in range(66)] + [hello[:60], hello[:1], hello[:0], hello[100:140]]
+    res = emu(voices, list(range(70)), tracks)
+    for v, tr, out in zip(voices, tracks, res):
+        ref = oracle.synthesize(v, tr)
+        assert len(out) == len(ref) and not np.isnan(out).any()
+        assert full_scale_error(out, ref) <= WIDE_TOL
+    v = default_voice("small_child")
+    tr = T.synthetic_track(9, 30)
+    assert full_scale_error(emu([v], [0], [tr], rate=500.0)[0], oracle.synthesize(v, tr, control_rate=500.0)) <= WIDE_TOL
+    params = np.repeat(hello[100:112], 9, axis=0)
+    assert full_scale_error(emu([v], [0], [params], steps=[1])[0], oracle.synthesize_samples(v, params)) <= WIDE_TOL

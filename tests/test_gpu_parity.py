@@ -251,6 +251,23 @@ def test_both_kernels_agree(synth, monkeypatch):
         assert full_scale_error(x, y) <= 1e-7
 
 
+def test_wide_batch_kernel_parity(synth, oracle, monkeypatch):
+    # GTTS_KERNEL=v3 forces the one-thread-per-utterance kernel (it is chosen on its own only for batches of very many
+    # short utterances): 200 ragged utterances, every one its own randomised voice, against the oracle; the
+    # down-sampling voice in the batch stays on the pipelined kernel
+    monkeypatch.setenv("GTTS_KERNEL", "v3")
+    rng = np.random.Generator(np.random.PCG64(77))
+    voices = [random_voice(np.random.Generator(np.random.PCG64(700 + u))) for u in range(197)]
+    voices += [default_voice("male"), default_voice("female"), dict(default_voice("baby"), vocal_tract_length=6.0)]
+    voices[3]["waveform"] = 1
+    tracks = [T.synthetic_track(800 + u, int(rng.integers(1, 300))) for u in range(200)]
+    outs = synth.synthesize(voices, tracks, voice_index=np.arange(200))
+    refs = _oracle_many(oracle, list(zip(voices, tracks)))
+    for out, ref in zip(outs, refs):
+        assert len(out) == len(ref)
+        assert full_scale_error(out, ref) <= TIGHT
+
+
 def test_pinned_host_output_is_written_directly(synth):
     # pinned host buffers are device-accessible: the kernel stores the audio straight into them
     # (device->host transfer overlapped with the synthesis); result must equal the staged path
