@@ -231,6 +231,16 @@ class Reference:
             raise RuntimeError(self.lib.ref_last_error().decode())
         return self._take(p, n)
 
+    def synthesize5(self, voice5, frames, control_rate=250.0, extra=None, model=5):
+        """Model 5 (or the plugin, model=2000 + extra dll_path) on a model-5 voice dict (gama_tts_b200.voices.default_voice5)."""
+        frames = _f32(frames).reshape(-1, 16)
+        p, n, rate = C.POINTER(C.c_float)(), C.c_long(), C.c_double()
+        rc = self.lib.ref_synthesize(config_text5(voice5, extra, model), control_rate, frames.ctypes.data, frames.shape[0],
+                                     C.byref(p), C.byref(n), C.byref(rate))
+        if rc:
+            raise RuntimeError(self.lib.ref_last_error().decode())
+        return self._take(p, n)
+
     def pcm16(self, audio, rate=48000.0):
         """The reference's own writer (Controller::writeOutputToFile + WAVEFileWriter) on a raw output buffer."""
         x = _f32(audio)
@@ -308,3 +318,85 @@ class Reference:
         if n < 0:
             raise RuntimeError(self.lib.ref_last_error().decode())
         return out[:n].copy()
+
+
+# ---- model 5 (VocalTractModel5<double, 1>) ------------------------------------------------------------------------
+VOICE5_KEYS_SCALAR = [
+    ("output_rate", float), ("waveform", int), ("glottal_pulse_tp", float), ("glottal_pulse_tn_min", float),
+    ("glottal_pulse_tn_max", float), ("breathiness", float), ("vocal_tract_length_offset", float),
+    ("vocal_tract_length", float), ("temperature", float), ("loss_factor", float), ("noise_modulation", int),
+    ("mix_offset", float), ("global_radius_coef", float), ("global_nasal_radius_coef", float),
+]
+VOICE5_KEYS_TAIL = [
+    ("glottal_noise_cutoff", float), ("frication_noise_cutoff", float), ("frication_factor", float),
+    ("min_glottal_loss", float), ("max_glottal_loss", float), ("glottal_lowpass_cutoff", float), ("bypass", int),
+    ("constant_radius_mouth_impedance", int), ("mouth_impedance_radius", float),
+]
+
+
+class Oracle5Voice(C.Structure):
+    _fields_ = ([(k, C.c_double if t is float else C.c_int) for k, t in VOICE5_KEYS_SCALAR]
+                + [("nasal_radius", C.c_double * 6), ("radius_coef", C.c_double * 8)]
+                + [(k, C.c_double if t is float else C.c_int) for k, t in VOICE5_KEYS_TAIL])
+
+
+def voice5_struct(voice):
+    s = Oracle5Voice()
+    for k, t in VOICE5_KEYS_SCALAR + VOICE5_KEYS_TAIL:
+        setattr(s, k, t(voice[k]))
+    for i in range(6):
+        s.nasal_radius[i] = float(voice["nasal_radius_%d" % (i + 2)])
+    for i in range(8):
+        s.radius_coef[i] = float(voice["radius_%d_coef" % (i + 1)])
+    return s
+
+
+def config_text5(voice, extra=None, model=5):
+    """A model-5 voice as the reference's key = value text (data/voice/english/5_xxx/vtm.txt + variant/xxx.txt)."""
+    lines = ["model = %d" % model, "log_parameters = false"]
+    for k, v in (extra or {}).items():
+        lines.append("%s = %s" % (k, v))
+    for k, t in VOICE5_KEYS_SCALAR + VOICE5_KEYS_TAIL:
+        if k == "constant_radius_mouth_impedance":
+            lines.append("%s = %s" % (k, "true" if voice[k] else "false"))
+        else:
+            lines.append("%s = %s" % (k, repr(float(voice[k])) if t is float else int(voice[k])))
+    for i in range(6):
+        lines.append("nasal_radius_%d = %r" % (i + 2, float(voice["nasal_radius_%d" % (i + 2)])))
+    for i in range(8):
+        lines.append("radius_%d_coef = %r" % (i + 1, float(voice["radius_%d_coef" % (i + 1)])))
+    return ("\n".join(lines) + "\n").encode()
+
+
+class Oracle5:
+    """oracle/tube5_oracle.c through ctypes."""
+
+    def __init__(self):
+        build(ref=False)
+        L = self.lib = C.CDLL(os.path.join(HERE, "liboracle.so"))
+        L.oracle5_synthesize.restype = C.c_long
+        L.oracle5_synthesize.argtypes = [C.POINTER(Oracle5Voice), C.c_double, C.c_int, C.c_void_p, C.c_long, C.c_void_p,
+                                         C.c_long, C.POINTER(C.c_double)]
+
+    def synthesize(self, voice, frames, control_rate=250.0, steps=0):
+        frames = _f32(frames).reshape(-1, 16)
+        vs = voice5_struct(voice)
+        rate = C.c_double()
+        probe = np.zeros(1, np.float32)
+        n = self.lib.oracle5_synthesize(C.byref(vs), control_rate, steps, frames.ctypes.data, frames.shape[0], probe.ctypes.data, 0,
+                                        C.byref(rate))
+        out = np.zeros(max(n, 1), np.float32)
+        n2 = self.lib.oracle5_synthesize(C.byref(vs), control_rate, steps, frames.ctypes.data, frames.shape[0], out.ctypes.data, n,
+                                         C.byref(rate))
+        assert n2 == n
+        return out[:n]
+
+    def synthesize_samples(self, voice, params):
+        return self.synthesize(voice, params, steps=1)[...]
+
+    def internal_rate(self, voice):
+        vs = voice5_struct(voice)
+        rate = C.c_double()
+        probe = np.zeros(1, np.float32)
+        self.lib.oracle5_synthesize(C.byref(vs), 250.0, 0, None, 0, probe.ctypes.data, 0, C.byref(rate))
+        return float(rate.value)

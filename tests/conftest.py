@@ -127,3 +127,28 @@ def snr_db(test, ref):
     if noise == 0:
         return float("inf")
     return float(10 * np.log10(sig / noise))
+
+
+class Golden5:
+    """tests/golden/golden5_v1.npz: the reference's model 5 on committed inputs (tools/make_golden5.py)."""
+
+    def __init__(self):
+        import json
+        self.z = np.load(os.path.join(GOLDEN, "golden5_v1.npz"))
+        self.names = [str(n) for n in self.z["names"]]
+        self._json = json
+
+    def case(self, name):
+        return (self._json.loads(str(self.z["voice_" + name])), self.z["track_" + name], self.z["ref_" + name],
+                self.z["nofma_" + name])
+
+
+@pytest.fixture(scope="session")
+def golden5():
+    return Golden5()
+
+
+@pytest.fixture(scope="session")
+def oracle5():
+    from oracle.pyoracle import Oracle5
+    return Oracle5()
