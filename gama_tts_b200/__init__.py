@@ -300,9 +300,74 @@ class TubeSynthesizer:
     def stream(self, voice, control_rate=voices.DEFAULT_CONTROL_RATE, steps_override=0):
         return Stream(self, voice, control_rate, steps_override)
 
+    # ---- model 5 (gtts5_*: VocalTractModel5<double, 1>) ----
+    def prepare5(self, voice_or_voices, frame_offsets, voice_index=None, control_rate=voices.DEFAULT_CONTROL_RATE,
+                 steps_override=None):
+        vl = [voice_or_voices] if isinstance(voice_or_voices, dict) else list(voice_or_voices)
+        return Batch5(self, vl, frame_offsets, voice_index, control_rate, steps_override)
+
+    def synthesize5(self, voice_or_voices, tracks, voice_index=None, control_rate=voices.DEFAULT_CONTROL_RATE,
+                    steps_override=None):
+        """Model-5 voices (voices.default_voice5): tracks -> list of float32 audio arrays (raw outputBuffer())."""
+        frames, fo = pack_tracks(tracks)
+        b = self.prepare5(voice_or_voices, fo, voice_index, control_rate, steps_override)
+        try:
+            return [a.copy() for a in b.split(b.run_host(frames))]
+        finally:
+            b.close()
+
     def close(self):
         if self._h:
             self._lib.gtts_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Batch5:
+    """gtts5_batch: a prepared batch of model-5 utterances."""
+
+    def __init__(self, synth, voice_list, frame_offsets, voice_index, control_rate, steps_override):
+        from .capi import voice5_array
+        self._lib = synth._lib
+        self._synth = synth
+        fo = np.ascontiguousarray(frame_offsets, np.int64)
+        self.n_utt = len(fo) - 1
+        va = voice5_array(voice_list)
+        vi = None if voice_index is None else np.ascontiguousarray(voice_index, np.int32)
+        so = None if steps_override is None else np.ascontiguousarray(steps_override, np.int32)
+        self._h = C.c_void_p()
+        check(self._lib.gtts5_batch_prepare(synth._h, va, len(voice_list), None if vi is None else vi.ctypes.data,
+                                            float(control_rate), None if so is None else so.ctypes.data, fo.ctypes.data,
+                                            self.n_utt, C.byref(self._h)))
+        self.out_offsets = np.zeros(self.n_utt + 1, np.int64)
+        self.n_out = np.zeros(max(self.n_utt, 1), np.int64)
+        self.n_internal = np.zeros(max(self.n_utt, 1), np.int64)
+        check(self._lib.gtts5_batch_layout(self._h, self.out_offsets.ctypes.data, self.n_out.ctypes.data, self.n_internal.ctypes.data))
+        self.n_out, self.n_internal = self.n_out[:self.n_utt], self.n_internal[:self.n_utt]
+        self.n_out_total = int(self.out_offsets[-1])
+        self.n_frames_total = int(fo[-1]) if len(fo) else 0
+
+    def run_host(self, frames):
+        frames = np.ascontiguousarray(frames, np.float32).reshape(-1, NUM_PARAMS)
+        assert frames.shape[0] == self.n_frames_total
+        out = np.zeros(max(self.n_out_total, 1), np.float32)
+        check(self._lib.gtts5_batch_run_host(self._h, frames.ctypes.data, out.ctypes.data))
+        return out
+
+    def run_device(self, d_frames_ptr, d_out_ptr, stream_ptr=0):
+        check(self._lib.gtts5_batch_run_device(self._h, d_frames_ptr, d_out_ptr, stream_ptr))
+
+    def split(self, out):
+        return [out[self.out_offsets[u]:self.out_offsets[u] + self.n_out[u]] for u in range(self.n_utt)]
+
+    def close(self):
+        if self._h:
+            self._lib.gtts5_batch_free(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):

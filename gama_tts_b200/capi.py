@@ -43,6 +43,46 @@ def voice_config(voice):
     return s
 
 
+class Voice5Config(C.Structure):
+    """struct gtts_voice5_config (model 5)"""
+    _fields_ = [
+        ("output_rate", C.c_double), ("waveform", C.c_int32), ("noise_modulation", C.c_int32), ("bypass", C.c_int32),
+        ("constant_radius_mouth_impedance", C.c_int32),
+        ("glottal_pulse_tp", C.c_double), ("glottal_pulse_tn_min", C.c_double), ("glottal_pulse_tn_max", C.c_double),
+        ("breathiness", C.c_double), ("vocal_tract_length_offset", C.c_double), ("vocal_tract_length", C.c_double),
+        ("temperature", C.c_double), ("loss_factor", C.c_double), ("mix_offset", C.c_double),
+        ("global_radius_coef", C.c_double), ("global_nasal_radius_coef", C.c_double),
+        ("nasal_radius", C.c_double * 6), ("radius_coef", C.c_double * 8),
+        ("glottal_noise_cutoff", C.c_double), ("frication_noise_cutoff", C.c_double), ("frication_factor", C.c_double),
+        ("min_glottal_loss", C.c_double), ("max_glottal_loss", C.c_double), ("glottal_lowpass_cutoff", C.c_double),
+        ("mouth_impedance_radius", C.c_double),
+    ]
+
+
+def voice5_config(voice):
+    """dict keyed like data/voice/english/5_xxx/vtm.txt + variant -> struct gtts_voice5_config."""
+    s = Voice5Config()
+    for name, ctype in Voice5Config._fields_:
+        if name == "nasal_radius":
+            for i in range(6):
+                s.nasal_radius[i] = float(voice["nasal_radius_%d" % (i + 2)])
+        elif name == "radius_coef":
+            for i in range(8):
+                s.radius_coef[i] = float(voice["radius_%d_coef" % (i + 1)])
+        elif ctype is C.c_int32:
+            setattr(s, name, int(voice[name]))
+        else:
+            setattr(s, name, float(voice[name]))
+    return s
+
+
+def voice5_array(voices):
+    arr = (Voice5Config * len(voices))()
+    for i, v in enumerate(voices):
+        arr[i] = voice5_config(v)
+    return arr
+
+
 def voice_array(voices):
     arr = (VoiceConfig * len(voices))()
     for i, v in enumerate(voices):
@@ -60,6 +100,8 @@ EXPORTS = [
     "gtts_multi_batch_run_host", "gtts_multi_batch_run_host_pcm16", "gtts_multi_batch_free",
     "gtts_batch_free", "gtts_batch_synthesize", "gtts_stream_open", "gtts_stream_push_frames",
     "gtts_stream_finish", "gtts_stream_reset", "gtts_stream_close",
+    "gtts5_voice_internal_rate", "gtts5_output_length", "gtts5_batch_prepare", "gtts5_batch_layout", "gtts5_batch_run_device",
+    "gtts5_batch_run_host", "gtts5_batch_free",
 ]
 
 _lib = None
@@ -121,6 +163,15 @@ def load():
     L.gtts_stream_reset.argtypes = [vp]
     L.gtts_stream_close.argtypes = [vp]
     L.gtts_stream_close.restype = None
+    PV5 = C.POINTER(Voice5Config)
+    L.gtts5_voice_internal_rate.argtypes = [PV5, C.POINTER(dbl)]
+    L.gtts5_output_length.argtypes = [PV5, dbl, i32, i64, C.POINTER(i32), C.POINTER(i64), C.POINTER(i64)]
+    L.gtts5_batch_prepare.argtypes = [vp, PV5, i32, vp, dbl, vp, vp, i64, C.POINTER(vp)]
+    L.gtts5_batch_layout.argtypes = [vp, vp, vp, vp]
+    L.gtts5_batch_run_device.argtypes = [vp, vp, vp, vp]
+    L.gtts5_batch_run_host.argtypes = [vp, vp, vp]
+    L.gtts5_batch_free.argtypes = [vp]
+    L.gtts5_batch_free.restype = None
     _lib = L
     return L
 

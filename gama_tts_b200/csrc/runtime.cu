@@ -25,6 +25,8 @@
 #include "tube_kernel_v1.cuh"
 #include "tube_kernel_v2.cuh"
 #include "tube_kernel_v3.cuh"
+#include "tube5_kernel.cuh"
+#include "model5_host.h"
 
 using namespace gtts;
 
@@ -572,7 +574,9 @@ int createHandle(int32_t device, gtts_handle** handle_out)
 	    (ce = cudaFuncSetAttribute(v2::tube_kernel_v2_stream, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	                               (int) v2::smem_bytes())) != cudaSuccess ||
 	    (ce = cudaFuncSetAttribute(v3::tube_kernel_v3, cudaFuncAttributeMaxDynamicSharedMemorySize,
-	                               (int) v3::smem_bytes())) != cudaSuccess) {
+	                               (int) v3::smem_bytes())) != cudaSuccess ||
+	    (ce = cudaFuncSetAttribute(m5::tube5_kernel<kWarpsPerCta>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                               (int) m5::smem_bytes(kWarpsPerCta))) != cudaSuccess) {
 		if (h->d_src_tab) cudaFree(h->d_src_tab);
 		delete h;
 		return failCuda(ce, "gtts_create: device setup");
@@ -1433,6 +1437,156 @@ int gtts_multi_batch_run_host_pcm16(gtts_multi_batch* b, const float* h_frames, 
 	} catch (const std::exception& e) {
 		return fail(GTTS_ERR_NOMEM, e.what());
 	}
+}
+
+} // extern "C"
+
+// ---- model 5 (VocalTractModel5<double, 1>): tube5_kernel.cuh, one warp per utterance ---------------------------------
+
+struct gtts5_batch {
+	gtts_handle* h = nullptr;
+	m5::BatchPlan5 plan;
+	m5::Voice5Dev* d_voices = nullptr;
+	UttDesc* d_utts = nullptr;
+	int32_t* d_order = nullptr;
+	int32_t* d_queue = nullptr;
+	float* d_frames = nullptr;
+	float* d_out = nullptr;
+	cudaStream_t stream = nullptr;
+};
+
+extern "C" {
+
+int gtts5_voice_internal_rate(const gtts_voice5_config* voice, double* fs_out)
+{
+	if (!voice || !fs_out) return fail(GTTS_ERR_INVALID, "null argument");
+	m5::Voice5Dev v;
+	bool unsupported = false;
+	const char* e = m5::deriveVoice5(*voice, v, &unsupported);
+	if (e && !unsupported) return fail(GTTS_ERR_INVALID, e);
+	*fs_out = v.fs;
+	return GTTS_OK;
+}
+
+int gtts5_output_length(const gtts_voice5_config* voice, double control_rate, int32_t steps, int64_t n_frames,
+			int32_t* steps_out, int64_t* n_internal_out, int64_t* n_output_out)
+{
+	if (!voice || n_frames < 0) return fail(GTTS_ERR_INVALID, "bad argument");
+	m5::Voice5Dev v;
+	bool unsupported = false;
+	const char* e = m5::deriveVoice5(*voice, v, &unsupported);
+	if (e) return fail(unsupported ? GTTS_ERR_UNSUPPORTED : GTTS_ERR_INVALID, e);
+	if (steps <= 0) {
+		if (!(control_rate > 0.0)) return fail(GTTS_ERR_INVALID, "control_rate must be positive");
+		steps = m5::controlSteps5(v.fs, control_rate);
+	}
+	if (steps <= 0) return fail(GTTS_ERR_INVALID, "control steps must be positive");
+	if (steps_out) *steps_out = steps;
+	if (n_internal_out) *n_internal_out = n_frames * steps;
+	if (n_output_out) *n_output_out = m5::outputLength5(v, n_frames * steps);
+	return GTTS_OK;
+}
+
+void gtts5_batch_free(gtts5_batch* b)
+{
+	if (!b) return;
+	cudaSetDevice(b->h->device);
+	cudaFree(b->d_voices); cudaFree(b->d_utts); cudaFree(b->d_order); cudaFree(b->d_queue);
+	cudaFree(b->d_frames); cudaFree(b->d_out);
+	if (b->stream) cudaStreamDestroy(b->stream);
+	delete b;
+}
+
+static int prepare5(gtts5_batch* b)
+{
+	m5::BatchPlan5& p = b->plan;
+	GTTS_CUDA(cudaSetDevice(b->h->device));
+	GTTS_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+	GTTS_CUDA(cudaMalloc(&b->d_voices, sizeof(m5::Voice5Dev) * std::max<size_t>(p.voices.size(), 1)));
+	GTTS_CUDA(cudaMalloc(&b->d_utts, sizeof(UttDesc) * std::max<size_t>(p.utts.size(), 1)));
+	GTTS_CUDA(cudaMalloc(&b->d_order, sizeof(int32_t) * std::max<size_t>(p.order.size(), 1)));
+	GTTS_CUDA(cudaMalloc(&b->d_queue, sizeof(int32_t)));
+	GTTS_CUDA(cudaMemcpyAsync(b->d_voices, p.voices.data(), sizeof(m5::Voice5Dev) * p.voices.size(), cudaMemcpyHostToDevice, b->stream));
+	if (!p.utts.empty()) {
+		GTTS_CUDA(cudaMemcpyAsync(b->d_utts, p.utts.data(), sizeof(UttDesc) * p.utts.size(), cudaMemcpyHostToDevice, b->stream));
+		GTTS_CUDA(cudaMemcpyAsync(b->d_order, p.order.data(), sizeof(int32_t) * p.order.size(), cudaMemcpyHostToDevice, b->stream));
+	}
+	GTTS_CUDA(cudaStreamSynchronize(b->stream));
+	return GTTS_OK;
+}
+
+int gtts5_batch_prepare(gtts_handle* h, const gtts_voice5_config* voices, int32_t n_voices,
+			const int32_t* voice_index, double control_rate, const int32_t* steps_override,
+			const int64_t* frame_offsets, int64_t n_utt, gtts5_batch** batch_out)
+{
+	if (!h || !batch_out) return fail(GTTS_ERR_INVALID, "null handle / output pointer");
+	*batch_out = nullptr;
+	try {
+		if (n_utt > std::numeric_limits<int32_t>::max()) return fail(GTTS_ERR_INVALID, "too many utterances");
+		gtts5_batch* b = new gtts5_batch;
+		b->h = h;
+		int err = GTTS_OK;
+		const std::string text = m5::planBatch5(voices, n_voices, voice_index, control_rate, steps_override, frame_offsets, n_utt, b->plan, &err);
+		if (err != GTTS_OK) { delete b; return fail(err, text); }
+		const int rc = prepare5(b);
+		if (rc != GTTS_OK) { gtts5_batch_free(b); return rc; }
+		*batch_out = b;
+		return GTTS_OK;
+	} catch (const std::exception& e) {
+		return fail(GTTS_ERR_NOMEM, e.what());
+	}
+}
+
+int gtts5_batch_layout(const gtts5_batch* b, int64_t* out_offsets, int64_t* n_out, int64_t* n_internal)
+{
+	if (!b) return fail(GTTS_ERR_INVALID, "null batch");
+	if (out_offsets) std::copy(b->plan.out_offsets.begin(), b->plan.out_offsets.end(), out_offsets);
+	for (size_t u = 0; u < b->plan.utts.size(); ++u) {
+		if (n_out) n_out[u] = b->plan.utts[u].n_out;
+		if (n_internal) n_internal[u] = b->plan.utts[u].n_internal;
+	}
+	return GTTS_OK;
+}
+
+int gtts5_batch_run_device(gtts5_batch* b, const float* d_frames, float* d_out, void* cuda_stream)
+{
+	if (!b) return fail(GTTS_ERR_INVALID, "null batch");
+	const int32_t nUtt = static_cast<int32_t>(b->plan.utts.size());
+	if (nUtt == 0) return GTTS_OK;
+	cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+	GTTS_CUDA(cudaSetDevice(b->h->device));
+	GTTS_CUDA(cudaMemsetAsync(b->d_queue, 0, sizeof(int32_t), stream));
+	m5::KernelParams5 P;
+	P.voices = b->d_voices;
+	P.utts = b->d_utts;
+	P.order = b->d_order;
+	P.frames = d_frames;
+	P.out = d_out;
+	P.src_tab = b->h->d_src_tab;
+	P.queue = b->d_queue;
+	P.n_utt = nUtt;
+	const int64_t ctasWanted = (static_cast<int64_t>(nUtt) + kWarpsPerCta - 1) / kWarpsPerCta;
+	const int grid = static_cast<int>(std::min<int64_t>(ctasWanted, b->h->sms));
+	m5::tube5_kernel<kWarpsPerCta><<<grid, kWarpsPerCta * 32, m5::smem_bytes(kWarpsPerCta), stream>>>(P);
+	GTTS_CUDA(cudaGetLastError());
+	return GTTS_OK;
+}
+
+int gtts5_batch_run_host(gtts5_batch* b, const float* h_frames, float* h_out)
+{
+	if (!b) return fail(GTTS_ERR_INVALID, "null batch");
+	const int64_t nFrames = b->plan.n_frames_total;
+	const int64_t nOut = b->plan.out_offsets.empty() ? 0 : b->plan.out_offsets.back();
+	if ((nFrames > 0 && !h_frames) || (nOut > 0 && !h_out)) return fail(GTTS_ERR_INVALID, "null host buffer");
+	GTTS_CUDA(cudaSetDevice(b->h->device));
+	if (!b->d_frames && nFrames > 0) GTTS_CUDA(cudaMalloc(&b->d_frames, sizeof(float) * kNumParams * nFrames));
+	if (!b->d_out && nOut > 0) GTTS_CUDA(cudaMalloc(&b->d_out, sizeof(float) * nOut));
+	if (nFrames > 0) GTTS_CUDA(cudaMemcpyAsync(b->d_frames, h_frames, sizeof(float) * kNumParams * nFrames, cudaMemcpyHostToDevice, b->stream));
+	const int rc = gtts5_batch_run_device(b, b->d_frames, b->d_out, b->stream);
+	if (rc != GTTS_OK) return rc;
+	if (nOut > 0) GTTS_CUDA(cudaMemcpyAsync(h_out, b->d_out, sizeof(float) * nOut, cudaMemcpyDeviceToHost, b->stream));
+	GTTS_CUDA(cudaStreamSynchronize(b->stream));
+	return GTTS_OK;
 }
 
 } // extern "C"

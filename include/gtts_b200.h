@@ -212,6 +212,64 @@ int gtts_stream_finish(gtts_stream* stream, float* out, int64_t out_capacity, in
 int gtts_stream_reset(gtts_stream* stream);
 void gtts_stream_close(gtts_stream* stream);
 
+/* ---- model 5 (BASELINE next row 1) -------------------------------------------------------------------------
+ * The same boundary for the reference's model 5, GS::VTM::VocalTractModel5<double, 1> -- the voice directories
+ * data/voice/english/5_xxx, which the reference's documentation uses by default:
+ *     setAllParameters / execSynthesisStep / finishSynthesis      gama_tts/src/vtm/VocalTractModel5.h:776-792, 527-582, 794-797
+ *     (Rosenberg-B source RosenbergBGlottalSource.h:112-150, Butterworth filters, pole-zero radiation impedance
+ *     PoleZeroRadiationImpedance.h:143-189, 30 + 21 flow-equation sections :646-730, down-sampling converter
+ *     SampleRateConverter.h:362-415, float difference filter * output rate :506-512)
+ * driven by the same Controller::synthesize interpolation (Controller.cpp:277-313).  The control frames are the same
+ * 16 parameters.  One warp per utterance (gama_tts_b200/csrc/tube5_kernel.cuh).  Internal rates from 50 kHz (below it the
+ * reference's radiation impedance refuses to construct) up to about 170 kHz (tracts down to 6.2 cm at 35 deg C: a
+ * converter wing of at most 48 taps) are accepted; the output rate must be below the internal rate. */
+typedef struct gtts_voice5_config {
+	double output_rate;                 /* Hz */
+	int32_t waveform;                   /* 0 = Rosenberg-B pulse, 1 = sine */
+	int32_t noise_modulation;
+	int32_t bypass;                     /* 1 = glottal waveform only */
+	int32_t constant_radius_mouth_impedance;
+	double glottal_pulse_tp;            /* % */
+	double glottal_pulse_tn_min;        /* % */
+	double glottal_pulse_tn_max;        /* % */
+	double breathiness;                 /* % */
+	double vocal_tract_length_offset;   /* cm */
+	double vocal_tract_length;          /* cm */
+	double temperature;                 /* deg C */
+	double loss_factor;                 /* % */
+	double mix_offset;                  /* dB */
+	double global_radius_coef;
+	double global_nasal_radius_coef;
+	double nasal_radius[6];             /* nasal_radius_2 .. nasal_radius_7, cm */
+	double radius_coef[8];              /* radius_1_coef .. radius_8_coef */
+	double glottal_noise_cutoff;        /* Hz */
+	double frication_noise_cutoff;      /* Hz */
+	double frication_factor;
+	double min_glottal_loss;            /* % */
+	double max_glottal_loss;            /* % */
+	double glottal_lowpass_cutoff;      /* Hz */
+	double mouth_impedance_radius;      /* cm, with constant_radius_mouth_impedance */
+} gtts_voice5_config;
+
+typedef struct gtts5_batch gtts5_batch;
+
+/* VocalTractModel5::internalSampleRate() (VocalTractModel5.h:464-465): a double for this model. */
+int gtts5_voice_internal_rate(const gtts_voice5_config* voice, double* fs_out);
+/* controlSteps (steps <= 0: rint(fs / control_rate), Controller.cpp:286), internal and output samples of a track. */
+int gtts5_output_length(const gtts_voice5_config* voice, double control_rate, int32_t steps, int64_t n_frames,
+			int32_t* steps_out, int64_t* n_internal_out, int64_t* n_output_out);
+/* Arguments as gtts_batch_prepare. */
+int gtts5_batch_prepare(gtts_handle* handle, const gtts_voice5_config* voices, int32_t n_voices,
+			const int32_t* voice_index, double control_rate, const int32_t* steps_override,
+			const int64_t* frame_offsets, int64_t n_utt, gtts5_batch** batch_out);
+/* out_offsets[n_utt + 1] (every utterance starts on a multiple of 64 samples), n_out[n_utt], n_internal[n_utt]; any may be NULL */
+int gtts5_batch_layout(const gtts5_batch* batch, int64_t* out_offsets, int64_t* n_out, int64_t* n_internal);
+/* Device buffers, asynchronous on cuda_stream. */
+int gtts5_batch_run_device(gtts5_batch* batch, const float* d_frames, float* d_out, void* cuda_stream);
+/* Host buffers (staged through device memory), synchronised on return. */
+int gtts5_batch_run_host(gtts5_batch* batch, const float* h_frames, float* h_out);
+void gtts5_batch_free(gtts5_batch* batch);
+
 #ifdef __cplusplus
 }
 #endif

@@ -324,3 +324,43 @@ extern "C" int emu_batch_v3(const gtts_voice_config* voices, int n_voices, const
 	}
 	return 0;
 }
+
+// ---- model 5 (tube5_kernel.cuh: one warp per utterance) -----------------------------------------------------------
+#include "../../gama_tts_b200/csrc/tube5_kernel.cuh"
+#include "../../gama_tts_b200/csrc/model5_host.h"
+
+extern "C" int emu_batch_m5(const gtts_voice5_config* voices, int n_voices, const int* voice_index, double control_rate,
+			const int* steps_override, const float* frames, const long long* frame_offsets, long long n_utt,
+			float* out, long long* out_offsets, long long* out_lengths, int warps_per_cta)
+{
+	using namespace gtts;
+	m5::BatchPlan5 plan;
+	int err = 0;
+	g_err = m5::planBatch5(voices, n_voices, voice_index, control_rate, steps_override,
+			reinterpret_cast<const int64_t*>(frame_offsets), n_utt, plan, &err);
+	if (err) return err;
+	for (long long u = 0; u <= n_utt; ++u) out_offsets[u] = plan.out_offsets[u];
+	for (long long u = 0; u < n_utt; ++u) out_lengths[u] = plan.utts[u].n_out;
+	if (!out) return 0;
+	lcgMultipliers(c_lcg);
+	c_lcg_init = lcgInitialState();
+	std::vector<double> h(kSrcFilterLen), dh(kSrcFilterLen);
+	buildSrcTables(h.data(), dh.data());
+	std::vector<double2> tab(kSrcFilterLen);
+	for (int i = 0; i < kSrcFilterLen; ++i) { tab[i].x = h[i]; tab[i].y = dh[i]; }
+	int queue = 0;
+	m5::KernelParams5 P;
+	P.voices = plan.voices.data();
+	P.utts = plan.utts.data();
+	P.order = plan.order.data();
+	P.frames = frames;
+	P.out = out;
+	P.src_tab = tab.data();
+	P.queue = &queue;
+	P.n_utt = static_cast<int32_t>(n_utt);
+	const int nthreads = warps_per_cta * 32;
+	std::vector<unsigned char> smem(m5::smem_bytes(warps_per_cta) + 64);
+	unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem.data()) + 15) & ~uintptr_t(15));
+	simt::run_cta(nthreads, [&](int tid) { m5::tube5_cta_body(P, base, tid, nthreads); });
+	return 0;
+}

@@ -471,3 +471,42 @@ def test_sharded_over_gpus_equals_one_gpu(synth):
         for i, out in zip(idx, part):
             assert np.array_equal(out, whole[i]), (r, i)
         dev.close()
+
+
+# ---- model 5 (gtts5_*, tube5_kernel.cuh) ------------------------------------------------------------------------------
+
+def test_model5_golden_vectors(synth, golden5):
+    # the reference's own model-5 outputs (tests/golden/golden5_v1.npz): all five shipped variants, randomised voices,
+    # constant-radius mouth impedance, sine source, bypass, modulation off, empty and one-frame tracks
+    for name in golden5.names:
+        voice, track, ref, _ = golden5.case(name)
+        out = synth.synthesize5(voice, [track])[0]
+        assert len(out) == len(ref), name
+        assert full_scale_error(out, ref) <= TIGHT, name
+
+
+def test_model5_ragged_batch_vs_oracle(synth, oracle5):
+    # 60 ragged utterances, every one its own randomised voice (internal rates 60-141 kHz), one batch: more warps
+    # than one CTA holds, the queue is used; control rates 250 and 500 Hz
+    from gama_tts_b200.voices import default_voice5, random_voice5
+    rng = np.random.Generator(np.random.PCG64(91))
+    voices = [random_voice5(np.random.Generator(np.random.PCG64(900 + u)), base=["male", "female", "baby"][u % 3]) for u in range(58)]
+    voices += [default_voice5("small_child"), default_voice5("large_child")]
+    tracks = [T.synthetic_track(950 + u, int(rng.integers(1, 200))) for u in range(60)]
+    for rate in (250.0, 500.0):
+        outs = synth.synthesize5(voices, tracks, voice_index=np.arange(60), control_rate=rate)
+        for v, tr, out in zip(voices, tracks, outs):
+            ref = oracle5.synthesize(v, tr, control_rate=rate)
+            assert len(out) == len(ref)
+            assert full_scale_error(out, ref) <= TIGHT
+
+
+def test_model5_rejects_what_the_reference_rejects(synth):
+    from gama_tts_b200.voices import default_voice5
+    tr = [T.synthetic_track(1, 5)]
+    with pytest.raises(g.GttsError) as e:
+        synth.synthesize5(dict(default_voice5("male"), vocal_tract_length=22.0), tr)     # internal rate below 50 kHz
+    assert e.value.code == g.capi.GTTS_ERR_INVALID
+    with pytest.raises(g.GttsError) as e:
+        synth.synthesize5(dict(default_voice5("male"), vocal_tract_length=5.0), tr)      # converter wing above 48 taps
+    assert e.value.code == g.capi.GTTS_ERR_UNSUPPORTED
