@@ -277,6 +277,44 @@ def config34_leg(synth, rank, world, dist, barrier, max_over_ranks, peak, args):
             "config4_bitwise_equal": bitwise}
 
 
+def model5_leg(synth, rank, peak):
+    """BASELINE next row 1, measured the same way on rank 0: a batch of model-5 utterances (voice 5_male, 60,411 Hz
+    internal rate, 48 kHz output), 12 per SM x 2 s each, device-resident, 3 warm-ups.  Work per unit: 397 flop
+    per internal sample + 168 per output sample (33-tap down-sampling converter), specials not counted."""
+    import torch
+    import gama_tts_b200 as g
+    from gama_tts_b200 import tracks as T
+    from gama_tts_b200.voices import default_voice5
+    if rank != 0:
+        return None
+    n_utt, n_frames = 1776, 500
+    tracks = [T.synthetic_track(SEED0 + 100000 + (u % 96), n_frames) for u in range(n_utt)]
+    frames, fo = g.pack_tracks(tracks)
+    b = synth.prepare5(default_voice5("male"), fo)
+    d_frames = torch.from_numpy(frames).cuda()
+    d_out = torch.empty(b.n_out_total, dtype=torch.float32, device="cuda")
+    s = torch.cuda.current_stream()
+    for _ in range(3):
+        b.run_device(d_frames.data_ptr(), d_out.data_ptr(), s.cuda_stream)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 3
+    e0.record(s)
+    for _ in range(reps):
+        b.run_device(d_frames.data_ptr(), d_out.data_ptr(), s.cuda_stream)
+    e1.record(s)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    n_internal, n_samples = int(b.n_internal.sum()), int(b.n_out.sum())
+    audio = n_samples / 48000.0
+    ach = (397.0 * n_internal + 168.0 * n_samples) / (ms * 1e-3) * 1e-12
+    finite = bool(torch.isfinite(d_out[::1009]).all().item())
+    b.close()
+    return {"workload": "%d model-5 utterances (voice 5_male, fs_int 60411.43 Hz) x %d frames (2 s), one GPU" % (n_utt, n_frames),
+            "kernel": "tube5_kernel", "utterances": n_utt, "audio_seconds": audio, "ms": ms, "value": audio / (ms * 1e-3),
+            "unit": UNIT, "warmup": 3, "reps": reps, "finite": finite, "roofline_frac": ach / peak, "achieved_tflops": ach}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -286,6 +324,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-config3", action="store_true", help="skip the config 3 / 4 leg")
     ap.add_argument("--config3-utts", type=int, default=16384)
+    ap.add_argument("--no-model5", action="store_true", help="skip the model-5 leg")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -412,6 +451,7 @@ def main():
 
     # ---- BASELINE configs 3 / 4: a fixed slice of the 65,536-utterance draw, sharded over the ranks ---------
     cfg34 = None if args.no_config3 else config34_leg(synth, rank, world, dist, barrier, max_over_ranks, peak, args)
+    m5 = None if args.no_model5 else model5_leg(synth, rank, peak)
 
     value = audio_seconds * world / (ms_dev * 1e-3)
     e2e_value = audio_seconds * world / (ms_e2e * 1e-3)
@@ -448,6 +488,8 @@ def main():
         }
         if cfg34 is not None:
             line["config3"] = cfg34
+        if m5 is not None:
+            line["model5"] = m5
         if world == 1 and not args.no_cpu_baseline:
             threads = host_threads()
             n_sample = min(N_UTT, threads * 16)

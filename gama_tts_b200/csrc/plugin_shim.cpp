@@ -48,8 +48,8 @@ public:
 	~B200VocalTractModel() noexcept override;
 
 	void reset() noexcept override;
-	double internalSampleRate() const noexcept override { return internalRate_; }
-	double outputSampleRate() const noexcept override { return voice_.output_rate; }
+	double internalSampleRate() const noexcept override { return model5_ ? internalRate5_ : internalRate_; }
+	double outputSampleRate() const noexcept override { return model5_ ? voice5_.output_rate : voice_.output_rate; }
 	void setParameter(int parameter, float value) noexcept override;
 	void setAllParameters(const std::vector<float>& parameters) noexcept override;
 	void execSynthesisStep() noexcept override;
@@ -59,7 +59,12 @@ public:
 private:
 	static gtts_handle* sharedHandle(int device);
 
+	void loadModel5(const GS::ConfigurationData& data);
+
 	gtts_voice_config voice_;
+	gtts_voice5_config voice5_;           // model-5 voice (the configuration has model 5's keys: see the constructor)
+	bool model5_ = false;
+	double internalRate5_ = 0.0;
 	gtts_handle* handle_ = nullptr;       // process-wide, not owned
 	int32_t internalRate_ = 0;
 	float current_[GTTS_NUM_PARAMS];
@@ -76,7 +81,23 @@ int g_lastStatus = GTTS_OK;                // status of the last finishSynthesis
 B200VocalTractModel::B200VocalTractModel(const GS::ConfigurationData& data, int device)
 {
 	std::memset(&voice_, 0, sizeof voice_);
+	std::memset(&voice5_, 0, sizeof voice5_);
 	std::memset(current_, 0, sizeof current_);
+	// Which of the reference's models this object stands in for: the configuration of a 5_xxx voice directory carries
+	// model 5's keys (VocalTractModel5.h:373-425), that of a 0_xxx directory model 0's; "model" itself says 2000 (the
+	// plugin) in both.
+	try {
+		(void) data.value<double>("glottal_noise_cutoff");
+		model5_ = true;
+	} catch (...) {
+		model5_ = false;
+	}
+	if (model5_) {
+		loadModel5(data);
+		handle_ = sharedHandle(device);
+		outputBuffer_.reserve(OUTPUT_BUFFER_RESERVE);
+		return;
+	}
 	voice_.output_rate = data.value<double>("output_rate");
 	voice_.waveform = data.value<int>("waveform");
 	voice_.glottal_pulse_tp = data.value<double>("glottal_pulse_tp");
@@ -104,6 +125,40 @@ B200VocalTractModel::B200VocalTractModel(const GS::ConfigurationData& data, int 
 	if (gtts_output_length(&voice_, 1, 0, &nInternal, &nOut) != GTTS_OK) throw std::runtime_error(gtts_last_error());
 	handle_ = sharedHandle(device);
 	outputBuffer_.reserve(OUTPUT_BUFFER_RESERVE);
+}
+
+// Same keys as VocalTractModel5::loadConfiguration (VocalTractModel5.h:373-425).
+void B200VocalTractModel::loadModel5(const GS::ConfigurationData& data)
+{
+	gtts_voice5_config& v = voice5_;
+	v.output_rate = data.value<double>("output_rate");
+	v.waveform = data.value<int>("waveform");
+	v.glottal_pulse_tp = data.value<double>("glottal_pulse_tp");
+	v.glottal_pulse_tn_min = data.value<double>("glottal_pulse_tn_min");
+	v.glottal_pulse_tn_max = data.value<double>("glottal_pulse_tn_max");
+	v.breathiness = data.value<double>("breathiness");
+	v.vocal_tract_length_offset = data.value<double>("vocal_tract_length_offset");
+	v.vocal_tract_length = data.value<double>("vocal_tract_length");
+	v.temperature = data.value<double>("temperature");
+	v.loss_factor = data.value<double>("loss_factor");
+	v.noise_modulation = data.value<int>("noise_modulation");
+	v.mix_offset = data.value<double>("mix_offset");
+	v.global_radius_coef = data.value<double>("global_radius_coef");
+	v.global_nasal_radius_coef = data.value<double>("global_nasal_radius_coef");
+	for (int i = 0; i < 6; ++i) v.nasal_radius[i] = data.value<double>("nasal_radius_" + std::to_string(i + 2));
+	for (int i = 0; i < 8; ++i) v.radius_coef[i] = data.value<double>("radius_" + std::to_string(i + 1) + "_coef");
+	v.glottal_noise_cutoff = data.value<double>("glottal_noise_cutoff");
+	v.frication_noise_cutoff = data.value<double>("frication_noise_cutoff");
+	v.frication_factor = data.value<double>("frication_factor");
+	v.min_glottal_loss = data.value<double>("min_glottal_loss");
+	v.max_glottal_loss = data.value<double>("max_glottal_loss");
+	v.glottal_lowpass_cutoff = data.value<double>("glottal_lowpass_cutoff");
+	v.bypass = data.value<int>("bypass");
+	v.constant_radius_mouth_impedance = data.value<bool>("constant_radius_mouth_impedance") ? 1 : 0;
+	if (v.constant_radius_mouth_impedance) v.mouth_impedance_radius = data.value<double>("mouth_impedance_radius");
+	int64_t nInternal = 0, nOut = 0;
+	if (gtts5_output_length(&v, 250.0, 1, 0, nullptr, &nInternal, &nOut) != GTTS_OK) throw std::runtime_error(gtts_last_error());
+	if (gtts5_voice_internal_rate(&v, &internalRate5_) != GTTS_OK) throw std::runtime_error(gtts_last_error());
 }
 
 // The host constructs one model per synthesis and dlcloses the plugin after it (VocalTractModelPlugin.cpp:95-98).
@@ -186,6 +241,33 @@ void B200VocalTractModel::finishSynthesis() noexcept
 		return;
 	}
 	g_lastStatus = GTTS_OK;
+	if (model5_) {
+		gtts5_batch* b5 = nullptr;
+		try {
+			const int64_t nSamples = static_cast<int64_t>(recorded_.size() / GTTS_NUM_PARAMS);
+			const int64_t frameOffsets[2] = {0, nSamples};
+			const int32_t steps[1] = {1};
+			int rc = gtts5_batch_prepare(handle_, &voice5_, 1, nullptr, 250.0, steps, frameOffsets, 1, &b5);
+			if (rc != GTTS_OK) { g_lastStatus = rc; fail(gtts_last_error()); failed_ = false; return; }
+			int64_t outOffsets[2] = {0, 0};
+			int64_t nOut = 0;
+			gtts5_batch_layout(b5, outOffsets, &nOut, nullptr);
+			const size_t base = outputBuffer_.size();
+			outputBuffer_.resize(base + static_cast<size_t>(outOffsets[1]));
+			rc = gtts5_batch_run_host(b5, recorded_.data(), outputBuffer_.data() + base);
+			gtts5_batch_free(b5);
+			b5 = nullptr;
+			if (rc != GTTS_OK) { g_lastStatus = rc; fail(gtts_last_error()); failed_ = false; return; }
+			outputBuffer_.resize(base + static_cast<size_t>(nOut));
+			recorded_.clear();
+		} catch (...) {
+			if (b5) gtts5_batch_free(b5);
+			g_lastStatus = GTTS_ERR_NOMEM;
+			fail("out of memory in finishSynthesis");
+			failed_ = false;
+		}
+		return;
+	}
 	gtts_batch* batch = nullptr;
 	try {
 		const int64_t nSamples = static_cast<int64_t>(recorded_.size() / GTTS_NUM_PARAMS);

@@ -49,6 +49,7 @@ int failCuda(cudaError_t e, const char* what)
 #define GTTS_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return failCuda(e_, #call); } while (0)
 
 constexpr int kWarpsPerCta = 8;
+constexpr int kWarps5 = 12;              // model-5 kernel: warps (utterances) per CTA, one CTA per SM (12 x 12 KB + the 53 KB converter table)
 
 // FP64 FMA-pipe peak probe: 8 independent register-resident DFMA chains per thread.
 __global__ void fp64_peak_kernel(double* out, int iters, double a, double b)
@@ -575,8 +576,8 @@ int createHandle(int32_t device, gtts_handle** handle_out)
 	                               (int) v2::smem_bytes())) != cudaSuccess ||
 	    (ce = cudaFuncSetAttribute(v3::tube_kernel_v3, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	                               (int) v3::smem_bytes())) != cudaSuccess ||
-	    (ce = cudaFuncSetAttribute(m5::tube5_kernel<kWarpsPerCta>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-	                               (int) m5::smem_bytes(kWarpsPerCta))) != cudaSuccess) {
+	    (ce = cudaFuncSetAttribute(m5::tube5_kernel<kWarps5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                               (int) m5::smem_bytes(kWarps5))) != cudaSuccess) {
 		if (h->d_src_tab) cudaFree(h->d_src_tab);
 		delete h;
 		return failCuda(ce, "gtts_create: device setup");
@@ -1565,9 +1566,10 @@ int gtts5_batch_run_device(gtts5_batch* b, const float* d_frames, float* d_out, 
 	P.src_tab = b->h->d_src_tab;
 	P.queue = b->d_queue;
 	P.n_utt = nUtt;
-	const int64_t ctasWanted = (static_cast<int64_t>(nUtt) + kWarpsPerCta - 1) / kWarpsPerCta;
+	// few utterances: one warp per CTA spreads them over the SMs; many: kWarps5 per SM
+	const int64_t ctasWanted = std::max<int64_t>(std::min<int64_t>(nUtt, b->h->sms), (static_cast<int64_t>(nUtt) + kWarps5 - 1) / kWarps5);
 	const int grid = static_cast<int>(std::min<int64_t>(ctasWanted, b->h->sms));
-	m5::tube5_kernel<kWarpsPerCta><<<grid, kWarpsPerCta * 32, m5::smem_bytes(kWarpsPerCta), stream>>>(P);
+	m5::tube5_kernel<kWarps5><<<grid, kWarps5 * 32, m5::smem_bytes(kWarps5), stream>>>(P);
 	GTTS_CUDA(cudaGetLastError());
 	return GTTS_OK;
 }

@@ -245,3 +245,39 @@ def test_emulated_wide_batch_kernel_matches_oracle(oracle, real_tracks):
     assert full_scale_error(emu([v], [0], [tr], rate=500.0)[0], oracle.synthesize(v, tr, control_rate=500.0)) <= WIDE_TOL
     params = np.repeat(hello[100:112], 9, axis=0)
     assert full_scale_error(emu([v], [0], [params], steps=[1])[0], oracle.synthesize_samples(v, params)) <= WIDE_TOL
+
+
+def test_emulated_model5_kernel_matches_oracle(oracle5, real_tracks):
+    # tube5_kernel.cuh under the emulator against oracle/tube5_oracle.c (itself bit-identical to the reference's model 5):
+    # with host libm and no FMA contraction the kernel's blocking, lane roles, shuffles and converter reproduce it
+    # bit for bit -- all source / output variants, a randomised voice, the shortest tract (39-tap wings), empty and
+    # one-frame tracks, two warps sharing the queue
+    from gama_tts_b200.capi import voice5_array
+    from gama_tts_b200.voices import default_voice5, random_voice5
+    subprocess.run(["make", "-s", "-C", os.path.join(HERE, "simt_emu")], check=True)
+    L = C.CDLL(os.path.join(HERE, "simt_emu", "libemu_tube.so"))
+    L.emu_last_error.restype = C.c_char_p
+    fn = L.emu_batch_m5
+    fn.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong,
+                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    hello, shells = real_tracks[0], real_tracks[2]
+    rng = np.random.Generator(np.random.PCG64(3))
+    voices = [default_voice5("male"), random_voice5(rng), default_voice5("baby"),
+              dict(default_voice5("male"), constant_radius_mouth_impedance=1), dict(default_voice5("male"), waveform=1),
+              dict(default_voice5("male"), bypass=1), dict(default_voice5("female"), noise_modulation=0)]
+    tracks = [hello[:24], shells[236:252], hello[104:116], hello[:9], hello[:9], hello[:9], hello[44:56], hello[:0], hello[:1]]
+    vidx = [0, 1, 2, 3, 4, 5, 6, 0, 0]
+    va = voice5_array(voices)
+    frames, fo = pack_tracks(tracks)
+    vi = np.ascontiguousarray(vidx, np.int32)
+    oo = np.zeros(len(tracks) + 1, np.int64)
+    ol = np.zeros(len(tracks) + 1, np.int64)
+    args = [va, len(voices), vi.ctypes.data, 250.0, None, frames.ctypes.data, fo.ctypes.data, len(tracks)]
+    assert fn(*args, None, oo.ctypes.data, ol.ctypes.data, 2) == 0, L.emu_last_error()
+    out = np.full(int(oo[-1]), np.nan, np.float32)
+    assert fn(*args, out.ctypes.data, oo.ctypes.data, ol.ctypes.data, 2) == 0, L.emu_last_error()
+    for u, (v_i, tr) in enumerate(zip(vidx, tracks)):
+        ref = oracle5.synthesize(voices[v_i], tr)
+        got = out[oo[u]:oo[u] + ol[u]]
+        assert len(got) == len(ref)
+        assert np.array_equal(got, ref), u

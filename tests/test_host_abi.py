@@ -18,7 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_header_symbols_all_exported(product_lib):
     hdr = open(os.path.join(ROOT, "include", "gtts_b200.h")).read()
-    declared = sorted(set(re.findall(r"\b(gtts_[a-z0-9_]+)\s*\(", hdr)))
+    declared = sorted(set(re.findall(r"\b(gtts5?_[a-z0-9_]+)\s*\(", hdr)))
     assert declared and set(declared) == set(capi.EXPORTS)
     for name in declared:
         assert hasattr(product_lib, name), name
@@ -130,3 +130,27 @@ def test_product_does_not_reference_the_oracle():
     # tube_kernel.cuh only *mentions* the emulator in a comment; it must not include it
     bad = [b for b in bad if not b.endswith("tube_kernel.cuh")]
     assert not bad, bad
+
+
+def test_model5_host_entry_points(product_lib, oracle5):
+    # gtts5_* host-only helpers: internal rate (a double for this model), control steps and output length against
+    # the model-5 oracle; what the reference refuses is refused, what this path does not implement says so
+    from gama_tts_b200.voices import default_voice5, random_voice5
+    assert C.sizeof(capi.Voice5Config) == 8 + 4 * 4 + 8 * (11 + 6 + 8 + 7)
+    rng = np.random.Generator(np.random.PCG64(2))
+    for v in [default_voice5(n) for n in ("male", "female", "large_child", "small_child", "baby")] + [random_voice5(rng)]:
+        vc = capi.voice5_config(v)
+        fs = C.c_double()
+        capi.check(product_lib.gtts5_voice_internal_rate(C.byref(vc), C.byref(fs)))
+        assert fs.value == oracle5.internal_rate(v)
+        tr = T.synthetic_track(4, 7)
+        steps, n_int, n_out = C.c_int32(), C.c_int64(), C.c_int64()
+        capi.check(product_lib.gtts5_output_length(C.byref(vc), 250.0, 0, len(tr), C.byref(steps), C.byref(n_int), C.byref(n_out)))
+        assert steps.value == int(np.rint(fs.value / 250.0)) and n_int.value == steps.value * len(tr)
+        assert n_out.value == len(oracle5.synthesize(v, tr))
+    assert abs(oracle5.internal_rate(default_voice5("male")) - 60411.428571428) < 1e-6
+    n_out = C.c_int64()
+    bad = capi.voice5_config(dict(default_voice5("male"), vocal_tract_length=22.0))
+    assert product_lib.gtts5_output_length(C.byref(bad), 250.0, 0, 5, None, None, C.byref(n_out)) == capi.GTTS_ERR_INVALID
+    short = capi.voice5_config(dict(default_voice5("male"), vocal_tract_length=5.0))
+    assert product_lib.gtts5_output_length(C.byref(short), 250.0, 0, 5, None, None, C.byref(n_out)) == capi.GTTS_ERR_UNSUPPORTED

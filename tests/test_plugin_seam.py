@@ -50,6 +50,20 @@ def test_reference_drives_plugin_through_its_own_seam(reference, oracle, real_tr
         assert full_scale_error(out, oracle.synthesize(v, track)) <= 2e-7
 
 
+@pytest.mark.gpu
+def test_reference_drives_plugin_model5_voice(reference, oracle5, real_tracks, product_lib):
+    # a 5_xxx voice (model 5's configuration keys) with model = 2000: the shim stands in for VocalTractModel5
+    from gama_tts_b200.voices import default_voice5
+    _need_plugin()
+    for var, track in (("male", real_tracks[0][:200]), ("female", real_tracks[1][300:380])):
+        v = default_voice5(var)
+        out = reference.synthesize5(v, track, model=2000, extra={"dll_path": PLUGIN})
+        builtin = reference.synthesize5(v, track)
+        assert len(out) == len(builtin)
+        assert full_scale_error(out, builtin) <= 2e-7
+        assert np.array_equal(builtin, oracle5.synthesize(v, track))
+
+
 STOCK = os.path.join(ROOT, "oracle", "_ref", "gama_tts")
 STOCK_VOICE = os.path.join(ROOT, "oracle", "_ref", "voice_0_male")
 

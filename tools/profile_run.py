@@ -17,6 +17,7 @@ def main():
     ap.add_argument("--frames", type=int, default=100)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--lib", default=None, help="time another build of the library (tools/ab_build.sh)")
+    ap.add_argument("--model5", action="store_true", help="model-5 utterances (voice 5_male) on tube5_kernel")
     args = ap.parse_args()
     import torch
     if args.lib:
@@ -29,7 +30,14 @@ def main():
     frames = np.concatenate([base[u % len(base)] for u in range(args.utts)])
     fo = np.arange(args.utts + 1, dtype=np.int64) * args.frames
     synth = g.TubeSynthesizer(0)
-    b = synth.prepare(default_voice("male"), fo)
+    if args.model5:
+        from gama_tts_b200.voices import default_voice5
+        b = synth.prepare5(default_voice5("male"), fo)
+        b.n_samples_total = int(b.n_out.sum())
+        steps = int(b.n_internal[0] // args.frames)
+    else:
+        b = synth.prepare(default_voice("male"), fo)
+        steps = 80
     d_frames = torch.from_numpy(frames).cuda()
     d_out = torch.zeros(b.n_out_total, dtype=torch.float32, device="cuda")
     s = torch.cuda.current_stream()
@@ -41,7 +49,7 @@ def main():
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
         print("launch %d: %.3f ms  (%.1f ns per internal sample per utterance, %.0f audio-s/s)" %
-              (r, ms, ms * 1e6 / (args.frames * 80), b.n_samples_total / 48000.0 / (ms * 1e-3)))
+              (r, ms, ms * 1e6 / (args.frames * steps), b.n_samples_total / 48000.0 / (ms * 1e-3)))
     print("checksum", float(d_out[::997].double().abs().sum()))
 
 
