@@ -4,9 +4,9 @@
 //   lane = sample    parameter conversion (VocalTractModel5.h:527-533, 610-630, 776-792: 2^x, 10^x, 9 junction
 //                    divisions, the mouth radiation impedance from R8 -- cos, sqrt, 2 divisions per sample --, bandpass
 //                    coefficients), noise by LCG jump-ahead, the Rosenberg-B pulse value from its phase, mixing
-//   lane = filter    the serial one- and two-pole filters, three at a time on three lanes: glottal-noise and
-//                    frication-noise Butterworth low-passes and the pulse phase; then the glottal low-pass; then the
-//                    frication bandpass
+//   lane = filter    the serial recurrences: the pulse phase (one lane); the three Butterworth low-passes -- glottal
+//                    noise, frication noise, glottal wave -- on three lanes in one instruction stream; the frication
+//                    bandpass (one lane)
 //   lane = section   the tube (:646-730): 30 oropharynx sections on lanes 0..29 and the 21 nasal sections on lanes
 //                    12..31, 0 -- N1 shares a lane with S13, so the three waves of the velum junction are already
 //                    where the four neighbour shuffles of a sample put them.  Flow-equation junctions and plain
@@ -14,9 +14,10 @@
 //   lane = output    down-sampling windowed-sinc converter (SampleRateConverter.h:362-415), then the float32
 //                    difference filter * output rate of the output callback (:497-513, DifferenceFilter.h:62-69)
 //
-// Arithmetic: IEEE double in the reference's order of evaluation, FMA contraction allowed; 2^x / 10^x by the
-// branch-free forms of tube_kernel.cuh (<= 2 ulp); cos / tan / sqrt / division as CUDA provides them (<= 2 ulp, sqrt
-// and division exact).  Noise generator and float32 interpolation bit-exact.
+// Arithmetic: IEEE double in the reference's order of evaluation, FMA contraction allowed; 2^x / 10^x / sin / cos and
+// the coefficient divisions by the branch-free forms of tube_kernel.cuh (<= 2 ulp; tan as sin / cos folded into the one
+// division that follows it); sqrt and the pulse-shape divisions exact.  Noise generator and float32 interpolation
+// bit-exact.
 //
 // Also compiled for the host by tests/simt_emu (GTTS_EMU): test infrastructure, never linked into the product.
 #ifndef GTTS_TUBE5_KERNEL_CUH_
@@ -25,6 +26,10 @@
 #include "tube_kernel.cuh"
 #include "tube5_types.h"
 
+#ifndef GTTS_M5_TUBE_CHUNK
+#define GTTS_M5_TUBE_CHUNK 1     // measured on B200: 1 -> 46.9 k audio-s/s, 2 -> 44.6 k, 4 -> 42.8 k, 8 -> 33.2 k (registers, not latency, are what is short)
+#endif
+
 namespace gtts {
 namespace m5 {
 
@@ -32,6 +37,7 @@ enum {
 	kRow = 33,
 	kRing = 128,                // tube-output ring (doubles)
 	kYRing = 64,                // raw converter outputs (float) for the difference filter
+	kTubeChunk = GTTS_M5_TUBE_CHUNK,   // samples whose operands the tube loop fetches at once
 };
 
 enum {
@@ -43,12 +49,13 @@ enum {
 	R_CT1, R_CT2, R_CT3, R_CR2, R_CR3,   // mouth radiation impedance
 	R_BPA2, R_BPA1, R_BPB0,
 	R_FL, R_FR,                 // frication weights of sections S6 + fo, S6 + fo + 1
+	R_FVL, R_FVR,               // frication values injected into those sections
 	R_MINGL, R_DGL,
 	R_NT2,                      // t2 the source takes at its next wrap
 	R_NOISE, R_GN, R_FN,
 	R_T, R_T2,                  // pulse phase and fall end per sample
 	R_PULSE,                    // source value, then the low-passed pulse
-	R_IN, R_FRIC, R_GL, R_FV,
+	R_IN, R_FRIC, R_GL,
 	R_FLOWM, R_FLOWN,
 	R_COUNT
 };
@@ -91,31 +98,36 @@ GTTS_DEV void stage_convert5(WarpSm5* S, const Voice5Dev& V, int lane, int nb)
 			r2[i] = r[i] * r[i];
 		}
 #pragma unroll
-		for (int i = 0; i < 7; ++i) S->row[R_J0 + i][lane] = (r2[i] - r2[i + 1]) / (r2[i] + r2[i + 1]);
+		for (int i = 0; i < 7; ++i) S->row[R_J0 + i][lane] = div_fast(r2[i] - r2[i + 1], r2[i] + r2[i + 1]);
 		const double vel = (double) p[15];
 		const double v2 = vel * vel;
 		{
 			// Junction3::configure (:281-292) with left == right == R4
-			const double c = 1.0 / (r2[3] + r2[3] + v2);
+			const double c = div_fast(1.0, r2[3] + r2[3] + v2);
 			S->row[R_VL][lane] = c * (r2[3] - r2[3] - v2);
 			S->row[R_VR][lane] = c * (r2[3] - r2[3] - v2);
 			S->row[R_VU][lane] = c * (v2 - r2[3] - r2[3]);
 		}
-		S->row[R_NJ1][lane] = (v2 - V.nr2_2) / (v2 + V.nr2_2);
+		S->row[R_NJ1][lane] = div_fast(v2 - V.nr2_2, v2 + V.nr2_2);
 		if (!V.const_mouth) {
 			// PoleZeroRadiationImpedance::update (PoleZeroRadiationImpedance.h:143-176), radius in metres
 			const double radius = r[7] * (double) 1.0e-2f;
 			const double rr = radius < 0.5e-2 ? 0.5e-2 : radius;
-			const double transFreq = 62.3371 / rr + 320.204;
+			const double transFreq = div_fast(62.3371, rr) + 320.204;
+#ifndef GTTS_EMU
+			double sinWT, cosWT;
+			gtts_sincos((2.0 * 3.14159265358979323846) * transFreq * V.Ts, sinWT, cosWT);
+#else
 			const double cosWT = cos((2.0 * 3.14159265358979323846) * transFreq * V.Ts);
+#endif
 			const double qa = 2.0 * cosWT;
 			const double qb = -2.0 * (cosWT + 1.0);
 			const double qc = cosWT + 1.0;
 			const double delta = qb * qb - 4.0 * qa * qc;
-			double a = (-qb - sqrt(delta)) / (2.0 * qa);
+			double a = div_fast(-qb - sqrt(delta), 2.0 * qa);
 			const double b = 2.0 * a - 1.0;
 			if (radius < 0.5e-2) a *= 40391.2 * (radius * radius);
-			const double coef = 1.0 / (a + 1.0);
+			const double coef = div_fast(1.0, a + 1.0);
 			S->row[R_CT1][lane] = (a + b) * coef;
 			S->row[R_CT2][lane] = 2.0 * coef;
 			S->row[R_CT3][lane] = -2.0 * b * coef;
@@ -128,9 +140,17 @@ GTTS_DEV void stage_convert5(WarpSm5* S, const Voice5Dev& V, int lane, int nb)
 		{
 			// BandpassFilter::update (BandpassFilter.h:88-110)
 			const double pi = 3.14159265358979323846;
+#ifndef GTTS_EMU
+			// a2 = (1 - tan x) / (1 + tan x) = (cos x - sin x) / (cos x + sin x): one division
+			double sx, cx, sy, cv;
+			gtts_sincos(pi * (double) p[6] * V.Ts, sx, cx);
+			gtts_sincos(2.0 * pi * (double) p[5] * V.Ts, sy, cv);
+			const double a2 = div_fast(cx - sx, cx + sx);
+#else
 			const double tv = tan(pi * (double) p[6] * V.Ts);
 			const double cv = cos(2.0 * pi * (double) p[5] * V.Ts);
 			const double a2 = (1.0 - tv) / (1.0 + tv);
+#endif
 			S->row[R_BPA2][lane] = a2;
 			S->row[R_BPA1][lane] = -(1.0 + a2) * cv;
 			S->row[R_BPB0][lane] = 0.5 - 0.5 * a2;
@@ -167,42 +187,35 @@ GTTS_DEV void stage_noise5(WarpSm5* S, int lane, int nb, unsigned long long& lcg
 }
 
 struct Serial5 {
-	double a, b, c, d;          // lane 0: glottal-noise filter x1, y1; lane 1: frication-noise x1, x2, y1, y2; lane 2: t, t2
-	double glX1, glY1;          // lane 0, second pass: glottal low-pass
-	double bpX1, bpX2, bpY1, bpY2;   // lane 0, third pass: frication bandpass
+	double x1, x2, y1, y2;      // lane 0: glottal-noise low-pass, lane 1: frication-noise low-pass, lane 2: glottal low-pass
+	double t, t2;               // lane 0: pulse phase and the end of its fall
+	double bpX1, bpX2, bpY1, bpY2;   // lane 0: frication bandpass
 };
 
-// the three feed-forward recurrences, one per lane
-GTTS_DEV void stage_serial_a(WarpSm5* S, const Voice5Dev& V, int lane, int nb, Serial5& s)
+// RosenbergBGlottalSource::getSample (:122-150): the phase and the fall end each sample sees, one lane
+GTTS_DEV void stage_phase5(WarpSm5* S, const Voice5Dev& V, int lane, int nb, Serial5& s)
 {
 	if (lane == 0) {
-		// Butterworth1LowPassFilter::filter (:89-96)
-		for (int j = 0; j < nb; ++j) {
-			const double x = S->row[R_NOISE][j];
-			const double y = V.gn_b0 * (x + s.a) - V.gn_a1 * s.b;
-			s.a = x; s.b = y;
-			S->row[R_GN][j] = y;
-		}
-	} else if (lane == 1) {
-		// Butterworth2LowPassFilter::filter (:104-113)
-		for (int j = 0; j < nb; ++j) {
-			const double x = S->row[R_NOISE][j];
-			const double y = V.fn_b0 * (x + s.b) + V.fn_b1 * s.a - V.fn_a1 * s.c - V.fn_a2 * s.d;
-			s.b = s.a; s.a = x; s.d = s.c; s.c = y;
-			S->row[R_FN][j] = y;
-		}
-	} else if (lane == 2) {
-		// RosenbergBGlottalSource::getSample (:122-150): the phase and the fall end each sample sees
 		const bool dynamic = V.waveform == 0 && V.tn_min != V.tn_max;
-		for (int j = 0; j < nb; ++j) {
-			S->row[R_T][j] = s.a;
-			S->row[R_T2][j] = s.b;
-			s.a += S->row[R_DT][j];
-			if (s.a > 1.0) {
-				s.a -= 1.0;
-				if (dynamic) s.b = S->row[R_NT2][j];
+		double t = s.t, t2 = s.t2;
+		for (int j0 = 0; j0 < nb; j0 += 4) {
+			double dt[4], nt2[4];
+#pragma unroll
+			for (int q = 0; q < 4; ++q) { dt[q] = S->row[R_DT][j0 + q]; nt2[q] = S->row[R_NT2][j0 + q]; }
+#pragma unroll
+			for (int q = 0; q < 4; ++q) {
+				if (j0 + q < nb) {
+					S->row[R_T][j0 + q] = t;
+					S->row[R_T2][j0 + q] = t2;
+					t += dt[q];
+					if (t > 1.0) {
+						t -= 1.0;
+						if (dynamic) t2 = nt2[q];
+					}
+				}
 			}
 		}
+		s.t = t; s.t2 = t2;
 	}
 	__syncwarp();
 }
@@ -230,15 +243,36 @@ GTTS_DEV void stage_pulse_value(WarpSm5* S, const Voice5Dev& V, int lane, int nb
 	__syncwarp();
 }
 
-GTTS_DEV void stage_serial_b(WarpSm5* S, const Voice5Dev& V, int lane, int nb, Serial5& s)
+// The three Butterworth low-passes, one per lane, in ONE instruction stream: the first-order ones
+// (Butterworth1LowpassFilter.h:89-96, y = b0 (x + x1) - a1 y1) are the second-order form
+// (Butterworth2LowpassFilter.h:104-113, y = b0 (x + x2) + b1 x1 - a1 y1 - a2 y2) with b1 = a2 = 0 and x1 in the place of
+// x2 -- the extra terms are exact zeros.  Lane 0: noise -> glottal noise, lane 1: noise -> frication noise,
+// lane 2: pulse value -> low-passed pulse (in place).
+GTTS_DEV void stage_lowpass5(WarpSm5* S, const Voice5Dev& V, int lane, int nb, Serial5& s)
 {
-	if (lane == 0) {
-		for (int j = 0; j < nb; ++j) {
-			const double x = S->row[R_PULSE][j];
-			const double y = V.gl_b0 * (x + s.glX1) - V.gl_a1 * s.glY1;
-			s.glX1 = x; s.glY1 = y;
-			S->row[R_PULSE][j] = y;
+	if (lane < 3) {
+		const bool second = lane == 1;
+		const double b0 = lane == 0 ? V.gn_b0 : (lane == 1 ? V.fn_b0 : V.gl_b0);
+		const double a1 = lane == 0 ? V.gn_a1 : (lane == 1 ? V.fn_a1 : V.gl_a1);
+		const double b1 = second ? V.fn_b1 : 0.0, a2 = second ? V.fn_a2 : 0.0;
+		const int inRow = lane == 2 ? R_PULSE : R_NOISE;
+		const int outRow = lane == 0 ? R_GN : (lane == 1 ? R_FN : R_PULSE);
+		double x1 = s.x1, x2 = s.x2, y1 = s.y1, y2 = s.y2;
+		for (int j0 = 0; j0 < nb; j0 += 4) {
+			double x[4];
+#pragma unroll
+			for (int q = 0; q < 4; ++q) x[q] = S->row[inRow][j0 + q];
+#pragma unroll
+			for (int q = 0; q < 4; ++q) {
+				if (j0 + q < nb) {
+					const double xa = second ? x2 : x1;
+					const double y = b0 * (x[q] + xa) + b1 * x1 - a1 * y1 - a2 * y2;
+					x2 = x1; x1 = x[q]; y2 = y1; y1 = y;
+					S->row[outRow][j0 + q] = y;
+				}
+			}
 		}
+		s.x1 = x1; s.x2 = x2; s.y1 = y1; s.y2 = y2;
 	}
 	__syncwarp();
 }
@@ -268,91 +302,154 @@ GTTS_DEV double stage_mix5(WarpSm5* S, const Voice5Dev& V, int lane, int nb)
 	return bypassSignal;
 }
 
-// frication bandpass (BandpassFilter.h:112-122) and the value injected into the tube
-GTTS_DEV void stage_serial_c(WarpSm5* S, const Voice5Dev& V, int lane, int nb, Serial5& s)
+// frication bandpass (BandpassFilter.h:112-122) and the values injected into the tube
+GTTS_DEV void stage_bandpass5(WarpSm5* S, const Voice5Dev& V, int lane, int nb, Serial5& s)
 {
 	if (lane == 0) {
-		for (int j = 0; j < nb; ++j) {
-			const double x = S->row[R_FRIC][j];
-			const double y = S->row[R_BPB0][j] * (x - s.bpX2) - S->row[R_BPA1][j] * s.bpY1 - S->row[R_BPA2][j] * s.bpY2;
-			s.bpX2 = s.bpX1; s.bpX1 = x; s.bpY2 = s.bpY1; s.bpY1 = y;
-			S->row[R_FV][j] = S->row[R_FA][j] * (V.fric_factor * y);
+		double x1 = s.bpX1, x2 = s.bpX2, y1 = s.bpY1, y2 = s.bpY2;
+		for (int j0 = 0; j0 < nb; j0 += 4) {
+			double x[4], b0[4], a1[4], a2[4], fa[4], wl[4], wr[4];
+#pragma unroll
+			for (int q = 0; q < 4; ++q) {
+				const int j = j0 + q;
+				x[q] = S->row[R_FRIC][j]; b0[q] = S->row[R_BPB0][j]; a1[q] = S->row[R_BPA1][j]; a2[q] = S->row[R_BPA2][j];
+				fa[q] = S->row[R_FA][j]; wl[q] = S->row[R_FL][j]; wr[q] = S->row[R_FR][j];
+			}
+#pragma unroll
+			for (int q = 0; q < 4; ++q) {
+				if (j0 + q < nb) {
+					const double y = b0[q] * (x[q] - x2) - a1[q] * y1 - a2[q] * y2;
+					x2 = x1; x1 = x[q]; y2 = y1; y1 = y;
+					const double fv = fa[q] * (V.fric_factor * y);
+					S->row[R_FVL][j0 + q] = fv * wl[q];
+					S->row[R_FVR][j0 + q] = fv * wr[q];
+				}
+			}
 		}
+		s.bpX1 = x1; s.bpX2 = x2; s.bpY1 = y1; s.bpY2 = y2;
 	}
 	__syncwarp();
 }
 
 struct Tube5 { double oT, oB, nT, nB, in1, outT1, outR1; };
 
-// the tube, lane = section (see the header of this file)
-GTTS_DEV void stage_tube5(WarpSm5* S, const Voice5Dev& V, int lane, int nb, Tube5& t)
+// What a lane does in the tube loop: five per-sample operand rows (a..e) and its role flags.
+enum {
+	F_KL = 1,                   // a = junction coefficient on the left boundary of the lane's oropharynx section
+	F_KR = 2,                   // b = junction coefficient on its right boundary
+	F_NKL = 4, F_NKR = 8,       // c = first nasal junction (per sample) on the left / right boundary of the nasal section
+	F_GLOT = 16,                // lane 0 (S1): a = glottal loss factor, d = input
+	F_V11 = 32,                 // lane 11 (S12): d = velum junction, left coefficient
+	F_V12 = 64,                 // lane 12 (S13 and N1): d = right coefficient, e = upper coefficient
+	F_MOUTH = 128,              // lane 29 (S30): a..e = radiation impedance cT1, cT2, cT3, cR2, cR3
+	F_NOSE = 256,               // lane 0 (N21): constant radiation impedance
+};
+
+struct Tube5Role {
+	int ra, rb, rc, rd, re;     // rows
+	int flags;
+	int flowRow;                // where an end lane stores its output flow
+	double nkLc, nkRc;          // fixed nasal junction coefficients (0: plain delay)
+};
+
+GTTS_DEV Tube5Role tube5_role(const Voice5Dev& V, int lane)
 {
-	const double d = V.damping;
-	const int ni = (lane - 12) & 31;                  // nasal section of this lane (N1 = 0 on lane 12 ... N21 = 20 on lane 0)
-	// oropharynx junction on the left / right boundary of section `lane` (J1..J7 between S3|S4, S5|S6, S9|S10, S15|S16,
-	// S21|S22, S25|S26, S27|S28), as a row of per-sample coefficients or -1
-	int rowL = -1, rowR = -1;
-	{
-		const int jl[7] = {2, 4, 8, 14, 20, 24, 26};
+	Tube5Role r;
+	r.ra = r.rb = r.rc = r.rd = r.re = R_DT;        // any row: the value is not used
+	r.flags = 0; r.flowRow = R_FLOWM; r.nkLc = 0.0; r.nkRc = 0.0;
+	// oropharynx junctions J1..J7 between S3|S4, S5|S6, S9|S10, S15|S16, S21|S22, S25|S26, S27|S28
+	const int jl[7] = {2, 4, 8, 14, 20, 24, 26};
 #pragma unroll
-		for (int q = 0; q < 7; ++q) {
-			if (jl[q] + 1 == lane) rowL = R_J0 + q;
-			if (jl[q] == lane) rowR = R_J0 + q;
-		}
+	for (int q = 0; q < 7; ++q) {
+		if (jl[q] + 1 == lane) { r.ra = R_J0 + q; r.flags |= F_KL; }
+		if (jl[q] == lane) { r.rb = R_J0 + q; r.flags |= F_KR; }
 	}
 	// nasal junctions NJ1..NJ6 between N3|N4, N6|N7, ... N18|N19: NJ1 per sample, the others fixed
-	double nkLc = 0.0, nkRc = 0.0;
-	bool nkLrow = false, nkRrow = false;
+	const int ni = (lane - 12) & 31;
 	if (ni < kNasal) {
-		if (ni >= 3 && ni % 3 == 0) { const int q = ni / 3 - 1; if (q == 0) nkLrow = true; else if (q < 6) nkLc = V.nasal_k[q]; }
-		if (ni % 3 == 2 && ni < 18) { const int q = ni / 3; if (q == 0) nkRrow = true; else nkRc = V.nasal_k[q]; }
+		if (ni >= 3 && ni % 3 == 0) { const int q = ni / 3 - 1; if (q == 0) { r.rc = R_NJ1; r.flags |= F_NKL; } else if (q < 6) r.nkLc = V.nasal_k[q]; }
+		if (ni % 3 == 2 && ni < 18) { const int q = ni / 3; if (q == 0) { r.rc = R_NJ1; r.flags |= F_NKR; } else r.nkRc = V.nasal_k[q]; }
 	}
-	const bool isMouth = lane == kOral - 1, isNose = lane == 0;
+	if (lane == 0) { r.ra = R_GL; r.rd = R_IN; r.flags |= F_GLOT | F_NOSE; r.flowRow = R_FLOWN; }
+	if (lane == 11) { r.rd = R_VL; r.flags |= F_V11; }
+	if (lane == 12) { r.rd = R_VR; r.re = R_VU; r.flags |= F_V12; }
+	if (lane == kOral - 1) { r.ra = R_CT1; r.rb = R_CT2; r.rc = R_CT3; r.rd = R_CR2; r.re = R_CR3; r.flags |= F_MOUTH; }
+	return r;
+}
+
+// The tube, lane = section (see the header of this file), without branches: every lane evaluates the same expressions
+// on its own operands, the few special sections (glottis, velum, the two open ends) by selecting operands and
+// results.  Operands are fetched four samples at a time, so a shared-memory latency is paid once per four steps.
+//   top    (X + cT Y) dT + Z        X = left neighbour's top, Y = X + own bottom, cT = -k, dT = d         propagate / junction
+//                                   X = own bottom, cT = 0, dT = glottal loss, Z = input                  S1
+//                                   X, Y += N1's bottom, cT = right coefficient                           S13
+//   bottom (W + cB V) d             W = right neighbour's bottom, V = own top + W, cB = k; W, V += N1's bottom on S12
+GTTS_DEV void stage_tube5(WarpSm5* S, const Voice5Dev& V, const Tube5Role& R, int lane, int nb, Tube5& t)
+{
+	const double d = V.damping;
+	const int fl = R.flags;
+	const bool fGlot = fl & F_GLOT, fV11 = fl & F_V11, fV12 = fl & F_V12, fMouth = fl & F_MOUTH, fNose = fl & F_NOSE;
+	const bool fEnd = fMouth || fNose;
 	const int prev = (lane + 31) & 31, next = (lane + 1) & 31;
-	for (int j = 0; j < nb; ++j) {
-		const double kL = rowL >= 0 ? S->row[rowL][j] : 0.0;
-		const double kR = rowR >= 0 ? S->row[rowR][j] : 0.0;
-		const double nkL = nkLrow ? S->row[R_NJ1][j] : nkLc;
-		const double nkR = nkRrow ? S->row[R_NJ1][j] : nkRc;
-		const double oTL = shfl_d(t.oT, prev, 32), oBR = shfl_d(t.oB, next, 32);
-		const double nTL = shfl_d(t.nT, prev, 32), nBR = shfl_d(t.nB, next, 32);
-		// propagate / propagateJunction (:316-325)
-		double noT = (oTL - kL * (oTL + t.oB)) * d;
-		double noB = (oBR + kR * (t.oT + oBR)) * d;
-		double nnT = (nTL - nkL * (nTL + t.nB)) * d;
-		double nnB = (nBR + nkR * (t.nT + nBR)) * d;
-		if (lane == 0) {
-			noT = t.oB * S->row[R_GL][j] + S->row[R_IN][j];       // :651
-		} else if (lane == 11) {
-			// 3-way junction (:326-332), S12 side: left.bottom
-			const double partial = t.oT + oBR + nBR;
-			noB = (oBR + nBR + S->row[R_VL][j] * partial) * d;
-		} else if (lane == 12) {
-			// S13 and N1: right.top and upper.top
-			const double partial = oTL + t.oB + t.nB;
-			noT = (oTL + t.nB + S->row[R_VR][j] * partial) * d;
-			nnT = (oTL + t.oB + S->row[R_VU][j] * partial) * d;
+	const double n1 = V.rad_n[0], n2 = V.rad_n[1], n3 = V.rad_n[2], n4 = V.rad_n[3], n5 = V.rad_n[4];
+	double oT = t.oT, oB = t.oB, nT = t.nT, nB = t.nB, in1 = t.in1, outT1 = t.outT1, outR1 = t.outR1;
+	for (int j0 = 0; j0 < nb; j0 += kTubeChunk) {
+		double ra[kTubeChunk], rb[kTubeChunk], rc[kTubeChunk], rd[kTubeChunk], re[kTubeChunk], fvl[kTubeChunk], fvr[kTubeChunk];
+		int fo[kTubeChunk];
+#pragma unroll
+		for (int q = 0; q < kTubeChunk; ++q) {
+			const int j = j0 + q;
+			ra[q] = S->row[R.ra][j]; rb[q] = S->row[R.rb][j]; rc[q] = S->row[R.rc][j]; rd[q] = S->row[R.rd][j]; re[q] = S->row[R.re][j];
+			fo[q] = S->fo[j];
+			fvl[q] = S->row[R_FVL][j];
+			fvr[q] = S->row[R_FVR][j];
 		}
-		if (isMouth || isNose) {
-			// PoleZeroRadiationImpedance::process (:178-189): S30 on lane 29, N21 on lane 0
-			const double in = isMouth ? t.oT : t.nT;
-			const double cT1 = isMouth ? S->row[R_CT1][j] : V.rad_n[0], cT2 = isMouth ? S->row[R_CT2][j] : V.rad_n[1];
-			const double cT3 = isMouth ? S->row[R_CT3][j] : V.rad_n[2], cR2 = isMouth ? S->row[R_CR2][j] : V.rad_n[3];
-			const double cR3 = isMouth ? S->row[R_CR3][j] : V.rad_n[4];
-			const double outT = cT1 * t.outT1 + cT2 * in + cT3 * t.in1;
-			const double outR = cT1 * t.outR1 + cR2 * in + cR3 * t.in1;
-			t.in1 = in; t.outT1 = outT; t.outR1 = outR;
-			if (isMouth) { noB = outR * d; S->row[R_FLOWM][j] = outT; }
-			else { nnB = outR * d; S->row[R_FLOWN][j] = outT; }
+#pragma unroll
+		for (int q = 0; q < kTubeChunk; ++q) {
+			if (j0 + q < nb) {
+				const double a = ra[q], b = rb[q], c = rc[q], dd = rd[q], e = re[q];
+				const double cT = fV12 ? dd : ((fl & F_KL) ? -a : 0.0);
+				const double dT = fGlot ? a : d;
+				const double Z = fGlot ? dd : 0.0;
+				const double cB = fV11 ? dd : ((fl & F_KR) ? b : 0.0);
+				const double nkL = (fl & F_NKL) ? c : R.nkLc;
+				const double nkR = (fl & F_NKR) ? c : R.nkRc;
+				const double c1 = fMouth ? a : n1, c2 = fMouth ? b : n2, c3 = fMouth ? c : n3, c4 = fMouth ? dd : n4, c5 = fMouth ? e : n5;
+				const double oTL = shfl_d(oT, prev, 32), oBR = shfl_d(oB, next, 32);
+				const double nTL = shfl_d(nT, prev, 32), nBR = shfl_d(nB, next, 32);
+				// oropharynx, top wave
+				const double up12 = fV12 ? nB : 0.0;                 // N1's bottom wave at the velum junction, seen from S13
+				const double X = (fGlot ? oB : oTL) + up12;
+				const double Y = (oTL + oB) + up12;
+				double noT = (X + cT * Y) * dT + Z;
+				// oropharynx, bottom wave
+				const double up11 = fV11 ? nBR : 0.0;                // the same wave seen from S12
+				const double W = oBR + up11;
+				const double Vv = (oT + oBR) + up11;
+				double noB = (W + cB * Vv) * d;
+				// nasal tract
+				const double nnTg = (nTL - nkL * (nTL + nB)) * d;
+				const double nnT12 = ((oTL + oB) + e * Y) * d;      // N1's top wave out of the velum junction
+				const double nnT = fV12 ? nnT12 : nnTg;
+				double nnB = (nBR + nkR * (nT + nBR)) * d;
+				// open ends: PoleZeroRadiationImpedance::process (:178-189), S30 on lane 29, N21 on lane 0
+				const double in = fMouth ? oT : nT;
+				const double outT = c1 * outT1 + c2 * in + c3 * in1;
+				const double outR = c1 * outR1 + c4 * in + c5 * in1;
+				in1 = in; outT1 = outT; outR1 = outR;
+				const double refl = outR * d;
+				noB = fMouth ? refl : noB;
+				nnB = fNose ? refl : nnB;
+				if (fEnd) S->row[R.flowRow][j0 + q] = outT;
+				// frication (:716-723)
+				const int f = fo[q];
+				const double add = (lane == 5 + f) ? fvl[q] : fvr[q];
+				if (lane == 5 + f || (lane == 6 + f && f < 22)) noT += add;
+				oT = noT; oB = noB; nT = nnT; nB = nnB;
+			}
 		}
-		// frication (:716-723)
-		{
-			const int fo = S->fo[j];
-			if (lane == 5 + fo) noT += S->row[R_FV][j] * S->row[R_FL][j];
-			else if (lane == 6 + fo && fo < 22) noT += S->row[R_FV][j] * S->row[R_FR][j];
-		}
-		t.oT = noT; t.oB = noB; t.nT = nnT; t.nB = nnB;
 	}
+	t.oT = oT; t.oB = oB; t.nT = nT; t.nB = nB; t.in1 = in1; t.outT1 = outT1; t.outR1 = outR1;
 	__syncwarp();
 }
 
@@ -416,11 +513,12 @@ GTTS_DEV void run_utterance5(WarpSm5* S, const double2* tab, const KernelParams5
 	const Voice5Dev& V = S->V;
 	unsigned long long lcg = c_lcg_init;
 	Serial5 s;
-	s.a = s.b = s.c = s.d = 0.0;
-	if (lane == 2) s.b = V.t1 + V.tn_max;           // t2 (RosenbergBGlottalSource.h:76-78)
-	s.glX1 = s.glY1 = 0.0;
+	s.x1 = s.x2 = s.y1 = s.y2 = 0.0;
+	s.t = 0.0;
+	s.t2 = V.t1 + V.tn_max;                         // RosenbergBGlottalSource.h:76-78
 	s.bpX1 = s.bpX2 = s.bpY1 = s.bpY2 = 0.0;
 	Tube5 t = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+	const Tube5Role role = tube5_role(V, lane);
 	long long nDone = 0, kDone = 0;
 	for (int i = lane; i < kRing; i += 32) S->xring[i] = 0.0;
 	for (int i = lane; i < kYRing; i += 32) S->yraw[i] = 0.0f;
@@ -447,16 +545,16 @@ GTTS_DEV void run_utterance5(WarpSm5* S, const double2* tab, const KernelParams5
 			__syncwarp();
 			stage_convert5(S, V, lane, nb);
 			stage_noise5(S, lane, nb, lcg);
-			stage_serial_a(S, V, lane, nb, s);
+			stage_phase5(S, V, lane, nb, s);
 			stage_pulse_value(S, V, lane, nb);
-			stage_serial_b(S, V, lane, nb, s);
+			stage_lowpass5(S, V, lane, nb, s);
 			const double bypassSignal = stage_mix5(S, V, lane, nb);
 			double x;
 			if (V.bypass == 1) {
 				x = bypassSignal;
 			} else {
-				stage_serial_c(S, V, lane, nb, s);
-				stage_tube5(S, V, lane, nb, t);
+				stage_bandpass5(S, V, lane, nb, s);
+				stage_tube5(S, V, role, lane, nb, t);
 				x = lane < nb ? S->row[R_FLOWM][lane] + S->row[R_FLOWN][lane] : 0.0;
 			}
 			if (lane < nb) S->xring[(nDone + lane) & (kRing - 1)] = x;
