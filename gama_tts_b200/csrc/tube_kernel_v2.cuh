@@ -4,13 +4,13 @@
 // iteration, through a software pipeline of warp roles.  Block b of an utterance is handled at slot iteration
 // it = b + stage:
 //
-//   stage 0   walker        float32 walk of parameter 0 (pitch)                              lane = (slot, parameter)
+//   stage 0   coef worker   float32 walk of parameter 0 (pitch)                              lane = parameter
 //   stage 1   slot helper   f0 -> oscillator increments                                      lane = sample
 //   stage 2   chain A       oscillator phase recurrence (serial)                             lane = slot
-//             walker        float32 walk of parameters 1..6
+//             coef worker   float32 walk of parameters 1..6
 //   stage 3   slot helper   amplitudes, frication taps, bandpass coefficients, noise (LCG jump-ahead), wavetable
 //                           lookup, 49-tap FIR, mixing                                        lane = sample
-//             walker        float32 walk of parameters 7..15 (radii, velum)
+//             coef worker   float32 walk of parameters 7..15 (radii, velum)
 //   stage 4   chain A2      frication bandpass biquad + tap signals (serial)                 lane = slot
 //             coef worker   junction coefficients (9 divisions per sample)                   lane = sample
 //   stage 5   tube warps    the waveguide: one cell per lane, 16 lanes per utterance, three shuffles per sample
@@ -24,8 +24,8 @@
 //    iteration parity, neighbours arrive without blocking, the type's warps wait without issuing.  That is the
 //    guarantee the CTA barrier gave, restricted to the pairs that need it; roles that are not neighbours drift apart
 //    by up to three iterations (bounded by the four-deep ring of slot control blocks).
-//  * The float32 parameter walks (Controller.cpp:297-311) run on two dedicated walker warps, 32 (slot, parameter)
-//    lanes per call instead of 7 or 9: a quarter of the instructions, and the serial walk is off the helpers.
+//  * The float32 parameter walks (Controller.cpp:297-311) run on the slots' coefficient workers (lanes 0..15 = the
+//    sixteen parameters, walk_slot), off the helpers.
 //  * SRC: every lane forms two consecutive outputs from ONE 27-sample window held in registers (half the window
 //    loads), coefficients still shared by all aligned slots.
 //  * The six junction coefficients that are per-voice constants stay in the tube lanes' registers; alpha_u of the
