@@ -148,7 +148,11 @@ extern unsigned long long c_lcg_init;
 GTTS_DEV double shfl_d(double v, int src, int width) { return __shfl_sync(0xffffffffu, v, src, width); }
 
 // Util::amplitude60dB (VTMUtil.h:50-67)
+#ifdef GTTS_AMP60_NOINLINE
+GTTS_DEV_NOINLINE double amp60(double db)
+#else
 GTTS_DEV double amp60(double db)
+#endif
 {
 	if (db <= 0.0) return 0.0;
 	if (db == 60.0) return 1.0;
@@ -159,7 +163,11 @@ GTTS_DEV double amp60(double db)
 // |x| < 1e5): reduction by pi / 2 in two parts, Taylor cores on |r| <= pi / 4 (degree 17 / 18), branch-free.
 // ~33 instructions for both values instead of the ~170 of libdevice's tan() + cos() with their special-case paths.
 #ifndef GTTS_EMU
+#ifdef GTTS_SINCOS_NOINLINE
+__device__ __noinline__ void gtts_sincos(double x, double& s, double& c)
+#else
 __device__ __forceinline__ void gtts_sincos(double x, double& s, double& c)
+#endif
 {
 	const double magic = 6755399441055744.0;
 	const double tt = fma(x, 0.6366197723675814, magic);

@@ -1,6 +1,6 @@
 // Decoupled, warp-specialised tube kernel (sm_100a), second generation of tube_kernel_v1.cuh.
 //
-// One persistent CTA per SM (24 warps, 80 registers) steps kSlots = 7 utterances, 32 internal samples ("block") per
+// One persistent CTA per SM (23 warps, 80 registers) steps kSlots = 7 utterances, 32 internal samples ("block") per
 // iteration, through a software pipeline of warp roles.  Block b of an utterance is handled at slot iteration
 // it = b + stage:
 //
@@ -38,6 +38,10 @@
 #define GTTS_TUBE_KERNEL_V2_CUH_
 
 #include "tube_kernel.cuh"
+
+#ifndef GTTS_ROLE_PRESET
+#define GTTS_ROLE_PRESET 0
+#endif
 
 namespace gtts {
 namespace v2 {
@@ -136,11 +140,6 @@ struct KernelParamsV2 {
 	int32_t debug_skip;           // development builds only (-DGTTS_EXPERIMENTS)
 	long long* prof;              // development builds only (-DGTTS_ROLE_PROFILE): [grid][2 * kWarps + 1]
 };
-
-// slots whose per-slot SRC (slots not in lockstep) runs on the two SRC warps; the rest on their coefficient workers
-#ifndef GTTS_SRC_OWN0
-#define GTTS_SRC_OWN0 4
-#endif
 
 #ifndef GTTS_SRC1_UNROLL
 #define GTTS_SRC1_UNROLL 1
@@ -926,18 +925,51 @@ GTTS_DEV_NOINLINE void src_down_task(CtaSm* C, const KernelParamsV2& P, int lane
 	}
 }
 
-// per-slot SRC (slots not in lockstep): the slot's own outputs, 64 per pass
-GTTS_DEV void src_slot_task(CtaSm* C, const KernelParamsV2& P, int lane, int slot, int p)
+// One output per lane, 32 consecutive outputs = one 128-byte row per call: the unit in which the per-slot SRC (slots
+// not in lockstep: mixed voices, ragged lengths -- BASELINE config 3) is shared out between three warps.  Same taps in
+// the same order as the reference (left wing j = 0..12 on x[e - 13 - j], then the right wing on x[e - 12 + j]).
+GTTS_DEV void src_task_row(CtaSm* C, const KernelParamsV2& P, int lane, int slot, unsigned inc, long long kb, long long k0w, long long k1, int p)
+{
+	const long long ka = kb + lane;
+	const unsigned long long ta = (unsigned long long) (ka < 0 ? 0 : ka) * inc;
+	const int ea = (int) (ta >> 16);
+	const unsigned fa = (unsigned) (ta & 0xFFFFu), ga = (~fa) & 0xFFFFu;
+	const double iL = (double) (fa & 0xFFu) / 256, iR = (double) (ga & 0xFFu) / 256;
+	const double2* pL = C->tab + (fa >> 8);
+	const double2* pR = C->tab + (ga >> 8);
+	const double* xw = C->slot[slot].xring + ((ea - 25) & (kSrcRing - 1));
+	double acc = 0.0;
+	constexpr int kUnroll = GTTS_SRC1_UNROLL;
+#pragma unroll kUnroll
+	for (int t = 0; t < kSrcZeroCrossings; ++t) {
+		const double2 c = pL[256 * t];
+		acc += (xw[12 - t] * (c.x + (c.y * iL)));
+	}
+#pragma unroll kUnroll
+	for (int t = 0; t < kSrcZeroCrossings; ++t) {
+		const double2 c = pR[256 * t];
+		acc += (xw[13 + t] * (c.x + (c.y * iR)));
+	}
+	if (ka >= k0w && ka < k1) P.out[C->slot[slot].ctl[p].U.out_begin + ka] = (float) acc;
+}
+
+// Per-slot SRC (slots not in lockstep): the slot's outputs of this block in rows of 32, dealt round-robin -- rotating
+// with the block, so that the shares even out -- to the slot's three workers: 0 its coefficient worker, 1 its helper,
+// 2 one of the SRC warps.  (Measured on the config-3 shape, where all of it ran on five warps: those five were the last
+// to arrive in every iteration, 9.3-9.8 k busy cycles against 5.3-5.8 k of the other coefficient workers and helpers.)
+// The down-sampling converter (variable tap count) stays whole on worker 0.
+GTTS_DEV void src_slot_task(CtaSm* C, const KernelParamsV2& P, int lane, int slot, int p, int part)
 {
 	const SlotSm::Ctl& K = C->slot[slot].ctl[p];
 	const int b = K.it - kStOut;
 	if (K.it < 0 || b < 0 || b >= K.nblocks) return;
-	if (K.inc > 65536u) { src_down_task(C, P, lane, slot, p); return; }
+	if (K.inc > 65536u) { if (part == 0) src_down_task(C, P, lane, slot, p); return; }
 	const long long k0 = K.src_k0, k1 = K.src_k1;
-	const long long a = K.U.out_begin & 1;
-	const long long kStart = ((k0 + a) & ~1ll) - a;            // pairs start on even absolute positions (8-byte stores)
+	const long long a = K.U.out_begin & 31;
+	const long long kStart = ((k0 + a) & ~31ll) - a;           // rows start on multiples of 32 samples of the output buffer
+	int t = (part + 3 - b % 3) % 3;                            // this worker's first row: (row + b) % 3 == part
 #pragma unroll 1
-	for (long long kb = kStart; kb < k1; kb += 64) src_task<1>(C, P, lane, slot, 1, K.inc, kb, k0, k1, p);
+	for (long long kb = kStart + 32ll * t; kb < k1; kb += 96) src_task_row(C, P, lane, slot, K.inc, kb, k0, k1, p);
 }
 
 // ---- chain A: oscillator phase of block it - 2, lane = slot (WavetableGlottalSource.h:196-199, 265-272) --------
@@ -1399,7 +1431,15 @@ GTTS_DEV void tube_v2_cta_body(const KernelParamsV2& P, unsigned char* smem, int
 	// Hardware warp w runs on SM sub-partition w % 4; which role runs where matters by a few percent (v1 measurements):
 	// tube warps one per sub-partition, the chains and the light workers spread next to them.
 #ifndef GTTS_ROLE_TABLE2
+#if GTTS_ROLE_PRESET == 1
+#define GTTS_ROLE_TABLE2 0, 1, 2, 3, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 6, 5, 4, 22, 21
+#elif GTTS_ROLE_PRESET == 2
+#define GTTS_ROLE_TABLE2 0, 1, 2, 3, 7, 11, 15, 18, 8, 12, 16, 19, 9, 13, 17, 20, 10, 14, 6, 5, 4, 22, 21
+#elif GTTS_ROLE_PRESET == 3
+#define GTTS_ROLE_TABLE2 0, 2, 7, 8, 1, 3, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 6, 5, 4, 22, 21
+#else
 #define GTTS_ROLE_TABLE2 0, 1, 2, 3, 5, 22, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 4, 21
+#endif
 #endif
 	const int hw = tid >> 5;
 	int role;
@@ -1454,29 +1494,32 @@ GTTS_DEV void tube_v2_cta_body(const KernelParamsV2& P, unsigned char* smem, int
 		HelperRegs hr = {};
 		hr.mult = c_lcg[lane];
 		hr.low = kNoLowMark;
-		SlotSm* S = &C->slot[role - kRoleHelper0];
-		GTTS_ROLE_LOOP2(kTypeHelper, if (!(skip & 4)) helper_iteration<ST>(S, P, lane, hr, p);)
+		const int slot = role - kRoleHelper0;
+		SlotSm* S = &C->slot[slot];
+		GTTS_ROLE_LOOP2(kTypeHelper,
+			if (!(skip & 4)) helper_iteration<ST>(S, P, lane, hr, p);
+			if (!(skip & 1) && !C->sched[p].src_shared && ((C->sched[p].src_mask >> slot) & 1)) src_slot_task(C, P, lane, slot, p, 1);)
 	} else if (role < kRoleSrcB) {
 		const int slot = role - kRoleCoef0;
 		WalkRegs wr = {0.f, 0.f, 0.f, 0.f, 0, 0};
 		GTTS_ROLE_LOOP2(kTypeCoef,
 			if (!(skip & 64)) walk_slot<ST>(&C->slot[slot], P, lane, p, wr);
 			if (!(skip & 2)) coef_task(&C->slot[slot], lane, p);
-			if (!(skip & 1) && slot >= GTTS_SRC_OWN0 && !C->sched[p].src_shared && ((C->sched[p].src_mask >> slot) & 1)) src_slot_task(C, P, lane, slot, p);)
+			if (!(skip & 1) && !C->sched[p].src_shared && ((C->sched[p].src_mask >> slot) & 1)) src_slot_task(C, P, lane, slot, p, 0);)
 	} else {
 		// The SRC warps.  Slots in lockstep (one voice, equal lengths: the batch case): the shared SRC tasks, windows
 		// of slots 0..3 | slots 3..6 with slot 3 left out (one instantiation).  Otherwise every slot converts its own
-		// outputs: the first GTTS_SRC_OWN0 slots here (half each), the others on their coefficient workers.
+		// outputs, a third of the rows here, the others on the slot's coefficient worker and helper (src_slot_task).
 		const int slot0 = role == kRoleSrcA ? 0 : 3;
 		const int keep = role == kRoleSrcA ? 0xf : 0xe;
-		const int own0 = role == kRoleSrcA ? 0 : GTTS_SRC_OWN0 / 2, own1 = role == kRoleSrcA ? GTTS_SRC_OWN0 / 2 : GTTS_SRC_OWN0;
+		const int own0 = role == kRoleSrcA ? 0 : 4, own1 = role == kRoleSrcA ? 4 : kSlots;     // per-slot SRC: the third share of slots 0..3 | 4..6
 		GTTS_ROLE_LOOP2(kTypeSrc,
 			if (!(skip & 1)) {
 				if (C->sched[p].src_shared) {
 					src_shared_group<4>(C, P, lane, slot0, keep, p);
 				} else {
 #pragma unroll 1
-					for (int q = own0; q < own1; ++q) if ((C->sched[p].src_mask >> q) & 1) src_slot_task(C, P, lane, q, p);
+					for (int q = own0; q < own1; ++q) if ((C->sched[p].src_mask >> q) & 1) src_slot_task(C, P, lane, q, p, 2);
 				}
 			})
 	}

@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--lib", default=None, help="time another build of the library (tools/ab_build.sh)")
     ap.add_argument("--model5", action="store_true", help="model-5 utterances (voice 5_male) on tube5_kernel")
+    ap.add_argument("--mixed", action="store_true", help="config-3-like: every utterance its own randomised voice, ragged lengths (0.5 .. 1.5 x --frames)")
     args = ap.parse_args()
     import torch
     if args.lib:
@@ -30,7 +31,19 @@ def main():
     frames = np.concatenate([base[u % len(base)] for u in range(args.utts)])
     fo = np.arange(args.utts + 1, dtype=np.int64) * args.frames
     synth = g.TubeSynthesizer(0)
-    if args.model5:
+    if args.mixed:
+        from gama_tts_b200.voices import random_voice
+        rng = np.random.Generator(np.random.PCG64(1))
+        lens = rng.integers(args.frames // 2, args.frames * 3 // 2 + 1, args.utts)
+        long_base = [T.synthetic_track(20240 + u, args.frames * 2) for u in range(64)]
+        frames = np.concatenate([long_base[u % 64][:lens[u]] for u in range(args.utts)])
+        fo = np.zeros(args.utts + 1, np.int64)
+        fo[1:] = np.cumsum(lens)
+        voices_l = [random_voice(np.random.Generator(np.random.PCG64(7 + u))) for u in range(args.utts)]
+        b = synth.prepare(voices_l, fo, voice_index=np.arange(args.utts, dtype=np.int32))
+        steps = float(b.n_internal.sum()) / float(lens.sum())
+        args.frames = float(lens.mean())
+    elif args.model5:
         from gama_tts_b200.voices import default_voice5
         b = synth.prepare5(default_voice5("male"), fo)
         b.n_samples_total = int(b.n_out.sum())
