@@ -362,6 +362,15 @@ class Batch5:
     def run_device(self, d_frames_ptr, d_out_ptr, stream_ptr=0):
         check(self._lib.gtts5_batch_run_device(self._h, d_frames_ptr, d_out_ptr, stream_ptr))
 
+    def run_host_pcm16(self, frames):
+        """-> (int16 payload in the batch layout, float32 scale per utterance): the reference's WAVE data."""
+        frames = np.ascontiguousarray(frames, np.float32).reshape(-1, NUM_PARAMS)
+        assert frames.shape[0] == self.n_frames_total
+        pcm = np.zeros(max(self.n_out_total, 1), np.int16)
+        scale = np.zeros(max(self.n_utt, 1), np.float32)
+        check(self._lib.gtts5_batch_run_host_pcm16(self._h, frames.ctypes.data, pcm.ctypes.data, scale.ctypes.data))
+        return pcm, scale[:self.n_utt]
+
     def split(self, out):
         return [out[self.out_offsets[u]:self.out_offsets[u] + self.n_out[u]] for u in range(self.n_utt)]
 

@@ -101,7 +101,7 @@ EXPORTS = [
     "gtts_batch_free", "gtts_batch_synthesize", "gtts_stream_open", "gtts_stream_push_frames",
     "gtts_stream_finish", "gtts_stream_reset", "gtts_stream_close",
     "gtts5_voice_internal_rate", "gtts5_output_length", "gtts5_batch_prepare", "gtts5_batch_layout", "gtts5_batch_run_device",
-    "gtts5_batch_run_host", "gtts5_batch_free",
+    "gtts5_batch_run_host", "gtts5_batch_run_device_pcm16", "gtts5_batch_run_host_pcm16", "gtts5_batch_free",
 ]
 
 _lib = None
@@ -170,6 +170,8 @@ def load():
     L.gtts5_batch_layout.argtypes = [vp, vp, vp, vp]
     L.gtts5_batch_run_device.argtypes = [vp, vp, vp, vp]
     L.gtts5_batch_run_host.argtypes = [vp, vp, vp]
+    L.gtts5_batch_run_device_pcm16.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.gtts5_batch_run_host_pcm16.argtypes = [vp, vp, vp, vp]
     L.gtts5_batch_free.argtypes = [vp]
     L.gtts5_batch_free.restype = None
     _lib = L

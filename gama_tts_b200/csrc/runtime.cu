@@ -1453,6 +1453,9 @@ struct gtts5_batch {
 	int32_t* d_queue = nullptr;
 	float* d_frames = nullptr;
 	float* d_out = nullptr;
+	short* d_pcm = nullptr;
+	unsigned* d_peak = nullptr;
+	float* d_scale = nullptr;
 	cudaStream_t stream = nullptr;
 };
 
@@ -1493,7 +1496,7 @@ void gtts5_batch_free(gtts5_batch* b)
 	if (!b) return;
 	cudaSetDevice(b->h->device);
 	cudaFree(b->d_voices); cudaFree(b->d_utts); cudaFree(b->d_order); cudaFree(b->d_queue);
-	cudaFree(b->d_frames); cudaFree(b->d_out);
+	cudaFree(b->d_frames); cudaFree(b->d_out); cudaFree(b->d_pcm); cudaFree(b->d_peak); cudaFree(b->d_scale);
 	if (b->stream) cudaStreamDestroy(b->stream);
 	delete b;
 }
@@ -1587,6 +1590,48 @@ int gtts5_batch_run_host(gtts5_batch* b, const float* h_frames, float* h_out)
 	const int rc = gtts5_batch_run_device(b, b->d_frames, b->d_out, b->stream);
 	if (rc != GTTS_OK) return rc;
 	if (nOut > 0) GTTS_CUDA(cudaMemcpyAsync(h_out, b->d_out, sizeof(float) * nOut, cudaMemcpyDeviceToHost, b->stream));
+	GTTS_CUDA(cudaStreamSynchronize(b->stream));
+	return GTTS_OK;
+}
+
+
+// The reference's output stage for model 5 (Controller::writeOutputToFile + WAVEFileWriter, as for model 0: see
+// gtts_batch_run_device_pcm16): per-utterance scale 0.95f / max|x| and the 16-bit payload, same kernels.
+int gtts5_batch_run_device_pcm16(gtts5_batch* b, const float* d_frames, float* d_audio, int16_t* d_pcm, float* d_scale, void* cuda_stream)
+{
+	if (!b) return fail(GTTS_ERR_INVALID, "null batch");
+	const int nUtt = static_cast<int>(b->plan.utts.size());
+	if (nUtt == 0) return GTTS_OK;
+	if (!d_audio || !d_pcm) return fail(GTTS_ERR_INVALID, "null device buffer");
+	cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+	const int rc = gtts5_batch_run_device(b, d_frames, d_audio, stream);
+	if (rc != GTTS_OK) return rc;
+	if (!b->d_peak) GTTS_CUDA(cudaMalloc(&b->d_peak, sizeof(unsigned) * nUtt));
+	utterance_peak_kernel<<<nUtt, 256, 0, stream>>>(d_audio, b->d_utts, b->d_peak);
+	GTTS_CUDA(cudaGetLastError());
+	utterance_pcm16_kernel<<<nUtt, 256, 0, stream>>>(d_audio, b->d_utts, b->d_utts, b->d_peak, reinterpret_cast<short*>(d_pcm), d_scale);
+	GTTS_CUDA(cudaGetLastError());
+	return GTTS_OK;
+}
+
+int gtts5_batch_run_host_pcm16(gtts5_batch* b, const float* h_frames, int16_t* h_pcm, float* h_scale)
+{
+	if (!b) return fail(GTTS_ERR_INVALID, "null batch");
+	const int64_t nFrames = b->plan.n_frames_total;
+	const int64_t nOut = b->plan.out_offsets.empty() ? 0 : b->plan.out_offsets.back();
+	const size_t nUtt = b->plan.utts.size();
+	if ((nFrames > 0 && !h_frames) || (nOut > 0 && !h_pcm)) return fail(GTTS_ERR_INVALID, "null host buffer");
+	if (nUtt == 0) return GTTS_OK;
+	GTTS_CUDA(cudaSetDevice(b->h->device));
+	if (!b->d_frames && nFrames > 0) GTTS_CUDA(cudaMalloc(&b->d_frames, sizeof(float) * kNumParams * nFrames));
+	if (!b->d_out && nOut > 0) GTTS_CUDA(cudaMalloc(&b->d_out, sizeof(float) * nOut));
+	if (!b->d_pcm && nOut > 0) GTTS_CUDA(cudaMalloc(&b->d_pcm, sizeof(short) * nOut));
+	if (!b->d_scale) GTTS_CUDA(cudaMalloc(&b->d_scale, sizeof(float) * nUtt));
+	if (nFrames > 0) GTTS_CUDA(cudaMemcpyAsync(b->d_frames, h_frames, sizeof(float) * kNumParams * nFrames, cudaMemcpyHostToDevice, b->stream));
+	const int rc = gtts5_batch_run_device_pcm16(b, b->d_frames, b->d_out, reinterpret_cast<int16_t*>(b->d_pcm), b->d_scale, b->stream);
+	if (rc != GTTS_OK) return rc;
+	if (nOut > 0) GTTS_CUDA(cudaMemcpyAsync(h_pcm, b->d_pcm, sizeof(short) * nOut, cudaMemcpyDeviceToHost, b->stream));
+	if (h_scale) GTTS_CUDA(cudaMemcpyAsync(h_scale, b->d_scale, sizeof(float) * nUtt, cudaMemcpyDeviceToHost, b->stream));
 	GTTS_CUDA(cudaStreamSynchronize(b->stream));
 	return GTTS_OK;
 }

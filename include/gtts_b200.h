@@ -268,6 +268,10 @@ int gtts5_batch_layout(const gtts5_batch* batch, int64_t* out_offsets, int64_t* 
 int gtts5_batch_run_device(gtts5_batch* batch, const float* d_frames, float* d_out, void* cuda_stream);
 /* Host buffers (staged through device memory), synchronised on return. */
 int gtts5_batch_run_host(gtts5_batch* batch, const float* h_frames, float* h_out);
+/* The reference's output stage (see gtts_batch_run_device_pcm16): per-utterance scale and 16-bit PCM payload. */
+int gtts5_batch_run_device_pcm16(gtts5_batch* batch, const float* d_frames, float* d_audio, int16_t* d_pcm,
+			float* d_scale, void* cuda_stream);
+int gtts5_batch_run_host_pcm16(gtts5_batch* batch, const float* h_frames, int16_t* h_pcm, float* h_scale);
 void gtts5_batch_free(gtts5_batch* batch);
 
 #ifdef __cplusplus

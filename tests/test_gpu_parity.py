@@ -510,3 +510,19 @@ def test_model5_rejects_what_the_reference_rejects(synth):
     with pytest.raises(g.GttsError) as e:
         synth.synthesize5(dict(default_voice5("male"), vocal_tract_length=5.0), tr)      # converter wing above 48 taps
     assert e.value.code == g.capi.GTTS_ERR_UNSUPPORTED
+
+
+def test_model5_pcm16_output_stage_is_bit_exact(synth, oracle, golden5):
+    # the reference's output stage on model-5 audio: scale and 16-bit payload of the float32 audio the kernel produced,
+    # against the oracle's restatement of the reference's writer (pinned by test_oracle.py) on the same audio
+    names = [n for n in golden5.names if n not in ("empty",)]
+    voices, tracks = zip(*[(golden5.case(n)[0], golden5.case(n)[1]) for n in names])
+    frames, fo = g.pack_tracks(list(tracks))
+    b = synth.prepare5(list(voices), fo, voice_index=np.arange(len(names)))
+    audio = b.split(b.run_host(frames))
+    pcm, scale = b.run_host_pcm16(frames)
+    for u, (a, p) in enumerate(zip(audio, b.split(pcm))):
+        ref_pcm, ref_scale = oracle.pcm16(a)
+        assert scale[u] == np.float32(ref_scale)
+        assert np.array_equal(p, ref_pcm), names[u]
+    b.close()
