@@ -378,13 +378,23 @@ GTTS_DEV void walk_block(const float* frames, long long nFrames, int steps, floa
 #pragma unroll 1
 	for (int j0 = 0; j0 < kBlock; j0 += 4) {
 		float v[4];
+		// the control period ends inside these four samples on some lane (the three groups of parameters of a slot are
+		// at different blocks): once per period; everywhere else the walk is four additions and one 16-byte store
+		if (__any_sync(0xffffffffu, restart >= j0 && restart < j0 + 4)) {
 #pragma unroll
-		for (int q = 0; q < 4; ++q) {
-			const bool r = (j0 + q) == restart;
-			c = r ? c1 : c;
-			d = r ? d1 : d;
-			v[q] = c;
-			c = __fadd_rn(c, d);
+			for (int q = 0; q < 4; ++q) {
+				const bool r = (j0 + q) == restart;
+				c = r ? c1 : c;
+				d = r ? d1 : d;
+				v[q] = c;
+				c = __fadd_rn(c, d);
+			}
+		} else {
+#pragma unroll
+			for (int q = 0; q < 4; ++q) {
+				v[q] = c;
+				c = __fadd_rn(c, d);
+			}
 		}
 		if (active) o[j0 >> 2] = make_float4(v[0], v[1], v[2], v[3]);
 	}
