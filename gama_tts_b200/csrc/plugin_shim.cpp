@@ -22,9 +22,15 @@
 // execSynthesisStep() records the 16 float parameters of that internal sample; finishSynthesis() runs
 // the whole recording as ONE utterance with steps = 1 (every recorded row is used verbatim for one
 // internal sample, so the host's own float32 interpolation is reproduced exactly) and fills the
-// output buffer.  Interactive callers (the editor drains outputBuffer() after every step, SURVEY.md
-// section 3.5) are not served: construction with is_interactive != 0 returns NULL, which the host
-// reports as "Could not construct the vocal tract model" (VocalTractModelPlugin.cpp:88-90).
+// output buffer.
+//
+// Interactive callers (gama_tts_editor/src/interactive/InteractiveAudio.cpp:131-186: the editor steps the model until
+// outputBuffer() holds what the audio callback needs, drains it, and steps on) are served in chunks: construction with
+// is_interactive != 0 opens a stream (gtts_stream_*), execSynthesisStep() queues the step's parameters and every
+// kInteractiveChunk steps the queue is synthesised and its audio appended to outputBuffer() -- the same samples as the
+// reference's model, available up to kInteractiveChunk - 1 internal samples (3 ms) later.  Model-0 voices only; an
+// interactive model-5 voice is refused (NULL: "Could not construct the vocal tract model",
+// VocalTractModelPlugin.cpp:88-90).
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -44,7 +50,7 @@ namespace {
 
 class B200VocalTractModel final : public GS::VTM::VocalTractModel {
 public:
-	B200VocalTractModel(const GS::ConfigurationData& data, int device);
+	B200VocalTractModel(const GS::ConfigurationData& data, int device, bool interactive);
 	~B200VocalTractModel() noexcept override;
 
 	void reset() noexcept override;
@@ -72,13 +78,21 @@ private:
 	std::vector<float> outputBuffer_;
 	bool failed_ = false;                  // recording abandoned: nothing more is recorded until finishSynthesis() / reset()
 
+	// interactive mode: a stream, fed kInteractiveChunk internal samples at a time
+	static constexpr int kInteractiveChunk = 64;
+	bool interactive_ = false;
+	gtts_stream* stream_ = nullptr;
+	std::vector<float> chunkOut_;
+	bool pushChunk(bool finish) noexcept;
+
 	void fail(const char* what) noexcept;
 };
 
 int g_lastStatus = GTTS_OK;                // status of the last finishSynthesis() in this process (GTTS_plugin_last_status)
 
 // Same keys, same order as VocalTractModel0::loadConfiguration (VocalTractModel0.h:266-305).
-B200VocalTractModel::B200VocalTractModel(const GS::ConfigurationData& data, int device)
+B200VocalTractModel::B200VocalTractModel(const GS::ConfigurationData& data, int device, bool interactive)
+		: interactive_(interactive)
 {
 	std::memset(&voice_, 0, sizeof voice_);
 	std::memset(&voice5_, 0, sizeof voice5_);
@@ -93,6 +107,7 @@ B200VocalTractModel::B200VocalTractModel(const GS::ConfigurationData& data, int 
 		model5_ = false;
 	}
 	if (model5_) {
+		if (interactive_) throw std::runtime_error("interactive mode is implemented for model-0 voices only");
 		loadModel5(data);
 		handle_ = sharedHandle(device);
 		outputBuffer_.reserve(OUTPUT_BUFFER_RESERVE);
@@ -125,6 +140,11 @@ B200VocalTractModel::B200VocalTractModel(const GS::ConfigurationData& data, int 
 	if (gtts_output_length(&voice_, 1, 0, &nInternal, &nOut) != GTTS_OK) throw std::runtime_error(gtts_last_error());
 	handle_ = sharedHandle(device);
 	outputBuffer_.reserve(OUTPUT_BUFFER_RESERVE);
+	if (interactive_) {
+		// every queued row is one internal sample (steps = 1), as in finishSynthesis() below
+		if (gtts_stream_open(handle_, &voice_, 250.0, 1, &stream_) != GTTS_OK) throw std::runtime_error(gtts_last_error());
+		chunkOut_.resize(static_cast<size_t>(kInteractiveChunk) * 8 + 256);
+	}
 }
 
 // Same keys as VocalTractModel5::loadConfiguration (VocalTractModel5.h:373-425).
@@ -177,7 +197,37 @@ gtts_handle* B200VocalTractModel::sharedHandle(int device)
 	return h;
 }
 
-B200VocalTractModel::~B200VocalTractModel() noexcept = default;
+B200VocalTractModel::~B200VocalTractModel() noexcept
+{
+	if (stream_) gtts_stream_close(stream_);
+}
+
+// Interactive mode: synthesises the queued steps and appends their audio to the output buffer.
+bool B200VocalTractModel::pushChunk(bool finish) noexcept
+{
+	try {
+		const int64_t n = static_cast<int64_t>(recorded_.size() / GTTS_NUM_PARAMS);
+		int64_t written = 0;
+		int rc = GTTS_OK;
+		if (n > 0) {
+			const size_t need = static_cast<size_t>(n) * 8 + 256;       // output rate / internal rate is below 8 for every tract length
+			if (chunkOut_.size() < need) chunkOut_.resize(need);
+			rc = gtts_stream_push_frames(stream_, recorded_.data(), n, chunkOut_.data(), static_cast<int64_t>(chunkOut_.size()), &written);
+			if (rc == GTTS_OK) outputBuffer_.insert(outputBuffer_.end(), chunkOut_.begin(), chunkOut_.begin() + written);
+			recorded_.clear();
+		}
+		if (rc == GTTS_OK && finish) {
+			rc = gtts_stream_finish(stream_, chunkOut_.data(), static_cast<int64_t>(chunkOut_.size()), &written);
+			if (rc == GTTS_OK) outputBuffer_.insert(outputBuffer_.end(), chunkOut_.begin(), chunkOut_.begin() + written);
+		}
+		if (rc != GTTS_OK) { g_lastStatus = rc; fail(gtts_last_error()); return false; }
+		return true;
+	} catch (...) {
+		g_lastStatus = GTTS_ERR_NOMEM;
+		fail("out of memory in the interactive chunk");
+		return false;
+	}
+}
 
 // VocalTractModel0::reset (VocalTractModel0.h:309-326): all dynamic state back to zero, output cleared;
 // like the reference, the current parameters are kept.
@@ -186,6 +236,7 @@ void B200VocalTractModel::reset() noexcept
 	recorded_.clear();
 	outputBuffer_.clear();
 	failed_ = false;
+	if (stream_ && gtts_stream_reset(stream_) != GTTS_OK) { g_lastStatus = GTTS_ERR_CUDA; fail(gtts_last_error()); }
 }
 
 // The VocalTractModel interface has no error channel (all eight virtuals are noexcept void, VocalTractModel.h:43-71)
@@ -228,7 +279,9 @@ void B200VocalTractModel::execSynthesisStep() noexcept
 	} catch (...) {
 		g_lastStatus = GTTS_ERR_NOMEM;
 		fail("out of memory while recording parameters");
+		return;
 	}
+	if (interactive_ && recorded_.size() >= static_cast<size_t>(kInteractiveChunk) * GTTS_NUM_PARAMS) pushChunk(false);
 }
 
 // VocalTractModel0.h:720-723 (SRC flush) -- here: the deferred synthesis of everything recorded.
@@ -241,6 +294,11 @@ void B200VocalTractModel::finishSynthesis() noexcept
 		return;
 	}
 	g_lastStatus = GTTS_OK;
+	if (interactive_) {
+		pushChunk(true);
+		failed_ = false;
+		return;
+	}
 	if (model5_) {
 		gtts5_batch* b5 = nullptr;
 		try {
@@ -303,14 +361,11 @@ extern "C" {
 // (gama_tts/src/vtm/VocalTractModelPlugin.cpp:37-38, 77, 82).
 void* GAMA_TTS_construct_vocal_tract_model(const void* config_data, int is_interactive)
 {
-	if (!config_data || is_interactive) {
-		if (is_interactive) std::fprintf(stderr, "[gtts_plugin] interactive mode is not supported by the batched GPU model\n");
-		return nullptr;
-	}
+	if (!config_data) return nullptr;
 	try {
 		const char* dev = std::getenv("GTTS_DEVICE");
 		const GS::ConfigurationData& data = *static_cast<const GS::ConfigurationData*>(config_data);
-		GS::VTM::VocalTractModel* vtm = new B200VocalTractModel(data, dev ? std::atoi(dev) : 0);
+		GS::VTM::VocalTractModel* vtm = new B200VocalTractModel(data, dev ? std::atoi(dev) : 0, is_interactive != 0);
 		return vtm;
 	} catch (const std::exception& e) {
 		std::fprintf(stderr, "[gtts_plugin] %s\n", e.what());

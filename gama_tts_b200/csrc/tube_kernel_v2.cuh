@@ -365,6 +365,9 @@ GTTS_DEV void walk_block(const float* frames, long long nFrames, int steps, floa
 		c1 = w.fn1;
 		d1 = __fmul_rn(__fsub_rn(w.fn2, w.fn1), invSteps);
 	}
+	// the groups of four samples in which some lane's control period ends (all 32 lanes vote here: the lanes of a
+	// per-sample utterance leave below)
+	const unsigned slowGroups = __reduce_or_sync(0xffffffffu, (restart >= 0 && restart < kBlock) ? (1u << (restart >> 2)) : 0u);
 	if (perSample) {
 		// one frame per internal sample (the plugin shim records the reference's per-sample parameters): the values
 		// ARE the frames, no walk; `frame` counts the samples consumed so far
@@ -380,7 +383,7 @@ GTTS_DEV void walk_block(const float* frames, long long nFrames, int steps, floa
 		float v[4];
 		// the control period ends inside these four samples on some lane (the three groups of parameters of a slot are
 		// at different blocks): once per period; everywhere else the walk is four additions and one 16-byte store
-		if (__any_sync(0xffffffffu, restart >= j0 && restart < j0 + 4)) {
+		if ((slowGroups >> (j0 >> 2)) & 1u) {
 #pragma unroll
 			for (int q = 0; q < 4; ++q) {
 				const bool r = (j0 + q) == restart;

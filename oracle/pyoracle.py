@@ -203,6 +203,7 @@ class Reference:
                                      C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_long), C.POINTER(C.c_double)]
         L.ref_synthesize_samples.argtypes = [C.c_char_p, C.c_void_p, C.c_long,
                                              C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_long)]
+        L.ref_interactive.argtypes = [C.c_char_p, C.c_void_p, C.c_long, C.c_long, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_long)]
         L.ref_free.argtypes = [C.c_void_p]
         L.ref_batch.argtypes = [C.POINTER(C.c_char_p), C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_long, C.c_int,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
@@ -237,6 +238,16 @@ class Reference:
         p, n, rate = C.POINTER(C.c_float)(), C.c_long(), C.c_double()
         rc = self.lib.ref_synthesize(config_text5(voice5, extra, model), control_rate, frames.ctypes.data, frames.shape[0],
                                      C.byref(p), C.byref(n), C.byref(rate))
+        if rc:
+            raise RuntimeError(self.lib.ref_last_error().decode())
+        return self._take(p, n)
+
+    def interactive(self, voice, params, callback_frames=1024, model=0, extra=None):
+        """The editor's interactive call pattern (InteractiveAudio.cpp:131-186) on per-step parameter rows."""
+        params = _f32(params).reshape(-1, 16)
+        p, n = C.POINTER(C.c_float)(), C.c_long()
+        rc = self.lib.ref_interactive(config_text(voice, model, extra), params.ctypes.data, params.shape[0], callback_frames,
+                                      C.byref(p), C.byref(n))
         if rc:
             raise RuntimeError(self.lib.ref_last_error().decode())
         return self._take(p, n)

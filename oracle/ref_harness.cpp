@@ -130,6 +130,51 @@ int ref_synthesize(const char* config_text, double control_rate, const float* fr
 	}
 }
 
+// The editor's interactive call pattern (gama_tts_editor/src/interactive/InteractiveAudio.cpp:131-186, the JACK process
+// callback) without JACK: the model is constructed with interactive = true; every callback wants `callback_frames`
+// output samples, takes what outputBuffer() holds with VTM::Util::getSamples (which clears the buffer once it is
+// used up, VTMUtil.cpp:30-46) and, if that is not enough, steps the model -- setParameter x 16 + execSynthesisStep,
+// one row of `params` per step -- until it is.  Runs until the rows are used up; returns every sample handed out.
+int ref_interactive(const char* config_text, const float* params, long n_steps, long callback_frames, float** out, long* n_out)
+{
+	try {
+		const std::string path = writeTempConfig(config_text);
+		std::unique_ptr<GS::VTM::VocalTractModel> vtm;
+		try {
+			GS::ConfigurationData data(path);
+			vtm = GS::VTM::VocalTractModel::getInstance(data, true);
+		} catch (...) {
+			unlink(path.c_str());
+			throw;
+		}
+		unlink(path.c_str());
+		std::vector<float> all, cb(static_cast<size_t>(callback_frames));
+		std::vector<float>& buf = vtm->outputBuffer();
+		std::size_t pos = 0;
+		long step = 0;
+		while (step < n_steps) {
+			const std::size_t n = GS::VTM::Util::getSamples(buf, pos, cb.data(), callback_frames, 1.0f);
+			all.insert(all.end(), cb.begin(), cb.begin() + n);
+			if (n == static_cast<std::size_t>(callback_frames)) continue;
+			const std::size_t target = callback_frames - n;
+			while (buf.size() < target && step < n_steps) {
+				for (int i = 0; i < 16; ++i) vtm->setParameter(i, params[step * 16 + i]);
+				vtm->execSynthesisStep();
+				++step;
+			}
+			const std::size_t n2 = GS::VTM::Util::getSamples(buf, pos, cb.data(), target, 1.0f);
+			all.insert(all.end(), cb.begin(), cb.begin() + n2);
+		}
+		*n_out = static_cast<long>(all.size());
+		*out = static_cast<float*>(std::malloc(sizeof(float) * std::max<size_t>(all.size(), 1)));
+		std::memcpy(*out, all.data(), sizeof(float) * all.size());
+		return 0;
+	} catch (const std::exception& e) {
+		g_err = e.what();
+		return 1;
+	}
+}
+
 // Same, but through the per-sample entry points with caller-supplied per-sample parameters (no
 // interpolation): what the plugin seam sees (setAllParameters + execSynthesisStep per internal sample).
 int ref_synthesize_samples(const char* config_text, const float* params, long n_samples, float** out, long* n_out)

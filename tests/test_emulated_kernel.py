@@ -281,3 +281,15 @@ def test_emulated_model5_kernel_matches_oracle(oracle5, real_tracks):
         got = out[oo[u]:oo[u] + ol[u]]
         assert len(got) == len(ref)
         assert np.array_equal(got, ref), u
+
+
+def test_emulated_pipelined_kernel_per_sample_mode(emu_v2, oracle, real_tracks):
+    # steps = 1 (what the plugin shim sends: one row per internal sample) on the pipelined kernel, together with a
+    # normally stepped utterance in the same CTA: the lanes of a per-sample walk leave walk_block early, the others
+    # go on to its warp votes
+    v = default_voice("male")
+    params = np.repeat(real_tracks[0][100:104], 40, axis=0)
+    tr = real_tracks[0][100:120]
+    outs = emu_v2([v], [0, 0], [params, tr], steps=[1, 0])
+    assert np.array_equal(outs[0], oracle.synthesize_samples(v, params))
+    assert np.array_equal(outs[1], oracle.synthesize(v, tr))

@@ -64,6 +64,28 @@ def test_reference_drives_plugin_model5_voice(reference, oracle5, real_tracks, p
         assert np.array_equal(builtin, oracle5.synthesize(v, track))
 
 
+@pytest.mark.gpu
+def test_interactive_call_pattern_through_the_seam(reference, real_tracks, product_lib):
+    # The editor's pattern (InteractiveAudio.cpp:131-186): the model is constructed interactive, stepped until
+    # outputBuffer() holds a callback's worth of samples, drained, stepped on.  The plugin serves it in chunks of 64
+    # internal samples through gtts_stream_*; what the host hears must be the built-in model's samples.
+    _need_plugin()
+    v = default_voice("male")
+    track = real_tracks[0][:150]
+    steps = 80
+    cur = np.repeat(track, steps, axis=0).astype(np.float32)                 # a held-parameter stand-in for the editor's filters
+    ramp = np.linspace(0.0, 1.0, steps, endpoint=False, dtype=np.float32)[None, :, None]
+    nxt = np.concatenate([track[1:], track[-1:]])
+    params = (track[:, None, :] + (nxt - track)[:, None, :] * ramp).reshape(-1, 16).astype(np.float32)
+    assert params.shape == cur.shape
+    for frames in (1024, 256):
+        builtin = reference.interactive(v, params, callback_frames=frames, model=0)
+        plugin = reference.interactive(v, params, callback_frames=frames, model=2000, extra={"dll_path": PLUGIN})
+        n = min(len(builtin), len(plugin))
+        assert n > 0.9 * len(params) * 48000 / 20034 and abs(len(builtin) - len(plugin)) <= 64 * 3 + frames
+        assert full_scale_error(plugin[:n], builtin[:n]) <= 2e-7
+
+
 STOCK = os.path.join(ROOT, "oracle", "_ref", "gama_tts")
 STOCK_VOICE = os.path.join(ROOT, "oracle", "_ref", "voice_0_male")
 
