@@ -310,9 +310,63 @@ def model5_leg(synth, rank, peak):
     ach = (397.0 * n_internal + 168.0 * n_samples) / (ms * 1e-3) * 1e-12
     finite = bool(torch.isfinite(d_out[::1009]).all().item())
     b.close()
-    return {"workload": "%d model-5 utterances (voice 5_male, fs_int 60411.43 Hz) x %d frames (2 s), one GPU" % (n_utt, n_frames),
+    # the reference's own model 5 on the host cores, a bounded sample of the same tracks
+    cpu = None
+    try:
+        from oracle import pyoracle
+        threads = host_threads()
+        n_sample = min(n_utt, threads * 4)
+        fo_s = np.arange(n_sample + 1, dtype=np.int64) * n_frames
+        sec, n_each, _ = pyoracle.Reference().batch(default_voice5("male"), frames[:n_sample * n_frames], fo_s, n_threads=threads)
+        cpu = {"value": float(n_each.sum()) / 48000.0 / sec, "unit": UNIT, "cores": threads, "kind": "reference",
+               "sample": "first %d of the %d tracks, %.2f s wall" % (n_sample, n_utt, sec)}
+    except Exception as e:        # the in-place build of the reference is absent
+        cpu = {"unavailable": str(e)[:120]}
+    return {"cpu_baseline": cpu, "workload": "%d model-5 utterances (voice 5_male, fs_int 60411.43 Hz) x %d frames (2 s), one GPU" % (n_utt, n_frames),
             "kernel": "tube5_kernel", "utterances": n_utt, "audio_seconds": audio, "ms": ms, "value": audio / (ms * 1e-3),
             "unit": UNIT, "warmup": 3, "reps": reps, "finite": finite, "roofline_frac": ach / peak, "achieved_tflops": ach}
+
+
+def small_configs_leg(synth, rank):
+    """BASELINE configs 1 and 5 on rank 0, so that the driver's run carries them: config 1 = ONE real sentence
+    ("Hello world.", 332 control frames captured from the reference's front end, tests/golden/real_tracks.npz) through
+    synthesize() -- planning, copies, kernel --, best of 5; config 5 = one utterance streamed control frame by control
+    frame through gtts_stream_* (5,000 single-frame pushes, host wall clock), and in pushes of 250 frames."""
+    if rank != 0:
+        return None
+    from gama_tts_b200.voices import default_voice
+    out = {}
+    v = default_voice("male")
+    try:
+        hello = np.load(os.path.join(ROOT, "tests", "golden", "real_tracks.npz"))["track0"]
+        best = None
+        for _ in range(6):
+            t0 = time.perf_counter()
+            audio = synth.synthesize(v, [hello])[0]
+            dt = time.perf_counter() - t0
+            best = dt if best is None or dt < best else best
+        out["config1"] = {"workload": "one sentence, %d control frames, voice 0_male/male, one utterance through synthesize()" % len(hello),
+                          "audio_seconds": len(audio) / 48000.0, "ms": best * 1e3, "value": len(audio) / 48000.0 / best, "unit": UNIT}
+    except Exception as e:
+        out["config1"] = {"unavailable": str(e)[:120]}
+    from gama_tts_b200 import tracks as T
+    track = T.tile_track(T.synthetic_track(99, 3000), 10000)
+    res = {}
+    for chunk, n in ((1, 5000), (250, 10000)):
+        st = synth.stream(v)
+        st.push(track[:chunk])                                  # first launch (graph instantiation) outside the clock
+        t0 = time.perf_counter()
+        produced = 0
+        for i in range(chunk, n, chunk):
+            produced += len(st.push(track[i:i + chunk]))
+        dt = time.perf_counter() - t0
+        st.finish()
+        st.close()
+        pushes = (n - chunk) // chunk
+        res["frames_per_push_%d" % chunk] = {"pushes": pushes, "us_per_push": dt / pushes * 1e6,
+                                             "value": produced / 48000.0 / dt, "unit": UNIT}
+    out["config5"] = dict(res, workload="one utterance streamed through gtts_stream_* (control rate 250 Hz: a frame is 4 ms of audio)")
+    return out
 
 
 def main():
@@ -452,6 +506,7 @@ def main():
     # ---- BASELINE configs 3 / 4: a fixed slice of the 65,536-utterance draw, sharded over the ranks ---------
     cfg34 = None if args.no_config3 else config34_leg(synth, rank, world, dist, barrier, max_over_ranks, peak, args)
     m5 = None if args.no_model5 else model5_leg(synth, rank, peak)
+    small = None if args.no_model5 else small_configs_leg(synth, rank)
 
     value = audio_seconds * world / (ms_dev * 1e-3)
     e2e_value = audio_seconds * world / (ms_e2e * 1e-3)
@@ -490,6 +545,8 @@ def main():
             line["config3"] = cfg34
         if m5 is not None:
             line["model5"] = m5
+        if small is not None:
+            line.update(small)
         if world == 1 and not args.no_cpu_baseline:
             threads = host_threads()
             n_sample = min(N_UTT, threads * 16)

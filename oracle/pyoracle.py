@@ -276,7 +276,8 @@ class Reference:
         fo = np.ascontiguousarray(frame_offsets, np.int64)
         U = len(fo) - 1
         vl = [voices] if isinstance(voices, dict) else list(voices)
-        texts = (C.c_char_p * len(vl))(*[config_text(v, model) for v in vl])
+        # a voice dict with model 5's keys (gama_tts_b200.voices.default_voice5) is written with them, model = 5
+        texts = (C.c_char_p * len(vl))(*[config_text5(v) if "glottal_noise_cutoff" in v else config_text(v, model) for v in vl])
         n_each = np.zeros(U, np.int64)
         out = None
         oo_ptr = None
