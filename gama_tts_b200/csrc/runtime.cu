@@ -378,40 +378,20 @@ int uploadPlan(gtts_batch* b)
 		if (std::strcmp(env, "v0") == 0) forceGeneral = true;
 		b->legacy_v1 = std::strcmp(env, "v1") == 0;
 	}
-	// The wide-batch kernel (one thread per utterance, tube_kernel_v3.cuh) is a throughput design: 128 utterances
-	// per SM, about 2.5 us per internal sample for each of them (measured), against 0.25 us on the pipelined kernel,
-	// which finds its parallelism inside the utterance.  Its run time is therefore bounded below by the longest
-	// utterance (a 20 s utterance alone takes 2.3 s), and it pays only for batches of many SHORT utterances: it
-	// takes the up-sampling utterances of a batch when the estimate below says so.  Measured on B200: BASELINE
-	// config 3 (lengths up to 20 s) is 4.5x slower on it than on the pipelined kernel, so configs 2-4 never take
-	// this path.  GTTS_KERNEL=v3 forces it (tests), any other GTTS_KERNEL value forbids it.
+	// The wide-batch kernel (one thread per utterance, tube_kernel_v3.cuh) is kept as a measured alternative, not a
+	// default: a thread advances one sample per ~2.5 us (one warp per SM sub-partition is what its shared-memory
+	// arrays leave room for), against 0.25 us per sample of an utterance on the pipelined kernel.  Measured on B200:
+	// BASELINE config 3 (lengths up to 20 s: the run time is bounded by the longest utterance) 4.5x slower, 37,888
+	// utterances of 0.5-1.5 s -- its best case -- 194 ms against 184 ms.  GTTS_KERNEL=v3 selects it (tests,
+	// tools/v3_probe.py, tools/v3_short_probe.py); it takes the up-sampling utterances of the batch.
 	{
-		bool wideForced = false, wideAllowed = !forceGeneral;
-		if (const char* env = std::getenv("GTTS_KERNEL")) {
-			if (std::strcmp(env, "v3") == 0) wideForced = true;
-			else wideAllowed = false;
-		}
+		bool wideForced = false;
+		if (const char* env = std::getenv("GTTS_KERNEL")) wideForced = std::strcmp(env, "v3") == 0;
 		auto wide = [&](int32_t u) { return p.voices[p.utts[u].voice].src_upsample != 0 && (p.utts[u].flags & 3) == 0; };
 		std::vector<int32_t> cand;
-		if (wideAllowed && !b->streaming) for (int32_t u : p.order) if (wide(u)) cand.push_back(u);
-		std::vector<int32_t> groups;
-		bool take = wideForced && !cand.empty();
-		if (!take && static_cast<int64_t>(cand.size()) >= 64ll * b->h->sms) {
-			groups = wideGroups(p, cand);
-			double iters = 0.0, longest = 0.0, samples = 0.0;
-			for (size_t g = 0; g < groups.size(); g += 32) {
-				const double n = static_cast<double>(p.utts[groups[g]].n_internal) + 26.0;     // lane 0 holds the group's longest
-				iters += n;
-				longest = std::max(longest, n);
-			}
-			for (int32_t u : cand) samples += static_cast<double>(p.utts[u].n_internal);
-			const double sms = static_cast<double>(b->h->sms);
-			const double estWide = std::max(longest, iters / (v3::kWarps * sms)) * 4900.0;   // cycles per iteration of a warp
-			const double estPipelined = samples * 70.0 / sms;                                // cycles per sample and SM, mixed voices
-			take = estWide * 1.25 < estPipelined;
-		}
-		if (take) {
-			if (groups.empty()) groups = wideGroups(p, cand);
+		if (wideForced && !forceGeneral && !b->streaming) for (int32_t u : p.order) if (wide(u)) cand.push_back(u);
+		if (!cand.empty()) {
+			const std::vector<int32_t> groups = wideGroups(p, cand);
 			p.order.erase(std::remove_if(p.order.begin(), p.order.end(), wide), p.order.end());
 			b->n_wide = static_cast<int32_t>(cand.size());
 			b->n_wide_groups = static_cast<int32_t>(groups.size() / 32);

@@ -252,8 +252,8 @@ def test_both_kernels_agree(synth, monkeypatch):
 
 
 def test_wide_batch_kernel_parity(synth, oracle, monkeypatch):
-    # GTTS_KERNEL=v3 forces the one-thread-per-utterance kernel (it is chosen on its own only for batches of very many
-    # short utterances): 200 ragged utterances, every one its own randomised voice, against the oracle; the
+    # GTTS_KERNEL=v3 selects the one-thread-per-utterance kernel (a measured alternative, never the default: DESIGN.md
+    # section 4.3): 200 ragged utterances, every one its own randomised voice, against the oracle; the
     # down-sampling voice in the batch stays on the pipelined kernel
     monkeypatch.setenv("GTTS_KERNEL", "v3")
     rng = np.random.Generator(np.random.PCG64(77))
