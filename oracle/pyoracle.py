@@ -26,7 +26,7 @@ VOICE_KEYS_SCALAR = [
 
 class OracleVoice(C.Structure):
     _fields_ = [(k, C.c_double if t is float else C.c_int) for k, t in VOICE_KEYS_SCALAR] + [
-        ("nasal_radius", C.c_double * 5), ("radius_coef", C.c_double * 8)]
+        ("nasal_radius", C.c_double * 5), ("radius_coef", C.c_double * 8), ("tube_model", C.c_int)]
 
 
 def voice_struct(voice):
@@ -37,6 +37,7 @@ def voice_struct(voice):
         s.nasal_radius[i] = float(voice["nasal_radius_%d" % (i + 1)])
     for i in range(8):
         s.radius_coef[i] = float(voice["radius_%d_coef" % (i + 1)])
+    s.tube_model = int(voice.get("tube_model", 0))      # 0: models 0 / 2, 3: model 3, 4: model 4 (same keys)
     return s
 
 

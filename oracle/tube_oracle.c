@@ -46,6 +46,11 @@ struct oracle_model {
 	/* tube state: [section][0 = top, 1 = bottom], previous-sample values */
 	double oral[N_ORAL][2], nasal[N_NASAL][2];
 	double refl_y1_m, rad_x1_m, rad_y1_m, refl_y1_n, rad_x1_n, rad_y1_n, throat_y1;
+	/* model 3: the two other phases of the three-sample section delay (the waves written at step n are read at step
+	   n + 3: three interleaved copies of the wave state, VocalTractModel2.h:234-250); model 4: its 30 + 18 sections */
+	double oral_d[2][N_ORAL][2], nasal_d[2][N_NASAL][2];
+	long   step;
+	double oral4[30][2], nasal4[18][2];
 	/* current parameters in double (setAllParameters) */
 	double P[N_PARAM];
 	/* SRC: all tube output is kept, conversion is done by the closed form at finish */
@@ -336,6 +341,11 @@ void oracle_reset(oracle_model* m)
 {
 	memset(m->oral, 0, sizeof m->oral);
 	memset(m->nasal, 0, sizeof m->nasal);
+	memset(m->oral_d, 0, sizeof m->oral_d);
+	memset(m->nasal_d, 0, sizeof m->nasal_d);
+	memset(m->oral4, 0, sizeof m->oral4);
+	memset(m->nasal4, 0, sizeof m->nasal4);
+	m->step = 0;
 	m->refl_y1_m = m->rad_x1_m = m->rad_y1_m = 0.0;
 	m->refl_y1_n = m->rad_x1_n = m->rad_y1_n = 0.0;
 	m->throat_y1 = 0.0;
@@ -369,7 +379,8 @@ oracle_model* oracle_create(const oracle_voice* voice)
 	m->nasal_r1 = nr[1];
 
 	const double c = 331.4 + (0.6 * v->temperature);
-	m->fs = (int) ((c * N_ORAL * 100.0) / length);
+	/* VocalTractModel0.h:344; VocalTractModel2.h:419 with SectionDelay = 3 and VocalTractModel4.h (30 sections): 30 */
+	m->fs = (int) ((c * (v->tube_model == 0 ? N_ORAL : 30) * 100.0) / length);
 	const double nyquist = (double) ((float) m->fs / 2.0f);
 	m->breath = v->breathiness / 100.0;
 	m->crossmix = 1.0 / amp60(v->mix_offset);
@@ -467,6 +478,79 @@ static double tube(oracle_model* m, double input, double fric, const double* k, 
 	return output;
 }
 
+/* ---- model 3: VocalTractModel2<double, 3>::vocalTract (VocalTractModel2.h:626-670) ----
+ * The same junctions as model 0, every section a delay line of three samples (in / out pointers over four slots,
+ * :234-250): what a step writes is read three steps later, so the wave state is three interleaved copies, each
+ * advanced every third step.  The end filters (reflection, radiation) run on every sample. */
+static double tube3(oracle_model* m, double input, double fric, const double* k, const double* alpha, const double* tap)
+{
+	const int ph = (int) (m->step % 3);
+	m->step += 1;
+	if (ph != 0) {
+		/* bring phase ph's copy into the working arrays, run the model-0 step, put it back */
+		double so[N_ORAL][2], sn[N_NASAL][2];
+		memcpy(so, m->oral, sizeof so); memcpy(sn, m->nasal, sizeof sn);
+		memcpy(m->oral, m->oral_d[ph - 1], sizeof so); memcpy(m->nasal, m->nasal_d[ph - 1], sizeof sn);
+		const double out = tube(m, input, fric, k, alpha, tap);
+		memcpy(m->oral_d[ph - 1], m->oral, sizeof so); memcpy(m->nasal_d[ph - 1], m->nasal, sizeof sn);
+		memcpy(m->oral, so, sizeof so); memcpy(m->nasal, sn, sizeof sn);
+		return out;
+	}
+	return tube(m, input, fric, k, alpha, tap);
+}
+
+/* ---- model 4: VocalTractModel4<double, 1>::vocalTract (VocalTractModel4.h:671-744) ----
+ * 30 oropharynx + 18 nasal sections of one sample; junctions J1..J7 between S3|S4, S5|S6, S9|S10, S15|S16, S21|S22,
+ * S25|S26, S27|S28, the 3-way junction between S12 and S13, nasal junctions every three sections; sections inside a
+ * region are plain copies (no damping, :303-307) except S18 -> S19, which carries frication tap FC5 (:308-312). */
+static double tube4(oracle_model* m, double input, double fric, const double* k, const double* alpha, const double* tap)
+{
+	enum { T = 0, B = 1, NO = 30, NN = 18 };
+	const double d = m->damping;
+	double (*o)[2] = m->oral4, (*n)[2] = m->nasal4;
+	double oo[NO][2], nn[NN][2];
+	/* junction index at the boundary i | i + 1 (or -1), frication tap injected into section i + 1 (or -1) */
+	static const int jn[NO - 1] = {-1, -1, 0, -1, 1, -1, -1, -1, 2, -1, -1, /*S12|S13: 3-way*/ -2, -1, -1, 3, -1, -1, /*S18|S19*/ -3, -1, -1, 4, -1, -1, -1, 5, -1, 6, -1, -1};
+	static const int ft[NO - 1] = {-1, -1, -1, -1, 0, -1, -1, -1, 1, -1, -1, 2, -1, -1, 3, -1, -1, 4, -1, -1, 5, -1, -1, -1, 6, -1, 7, -1, -1};
+	oo[0][T] = o[0][B] * d + input;
+	for (int i = 0; i < NO - 1; ++i) {
+		const double fn = ft[i] >= 0 ? tap[ft[i]] * fric : 0.0;
+		if (jn[i] >= 0) {
+			const double delta = k[jn[i]] * (o[i][T] - o[i + 1][B]);
+			oo[i + 1][T] = (o[i][T] + delta) * d + fn;
+			oo[i][B] = (o[i + 1][B] + delta) * d;
+		} else if (jn[i] == -2) {
+			const double jp = alpha[0] * o[i][T] + alpha[1] * o[i + 1][B] + alpha[2] * n[0][B];
+			oo[i][B] = (jp - o[i][T]) * d;
+			oo[i + 1][T] = (jp - o[i + 1][B]) * d + fn;
+			nn[0][T] = (jp - n[0][B]) * d;
+		} else if (jn[i] == -3) {
+			oo[i + 1][T] = o[i][T] * d + fn;
+			oo[i][B] = o[i + 1][B] * d;
+		} else {
+			oo[i + 1][T] = o[i][T];
+			oo[i][B] = o[i + 1][B];
+		}
+	}
+	oo[NO - 1][B] = d * refl(m->refl_b0_m, m->refl_a1_m, &m->refl_y1_m, k[7] * o[NO - 1][T]);
+	double output = rad(m->rad_m, &m->rad_x1_m, &m->rad_y1_m, (1.0 + k[7]) * o[NO - 1][T]);
+	for (int i = 0; i < NN - 1; ++i) {
+		if (i % 3 == 2) {
+			const double delta = m->nasal_k[i / 3] * (n[i][T] - n[i + 1][B]);
+			nn[i + 1][T] = (n[i][T] + delta) * d + 0.0;
+			nn[i][B] = (n[i + 1][B] + delta) * d;
+		} else {
+			nn[i + 1][T] = n[i][T];
+			nn[i][B] = n[i + 1][B];
+		}
+	}
+	nn[NN - 1][B] = d * refl(m->refl_b0_n, m->refl_a1_n, &m->refl_y1_n, m->nasal_k[5] * n[NN - 1][T]);
+	output += rad(m->rad_n, &m->rad_x1_n, &m->rad_y1_n, (1.0 + m->nasal_k[5]) * n[NN - 1][T]);
+	memcpy(m->oral4, oo, sizeof oo);
+	memcpy(m->nasal4, nn, sizeof nn);
+	return output;
+}
+
 /* ---- :698-716 (setAllParameters) + :396-445 (execSynthesisStep) ---- */
 void oracle_step(oracle_model* m, const float* p)
 {
@@ -548,7 +632,9 @@ void oracle_step(oracle_model* m, const float* p)
 	const double fr = m->bp_b0 * (sig - m->bp_x2) - m->bp_a1 * m->bp_y1 - m->bp_a2 * m->bp_y2;
 	m->bp_x2 = m->bp_x1; m->bp_x1 = sig; m->bp_y2 = m->bp_y1; m->bp_y1 = fr;
 
-	double s = tube(m, (pulse + (ah1 * sig)) * 0.125, fr, k, alpha, tap);
+	const double tube_in = (pulse + (ah1 * sig)) * 0.125;
+	double s = m->v.tube_model == 3 ? tube3(m, tube_in, fr, k, alpha, tap)
+	         : (m->v.tube_model == 4 ? tube4(m, tube_in, fr, k, alpha, tap) : tube(m, tube_in, fr, k, alpha, tap));
 	/* Throat.h:80-85 */
 	{
 		const double y = m->throat_b0 * (pulse * 0.125) - m->throat_a1 * m->throat_y1;
