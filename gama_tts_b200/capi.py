@@ -23,6 +23,7 @@ class VoiceConfig(C.Structure):
         ("nose_coefficient", C.c_double), ("throat_cutoff", C.c_double), ("throat_volume", C.c_double),
         ("mix_offset", C.c_double), ("global_radius_coef", C.c_double), ("global_nasal_radius_coef", C.c_double),
         ("aperture_radius", C.c_double), ("nasal_radius", C.c_double * 5), ("radius_coef", C.c_double * 8),
+        ("tube_model", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 
@@ -36,6 +37,8 @@ def voice_config(voice):
         elif name == "radius_coef":
             for i in range(8):
                 s.radius_coef[i] = float(voice["radius_%d_coef" % (i + 1)])
+        elif name in ("tube_model", "reserved_"):
+            setattr(s, name, int(voice.get(name, 0)))        # 0: models 0 / 2, 3: model 3, 4: model 4
         elif ctype is C.c_int32:
             setattr(s, name, int(voice[name]))
         else:

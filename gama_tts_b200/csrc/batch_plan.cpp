@@ -16,7 +16,10 @@ std::string planBatch(const gtts_voice_config* voices, int32_t nVoices, const in
 	plan.voices.resize(nVoices);
 	for (int32_t i = 0; i < nVoices; ++i) {
 		const char* e = deriveVoice(voices[i], plan.voices[i]);
-		if (e) return std::string("voice ") + std::to_string(i) + ": " + e;
+		if (e) {
+			if (std::string(e).find("not implemented") != std::string::npos) *err = GTTS_ERR_UNSUPPORTED;
+			return std::string("voice ") + std::to_string(i) + ": " + e;
+		}
 	}
 	plan.utts.resize(nUtt);
 	plan.out_offsets.assign(nUtt + 1, 0);

@@ -73,7 +73,8 @@ int internalRate(const gtts_voice_config& c)
 	double length = c.vocal_tract_length_offset + c.vocal_tract_length;
 	if (length < 3.0) length = 3.0; else if (length > 30.0) length = 30.0;
 	const double speed = 331.4 + (0.6 * c.temperature);       // VTMUtil.h:107-113
-	return static_cast<int>((speed * 10 * 100.0) / length);
+	// models 3 and 4: 30 section delays along the tract instead of 10 (VocalTractModel2.h:419, VocalTractModel4.h)
+	return static_cast<int>((speed * (c.tube_model == 0 ? 10 : 30) * 100.0) / length);
 }
 
 int controlSteps(int fs, double controlRate)
@@ -86,6 +87,8 @@ const char* deriveVoice(const gtts_voice_config& c, VoiceDev& v)
 	std::memset(&v, 0, sizeof v);
 	if (!(c.output_rate > 0.0)) return "output_rate must be positive";
 	if (c.waveform != 0 && c.waveform != 1) return "waveform must be 0 (pulse) or 1 (sine)";
+	if (c.tube_model != 0 && c.tube_model != 3 && c.tube_model != 4) return "tube_model must be 0 (models 0 / 2), 3 or 4";
+	v.tube_model = c.tube_model;
 	v.fs = internalRate(c);
 	if (v.fs <= 0) return "internal sample rate is not positive";
 	v.waveform = c.waveform;
@@ -149,6 +152,8 @@ const char* deriveVoice(const gtts_voice_config& c, VoiceDev& v)
 		v.src_upsample = 0;
 		v.src_phase_inc = static_cast<uint32_t>(std::rint(v.src_ratio * 65536));
 		v.src_pad = static_cast<int>(kSrcZeroCrossings / rounded) + 1;
+		// the kernels' 128-entry ring holds a converter window of 2 pad + 32 inputs (models 3 / 4 with a tract below ~6.2 cm)
+		if (v.src_pad > 48) return "internal rate above ~3.6 x the output rate (converter wing longer than 48 taps) is not implemented";
 	}
 	return nullptr;
 }

@@ -134,6 +134,14 @@ B200VocalTractModel::B200VocalTractModel(const GS::ConfigurationData& data, int 
 	voice_.aperture_radius = data.value<double>("aperture_radius");
 	for (int i = 0; i < 5; ++i) voice_.nasal_radius[i] = data.value<double>("nasal_radius_" + std::to_string(i + 1));
 	for (int i = 0; i < 8; ++i) voice_.radius_coef[i] = data.value<double>("radius_" + std::to_string(i + 1) + "_coef");
+	// "model" says 2000 here; a host that wants the plugin to stand in for model 3 or 4 (same keys as model 0) adds
+	// plugin_tube_model = 3 | 4 to the configuration (absent: models 0 / 2)
+	try {
+		voice_.tube_model = data.value<int>("plugin_tube_model");
+	} catch (...) {
+		voice_.tube_model = 0;
+	}
+	if (interactive_ && voice_.tube_model != 0) throw std::runtime_error("interactive mode is implemented for model-0 voices only");
 
 	if (gtts_voice_internal_rate(&voice_, &internalRate_) != GTTS_OK) throw std::runtime_error(gtts_last_error());
 	int64_t nInternal = 0, nOut = 0;

@@ -387,7 +387,7 @@ int uploadPlan(gtts_batch* b)
 	{
 		bool wideForced = false;
 		if (const char* env = std::getenv("GTTS_KERNEL")) wideForced = std::strcmp(env, "v3") == 0;
-		auto wide = [&](int32_t u) { return p.voices[p.utts[u].voice].src_upsample != 0 && (p.utts[u].flags & 3) == 0; };
+		auto wide = [&](int32_t u) { const VoiceDev& v = p.voices[p.utts[u].voice]; return v.src_upsample != 0 && v.tube_model == 0 && (p.utts[u].flags & 3) == 0; };
 		std::vector<int32_t> cand;
 		if (wideForced && !forceGeneral && !b->streaming) for (int32_t u : p.order) if (wide(u)) cand.push_back(u);
 		if (!cand.empty()) {
@@ -400,7 +400,8 @@ int uploadPlan(gtts_batch* b)
 			GTTS_CUDA(cudaStreamSynchronize(b->stream));      // `groups` goes out of scope
 		}
 	}
-	auto fast = [&](int32_t u) { const UttDesc& d = p.utts[u]; return !forceGeneral && (d.steps >= kBlock || d.steps == 1); };
+	// (models 3 and 4 -- VoiceDev::tube_model -- exist in the general kernel only)
+	auto fast = [&](int32_t u) { const UttDesc& d = p.utts[u]; return !forceGeneral && p.voices[d.voice].tube_model == 0 && (d.steps >= kBlock || d.steps == 1); };
 	const auto mid = std::stable_partition(p.order.begin(), p.order.end(), fast);
 	b->n_fast = static_cast<int32_t>(mid - p.order.begin());
 	if (b->n_fast > 0 || b->n_wide > 0) {
@@ -938,6 +939,7 @@ int gtts_stream_open(gtts_handle* h, const gtts_voice_config* voice, double cont
 	if (!s) return fail(GTTS_ERR_NOMEM, "out of memory");
 	s->h = h;
 	s->voice = *voice;
+	if (voice->tube_model != 0) { delete s; return fail(GTTS_ERR_UNSUPPORTED, "streaming is implemented for models 0 / 2 only (tube_model 0)"); }
 	// a one-utterance batch whose descriptor is rewritten for every chunk
 	const int64_t fo[2] = {0, 0};
 	const int32_t so[1] = {steps_override};

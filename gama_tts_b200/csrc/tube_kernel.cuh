@@ -491,63 +491,167 @@ GTTS_DEV TubeRole tube_role(const VoiceDev& V, int lane)
 	return r;
 }
 
+// one internal sample of the tube (the waves of sample j from those in `t`)
+GTTS_DEV void tube_step(WarpSm* S, const TubeRole& R, double d, int g, int base, int rowA, int rowB, int j, TubeLane& t)
+{
+	const double kA = R.rowA < 0 ? R.constA : S->row[rowA][j];
+	const double kB = R.rowB < 0 ? R.constB : S->row[rowB][j];
+	const int ip = S->ip[j];
+	const double pa = S->row[R_PA][j], pb = S->row[R_PB][j];
+	const double tfA = (R.tapA == ip) ? pa : ((R.tapA == ip + 1) ? pb : 0.0);
+	const double tfB = (R.tapB == ip) ? pa : ((R.tapB == ip + 1) ? pb : 0.0);
+
+	// cell A: always a 2-port junction
+	const double dlA = kA * (t.aT - t.aB);
+	const double aTo = ((t.aT + dlA) * d) + tfA;
+	const double aBo = (t.aB + dlA) * d;
+
+	double bTo, bBo, linkOut = aBo;
+	if (g == 1) {
+		// 3-way junction (:595-604): bT = T[S4], bB = B[S5], extra = NB[N1]
+		const double aL = S->row[R_AL][j], aU = S->row[R_AU][j];
+		const double jp = (aL * t.bT) + (aL * t.bB) + (aU * t.extra);
+		bBo = (jp - t.bT) * d;
+		bTo = ((jp - t.bB) * d) + tfB;
+		linkOut = (jp - t.extra) * d;              // NT[N1] of the next sample
+	} else if (g == 4 || g == 7) {
+		// open end (:634-636, 653-654): reflection lowpass, y = b0 x - a1 y1
+		if (g == 4) S->row[R_ENDM][j] = t.bT; else S->row[R_ENDN][j] = t.bT;
+		const double y = R.refl_b0 * (kB * t.bT) - R.refl_a1 * t.extra;
+		t.extra = y;
+		bBo = d * y;
+		bTo = 0.0;
+	} else {
+		const double dlB = kB * (t.bT - t.bB);
+		bTo = ((t.bT + dlB) * d) + tfB;
+		bBo = (t.bB + dlB) * d;
+	}
+
+	// exchange with the neighbouring lanes
+	const double fromPrev = shfl_d(bTo, base + ((g + 7) & 7), 32);       // B.Tout of lane g-1
+	const double fromNext = shfl_d(aBo, base + ((g + 1) & 7), 32);       // A.Bout of lane g+1
+	const double link = shfl_d(linkOut, base + ((g == 1) ? 5 : 1), 32);  // lane 1 <-> lane 5
+	double nextAT = fromPrev;
+	if (g == 0) {
+		nextAT = (t.extra * d) + S->row[R_IN][j];   // T[S1] = B[S1] d + input (:572-573)
+		t.extra = aBo;                             // B[S1] of the next sample
+	} else if (g == 5) {
+		nextAT = link;                             // NT[N1] from the 3-way junction
+	} else if (g == 1) {
+		t.extra = link;                            // NB[N1] from lane 5's cell A
+	}
+	t.aT = nextAT;
+	t.aB = bBo;
+	t.bT = aTo;
+	t.bB = fromNext;
+}
+
 GTTS_DEV void stage_tube(WarpSm* S, const VoiceDev& V, const TubeRole& R, int lane, int nb, TubeLane& t)
 {
 	const double d = V.damping;
 	const int g = R.g;
 	const int base = lane & ~7;
 	const int rowA = R.rowA < 0 ? 0 : R.rowA, rowB = R.rowB < 0 ? 0 : R.rowB;
+	for (int j = 0; j < nb; ++j) tube_step(S, R, d, g, base, rowA, rowB, j, t);
+	__syncwarp();
+}
+
+// Model 3 (VocalTractModel2<double, 3>, VocalTractModel2.h:234-268, 626-670): every section is a delay line of three
+// samples -- what a step writes is read three steps later -- so the wave state is three interleaved copies of the
+// model-0 state, each advanced every third sample; t[0] is the copy of the current sample.  The reflection filters
+// of the two open ends run on every sample: their state (`extra` of lanes 4 and 7) is shared by the copies.
+GTTS_DEV void stage_tube_delay3(WarpSm* S, const VoiceDev& V, const TubeRole& R, int lane, int nb, TubeLane* t)
+{
+	const double d = V.damping;
+	const int g = R.g;
+	const int base = lane & ~7;
+	const int rowA = R.rowA < 0 ? 0 : R.rowA, rowB = R.rowB < 0 ? 0 : R.rowB;
+	const bool isEnd = g == 4 || g == 7;
 	for (int j = 0; j < nb; ++j) {
-		const double kA = R.rowA < 0 ? R.constA : S->row[rowA][j];
-		const double kB = R.rowB < 0 ? R.constB : S->row[rowB][j];
+		TubeLane cur = t[0];
+		tube_step(S, R, d, g, base, rowA, rowB, j, cur);
+		t[0] = t[1];
+		t[1] = t[2];
+		t[2] = cur;
+		if (isEnd) { t[0].extra = cur.extra; t[1].extra = cur.extra; }
+	}
+	__syncwarp();
+}
+
+// Model 4 (VocalTractModel4<double, 1>, VocalTractModel4.h:671-744): 30 oropharynx sections on lanes 0..29, the 18
+// nasal sections on lanes 12..29 (N1 shares a lane with S13 -- the three waves of the velum junction are where the four
+// neighbour shuffles of a sample put them -- and N18 shares lane 29 with S30: both open ends on one lane).  The
+// junctions of model 0 (pressure waves) at the region boundaries S3|S4, S5|S6, S9|S10, S15|S16, S21|S22, S25|S26,
+// S27|S28 and every third nasal section; sections inside a region are plain copies without damping (:303-307), except
+// S18 -> S19, which carries frication tap FC5 and is damped (:308-312).  Coefficients, taps and end filters are the
+// ones the model-0 stages of this kernel produce.
+struct Tube4Lane { double oT, oB, nT, nB, yM, yN; };
+
+GTTS_DEV void stage_tube4(WarpSm* S, const VoiceDev& V, int lane, int nb, Tube4Lane& t)
+{
+	const double d = V.damping;
+	// boundary (lane - 1 | lane): junction row / damping / frication tap of this section's top wave; boundary
+	// (lane | lane + 1): junction row / damping of its bottom wave
+	int rowL = -1, rowR = -1, tapL = -100;
+	double dL = 1.0, dR = 1.0;
+	{
+		const int jl[7] = {2, 4, 8, 14, 20, 24, 26};          // left section of J1..J7
+		const int jt[7] = {-100, 0, 1, 3, 5, 6, 7};           // frication tap injected behind the junction (FC1 at J2 ... FC8 at J7)
+#pragma unroll
+		for (int q = 0; q < 7; ++q) {
+			if (jl[q] + 1 == lane) { rowL = R_K0 + q; dL = d; tapL = jt[q]; }
+			if (jl[q] == lane) { rowR = R_K0 + q; dR = d; }
+		}
+		if (lane == 18) { dL = d; tapL = 4; }                 // S18 -> S19: damped, FC5
+		if (lane == 17) dR = d;
+		if (lane == 12) tapL = 2;                             // FC3 behind the velum junction
+	}
+	const int ni = lane - 12;                                 // nasal section (valid 0..17)
+	double nkLc = 0.0, nkRc = 0.0, ndL = 1.0, ndR = 1.0;
+	bool nkLrow = false, nkRrow = false;
+	if (ni >= 0 && ni < 18) {
+		if (ni >= 3 && ni % 3 == 0) { const int q = ni / 3 - 1; ndL = d; if (q == 0) nkLrow = true; else nkLc = V.nasal_k[q]; }
+		if (ni % 3 == 2 && ni < 17) { const int q = ni / 3; ndR = d; if (q == 0) nkRrow = true; else nkRc = V.nasal_k[q]; }
+	}
+	const int prev = (lane + 31) & 31, next = (lane + 1) & 31;
+	for (int j = 0; j < nb; ++j) {
+		const double kL = rowL >= 0 ? S->row[rowL][j] : 0.0;
+		const double kR = rowR >= 0 ? S->row[rowR][j] : 0.0;
+		const double nkL = nkLrow ? S->row[R_NK0][j] : nkLc;
+		const double nkR = nkRrow ? S->row[R_NK0][j] : nkRc;
 		const int ip = S->ip[j];
-		const double pa = S->row[R_PA][j], pb = S->row[R_PB][j];
-		const double tfA = (R.tapA == ip) ? pa : ((R.tapA == ip + 1) ? pb : 0.0);
-		const double tfB = (R.tapB == ip) ? pa : ((R.tapB == ip + 1) ? pb : 0.0);
-
-		// cell A: always a 2-port junction
-		const double dlA = kA * (t.aT - t.aB);
-		const double aTo = ((t.aT + dlA) * d) + tfA;
-		const double aBo = (t.aB + dlA) * d;
-
-		double bTo, bBo, linkOut = aBo;
-		if (g == 1) {
-			// 3-way junction (:595-604): bT = T[S4], bB = B[S5], extra = NB[N1]
+		const double tf = (tapL == ip) ? S->row[R_PA][j] : ((tapL == ip + 1) ? S->row[R_PB][j] : 0.0);
+		const double oTL = shfl_d(t.oT, prev, 32), oBR = shfl_d(t.oB, next, 32);
+		const double nTL = shfl_d(t.nT, prev, 32), nBR = shfl_d(t.nB, next, 32);
+		// propagate / propagateJunction (VocalTractModel4.h:303-318)
+		double noT = (oTL + kL * (oTL - t.oB)) * dL + tf;
+		double noB = (oBR + kR * (t.oT - oBR)) * dR;
+		double nnT = (nTL + nkL * (nTL - t.nB)) * ndL;
+		double nnB = (nBR + nkR * (t.nT - nBR)) * ndR;
+		if (lane == 0) {
+			noT = t.oB * d + S->row[R_IN][j];                                   // :676
+		} else if (lane == 11) {
+			// 3-way junction (:319-328), S12 side
 			const double aL = S->row[R_AL][j], aU = S->row[R_AU][j];
-			const double jp = (aL * t.bT) + (aL * t.bB) + (aU * t.extra);
-			bBo = (jp - t.bT) * d;
-			bTo = ((jp - t.bB) * d) + tfB;
-			linkOut = (jp - t.extra) * d;              // NT[N1] of the next sample
-		} else if (g == 4 || g == 7) {
-			// open end (:634-636, 653-654): reflection lowpass, y = b0 x - a1 y1
-			if (g == 4) S->row[R_ENDM][j] = t.bT; else S->row[R_ENDN][j] = t.bT;
-			const double y = R.refl_b0 * (kB * t.bT) - R.refl_a1 * t.extra;
-			t.extra = y;
-			bBo = d * y;
-			bTo = 0.0;
-		} else {
-			const double dlB = kB * (t.bT - t.bB);
-			bTo = ((t.bT + dlB) * d) + tfB;
-			bBo = (t.bB + dlB) * d;
+			const double jp = aL * t.oT + aL * oBR + aU * nBR;
+			noB = (jp - t.oT) * d;
+		} else if (lane == 12) {
+			const double aL = S->row[R_AL][j], aU = S->row[R_AU][j];
+			const double jp = aL * oTL + aL * t.oB + aU * t.nB;
+			noT = (jp - t.oB) * d + tf;
+			nnT = (jp - t.nB) * d;
+		} else if (lane == 29) {
+			// both open ends (:712-716, 737-741): reflection low-pass; the radiation filters run in stage_post
+			S->row[R_ENDM][j] = t.oT;
+			S->row[R_ENDN][j] = t.nT;
+			const double ym = V.refl_b0_m * (S->row[R_K7][j] * t.oT) - V.refl_a1_m * t.yM;
+			t.yM = ym;
+			noB = d * ym;
+			const double yn = V.refl_b0_n * (V.nasal_k[5] * t.nT) - V.refl_a1_n * t.yN;
+			t.yN = yn;
+			nnB = d * yn;
 		}
-
-		// exchange with the neighbouring lanes
-		const double fromPrev = shfl_d(bTo, base + ((g + 7) & 7), 32);       // B.Tout of lane g-1
-		const double fromNext = shfl_d(aBo, base + ((g + 1) & 7), 32);       // A.Bout of lane g+1
-		const double link = shfl_d(linkOut, base + ((g == 1) ? 5 : 1), 32);  // lane 1 <-> lane 5
-		double nextAT = fromPrev;
-		if (g == 0) {
-			nextAT = (t.extra * d) + S->row[R_IN][j];   // T[S1] = B[S1] d + input (:572-573)
-			t.extra = aBo;                             // B[S1] of the next sample
-		} else if (g == 5) {
-			nextAT = link;                             // NT[N1] from the 3-way junction
-		} else if (g == 1) {
-			t.extra = link;                            // NB[N1] from lane 5's cell A
-		}
-		t.aT = nextAT;
-		t.aB = bBo;
-		t.bT = aTo;
-		t.bB = fromNext;
+		t.oT = noT; t.oB = noB; t.nT = nnT; t.nB = nnB;
 	}
 	__syncwarp();
 }
@@ -588,7 +692,7 @@ GTTS_DEV void stage_post(WarpSm* S, const VoiceDev& V, int lane, int nb, long lo
 // f = (k inc) & 0xFFFF; left wing taps h[L + 256 j] on x[e-13-j], right wing taps (from ~f) on
 // x[e-12+j]; one accumulator, left wing first.  Produces outputs [kDone, kEnd).
 GTTS_DEV void stage_src(const WarpSm* S, const double2* tab, const VoiceDev& V, int lane,
-			long long kDone, long long kEnd, float* out)
+			long long kDone, long long kEnd, float* out, long long nEnd)
 {
 	for (long long k = kDone + lane; k < kEnd; k += 32) {
 		const unsigned long long t = (unsigned long long) k * V.src_inc;
@@ -603,7 +707,7 @@ GTTS_DEV void stage_src(const WarpSm* S, const double2* tab, const VoiceDev& V, 
 			unsigned ii;
 			while ((ii = (ph >> 8)) < (unsigned) kSrcFilterLen) {
 				const double2 c = tab[ii];
-				acc += S->xring[(int) (pos & (kSrcRing - 1))] * (c.x + (c.y * ((double) (ph & 0xFFu) / 256)));
+				acc += (pos < nEnd ? S->xring[(int) (pos & (kSrcRing - 1))] : 0.0) * (c.x + (c.y * ((double) (ph & 0xFFu) / 256)));
 				pos -= 1;
 				ph += V.src_phase_inc;
 			}
@@ -611,7 +715,7 @@ GTTS_DEV void stage_src(const WarpSm* S, const double2* tab, const VoiceDev& V, 
 			pos = (long long) e - V.src_pad + 1;
 			while ((ii = (ph >> 8)) < (unsigned) kSrcFilterLen) {
 				const double2 c = tab[ii];
-				acc += S->xring[(int) (pos & (kSrcRing - 1))] * (c.x + (c.y * ((double) (ph & 0xFFu) / 256)));
+				acc += (pos < nEnd ? S->xring[(int) (pos & (kSrcRing - 1))] : 0.0) * (c.x + (c.y * ((double) (ph & 0xFFu) / 256)));
 				pos += 1;
 				ph += V.src_phase_inc;
 			}
@@ -668,6 +772,9 @@ GTTS_DEV void build_table(WarpSm* S, const VoiceDev& V, int lane)
 }
 
 // ---- per-utterance driver: one warp, all stages in sequence -----------------------------------------
+// TM: the voice's tube (VoiceDev::tube_model): 0 models 0 / 2, 3 model 3, 4 model 4.  Streaming state (UttState) exists
+// for TM == 0 only; the host refuses streams of the other models.
+template<int TM>
 GTTS_DEV void run_utterance(WarpSm* S, const double2* tab, const KernelParams& P, const UttDesc& U, int lane)
 {
 	const VoiceDev V = P.voices[U.voice];
@@ -680,6 +787,9 @@ GTTS_DEV void run_utterance(WarpSm* S, const double2* tab, const KernelParams& P
 	double seed = 0.7892347, noiseX1 = 0.0, pos = 0.0;
 	BandpassState bp = {0.0, 0.0, 0.0, 0.0};
 	TubeLane tl = {0.0, 0.0, 0.0, 0.0, 0.0};
+	TubeLane tl3[TM == 3 ? 3 : 1];
+	for (int q = 0; q < (TM == 3 ? 3 : 1); ++q) tl3[q] = tl;
+	Tube4Lane tl4 = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 	PostState ps = {0.0, 0.0};
 	long long nDone = 0, kDone = 0;
 	int tableLow = kNoLowMark;
@@ -724,6 +834,7 @@ GTTS_DEV void run_utterance(WarpSm* S, const double2* tab, const KernelParams& P
 
 	float* out = P.out + U.out_begin;
 	const long long nOutTotal = U.n_out;
+	const long long nEnd = nDone + U.n_internal;      // inputs of this utterance (stream: up to the end of this chunk)
 	const float* frames = P.frames + U.frame_begin * kNumParams;
 
 	for (long long p = 0; p < U.n_frames; ++p) {
@@ -744,23 +855,26 @@ GTTS_DEV void run_utterance(WarpSm* S, const double2* tab, const KernelParams& P
 			stage_lookup(S, V, lane, nb, nDone, tableLow);
 			stage_fir_mix(S, V, lane, nb, nDone, lp);
 			stage_bandpass(S, lane, nb, bp);
-			stage_tube(S, V, role, lane, nb, tl);
+			if (TM == 3) stage_tube_delay3(S, V, role, lane, nb, tl3);
+			else if (TM == 4) stage_tube4(S, V, lane, nb, tl4);
+			else stage_tube(S, V, role, lane, nb, tl);
 			stage_post(S, V, lane, nb, nDone, ps);
 			nDone += nb;
 			// outputs whose right wing is complete: (k inc) >> 16 <= nDone - 1
 			long long kEnd = (long long) ((((unsigned long long) nDone << 16) + V.src_inc - 1) / V.src_inc);
 			if (kEnd > nOutTotal) kEnd = nOutTotal;
-			stage_src(S, tab, V, lane, kDone, kEnd, out);
+			stage_src(S, tab, V, lane, kDone, kEnd, out, nEnd);
 			if (kEnd > kDone) kDone = kEnd;
 			__syncwarp();
 		}
 	}
 
 	if (!noFlush) {
-		// flushBuffer(): 2*pad zeros, then everything that is left (SampleRateConverter.h:462-471)
-		for (int i = lane; i < 2 * V.src_pad; i += 32) S->xring[(nDone + i) & (kSrcRing - 1)] = 0.0;
+		// flushBuffer(): 2*pad zeros, then everything that is left (SampleRateConverter.h:462-471).  The down-sampling
+		// converter takes the inputs past the end as zero instead (up to 96 zeros do not fit the ring next to its window).
+		if (V.src_upsample) for (int i = lane; i < 2 * V.src_pad; i += 32) S->xring[(nDone + i) & (kSrcRing - 1)] = 0.0;
 		__syncwarp();
-		stage_src(S, tab, V, lane, kDone, nOutTotal, out);
+		stage_src(S, tab, V, lane, kDone, nOutTotal, out, nEnd);
 		kDone = nOutTotal;
 	}
 
@@ -814,7 +928,10 @@ GTTS_DEV void tube_cta_body(const KernelParams& P, unsigned char* smem, int tid,
 		q = __shfl_sync(0xffffffffu, q, 0, 32);
 		if (q >= P.n_utt) break;
 		const UttDesc U = P.utts[P.order[q]];
-		run_utterance(S, tab, P, U, lane);
+		const int tm = P.voices[U.voice].tube_model;      // warp-uniform
+		if (tm == 3) run_utterance<3>(S, tab, P, U, lane);
+		else if (tm == 4) run_utterance<4>(S, tab, P, U, lane);
+		else run_utterance<0>(S, tab, P, U, lane);
 	}
 }
 

@@ -27,7 +27,7 @@ struct VoiceDev {
 	int32_t src_pad;
 	uint32_t src_inc;            // timeRegisterIncrement_
 	uint32_t src_phase_inc;      // downsampling only
-	int32_t pad0_;
+	int32_t tube_model;          // 0: models 0 / 2; 3: three-sample section delay; 4: 30 + 18 sections (general kernel only)
 	double src_ratio;            // output_rate / fs
 	double tn_length;            // div2 - div1
 	double tn_delta;             // rint(512 (tnMax - tnMin)/100); != 0 -> fall segment depends on amplitude

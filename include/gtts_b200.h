@@ -29,7 +29,7 @@ extern "C" {
 #endif
 
 #define GTTS_NUM_PARAMS 16          /* control parameters per frame (artic.xml:38-53 order) */
-#define GTTS_ABI_VERSION 1
+#define GTTS_ABI_VERSION 2          /* 2: gtts_voice_config::tube_model */
 
 enum {
 	GTTS_OK = 0,
@@ -72,6 +72,14 @@ typedef struct gtts_voice_config {
 	double aperture_radius;             /* cm */
 	double nasal_radius[5];             /* nasal_radius_1 .. nasal_radius_5, cm */
 	double radius_coef[8];              /* radius_1_coef .. radius_8_coef */
+	/* Which of the reference's models that read THIS key set the voice runs on (VocalTractModel.cpp:38-49):
+	 *   0  models 0 and 2: VocalTractModel0<double> / VocalTractModel2<double, 1> -- the same arithmetic
+	 *   3  model 3: VocalTractModel2<double, 3>, three samples of delay per section (VocalTractModel2.h:234-268, 626-670)
+	 *   4  model 4: VocalTractModel4<double, 1>, 30 + 18 sections (VocalTractModel4.h:671-744)
+	 * Models 3 and 4 run at three times the internal rate (60,102 Hz for 0_male) on the general kernel: batch entry
+	 * points and the plugin seam; no streaming. */
+	int32_t tube_model;
+	int32_t reserved_;                  /* 0 */
 } gtts_voice_config;
 
 typedef struct gtts_handle gtts_handle;    /* one per GPU */

@@ -293,3 +293,21 @@ def test_emulated_pipelined_kernel_per_sample_mode(emu_v2, oracle, real_tracks):
     outs = emu_v2([v], [0, 0], [params, tr], steps=[1, 0])
     assert np.array_equal(outs[0], oracle.synthesize_samples(v, params))
     assert np.array_equal(outs[1], oracle.synthesize(v, tr))
+
+
+def test_emulated_general_kernel_models_3_and_4(emu, oracle, real_tracks):
+    # tube_model 3 (three-sample section delay: three interleaved wave states) and 4 (30 + 18 sections, lane = section)
+    # on the general kernel, at three times the internal rate (down-sampling converter, up to 39 taps a wing for the
+    # shortest tract), mixed with model-0 utterances in one CTA: bit-identical to the oracle
+    rng = np.random.Generator(np.random.PCG64(4))
+    hello, shells = real_tracks[0], real_tracks[2]
+    base = [default_voice("male"), default_voice("baby"), random_voice(rng)]
+    voices = [dict(v, tube_model=m) for m in (3, 4, 0) for v in base]
+    tracks = [hello[:20], hello[104:114], T.synthetic_track(6, 14)] * 3
+    res = emu(voices, list(range(9)), tracks, warps=2)
+    for v, tr, out in zip(voices, tracks, res):
+        ref = oracle.synthesize(v, tr)
+        assert len(out) == len(ref)
+        assert full_scale_error(out, ref) <= 1e-9
+        if v["glottal_pulse_tn_min"] == v["glottal_pulse_tn_max"]:
+            assert np.array_equal(out, ref)

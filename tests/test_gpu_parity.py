@@ -526,3 +526,27 @@ def test_model5_pcm16_output_stage_is_bit_exact(synth, oracle, golden5):
         assert scale[u] == np.float32(ref_scale)
         assert np.array_equal(p, ref_pcm), names[u]
     b.close()
+
+
+# ---- models 2, 3 and 4 (gtts_voice_config::tube_model, general kernel) ------------------------------------------------
+
+def test_models_3_and_4_vs_oracle(synth, oracle, real_tracks):
+    # VocalTractModel2<double, 3> and VocalTractModel4<double, 1> (the oracle is bit-identical to the reference's models,
+    # tests/test_oracle.py): the five shipped variants and randomised voices, ragged, mixed with model-0 utterances in
+    # one batch (those go to the pipelined kernel); control rates 250 and 500 Hz
+    rng = np.random.Generator(np.random.PCG64(17))
+    base = [default_voice(n) for n in ("male", "female", "large_child", "small_child", "baby")] + [random_voice(rng) for _ in range(5)]
+    voices = [dict(v, tube_model=m) for m in (3, 4, 0) for v in base]
+    tracks = [real_tracks[i % 4][40 * i: 40 * i + int(rng.integers(1, 120))] for i in range(len(voices))]
+    for rate in (250.0, 500.0):
+        outs = synth.synthesize(voices, tracks, voice_index=np.arange(len(voices)), control_rate=rate)
+        for v, tr, out in zip(voices, tracks, outs):
+            ref = oracle.synthesize(v, tr, control_rate=rate)
+            assert len(out) == len(ref)
+            assert full_scale_error(out, ref) <= TIGHT, v["tube_model"]
+
+
+def test_models_3_and_4_are_batch_only(synth):
+    with pytest.raises(g.GttsError) as e:
+        synth.stream(dict(default_voice("male"), tube_model=3))
+    assert e.value.code == g.capi.GTTS_ERR_UNSUPPORTED

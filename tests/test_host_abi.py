@@ -22,12 +22,12 @@ def test_header_symbols_all_exported(product_lib):
     assert declared and set(declared) == set(capi.EXPORTS)
     for name in declared:
         assert hasattr(product_lib, name), name
-    assert product_lib.gtts_abi_version() == 1
+    assert product_lib.gtts_abi_version() == 2
 
 
 def test_voice_struct_layout_matches_header():
-    # 2 int32 + 17 doubles + 5 + 8 doubles
-    assert C.sizeof(capi.VoiceConfig) == 8 + 8 + 8 * (16 + 5 + 8) + 0 or C.sizeof(capi.VoiceConfig) == 8 * (1 + 1 + 16 + 5 + 8)
+    # 2 int32 + 17 doubles + 5 + 8 doubles + 2 int32 (tube_model, reserved)
+    assert C.sizeof(capi.VoiceConfig) == 8 * (1 + 1 + 16 + 5 + 8 + 1)
 
 
 def test_internal_rate_and_steps(product_lib):
@@ -154,3 +154,20 @@ def test_model5_host_entry_points(product_lib, oracle5):
     assert product_lib.gtts5_output_length(C.byref(bad), 250.0, 0, 5, None, None, C.byref(n_out)) == capi.GTTS_ERR_INVALID
     short = capi.voice5_config(dict(default_voice5("male"), vocal_tract_length=5.0))
     assert product_lib.gtts5_output_length(C.byref(short), 250.0, 0, 5, None, None, C.byref(n_out)) == capi.GTTS_ERR_UNSUPPORTED
+
+
+def test_models_3_and_4_host_entry_points(product_lib, oracle):
+    # tube_model 3 / 4 (VocalTractModel2<double, 3>, VocalTractModel4<double, 1>): internal rate (30 delays along the
+    # tract), control steps and output length against the oracle; anything else is refused; a tract too short for the
+    # kernels' converter ring says so
+    for tm in (3, 4):
+        for var, fs in (("male", 60102), ("female", 70119), ("baby", 140239)):
+            v = dict(default_voice(var), tube_model=tm)
+            assert g.internal_rate(v) == fs == int(oracle.internal_rate(v))
+            tr = T.synthetic_track(4, 7)
+            assert g.output_length(v, len(tr))[1] == len(oracle.synthesize(v, tr))
+    n_int, n_out = C.c_int64(), C.c_int64()
+    bad = capi.voice_config(dict(default_voice("male"), tube_model=1))
+    assert product_lib.gtts_output_length(C.byref(bad), 80, 5, C.byref(n_int), C.byref(n_out)) == capi.GTTS_ERR_INVALID
+    short = capi.voice_config(dict(default_voice("male"), tube_model=4, vocal_tract_length=5.0))
+    assert product_lib.gtts_output_length(C.byref(short), 80, 5, C.byref(n_int), C.byref(n_out)) != capi.GTTS_OK
