@@ -315,7 +315,7 @@ def model5_leg(synth, rank, peak):
     try:
         from oracle import pyoracle
         threads = host_threads()
-        n_sample = min(n_utt, threads * 4)
+        n_sample = min(n_utt, threads * 16)
         fo_s = np.arange(n_sample + 1, dtype=np.int64) * n_frames
         sec, n_each, _ = pyoracle.Reference().batch(default_voice5("male"), frames[:n_sample * n_frames], fo_s, n_threads=threads)
         cpu = {"value": float(n_each.sum()) / 48000.0 / sec, "unit": UNIT, "cores": threads, "kind": "reference",
@@ -325,6 +325,43 @@ def model5_leg(synth, rank, peak):
     return {"cpu_baseline": cpu, "workload": "%d model-5 utterances (voice 5_male, fs_int 60411.43 Hz) x %d frames (2 s), one GPU" % (n_utt, n_frames),
             "kernel": "tube5_kernel", "utterances": n_utt, "audio_seconds": audio, "ms": ms, "value": audio / (ms * 1e-3),
             "unit": UNIT, "warmup": 3, "reps": reps, "finite": finite, "roofline_frac": ach / peak, "achieved_tflops": ach}
+
+
+def models34_leg(synth, rank):
+    """Models 3 and 4 (gtts_voice_config::tube_model, general kernel: one warp per utterance) on rank 0: 1,184 utterances
+    x 1 s of the male voice at 60,102 Hz internal rate, device-resident, 2 warm-ups."""
+    import torch
+    import gama_tts_b200 as g
+    from gama_tts_b200 import tracks as T
+    from gama_tts_b200.voices import default_voice
+    if rank != 0:
+        return None
+    out = {}
+    n_utt, n_frames = 1184, 250
+    tracks = [T.synthetic_track(SEED0 + 200000 + (u % 64), n_frames) for u in range(n_utt)]
+    frames, fo = g.pack_tracks(tracks)
+    d_frames = torch.from_numpy(frames).cuda()
+    s = torch.cuda.current_stream()
+    for tm in (3, 4):
+        b = synth.prepare(dict(default_voice("male"), tube_model=tm), fo)
+        d_out = torch.empty(b.n_out_total, dtype=torch.float32, device="cuda")
+        for _ in range(2):
+            b.run_device(d_frames.data_ptr(), d_out.data_ptr(), s.cuda_stream)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(s)
+        for _ in range(2):
+            b.run_device(d_frames.data_ptr(), d_out.data_ptr(), s.cuda_stream)
+        e1.record(s)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 2
+        audio = b.n_samples_total / 48000.0
+        out["model%d" % tm] = {"workload": "%d utterances x %d frames (1 s), voice 0_male/male as model %d" % (n_utt, n_frames, tm),
+                               "kernel": "tube_kernel_v0", "ms": ms, "value": audio / (ms * 1e-3), "unit": UNIT,
+                               "finite": bool(torch.isfinite(d_out[::1009]).all().item())}
+        b.close()
+        del d_out
+    return out
 
 
 def small_configs_leg(synth, rank):
@@ -507,6 +544,7 @@ def main():
     cfg34 = None if args.no_config3 else config34_leg(synth, rank, world, dist, barrier, max_over_ranks, peak, args)
     m5 = None if args.no_model5 else model5_leg(synth, rank, peak)
     small = None if args.no_model5 else small_configs_leg(synth, rank)
+    m34 = None if args.no_model5 else models34_leg(synth, rank)
 
     value = audio_seconds * world / (ms_dev * 1e-3)
     e2e_value = audio_seconds * world / (ms_e2e * 1e-3)
@@ -547,6 +585,8 @@ def main():
             line["model5"] = m5
         if small is not None:
             line.update(small)
+        if m34 is not None:
+            line.update(m34)
         if world == 1 and not args.no_cpu_baseline:
             threads = host_threads()
             n_sample = min(N_UTT, threads * 16)

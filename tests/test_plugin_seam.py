@@ -86,6 +86,20 @@ def test_interactive_call_pattern_through_the_seam(reference, real_tracks, produ
         assert full_scale_error(plugin[:n], builtin[:n]) <= 2e-7
 
 
+@pytest.mark.gpu
+def test_reference_drives_plugin_as_models_3_and_4(reference, real_tracks, product_lib):
+    # plugin_tube_model = 3 | 4 next to model = 2000: the shim stands in for VocalTractModel2<double, 3> /
+    # VocalTractModel4<double, 1> (same configuration keys as model 0)
+    _need_plugin()
+    v = default_voice("male")
+    track = real_tracks[0][:120]
+    for tm in (3, 4):
+        out = reference.synthesize(v, track, model=2000, extra={"dll_path": PLUGIN, "plugin_tube_model": tm})
+        builtin = reference.synthesize(v, track, model=tm)
+        assert len(out) == len(builtin)
+        assert full_scale_error(out, builtin) <= 2e-7
+
+
 STOCK = os.path.join(ROOT, "oracle", "_ref", "gama_tts")
 STOCK_VOICE = os.path.join(ROOT, "oracle", "_ref", "voice_0_male")
 
