@@ -413,3 +413,37 @@ class Oracle5:
         probe = np.zeros(1, np.float32)
         self.lib.oracle5_synthesize(C.byref(vs), 250.0, 0, None, 0, probe.ctypes.data, 0, C.byref(rate))
         return float(rate.value)
+
+
+# ---- control-frame generation (oracle/events_oracle.c) -------------------------------------------------------------
+EVENT_DTYPE = np.dtype([("time", "<i4"), ("has_interp", "<i4"), ("param", "<f8", 16), ("special", "<f8", 16),
+                        ("a", "<f8"), ("b", "<f8"), ("c", "<f8"), ("d", "<f8")])
+EVENT_CONFIG_DTYPE = np.dtype([("control_period", "<i4"), ("macro_intonation", "<i4"), ("micro_intonation", "<i4"),
+                               ("intonation_drift", "<i4"), ("smooth_intonation", "<i4"), ("pad_", "<i4"),
+                               ("initial_pitch", "<f8"), ("mean_pitch", "<f8"), ("drift_deviation2", "<f8"),
+                               ("drift_offset", "<f8"), ("drift_seed", "<f8"), ("drift_b0", "<f8"), ("drift_b1", "<f8"),
+                               ("drift_a1", "<f8"), ("drift_a2", "<f8"), ("drift_x1", "<f8"), ("drift_x2", "<f8"),
+                               ("drift_y1", "<f8"), ("drift_y2", "<f8")])
+
+
+class OracleEvents:
+    """oracle/events_oracle.c through ctypes: event list -> control frames (EventList::generateOutput)."""
+
+    def __init__(self):
+        build(ref=False)
+        L = self.lib = C.CDLL(os.path.join(HERE, "liboracle.so"))
+        L.oracle_events_generate.restype = C.c_long
+        L.oracle_events_generate.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_long]
+
+    def generate(self, cfg, events):
+        """cfg: EVENT_CONFIG_DTYPE scalar (not modified), events: EVENT_DTYPE array -> (frames [F, 16] float32,
+        cfg after the call, i.e. with the drift generator's state advanced)."""
+        cfg = np.array(cfg, dtype=EVENT_CONFIG_DTYPE).reshape(1).copy()
+        ev = np.ascontiguousarray(events, dtype=EVENT_DTYPE)
+        before = cfg.copy()
+        n = self.lib.oracle_events_generate(cfg.ctypes.data, ev.ctypes.data, len(ev), None, 0)
+        frames = np.zeros((max(n, 1), 16), np.float32)
+        cfg = before
+        n2 = self.lib.oracle_events_generate(cfg.ctypes.data, ev.ctypes.data, len(ev), frames.ctypes.data, n)
+        assert n2 == n
+        return frames[:n], cfg[0]
