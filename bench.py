@@ -364,6 +364,96 @@ def models34_leg(synth, rank):
     return out
 
 
+def events_leg(synth, rank):
+    """BASELINE next row 3 on rank 0: control-frame generation on the device (events_kernel: EventList::generateOutput).
+    (a) the event lists of the headline workload's shape (1,024 utterances of about 10 s) alone and chained in front of the
+    synthesis on one stream, (b) a batch that fills the GPU (37,888 chunks of about 2 s), whose algorithmic bytes (296 per
+    event read, 64 per frame written) over its time are set against the measured HBM copy rate.  CPU: the oracle port of
+    generateOutput, one thread, on a sample."""
+    import torch
+    import gama_tts_b200 as g
+    from gama_tts_b200.events import event_config, synthetic_events
+    from gama_tts_b200.voices import default_voice
+    if rank != 0:
+        return None
+    s = torch.cuda.current_stream()
+
+    def timed(fn, warm=3, reps=5):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(s)
+        for _ in range(reps):
+            fn()
+        e1.record(s)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    def batch(n_chunks, n_postures, distinct):
+        base = [synthetic_events(SEED0 + 300000 + k, n_postures) for k in range(distinct)]
+        lists = [base[u % distinct] for u in range(n_chunks)]
+        events, eo = g.pack_events(lists)
+        cfgs = np.array([event_config()] * n_chunks)
+        eb = synth.prepare_events(cfgs, events, eo)
+        return eb, events, cfgs, lists
+
+    out = {}
+    # (a) the headline shape, chained in front of the synthesis
+    eb, events, cfgs, lists = batch(N_UTT, 79, 96)
+    d_events = torch.from_numpy(events.view(np.uint8)).cuda()
+    d_frames = torch.empty(eb.n_frames_total * 16, dtype=torch.float32, device="cuda")
+    tb = synth.prepare(default_voice("male"), eb.frame_offsets)
+    d_out = torch.empty(tb.n_out_total, dtype=torch.float32, device="cuda")
+    ms_ev = timed(lambda: eb.run_device(d_events.data_ptr(), d_frames.data_ptr(), 0, s.cuda_stream))
+    ms_tube = timed(lambda: tb.run_device(d_frames.data_ptr(), d_out.data_ptr(), s.cuda_stream), warm=2, reps=3)
+
+    def chained():
+        eb.run_device(d_events.data_ptr(), d_frames.data_ptr(), 0, s.cuda_stream)
+        tb.run_device(d_frames.data_ptr(), d_out.data_ptr(), s.cuda_stream)
+    ms_both = timed(chained, warm=2, reps=3)
+    audio = tb.n_samples_total / 48000.0
+    out["headline_shape"] = {
+        "workload": "%d utterances, %d events -> %d frames (%.1f s each on average), voice 0_male/male" % (
+            N_UTT, eb.n_events_total, eb.n_frames_total, eb.n_frames_total * 0.004 / N_UTT),
+        "events_kernel_ms": ms_ev, "synthesis_ms": ms_tube, "events_then_synthesis_ms": ms_both,
+        "value": audio / (ms_both * 1e-3), "unit": UNIT, "finite": bool(torch.isfinite(d_out[::1009]).all().item()),
+        "h2d_bytes_events": int(events.nbytes), "h2d_bytes_frames_avoided": int(eb.n_frames_total * 64)}
+    # CPU: the oracle port on a sample of the same lists
+    try:
+        from oracle.pyoracle import OracleEvents
+        o = OracleEvents()
+        t0 = time.perf_counter()
+        n = 0
+        for k in range(96):
+            n += len(o.generate(cfgs[k], lists[k])[0])
+        sec = (time.perf_counter() - t0) / 2      # generate() runs the list twice (count, then fill)
+        out["cpu_baseline"] = {"value": n / sec, "unit": "frames/s", "cores": 1, "kind": "port", "sample": "96 lists, %.3f s" % sec}
+    except Exception as e:
+        out["cpu_baseline"] = {"unavailable": str(e)[:120]}
+    tb.close()
+    eb.close()
+    del d_out, d_frames, d_events
+    # (b) a batch that fills the GPU
+    eb, events, cfgs, lists = batch(37888, 16, 128)
+    d_events = torch.from_numpy(events.view(np.uint8)).cuda()
+    d_frames = torch.empty(eb.n_frames_total * 16, dtype=torch.float32, device="cuda")
+    ms = timed(lambda: eb.run_device(d_events.data_ptr(), d_frames.data_ptr(), 0, s.cuda_stream))
+    nbytes = events.nbytes + eb.n_frames_total * 64
+    try:
+        hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        src = "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        hbm, src = 6550.0, "fallback of B200_PROFILING.md"
+    gbs = nbytes / (ms * 1e-3) * 1e-9
+    out["full_gpu"] = {"workload": "%d chunks, %d events -> %d frames" % (37888, eb.n_events_total, eb.n_frames_total),
+                       "ms": ms, "value": eb.n_frames_total / (ms * 1e-3), "unit": "frames/s",
+                       "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+                                    "peak_source": src, "bytes_per_launch_algorithmic": int(nbytes)}}
+    eb.close()
+    return out
+
+
 def small_configs_leg(synth, rank):
     """BASELINE configs 1 and 5 on rank 0, so that the driver's run carries them: config 1 = ONE real sentence
     ("Hello world.", 332 control frames captured from the reference's front end, tests/golden/real_tracks.npz) through
@@ -545,6 +635,7 @@ def main():
     m5 = None if args.no_model5 else model5_leg(synth, rank, peak)
     small = None if args.no_model5 else small_configs_leg(synth, rank)
     m34 = None if args.no_model5 else models34_leg(synth, rank)
+    evl = None if args.no_model5 else events_leg(synth, rank)
 
     value = audio_seconds * world / (ms_dev * 1e-3)
     e2e_value = audio_seconds * world / (ms_e2e * 1e-3)
@@ -587,6 +678,8 @@ def main():
             line.update(small)
         if m34 is not None:
             line.update(m34)
+        if evl is not None:
+            line["control_frames"] = evl
         if world == 1 and not args.no_cpu_baseline:
             threads = host_threads()
             n_sample = min(N_UTT, threads * 16)

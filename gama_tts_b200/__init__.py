@@ -316,9 +316,94 @@ class TubeSynthesizer:
         finally:
             b.close()
 
+    # ---- control-frame generation (gtts_events_*: EventList::generateOutput) ----
+    def prepare_events(self, configs, events, event_offsets, continues_previous=None):
+        return EventsBatch(self, configs, events, event_offsets, continues_previous)
+
+    def control_frames(self, configs, event_lists, continues_previous=None):
+        """One config record (capi.EVENT_CONFIG_DTYPE) and one event array (capi.EVENT_DTYPE) per chunk ->
+        list of float32 [frames, 16] control tracks, one per chunk (EventList::generateOutput on the device)."""
+        events, eo = pack_events(event_lists)
+        b = self.prepare_events(configs, events, eo, continues_previous)
+        try:
+            frames, _ = b.run_host(events)
+            return [frames[b.frame_offsets[c]:b.frame_offsets[c + 1]].copy() for c in range(b.n_chunks)]
+        finally:
+            b.close()
+
     def close(self):
         if self._h:
             self._lib.gtts_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def pack_events(event_lists):
+    """list of capi.EVENT_DTYPE arrays -> (packed events, event_offsets[n + 1])."""
+    lists = [np.ascontiguousarray(e, capi.EVENT_DTYPE).reshape(-1) for e in event_lists]
+    eo = np.zeros(len(lists) + 1, np.int64)
+    if lists:
+        eo[1:] = np.cumsum([len(e) for e in lists])
+    events = np.concatenate(lists) if lists else np.zeros(0, capi.EVENT_DTYPE)
+    return np.ascontiguousarray(events), eo
+
+
+def events_frame_count(config, events):
+    """Frames EventList::generateOutput makes of an event list (host arithmetic on the times)."""
+    cfg = np.array(config, capi.EVENT_CONFIG_DTYPE).reshape(1)
+    ev = np.ascontiguousarray(events, capi.EVENT_DTYPE).reshape(-1)
+    n = C.c_int64()
+    check(load().gtts_events_frame_count(cfg.ctypes.data, ev.ctypes.data, len(ev), C.byref(n)))
+    return int(n.value)
+
+
+class EventsBatch:
+    """gtts_events_batch: a prepared batch of chunks (event lists) whose control frames are generated on the device."""
+
+    def __init__(self, synth, configs, events, event_offsets, continues_previous=None):
+        self._lib = synth._lib
+        self._synth = synth
+        cfgs = np.ascontiguousarray(configs, capi.EVENT_CONFIG_DTYPE).reshape(-1)
+        ev = np.ascontiguousarray(events, capi.EVENT_DTYPE).reshape(-1)
+        eo = np.ascontiguousarray(event_offsets, np.int64)
+        self.n_chunks = len(eo) - 1
+        assert len(cfgs) == self.n_chunks
+        cp = None if continues_previous is None else np.ascontiguousarray(continues_previous, np.int32)
+        self._h = C.c_void_p()
+        check(self._lib.gtts_events_prepare(synth._h, cfgs.ctypes.data, None if cp is None else cp.ctypes.data, ev.ctypes.data,
+                                            eo.ctypes.data, self.n_chunks, C.byref(self._h)))
+        self.event_offsets = eo
+        self.frame_offsets = np.zeros(self.n_chunks + 1, np.int64)
+        check(self._lib.gtts_events_layout(self._h, self.frame_offsets.ctypes.data))
+        self.n_frames_total = int(self.frame_offsets[-1])
+        self.n_events_total = int(eo[-1]) if len(eo) else 0
+        first = np.ones(self.n_chunks, bool) if cp is None else (cp == 0)
+        if self.n_chunks:
+            first[0] = True
+        # frame_offsets of the utterances (chains of chunks): the frame_offsets argument of gtts_batch_prepare
+        self.utterance_frame_offsets = np.concatenate([self.frame_offsets[:-1][first], self.frame_offsets[-1:]])
+
+    def run_host(self, events):
+        """-> (frames [n_frames_total, 16] float32, configs with the drift state each chunk left)."""
+        ev = np.ascontiguousarray(events, capi.EVENT_DTYPE).reshape(-1)
+        assert len(ev) == self.n_events_total
+        frames = np.zeros((max(self.n_frames_total, 1), NUM_PARAMS), np.float32)
+        cfg_out = np.zeros(max(self.n_chunks, 1), capi.EVENT_CONFIG_DTYPE)
+        check(self._lib.gtts_events_run_host(self._h, ev.ctypes.data, frames.ctypes.data, cfg_out.ctypes.data))
+        return frames[:self.n_frames_total], cfg_out[:self.n_chunks]
+
+    def run_device(self, d_events_ptr, d_frames_ptr, d_configs_out_ptr=0, stream_ptr=0):
+        check(self._lib.gtts_events_run_device(self._h, C.c_void_p(d_events_ptr), C.c_void_p(d_frames_ptr),
+                                               C.c_void_p(d_configs_out_ptr), C.c_void_p(stream_ptr)))
+
+    def close(self):
+        if self._h:
+            self._lib.gtts_events_free(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):

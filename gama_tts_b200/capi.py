@@ -5,6 +5,8 @@ Python is test / benchmark orchestration only; the product is the C-ABI library
 the library is missing -- there is no Python or CPU implementation to fall back to.
 """
 import ctypes as C
+
+import numpy as np
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -93,6 +95,17 @@ def voice_array(voices):
     return arr
 
 
+# struct gtts_event / gtts_event_config (include/gtts_b200.h) as numpy record types
+EVENT_DTYPE = np.dtype([("time", "<i4"), ("has_interp", "<i4"), ("param", "<f8", 16), ("special", "<f8", 16),
+                        ("a", "<f8"), ("b", "<f8"), ("c", "<f8"), ("d", "<f8")])
+EVENT_CONFIG_DTYPE = np.dtype([("control_period", "<i4"), ("macro_intonation", "<i4"), ("micro_intonation", "<i4"),
+                               ("intonation_drift", "<i4"), ("smooth_intonation", "<i4"), ("reserved", "<i4"),
+                               ("initial_pitch", "<f8"), ("mean_pitch", "<f8"), ("drift_deviation2", "<f8"),
+                               ("drift_offset", "<f8"), ("drift_seed", "<f8"), ("drift_b0", "<f8"), ("drift_b1", "<f8"),
+                               ("drift_a1", "<f8"), ("drift_a2", "<f8"), ("drift_x1", "<f8"), ("drift_x2", "<f8"),
+                               ("drift_y1", "<f8"), ("drift_y2", "<f8")])
+assert EVENT_DTYPE.itemsize == 296 and EVENT_CONFIG_DTYPE.itemsize == 128
+
 EXPORTS = [
     "gtts_last_error", "gtts_abi_version", "gtts_voice_internal_rate", "gtts_voice_control_steps",
     "gtts_output_length", "gtts_shard_plan", "gtts_probe_fir_taps", "gtts_probe_src_tables",
@@ -105,6 +118,8 @@ EXPORTS = [
     "gtts_stream_finish", "gtts_stream_reset", "gtts_stream_close",
     "gtts5_voice_internal_rate", "gtts5_output_length", "gtts5_batch_prepare", "gtts5_batch_layout", "gtts5_batch_run_device",
     "gtts5_batch_run_host", "gtts5_batch_run_device_pcm16", "gtts5_batch_run_host_pcm16", "gtts5_batch_free",
+    "gtts_events_drift_setup", "gtts_events_frame_count", "gtts_events_prepare", "gtts_events_layout", "gtts_events_run_device", "gtts_events_run_host",
+    "gtts_events_free",
 ]
 
 _lib = None
@@ -177,6 +192,14 @@ def load():
     L.gtts5_batch_run_host_pcm16.argtypes = [vp, vp, vp, vp]
     L.gtts5_batch_free.argtypes = [vp]
     L.gtts5_batch_free.restype = None
+    L.gtts_events_drift_setup.argtypes = [dbl, dbl, dbl, vp]
+    L.gtts_events_frame_count.argtypes = [vp, vp, i64, C.POINTER(i64)]
+    L.gtts_events_prepare.argtypes = [vp, vp, vp, vp, vp, i64, C.POINTER(vp)]
+    L.gtts_events_layout.argtypes = [vp, vp]
+    L.gtts_events_run_device.argtypes = [vp, vp, vp, vp, vp]
+    L.gtts_events_run_host.argtypes = [vp, vp, vp, vp]
+    L.gtts_events_free.argtypes = [vp]
+    L.gtts_events_free.restype = None
     _lib = L
     return L
 

@@ -27,6 +27,7 @@
 #include "tube_kernel_v3.cuh"
 #include "tube5_kernel.cuh"
 #include "model5_host.h"
+#include "events_kernel.cuh"
 
 using namespace gtts;
 
@@ -1615,6 +1616,148 @@ int gtts5_batch_run_host_pcm16(gtts5_batch* b, const float* h_frames, int16_t* h
 	if (nOut > 0) GTTS_CUDA(cudaMemcpyAsync(h_pcm, b->d_pcm, sizeof(short) * nOut, cudaMemcpyDeviceToHost, b->stream));
 	if (h_scale) GTTS_CUDA(cudaMemcpyAsync(h_scale, b->d_scale, sizeof(float) * nUtt, cudaMemcpyDeviceToHost, b->stream));
 	GTTS_CUDA(cudaStreamSynchronize(b->stream));
+	return GTTS_OK;
+}
+
+// ---- control-frame generation on the device (events_kernel.cuh) ---------------------------------------------------
+
+struct gtts_events_batch {
+	gtts_handle* h = nullptr;
+	evt::EventsPlan plan;
+	gtts_event_config* d_cfgs = nullptr;
+	gtts_event_config* d_cfgs_out = nullptr;   // run_host
+	evt::ChunkDesc* d_chunks = nullptr;
+	evt::ChainDesc* d_chains = nullptr;
+	int32_t* d_order = nullptr;
+	int32_t* d_queue = nullptr;
+	gtts_event* d_events = nullptr;            // run_host staging
+	float* d_frames = nullptr;
+	cudaStream_t stream = nullptr;
+};
+
+void gtts_events_free(gtts_events_batch* b)
+{
+	if (!b) return;
+	cudaSetDevice(b->h->device);
+	cudaFree(b->d_cfgs); cudaFree(b->d_cfgs_out); cudaFree(b->d_chunks); cudaFree(b->d_chains); cudaFree(b->d_order);
+	cudaFree(b->d_queue); cudaFree(b->d_events); cudaFree(b->d_frames);
+	if (b->stream) cudaStreamDestroy(b->stream);
+	delete b;
+}
+
+int gtts_events_drift_setup(double deviation, double sample_rate, double lowpass_cutoff, gtts_event_config* config)
+{
+	if (!config) return fail(GTTS_ERR_INVALID, "null config");
+	if (!evt::driftSetup(deviation, sample_rate, lowpass_cutoff, *config))
+		return fail(GTTS_ERR_INVALID, "drift low-pass cutoff must lie between 1 Hz and 0.48 of the control rate");
+	return GTTS_OK;
+}
+
+int gtts_events_frame_count(const gtts_event_config* config, const gtts_event* events, int64_t n_events, int64_t* n_frames_out)
+{
+	if (!config || !n_frames_out || (n_events > 0 && !events) || n_events < 0) return fail(GTTS_ERR_INVALID, "null argument");
+	if (config->control_period <= 0) return fail(GTTS_ERR_INVALID, "control_period must be positive");
+	*n_frames_out = evt::countFrames(config->control_period, events, n_events);
+	return GTTS_OK;
+}
+
+static int prepareEvents(gtts_events_batch* b)
+{
+	const evt::EventsPlan& p = b->plan;
+	GTTS_CUDA(cudaSetDevice(b->h->device));
+	GTTS_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+	const size_t nChunks = p.chunks.size(), nChains = p.chains.size();
+	GTTS_CUDA(cudaMalloc(&b->d_cfgs, sizeof(gtts_event_config) * std::max<size_t>(nChunks, 1)));
+	GTTS_CUDA(cudaMalloc(&b->d_chunks, sizeof(evt::ChunkDesc) * std::max<size_t>(nChunks, 1)));
+	GTTS_CUDA(cudaMalloc(&b->d_chains, sizeof(evt::ChainDesc) * std::max<size_t>(nChains, 1)));
+	GTTS_CUDA(cudaMalloc(&b->d_order, sizeof(int32_t) * std::max<size_t>(nChains, 1)));
+	GTTS_CUDA(cudaMalloc(&b->d_queue, 2 * sizeof(int32_t)));
+	if (nChunks > 0) {
+		GTTS_CUDA(cudaMemcpyAsync(b->d_cfgs, p.cfgs.data(), sizeof(gtts_event_config) * nChunks, cudaMemcpyHostToDevice, b->stream));
+		GTTS_CUDA(cudaMemcpyAsync(b->d_chunks, p.chunks.data(), sizeof(evt::ChunkDesc) * nChunks, cudaMemcpyHostToDevice, b->stream));
+		GTTS_CUDA(cudaMemcpyAsync(b->d_chains, p.chains.data(), sizeof(evt::ChainDesc) * nChains, cudaMemcpyHostToDevice, b->stream));
+		GTTS_CUDA(cudaMemcpyAsync(b->d_order, p.order.data(), sizeof(int32_t) * nChains, cudaMemcpyHostToDevice, b->stream));
+	}
+	GTTS_CUDA(cudaStreamSynchronize(b->stream));
+	return GTTS_OK;
+}
+
+int gtts_events_prepare(gtts_handle* h, const gtts_event_config* configs, const int32_t* continues_previous,
+			const gtts_event* events, const int64_t* event_offsets, int64_t n_chunks, gtts_events_batch** batch_out)
+{
+	if (!h || !batch_out) return fail(GTTS_ERR_INVALID, "null handle / output pointer");
+	*batch_out = nullptr;
+	try {
+		gtts_events_batch* b = new gtts_events_batch;
+		b->h = h;
+		int err = GTTS_OK;
+		const std::string text = evt::planEvents(configs, continues_previous, events, event_offsets, n_chunks, b->plan, &err);
+		if (err != GTTS_OK) { delete b; return fail(err, text); }
+		const int rc = prepareEvents(b);
+		if (rc != GTTS_OK) { gtts_events_free(b); return rc; }
+		*batch_out = b;
+		return GTTS_OK;
+	} catch (const std::exception& e) {
+		return fail(GTTS_ERR_NOMEM, e.what());
+	}
+}
+
+int gtts_events_layout(const gtts_events_batch* b, int64_t* frame_offsets)
+{
+	if (!b || !frame_offsets) return fail(GTTS_ERR_INVALID, "null argument");
+	std::copy(b->plan.frame_offsets.begin(), b->plan.frame_offsets.end(), frame_offsets);
+	return GTTS_OK;
+}
+
+int gtts_events_run_device(gtts_events_batch* b, const gtts_event* d_events, float* d_frames, gtts_event_config* d_configs_out,
+			void* cuda_stream)
+{
+	if (!b) return fail(GTTS_ERR_INVALID, "null batch");
+	const int nChains = static_cast<int>(b->plan.chains.size());
+	if (nChains == 0) return GTTS_OK;
+	if ((b->plan.n_events_total > 0 && !d_events) || (b->plan.frame_offsets.back() > 0 && !d_frames))
+		return fail(GTTS_ERR_INVALID, "null device buffer");
+	cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+	GTTS_CUDA(cudaSetDevice(b->h->device));
+	GTTS_CUDA(cudaMemsetAsync(b->d_queue, 0, 2 * sizeof(int32_t), stream));
+	evt::EventsParams P;
+	P.events = reinterpret_cast<const double*>(d_events);
+	P.cfgs = b->d_cfgs;
+	P.cfgs_out = d_configs_out;
+	P.chunks = b->d_chunks;
+	P.chains = b->d_chains;
+	P.order = b->d_order;
+	P.frames = d_frames;
+	P.queue = b->d_queue;
+	P.n_chains = nChains;
+	// one warp per utterance; CTAs up to eight per SM, a whole number of waves when the batch is that large
+	const int ctasWanted = (nChains + evt::kEventsWarps - 1) / evt::kEventsWarps;
+	const int grid = std::min(ctasWanted, b->h->sms * 8);
+	evt::events_kernel<<<grid, evt::kEventsWarps * 32, 0, stream>>>(P);
+	GTTS_CUDA(cudaGetLastError());
+	return GTTS_OK;
+}
+
+int gtts_events_run_host(gtts_events_batch* b, const gtts_event* h_events, float* h_frames, gtts_event_config* configs_out)
+{
+	if (!b) return fail(GTTS_ERR_INVALID, "null batch");
+	const int64_t nEvents = b->plan.n_events_total, nFrames = b->plan.frame_offsets.empty() ? 0 : b->plan.frame_offsets.back();
+	const size_t nChunks = b->plan.chunks.size();
+	if ((nEvents > 0 && !h_events) || (nFrames > 0 && !h_frames)) return fail(GTTS_ERR_INVALID, "null host buffer");
+	if (nChunks == 0) return GTTS_OK;
+	GTTS_CUDA(cudaSetDevice(b->h->device));
+	if (!b->d_events && nEvents > 0) GTTS_CUDA(cudaMalloc(&b->d_events, sizeof(gtts_event) * nEvents));
+	if (!b->d_frames && nFrames > 0) GTTS_CUDA(cudaMalloc(&b->d_frames, sizeof(float) * kNumParams * nFrames));
+	if (!b->d_cfgs_out) GTTS_CUDA(cudaMalloc(&b->d_cfgs_out, sizeof(gtts_event_config) * nChunks));
+	if (nEvents > 0) GTTS_CUDA(cudaMemcpyAsync(b->d_events, h_events, sizeof(gtts_event) * nEvents, cudaMemcpyHostToDevice, b->stream));
+	const int rc = gtts_events_run_device(b, b->d_events, b->d_frames, b->d_cfgs_out, b->stream);
+	if (rc != GTTS_OK) return rc;
+	int32_t flags[2] = {0, 0};
+	GTTS_CUDA(cudaMemcpyAsync(flags, b->d_queue, sizeof flags, cudaMemcpyDeviceToHost, b->stream));
+	if (nFrames > 0) GTTS_CUDA(cudaMemcpyAsync(h_frames, b->d_frames, sizeof(float) * kNumParams * nFrames, cudaMemcpyDeviceToHost, b->stream));
+	if (configs_out) GTTS_CUDA(cudaMemcpyAsync(configs_out, b->d_cfgs_out, sizeof(gtts_event_config) * nChunks, cudaMemcpyDeviceToHost, b->stream));
+	GTTS_CUDA(cudaStreamSynchronize(b->stream));
+	if (flags[1]) return fail(GTTS_ERR_CUDA, "control-frame kernel: a chunk produced a frame count other than planned");
 	return GTTS_OK;
 }
 

@@ -282,6 +282,65 @@ int gtts5_batch_run_device_pcm16(gtts5_batch* batch, const float* d_frames, floa
 int gtts5_batch_run_host_pcm16(gtts5_batch* batch, const float* h_frames, int16_t* h_pcm, float* h_scale);
 void gtts5_batch_free(gtts5_batch* batch);
 
+/* ---- control-frame generation on the device (BASELINE next row 3) -------------------------------------------------
+ * From the event list of a chunk of an utterance to its control frames -- the float32 [frame][16] array every batch
+ * call above takes -- in device memory, so that the frames never cross PCIe:
+ *     EventList::generateOutput      gama_tts/src/vtm_control_model/EventList.cpp:929-1091
+ *     DriftGenerator::drift          gama_tts/src/vtm_control_model/DriftGenerator.cpp:72-84 (its low-pass:
+ *                                    gama_tts/src/vtm/Butterworth2LowpassFilter.h:104-113)
+ * What stays on the host is what builds the event list (text parser, rule engine, EventList::generateEventList and
+ * applyIntonation): the binding copies EventList::list_ into gtts_event records.  Output: bit-identical
+ * to the reference's frames (float32), IEEE double arithmetic in its order of evaluation without FMA contraction. */
+typedef struct gtts_event {             /* Event, gama_tts/src/vtm_control_model/EventList.h:113-161 */
+	int32_t time;                       /* ms from the start of the chunk */
+	int32_t has_interp;                 /* interpData present (macro-intonation polynomial of the segment that starts here) */
+	double param[16];                   /* parameters; +infinity = Event::EMPTY_PARAMETER */
+	double special[16];                 /* specialParameters, same convention */
+	double a, b, c, d;                  /* interpData->a .. d */
+} gtts_event;
+
+typedef struct gtts_event_config {      /* what generateOutput reads besides the events */
+	int32_t control_period;             /* ms (vtm_control_model.txt: control_period) */
+	int32_t macro_intonation, micro_intonation, intonation_drift, smooth_intonation;   /* EventList.h:182-192 */
+	int32_t reserved;
+	double initial_pitch, mean_pitch;   /* EventList::setInitialPitch / setMeanPitch */
+	double drift_deviation2, drift_offset;   /* DriftGenerator::setUp: 2 deviation, deviation */
+	double drift_seed;                  /* the generator's state: the chaotic seed ... */
+	double drift_b0, drift_b1, drift_a1, drift_a2;   /* ... its Butterworth-2 low-pass (Butterworth2LowpassFilter::update) ... */
+	double drift_x1, drift_x2, drift_y1, drift_y2;   /* ... and the filter's history */
+} gtts_event_config;
+
+typedef struct gtts_events_batch gtts_events_batch;
+
+/* Fills the drift_* members of *config as a fresh generator has them: DriftGenerator::DriftGenerator + setUp(deviation,
+ * sample_rate, lowpass_cutoff) (DriftGenerator.cpp:23-34, 55-63; Butterworth2LowPassFilter::update,
+ * Butterworth2LowpassFilter.h:80-100) -- called by EventList::setUpDriftGenerator with drift_deviation, the control rate and
+ * drift_lowpass_cutoff of vtm_control_model.txt (Controller.cpp:73).  The cutoff must lie in [1, 0.48 sample_rate]. */
+int gtts_events_drift_setup(double deviation, double sample_rate, double lowpass_cutoff, gtts_event_config* config);
+/* Frames generateOutput makes of an event list (host arithmetic on the event times only; 0 for fewer than 2 events). */
+int gtts_events_frame_count(const gtts_event_config* config, const gtts_event* events, int64_t n_events, int64_t* n_frames_out);
+/* Plans a batch of n_chunks chunks.
+ *   configs[n_chunks]            one per chunk
+ *   continues_previous[n_chunks] NULL, or nonzero where chunk c is the next chunk of the utterance of chunk c - 1: its drift
+ *                                generator goes on from the state chunk c - 1 left (the drift_* state in configs[c] is
+ *                                ignored), as Controller::getParametersFromPhoneticString does (Controller.cpp:119-156)
+ *   events, event_offsets        chunk c owns events [event_offsets[c], event_offsets[c + 1]) of the packed host array;
+ *                                only the times are read here (the frame layout follows from them)
+ * All arrays are host memory and are copied. */
+int gtts_events_prepare(gtts_handle* handle, const gtts_event_config* configs, const int32_t* continues_previous,
+			const gtts_event* events, const int64_t* event_offsets, int64_t n_chunks, gtts_events_batch** batch_out);
+/* frame_offsets[n_chunks + 1]: chunk c produces frames [frame_offsets[c], frame_offsets[c + 1]) of the packed frame array --
+ * with the entries of the utterances' first chunks, the frame_offsets argument of gtts_batch_prepare. */
+int gtts_events_layout(const gtts_events_batch* batch, int64_t* frame_offsets);
+/* Device buffers, asynchronous on cuda_stream: d_events gtts_event [event_offsets[n_chunks]] (8-byte aligned),
+ * d_frames float32 [frame_offsets[n_chunks]][16]; d_configs_out NULL or gtts_event_config [n_chunks] receiving the configs with
+ * the drift generator's state as each chunk left it.  A following gtts_batch_run_device on the same stream reads d_frames. */
+int gtts_events_run_device(gtts_events_batch* batch, const gtts_event* d_events, float* d_frames,
+			gtts_event_config* d_configs_out, void* cuda_stream);
+/* Host buffers (staged), synchronised on return; configs_out may be NULL. */
+int gtts_events_run_host(gtts_events_batch* batch, const gtts_event* h_events, float* h_frames, gtts_event_config* configs_out);
+void gtts_events_free(gtts_events_batch* batch);
+
 #ifdef __cplusplus
 }
 #endif

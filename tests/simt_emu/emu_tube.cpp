@@ -364,3 +364,33 @@ extern "C" int emu_batch_m5(const gtts_voice5_config* voices, int n_voices, cons
 	simt::run_cta(nthreads, [&](int tid) { m5::tube5_cta_body(P, base, tid, nthreads); });
 	return 0;
 }
+
+// ---- control-frame generation (events_kernel.cuh: one warp per utterance) -------------------------------------------
+#include "../../gama_tts_b200/csrc/events_kernel.cuh"
+
+extern "C" int emu_events(const gtts_event_config* configs, const int* continues_previous, const gtts_event* events,
+			const long long* event_offsets, long long n_chunks, float* frames, long long* frame_offsets,
+			gtts_event_config* configs_out, int warps_per_cta)
+{
+	using namespace gtts;
+	evt::EventsPlan plan;
+	int err = 0;
+	g_err = evt::planEvents(configs, continues_previous, events, reinterpret_cast<const int64_t*>(event_offsets), n_chunks, plan, &err);
+	if (err) return err;
+	for (long long c = 0; c <= n_chunks; ++c) frame_offsets[c] = plan.frame_offsets[c];
+	if (!frames) return 0;
+	int queue[2] = {0, 0};
+	evt::EventsParams P;
+	P.events = reinterpret_cast<const double*>(events);
+	P.cfgs = plan.cfgs.data();
+	P.cfgs_out = configs_out;
+	P.chunks = plan.chunks.data();
+	P.chains = plan.chains.data();
+	P.order = plan.order.data();
+	P.frames = frames;
+	P.queue = queue;
+	P.n_chains = static_cast<int32_t>(plan.chains.size());
+	simt::run_cta(warps_per_cta * 32, [&](int tid) { evt::events_cta_body(P, tid); });
+	if (queue[1]) { g_err = "frame count mismatch"; return GTTS_ERR_CUDA; }
+	return 0;
+}

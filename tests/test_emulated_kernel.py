@@ -311,3 +311,89 @@ def test_emulated_general_kernel_models_3_and_4(emu, oracle, real_tracks):
         assert full_scale_error(out, ref) <= 1e-9
         if v["glottal_pulse_tn_min"] == v["glottal_pulse_tn_max"]:
             assert np.array_equal(out, ref)
+
+
+# ---- control-frame generation (events_kernel.cuh) ----------------------------------------------------------------------
+
+@pytest.fixture(scope="module")
+def emu_events(emu):
+    from gama_tts_b200 import capi
+    L = C.CDLL(os.path.join(HERE, "simt_emu", "libemu_tube.so"))
+    L.emu_last_error.restype = C.c_char_p
+    L.emu_events.argtypes = [C.c_void_p] * 8 + [C.c_int]
+
+    def run(cfgs, event_lists, continues=None, warps=3):
+        cfgs = np.ascontiguousarray(cfgs, capi.EVENT_CONFIG_DTYPE).reshape(-1)
+        ev, eo = g_pack_events(event_lists)
+        cp = None if continues is None else np.ascontiguousarray(continues, np.int32)
+        fo = np.zeros(len(event_lists) + 1, np.int64)
+        args = [cfgs.ctypes.data, None if cp is None else cp.ctypes.data, ev.ctypes.data, eo.ctypes.data, len(event_lists)]
+        assert L.emu_events(*args, None, fo.ctypes.data, None, warps) == 0, L.emu_last_error()
+        frames = np.zeros((max(int(fo[-1]), 1), 16), np.float32)
+        out = np.zeros(max(len(event_lists), 1), capi.EVENT_CONFIG_DTYPE)
+        assert L.emu_events(*args, frames.ctypes.data, fo.ctypes.data, out.ctypes.data, warps) == 0, L.emu_last_error()
+        return [frames[fo[c]:fo[c + 1]] for c in range(len(event_lists))], out[:len(event_lists)]
+    return run
+
+
+def g_pack_events(event_lists):
+    from gama_tts_b200 import pack_events
+    return pack_events(event_lists)
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def test_emulated_events_kernel_reference_fixtures(emu_events):
+    # the frames the unmodified reference front end produced (tests/golden/events_v1.npz), the two-chunk utterances as
+    # chains (the second chunk's own drift state is wiped: it must come from the first chunk): bit for bit
+    from gama_tts_b200 import capi
+    z = np.load(os.path.join(HERE, "golden", "events_v1.npz"))
+    names = [str(n) for n in z["names"]]
+    cfgs = np.array([z["cfg_" + n] for n in names]).astype(capi.EVENT_CONFIG_DTYPE)
+    cont = np.array([n.endswith("_1") for n in names], np.int32)
+    for k in ("drift_seed", "drift_x1", "drift_x2", "drift_y1", "drift_y2"):
+        cfgs[k][cont == 1] = 0.0
+    frames, out = emu_events(cfgs, [z["ev_" + n] for n in names], cont)
+    for i, n in enumerate(names):
+        assert frames[i].shape == z["frames_" + n].shape, n
+        assert np.array_equal(_bits(frames[i]), _bits(z["frames_" + n])), n
+    # the state a first chunk leaves is the state the reference's second chunk started from
+    i = names.index("shells_0")
+    for k in ("drift_seed", "drift_x1", "drift_x2", "drift_y1", "drift_y2"):
+        assert out[k][i] == z["cfg_shells_1"][k], k
+
+
+def test_emulated_events_kernel_synthetic_lists_vs_oracle(emu_events):
+    # synthetic lists: every flag combination, control periods 1 / 4 / 10 ms, events closer than a period or at equal
+    # times, special parameters, lists of 0 / 1 / 2 events, a three-chunk utterance
+    from gama_tts_b200.events import event_config, synthetic_events
+    from oracle.pyoracle import OracleEvents
+    o = OracleEvents()
+    cfgs, lists, cont = [], [], []
+    for seed in range(16):
+        cfgs.append(event_config(control_period=(4, 1, 10)[seed % 3], macro=seed & 1, micro=(seed >> 1) & 1,
+                                 drift=(seed >> 2) & 1, smooth=(seed >> 3) & 1))
+        lists.append(synthetic_events(100 + seed, 2 + seed % 7, special_rate=0.05, tight=seed % 2 == 0))
+        cont.append(0)
+    for n in (0, 1, 2):
+        cfgs.append(event_config())
+        lists.append(synthetic_events(7, 3)[:n])
+        cont.append(0)
+    for k in range(3):
+        cfgs.append(event_config())
+        lists.append(synthetic_events(200 + k, 5))
+        cont.append(int(k > 0))
+    frames, out = emu_events(np.array(cfgs), lists, cont)
+    carried = None
+    for i, (c, ev) in enumerate(zip(cfgs, lists)):
+        if cont[i]:
+            c = c.copy()
+            for k in ("drift_seed", "drift_x1", "drift_x2", "drift_y1", "drift_y2"):
+                c[k] = carried[k]
+        want, carried = o.generate(c, ev)
+        assert frames[i].shape == want.shape, i
+        assert np.array_equal(_bits(frames[i]), _bits(want)), i
+        for k in ("drift_seed", "drift_y1"):
+            assert out[k][i] == carried[k], (i, k)

@@ -550,3 +550,123 @@ def test_models_3_and_4_are_batch_only(synth):
     with pytest.raises(g.GttsError) as e:
         synth.stream(dict(default_voice("male"), tube_model=3))
     assert e.value.code == g.capi.GTTS_ERR_UNSUPPORTED
+
+
+# ---- control-frame generation on the device (gtts_events_*, events_kernel.cuh) -----------------------------------------
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def test_events_reference_fixtures_bit_exact(synth):
+    # the frames the unmodified reference front end produced from its own event lists (tests/golden/events_v1.npz),
+    # two-chunk utterances as chains whose second chunk takes the drift state the first one left
+    import os
+    from gama_tts_b200 import capi
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "events_v1.npz"))
+    names = [str(n) for n in z["names"]]
+    cfgs = np.array([z["cfg_" + n] for n in names]).astype(capi.EVENT_CONFIG_DTYPE)
+    cont = np.array([n.endswith("_1") for n in names], np.int32)
+    for k in ("drift_seed", "drift_x1", "drift_x2", "drift_y1", "drift_y2"):
+        cfgs[k][cont == 1] = 0.0
+    frames = synth.control_frames(cfgs, [z["ev_" + n] for n in names], cont)
+    for i, n in enumerate(names):
+        assert frames[i].shape == z["frames_" + n].shape, n
+        assert np.array_equal(_bits(frames[i]), _bits(z["frames_" + n])), n
+
+
+def test_events_ragged_batch_vs_oracle(synth):
+    # 3,000 chunks (more than the resident warps of the GPU: the queue is exercised), every flag combination, control
+    # periods 1 / 4 / 10 ms, events closer than a period, lists of 0 / 1 / 2 events, chains of up to three chunks;
+    # 300 of them and every chain checked bit for bit against the oracle, the drift state a chunk leaves included
+    from gama_tts_b200.events import event_config, synthetic_events
+    from oracle.pyoracle import OracleEvents
+    o = OracleEvents()
+    rng = np.random.Generator(np.random.PCG64(11))
+    cfgs, lists, cont = [], [], []
+    for i in range(3000):
+        seed = int(rng.integers(0, 1 << 30))
+        cfgs.append(event_config(control_period=(4, 4, 1, 10)[i % 4], macro=i & 1, micro=(i >> 1) & 1, drift=(i >> 2) & 1,
+                                 smooth=(i >> 3) & 1))
+        n_post = int(rng.integers(1, 40))
+        ev = synthetic_events(seed, n_post, special_rate=0.03, tight=i % 5 == 0)
+        if i % 97 == 0:
+            ev = ev[:i // 97 % 3]
+        lists.append(ev)
+        cont.append(int(i % 7 in (5, 6) and i > 0))
+    frames_list = synth.control_frames(np.array(cfgs), lists, cont)
+    events, eo = g.pack_events(lists)
+    b = synth.prepare_events(np.array(cfgs), events, eo, cont)
+    frames, out = b.run_host(events)
+    b.close()
+    checked = 0
+    carried = None
+    for i in range(3000):
+        in_chain = cont[i] or (i + 1 < 3000 and cont[i + 1])
+        if not (in_chain or i % 10 == 0):
+            carried = None
+            continue
+        c = cfgs[i].copy()
+        if cont[i]:
+            assert carried is not None
+            for k in ("drift_seed", "drift_x1", "drift_x2", "drift_y1", "drift_y2"):
+                c[k] = carried[k]
+        want, carried = o.generate(c, lists[i])
+        assert frames_list[i].shape == want.shape, i
+        assert np.array_equal(_bits(frames_list[i]), _bits(want)), i
+        assert np.array_equal(_bits(frames[b.frame_offsets[i]:b.frame_offsets[i + 1]]), _bits(want)), i
+        for k in ("drift_seed", "drift_x1", "drift_y2"):
+            assert out[k][i] == carried[k], (i, k)
+        checked += 1
+    assert checked >= 300
+
+
+def test_events_to_audio_without_leaving_the_device(synth, oracle):
+    # the chain the row exists for: event lists -> control frames (events_kernel) -> audio (tube kernel) on one stream, the
+    # frames never on the host.  The audio equals, bit for bit, what the same kernel makes of the oracle's frames fed from
+    # the host, and is within the tolerance of the oracle's audio.
+    import torch
+    from gama_tts_b200 import capi
+    from gama_tts_b200.events import event_config, synthetic_events
+    from oracle.pyoracle import OracleEvents
+    o = OracleEvents()
+    v = default_voice("male")
+    cfgs, lists, cont = [], [], []
+    for u in range(40):
+        chunks = 1 + u % 3
+        for k in range(chunks):
+            cfgs.append(event_config())
+            lists.append(synthetic_events(500 + 10 * u + k, 3 + (u + k) % 6))
+            cont.append(int(k > 0))
+    events, eo = g.pack_events(lists)
+    eb = synth.prepare_events(np.array(cfgs), events, eo, cont)
+    fo = eb.utterance_frame_offsets
+    assert len(fo) == 41 and fo[-1] == eb.n_frames_total
+    tb = synth.prepare(v, fo)
+    s = torch.cuda.current_stream()
+    d_events = torch.from_numpy(events.view(np.uint8)).cuda()
+    d_frames = torch.zeros(eb.n_frames_total * 16, dtype=torch.float32, device="cuda")
+    d_out = torch.zeros(tb.n_out_total, dtype=torch.float32, device="cuda")
+    eb.run_device(d_events.data_ptr(), d_frames.data_ptr(), 0, s.cuda_stream)
+    tb.run_device(d_frames.data_ptr(), d_out.data_ptr(), s.cuda_stream)
+    torch.cuda.synchronize()
+    audio = tb.split(d_out.cpu().numpy())
+    # the oracle's frames, chained chunk by chunk
+    want_frames, carried = [], None
+    for i, (c, ev) in enumerate(zip(cfgs, lists)):
+        c = c.copy()
+        if cont[i]:
+            for k in ("drift_seed", "drift_x1", "drift_x2", "drift_y1", "drift_y2"):
+                c[k] = carried[k]
+        f, carried = o.generate(c, ev)
+        want_frames.append(f)
+    want_frames = np.concatenate(want_frames)
+    assert np.array_equal(_bits(d_frames.cpu().numpy().reshape(-1, 16)), _bits(want_frames))
+    host = tb.split(tb.run_host(want_frames))
+    for u in range(40):
+        assert np.array_equal(audio[u], host[u]), u
+    for u in (0, 7, 23, 39):
+        ref = oracle.synthesize(v, want_frames[fo[u]:fo[u + 1]])
+        assert len(ref) == len(audio[u]) and full_scale_error(audio[u], ref) <= TIGHT, u
+    eb.close()
+    tb.close()

@@ -171,3 +171,60 @@ def test_models_3_and_4_host_entry_points(product_lib, oracle):
     assert product_lib.gtts_output_length(C.byref(bad), 80, 5, C.byref(n_int), C.byref(n_out)) == capi.GTTS_ERR_INVALID
     short = capi.voice_config(dict(default_voice("male"), tube_model=4, vocal_tract_length=5.0))
     assert product_lib.gtts_output_length(C.byref(short), 80, 5, C.byref(n_int), C.byref(n_out)) != capi.GTTS_OK
+
+
+# ---- control-frame generation: host entry points (gtts_events_*) -------------------------------------------------------
+
+def _golden_events():
+    z = np.load(os.path.join(ROOT, "tests", "golden", "events_v1.npz"))
+    return z, [str(n) for n in z["names"]]
+
+
+def test_event_structs_match_header():
+    hdr = open(os.path.join(ROOT, "include", "gtts_b200.h")).read()
+    assert "typedef struct gtts_event {" in hdr and "typedef struct gtts_event_config {" in hdr
+    from oracle.pyoracle import EVENT_DTYPE, EVENT_CONFIG_DTYPE
+    assert capi.EVENT_DTYPE.itemsize == EVENT_DTYPE.itemsize == 296
+    assert capi.EVENT_CONFIG_DTYPE.itemsize == EVENT_CONFIG_DTYPE.itemsize == 128
+    assert [capi.EVENT_CONFIG_DTYPE.fields[n][1] for n in capi.EVENT_CONFIG_DTYPE.names] == \
+           [EVENT_CONFIG_DTYPE.fields[n][1] for n in EVENT_CONFIG_DTYPE.names]
+
+
+def test_events_frame_count_and_drift_setup_match_reference_fixtures(product_lib):
+    # the frame counts and the drift generator's constants the unmodified reference had (tests/golden/events_v1.npz)
+    from gama_tts_b200.events import event_config, synthetic_events
+    from oracle.pyoracle import OracleEvents
+    z, names = _golden_events()
+    for n in names:
+        cfg = z["cfg_" + n].astype(capi.EVENT_CONFIG_DTYPE)
+        assert g.events_frame_count(cfg, z["ev_" + n]) == len(z["frames_" + n]), n
+    fresh = event_config()
+    ref = z["cfg_hello_0"]
+    for k in ("drift_deviation2", "drift_offset", "drift_seed", "drift_b0", "drift_b1", "drift_a1", "drift_a2", "drift_x1", "drift_y2"):
+        assert fresh[k] == ref[k], k
+    cfg = np.zeros(1, capi.EVENT_CONFIG_DTYPE)
+    assert product_lib.gtts_events_drift_setup(4.0, 250.0, 0.5, cfg.ctypes.data) == capi.GTTS_ERR_INVALID     # below 1 Hz
+    assert product_lib.gtts_events_drift_setup(4.0, 250.0, 121.0, cfg.ctypes.data) == capi.GTTS_ERR_INVALID   # above 0.48 fs
+    # synthetic lists, also with events closer than a control period: the host's count is what the oracle produces
+    o = OracleEvents()
+    for seed in range(8):
+        ev = synthetic_events(seed, 3 + seed, tight=seed % 2 == 1)
+        for period in (1, 4, 10):
+            c = event_config(control_period=period)
+            assert g.events_frame_count(c, ev) == len(o.generate(c, ev)[0]), (seed, period)
+    assert g.events_frame_count(fresh, ev[:1]) == 0 and g.events_frame_count(fresh, ev[:0]) == 0
+
+
+def test_events_prepare_fails_loudly_without_a_gpu_or_on_bad_input(product_lib):
+    from gama_tts_b200.events import event_config, synthetic_events
+    ev = synthetic_events(1, 3)
+    eo = np.array([0, len(ev)], np.int64)
+    cfg = np.array([event_config()], capi.EVENT_CONFIG_DTYPE)
+    h = C.c_void_p()
+    assert product_lib.gtts_events_prepare(None, cfg.ctypes.data, None, ev.ctypes.data, eo.ctypes.data, 1, C.byref(h)) == capi.GTTS_ERR_INVALID
+    assert product_lib.gtts_events_run_host(None, ev.ctypes.data, None, None) == capi.GTTS_ERR_INVALID
+    assert product_lib.gtts_events_run_device(None, None, None, None, None) == capi.GTTS_ERR_INVALID
+    n = C.c_int64()
+    bad = cfg.copy()
+    bad["control_period"] = 0
+    assert product_lib.gtts_events_frame_count(bad.ctypes.data, ev.ctypes.data, len(ev), C.byref(n)) == capi.GTTS_ERR_INVALID
