@@ -400,7 +400,7 @@ def events_leg(synth, rank):
 
     out = {}
     # (a) the headline shape, chained in front of the synthesis
-    eb, events, cfgs, lists = batch(N_UTT, 79, 96)
+    eb, events, cfgs, lists = batch(N_UTT, 74, 96)
     d_events = torch.from_numpy(events.view(np.uint8)).cuda()
     d_frames = torch.empty(eb.n_frames_total * 16, dtype=torch.float32, device="cuda")
     tb = synth.prepare(default_voice("male"), eb.frame_offsets)

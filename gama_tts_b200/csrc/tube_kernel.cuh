@@ -347,7 +347,7 @@ GTTS_DEV double table_at(const WarpSm* S, const VoiceDev& V, unsigned i, bool dy
 		return 1.0 - (x * x);
 	}
 	if ((int) i >= low && i < (unsigned) V.div1) return 0.0;      // rise segment zeroed by an earlier closure point below div1
-	return S->table[i];
+	return S->table[i & (kTableLen - 1)];     // in range already unless the pitch is absurd: no read outside the table then either
 }
 
 // ---- stage: wavetable lookup of both half samples, lane = sample (:212-228) --------------------------

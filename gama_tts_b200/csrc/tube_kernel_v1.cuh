@@ -420,13 +420,13 @@ GTTS_DEV void helper_iteration(CtaSm* C, SlotSm* S, const KernelParamsV1& P, int
 					const double x = (double) (int) (lo - V.div1) * inv;
 					tl = (lo >= (unsigned) nd2) ? 0.0 : 1.0 - (x * x);
 				} else {
-					tl = table[lo];
+					tl = table[lo & (kTableLen - 1)];
 				}
 				if (dynamic && up >= (unsigned) V.div1 && up < (unsigned) V.div2) {
 					const double x = (double) (int) (up - V.div1) * inv;
 					tu = (up >= (unsigned) nd2) ? 0.0 : 1.0 - (x * x);
 				} else {
-					tu = table[up];
+					tu = table[up & (kTableLen - 1)];
 				}
 				v[s] = tl + ((pos - (double) lo) * (tu - tl));
 			}

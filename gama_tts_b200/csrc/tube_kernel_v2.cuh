@@ -613,13 +613,13 @@ GTTS_DEV void helper_iteration(SlotSm* S, const KernelParamsV2& P, int lane, Hel
 					const double x = (double) (int) (lo - V.div1) * inv;
 					tl = (lo >= (unsigned) nd2) ? 0.0 : 1.0 - (x * x);
 				} else {
-					tl = ((int) lo >= low) ? 0.0 : table[lo];
+					tl = ((int) lo >= low) ? 0.0 : table[lo & (kTableLen - 1)];   // the mask only acts on an absurd pitch (position beyond the table): no stray read
 				}
 				if (dynamic && up >= (unsigned) V.div1 && up < (unsigned) V.div2) {
 					const double x = (double) (int) (up - V.div1) * inv;
 					tu = (up >= (unsigned) nd2) ? 0.0 : 1.0 - (x * x);
 				} else {
-					tu = ((int) up >= low) ? 0.0 : table[up];
+					tu = ((int) up >= low) ? 0.0 : table[up & (kTableLen - 1)];
 				}
 				v[s] = tl + ((pos - (double) lo) * (tu - tl));
 			}

@@ -20,30 +20,40 @@ def event_config(control_period=4, macro=1, micro=1, drift=1, smooth=1, initial_
     return cfg[0]
 
 
-def synthetic_events(seed, n_postures, special_rate=0.02, tight=False):
-    """An event list of about 4 events per posture: times ascending (not multiples of the control period; with `tight` some
-    closer than a period or equal), the first event with every parameter set, later ones with about half of them, a few
+def synthetic_events(seed, n_postures, special_rate=0.02, tight=False, grid=4):
+    """An event list of about 4 events per posture: times ascending on a grid of `grid` ms, 2 to 15 grid steps apart, as the
+    rule engine's are (with `tight`: any millisecond, some closer than a period or at equal times -- the reference then
+    divides by zero and so do we), the first event with every parameter set, later ones with about half of them, a few
     special parameters, a macro-intonation polynomial on about one event in ten, the last event with every parameter."""
     rng = np.random.Generator(np.random.PCG64(seed))
     n = max(2, 4 * n_postures)
     ev = np.zeros(n, capi.EVENT_DTYPE)
-    gaps = rng.integers(1 if tight else 5, 60, n)
     if tight:
+        gaps = rng.integers(1, 60, n)
         gaps[rng.random(n) < 0.15] = 0
+    else:
+        gaps = grid * rng.integers(2, 16, n)
     gaps[0] = 0
     ev["time"] = np.cumsum(gaps)
     targets = tracks.POSTURE_TARGETS[rng.integers(0, len(tracks.POSTURE_TARGETS), n)].astype(np.float64)
     targets += rng.normal(0.0, 0.01, targets.shape)
+    span = tracks.PARAM_MAX - tracks.PARAM_MIN
+    targets = np.clip(targets, tracks.PARAM_MIN + 0.02 * span, tracks.PARAM_MAX - 0.02 * span)   # room for the special parameters
     keep = rng.random((n, 16)) < 0.5
     keep[0] = keep[-1] = True
     ev["param"] = np.where(keep, targets, EMPTY)
     ev["param"][1:, 0] = np.where(keep[1:, 0], rng.normal(0.0, 1.0, n - 1), EMPTY)       # micro intonation
     sp = rng.random((n, 16)) < special_rate
-    ev["special"] = np.where(sp, rng.normal(0.0, 0.05, (n, 16)), EMPTY)
+    ev["special"] = np.where(sp, np.clip(rng.normal(0.0, 0.003, (n, 16)), -0.01, 0.01) * span, EMPTY)
+    # macro intonation: from an event on, y0 + m (x - t0) + q (x - t0)^3 semitones in the chunk's time x (ms), as
+    # coefficients of x (the reference fits them through its intonation points: a few semitones over a tone group)
     interp = rng.random(n) < 0.1
+    interp[0] = tight and interp[0]       # a polynomial on the event at time 0 makes the first segment's slope x / 0
+    t0 = ev["time"].astype(np.float64)
+    y0, m, q = rng.normal(-2.0, 2.0, n), rng.uniform(-0.002, 0.002, n), rng.uniform(-2e-10, 2e-10, n)
     ev["has_interp"] = interp
-    ev["a"] = np.where(interp, rng.normal(0.0, 1e-8, n), 0.0)
-    ev["b"] = np.where(interp, rng.normal(0.0, 1e-5, n), 0.0)
-    ev["c"] = np.where(interp, rng.normal(0.0, 1e-2, n), 0.0)
-    ev["d"] = np.where(interp, rng.normal(-2.0, 2.0, n), 0.0)
+    ev["a"] = np.where(interp, q, 0.0)
+    ev["b"] = np.where(interp, -3.0 * q * t0, 0.0)
+    ev["c"] = np.where(interp, m + 3.0 * q * t0 * t0, 0.0)
+    ev["d"] = np.where(interp, y0 - m * t0 - q * t0 ** 3, 0.0)
     return ev

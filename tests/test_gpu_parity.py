@@ -555,7 +555,10 @@ def test_models_3_and_4_are_batch_only(synth):
 # ---- control-frame generation on the device (gtts_events_*, events_kernel.cuh) -----------------------------------------
 
 def _bits(a):
-    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+    # bit patterns; every NaN as one pattern (events at the time of the frame being made divide 0 by 0 in the reference:
+    # x86 returns its negative default NaN, the GPU its canonical one -- a NaN either way)
+    a = np.ascontiguousarray(a, np.float32)
+    return np.where(np.isnan(a), np.uint32(0x7fc00000), a.view(np.uint32))
 
 
 def test_events_reference_fixtures_bit_exact(synth):
