@@ -80,6 +80,10 @@ std::string planEvents(const gtts_event_config* configs, const int32_t* continue
 	plan.order.resize(plan.chains.size());
 	std::iota(plan.order.begin(), plan.order.end(), 0);
 	std::stable_sort(plan.order.begin(), plan.order.end(), [&](int32_t a, int32_t b) { return chainFrames[a] > chainFrames[b]; });
+	plan.chunk_order.resize(n_chunks);
+	std::iota(plan.chunk_order.begin(), plan.chunk_order.end(), 0);
+	std::stable_sort(plan.chunk_order.begin(), plan.chunk_order.end(),
+			[&](int32_t a, int32_t b) { return plan.chunks[a].n_frames > plan.chunks[b].n_frames; });
 	*err = GTTS_OK;
 	return std::string();
 }

@@ -33,6 +33,7 @@ struct EventsPlan {
 	std::vector<ChunkDesc> chunks;
 	std::vector<ChainDesc> chains;
 	std::vector<int32_t> order;             // chains by frames, longest first
+	std::vector<int32_t> chunk_order;       // chunks by frames, longest first
 	std::vector<int64_t> frame_offsets;     // [n_chunks + 1]
 	int64_t n_events_total = 0;
 };

@@ -1629,6 +1629,8 @@ struct gtts_events_batch {
 	evt::ChunkDesc* d_chunks = nullptr;
 	evt::ChainDesc* d_chains = nullptr;
 	int32_t* d_order = nullptr;
+	int32_t* d_chunk_order = nullptr;
+	float* d_drift = nullptr;                  // scratch: the drift generator's output per frame
 	int32_t* d_queue = nullptr;
 	gtts_event* d_events = nullptr;            // run_host staging
 	float* d_frames = nullptr;
@@ -1640,7 +1642,7 @@ void gtts_events_free(gtts_events_batch* b)
 	if (!b) return;
 	cudaSetDevice(b->h->device);
 	cudaFree(b->d_cfgs); cudaFree(b->d_cfgs_out); cudaFree(b->d_chunks); cudaFree(b->d_chains); cudaFree(b->d_order);
-	cudaFree(b->d_queue); cudaFree(b->d_events); cudaFree(b->d_frames);
+	cudaFree(b->d_queue); cudaFree(b->d_events); cudaFree(b->d_frames); cudaFree(b->d_chunk_order); cudaFree(b->d_drift);
 	if (b->stream) cudaStreamDestroy(b->stream);
 	delete b;
 }
@@ -1671,8 +1673,11 @@ static int prepareEvents(gtts_events_batch* b)
 	GTTS_CUDA(cudaMalloc(&b->d_chunks, sizeof(evt::ChunkDesc) * std::max<size_t>(nChunks, 1)));
 	GTTS_CUDA(cudaMalloc(&b->d_chains, sizeof(evt::ChainDesc) * std::max<size_t>(nChains, 1)));
 	GTTS_CUDA(cudaMalloc(&b->d_order, sizeof(int32_t) * std::max<size_t>(nChains, 1)));
+	GTTS_CUDA(cudaMalloc(&b->d_chunk_order, sizeof(int32_t) * std::max<size_t>(nChunks, 1)));
+	GTTS_CUDA(cudaMalloc(&b->d_drift, sizeof(float) * std::max<int64_t>(p.frame_offsets.empty() ? 0 : p.frame_offsets.back(), 1)));
 	GTTS_CUDA(cudaMalloc(&b->d_queue, 2 * sizeof(int32_t)));
 	if (nChunks > 0) {
+		GTTS_CUDA(cudaMemcpyAsync(b->d_chunk_order, p.chunk_order.data(), sizeof(int32_t) * nChunks, cudaMemcpyHostToDevice, b->stream));
 		GTTS_CUDA(cudaMemcpyAsync(b->d_cfgs, p.cfgs.data(), sizeof(gtts_event_config) * nChunks, cudaMemcpyHostToDevice, b->stream));
 		GTTS_CUDA(cudaMemcpyAsync(b->d_chunks, p.chunks.data(), sizeof(evt::ChunkDesc) * nChunks, cudaMemcpyHostToDevice, b->stream));
 		GTTS_CUDA(cudaMemcpyAsync(b->d_chains, p.chains.data(), sizeof(evt::ChainDesc) * nChains, cudaMemcpyHostToDevice, b->stream));
@@ -1727,13 +1732,24 @@ int gtts_events_run_device(gtts_events_batch* b, const gtts_event* d_events, flo
 	P.chunks = b->d_chunks;
 	P.chains = b->d_chains;
 	P.order = b->d_order;
+	P.chunk_order = b->d_chunk_order;
 	P.frames = d_frames;
+	P.drift = b->d_drift;
 	P.queue = b->d_queue;
 	P.n_chains = nChains;
-	// one warp per utterance; CTAs up to eight per SM, a whole number of waves when the batch is that large
-	const int ctasWanted = (nChains + evt::kEventsWarps - 1) / evt::kEventsWarps;
-	const int grid = std::min(ctasWanted, b->h->sms * 8);
-	evt::events_kernel<<<grid, evt::kEventsWarps * 32, 0, stream>>>(P);
+	P.n_chunks = static_cast<int>(b->plan.chunks.size());
+	// drift pass: one thread per utterance
+	evt::events_drift_kernel<<<(nChains + evt::kDriftThreads - 1) / evt::kDriftThreads, evt::kDriftThreads, 0, stream>>>(P);
+	GTTS_CUDA(cudaGetLastError());
+	// frame pass: one warp per chunk from a queue; three CTAs of eight warps per SM are resident
+	const int ctasWanted = (P.n_chunks + evt::kEventsWarps - 1) / evt::kEventsWarps;
+	const int grid = std::min(ctasWanted, b->h->sms * 3);
+	static bool attributeSet[64] = {};
+	if (b->h->device < 64 && !attributeSet[b->h->device]) {
+		GTTS_CUDA(cudaFuncSetAttribute(evt::events_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, evt::kEventsSmem));
+		attributeSet[b->h->device] = true;
+	}
+	evt::events_kernel<<<grid, evt::kEventsWarps * 32, evt::kEventsSmem, stream>>>(P);
 	GTTS_CUDA(cudaGetLastError());
 	return GTTS_OK;
 }

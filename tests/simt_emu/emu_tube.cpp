@@ -387,10 +387,17 @@ extern "C" int emu_events(const gtts_event_config* configs, const int* continues
 	P.chunks = plan.chunks.data();
 	P.chains = plan.chains.data();
 	P.order = plan.order.data();
+	P.chunk_order = plan.chunk_order.data();
 	P.frames = frames;
+	std::vector<float> drift(static_cast<size_t>(plan.frame_offsets.back()) + 1);
+	P.drift = drift.data();
 	P.queue = queue;
 	P.n_chains = static_cast<int32_t>(plan.chains.size());
-	simt::run_cta(warps_per_cta * 32, [&](int tid) { evt::events_cta_body(P, tid); });
+	P.n_chunks = static_cast<int32_t>(plan.chunks.size());
+	for (int t = 0; t < P.n_chains; ++t) evt::drift_body(P, t);
+	std::vector<double> ring(static_cast<size_t>(warps_per_cta) * evt::kRingRows * evt::kEventDoubles);
+	std::vector<unsigned> masks(static_cast<size_t>(warps_per_cta) * evt::kMaskWords * 32);
+	simt::run_cta(warps_per_cta * 32, [&](int tid) { evt::events_cta_body(P, ring.data(), masks.data(), tid); });
 	if (queue[1]) { g_err = "frame count mismatch"; return GTTS_ERR_CUDA; }
 	return 0;
 }

@@ -385,6 +385,11 @@ def test_emulated_events_kernel_synthetic_lists_vs_oracle(emu_events):
         cfgs.append(event_config())
         lists.append(synthetic_events(200 + k, 5))
         cont.append(int(k > 0))
+    # lists longer than the kernel's occupancy-mask window (512 rows): the window moves, and scans run past its end
+    for k, n_post in enumerate((150, 400)):
+        cfgs.append(event_config(smooth=k))
+        lists.append(synthetic_events(300 + k, n_post, special_rate=0.004, tight=k == 1))
+        cont.append(0)
     frames, out = emu_events(np.array(cfgs), lists, cont)
     carried = None
     for i, (c, ev) in enumerate(zip(cfgs, lists)):
