@@ -668,6 +668,7 @@ def main():
                          "hbm_bytes_per_launch_algorithmic": int(frames_np.nbytes + n_samples * 4)},
             "clocks": clocks,
             "kernel": json.loads(synth.describe()),
+            "kernel_used": batch.last_kernel(),
             "checksum": checksum,
         }
         if cfg34 is not None:

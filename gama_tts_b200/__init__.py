@@ -137,6 +137,9 @@ class Batch:
         check(self._lib.gtts_batch_last_launches(self._h, C.byref(n)))
         return n.value
 
+    def last_kernel(self):
+        return self._lib.gtts_batch_last_kernel(self._h).decode()
+
     def split(self, packed):
         return [packed[self.out_offsets[u]:self.out_offsets[u] + self.n_out[u]] for u in range(self.n_utt)]
 

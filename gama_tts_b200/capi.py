@@ -111,7 +111,7 @@ EXPORTS = [
     "gtts_output_length", "gtts_shard_plan", "gtts_probe_fir_taps", "gtts_probe_src_tables",
     "gtts_probe_voice_constants", "gtts_probe_fp64_peak", "gtts_probe_exp", "gtts_create", "gtts_destroy", "gtts_describe", "gtts_batch_prepare",
     "gtts_batch_layout", "gtts_batch_lengths", "gtts_batch_run_device", "gtts_batch_run_host", "gtts_batch_run_device_pcm16",
-    "gtts_batch_run_host_pcm16", "gtts_batch_submit_host_pcm16", "gtts_batch_wait", "gtts_batch_checksum_device", "gtts_batch_last_launches",
+    "gtts_batch_run_host_pcm16", "gtts_batch_submit_host_pcm16", "gtts_batch_wait", "gtts_batch_checksum_device", "gtts_batch_last_launches", "gtts_batch_last_kernel",
     "gtts_multi_create", "gtts_multi_destroy", "gtts_multi_device_count", "gtts_multi_batch_prepare", "gtts_multi_batch_layout",
     "gtts_multi_batch_run_host", "gtts_multi_batch_run_host_pcm16", "gtts_multi_batch_free",
     "gtts_batch_free", "gtts_batch_synthesize", "gtts_stream_open", "gtts_stream_push_frames",
@@ -172,6 +172,8 @@ def load():
     L.gtts_multi_batch_free.argtypes = [vp]
     L.gtts_multi_batch_free.restype = None
     L.gtts_batch_last_launches.argtypes = [vp, C.POINTER(i32)]
+    L.gtts_batch_last_kernel.argtypes = [vp]
+    L.gtts_batch_last_kernel.restype = C.c_char_p
     L.gtts_batch_free.argtypes = [vp]
     L.gtts_batch_free.restype = None
     L.gtts_batch_synthesize.argtypes = [vp, PV, i32, vp, dbl, vp, vp, i64, vp, i64, vp]

@@ -183,7 +183,8 @@ struct gtts_batch {
 	cudaEvent_t ev_synth = nullptr;
 	int32_t last_launches = 0;
 	double* d_tables = nullptr;         // per-voice glottal wavetables (v1 kernel)
-	bool legacy_v1 = false;             // GTTS_KERNEL=v1: the barrier-per-iteration kernel instead of v2 (A/B measurements)
+	int kernel_hint = -1;               // shard of a multi-GPU batch: 1 = the whole batch is uniform (tube_kernel_v1), 0 = not
+	bool legacy_v1 = false;             // tube_kernel_v1 (one CTA barrier per iteration) instead of v2: uniform batches, or GTTS_KERNEL=v1
 	bool streaming = false;             // one-utterance batch of a gtts_stream (set before the plan is uploaded)
 	int32_t n_fast = 0;                 // the first n_fast entries of the order list run on the pipelined kernel
 	int32_t* d_order_wide = nullptr;    // wide-batch kernel (one thread per utterance): n_wide_groups x 32 indices, -1 = empty lane
@@ -315,7 +316,7 @@ int launchBatch(gtts_batch* b, const float* dFrames, float* dOut, cudaStream_t s
 		b->last_kernel = nWide > 0 ? "tube_kernel_v3+tube_kernel_v2" : "tube_kernel_v2";
 		b->last_launches += 1;
 	} else if (nFast > 0) {
-		// the barrier-per-iteration predecessor (GTTS_KERNEL=v1), kept for A/B measurements
+		// the barrier-per-iteration kernel: batches whose utterances all have one voice and one length (prepare), or GTTS_KERNEL=v1
 		v1::KernelParamsV1 Q;
 		Q.voices = b->d_voices;
 		Q.tables = b->d_tables;
@@ -405,6 +406,25 @@ int uploadPlan(gtts_batch* b)
 	auto fast = [&](int32_t u) { const UttDesc& d = p.utts[u]; return !forceGeneral && p.voices[d.voice].tube_model == 0 && (d.steps >= kBlock || d.steps == 1); };
 	const auto mid = std::stable_partition(p.order.begin(), p.order.end(), fast);
 	b->n_fast = static_cast<int32_t>(mid - p.order.begin());
+	// Which pipelined kernel: when every utterance of the part has the same voice and length (BASELINE config 2), all
+	// slots of a CTA stay aligned, the CTA-wide barrier of tube_kernel_v1 costs next to nothing and its smaller code wins:
+	// measured on B200 25.7 ms against 27.4 ms on tube_kernel_v2 for 1,024 x 10 s.  Ragged or mixed-voice batches
+	// (config 3) are where v2's decoupled roles pay: 208 k against 169 k audio-s/s.  GTTS_KERNEL=v1 / v2 forces one.
+	// A shard of a multi-GPU batch takes the choice made for the whole batch (kernel_hint), so that its audio stays bit
+	// for bit what one GPU produces.
+	if (b->n_fast > 0 && !std::getenv("GTTS_KERNEL")) {
+		if (b->kernel_hint >= 0) {
+			b->legacy_v1 = b->kernel_hint == 1;
+		} else {
+			const UttDesc& first = p.utts[p.order[0]];
+			bool uniform = true;
+			for (int32_t i = 1; i < b->n_fast && uniform; ++i) {
+				const UttDesc& d = p.utts[p.order[i]];
+				uniform = d.voice == first.voice && d.n_frames == first.n_frames && d.steps == first.steps;
+			}
+			b->legacy_v1 = uniform && b->n_fast > 1;
+		}
+	}
 	if (b->n_fast > 0 || b->n_wide > 0) {
 		std::vector<double> tables(p.voices.size() * kTableLen);
 		for (size_t v = 0; v < p.voices.size(); ++v) buildWavetable(p.voices[v], tables.data() + v * kTableLen);
@@ -571,9 +591,11 @@ int createHandle(int32_t device, gtts_handle** handle_out)
 	std::snprintf(buf, sizeof buf,
 			"{\"device\": %d, \"name\": \"%s\", \"sm\": \"%d.%d\", \"sms\": %d, "
 			"\"kernels\": {\"tube_kernel_v2\": {\"warps_per_cta\": %d, \"utterance_slots_per_cta\": %d, \"smem_per_cta\": %zu}, "
+			"\"tube_kernel_v1\": {\"warps_per_cta\": %d, \"utterance_slots_per_cta\": %d, \"smem_per_cta\": %zu, "
+			"\"used_for\": \"batches of one voice and one length\"}, "
 			"\"tube_kernel_v0\": {\"warps_per_cta\": %d, \"utterances_per_warp\": 1, \"smem_per_cta\": %zu}}}",
 			device, prop.name, prop.major, prop.minor, h->sms, (int) v2::kWarps, (int) v2::kSlots, v2::smem_bytes(),
-			kWarpsPerCta, tube_smem_bytes(kWarpsPerCta));
+			(int) (v1::kThreads / 32), (int) v1::kSlots, v1::smem_bytes(), kWarpsPerCta, tube_smem_bytes(kWarpsPerCta));
 	h->description = buf;
 	*handle_out = h;
 	return GTTS_OK;
@@ -895,6 +917,8 @@ int gtts_batch_last_launches(const gtts_batch* b, int32_t* n_out)
 	*n_out = b->last_launches;
 	return GTTS_OK;
 }
+
+const char* gtts_batch_last_kernel(const gtts_batch* b) { return b ? b->last_kernel : "none"; }
 
 void gtts_batch_free(gtts_batch* b)
 {
@@ -1266,9 +1290,15 @@ int gtts_multi_batch_prepare(gtts_multi* m, const gtts_voice_config* voices, int
 		b->shard_of.assign(static_cast<size_t>(n_utt), 0);
 		if (n_utt > 0) shardPlan(cost.data(), n_utt, nDev, b->shard_of.data());
 		b->shards.assign(nDev, nullptr);
+		bool uniform = n_utt > 1;
+		for (int64_t u = 1; u < n_utt && uniform; ++u) {
+			const UttDesc& d = b->plan.utts[u], & first = b->plan.utts[0];
+			uniform = d.voice == first.voice && d.n_frames == first.n_frames && d.steps == first.steps;
+		}
 		for (int g = 0; g < nDev; ++g) {
 			gtts_batch* sb = new gtts_batch;
 			sb->h = m->handles[g];
+			sb->kernel_hint = uniform ? 1 : 0;
 			sb->plan.voices = b->plan.voices;
 			for (int64_t u = 0; u < n_utt; ++u) if (b->shard_of[u] == g) sb->plan.utts.push_back(b->plan.utts[u]);   // global frame_begin / out_begin kept
 			sb->plan.out_offsets = b->plan.out_offsets;              // sizes of the caller's buffers

@@ -173,6 +173,9 @@ int gtts_batch_wait(gtts_batch* batch);
 int gtts_batch_checksum_device(gtts_batch* batch, const float* d_audio, uint64_t* d_sums, void* cuda_stream);
 /* Number of kernel launches the last run issued (for bench.py's gpu_launches claim). */
 int gtts_batch_last_launches(const gtts_batch* batch, int32_t* n_out);
+/* Name of the synthesis kernel(s) the last run launched ("tube_kernel_v1": batches of one voice and one length,
+ * "tube_kernel_v2": ragged / mixed-voice batches, "tube_kernel_v0": short control periods, models 3 / 4, streams), for logs. */
+const char* gtts_batch_last_kernel(const gtts_batch* batch);
 void gtts_batch_free(gtts_batch* batch);
 
 /* One-call convenience over prepare + run_host + free (what a C caller of the reference's

@@ -552,6 +552,35 @@ def test_models_3_and_4_are_batch_only(synth):
     assert e.value.code == g.capi.GTTS_ERR_UNSUPPORTED
 
 
+def test_pipelined_kernel_choice(synth, oracle, monkeypatch):
+    # a batch of one voice and one length runs on tube_kernel_v1 (aligned slots: its CTA barrier is free and its code is
+    # smaller), anything ragged or of several voices on tube_kernel_v2; both against the oracle, and equal to each other
+    monkeypatch.delenv("GTTS_KERNEL", raising=False)
+    v = default_voice("male")
+    uniform = [T.synthetic_track(900 + i, 50) for i in range(12)]
+    frames, fo = g.pack_tracks(uniform)
+    b = synth.prepare(v, fo)
+    a1 = [x.copy() for x in b.split(b.run_host(frames))]
+    assert b.last_kernel() == "tube_kernel_v1"
+    b.close()
+    ragged = uniform[:11] + [T.synthetic_track(950, 37)]
+    frames_r, fo_r = g.pack_tracks(ragged)
+    b = synth.prepare(v, fo_r)
+    a2 = [x.copy() for x in b.split(b.run_host(frames_r))]
+    assert b.last_kernel() == "tube_kernel_v2"
+    b.close()
+    monkeypatch.setenv("GTTS_KERNEL", "v2")
+    b = synth.prepare(v, fo)
+    a3 = [x.copy() for x in b.split(b.run_host(frames))]
+    assert b.last_kernel() == "tube_kernel_v2"
+    b.close()
+    for u in range(11):
+        assert np.array_equal(a2[u], a3[u]), u                       # the same kernel, whatever the batch around the utterance
+        assert full_scale_error(a1[u], a2[u]) <= 1e-7, u             # two kernels: different FMA contraction
+    for u in (0, 5, 11):
+        assert full_scale_error(a1[u], oracle.synthesize(v, uniform[u])) <= TIGHT
+
+
 # ---- control-frame generation on the device (gtts_events_*, events_kernel.cuh) -----------------------------------------
 
 def _bits(a):
