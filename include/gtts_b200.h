@@ -173,7 +173,12 @@ int gtts_batch_wait(gtts_batch* batch);
 int gtts_batch_checksum_device(gtts_batch* batch, const float* d_audio, uint64_t* d_sums, void* cuda_stream);
 /* Number of kernel launches the last run issued (for bench.py's gpu_launches claim). */
 int gtts_batch_last_launches(const gtts_batch* batch, int32_t* n_out);
-/* Name of the synthesis kernel(s) the last run launched ("tube_kernel_v1": batches of one voice and one length,
+/* Determinism: a run is bit-reproducible, and an utterance's audio does not depend on what else is in the batch as long as
+ * the same kernel synthesises it.  Two pipelined kernels exist (same operations, different multiply-adds contracted: their
+ * outputs differ by <= 1e-7 of full scale, the reference's own FMA on / off noise floor): a batch whose utterances all have
+ * one voice and one length takes tube_kernel_v1, any other tube_kernel_v2; the environment variable GTTS_KERNEL=v2 (or v1)
+ * pins one for every batch.  The shards of a gtts_multi batch take the whole batch's choice.
+ * Name of the synthesis kernel(s) the last run launched ("tube_kernel_v1": batches of one voice and one length,
  * "tube_kernel_v2": ragged / mixed-voice batches, "tube_kernel_v0": short control periods, models 3 / 4, streams), for logs. */
 const char* gtts_batch_last_kernel(const gtts_batch* batch);
 void gtts_batch_free(gtts_batch* batch);

@@ -179,7 +179,19 @@ def test_config2_full_batch_parity(synth, oracle):
         worst = max(worst, full_scale_error(outs[i], ref))
         assert snr_db(outs[i], ref) >= 100.0
     assert worst <= TIGHT, worst
-    assert np.array_equal(outs[7], synth.synthesize(v, [tracks[7]])[0])
+    # the uniform batch runs on tube_kernel_v1, one utterance alone on tube_kernel_v2 (test_pipelined_kernel_choice): the same
+    # operations with different multiply-adds contracted, so equal to within the FMA noise floor; bitwise under one kernel
+    assert b_last_kernel(synth, v, tracks[:2]) == "tube_kernel_v1"
+    assert full_scale_error(outs[7], synth.synthesize(v, [tracks[7]])[0]) <= 1e-7
+
+
+def b_last_kernel(synth, voice, tracks):
+    frames, fo = g.pack_tracks(tracks)
+    b = synth.prepare(voice, fo)
+    b.run_host(frames)
+    name = b.last_kernel()
+    b.close()
+    return name
 
 
 def test_pcm16_output_stage_is_bit_exact(synth, oracle, golden, real_tracks):
