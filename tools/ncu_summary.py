@@ -24,14 +24,17 @@ def main():
     print(sys.argv[2] if len(sys.argv) > 2 else rep)
     txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(txt.splitlines()))
-    hdr, units, vals = rows[0], rows[1], rows[2]
-    m = {h: (v, u) for h, u, v in zip(hdr, units, vals)}
-    for k in KEYS:
-        if k in m:
-            print("%s = %s %s" % (k, m[k][0], m[k][1]))
-    for h in hdr:
-        if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio"):
-            print("%s = %s %s" % (h, m[h][0], m[h][1]))
+    hdr, units = rows[0], rows[1]
+    for vals in rows[2:]:           # one row per captured kernel launch
+        m = {h: (v, u) for h, u, v in zip(hdr, units, vals)}
+        if len(rows) > 3 and "Kernel Name" in m:
+            print("---- %s" % m["Kernel Name"][0])
+        for k in KEYS:
+            if k in m:
+                print("%s = %s %s" % (k, m[k][0], m[k][1]))
+        for h in hdr:
+            if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio"):
+                print("%s = %s %s" % (h, m[h][0], m[h][1]))
 
 
 if __name__ == "__main__":
