@@ -434,6 +434,64 @@ def events_leg(synth, rank):
     tb.close()
     eb.close()
     del d_out, d_frames, d_events
+    # (c) BASELINE config 2 itself, from event lists: 1,024 utterances of exactly 2,500 frames, so the synthesis is the
+    # headline's (one voice, one length).  End to end from HOST event lists to the HOST 16-bit payload, synchronous: pinned
+    # events -> device, drift + frame passes, synthesis, output stage, payload -> pinned host; against the same utterances
+    # entering as host FRAMES (gtts_batch_run_host_pcm16: the frames cross PCIe instead of the events).
+    base = [synthetic_events(SEED0 + 310000 + k, 74, duration_ms=10000) for k in range(96)]
+    lists = [base[u % 96] for u in range(N_UTT)]
+    events, eo = g.pack_events(lists)
+    eb = synth.prepare_events(np.array([event_config()] * N_UTT), events, eo)
+    assert eb.n_frames_total == N_UTT * N_FRAMES
+    tb = synth.prepare(default_voice("male"), eb.frame_offsets)
+    h_events = torch.from_numpy(events.view(np.uint8)).pin_memory()
+    d_events = torch.empty_like(h_events, device="cuda")
+    d_frames = torch.empty(eb.n_frames_total * 16, dtype=torch.float32, device="cuda")
+    d_audio = torch.empty(tb.n_out_total, dtype=torch.float32, device="cuda")
+    d_pcm = torch.empty(tb.n_out_total, dtype=torch.int16, device="cuda")
+    h_pcm = torch.empty(tb.n_out_total, dtype=torch.int16).pin_memory()
+    h_frames = torch.empty(eb.n_frames_total * 16, dtype=torch.float32).pin_memory()
+
+    def from_events():
+        d_events.copy_(h_events, non_blocking=True)
+        eb.run_device(d_events.data_ptr(), d_frames.data_ptr(), 0, s.cuda_stream)
+        tb.run_device_pcm16(d_frames.data_ptr(), d_audio.data_ptr(), d_pcm.data_ptr(), 0, s.cuda_stream)
+        h_pcm.copy_(d_pcm, non_blocking=True)
+        torch.cuda.synchronize()
+
+    def wall(fn, warm=2, reps=5):
+        for _ in range(warm):
+            fn()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        return (time.perf_counter() - t0) / reps * 1e3
+    def payload_sum():      # over the utterances' own samples (the up to 63 samples between two utterances are never written)
+        return sum(int(h_pcm[int(tb.out_offsets[u]):int(tb.out_offsets[u] + tb.n_out[u])].to(torch.int64).sum().item())
+                   for u in range(0, N_UTT, 37))
+    ms_events_e2e = wall(from_events)
+    sum_events = payload_sum()
+    h_frames.copy_(d_frames)
+    torch.cuda.synchronize()
+    ms_frames_e2e = wall(lambda: tb.run_host_pcm16_ptr(h_frames.data_ptr(), h_pcm.data_ptr(), 0))
+    sum_frames = payload_sum()
+    ms_dev = timed(lambda: (eb.run_device(d_events.data_ptr(), d_frames.data_ptr(), 0, s.cuda_stream),
+                            tb.run_device(d_frames.data_ptr(), d_audio.data_ptr(), s.cuda_stream)), warm=2, reps=5)
+    ms_synth = timed(lambda: tb.run_device(d_frames.data_ptr(), d_audio.data_ptr(), s.cuda_stream), warm=1, reps=5)
+    audio = tb.n_samples_total / 48000.0
+    out["config2_from_events"] = {
+        "workload": "BASELINE config 2 from event lists: %d utterances x %d frames (10 s), %d events, voice 0_male/male" % (
+            N_UTT, N_FRAMES, eb.n_events_total),
+        "kernel_used": tb.last_kernel(), "device_resident_ms": ms_dev, "synthesis_alone_ms": ms_synth,
+        "value": audio / (ms_dev * 1e-3), "unit": UNIT,
+        "e2e_from_host_events": {"ms": ms_events_e2e, "value": audio / (ms_events_e2e * 1e-3), "h2d_bytes": int(events.nbytes),
+                                 "d2h_bytes": int(tb.n_samples_total * 2)},
+        "e2e_from_host_frames": {"ms": ms_frames_e2e, "value": audio / (ms_frames_e2e * 1e-3), "h2d_bytes": int(eb.n_frames_total * 64),
+                                 "d2h_bytes": int(tb.n_samples_total * 2)},
+        "same_payload": sum_events == sum_frames}
+    tb.close()
+    eb.close()
+    del d_audio, d_pcm, d_frames, d_events, h_pcm, h_frames, h_events
     # (b) a batch that fills the GPU
     eb, events, cfgs, lists = batch(37888, 16, 128)
     d_events = torch.from_numpy(events.view(np.uint8)).cuda()

@@ -103,6 +103,10 @@ class Batch:
         check(self._lib.gtts_batch_run_device(self._h, C.c_void_p(d_frames_ptr), C.c_void_p(d_out_ptr),
                                               C.c_void_p(stream_ptr)))
 
+    def run_device_pcm16(self, d_frames_ptr, d_audio_ptr, d_pcm_ptr, d_scale_ptr=0, stream_ptr=0):
+        check(self._lib.gtts_batch_run_device_pcm16(self._h, C.c_void_p(d_frames_ptr), C.c_void_p(d_audio_ptr), C.c_void_p(d_pcm_ptr),
+                                                    C.c_void_p(d_scale_ptr), C.c_void_p(stream_ptr)))
+
     def run_host(self, frames, out=None):
         frames = np.ascontiguousarray(frames, np.float32)
         if out is None:

@@ -20,10 +20,12 @@ def event_config(control_period=4, macro=1, micro=1, drift=1, smooth=1, initial_
     return cfg[0]
 
 
-def synthetic_events(seed, n_postures, special_rate=0.02, tight=False, grid=4):
+def synthetic_events(seed, n_postures, special_rate=0.02, tight=False, grid=4, duration_ms=None):
     """An event list of about 4 events per posture: times ascending on a grid of `grid` ms, 2 to 15 grid steps apart, as the
     rule engine's are (with `tight`: any millisecond, some closer than a period or at equal times -- the reference then
-    divides by zero and so do we), the first event with every parameter set, later ones with about half of them, a few
+    divides by zero and so do we), with `duration_ms` (a multiple of `grid`) the list is cut so that its last event falls exactly
+    there (duration_ms / control period frames when the period is the grid: batches of one length), the first event with every
+    parameter set, later ones with about half of them, a few
     special parameters, a macro-intonation polynomial on about one event in ten, the last event with every parameter."""
     rng = np.random.Generator(np.random.PCG64(seed))
     n = max(2, 4 * n_postures)
@@ -34,7 +36,16 @@ def synthetic_events(seed, n_postures, special_rate=0.02, tight=False, grid=4):
     else:
         gaps = grid * rng.integers(2, 16, n)
     gaps[0] = 0
-    ev["time"] = np.cumsum(gaps)
+    times = np.cumsum(gaps)
+    if duration_ms is not None:
+        assert not tight and duration_ms % grid == 0
+        while times[-1] < duration_ms:                       # not enough postures for the duration: more events
+            more = grid * rng.integers(2, 16, n)
+            times = np.concatenate([times, times[-1] + np.cumsum(more)])
+        n = int(np.searchsorted(times, duration_ms - grid, side="right")) + 1      # events before the end, then the last one
+        times = np.concatenate([times[:n - 1], [duration_ms]])
+        ev = np.zeros(n, capi.EVENT_DTYPE)
+    ev["time"] = times
     targets = tracks.POSTURE_TARGETS[rng.integers(0, len(tracks.POSTURE_TARGETS), n)].astype(np.float64)
     targets += rng.normal(0.0, 0.01, targets.shape)
     span = tracks.PARAM_MAX - tracks.PARAM_MIN
