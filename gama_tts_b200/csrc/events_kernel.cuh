@@ -183,7 +183,7 @@ GTTS_DEV int scan_column(const Ring& R, int col, int from, double* value, int* t
 }
 
 // One chunk on one warp.  Returns the number of frames written.
-GTTS_DEV int chunk_frames(const gtts_event_config& c, const double* ev, int n, float* frames, const float* driftRow, double* ringRows, unsigned* maskWords, int lane)
+GTTS_DEV int chunk_frames(const gtts_event_config& c, const double* ev, int n, float* frames, const float* driftRow, double* ringRows, unsigned* maskWords, float* pitch, int lane)
 {
 	if (n < 2) return 0;                                    // :931-933
 	const int j = lane & 15, half = lane >> 4;
@@ -233,38 +233,71 @@ GTTS_DEV int chunk_frames(const gtts_event_config& c, const double* ev, int n, f
 	}
 	const bool micro = c.micro_intonation != 0, drift = c.intonation_drift != 0;
 	const float meanPitch = (float) c.mean_pitch;
+	const int periodShift = (period & (period - 1)) == 0 ? 31 - __clz(period) : -1;      // control periods of 1, 2, 4, 8 ms: a shift
 
 	int target = 1, now = 0, nFrames = 0;
 	double rowP = ring_row(R, 1)[colP], rowS = ring_row(R, 1)[colS];   // entries of row `target` (the "previous event" of the next boundary)
 	int targetTime = row_time(ring_row(R, 1));
 	for (;;) {
 		// ---- the frames of this segment: one while now < targetTime, at least one (:985-1024) ----
-		do {
-			const bool two = now + period < targetTime;         // a second frame belongs to this segment
-			const bool mine = !half || two;
-			float dval = 0.0f;
-			if (drift && j == 0 && mine) dval = driftRow[nFrames + half];
-			const double c1 = dlt != 0.0 ? __dadd_rn(cur, dlt) : cur;
-			const double s1 = sdlt != 0.0 ? __dadd_rn(scur, sdlt) : scur;
-			float p = (float) __dadd_rn(half ? c1 : cur, half ? s1 : scur);
-			if (j == 0) {
-				if (!micro) p = 0.0f;
-				if (drift) p = __fadd_rn(p, dval);
-				if (macro) {
-					const double x = (double) (now + half * period);
-					const double intonation = smooth
-						? __dadd_rn(__dmul_rn(x, __dadd_rn(__dmul_rn(x, __dadd_rn(__dmul_rn(x, pa), pb)), pc)), pd)
-						: __dadd_rn(__dmul_rn(x, pa), pb);
-					p = __fadd_rn(p, (float) intonation);
+		// In blocks of up to 32 frames: first the pitch terms of the block's frames, one frame per lane (the drift
+		// value of the scratch array, the polynomial at the frame's time: neither depends on the accumulated values),
+		// into the warp's 64 floats of shared memory; then the frames pair by pair.  `value += delta` is applied
+		// unconditionally: the reference skips a zero delta, which differs only in the sign of a zero value, and
+		// that sign never reaches a frame (the special value it is added to is never -0).
+		const int span = targetTime - now;
+		int k = span > 0 ? (periodShift >= 0 ? (span + period - 1) >> periodShift : (span + period - 1) / period) : 1;
+		while (k > 0) {
+			const int blk = k < 32 ? k : 32;
+			if (drift || macro) {
+				float addD = 0.0f, addI = 0.0f;
+				if (lane < blk) {
+					if (drift) addD = driftRow[nFrames + lane];
+					if (macro) {
+						const double x = (double) (now + lane * period);
+						addI = (float) (smooth
+							? __dadd_rn(__dmul_rn(x, __dadd_rn(__dmul_rn(x, __dadd_rn(__dmul_rn(x, pa), pb)), pc)), pd)
+							: __dadd_rn(__dmul_rn(x, pa), pb));
+					}
 				}
-				p = __fadd_rn(p, meanPitch);
+				__syncwarp();                               // the previous block's readers are done
+				pitch[lane] = addD;
+				pitch[32 + lane] = addI;
+				__syncwarp();
 			}
-			if (mine) frames[(int64_t) (nFrames + half) * 16 + j] = p;
-			cur = two && dlt != 0.0 ? __dadd_rn(c1, dlt) : c1;
-			scur = two && sdlt != 0.0 ? __dadd_rn(s1, sdlt) : s1;
-			now += two ? 2 * period : period;
-			nFrames += two ? 2 : 1;
-		} while (now < targetTime);
+			float* o = frames + (int64_t) (nFrames + half) * 16 + j;
+			const float* pt = pitch + half;
+			for (int i = blk >> 1; i > 0; --i) {
+				const double c1 = __dadd_rn(cur, dlt), s1 = __dadd_rn(scur, sdlt);
+				float p = (float) __dadd_rn(half ? c1 : cur, half ? s1 : scur);
+				if (j == 0) {
+					if (!micro) p = 0.0f;
+					if (drift) p = __fadd_rn(p, pt[0]);
+					if (macro) p = __fadd_rn(p, pt[32]);
+					p = __fadd_rn(p, meanPitch);
+				}
+				*o = p;
+				o += 32;
+				pt += 2;
+				cur = __dadd_rn(c1, dlt);
+				scur = __dadd_rn(s1, sdlt);
+			}
+			if (blk & 1) {                                   // the odd frame: lanes 0..15
+				float p = (float) __dadd_rn(cur, scur);
+				if (j == 0) {
+					if (!micro) p = 0.0f;
+					if (drift) p = __fadd_rn(p, pitch[blk - 1]);
+					if (macro) p = __fadd_rn(p, pitch[32 + blk - 1]);
+					p = __fadd_rn(p, meanPitch);
+				}
+				if (!half) *o = p;
+				cur = __dadd_rn(cur, dlt);
+				scur = __dadd_rn(scur, sdlt);
+			}
+			now += blk * period;
+			nFrames += blk;
+			k -= blk;
+		}
 		// ---- segment boundary (:1026-1087) ----
 		if (++target == n) break;
 		// row target - 2 is dead: its slot takes row target + 14; all but the newest copies have landed
@@ -329,11 +362,12 @@ GTTS_DEV void drift_body(const EventsParams& P, int t)
 }
 
 // Frame pass: the warps of a CTA take chunks from the queue until it is empty.
-GTTS_DEV void events_cta_body(const EventsParams& P, double* ringBase, unsigned* maskBase, int tid)
+GTTS_DEV void events_cta_body(const EventsParams& P, double* ringBase, unsigned* maskBase, float* pitchBase, int tid)
 {
 	const int lane = tid & 31;
 	double* ringRows = ringBase + (tid >> 5) * (kRingRows * kEventDoubles);
 	unsigned* maskWords = maskBase + (tid >> 5) * (kMaskWords * 32);
+	float* pitch = pitchBase + (tid >> 5) * 64;
 	for (;;) {
 		int slot = 0;
 		if (lane == 0) slot = atomicAdd(P.queue, 1);
@@ -343,21 +377,22 @@ GTTS_DEV void events_cta_body(const EventsParams& P, double* ringBase, unsigned*
 		const gtts_event_config c = P.cfgs[ci];
 		const ChunkDesc d = P.chunks[ci];
 		const int made = chunk_frames(c, P.events + d.event_offset * kEventDoubles, d.n_events, P.frames + d.frame_offset * 16,
-				P.drift + d.frame_offset, ringRows, maskWords, lane);
+				P.drift + d.frame_offset, ringRows, maskWords, pitch, lane);
 		if (lane == 0 && made != d.n_frames) P.queue[1] = 1;
 	}
 }
 
 #ifndef GTTS_EMU
 constexpr int kEventsWarps = 8;
-constexpr int kEventsSmem = kEventsWarps * (kRingRows * kEventDoubles * 8 + kMaskWords * 32 * 4);   // 54,272 bytes
+constexpr int kEventsSmem = kEventsWarps * (kRingRows * kEventDoubles * 8 + kMaskWords * 32 * 4 + 64 * 4);   // 56,320 bytes
 
 __global__ void __launch_bounds__(kEventsWarps * 32, 3) events_kernel(const EventsParams P)
 {
 	extern __shared__ double smem_events[];
 	double* ring = smem_events;
 	unsigned* masks = reinterpret_cast<unsigned*>(ring + kEventsWarps * kRingRows * kEventDoubles);
-	events_cta_body(P, ring, masks, (int) threadIdx.x);
+	float* pitch = reinterpret_cast<float*>(masks + kEventsWarps * kMaskWords * 32);
+	events_cta_body(P, ring, masks, pitch, (int) threadIdx.x);
 }
 
 constexpr int kDriftThreads = 32;

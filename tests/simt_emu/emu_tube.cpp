@@ -397,7 +397,8 @@ extern "C" int emu_events(const gtts_event_config* configs, const int* continues
 	for (int t = 0; t < P.n_chains; ++t) evt::drift_body(P, t);
 	std::vector<double> ring(static_cast<size_t>(warps_per_cta) * evt::kRingRows * evt::kEventDoubles);
 	std::vector<unsigned> masks(static_cast<size_t>(warps_per_cta) * evt::kMaskWords * 32);
-	simt::run_cta(warps_per_cta * 32, [&](int tid) { evt::events_cta_body(P, ring.data(), masks.data(), tid); });
+	std::vector<float> pitch(static_cast<size_t>(warps_per_cta) * 64);
+	simt::run_cta(warps_per_cta * 32, [&](int tid) { evt::events_cta_body(P, ring.data(), masks.data(), pitch.data(), tid); });
 	if (queue[1]) { g_err = "frame count mismatch"; return GTTS_ERR_CUDA; }
 	return 0;
 }

@@ -390,6 +390,20 @@ def test_emulated_events_kernel_synthetic_lists_vs_oracle(emu_events):
         cfgs.append(event_config(smooth=k))
         lists.append(synthetic_events(300 + k, n_post, special_rate=0.004, tight=k == 1))
         cont.append(0)
+    # signed zeros: the kernel adds a zero delta where the reference skips it; values and targets of -0.0 / +0.0 and
+    # ramps that land exactly on zero must still give the reference's bits (mean pitch 0 keeps a zero pitch a zero)
+    rng = np.random.Generator(np.random.PCG64(5))
+    for k in range(6):
+        ev = synthetic_events(400 + k, 6)
+        vals = np.array([-0.0, 0.0, 1.0, -1.0, 0.25, -0.25])
+        keep = ~np.isinf(ev["param"])
+        ev["param"] = np.where(keep, vals[rng.integers(0, 6, ev["param"].shape)], np.inf)
+        keep = rng.random(ev["special"].shape) < 0.2
+        ev["special"] = np.where(keep, vals[rng.integers(0, 6, ev["special"].shape)], np.inf)
+        ev["time"] = 8 * np.arange(len(ev))
+        cfgs.append(event_config(macro=0, micro=1, drift=0, mean_pitch=0.0 if k % 2 else -0.0))
+        lists.append(ev)
+        cont.append(0)
     frames, out = emu_events(np.array(cfgs), lists, cont)
     carried = None
     for i, (c, ev) in enumerate(zip(cfgs, lists)):
