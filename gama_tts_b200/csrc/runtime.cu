@@ -579,7 +579,9 @@ int createHandle(int32_t device, gtts_handle** handle_out)
 	    (ce = cudaFuncSetAttribute(v3::tube_kernel_v3, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	                               (int) v3::smem_bytes())) != cudaSuccess ||
 	    (ce = cudaFuncSetAttribute(m5::tube5_kernel<kWarps5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-	                               (int) m5::smem_bytes(kWarps5))) != cudaSuccess) {
+	                               (int) m5::smem_bytes(kWarps5))) != cudaSuccess ||
+	    (ce = cudaFuncSetAttribute(evt::events_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                               evt::kEventsSmem)) != cudaSuccess) {
 		if (h->d_src_tab) cudaFree(h->d_src_tab);
 		delete h;
 		return failCuda(ce, "gtts_create: device setup");
@@ -1752,6 +1754,8 @@ int gtts_events_run_device(gtts_events_batch* b, const gtts_event* d_events, flo
 	if (nChains == 0) return GTTS_OK;
 	if ((b->plan.n_events_total > 0 && !d_events) || (b->plan.frame_offsets.back() > 0 && !d_frames))
 		return fail(GTTS_ERR_INVALID, "null device buffer");
+	if (reinterpret_cast<uintptr_t>(d_events) % 8 != 0 || reinterpret_cast<uintptr_t>(d_frames) % 4 != 0)
+		return fail(GTTS_ERR_INVALID, "d_events must be 8-byte aligned and d_frames 4-byte aligned");
 	cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
 	GTTS_CUDA(cudaSetDevice(b->h->device));
 	GTTS_CUDA(cudaMemsetAsync(b->d_queue, 0, 2 * sizeof(int32_t), stream));
@@ -1774,11 +1778,6 @@ int gtts_events_run_device(gtts_events_batch* b, const gtts_event* d_events, flo
 	// frame pass: one warp per chunk from a queue; three CTAs of eight warps per SM are resident
 	const int ctasWanted = (P.n_chunks + evt::kEventsWarps - 1) / evt::kEventsWarps;
 	const int grid = std::min(ctasWanted, b->h->sms * 3);
-	static bool attributeSet[64] = {};
-	if (b->h->device < 64 && !attributeSet[b->h->device]) {
-		GTTS_CUDA(cudaFuncSetAttribute(evt::events_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, evt::kEventsSmem));
-		attributeSet[b->h->device] = true;
-	}
 	evt::events_kernel<<<grid, evt::kEventsWarps * 32, evt::kEventsSmem, stream>>>(P);
 	GTTS_CUDA(cudaGetLastError());
 	return GTTS_OK;

@@ -32,6 +32,21 @@ def shard_utterances(cost, world_size):
     return [np.nonzero(owner == r)[0] for r in range(world_size)]
 
 
+def shard_event_chunks(configs, event_lists, continues_previous, world_size):
+    """Control-frame generation over several GPUs: the chunks of an utterance share one drift generator and stay
+    together; utterances are dealt by their frame counts (host arithmetic on the event times, gtts_events_frame_count).
+    Returns a list of chunk-index arrays, one per rank, chunks in their original order."""
+    from . import events_frame_count
+    n = len(event_lists)
+    cont = np.zeros(n, np.int32) if continues_previous is None else np.asarray(continues_previous, np.int32)
+    first = np.nonzero((cont == 0) | (np.arange(n) == 0))[0]                 # first chunk of every utterance
+    chain_of = np.searchsorted(first, np.arange(n), side="right") - 1
+    frames = np.array([events_frame_count(configs[c], event_lists[c]) for c in range(n)], np.int64)
+    cost = np.bincount(chain_of, weights=frames, minlength=len(first)).astype(np.int64) + 1
+    owner = shard_plan(cost, world_size)
+    return [np.nonzero(owner[chain_of] == r)[0] for r in range(world_size)]
+
+
 def max_over_ranks(value, dist=None, device=None):
     """max of a python float over all ranks (identity without a process group)."""
     if dist is None or not dist.is_initialized():
