@@ -714,3 +714,29 @@ def test_events_to_audio_without_leaving_the_device(synth, oracle):
         assert len(ref) == len(audio[u]) and full_scale_error(audio[u], ref) <= TIGHT, u
     eb.close()
     tb.close()
+
+
+@pytest.mark.slow
+def test_events_full_gpu_batch_properties(synth):
+    # 37,888 chunks (8 warps x 3 CTAs x 148 SMs = 3,552 resident warps: every warp takes ten or more chunks from the queue),
+    # 128 distinct lists tiled: each distinct list is checked against the oracle bit for bit, and every copy of a list must
+    # give the bits of its first copy whatever its place in the batch and whichever warp took it (size-independent property)
+    from gama_tts_b200.events import event_config, synthetic_events
+    from oracle.pyoracle import OracleEvents
+    n, distinct = 37888, 128
+    base = [synthetic_events(8000 + k, 4 + k % 9, special_rate=0.03) for k in range(distinct)]
+    cfgs = [event_config(macro=k & 1, micro=(k >> 1) & 1, drift=(k >> 2) & 1, smooth=(k >> 3) & 1) for k in range(distinct)]
+    lists = [base[u % distinct] for u in range(n)]
+    events, eo = g.pack_events(lists)
+    b = synth.prepare_events(np.array([cfgs[u % distinct] for u in range(n)]), events, eo)
+    frames, out = b.run_host(events)
+    fo = b.frame_offsets
+    b.close()
+    o = OracleEvents()
+    for k in range(distinct):
+        want, state = o.generate(cfgs[k], base[k])
+        first = frames[fo[k]:fo[k + 1]]
+        assert first.shape == want.shape and np.array_equal(_bits(first), _bits(want)), k
+        assert out["drift_seed"][k] == state["drift_seed"] and out["drift_y1"][k] == state["drift_y1"], k
+        for u in range(k + distinct, n, distinct):
+            assert np.array_equal(frames[fo[u]:fo[u + 1]].view(np.uint32), first.view(np.uint32)), (k, u)
