@@ -26,6 +26,9 @@
 #include "tube_kernel.cuh"
 
 // Unrolling knobs: the kernel is sensitive to its instruction-cache footprint (tools/ab_build.sh NAME -D...)
+#ifndef GTTS_WALK_UNROLL
+#define GTTS_WALK_UNROLL 1
+#endif
 #ifndef GTTS_FIR_UNROLL
 #define GTTS_FIR_UNROLL 4
 #endif
@@ -42,7 +45,7 @@
 namespace gtts {
 namespace v1 {
 
-constexpr int kFirUnroll = GTTS_FIR_UNROLL, kCoefUnroll = GTTS_COEF_UNROLL;
+constexpr int kFirUnroll = GTTS_FIR_UNROLL, kCoefUnroll = GTTS_COEF_UNROLL, kWalkUnroll = GTTS_WALK_UNROLL;
 
 // keeps the first use of a register inside the branch it is written in (the compiler would otherwise hoist
 // cheap arithmetic on it above the branch)
@@ -207,7 +210,7 @@ GTTS_DEV void walk_block(const float* frames, long long nFrames, int steps, floa
 	const int mine = reaches ? first : 2 * kBlock;
 	const int ra = __shfl_sync(0xffffffffu, mine, 0), rb = __shfl_sync(0xffffffffu, mine, 1);
 	float4* o = reinterpret_cast<float4*>(out);
-#pragma unroll 1
+#pragma unroll kWalkUnroll
 	for (int j0 = 0; j0 < kBlock; j0 += 4) {
 		float v[4];
 		if ((unsigned) (ra - j0) >= 4u && (unsigned) (rb - j0) >= 4u) {
