@@ -10,7 +10,13 @@
 // as one binary file.  tools/make_golden_events.py turns it into tests/golden/events_v1.npz.  Needs /root/reference
 // (sources and voice data): container only.
 //
-// usage: [REF_EVENTS_FLAGS=macro,micro,drift,smooth] ref_events <voice dir> <out.bin> <text...>
+// With GTTS_LIB=<path to libgtts_b200.so> it is also the SEAM TEST of the control-frame path: the binding INTEGRATION.md
+// describes -- EventList::list_ copied into gtts_event records, gtts_events_prepare / gtts_events_run_host in place of
+// generateOutput -- runs inside the reference's own process on the chunks of the utterance (one batch, later chunks
+// chained to the first through continues_previous) and its frames are compared bit for bit with the reference's
+// (tests/test_plugin_seam.py, on a GPU box with the prebuilt binary and the voice directory copied next to it).
+//
+// usage: [REF_EVENTS_FLAGS=macro,micro,drift,smooth] [GTTS_LIB=...] ref_events <voice dir> <out.bin> <text...>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -33,6 +39,9 @@
 #include "Model.h"
 #include "TextParser.h"
 #include "PhoneticStringParser.h"
+
+#include <dlfcn.h>
+#include "../include/gtts_b200.h"
 
 namespace {
 
@@ -68,6 +77,11 @@ int main(int argc, char* argv[])
 		c.phoneticStringParser_ = std::make_unique<VTMControlModel::PhoneticStringParser>(c.index_, c.model_, el);
 		std::size_t pos = 0, size = 0;
 		int chunks = 0;
+		std::vector<gtts_event_config> gCfgs;
+		std::vector<int32_t> gCont;
+		std::vector<gtts_event> gEvents;
+		std::vector<int64_t> gOffsets{0};
+		std::vector<float> refFrames;
 		while (pos < phoneticString.size()) {
 			if (c.nextChunk(phoneticString, pos, size)) {
 				el.setUp();
@@ -94,19 +108,77 @@ int main(int argc, char* argv[])
 					put(f, e->interpData ? e->interpData->a : z); put(f, e->interpData ? e->interpData->b : z);
 					put(f, e->interpData ? e->interpData->c : z); put(f, e->interpData ? e->interpData->d : z);
 				}
+				// ---- the binding of INTEGRATION.md: the same inputs as C-ABI records ----
+				{
+					gtts_event_config g = {};
+					g.control_period = el.controlPeriod_;
+					g.macro_intonation = el.macroIntonation_; g.micro_intonation = el.microIntonation_;
+					g.intonation_drift = el.intonationDrift_; g.smooth_intonation = el.smoothIntonation_;
+					g.initial_pitch = el.initialPitch_; g.mean_pitch = el.meanPitch_;
+					g.drift_deviation2 = d.pitchDeviation_; g.drift_offset = d.pitchOffset_;
+					g.drift_b0 = d.filter_.b0_; g.drift_b1 = d.filter_.b1_; g.drift_a1 = d.filter_.a1_; g.drift_a2 = d.filter_.a2_;
+					if (gCfgs.empty()) {     // later chunks: the state is carried on the device (continues_previous)
+						g.drift_seed = d.seed_;
+						g.drift_x1 = d.filter_.x1_; g.drift_x2 = d.filter_.x2_; g.drift_y1 = d.filter_.y1_; g.drift_y2 = d.filter_.y2_;
+					}
+					gCont.push_back(gCfgs.empty() ? 0 : 1);
+					gCfgs.push_back(g);
+					for (const auto& e : el.list_) {
+						gtts_event ev = {};
+						ev.time = e->time;
+						ev.has_interp = e->interpData ? 1 : 0;
+						for (int j = 0; j < 16; ++j) { ev.param[j] = e->parameters[j]; ev.special[j] = e->specialParameters[j]; }
+						if (e->interpData) { ev.a = e->interpData->a; ev.b = e->interpData->b; ev.c = e->interpData->c; ev.d = e->interpData->d; }
+						gEvents.push_back(ev);
+					}
+					gOffsets.push_back(static_cast<int64_t>(gEvents.size()));
+				}
 				// ---- run it, dump the frames of this chunk ----
 				const std::size_t before = c.vtmParamList_.size();
 				el.generateOutput(c.vtmParamList_);
 				const int nFrames = static_cast<int>(c.vtmParamList_.size() - before);
 				put(f, nFrames);
 				for (std::size_t i = before; i < c.vtmParamList_.size(); ++i) {
-					for (int j = 0; j < 16; ++j) put(f, float(c.vtmParamList_[i][j]));
+					for (int j = 0; j < 16; ++j) { put(f, float(c.vtmParamList_[i][j])); refFrames.push_back(c.vtmParamList_[i][j]); }
 				}
 				++chunks;
 			}
 			pos += size;
 		}
 		std::cout << "chunks " << chunks << " frames " << c.vtmParamList_.size() << std::endl;
+		if (const char* libPath = std::getenv("GTTS_LIB")) {
+			void* lib = dlopen(libPath, RTLD_NOW);
+			if (!lib) { std::cerr << "dlopen: " << dlerror() << std::endl; return 3; }
+			auto sym = [&](const char* name) { void* p = dlsym(lib, name); if (!p) { std::cerr << "missing " << name << std::endl; std::exit(3); } return p; };
+			auto create = reinterpret_cast<decltype(&gtts_create)>(sym("gtts_create"));
+			auto lastError = reinterpret_cast<decltype(&gtts_last_error)>(sym("gtts_last_error"));
+			auto prepare = reinterpret_cast<decltype(&gtts_events_prepare)>(sym("gtts_events_prepare"));
+			auto layout = reinterpret_cast<decltype(&gtts_events_layout)>(sym("gtts_events_layout"));
+			auto runHost = reinterpret_cast<decltype(&gtts_events_run_host)>(sym("gtts_events_run_host"));
+			auto freeBatch = reinterpret_cast<decltype(&gtts_events_free)>(sym("gtts_events_free"));
+			auto destroy = reinterpret_cast<decltype(&gtts_destroy)>(sym("gtts_destroy"));
+			gtts_handle* h = nullptr;
+			if (create(0, &h) != GTTS_OK) { std::cerr << "gtts_create: " << lastError() << std::endl; return 4; }
+			gtts_events_batch* b = nullptr;
+			if (prepare(h, gCfgs.data(), gCont.data(), gEvents.data(), gOffsets.data(), static_cast<int64_t>(gCfgs.size()), &b) != GTTS_OK) {
+				std::cerr << "gtts_events_prepare: " << lastError() << std::endl; return 4;
+			}
+			std::vector<int64_t> fo(gCfgs.size() + 1);
+			layout(b, fo.data());
+			std::vector<float> got(static_cast<std::size_t>(fo.back()) * 16 + 1);
+			if (runHost(b, gEvents.data(), got.data(), nullptr) != GTTS_OK) { std::cerr << "gtts_events_run_host: " << lastError() << std::endl; return 4; }
+			long mismatches = fo.back() * 16 == static_cast<int64_t>(refFrames.size()) ? 0 : -1;
+			if (mismatches == 0) {
+				for (std::size_t i = 0; i < refFrames.size(); ++i) {
+					const bool bothNaN = refFrames[i] != refFrames[i] && got[i] != got[i];
+					if (!bothNaN && std::memcmp(&refFrames[i], &got[i], 4) != 0) ++mismatches;
+				}
+			}
+			std::cout << "gpu_check chunks " << gCfgs.size() << " frames " << fo.back() << " mismatches " << mismatches << std::endl;
+			freeBatch(b);
+			destroy(h);
+			if (mismatches != 0) return 5;
+		}
 	} catch (std::exception& e) {
 		std::cerr << "Exception: " << e.what() << std::endl;
 		return 1;

@@ -150,3 +150,51 @@ def test_stock_gama_tts_binary_reports_a_missing_gpu(tmp_path, real_tracks, prod
     np.savetxt(params, real_tracks[0][:20], fmt="%.9g")
     rc, err, data = _stock_run(tmp_path, "nogpu", params, 2000, "\ndll_path = %s\n" % PLUGIN)
     assert rc != 0 and "Could not construct" in err and len(data) == 0
+
+
+# ---- control-frame generation through the reference's own front end ----------------------
+
+REF_EVENTS = os.path.join(ROOT, "oracle", "_ref", "ref_events")
+VOICE_DIR = os.path.join(ROOT, "oracle", "_ref", "voice_0_male")
+PRODUCT = os.path.join(ROOT, "gama_tts_b200", "csrc", "libgtts_b200.so")
+
+
+def _run_ref_events(tmp_path, text, flags=None, lib=True):
+    import subprocess
+    if not (os.path.exists(REF_EVENTS) and os.path.isdir(VOICE_DIR)):
+        pytest.skip("oracle/_ref/ref_events not built (needs the reference sources at build time)")
+    env = dict(os.environ)
+    if lib:
+        env["GTTS_LIB"] = PRODUCT
+    if flags:
+        env["REF_EVENTS_FLAGS"] = flags
+    return subprocess.run([REF_EVENTS, VOICE_DIR, str(tmp_path / "events.bin"), text], env=env, capture_output=True, text=True,
+                          timeout=300)
+
+
+@pytest.mark.gpu
+def test_reference_front_end_drives_the_control_frame_kernel(tmp_path, product_lib):
+    # The unmodified reference front end (text parser, rule engine, generateEventList, applyIntonation) builds the event
+    # lists of a text; inside its process EventList::list_ is copied into gtts_event records and gtts_events_prepare /
+    # gtts_events_run_host take the place of generateOutput (the binding of INTEGRATION.md, compiled into
+    # oracle/ref_events.cpp); the frames must be the reference's own, bit for bit.  The chunks of the utterance are one
+    # batch, later chunks chained to the first (continues_previous), so the drift generator's state is carried on the device.
+    cases = [("Hello world.", None),
+             ("She sells sea shells by the sea shore. The shells she sells are surely sea shells. Are they?", None),
+             ("Why did the old clock stop? Nobody wound it.", "1,1,1,0"),
+             ("Monotone machines speak like this, all day long.", "0,0,1,1"),
+             ("In 1984, 3 of 12 ships sailed at 6:45.", "1,0,0,1")]
+    for text, flags in cases:
+        r = _run_ref_events(tmp_path, text, flags)
+        assert r.returncode == 0, (text, r.stdout[-300:], r.stderr[-300:])
+        line = [l for l in r.stdout.splitlines() if l.startswith("gpu_check")]
+        assert line and line[0].split()[-2:] == ["mismatches", "0"], (text, r.stdout[-300:])
+        assert int(line[0].split()[4]) > 100                         # frames
+
+
+def test_reference_front_end_reports_a_missing_gpu(tmp_path, product_lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = _run_ref_events(tmp_path, "Hello world.")
+    assert r.returncode == 4 and "gtts_create" in r.stderr               # no CPU path behind the binding
