@@ -416,3 +416,42 @@ def test_emulated_events_kernel_synthetic_lists_vs_oracle(emu_events):
         assert np.array_equal(_bits(frames[i]), _bits(want)), i
         for k in ("drift_seed", "drift_y1"):
             assert out[k][i] == carried[k], (i, k)
+
+
+def test_events_plan_refusals():
+    # the host planner behind gtts_events_prepare (events_host.cpp, here through the emulator's entry point, which needs
+    # no device): what it refuses and why
+    from gama_tts_b200 import capi, pack_events
+    from gama_tts_b200.events import event_config, synthetic_events
+    subprocess.run(["make", "-s", "-C", os.path.join(HERE, "simt_emu")], check=True)
+    L = C.CDLL(os.path.join(HERE, "simt_emu", "libemu_tube.so"))
+    L.emu_last_error.restype = C.c_char_p
+    L.emu_events.argtypes = [C.c_void_p] * 8 + [C.c_int]
+
+    def plan(cfgs, lists, offsets=None):
+        cfgs = np.ascontiguousarray(cfgs, capi.EVENT_CONFIG_DTYPE).reshape(-1)
+        ev, eo = pack_events(lists)
+        if offsets is not None:
+            eo = np.ascontiguousarray(offsets, np.int64)
+        fo = np.zeros(len(eo), np.int64)
+        rc = L.emu_events(cfgs.ctypes.data, None, ev.ctypes.data, eo.ctypes.data, len(eo) - 1, None, fo.ctypes.data, None, 1)
+        return rc, L.emu_last_error().decode(), fo
+
+    ev = synthetic_events(3, 4)
+    rc, _, fo = plan([event_config()], [ev])
+    assert rc == 0 and fo[1] > 0
+    bad = event_config()
+    bad["control_period"] = 0
+    rc, msg, _ = plan([bad], [ev])
+    assert rc == capi.GTTS_ERR_INVALID and "control_period" in msg
+    neg = ev.copy()
+    neg["time"][2] = -4
+    rc, msg, _ = plan([event_config()], [neg])
+    assert rc == capi.GTTS_ERR_INVALID and "time" in msg
+    rc, msg, _ = plan([event_config(), event_config()], [ev, ev], offsets=[0, len(ev), len(ev) - 1])
+    assert rc == capi.GTTS_ERR_INVALID and "decrease" in msg
+    rc, msg, _ = plan([event_config()], [ev], offsets=[1, len(ev)])
+    assert rc == capi.GTTS_ERR_INVALID and "event_offsets[0]" in msg
+    # an empty batch and a batch of empty lists are fine: no frames
+    rc, _, fo = plan([event_config(), event_config()], [ev[:0], ev[:1]])
+    assert rc == 0 and fo[-1] == 0
