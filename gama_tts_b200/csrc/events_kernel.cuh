@@ -101,11 +101,13 @@ struct Ring {
 // column" read row by row from global memory is a chain of round trips that dominated the first version (95 such scans
 // of about 50 rows per 10 s utterance: two thirds of its time).  One coalesced pass over the rows of a window of 512
 // leaves every column's occupancy as 16 words in shared memory; a scan is then a find-first-set over at most 16 words.
-GTTS_DEV_NOINLINE void build_masks(Ring& R, int base, int lane)
+GTTS_DEV_NOINLINE int build_masks(const double* ev, int n, unsigned* mask, int base, int lane)
 {
-	const int end = base + kMaskRows < R.n ? base + kMaskRows : R.n;
+	// (out of line, with scalar arguments: the caller's Ring stays in registers and the eight loads in flight here do not
+	// count against the frame loop's register budget.)  Returns the end of the window.
+	const int end = base + kMaskRows < n ? base + kMaskRows : n;
 	__syncwarp();                                           // the readers of the previous window are done
-	const double* col = R.ev + 1 + lane;
+	const double* col = ev + 1 + lane;
 	for (int w = 0; base + 32 * w < end; ++w) {
 		unsigned word = 0;
 		const int k0 = base + 32 * w;
@@ -115,11 +117,10 @@ GTTS_DEV_NOINLINE void build_masks(Ring& R, int base, int lane)
 			const double v = col[(int64_t) k * kEventDoubles];
 			if (k0 + r < end && !is_empty(v)) word |= 1u << r;
 		}
-		R.mask[w * 32 + lane] = word;
+		mask[w * 32 + lane] = word;
 	}
-	R.maskBase = base;
-	R.maskEnd = end;
 	__syncwarp();
+	return end;
 }
 
 GTTS_DEV void ring_issue(Ring& R, int lane)
@@ -195,7 +196,8 @@ GTTS_DEV int chunk_frames(const gtts_event_config& c, const double* ev, int n, f
 	Ring R = {ringRows, ev, n, 0, 0, maskWords, 0, 0};
 	__syncwarp();                                           // the previous chunk's readers are done with the ring
 	for (int r = 0; r < kRingRows; ++r) ring_issue(R, lane);
-	build_masks(R, 0, lane);
+	R.maskBase = 0;
+	R.maskEnd = build_masks(ev, n, maskWords, 0, lane);
 	ring_wait<0>();
 	__syncwarp();
 	R.safe = kRingRows;
@@ -306,7 +308,10 @@ GTTS_DEV int chunk_frames(const gtts_event_config& c, const double* ev, int n, f
 		ring_wait<kRingPending>();
 		__syncwarp();
 		R.safe = R.issued - kRingPending;
-		if (R.maskEnd < n && target + kMaskRows / 4 > R.maskEnd) build_masks(R, target, lane);
+		if (R.maskEnd < n && target + kMaskRows / 4 > R.maskEnd) {
+			R.maskBase = target;
+			R.maskEnd = build_masks(ev, n, maskWords, target, lane);
+		}
 		const double* rowT = ring_row(R, target);
 		targetTime = row_time(rowT);
 		const double prevP = rowP, prevS = rowS;
@@ -386,7 +391,11 @@ GTTS_DEV void events_cta_body(const EventsParams& P, double* ringBase, unsigned*
 constexpr int kEventsWarps = 8;
 constexpr int kEventsSmem = kEventsWarps * (kRingRows * kEventDoubles * 8 + kMaskWords * 32 * 4 + 64 * 4);   // 56,320 bytes
 
-__global__ void __launch_bounds__(kEventsWarps * 32, 3) events_kernel(const EventsParams P)
+// Two builds of the frame pass: 3 resident CTAs per SM at 80 registers -- the faster warp, for batches that do not fill
+// the GPU (1,024 chunks: 0.72 ms against 0.78) -- and 4 at 64 registers -- more warps to cover each other's waits, for
+// batches that do (37,888 chunks: 1.58 ms against 1.72; 2 CTAs per SM: 2.20 ms).
+template<int CTAS>
+__global__ void __launch_bounds__(kEventsWarps * 32, CTAS) events_kernel(const EventsParams P)
 {
 	extern __shared__ double smem_events[];
 	double* ring = smem_events;

@@ -580,7 +580,9 @@ int createHandle(int32_t device, gtts_handle** handle_out)
 	                               (int) v3::smem_bytes())) != cudaSuccess ||
 	    (ce = cudaFuncSetAttribute(m5::tube5_kernel<kWarps5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	                               (int) m5::smem_bytes(kWarps5))) != cudaSuccess ||
-	    (ce = cudaFuncSetAttribute(evt::events_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	    (ce = cudaFuncSetAttribute(evt::events_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                               evt::kEventsSmem)) != cudaSuccess ||
+	    (ce = cudaFuncSetAttribute(evt::events_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	                               evt::kEventsSmem)) != cudaSuccess) {
 		if (h->d_src_tab) cudaFree(h->d_src_tab);
 		delete h;
@@ -1775,10 +1777,14 @@ int gtts_events_run_device(gtts_events_batch* b, const gtts_event* d_events, flo
 	// drift pass: one thread per utterance
 	evt::events_drift_kernel<<<(nChains + evt::kDriftThreads - 1) / evt::kDriftThreads, evt::kDriftThreads, 0, stream>>>(P);
 	GTTS_CUDA(cudaGetLastError());
-	// frame pass: one warp per chunk from a queue; three CTAs of eight warps per SM are resident
+	// frame pass: one warp per chunk from a queue; CTAs of eight warps, three per SM resident, or four (64 registers) when
+	// the batch has more chunks than three per SM keep busy
 	const int ctasWanted = (P.n_chunks + evt::kEventsWarps - 1) / evt::kEventsWarps;
-	const int grid = std::min(ctasWanted, b->h->sms * 3);
-	evt::events_kernel<<<grid, evt::kEventsWarps * 32, evt::kEventsSmem, stream>>>(P);
+	if (ctasWanted > b->h->sms * 3) {
+		evt::events_kernel<4><<<std::min(ctasWanted, b->h->sms * 4), evt::kEventsWarps * 32, evt::kEventsSmem, stream>>>(P);
+	} else {
+		evt::events_kernel<3><<<ctasWanted, evt::kEventsWarps * 32, evt::kEventsSmem, stream>>>(P);
+	}
 	GTTS_CUDA(cudaGetLastError());
 	return GTTS_OK;
 }

@@ -18,7 +18,11 @@ if __name__ == "__main__":
     ap.add_argument("--chunks", type=int, default=37888)
     ap.add_argument("--postures", type=int, default=16)
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--lib", default=None, help="time another build of the library (tools/ab_build.sh)")
     a = ap.parse_args()
+    if a.lib:
+        from gama_tts_b200 import capi
+        capi.LIB_PATH = os.path.abspath(a.lib)
     synth = g.TubeSynthesizer(0)
     base = [synthetic_events(1000 + k, a.postures) for k in range(128)]
     events, eo = g.pack_events([base[u % 128] for u in range(a.chunks)])
