@@ -242,6 +242,37 @@ class MultiSynthesizer:
         finally:
             self._lib.gtts_multi_batch_free(b)
 
+    def synthesize5(self, voice_or_voices, tracks, voice_index=None, control_rate=voices.DEFAULT_CONTROL_RATE,
+                    steps_override=None, pcm16=False, return_shards=False):
+        """Model-5 voices over the GPUs (gtts5_multi_batch_*): same results as TubeSynthesizer.synthesize5, bit for bit."""
+        from .capi import voice5_array
+        vl = [voice_or_voices] if isinstance(voice_or_voices, dict) else list(voice_or_voices)
+        frames, fo = pack_tracks(tracks)
+        va = voice5_array(vl)
+        vi = None if voice_index is None else np.ascontiguousarray(voice_index, np.int32)
+        so = None if steps_override is None else np.ascontiguousarray(steps_override, np.int32)
+        b = C.c_void_p()
+        n = len(tracks)
+        check(self._lib.gtts5_multi_batch_prepare(self._h, va, len(vl), None if vi is None else vi.ctypes.data, float(control_rate),
+                                                  None if so is None else so.ctypes.data, fo.ctypes.data, n, C.byref(b)))
+        try:
+            oo = np.zeros(n + 1, np.int64)
+            no = np.zeros(max(n, 1), np.int64)
+            sh = np.zeros(max(n, 1), np.int32)
+            check(self._lib.gtts5_multi_batch_layout(b, oo.ctypes.data, no.ctypes.data, sh.ctypes.data))
+            if pcm16:
+                out = np.zeros(int(oo[-1]) + 1, np.int16)
+                scale = np.zeros(max(n, 1), np.float32)
+                check(self._lib.gtts5_multi_batch_run_host_pcm16(b, frames.ctypes.data, out.ctypes.data, scale.ctypes.data))
+                res = ([out[oo[u]:oo[u] + no[u]].copy() for u in range(n)], scale[:n])
+            else:
+                out = np.zeros(int(oo[-1]) + 1, np.float32)
+                check(self._lib.gtts5_multi_batch_run_host(b, frames.ctypes.data, out.ctypes.data))
+                res = [out[oo[u]:oo[u] + no[u]].copy() for u in range(n)]
+            return (res, sh[:n].copy()) if return_shards else res
+        finally:
+            self._lib.gtts5_multi_batch_free(b)
+
     def close(self):
         if self._h:
             self._lib.gtts_multi_destroy(self._h)

@@ -118,6 +118,8 @@ EXPORTS = [
     "gtts_stream_finish", "gtts_stream_reset", "gtts_stream_close",
     "gtts5_voice_internal_rate", "gtts5_output_length", "gtts5_batch_prepare", "gtts5_batch_layout", "gtts5_batch_run_device",
     "gtts5_batch_run_host", "gtts5_batch_run_device_pcm16", "gtts5_batch_run_host_pcm16", "gtts5_batch_free",
+    "gtts5_multi_batch_prepare", "gtts5_multi_batch_layout", "gtts5_multi_batch_run_host", "gtts5_multi_batch_run_host_pcm16",
+    "gtts5_multi_batch_free",
     "gtts_events_drift_setup", "gtts_events_frame_count", "gtts_events_prepare", "gtts_events_layout", "gtts_events_run_device", "gtts_events_run_host",
     "gtts_events_free",
 ]
@@ -194,6 +196,12 @@ def load():
     L.gtts5_batch_run_host_pcm16.argtypes = [vp, vp, vp, vp]
     L.gtts5_batch_free.argtypes = [vp]
     L.gtts5_batch_free.restype = None
+    L.gtts5_multi_batch_prepare.argtypes = [vp, PV5, i32, vp, dbl, vp, vp, i64, C.POINTER(vp)]
+    L.gtts5_multi_batch_layout.argtypes = [vp, vp, vp, vp]
+    L.gtts5_multi_batch_run_host.argtypes = [vp, vp, vp]
+    L.gtts5_multi_batch_run_host_pcm16.argtypes = [vp, vp, vp, vp]
+    L.gtts5_multi_batch_free.argtypes = [vp]
+    L.gtts5_multi_batch_free.restype = None
     L.gtts_events_drift_setup.argtypes = [dbl, dbl, dbl, vp]
     L.gtts_events_frame_count.argtypes = [vp, vp, i64, C.POINTER(i64)]
     L.gtts_events_prepare.argtypes = [vp, vp, vp, vp, vp, i64, C.POINTER(vp)]

@@ -1653,6 +1653,156 @@ int gtts5_batch_run_host_pcm16(gtts5_batch* b, const float* h_frames, int16_t* h
 	return GTTS_OK;
 }
 
+// ---- model 5 over the GPUs of a box -----------------------------------------------------------------------------------
+// Same partition as gtts_multi_batch (by utterance, no inter-GPU traffic).  The model-5 kernel takes device buffers, so
+// every GPU's host thread packs its utterances' frames, runs its own gtts5_batch and puts the audio (or the 16-bit
+// payload) at the utterances' offsets of the caller's buffer.  One warp synthesises one utterance whatever else is in
+// the batch: the result is bit for bit that of one GPU.
+
+struct gtts5_multi_batch {
+	gtts_multi* m = nullptr;
+	m5::BatchPlan5 plan;                         // the whole batch: layout, lengths
+	std::vector<int32_t> shard_of;
+	std::vector<gtts5_batch*> shards;            // one per GPU (nullptr: no utterance)
+	std::vector<std::vector<int64_t>> members;   // utterances of each shard, ascending
+	std::vector<int64_t> frame_offsets;          // the caller's
+};
+
+void gtts5_multi_batch_free(gtts5_multi_batch* b)
+{
+	if (!b) return;
+	for (gtts5_batch* sb : b->shards) gtts5_batch_free(sb);
+	delete b;
+}
+
+int gtts5_multi_batch_prepare(gtts_multi* m, const gtts_voice5_config* voices, int32_t n_voices, const int32_t* voice_index,
+			double control_rate, const int32_t* steps_override, const int64_t* frame_offsets, int64_t n_utt,
+			gtts5_multi_batch** batch_out)
+{
+	if (!m || !batch_out) return fail(GTTS_ERR_INVALID, "null multi handle / output pointer");
+	*batch_out = nullptr;
+	gtts5_multi_batch* b = nullptr;
+	try {
+		if (n_utt > std::numeric_limits<int32_t>::max()) return fail(GTTS_ERR_INVALID, "too many utterances");
+		b = new gtts5_multi_batch;
+		b->m = m;
+		int err = GTTS_OK;
+		const std::string msg = m5::planBatch5(voices, n_voices, voice_index, control_rate, steps_override, frame_offsets, n_utt, b->plan, &err);
+		if (err != GTTS_OK) { delete b; return fail(err, msg); }
+		b->frame_offsets.assign(frame_offsets, frame_offsets + n_utt + 1);
+		const int nDev = static_cast<int>(m->handles.size());
+		std::vector<int64_t> cost(static_cast<size_t>(n_utt));
+		for (int64_t u = 0; u < n_utt; ++u) cost[u] = b->plan.utts[u].n_internal + b->plan.utts[u].n_out + 1;
+		b->shard_of.assign(static_cast<size_t>(n_utt), 0);
+		if (n_utt > 0) shardPlan(cost.data(), n_utt, nDev, b->shard_of.data());
+		b->shards.assign(nDev, nullptr);
+		b->members.assign(nDev, {});
+		for (int64_t u = 0; u < n_utt; ++u) b->members[b->shard_of[u]].push_back(u);
+		for (int g = 0; g < nDev; ++g) {
+			const std::vector<int64_t>& mem = b->members[g];
+			if (mem.empty()) continue;
+			std::vector<int64_t> fo(mem.size() + 1, 0);
+			std::vector<int32_t> vi(mem.size(), 0), so(mem.size(), 0);
+			for (size_t i = 0; i < mem.size(); ++i) {
+				const int64_t u = mem[i];
+				fo[i + 1] = fo[i] + (frame_offsets[u + 1] - frame_offsets[u]);
+				vi[i] = voice_index ? voice_index[u] : 0;
+				so[i] = steps_override ? steps_override[u] : 0;
+			}
+			const int rc = gtts5_batch_prepare(m->handles[g], voices, n_voices, vi.data(), control_rate, steps_override ? so.data() : nullptr,
+					fo.data(), static_cast<int64_t>(mem.size()), &b->shards[g]);
+			if (rc != GTTS_OK) { gtts5_multi_batch_free(b); return rc; }
+		}
+	} catch (const std::exception& e) {
+		gtts5_multi_batch_free(b);
+		return fail(GTTS_ERR_NOMEM, e.what());
+	}
+	*batch_out = b;
+	return GTTS_OK;
+}
+
+int gtts5_multi_batch_layout(const gtts5_multi_batch* b, int64_t* out_offsets, int64_t* n_out, int32_t* shard_of)
+{
+	if (!b) return fail(GTTS_ERR_INVALID, "null batch");
+	if (out_offsets) std::copy(b->plan.out_offsets.begin(), b->plan.out_offsets.end(), out_offsets);
+	if (n_out) for (size_t u = 0; u < b->plan.utts.size(); ++u) n_out[u] = b->plan.utts[u].n_out;
+	if (shard_of) std::copy(b->shard_of.begin(), b->shard_of.end(), shard_of);
+	return GTTS_OK;
+}
+
+static int multiRun5(gtts5_multi_batch* b, const float* h_frames, float* h_out, int16_t* h_pcm, float* h_scale)
+{
+	if (!b) return fail(GTTS_ERR_INVALID, "null batch");
+	const int64_t nOut = b->plan.out_offsets.empty() ? 0 : b->plan.out_offsets.back();
+	if ((b->plan.n_frames_total > 0 && !h_frames) || (nOut > 0 && !h_out && !h_pcm)) return fail(GTTS_ERR_INVALID, "null host buffer");
+	const size_t nDev = b->shards.size();
+	std::vector<int> codes(nDev, GTTS_OK);
+	std::vector<std::string> texts(nDev);
+	std::vector<std::thread> pool;
+	for (size_t g = 0; g < nDev; ++g) {
+		gtts5_batch* sb = b->shards[g];
+		if (!sb) continue;
+		pool.emplace_back([=, &codes, &texts]() {
+			try {
+				const std::vector<int64_t>& mem = b->members[g];
+				std::vector<float> frames(static_cast<size_t>(sb->plan.n_frames_total) * kNumParams + 1);
+				size_t at = 0;
+				for (int64_t u : mem) {
+					const size_t n = static_cast<size_t>(b->frame_offsets[u + 1] - b->frame_offsets[u]) * kNumParams;
+					std::memcpy(frames.data() + at, h_frames + b->frame_offsets[u] * kNumParams, n * sizeof(float));
+					at += n;
+				}
+				const size_t subOut = static_cast<size_t>(sb->plan.out_offsets.back());
+				int r;
+				if (h_pcm) {
+					std::vector<int16_t> pcm(subOut + 1);
+					std::vector<float> scale(mem.size());
+					r = gtts5_batch_run_host_pcm16(sb, frames.data(), pcm.data(), scale.data());
+					for (size_t i = 0; r == GTTS_OK && i < mem.size(); ++i) {
+						const UttDesc& d = b->plan.utts[mem[i]];
+						std::memcpy(h_pcm + d.out_begin, pcm.data() + sb->plan.utts[i].out_begin, sizeof(int16_t) * static_cast<size_t>(d.n_out));
+						if (h_scale) h_scale[mem[i]] = scale[i];
+					}
+				} else {
+					std::vector<float> out(subOut + 1);
+					r = gtts5_batch_run_host(sb, frames.data(), out.data());
+					for (size_t i = 0; r == GTTS_OK && i < mem.size(); ++i) {
+						const UttDesc& d = b->plan.utts[mem[i]];
+						std::memcpy(h_out + d.out_begin, out.data() + sb->plan.utts[i].out_begin, sizeof(float) * static_cast<size_t>(d.n_out));
+					}
+				}
+				codes[g] = r;
+				if (r != GTTS_OK) texts[g] = gtts_last_error();
+			} catch (const std::exception& e) {
+				codes[g] = GTTS_ERR_NOMEM;
+				texts[g] = e.what();
+			}
+		});
+	}
+	for (std::thread& t : pool) t.join();
+	for (size_t g = 0; g < nDev; ++g) if (codes[g] != GTTS_OK) return fail(codes[g], "GPU " + std::to_string(g) + ": " + texts[g]);
+	return GTTS_OK;
+}
+
+int gtts5_multi_batch_run_host(gtts5_multi_batch* b, const float* h_frames, float* h_out)
+{
+	try {
+		return multiRun5(b, h_frames, h_out, nullptr, nullptr);
+	} catch (const std::exception& e) {
+		return fail(GTTS_ERR_NOMEM, e.what());
+	}
+}
+
+int gtts5_multi_batch_run_host_pcm16(gtts5_multi_batch* b, const float* h_frames, int16_t* h_pcm, float* h_scale)
+{
+	if (!h_pcm) return fail(GTTS_ERR_INVALID, "null host buffer");
+	try {
+		return multiRun5(b, h_frames, nullptr, h_pcm, h_scale);
+	} catch (const std::exception& e) {
+		return fail(GTTS_ERR_NOMEM, e.what());
+	}
+}
+
 // ---- control-frame generation on the device (events_kernel.cuh) ---------------------------------------------------
 
 struct gtts_events_batch {

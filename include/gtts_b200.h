@@ -290,6 +290,18 @@ int gtts5_batch_run_device_pcm16(gtts5_batch* batch, const float* d_frames, floa
 int gtts5_batch_run_host_pcm16(gtts5_batch* batch, const float* h_frames, int16_t* h_pcm, float* h_scale);
 void gtts5_batch_free(gtts5_batch* batch);
 
+/* Model 5 over the GPUs of a box (gtts_multi_create above): the batch partitioned by utterance as in gtts_multi_batch_*, one
+ * host thread per GPU, every utterance's audio (or 16-bit payload, with its scale) at its offset of the caller's ONE buffer
+ * (layout as gtts5_batch_layout of the whole batch).  Bit for bit the result of one GPU. */
+typedef struct gtts5_multi_batch gtts5_multi_batch;
+int gtts5_multi_batch_prepare(gtts_multi* multi, const gtts_voice5_config* voices, int32_t n_voices,
+			const int32_t* voice_index, double control_rate, const int32_t* steps_override,
+			const int64_t* frame_offsets, int64_t n_utt, gtts5_multi_batch** batch_out);
+int gtts5_multi_batch_layout(const gtts5_multi_batch* batch, int64_t* out_offsets, int64_t* n_out, int32_t* shard_of);
+int gtts5_multi_batch_run_host(gtts5_multi_batch* batch, const float* h_frames, float* h_out);
+int gtts5_multi_batch_run_host_pcm16(gtts5_multi_batch* batch, const float* h_frames, int16_t* h_pcm, float* h_scale);
+void gtts5_multi_batch_free(gtts5_multi_batch* batch);
+
 /* ---- control-frame generation on the device (BASELINE next row 3) -------------------------------------------------
  * From the event list of a chunk of an utterance to its control frames -- the float32 [frame][16] array every batch
  * call above takes -- in device memory, so that the frames never cross PCIe:

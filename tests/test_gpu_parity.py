@@ -513,6 +513,38 @@ def test_model5_ragged_batch_vs_oracle(synth, oracle5):
             assert full_scale_error(out, ref) <= TIGHT
 
 
+def test_model5_multi_gpu_dispatch_through_the_c_abi(synth, oracle5):
+    # gtts5_multi_*: a ragged model-5 batch of several voices over every GPU of the box (one on the driver's test box: the
+    # packing / scattering path is the same), float32 and 16-bit payload, bit for bit the one-GPU result
+    import torch
+    from gama_tts_b200.voices import default_voice5, random_voice5
+    rng = np.random.Generator(np.random.PCG64(17))
+    voices = [default_voice5("male"), default_voice5("female"), random_voice5(rng, base="baby")]
+    n = 40
+    vidx = rng.integers(0, 3, n)
+    tracks = [T.synthetic_track(5200 + i, int(rng.integers(0, 90))) for i in range(n)]
+    whole = synth.synthesize5(voices, tracks, voice_index=vidx)
+    multi = g.MultiSynthesizer(list(range(torch.cuda.device_count())))
+    outs, shard_of = multi.synthesize5(voices, tracks, voice_index=vidx, return_shards=True)
+    assert set(shard_of.tolist()) == set(range(min(torch.cuda.device_count(), n)))
+    for u in range(n):
+        assert np.array_equal(outs[u], whole[u]), u
+    fo = np.zeros(n + 1, np.int64)
+    fo[1:] = np.cumsum([len(t) for t in tracks])
+    b = synth.prepare5(voices, fo, vidx)
+    want_pcm, want_scale = b.run_host_pcm16(np.concatenate(tracks))
+    want_pcm = b.split(want_pcm)
+    b.close()
+    (pcm, scale) = multi.synthesize5(voices, tracks, voice_index=vidx, pcm16=True)
+    assert np.array_equal(scale, want_scale)
+    for u in range(n):
+        assert np.array_equal(pcm[u], want_pcm[u]), u
+    multi.close()
+    for u in (0, 13, 39):
+        ref = oracle5.synthesize(voices[vidx[u]], tracks[u])
+        assert len(ref) == len(whole[u]) and full_scale_error(whole[u], ref) <= TIGHT
+
+
 def test_model5_rejects_what_the_reference_rejects(synth):
     from gama_tts_b200.voices import default_voice5
     tr = [T.synthetic_track(1, 5)]
