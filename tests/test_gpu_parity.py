@@ -513,6 +513,22 @@ def test_model5_ragged_batch_vs_oracle(synth, oracle5):
             assert full_scale_error(out, ref) <= TIGHT
 
 
+def test_models_3_and_4_multi_gpu_dispatch(synth):
+    # models 3 / 4 are voices of the model-0 ABI (tube_model), so gtts_multi_* takes them as they are: bitwise equal to one GPU
+    import torch
+    rng = np.random.Generator(np.random.PCG64(23))
+    voices = [dict(default_voice("male"), tube_model=3), dict(default_voice("female"), tube_model=4), default_voice("male")]
+    n = 18
+    vidx = np.arange(n) % 3
+    tracks = [T.synthetic_track(5300 + i, int(rng.integers(1, 50))) for i in range(n)]
+    whole = synth.synthesize(voices, tracks, voice_index=vidx)
+    multi = g.MultiSynthesizer(list(range(torch.cuda.device_count())))
+    outs = multi.synthesize(voices, tracks, voice_index=vidx)
+    multi.close()
+    for u in range(n):
+        assert np.array_equal(outs[u], whole[u]), u
+
+
 def test_model5_multi_gpu_dispatch_through_the_c_abi(synth, oracle5):
     # gtts5_multi_*: a ragged model-5 batch of several voices over every GPU of the box (one on the driver's test box: the
     # packing / scattering path is the same), float32 and 16-bit payload, bit for bit the one-GPU result
