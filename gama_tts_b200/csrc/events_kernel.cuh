@@ -269,20 +269,23 @@ GTTS_DEV int chunk_frames(const gtts_event_config& c, const double* ev, int n, f
 			}
 			float* o = frames + (int64_t) (nFrames + half) * 16 + j;
 			const float* pt = pitch + half;
+			// lanes 16..31 emit the value one delta on: cur + (half ? dlt : 0) is the same addition as the c1 of the next
+			// line for them and leaves the value as it is for lanes 0..15 (a -0 becomes +0: see above), without selects.
+			// The pitch terms are evaluated by every lane (uniform conditions, broadcast reads) and kept by parameter 0: no
+			// divergent branch in the loop.
+			const double stepP = half ? dlt : 0.0, stepS = half ? sdlt : 0.0;
+#pragma unroll 2
 			for (int i = blk >> 1; i > 0; --i) {
-				const double c1 = __dadd_rn(cur, dlt), s1 = __dadd_rn(scur, sdlt);
-				float p = (float) __dadd_rn(half ? c1 : cur, half ? s1 : scur);
-				if (j == 0) {
-					if (!micro) p = 0.0f;
-					if (drift) p = __fadd_rn(p, pt[0]);
-					if (macro) p = __fadd_rn(p, pt[32]);
-					p = __fadd_rn(p, meanPitch);
-				}
-				*o = p;
+				float p = (float) __dadd_rn(__dadd_rn(cur, stepP), __dadd_rn(scur, stepS));
+				float q = micro ? p : 0.0f;
+				if (drift) q = __fadd_rn(q, pt[0]);
+				if (macro) q = __fadd_rn(q, pt[32]);
+				q = __fadd_rn(q, meanPitch);
+				*o = j == 0 ? q : p;
 				o += 32;
 				pt += 2;
-				cur = __dadd_rn(c1, dlt);
-				scur = __dadd_rn(s1, sdlt);
+				cur = __dadd_rn(__dadd_rn(cur, dlt), dlt);
+				scur = __dadd_rn(__dadd_rn(scur, sdlt), sdlt);
 			}
 			if (blk & 1) {                                   // the odd frame: lanes 0..15
 				float p = (float) __dadd_rn(cur, scur);
