@@ -10,7 +10,10 @@
  *     VocalTractModel::finishSynthesis()       gama_tts/src/vtm/VocalTractModel.h:57, VocalTractModel0.h:720-723
  *     VocalTractModel::outputBuffer()          gama_tts/src/vtm/VocalTractModel.h:59
  *
- * for U independent utterances at once on one GPU.  Plain pointers and sizes only; no C++ or torch
+ * for U independent utterances at once on one GPU -- and, either side of it: the same for models 3 / 4 / 5 (tube_model,
+ * gtts5_*), the output stage (peak normalisation + 16-bit PCM, *_pcm16), one batch over the GPUs of a box (gtts_multi_*,
+ * gtts5_multi_*), frame-by-frame streaming (gtts_stream_*), and the control frames themselves from the rule engine's event
+ * lists (EventList::generateOutput, gtts_events_*).  Plain pointers and sizes only; no C++ or torch
  * types cross this boundary.  The C++ plugin shim that the unmodified reference loads through
  * VocalTractModelPlugin (gama_tts/src/vtm/VocalTractModelPlugin.cpp:40-48, model = 2000) is built on
  * top of these entry points (gama_tts_b200/csrc/plugin_shim.cpp); INTEGRATION.md shows the bindings.
