@@ -62,7 +62,8 @@ std::string planEvents(const gtts_event_config* configs, const int32_t* continue
 			if (t < 0 || t > (int64_t(1) << 30)) return "event time out of range";
 		}
 		const int64_t frames = countFrames(configs[c].control_period, events + event_offsets[c], n);
-		if (frames > std::numeric_limits<int32_t>::max()) return "chunk too long";
+		// the kernel keeps the chunk's time in milliseconds and its frame count in 32-bit integers
+		if (frames > (int64_t(1) << 30) || frames * configs[c].control_period > (int64_t(1) << 30)) return "chunk too long";
 		plan.chunks[c].event_offset = event_offsets[c];
 		plan.chunks[c].frame_offset = plan.frame_offsets[c];
 		plan.chunks[c].n_events = static_cast<int32_t>(n);

@@ -452,6 +452,18 @@ def test_events_plan_refusals():
     assert rc == capi.GTTS_ERR_INVALID and "decrease" in msg
     rc, msg, _ = plan([event_config()], [ev], offsets=[1, len(ev)])
     assert rc == capi.GTTS_ERR_INVALID and "event_offsets[0]" in msg
+    far = ev.copy()
+    far["time"][-1] = 1 << 30
+    huge = event_config()
+    huge["control_period"] = 1
+    rc, msg, _ = plan([huge], [far])
+    assert rc == 0                                              # 2^30 ms at a period of 1 ms: the largest chunk accepted
+    many = np.repeat(ev[:2], 600000)                            # 1.2 M events at the same two times: a frame each, period 1000 ms
+    many["time"] = 0
+    slow = event_config()
+    slow["control_period"] = 1000
+    rc, msg, _ = plan([slow], [many])
+    assert rc == capi.GTTS_ERR_INVALID and "too long" in msg    # its clock would pass 2^30 ms
     # an empty batch and a batch of empty lists are fine: no frames
     rc, _, fo = plan([event_config(), event_config()], [ev[:0], ev[:1]])
     assert rc == 0 and fo[-1] == 0
