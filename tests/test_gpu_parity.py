@@ -641,6 +641,27 @@ def test_pipelined_kernel_choice(synth, oracle, monkeypatch):
         assert full_scale_error(a1[u], oracle.synthesize(v, uniform[u])) <= TIGHT
 
 
+def test_uniform_batches_on_v1_every_variant(synth, oracle, real_tracks, monkeypatch):
+    # the kernel BASELINE config 2 runs on (tube_kernel_v1: batches of one voice and one length), on every shipped variant,
+    # randomised voices (incl. tn_min != tn_max: the analytic fall segment) and control rates, every utterance against the oracle
+    monkeypatch.delenv("GTTS_KERNEL", raising=False)
+    rng = np.random.Generator(np.random.PCG64(77))
+    voices = [default_voice(v) for v in ("male", "female", "large_child", "small_child", "baby")] + [random_voice(rng) for _ in range(3)]
+    for k, v in enumerate(voices):
+        rate = (250.0, 250.0, 500.0, 200.0)[k % 4]
+        n_frames = 40 + 7 * k
+        tracks = [T.synthetic_track(6000 + 16 * k + i, n_frames) for i in range(9)] + [real_tracks[k % len(real_tracks)][:n_frames]]
+        frames, fo = g.pack_tracks(tracks)
+        b = synth.prepare(v, fo, control_rate=rate)
+        outs = [x.copy() for x in b.split(b.run_host(frames))]
+        assert b.last_kernel() == "tube_kernel_v1", k
+        b.close()
+        for tr, out in zip(tracks, outs):
+            ref = oracle.synthesize(v, tr, control_rate=rate)
+            assert len(out) == len(ref), k
+            assert full_scale_error(out, ref) <= TIGHT, k
+
+
 # ---- control-frame generation on the device (gtts_events_*, events_kernel.cuh) -----------------------------------------
 
 def _bits(a):
